@@ -1,0 +1,297 @@
+/*
+ * swgn.h -- C ABI of the Blackwell-native sliding-window Gauss-Newton solver.
+ *
+ * This is the drop-in boundary for the reference's hot path:
+ * everything the reference does between `ceres::Solve(options, &my_problem, &summary)`
+ * (RVI/swf/swf_image.cpp:219) and the read-backs `UpdateSchur` / `UpdateSchurHessianOnly`
+ * (RVI/swf/swf_gnss.cpp:25-94) and `LambdaSearch` (RVI/swf/swf_lambda.cpp:82-245) is reachable
+ * through the entry points below.  The header-compatible C++ shim in include/ceres/ sits on top
+ * of this ABI; the CUDA implementation (libswgn.so) sits underneath.
+ *
+ * Conventions: plain C structs, pointers and sizes; the caller owns every host buffer it passes
+ * in or receives results in; the library owns device memory behind the opaque handle; every
+ * entry point returns a swgn_status (0 = ok) and never throws or aborts across the boundary.
+ * There is no CPU implementation behind this ABI: if no CUDA device is usable the create call
+ * fails with SWGN_ERR_NO_DEVICE.
+ *
+ * RVI/   = /root/reference/rtk_visual_inertial_src/rtk_visual_inertial/src/
+ * CERES/ = ceres-solver-modified/ inside /root/reference/ceres-solver-modified.tar
+ */
+#ifndef SWGN_H_
+#define SWGN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t swgn_status;
+enum {
+  SWGN_OK = 0,
+  SWGN_ERR_INVALID = 1,      /* malformed graph / argument (Ceres would CHECK-fail) */
+  SWGN_ERR_NO_DEVICE = 2,    /* no usable CUDA device: there is no CPU fallback */
+  SWGN_ERR_CUDA = 3,         /* a CUDA runtime call failed; see swgn_last_error() */
+  SWGN_ERR_ORDERING = 4,     /* group 0 of the ordering is not an independent set
+                                (CERES/internal/ceres/program.cc:413-434) */
+  SWGN_ERR_TOO_LARGE = 5,    /* reduced system >= 1024 rows with exports requested
+                                (CERES/internal/ceres/schur_complement_solver.cc:178,256) */
+  SWGN_ERR_UNSUPPORTED = 6
+};
+
+/* ---- parameter blocks ------------------------------------------------------------------ */
+enum { SWGN_MANIFOLD_EUCLIDEAN = 0,
+       /* 7 -> 6: p += dp ; q <- normalize(q * [1, dtheta/2]); layout (px,py,pz,qx,qy,qz,qw)
+          RVI/factor/pose_local_parameterization.cpp:5-27 */
+       SWGN_MANIFOLD_POSE = 1 };
+
+/* ---- GNSS factor kinds (RVI/factor/gnss_factor.h) ---------------------------------------- */
+enum {
+  SWGN_GNSS_SPP_PSEUDORANGE = 0, /* <1;7,1>   (pose, clk)        gnss_factor.cpp:9-39    */
+  SWGN_GNSS_SPP_CARRIER     = 1, /* <1;7,1,1> (pose, clk, N)     gnss_factor.cpp:45-80   */
+  SWGN_GNSS_RTK_CARRIER     = 2, /* <1;7,1,1> (pose, N, clk)     gnss_factor.cpp:105-138 */
+  SWGN_GNSS_RTK_PSEUDORANGE = 3, /* <1;7,1>   (pose, clk)        gnss_factor.cpp:140-168 */
+  SWGN_GNSS_DOPPLER         = 4, /* <1;9,1,7> (sb, drift, pose)  gnss_factor.cpp:174-212 */
+  SWGN_GNSS_FIXED_INTEGER   = 5  /* <1;1,1>   (N_ref, N_a)       gnss_factor.cpp:85-96   */
+};
+/* per-factor constant record, SWGN_GNSS_STRIDE doubles */
+enum {
+  SWGN_GNSS_SAT_POS = 0,   /* [3] satellite ECEF position                                   */
+  SWGN_GNSS_SAT_VEL = 3,   /* [3] satellite ECEF velocity (Doppler only)                    */
+  SWGN_GNSS_BASE_POS = 6,  /* [3] base_pos added to the pose translation                    */
+  SWGN_GNSS_MEAS = 9,      /* P1 | L1_lam | D1_lam | N21                                     */
+  SWGN_GNSS_LAM = 10,      /* wavelength (carrier types)                                     */
+  SWGN_GNSS_WEIGHT = 11,   /* sqrt-information actually multiplied in: istd, or
+                              1/sqrt(varerr2(el,dt,var)) evaluated on the host with the
+                              reference's single-precision sinf (gnss_factor.cpp:98-103)    */
+  SWGN_GNSS_EL = 12, SWGN_GNSS_DT = 13, SWGN_GNSS_VAR = 14, /* provenance of WEIGHT          */
+  SWGN_GNSS_STRIDE = 16
+};
+
+/* per-IMU-factor constant record (fields of IntegrationBase, RVI/factor/integration_base.h) */
+enum {
+  SWGN_IMU_DELTA_P = 0,    /* [3]                                                            */
+  SWGN_IMU_DELTA_Q = 3,    /* [4] x,y,z,w                                                    */
+  SWGN_IMU_DELTA_V = 7,    /* [3]                                                            */
+  SWGN_IMU_LIN_BA = 10,    /* [3] linearized_ba                                              */
+  SWGN_IMU_LIN_BG = 13,    /* [3] linearized_bg                                              */
+  SWGN_IMU_GYRI = 16,      /* [3]                                                            */
+  SWGN_IMU_GYRJ = 19,      /* [3]                                                            */
+  SWGN_IMU_SUM_DT = 22,
+  SWGN_IMU_JACOBIAN = 24,  /* [225] 15x15 row-major d(delta)/d(bias) accumulated Jacobian    */
+  SWGN_IMU_SQRT_INFO = 249,/* [225] 15x15 row-major, = LLT(cov^-1).L^T  (get_sqrtinfo)       */
+  SWGN_IMU_STRIDE = 474
+};
+
+/*
+ * One sliding window as a flat factor graph: the content of the reference's long-lived
+ * `ceres::Problem my_problem` plus `options.linear_solver_ordering` at the moment of Solve.
+ * All arrays are caller-owned and only read.
+ */
+typedef struct swgn_graph {
+  /* parameter blocks (identity in the reference = raw double*, here = index) */
+  int32_t n_blocks;
+  const int32_t* block_size;     /* global size                                              */
+  const int32_t* block_manifold; /* SWGN_MANIFOLD_*                                          */
+  const int32_t* block_const;    /* != 0: SetParameterBlockConstant                          */
+  const int32_t* block_group;    /* ParameterBlockOrdering group id; 0 = eliminated e-blocks;
+                                    ties inside a group are broken by block index (the
+                                    reference breaks them by pointer value, ordered_groups.h) */
+  const int32_t* block_offset;   /* first double of the block inside state[]                 */
+  int32_t n_state;
+  const double* state;           /* initial values, n_state doubles                          */
+
+  /* application globals the factors read (RVI/parameter/parameters.h:88,94,100) */
+  double Pbg[3];                 /* IMU -> GNSS antenna lever arm                            */
+  double gravity[3];             /* Rwgw * G, gravity in the ECEF-aligned world frame        */
+  double proj_sqrt_info[4];      /* projection_factor::sqrt_info, 2x2 row-major (swf.cpp:47) */
+  double proj_cauchy_a;          /* CauchyLoss(a) on every projection factor; <= 0: no loss  */
+
+  /* projection_factor <2;7,7,3>: (pose_j, cam extrinsic, world landmark) */
+  int32_t n_proj;
+  const int32_t* proj_blocks;    /* 3 per factor                                             */
+  const double* proj_uv;         /* 2 per factor: pts.x, pts.y on the normalised plane       */
+
+  /* IMUFactor <15;7,9,7,9>: (pose_i, sb_i, pose_j, sb_j) */
+  int32_t n_imu;
+  const int32_t* imu_blocks;     /* 4 per factor                                             */
+  const double* imu_data;        /* SWGN_IMU_STRIDE per factor                               */
+
+  /* GNSS scalar factors */
+  int32_t n_gnss;
+  const int32_t* gnss_kind;      /* SWGN_GNSS_*                                              */
+  const int32_t* gnss_blocks;    /* 3 per factor in the factor's own parameter order, -1 pad */
+  const double* gnss_data;       /* SWGN_GNSS_STRIDE per factor                              */
+
+  /* MarginalizationFactor: r = r0 + J0 * (x [-] x0)  (marginalization_factor.cpp:410-446) */
+  int32_t n_prior;
+  const int32_t* prior_n;        /* rows (= columns) of J0 per prior                         */
+  const int32_t* prior_blk_begin;/* n_prior+1 offsets into prior_blocks/prior_blk_idx        */
+  const int32_t* prior_blocks;   /* keep blocks                                              */
+  const int32_t* prior_blk_idx;  /* first tangent column of that block in J0                 */
+  const int64_t* prior_x0_begin; /* n_prior offsets into prior_x0                            */
+  const double* prior_x0;        /* linearisation point, global sizes, keep-block order      */
+  const int64_t* prior_J_begin;  /* n_prior offsets into prior_J                             */
+  const double* prior_J;         /* J0, n x n row-major                                      */
+  const int64_t* prior_r_begin;  /* n_prior offsets into prior_r0                            */
+  const double* prior_r0;
+
+  /* InitialBlackFactor <1;1>: r = x * istd (initial_factor.cpp:90-96) */
+  int32_t n_unit;
+  const int32_t* unit_block;
+  const double* unit_istd;
+
+  /* residual-block program order (the order of AddResidualBlock calls).  Entry k encodes
+     (kind << 28 | index) with kind 0 proj, 1 imu, 2 gnss, 3 prior, 4 unit.  May be NULL:
+     then the order is proj, imu, gnss, prior, unit.  It only influences summation order.  */
+  int32_t n_order;
+  const uint32_t* order;
+
+  /* ResidualBlock::is_use masks (CERES/internal/ceres/residual_block.h:135), one byte per
+     factor in the same kind-major layout as above (proj, imu, gnss, prior, unit); NULL = all
+     used. */
+  const uint8_t* is_use;
+} swgn_graph;
+
+/* ---- solver options: the subset of ceres::Solver::Options the reference sets, with the
+   reference's effective defaults ------------------------------------ */
+typedef struct swgn_options {
+  int32_t max_num_iterations;            /* 8    yaml MAX_NUM_ITERATIONS                     */
+  int32_t max_num_consecutive_invalid_steps; /* 5  solver.h:303                              */
+  double initial_trust_region_radius;    /* 1e4  solver.h:277                                */
+  double max_trust_region_radius;        /* 1e16 solver.h:278                                */
+  double min_trust_region_radius;        /* 1e-32 solver.h:282                               */
+  double min_relative_decrease;          /* 1e-3 solver.h:286                                */
+  double min_lm_diagonal;                /* 1e-6 solver.h:295                                */
+  double max_lm_diagonal;                /* 1e32 solver.h:296                                */
+  double function_tolerance;             /* 1e-6 solver.h:309                                */
+  double gradient_tolerance;             /* 1e-10 solver.h:316                               */
+  double parameter_tolerance;            /* 1e-8 solver.h:322                                */
+  double dogleg_min_mu;                  /* 1e-12: the reference's modified kMinMu
+                                            (CERES/internal/ceres/dogleg_strategy.cc:51)     */
+  int32_t is_optimize;                   /* ceres::internal::is_optimize; 0 = export mode:
+                                            evaluate + eliminate once, export S and r,
+                                            leave the state untouched
+                                            (schur_complement_solver.cc:172-188)             */
+  int32_t n_parameter_head;              /* ceres::internal::parameter_head.size(); the head
+                                            blocks are the LAST n_parameter_head groups of the
+                                            ordering (swf_gnss.cpp:775-782)                  */
+  int32_t device;                        /* CUDA device ordinal                              */
+  int32_t reserved;
+} swgn_options;
+
+enum { SWGN_CONVERGENCE = 0, SWGN_NO_CONVERGENCE = 1, SWGN_FAILURE = 2 };
+
+typedef struct swgn_summary {
+  double initial_cost;
+  double final_cost;
+  double fixed_cost;
+  int32_t num_successful_steps;   /* counts iteration 0 like Ceres does                      */
+  int32_t num_unsuccessful_steps;
+  int32_t num_iterations;         /* trust-region iterations executed (excluding iteration 0) */
+  int32_t num_linear_solves;      /* Schur eliminate + Cholesky executions                   */
+  int32_t termination_type;       /* SWGN_CONVERGENCE / NO_CONVERGENCE / FAILURE             */
+  int32_t n_e;                    /* tangent dimension of eliminated blocks                  */
+  int32_t n_f;                    /* rows of the reduced system (hs_row)                     */
+  int32_t n_residuals;
+} swgn_summary;
+
+typedef struct swgn_batch swgn_batch;   /* opaque: n independent windows on one device */
+
+void swgn_default_options(swgn_options* o);
+const char* swgn_last_error(void);
+const char* swgn_version(void);
+int32_t swgn_device_count(void);
+
+/* Preprocess (reduced program, ordering, chunk structure: CERES trust_region_preprocessor.cc
+   :360-393) and upload n_windows graphs.  Windows are independent. */
+swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows,
+                              const swgn_graph* const* graphs, swgn_batch** out);
+void swgn_batch_destroy(swgn_batch* b);
+int32_t swgn_batch_size(const swgn_batch* b);
+
+/* Re-upload initial states only (structure unchanged): state_w has graphs[w]->n_state doubles. */
+swgn_status swgn_batch_set_state(swgn_batch* b, int32_t window, const double* state);
+
+/* The whole trust-region solve = ceres::Solve with DENSE_SCHUR + DOGLEG
+   (CERES trust_region_minimizer.cc:67-134).  summaries may be NULL, else n_windows entries.
+   With is_optimize == 0 this is the export-mode solve. */
+swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries);
+
+/* Timing of the last swgn_batch_solve measured with CUDA events on the library's stream:
+   total milliseconds, and the part spent in Schur-elimination launches with their count. */
+swgn_status swgn_batch_last_timing(const swgn_batch* b, double* total_ms, double* schur_ms,
+                                   int32_t* schur_launches, int32_t* kernel_launches);
+
+/* Result read-backs (device -> caller buffer). */
+swgn_status swgn_batch_get_state(swgn_batch* b, int32_t window, double* state);
+/* ceres::internal::{lhs_out, rhs_out, hs_row}: reduced system of the last Eliminate, row-major
+   n x n with only the upper triangle meaningful; S and r may be NULL to query n. */
+swgn_status swgn_batch_get_reduced(swgn_batch* b, int32_t window, double* S, double* r,
+                                   int32_t* n);
+/* ceres::internal::lhs_out2: lower Cholesky factor of the last reduced solve, n x n row-major,
+   strictly-upper part zero. */
+swgn_status swgn_batch_get_cholesky(swgn_batch* b, int32_t window, double* L, int32_t* n);
+/* UpdateSchurHessianOnly (RVI/swf/swf_gnss.cpp:65-94): A = L_nn L_nn^T for the trailing
+   n_tail rows; A is n_tail x n_tail row-major. */
+swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t window, int32_t n_tail,
+                                            double* A);
+
+/* ---- staged entry points (used by the parity tests; each is one device pass) ------------- */
+/* Evaluate r, cost, gradient g = J^T r at the current state (ProgramEvaluator::Evaluate).
+   Output buffers may be NULL.  residuals: n_residuals doubles in the library's row order;
+   gradient: n_e + n_f doubles in column order. */
+swgn_status swgn_batch_evaluate(swgn_batch* b, int32_t window, double* cost, double* residuals,
+                                double* gradient);
+/* Column order actually used: for every column block its graph block index, tangent offset and
+   tangent size; n_cols may be queried with the arrays NULL. */
+swgn_status swgn_batch_get_columns(swgn_batch* b, int32_t window, int32_t* n_cols,
+                                   int32_t* block, int32_t* offset, int32_t* size);
+/* Row order actually used: for every row block the program-order index of its residual block
+   (index into swgn_graph.order semantics) and its first residual row. */
+swgn_status swgn_batch_get_rows(swgn_batch* b, int32_t window, int32_t* n_rows, int32_t* factor,
+                                int32_t* offset);
+/* Dense copy of the block-sparse Jacobian (n_residuals x (n_e+n_f), row-major) for tests. */
+swgn_status swgn_batch_get_dense_jacobian(swgn_batch* b, int32_t window, double* J);
+/* One linear solve on the current linearisation with LM diagonal D (n_e+n_f entries, may be
+   NULL): Eliminate -> Cholesky -> BackSubstitute; x receives the n_e+n_f solution of
+   min |J x - r|^2 + |D x|^2 (CERES schur_complement_solver.cc:126-202). */
+swgn_status swgn_batch_linear_solve(swgn_batch* b, int32_t window, const double* D, double* x);
+
+/* ---- ambiguity resolution (K7/K8) --------------------------------------------------------- */
+/* RTKLIB-style lambda()/mlambda as shipped in RVI/gnss/src/lambda.cpp:204-235, batched:
+   problem k has n[k] float ambiguities a_k (n[k]) and covariance Q_k (n[k] x n[k], column-major),
+   concatenated.  Outputs: F (n[k] x m column-major, concatenated), s (m per problem),
+   info (0 ok, -1 failure) per problem.  Runs on the device; bit-identical to the reference's
+   double-precision arithmetic (compiled without FMA contraction). */
+swgn_status swgn_lambda_batch(int32_t device, int32_t n_problems, const int32_t* n, int32_t m,
+                              const double* a, const double* Q, double* F, double* s,
+                              int32_t* info);
+
+/* Double-difference construction + LAMBDA + ratio test = the decision part of LambdaSearch
+   (RVI/swf/swf_lambda.cpp:101-245) for one window, given the ambiguity information matrix A
+   (n x n row-major, from swgn_batch_get_tail_information) and the float values y.
+   The GNSS epochs of the window (rovers[0..rover_count-1], oldest first) are given as a CSR
+   list: epoch e observes obs_amb[epoch_begin[e] .. epoch_begin[e+1]) where obs_amb is the index
+   of the observed ambiguity inside A/y (or -1 when that ambiguity is not part of A) and
+   obs_sysfreq = sys*2+f in 0..5.  Epochs are visited newest first; last_fix selects the
+   0.2 / 1.4 gate (swf_lambda.cpp:163). */
+typedef struct swgn_fix_result {
+  int32_t n_dd;          /* rows of D                                                        */
+  int32_t status;        /* 0 searched, 1 too few ambiguities (n < 6), 2 too few DD rows,
+                            3 lambda() failed                                                */
+  int32_t search_ok;     /* ratio test decision                                              */
+  int32_t n_different;   /* entries where the two best candidates differ                    */
+  double s[2];           /* squared norms of the two best candidates                        */
+  double s0_partial, s1_partial;
+} swgn_fix_result;
+swgn_status swgn_ambiguity_fix(int32_t device, int32_t n, const double* A, const double* y,
+                               int32_t n_epochs, const int32_t* epoch_begin,
+                               const int32_t* obs_amb, const int32_t* obs_sysfreq,
+                               int32_t last_fix, int32_t* dd_pairs /* 2 per row: (a, ref) */,
+                               double* F /* n_dd x 2 column-major */, swgn_fix_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWGN_H_ */

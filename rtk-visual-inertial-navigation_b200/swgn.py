@@ -1,0 +1,331 @@
+"""ctypes binding of the C ABI in include/swgn.h (libswgn.so) and of the synthetic-window
+generator (libswgn_synth.so).  Harness-side only: tests/, bench.py and __graft_entry__ use it to
+reach the product exactly the way a C/C++ host would.  There is no Python compute path and no CPU
+fallback: loading fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+i32, i64, f64 = C.c_int32, C.c_int64, C.c_double
+P = C.POINTER
+
+
+class Graph(C.Structure):
+    _fields_ = [
+        ("n_blocks", i32), ("block_size", P(i32)), ("block_manifold", P(i32)),
+        ("block_const", P(i32)), ("block_group", P(i32)), ("block_offset", P(i32)),
+        ("n_state", i32), ("state", P(f64)),
+        ("Pbg", f64 * 3), ("gravity", f64 * 3), ("proj_sqrt_info", f64 * 4), ("proj_cauchy_a", f64),
+        ("n_proj", i32), ("proj_blocks", P(i32)), ("proj_uv", P(f64)),
+        ("n_imu", i32), ("imu_blocks", P(i32)), ("imu_data", P(f64)),
+        ("n_gnss", i32), ("gnss_kind", P(i32)), ("gnss_blocks", P(i32)), ("gnss_data", P(f64)),
+        ("n_prior", i32), ("prior_n", P(i32)), ("prior_blk_begin", P(i32)),
+        ("prior_blocks", P(i32)), ("prior_blk_idx", P(i32)),
+        ("prior_x0_begin", P(i64)), ("prior_x0", P(f64)),
+        ("prior_J_begin", P(i64)), ("prior_J", P(f64)),
+        ("prior_r_begin", P(i64)), ("prior_r0", P(f64)),
+        ("n_unit", i32), ("unit_block", P(i32)), ("unit_istd", P(f64)),
+        ("n_order", i32), ("order", P(C.c_uint32)),
+        ("is_use", P(C.c_uint8)),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", i32), ("max_num_consecutive_invalid_steps", i32),
+        ("initial_trust_region_radius", f64), ("max_trust_region_radius", f64),
+        ("min_trust_region_radius", f64), ("min_relative_decrease", f64),
+        ("min_lm_diagonal", f64), ("max_lm_diagonal", f64),
+        ("function_tolerance", f64), ("gradient_tolerance", f64), ("parameter_tolerance", f64),
+        ("dogleg_min_mu", f64),
+        ("is_optimize", i32), ("n_parameter_head", i32), ("device", i32), ("reserved", i32),
+    ]
+
+
+class Summary(C.Structure):
+    _fields_ = [
+        ("initial_cost", f64), ("final_cost", f64), ("fixed_cost", f64),
+        ("num_successful_steps", i32), ("num_unsuccessful_steps", i32),
+        ("num_iterations", i32), ("num_linear_solves", i32), ("termination_type", i32),
+        ("n_e", i32), ("n_f", i32), ("n_residuals", i32),
+    ]
+
+
+class FixResult(C.Structure):
+    _fields_ = [("n_dd", i32), ("status", i32), ("search_ok", i32), ("n_different", i32),
+                ("s", f64 * 2), ("s0_partial", f64), ("s1_partial", f64)]
+
+
+class SynthConfig(C.Structure):
+    _fields_ = [("n_keyframes", i32), ("n_landmarks", i32), ("n_gnss_epochs", i32),
+                ("n_sats", i32), ("seed0", C.c_uint64), ("state_noise", f64)]
+
+
+def _dp(a):
+    return a.ctypes.data_as(P(f64))
+
+
+def _ip(a):
+    return a.ctypes.data_as(P(i32))
+
+
+_synth = None
+_lib = None
+
+
+def synth_lib():
+    global _synth
+    if _synth is None:
+        L = C.CDLL(os.path.join(HERE, "libswgn_synth.so"))
+        L.swgn_synth_create.restype = C.c_void_p
+        L.swgn_synth_create.argtypes = [P(SynthConfig), C.c_uint64]
+        L.swgn_synth_destroy.argtypes = [C.c_void_p]
+        L.swgn_synth_graph.restype = P(Graph)
+        L.swgn_synth_graph.argtypes = [C.c_void_p]
+        L.swgn_synth_truth.restype = P(f64)
+        L.swgn_synth_truth.argtypes = [C.c_void_p]
+        L.swgn_synth_options.argtypes = [C.c_void_p, P(Options)]
+        L.swgn_synth_info.argtypes = [C.c_void_p, P(i32)]
+        L.swgn_synth_default_config.argtypes = [i32, P(SynthConfig)]
+        L.swgn_synth_ambiguity_epochs.restype = i32
+        L.swgn_synth_ambiguity_epochs.argtypes = [C.c_void_p, P(i32), P(i32), P(i32), P(i32)]
+        L.swgn_synth_true_ambiguities.restype = P(f64)
+        L.swgn_synth_true_ambiguities.argtypes = [C.c_void_p]
+        _synth = L
+    return _synth
+
+
+class SynthWindow:
+    """One synthetic window.  which=1: 5 KF x 50 LM VI-only; which=2: the
+    20 KF x 300 LM x 10 GNSS-epoch BASELINE window."""
+
+    def __init__(self, which=2, window_id=0, **overrides):
+        L = synth_lib()
+        cfg = SynthConfig()
+        L.swgn_synth_default_config(which, C.byref(cfg))
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.h = L.swgn_synth_create(C.byref(cfg), window_id)
+        if not self.h:
+            raise RuntimeError("swgn_synth_create failed")
+        self.graph_p = L.swgn_synth_graph(self.h)
+        self.graph = self.graph_p.contents
+        info = (i32 * 8)()
+        L.swgn_synth_info(self.h, info)
+        (self.n_frames, self.n_obs, self.n_imu, self.n_gnss, self.n_amb, self.first_amb_block,
+         self.n_prior_rows, self.n_blocks) = list(info)
+        self.n_state = self.graph.n_state
+
+    def options(self):
+        o = Options()
+        synth_lib().swgn_synth_options(self.h, C.byref(o))
+        return o
+
+    def state0(self):
+        return np.ctypeslib.as_array(self.graph.state, shape=(self.n_state,)).copy()
+
+    def truth(self):
+        return np.ctypeslib.as_array(synth_lib().swgn_synth_truth(self.h), shape=(self.n_state,)).copy()
+
+    def block_offsets(self):
+        return np.ctypeslib.as_array(self.graph.block_offset, shape=(self.n_blocks,)).copy()
+
+    def ambiguity_epochs(self):
+        L = synth_lib()
+        n_obs = i32()
+        ne = L.swgn_synth_ambiguity_epochs(self.h, None, None, None, C.byref(n_obs))
+        eb = np.zeros(ne + 1, np.int32)
+        oa = np.zeros(max(n_obs.value, 1), np.int32)
+        sf = np.zeros(max(n_obs.value, 1), np.int32)
+        L.swgn_synth_ambiguity_epochs(self.h, _ip(eb), _ip(oa), _ip(sf), None)
+        return eb, oa[:n_obs.value], sf[:n_obs.value]
+
+    def true_ambiguities(self):
+        return np.ctypeslib.as_array(synth_lib().swgn_synth_true_ambiguities(self.h),
+                                     shape=(self.n_amb,)).copy()
+
+    def __del__(self):
+        try:
+            if self.h:
+                synth_lib().swgn_synth_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def lib():
+    """libswgn.so: the CUDA product.  Raises if it is not built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libswgn.so")
+        if not os.path.exists(path):
+            raise RuntimeError("libswgn.so is not built (run __graft_entry__.build()); "
+                               "there is no CPU fallback for the solver")
+        L = C.CDLL(path)
+        L.swgn_last_error.restype = C.c_char_p
+        L.swgn_version.restype = C.c_char_p
+        L.swgn_default_options.argtypes = [P(Options)]
+        L.swgn_batch_create.argtypes = [P(Options), i32, P(P(Graph)), P(C.c_void_p)]
+        L.swgn_batch_destroy.argtypes = [C.c_void_p]
+        L.swgn_batch_size.argtypes = [C.c_void_p]
+        L.swgn_batch_set_state.argtypes = [C.c_void_p, i32, P(f64)]
+        L.swgn_batch_solve.argtypes = [C.c_void_p, P(Summary)]
+        L.swgn_batch_last_timing.argtypes = [C.c_void_p, P(f64), P(f64), P(i32), P(i32)]
+        L.swgn_batch_get_state.argtypes = [C.c_void_p, i32, P(f64)]
+        L.swgn_batch_get_reduced.argtypes = [C.c_void_p, i32, P(f64), P(f64), P(i32)]
+        L.swgn_batch_get_cholesky.argtypes = [C.c_void_p, i32, P(f64), P(i32)]
+        L.swgn_batch_get_tail_information.argtypes = [C.c_void_p, i32, i32, P(f64)]
+        L.swgn_batch_evaluate.argtypes = [C.c_void_p, i32, P(f64), P(f64), P(f64)]
+        L.swgn_batch_get_columns.argtypes = [C.c_void_p, i32, P(i32), P(i32), P(i32), P(i32)]
+        L.swgn_batch_get_rows.argtypes = [C.c_void_p, i32, P(i32), P(i32), P(i32)]
+        L.swgn_batch_get_dense_jacobian.argtypes = [C.c_void_p, i32, P(f64)]
+        L.swgn_batch_linear_solve.argtypes = [C.c_void_p, i32, P(f64), P(f64)]
+        L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
+        L.swgn_ambiguity_fix.argtypes = [i32, i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32),
+                                         i32, P(i32), P(f64), P(FixResult)]
+        _lib = L
+    return _lib
+
+
+def default_options():
+    o = Options()
+    lib().swgn_default_options(C.byref(o))
+    return o
+
+
+def _check(st, what):
+    if st != 0:
+        raise RuntimeError("%s failed: status %d: %s" % (what, st, lib().swgn_last_error().decode()))
+
+
+class Batch:
+    """swgn_batch: n independent windows resident on one device."""
+
+    def __init__(self, graph_ptrs, options):
+        L = lib()
+        n = len(graph_ptrs)
+        arr = (P(Graph) * n)(*graph_ptrs)
+        self.h = C.c_void_p()
+        self.n = n
+        self.options = options
+        _check(L.swgn_batch_create(C.byref(options), n, arr, C.byref(self.h)), "swgn_batch_create")
+
+    def solve(self):
+        sm = (Summary * self.n)()
+        _check(lib().swgn_batch_solve(self.h, sm), "swgn_batch_solve")
+        return sm
+
+    def timing(self):
+        t, s = f64(), f64()
+        nl, kl = i32(), i32()
+        _check(lib().swgn_batch_last_timing(self.h, C.byref(t), C.byref(s), C.byref(nl), C.byref(kl)),
+               "swgn_batch_last_timing")
+        return t.value, s.value, nl.value, kl.value
+
+    def set_state(self, w, x):
+        x = np.ascontiguousarray(x, np.float64)
+        _check(lib().swgn_batch_set_state(self.h, w, _dp(x)), "swgn_batch_set_state")
+
+    def get_state(self, w, n_state):
+        x = np.zeros(n_state)
+        _check(lib().swgn_batch_get_state(self.h, w, _dp(x)), "swgn_batch_get_state")
+        return x
+
+    def get_reduced(self, w):
+        n = i32()
+        _check(lib().swgn_batch_get_reduced(self.h, w, None, None, C.byref(n)), "get_reduced")
+        S = np.zeros((n.value, n.value))
+        r = np.zeros(n.value)
+        _check(lib().swgn_batch_get_reduced(self.h, w, _dp(S), _dp(r), C.byref(n)), "get_reduced")
+        return S, r
+
+    def get_cholesky(self, w):
+        n = i32()
+        _check(lib().swgn_batch_get_cholesky(self.h, w, None, C.byref(n)), "get_cholesky")
+        Lm = np.zeros((n.value, n.value))
+        _check(lib().swgn_batch_get_cholesky(self.h, w, _dp(Lm), C.byref(n)), "get_cholesky")
+        return Lm
+
+    def tail_information(self, w, n_tail):
+        A = np.zeros((n_tail, n_tail))
+        _check(lib().swgn_batch_get_tail_information(self.h, w, n_tail, _dp(A)), "tail_information")
+        return A
+
+    def columns(self, w):
+        n = i32()
+        _check(lib().swgn_batch_get_columns(self.h, w, C.byref(n), None, None, None), "get_columns")
+        b, o, s = (np.zeros(n.value, np.int32) for _ in range(3))
+        _check(lib().swgn_batch_get_columns(self.h, w, C.byref(n), _ip(b), _ip(o), _ip(s)), "get_columns")
+        return b, o, s
+
+    def rows(self, w):
+        n = i32()
+        _check(lib().swgn_batch_get_rows(self.h, w, C.byref(n), None, None), "get_rows")
+        f, o = (np.zeros(n.value, np.int32) for _ in range(2))
+        _check(lib().swgn_batch_get_rows(self.h, w, C.byref(n), _ip(f), _ip(o)), "get_rows")
+        return f, o
+
+    def evaluate(self, w, n_res, n_cols):
+        cost = f64()
+        r = np.zeros(n_res)
+        g = np.zeros(n_cols)
+        _check(lib().swgn_batch_evaluate(self.h, w, C.byref(cost), _dp(r), _dp(g)), "evaluate")
+        return cost.value, r, g
+
+    def dense_jacobian(self, w, n_res, n_cols):
+        J = np.zeros((n_res, n_cols))
+        _check(lib().swgn_batch_get_dense_jacobian(self.h, w, _dp(J)), "dense_jacobian")
+        return J
+
+    def linear_solve(self, w, D, n_cols):
+        x = np.zeros(n_cols)
+        Dp = None
+        if D is not None:
+            D = np.ascontiguousarray(D, np.float64)
+            Dp = _dp(D)
+        _check(lib().swgn_batch_linear_solve(self.h, w, Dp, _dp(x)), "linear_solve")
+        return x
+
+    def close(self):
+        if self.h:
+            lib().swgn_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lambda_batch(ns, m, a, Q, device=0):
+    ns = np.ascontiguousarray(ns, np.int32)
+    a = np.ascontiguousarray(a, np.float64)
+    Q = np.ascontiguousarray(Q, np.float64)
+    F = np.zeros(int(ns.sum()) * m)
+    s = np.zeros(len(ns) * m)
+    info = np.zeros(len(ns), np.int32)
+    _check(lib().swgn_lambda_batch(device, len(ns), _ip(ns), m, _dp(a), _dp(Q), _dp(F), _dp(s),
+                                   _ip(info)), "swgn_lambda_batch")
+    return F, s, info
+
+
+def ambiguity_fix(A, y, epoch_begin, obs_amb, obs_sysfreq, last_fix=0, device=0):
+    n = len(y)
+    A = np.ascontiguousarray(A, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    eb = np.ascontiguousarray(epoch_begin, np.int32)
+    oa = np.ascontiguousarray(obs_amb, np.int32)
+    sf = np.ascontiguousarray(obs_sysfreq, np.int32)
+    pairs = np.zeros(2 * max(n, 1) * max(len(eb) - 1, 1), np.int32)
+    F = np.zeros(2 * max(n, 1) * max(len(eb) - 1, 1))
+    res = FixResult()
+    _check(lib().swgn_ambiguity_fix(device, n, _dp(A), _dp(y), len(eb) - 1, _ip(eb), _ip(oa), _ip(sf),
+                                    last_fix, _ip(pairs), _dp(F), C.byref(res)), "swgn_ambiguity_fix")
+    nb = res.n_dd
+    return pairs[:2 * nb].reshape(nb, 2), F[:2 * nb].reshape(2, nb).T.copy(), res
