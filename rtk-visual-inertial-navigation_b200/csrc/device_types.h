@@ -1,0 +1,128 @@
+// Plain-old-data descriptors shared by the host planner and the CUDA kernels.
+//
+// HBM layout (one swgn_batch): three pools hold every window back to back,
+//   ipool : int32  index arrays  (structure; read-only after upload)
+//   cpool : double factor constants (read-only after upload)
+//   wpool : double work arrays (state, residuals, block-sparse Jacobian values, vectors, the
+//           reduced system S | rhs, chunk inverses)
+// and WinDesc[w] carries the per-window counts plus 64-bit offsets of each array inside its pool.
+// All per-window arrays start on 16-byte boundaries so kernels can use 128-bit accesses.
+#pragma once
+#include <stdint.h>
+
+namespace swgn {
+
+enum IArr {
+  I_COL_STATE = 0,  // [n_cols] offset of the block inside the window state
+  I_COL_SIZE,       // [n_cols] tangent (local) size
+  I_COL_GSIZE,      // [n_cols] ambient (global) size
+  I_COL_POS,        // [n_cols] tangent offset; e-blocks first
+  I_COL_BLOCK,      // [n_cols] graph block index (for read-backs)
+  I_TCOL,           // [n_t]    column block of every tangent scalar
+  I_ROW_RES,        // [n_rows] first residual row
+  I_ROW_NRES,       // [n_rows]
+  I_ROW_CELL,       // [n_rows+1] CSR into cells
+  I_ROW_FACTOR,     // [n_rows] program-order index of the residual block (read-backs)
+  I_CELL_COL,       // [n_cells]
+  I_CELL_VAL,       // [n_cells] offset of the cell's values (row-major n_res x col_size) in W_JAC
+  I_CELL_SLOT,      // [n_cells] slot of the cell in its chunk's E'F buffer, -1 for the e-cell/no chunk
+  I_RS_ROW,         // [n_res] row block of every residual scalar
+  I_CHUNK_ROW,      // [n_chunks+1] row range of every chunk
+  I_CHUNK_ECOL,     // [n_chunks]
+  I_CHUNK_SLOT,     // [n_chunks+1] CSR into slots
+  I_CHUNK_INV,      // [n_chunks] offset of (E'E + D^2)^-1 inside W_EINV
+  I_SLOT_COL,       // [n_slots] f column of the slot, ascending inside a chunk
+  I_SLOT_BUF,       // [n_slots] offset of the e x f block inside the chunk buffer
+  I_CSC_PTR,        // [n_cols+1]
+  I_CSC_ROW,        // [nnz] row block
+  I_CSC_VAL,        // [nnz] value offset
+  I_PROJ,           // [n_proj * 8]  state_off[3], jac_off[3], res_off, 0
+  I_IMU,            // [n_imu * 12]  state_off[4], jac_off[4], res_off, 0,0,0
+  I_GNSS,           // [n_gnss * 8]  kind, state_off[3], jac_off[3], res_off
+  I_PRIOR,          // [n_prior * 8] n, n_blk, res_off, blk_begin, J_off, r0_off, 0, 0
+  I_PRIOR_BLK,      // [n_prior_blk * 6] state_off, gsize, idx, jac_off, x0_off, 0
+  I_UNIT,           // [n_unit * 4]  state_off, jac_off, res_off, 0
+  NUM_IARR
+};
+
+enum CArr {
+  C_GLOBALS = 0,  // Pbg[3], gravity[3], proj_sqrt_info[4], cauchy_a, pad -> 12
+  C_PROJ_UV,      // [n_proj * 2]
+  C_IMU,          // [n_imu * IMU_DEV_STRIDE]
+  C_GNSS,         // [n_gnss * GNSS_DEV_STRIDE]
+  C_PRIOR_J,      // concatenated n x n row-major
+  C_PRIOR_R0,
+  C_PRIOR_X0,
+  C_UNIT,         // [n_unit]
+  NUM_CARR
+};
+
+enum WArr {
+  W_X = 0,   // [n_state] current point
+  W_XCAND,   // [n_state] candidate point
+  W_XBEST,   // [n_state] lowest-cost point seen (what goes back to the user)
+  W_X0,      // [n_state] state at upload (restored when a solve fails)
+  W_RES,     // [n_res]
+  W_JAC,     // [n_jac] block-sparse Jacobian values, cells in row order
+  W_DIAG,    // [n_t] sqrt(clamp(colnorm^2))
+  W_G,       // [n_t] J^T r
+  W_GHAT,    // [n_t] J^T r / diag
+  W_GN,      // [n_t] scaled Gauss-Newton step
+  W_STEP,    // [n_t] trust-region step (unscaled)
+  W_Y,       // [n_t] linear solve output [y_e ; z]
+  W_LMD,     // [n_t] LM diagonal D = diag * sqrt(mu)
+  W_S,       // [n_f * ld] reduced system, row-major upper triangle; column n_f holds the rhs
+  W_SCOPY,   // [n_f * ld] copy of S|rhs before factorisation (exports / tests)
+  W_EINV,    // chunk inverses
+  NUM_WARR
+};
+
+enum { IMU_DEV_STRIDE = 296, GNSS_DEV_STRIDE = 12 };
+// IMU device record: [0..23] as the ABI record's first 24 doubles, [24..68] the five 3x3 blocks
+// dp_dba, dp_dbg, dq_dbg, dv_dba, dv_dbg (row-major), [70..294] sqrt_info 15x15 row-major
+enum { IMU_DEV_BLOCKS = 24, IMU_DEV_SQRT = 70 };
+
+enum FactorKind { K_PROJ = 0, K_IMU = 1, K_GNSS = 2, K_PRIOR = 3, K_UNIT = 4 };
+
+struct WinDesc {
+  int32_t n_state, n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_cells, n_chunks, n_slots;
+  int32_t n_jac, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, max_buf, n_einv, n_head;
+  int64_t ioff[NUM_IARR];
+  int64_t coff[NUM_CARR];
+  int64_t woff[NUM_WARR];
+};
+
+// per-window trust-region state (TrustRegionMinimizer + DoglegStrategy + StepEvaluator members)
+struct TRState {
+  double x_cost, candidate_cost, minimum_cost, model_cost_change, fixed_cost, initial_cost;
+  double final_cost;           // running minimum of the recorded iteration costs
+  double radius, mu, alpha, dogleg_step_norm, x_norm;
+  double gradient_max_norm;
+  double ghat_norm;            // |J^T r / d|
+  double relative_decrease, step_norm, iter_cost;
+  double se_min, se_cur, se_ref, se_cand, se_acc_ref, se_acc_cand;
+  int32_t se_nonmono;
+  int32_t iteration, num_successful, num_unsuccessful, num_consecutive_invalid;
+  int32_t num_linear_solves;
+  int32_t reuse;               // DoglegStrategy::reuse_
+  int32_t active;              // minimiser still running
+  int32_t termination;         // SWGN_CONVERGENCE / NO_CONVERGENCE / FAILURE
+  int32_t last_successful;     // iteration_summary_.step_is_successful of the finished iteration
+  int32_t need_solve;          // this iteration still needs a (re)try of the linear solve
+  int32_t solve_ok;            // linear solve of this iteration produced a finite GN step
+  int32_t step_valid;          // model_cost_change > 0
+  int32_t accepted;            // step accepted at the end of this iteration
+  int32_t eval_failed;
+  int32_t have_factor;         // W_S currently holds a Cholesky factor (lhs_out2 available)
+  int32_t pad;
+};
+
+struct SolverParams {
+  int32_t max_num_iterations, max_num_consecutive_invalid_steps;
+  double initial_radius, max_radius, min_radius, min_relative_decrease;
+  double min_lm_diagonal, max_lm_diagonal;
+  double function_tolerance, gradient_tolerance, parameter_tolerance, min_mu;
+  int32_t is_optimize, n_parameter_head, keep_reduced, pad;
+};
+
+}  // namespace swgn

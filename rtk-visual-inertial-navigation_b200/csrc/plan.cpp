@@ -1,0 +1,413 @@
+// Host-side preprocessing of one window (see plan.h).  Integer/structural work only; all
+// arithmetic of the solve happens on the device.
+#include "plan.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace swgn {
+namespace {
+
+struct Factor {
+  int kind, idx;             // storage position inside its kind table
+  std::vector<int> blocks;   // graph block ids in the factor's own parameter order
+  int nres;
+  bool is_use = true;
+  bool active = false;       // part of the reduced program
+  int res_off = -1;          // first residual row (active only)
+  std::vector<int> jac_off;  // per parameter: offset of its cell in W_JAC, -1 constant/inactive
+};
+
+inline int local_size(int size, int manifold) { return manifold == SWGN_MANIFOLD_POSE ? 6 : size; }
+inline int64_t align2(int64_t x) { return (x + 1) & ~int64_t(1); }
+
+}  // namespace
+
+swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P, std::string* err) {
+  auto fail = [&](swgn_status st, const char* m) {
+    if (err) *err = m;
+    return st;
+  };
+  if (!g || g->n_blocks <= 0 || !g->block_size || !g->state) return fail(SWGN_ERR_INVALID, "empty graph");
+  const int nb = g->n_blocks;
+  for (int i = 0; i < nb; ++i) {
+    if (g->block_size[i] <= 0) return fail(SWGN_ERR_INVALID, "non-positive block size");
+    if (g->block_manifold[i] == SWGN_MANIFOLD_POSE && g->block_size[i] != 7)
+      return fail(SWGN_ERR_INVALID, "pose manifold on a block that is not 7-dim");
+    if (g->block_offset[i] < 0 || g->block_offset[i] + g->block_size[i] > g->n_state)
+      return fail(SWGN_ERR_INVALID, "block outside the state vector");
+  }
+
+  // ---- factors, kind-major storage
+  std::vector<Factor> fac;
+  int kind_begin[6] = {0, 0, 0, 0, 0, 0};
+  auto add_factor = [&](int kind, int idx, const int32_t* blocks, int n, int nres) -> bool {
+    Factor f;
+    f.kind = kind;
+    f.idx = idx;
+    f.nres = nres;
+    for (int k = 0; k < n; ++k) {
+      if (blocks[k] < 0 || blocks[k] >= nb) return false;
+      f.blocks.push_back(blocks[k]);
+    }
+    f.jac_off.assign(n, -1);
+    fac.push_back(f);
+    return true;
+  };
+  static const int kGnssArity[6] = {2, 3, 3, 2, 3, 2};
+  static const int kGnssSizes[6][3] = {{7, 1, 0}, {7, 1, 1}, {7, 1, 1}, {7, 1, 0}, {9, 1, 7}, {1, 1, 0}};
+  for (int i = 0; i < g->n_proj; ++i)
+    if (!add_factor(K_PROJ, i, g->proj_blocks + 3 * i, 3, 2)) return fail(SWGN_ERR_INVALID, "bad proj block");
+  kind_begin[1] = (int)fac.size();
+  for (int i = 0; i < g->n_imu; ++i)
+    if (!add_factor(K_IMU, i, g->imu_blocks + 4 * i, 4, 15)) return fail(SWGN_ERR_INVALID, "bad imu block");
+  kind_begin[2] = (int)fac.size();
+  for (int i = 0; i < g->n_gnss; ++i) {
+    int k = g->gnss_kind[i];
+    if (k < 0 || k > 5) return fail(SWGN_ERR_INVALID, "bad gnss kind");
+    if (!add_factor(K_GNSS, i, g->gnss_blocks + 3 * i, kGnssArity[k], 1)) return fail(SWGN_ERR_INVALID, "bad gnss block");
+    for (int p = 0; p < kGnssArity[k]; ++p)
+      if (g->block_size[fac.back().blocks[p]] != kGnssSizes[k][p]) return fail(SWGN_ERR_INVALID, "gnss block size mismatch");
+  }
+  kind_begin[3] = (int)fac.size();
+  for (int i = 0; i < g->n_prior; ++i) {
+    int b0 = g->prior_blk_begin[i], b1 = g->prior_blk_begin[i + 1];
+    if (!add_factor(K_PRIOR, i, g->prior_blocks + b0, b1 - b0, g->prior_n[i])) return fail(SWGN_ERR_INVALID, "bad prior block");
+  }
+  kind_begin[4] = (int)fac.size();
+  for (int i = 0; i < g->n_unit; ++i) {
+    if (!add_factor(K_UNIT, i, g->unit_block + i, 1, 1)) return fail(SWGN_ERR_INVALID, "bad unit block");
+    if (g->block_size[g->unit_block[i]] != 1) return fail(SWGN_ERR_INVALID, "unit factor on a non-scalar block");
+  }
+  kind_begin[5] = (int)fac.size();
+  for (const Factor& f : fac) {
+    static const int proj_sz[3] = {7, 7, 3}, imu_sz[4] = {7, 9, 7, 9};
+    if (f.kind == K_PROJ)
+      for (int p = 0; p < 3; ++p)
+        if (g->block_size[f.blocks[p]] != proj_sz[p]) return fail(SWGN_ERR_INVALID, "proj block size mismatch");
+    if (f.kind == K_IMU)
+      for (int p = 0; p < 4; ++p)
+        if (g->block_size[f.blocks[p]] != imu_sz[p]) return fail(SWGN_ERR_INVALID, "imu block size mismatch");
+    for (size_t a = 0; a < f.blocks.size(); ++a)
+      for (size_t b = a + 1; b < f.blocks.size(); ++b)
+        if (f.blocks[a] == f.blocks[b]) return fail(SWGN_ERR_INVALID, "duplicate parameter block in a residual block");
+  }
+  if (g->is_use)
+    for (size_t i = 0; i < fac.size(); ++i) fac[i].is_use = g->is_use[i] != 0;
+
+  // ---- program order
+  std::vector<int> program;
+  if (g->order && g->n_order > 0) {
+    std::vector<char> seen(fac.size(), 0);
+    for (int k = 0; k < g->n_order; ++k) {
+      uint32_t kind = g->order[k] >> 28, idx = g->order[k] & 0x0fffffffu;
+      if (kind > 4 || (int)idx >= kind_begin[kind + 1] - kind_begin[kind]) return fail(SWGN_ERR_INVALID, "bad program order entry");
+      int f = kind_begin[kind] + (int)idx;
+      if (seen[f]) return fail(SWGN_ERR_INVALID, "residual block listed twice in the program order");
+      seen[f] = 1;
+      program.push_back(f);
+    }
+    if (program.size() != fac.size()) return fail(SWGN_ERR_INVALID, "program order does not list every residual block");
+  } else {
+    program.resize(fac.size());
+    std::iota(program.begin(), program.end(), 0);
+  }
+  std::vector<int> program_index(fac.size());
+  for (size_t k = 0; k < program.size(); ++k) program_index[program[k]] = (int)k;
+
+  // ---- RemoveFixedBlocks (CERES program.cc:304-411 with the is_use mask, M3)
+  std::vector<char> referenced(nb, 0);
+  int n_active = 0;
+  for (int fi : program) {
+    Factor& f = fac[fi];
+    bool all_const = true;
+    for (int b : f.blocks)
+      if (!g->block_const[b]) {
+        all_const = false;
+        referenced[b] = 1;
+      }
+    f.active = !all_const && f.is_use;
+    n_active += f.active;
+  }
+  std::vector<int> cols;
+  for (int b = 0; b < nb; ++b)
+    if (referenced[b]) cols.push_back(b);
+  if (cols.empty() || n_active == 0) return fail(SWGN_ERR_INVALID, "nothing to optimise: empty reduced program");
+
+  // ---- ordering (reorder_program.cc:209-245): group ascending, then block index
+  int min_group_all = INT32_MAX, min_group = INT32_MAX;
+  for (int b = 0; b < nb; ++b)
+    if (g->block_group[b] >= 0) min_group_all = std::min(min_group_all, g->block_group[b]);
+  for (int b : cols) {
+    if (g->block_group[b] < 0) return fail(SWGN_ERR_ORDERING, "a variable parameter block is missing from the ordering");
+    min_group = std::min(min_group, g->block_group[b]);
+  }
+  if (min_group != min_group_all)
+    return fail(SWGN_ERR_UNSUPPORTED,
+                "first elimination group is empty after removing fixed blocks (Ceres would switch linear solver)");
+  std::stable_sort(cols.begin(), cols.end(), [&](int a, int b) {
+    if (g->block_group[a] != g->block_group[b]) return g->block_group[a] < g->block_group[b];
+    return a < b;
+  });
+  const int n_cols = (int)cols.size();
+  int n_ecols = 0;
+  for (int b : cols) n_ecols += (g->block_group[b] == min_group);
+  std::vector<int> col_of_block(nb, -1), col_pos(n_cols), col_size(n_cols);
+  int n_t = 0, n_e = 0;
+  for (int c = 0; c < n_cols; ++c) {
+    col_of_block[cols[c]] = c;
+    col_size[c] = local_size(g->block_size[cols[c]], g->block_manifold[cols[c]]);
+    col_pos[c] = n_t;
+    n_t += col_size[c];
+    if (c < n_ecols) n_e += col_size[c];
+  }
+  const int n_f = n_t - n_e;
+
+  // ---- independence of the e-blocks (program.cc:413-434) + lexicographic row order
+  // (reorder_program.cc:247-326: buckets filled back to front)
+  std::vector<int> active_list, minpos;
+  std::vector<int> hist(n_ecols + 1, 0);
+  for (int fi : program) {
+    Factor& f = fac[fi];
+    if (!f.active) continue;
+    int cnt = 0, pos = n_ecols;
+    for (int b : f.blocks) {
+      int c = col_of_block[b];
+      if (g->block_const[b] || c < 0) continue;
+      if (c < n_ecols) ++cnt;
+      pos = std::min(pos, c);
+    }
+    if (cnt > 1) return fail(SWGN_ERR_ORDERING, "The first elimination group is not an independent set");
+    active_list.push_back(fi);
+    minpos.push_back(pos);
+    hist[pos]++;
+  }
+  for (int e = 0; e < n_ecols; ++e)
+    if (hist[e] == 0) return fail(SWGN_ERR_INVALID, "an eliminated parameter block has no residual block");
+  std::vector<int> offsets(n_ecols + 1);
+  std::partial_sum(hist.begin(), hist.end(), offsets.begin());
+  std::vector<int> rows(active_list.size(), -1);
+  for (size_t i = 0; i < active_list.size(); ++i) rows[--offsets[minpos[i]]] = active_list[i];
+  const int n_rows = (int)rows.size();
+
+  // ---- cells, Jacobian value offsets, chunks, slots
+  std::vector<int32_t>*I = P->iarr;
+  for (int a = 0; a < NUM_IARR; ++a) I[a].clear();
+  for (int a = 0; a < NUM_CARR; ++a) P->carr[a].clear();
+  int n_res = 0, n_jac = 0;
+  int64_t schur_doubles = 0;
+  I[I_ROW_CELL].push_back(0);
+  for (int r = 0; r < n_rows; ++r) {
+    Factor& f = fac[rows[r]];
+    f.res_off = n_res;
+    I[I_ROW_RES].push_back(n_res);
+    I[I_ROW_NRES].push_back(f.nres);
+    I[I_ROW_FACTOR].push_back(program_index[rows[r]]);
+    for (int k = 0; k < f.nres; ++k) I[I_RS_ROW].push_back(r);
+    std::vector<std::pair<int, int>> cells;  // (col, param slot)
+    for (size_t p = 0; p < f.blocks.size(); ++p) {
+      int b = f.blocks[p];
+      if (g->block_const[b]) continue;
+      cells.push_back({col_of_block[b], (int)p});
+    }
+    std::sort(cells.begin(), cells.end());
+    for (auto& c : cells) {
+      I[I_CELL_COL].push_back(c.first);
+      I[I_CELL_VAL].push_back(n_jac);
+      I[I_CELL_SLOT].push_back(-1);
+      f.jac_off[c.second] = n_jac;
+      n_jac += f.nres * col_size[c.first];
+      schur_doubles += (int64_t)f.nres * col_size[c.first];
+    }
+    schur_doubles += f.nres;
+    I[I_ROW_CELL].push_back((int32_t)I[I_CELL_COL].size());
+    n_res += f.nres;
+  }
+  const int n_cells = (int)I[I_CELL_COL].size();
+  // chunks (schur_eliminator_impl.h:118-156)
+  int n_einv = 0, max_buf = 1;
+  {
+    int r = 0;
+    I[I_CHUNK_ROW].push_back(0);
+    I[I_CHUNK_SLOT].push_back(0);
+    while (r < n_rows) {
+      int first_cell = I[I_ROW_CELL][r];
+      int e = I[I_CELL_COL][first_cell];
+      if (e >= n_ecols) break;
+      int r1 = r;
+      std::vector<int> fcols;
+      while (r1 < n_rows && I[I_CELL_COL][I[I_ROW_CELL][r1]] == e) {
+        for (int c = I[I_ROW_CELL][r1] + 1; c < I[I_ROW_CELL][r1 + 1]; ++c) fcols.push_back(I[I_CELL_COL][c]);
+        ++r1;
+      }
+      std::sort(fcols.begin(), fcols.end());
+      fcols.erase(std::unique(fcols.begin(), fcols.end()), fcols.end());
+      const int es = col_size[e];
+      int slot0 = (int)I[I_SLOT_COL].size(), buf = 0;
+      for (int fc : fcols) {
+        I[I_SLOT_COL].push_back(fc);
+        I[I_SLOT_BUF].push_back(buf);
+        buf += es * col_size[fc];
+      }
+      max_buf = std::max(max_buf, buf);
+      for (int rr = r; rr < r1; ++rr)
+        for (int c = I[I_ROW_CELL][rr] + 1; c < I[I_ROW_CELL][rr + 1]; ++c) {
+          int fc = I[I_CELL_COL][c];
+          int s = (int)(std::lower_bound(fcols.begin(), fcols.end(), fc) - fcols.begin());
+          I[I_CELL_SLOT][c] = s;
+        }
+      (void)slot0;
+      I[I_CHUNK_ECOL].push_back(e);
+      I[I_CHUNK_INV].push_back(n_einv);
+      n_einv += (int)align2(es * es);
+      I[I_CHUNK_ROW].push_back(r1);
+      I[I_CHUNK_SLOT].push_back((int32_t)I[I_SLOT_COL].size());
+      r = r1;
+    }
+  }
+  const int n_chunks = (int)I[I_CHUNK_ECOL].size();
+  if (n_chunks != n_ecols) return fail(SWGN_ERR_INVALID, "chunk detection does not match the eliminated blocks");
+  const int n_slots = (int)I[I_SLOT_COL].size();
+  // CSC
+  {
+    std::vector<int> cnt(n_cols + 1, 0);
+    for (int c = 0; c < n_cells; ++c) cnt[I[I_CELL_COL][c] + 1]++;
+    std::partial_sum(cnt.begin(), cnt.end(), cnt.begin());
+    I[I_CSC_PTR].assign(cnt.begin(), cnt.end());
+    I[I_CSC_ROW].assign(n_cells, 0);
+    I[I_CSC_VAL].assign(n_cells, 0);
+    std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+    for (int r = 0; r < n_rows; ++r)
+      for (int c = I[I_ROW_CELL][r]; c < I[I_ROW_CELL][r + 1]; ++c) {
+        int col = I[I_CELL_COL][c];
+        I[I_CSC_ROW][cur[col]] = r;
+        I[I_CSC_VAL][cur[col]] = I[I_CELL_VAL][c];
+        cur[col]++;
+      }
+  }
+  for (int c = 0; c < n_cols; ++c) {
+    I[I_COL_STATE].push_back(g->block_offset[cols[c]]);
+    I[I_COL_SIZE].push_back(col_size[c]);
+    I[I_COL_GSIZE].push_back(g->block_size[cols[c]]);
+    I[I_COL_POS].push_back(col_pos[c]);
+    I[I_COL_BLOCK].push_back(cols[c]);
+    for (int k = 0; k < col_size[c]; ++k) I[I_TCOL].push_back(c);
+  }
+
+  // ---- factor tables + constants (kind-major storage order)
+  std::vector<double>* Cc = P->carr;
+  Cc[C_GLOBALS] = {g->Pbg[0], g->Pbg[1], g->Pbg[2], g->gravity[0], g->gravity[1], g->gravity[2],
+                   g->proj_sqrt_info[0], g->proj_sqrt_info[1], g->proj_sqrt_info[2], g->proj_sqrt_info[3],
+                   g->proj_cauchy_a, 0.0};
+  auto soff = [&](int b) { return g->block_offset[b]; };
+  for (int i = 0; i < g->n_proj; ++i) {
+    const Factor& f = fac[kind_begin[0] + i];
+    int32_t rec[8] = {soff(f.blocks[0]), soff(f.blocks[1]), soff(f.blocks[2]), f.jac_off[0], f.jac_off[1],
+                      f.jac_off[2], f.active ? f.res_off : -1, 0};
+    I[I_PROJ].insert(I[I_PROJ].end(), rec, rec + 8);
+    Cc[C_PROJ_UV].push_back(g->proj_uv[2 * i]);
+    Cc[C_PROJ_UV].push_back(g->proj_uv[2 * i + 1]);
+  }
+  for (int i = 0; i < g->n_imu; ++i) {
+    const Factor& f = fac[kind_begin[1] + i];
+    int32_t rec[12] = {soff(f.blocks[0]), soff(f.blocks[1]), soff(f.blocks[2]), soff(f.blocks[3]),
+                       f.jac_off[0], f.jac_off[1], f.jac_off[2], f.jac_off[3], f.active ? f.res_off : -1, 0, 0, 0};
+    I[I_IMU].insert(I[I_IMU].end(), rec, rec + 12);
+    const double* src = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
+    size_t o = Cc[C_IMU].size();
+    Cc[C_IMU].resize(o + IMU_DEV_STRIDE, 0.0);
+    double* dst = Cc[C_IMU].data() + o;
+    for (int k = 0; k < 24; ++k) dst[k] = src[k];
+    const double* J = src + SWGN_IMU_JACOBIAN;
+    static const int blk[5][2] = {{0, 9}, {0, 12}, {3, 12}, {6, 9}, {6, 12}};  // dp_dba dp_dbg dq_dbg dv_dba dv_dbg
+    for (int bI = 0; bI < 5; ++bI)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) dst[IMU_DEV_BLOCKS + bI * 9 + r * 3 + c] = J[(blk[bI][0] + r) * 15 + blk[bI][1] + c];
+    for (int k = 0; k < 225; ++k) dst[IMU_DEV_SQRT + k] = src[SWGN_IMU_SQRT_INFO + k];
+  }
+  for (int i = 0; i < g->n_gnss; ++i) {
+    const Factor& f = fac[kind_begin[2] + i];
+    int32_t rec[8] = {g->gnss_kind[i], soff(f.blocks[0]), soff(f.blocks[1]), f.blocks.size() > 2 ? soff(f.blocks[2]) : 0,
+                      f.jac_off[0], f.jac_off[1], f.blocks.size() > 2 ? f.jac_off[2] : -1, f.active ? f.res_off : -1};
+    I[I_GNSS].insert(I[I_GNSS].end(), rec, rec + 8);
+    const double* src = g->gnss_data + (size_t)SWGN_GNSS_STRIDE * i;
+    for (int k = 0; k < 9; ++k) Cc[C_GNSS].push_back(src[k]);
+    Cc[C_GNSS].push_back(src[SWGN_GNSS_MEAS]);
+    Cc[C_GNSS].push_back(src[SWGN_GNSS_LAM]);
+    Cc[C_GNSS].push_back(src[SWGN_GNSS_WEIGHT]);
+  }
+  int n_prior_blk = 0;
+  for (int i = 0; i < g->n_prior; ++i) {
+    const Factor& f = fac[kind_begin[3] + i];
+    const int n = g->prior_n[i];
+    int32_t rec[8] = {n, (int32_t)f.blocks.size(), f.active ? f.res_off : -1, n_prior_blk,
+                      (int32_t)Cc[C_PRIOR_J].size(), (int32_t)Cc[C_PRIOR_R0].size(), 0, 0};
+    I[I_PRIOR].insert(I[I_PRIOR].end(), rec, rec + 8);
+    const double* x0 = g->prior_x0 + g->prior_x0_begin[i];
+    int x0o = 0;
+    for (size_t p = 0; p < f.blocks.size(); ++p) {
+      int b = f.blocks[p];
+      int idx = g->prior_blk_idx[g->prior_blk_begin[i] + p];
+      int ls = local_size(g->block_size[b], g->block_manifold[b]);
+      if (idx < 0 || idx + ls > n) return fail(SWGN_ERR_INVALID, "prior block column range outside J0");
+      int32_t br[6] = {soff(b), g->block_size[b], idx, f.jac_off[p], (int32_t)Cc[C_PRIOR_X0].size(), ls};
+      I[I_PRIOR_BLK].insert(I[I_PRIOR_BLK].end(), br, br + 6);
+      for (int k = 0; k < g->block_size[b]; ++k) Cc[C_PRIOR_X0].push_back(x0[x0o + k]);
+      x0o += g->block_size[b];
+      ++n_prior_blk;
+    }
+    const double* J0 = g->prior_J + g->prior_J_begin[i];
+    Cc[C_PRIOR_J].insert(Cc[C_PRIOR_J].end(), J0, J0 + (size_t)n * n);
+    const double* r0 = g->prior_r0 + g->prior_r_begin[i];
+    Cc[C_PRIOR_R0].insert(Cc[C_PRIOR_R0].end(), r0, r0 + n);
+  }
+  for (int i = 0; i < g->n_unit; ++i) {
+    const Factor& f = fac[kind_begin[4] + i];
+    int32_t rec[4] = {soff(f.blocks[0]), f.jac_off[0], f.active ? f.res_off : -1, 0};
+    I[I_UNIT].insert(I[I_UNIT].end(), rec, rec + 4);
+    Cc[C_UNIT].push_back(g->unit_istd[i]);
+  }
+
+  // ---- descriptor
+  WinDesc& d = P->d;
+  d = WinDesc();
+  d.n_state = g->n_state;
+  d.n_cols = n_cols;
+  d.n_ecols = n_ecols;
+  d.n_e = n_e;
+  d.n_f = n_f;
+  d.n_t = n_t;
+  d.n_res = n_res;
+  d.n_rows = n_rows;
+  d.n_cells = n_cells;
+  d.n_chunks = n_chunks;
+  d.n_slots = n_slots;
+  d.n_jac = n_jac;
+  d.ld = (n_f + 1 + 3) & ~3;
+  d.n_proj = g->n_proj;
+  d.n_imu = g->n_imu;
+  d.n_gnss = g->n_gnss;
+  d.n_prior = g->n_prior;
+  d.n_prior_blk = n_prior_blk;
+  d.n_unit = g->n_unit;
+  d.max_buf = max_buf;
+  d.n_einv = n_einv;
+  // tangent size of the trailing parameter_head groups (UpdateSchurHessianOnly's n)
+  d.n_head = 0;
+  if (n_parameter_head > 0) {
+    if (n_parameter_head > n_cols - n_ecols) return fail(SWGN_ERR_INVALID, "n_parameter_head exceeds the retained blocks");
+    for (int c = n_cols - n_parameter_head; c < n_cols; ++c) d.n_head += col_size[c];
+  }
+  P->state.assign(g->state, g->state + g->n_state);
+  int64_t* W = P->wsize;
+  W[W_X] = W[W_XCAND] = W[W_XBEST] = W[W_X0] = align2(g->n_state);
+  W[W_RES] = align2(n_res);
+  W[W_JAC] = align2(n_jac);
+  W[W_DIAG] = W[W_G] = W[W_GHAT] = W[W_GN] = W[W_STEP] = W[W_Y] = W[W_LMD] = align2(n_t);
+  W[W_S] = W[W_SCOPY] = align2((int64_t)n_f * d.ld);
+  W[W_EINV] = align2(n_einv);
+  P->schur_doubles = schur_doubles + n_t + (int64_t)n_f * (n_f + 1) / 2 + n_f + n_e;
+  return SWGN_OK;
+}
+
+}  // namespace swgn

@@ -1,0 +1,28 @@
+// Host-side preprocessing of one window: what Ceres does in TrustRegionPreprocessor::Preprocess
+// on every Solve (CERES/internal/ceres/trust_region_preprocessor.cc:360-393) -- reduced program,
+// ordering, e-block independence check, lexicographic row order, block-sparse structure, Schur
+// chunks -- flattened into the index arrays the kernels consume (device_types.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/swgn.h"
+#include "device_types.h"
+
+namespace swgn {
+
+struct WindowPlan {
+  WinDesc d;                               // counts filled; offsets filled by the batch
+  std::vector<int32_t> iarr[NUM_IARR];
+  std::vector<double> carr[NUM_CARR];
+  int64_t wsize[NUM_WARR];
+  std::vector<double> state;               // initial state (graph layout)
+  // algorithmic traffic of one Schur elimination on the materialised Jacobian, in doubles
+  // (SURVEY.md 8d formula): J blocks at their stored size + residuals + D in, S upper + r + y out
+  int64_t schur_doubles;
+};
+
+// returns SWGN_OK or an error status with *err filled
+swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* out, std::string* err);
+
+}  // namespace swgn
