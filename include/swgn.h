@@ -223,8 +223,18 @@ swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries);
 swgn_status swgn_batch_last_timing(const swgn_batch* b, double* total_ms, double* schur_ms,
                                    int32_t* schur_launches, int32_t* kernel_launches);
 
+/* Algorithmic bytes of one Schur elimination of `window` on the materialised Jacobian (J blocks
+   at their stored size, residuals and D in; upper triangle of S, r and the back-substituted y
+   out): the numerator of the Schur kernel's HBM roofline. */
+int64_t swgn_batch_schur_bytes(const swgn_batch* b, int32_t window);
+
 /* Result read-backs (device -> caller buffer). */
 swgn_status swgn_batch_get_state(swgn_batch* b, int32_t window, double* state);
+/* Whole-batch variants: the states of all windows back to back (window w starts at the sum of
+   graphs[0..w-1]->n_state), moved with one copy. */
+int64_t swgn_batch_states_size(const swgn_batch* b);
+swgn_status swgn_batch_set_states(swgn_batch* b, const double* states);
+swgn_status swgn_batch_get_states(swgn_batch* b, double* states);
 /* ceres::internal::{lhs_out, rhs_out, hs_row}: reduced system of the last Eliminate, row-major
    n x n with only the upper triangle meaningful; S and r may be NULL to query n. */
 swgn_status swgn_batch_get_reduced(swgn_batch* b, int32_t window, double* S, double* r,

@@ -1,0 +1,577 @@
+// C ABI of the solver (include/swgn.h): window planning on the host, pools in HBM, and the tick
+// loop that drives the per-window trust-region state machines (k_tr.cu).  There is no CPU compute
+// path in here: without a CUDA device swgn_batch_create fails with SWGN_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/swgn.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace swgn {
+cudaError_t configure_schur(const DeviceBatch& b);
+cudaError_t configure_chol(const DeviceBatch& b);
+void launch_gather_states(const DeviceBatch& b, double* dst, const int64_t* offs, int to_device, cudaStream_t s);
+}  // namespace swgn
+
+using namespace swgn;
+
+namespace {
+thread_local std::string g_err;
+swgn_status fail(swgn_status st, const std::string& m) {
+  g_err = m;
+  return st;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(SWGN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+}  // namespace
+
+struct swgn_batch {
+  int n = 0, device = 0;
+  swgn_options opt;
+  cudaStream_t stream = nullptr;
+  std::vector<WinDesc> desc;
+  std::vector<int64_t> schur_doubles;
+  std::vector<int64_t> state_off;  // prefix offsets of the packed state staging buffer
+  WinDesc* d_desc = nullptr;
+  int32_t* d_ipool = nullptr;
+  double* d_cpool = nullptr;
+  double* d_wpool = nullptr;
+  TRState* d_state = nullptr;
+  int32_t* d_counters = nullptr;
+  int32_t* h_counters = nullptr;  // pinned
+  double* d_stage = nullptr;      // packed states of all windows
+  int64_t* d_state_off = nullptr;
+  double* h_stage = nullptr;      // pinned
+  size_t ipool_n = 0, cpool_n = 0, wpool_n = 0;
+  DeviceBatch db;
+  std::vector<TRState> h_state;
+  bool has_scopy = false;
+  // timing of the last solve
+  std::vector<cudaEvent_t> ev;  // [0] start, [1] stop, then pairs around every Schur launch
+  double total_ms = 0, schur_ms = 0;
+  int schur_launches = 0, kernel_launches = 0;
+  bool solved = false;
+};
+
+extern "C" {
+
+void swgn_default_options(swgn_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 8;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->dogleg_min_mu = 1e-12;
+  o->is_optimize = 1;
+  o->n_parameter_head = 0;
+  o->device = 0;
+}
+
+const char* swgn_last_error(void) { return g_err.c_str(); }
+const char* swgn_version(void) { return "swgn 0.1 (sm_100a)"; }
+int32_t swgn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void swgn_batch_destroy(swgn_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
+  cudaFree(b->d_desc);
+  cudaFree(b->d_ipool);
+  cudaFree(b->d_cpool);
+  cudaFree(b->d_wpool);
+  cudaFree(b->d_state);
+  cudaFree(b->d_counters);
+  cudaFree(b->d_stage);
+  cudaFree(b->d_state_off);
+  if (b->h_counters) cudaFreeHost(b->h_counters);
+  if (b->h_stage) cudaFreeHost(b->h_stage);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, const swgn_graph* const* graphs,
+                              swgn_batch** out) {
+  if (!options || !graphs || !out || n_windows <= 0) return fail(SWGN_ERR_INVALID, "bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || options->device < 0 || options->device >= ndev)
+    return fail(SWGN_ERR_NO_DEVICE, "no usable CUDA device (the solver has no CPU fallback)");
+  CU(cudaSetDevice(options->device));
+
+  // ---- plan every window (host, structural work only), in parallel
+  std::vector<WindowPlan> plans(n_windows);
+  std::vector<swgn_status> sts(n_windows, SWGN_OK);
+  std::vector<std::string> errs(n_windows);
+  {
+    const int nt = std::max(1, std::min<int>(n_windows / 4, (int)std::thread::hardware_concurrency()));
+    std::atomic<int> next(0);
+    auto work = [&]() {
+      for (;;) {
+        const int w = next.fetch_add(1);
+        if (w >= n_windows) break;
+        sts[w] = build_plan(graphs[w], options->n_parameter_head, &plans[w], &errs[w]);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  for (int w = 0; w < n_windows; ++w)
+    if (sts[w] != SWGN_OK) return fail(sts[w], "window " + std::to_string(w) + ": " + errs[w]);
+
+  swgn_batch* b = new swgn_batch();
+  b->n = n_windows;
+  b->device = options->device;
+  b->opt = *options;
+  b->desc.resize(n_windows);
+  b->schur_doubles.resize(n_windows);
+  b->state_off.resize(n_windows + 1);
+  b->has_scopy = n_windows <= 256;
+  size_t io = 0, co = 0, wo = 0;
+  int max_wbuf = 0, max_nf = 0, max_prior_n = 0;
+  auto al = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
+  int64_t so = 0;
+  for (int w = 0; w < n_windows; ++w) {
+    WindowPlan& p = plans[w];
+    WinDesc& d = p.d;
+    for (int a = 0; a < NUM_IARR; ++a) {
+      d.ioff[a] = (int64_t)io;
+      io = al(io + p.iarr[a].size(), 4);
+    }
+    for (int a = 0; a < NUM_CARR; ++a) {
+      d.coff[a] = (int64_t)co;
+      co = al(co + p.carr[a].size(), 2);
+    }
+    for (int a = 0; a < NUM_WARR; ++a) {
+      d.woff[a] = (int64_t)wo;
+      if (a == W_SCOPY && !b->has_scopy) continue;
+      wo += (size_t)p.wsize[a];  // sizes are even: 16-byte alignment is preserved, JW stays contiguous
+    }
+    b->desc[w] = d;
+    b->schur_doubles[w] = p.schur_doubles;
+    b->state_off[w] = so;
+    so += d.n_state;
+    max_wbuf = std::max(max_wbuf, d.max_wbuf);
+    max_nf = std::max(max_nf, d.n_f);
+    max_prior_n = std::max(max_prior_n, d.max_prior_n);
+    if (options->n_parameter_head > 0 && d.n_f >= 1024) {
+      swgn_batch_destroy(b);
+      return fail(SWGN_ERR_TOO_LARGE, "reduced system has >= 1024 rows with exports requested");
+    }
+  }
+  b->state_off[n_windows] = so;
+  b->ipool_n = io;
+  b->cpool_n = co;
+  b->wpool_n = wo;
+
+  auto bail = [&](cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    swgn_batch_destroy(b);
+    return fail(SWGN_ERR_CUDA, m);
+  };
+#define CB(call)                                  \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) return bail(e_, #call); \
+  } while (0)
+  CB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  CB(cudaMalloc(&b->d_desc, sizeof(WinDesc) * n_windows));
+  CB(cudaMalloc(&b->d_ipool, sizeof(int32_t) * std::max<size_t>(io, 4)));
+  CB(cudaMalloc(&b->d_cpool, sizeof(double) * std::max<size_t>(co, 2)));
+  CB(cudaMalloc(&b->d_wpool, sizeof(double) * std::max<size_t>(wo, 2)));
+  CB(cudaMalloc(&b->d_state, sizeof(TRState) * n_windows));
+  CB(cudaMalloc(&b->d_counters, sizeof(int32_t) * 4));
+  CB(cudaMalloc(&b->d_stage, sizeof(double) * std::max<int64_t>(so, 2)));
+  CB(cudaMalloc(&b->d_state_off, sizeof(int64_t) * (n_windows + 1)));
+  CB(cudaMallocHost(&b->h_counters, sizeof(int32_t) * 4));
+  CB(cudaMallocHost(&b->h_stage, sizeof(double) * std::max<int64_t>(so, 2)));
+  CB(cudaMemsetAsync(b->d_wpool, 0, sizeof(double) * std::max<size_t>(wo, 2), b->stream));
+  CB(cudaMemsetAsync(b->d_state, 0, sizeof(TRState) * n_windows, b->stream));
+  {
+    // pack the pools on the host and upload each with one copy
+    std::vector<int32_t> hi(std::max<size_t>(io, 4), 0);
+    std::vector<double> hc(std::max<size_t>(co, 2), 0.0);
+    for (int w = 0; w < n_windows; ++w) {
+      const WindowPlan& p = plans[w];
+      for (int a = 0; a < NUM_IARR; ++a)
+        if (!p.iarr[a].empty()) std::memcpy(hi.data() + b->desc[w].ioff[a], p.iarr[a].data(), sizeof(int32_t) * p.iarr[a].size());
+      for (int a = 0; a < NUM_CARR; ++a)
+        if (!p.carr[a].empty()) std::memcpy(hc.data() + b->desc[w].coff[a], p.carr[a].data(), sizeof(double) * p.carr[a].size());
+      std::memcpy(b->h_stage + b->state_off[w], p.state.data(), sizeof(double) * p.state.size());
+    }
+    CB(cudaMemcpyAsync(b->d_ipool, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice, b->stream));
+    CB(cudaMemcpyAsync(b->d_cpool, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, b->stream));
+    CB(cudaMemcpyAsync(b->d_desc, b->desc.data(), sizeof(WinDesc) * n_windows, cudaMemcpyHostToDevice, b->stream));
+    CB(cudaMemcpyAsync(b->d_state_off, b->state_off.data(), sizeof(int64_t) * (n_windows + 1), cudaMemcpyHostToDevice, b->stream));
+    CB(cudaMemcpyAsync(b->d_stage, b->h_stage, sizeof(double) * so, cudaMemcpyHostToDevice, b->stream));
+    CB(cudaStreamSynchronize(b->stream));  // hi / hc go out of scope
+  }
+  DeviceBatch& db = b->db;
+  std::memset(&db, 0, sizeof(db));
+  db.n_windows = n_windows;
+  db.desc = b->d_desc;
+  db.ipool = b->d_ipool;
+  db.cpool = b->d_cpool;
+  db.wpool = b->d_wpool;
+  db.state = b->d_state;
+  db.counters = b->d_counters;
+  db.max_wbuf = max_wbuf;
+  db.max_nf = max_nf;
+  db.max_prior_n = max_prior_n;
+  db.keep_copy = 0;
+  SolverParams& P = db.params;
+  P.max_num_iterations = options->max_num_iterations;
+  P.max_num_consecutive_invalid_steps = options->max_num_consecutive_invalid_steps;
+  P.initial_radius = options->initial_trust_region_radius;
+  P.max_radius = options->max_trust_region_radius;
+  P.min_radius = options->min_trust_region_radius;
+  P.min_relative_decrease = options->min_relative_decrease;
+  P.min_lm_diagonal = options->min_lm_diagonal;
+  P.max_lm_diagonal = options->max_lm_diagonal;
+  P.function_tolerance = options->function_tolerance;
+  P.gradient_tolerance = options->gradient_tolerance;
+  P.parameter_tolerance = options->parameter_tolerance;
+  P.min_mu = options->dogleg_min_mu;
+  P.is_optimize = options->is_optimize;
+  P.n_parameter_head = options->n_parameter_head;
+  P.export_mode = (options->n_parameter_head > 0 && !options->is_optimize) ? 1 : 0;
+  CB(configure_schur(db));
+  CB(configure_chol(db));
+  launch_gather_states(db, b->d_stage, b->d_state_off, 1, b->stream);
+  CB(cudaGetLastError());
+  CB(cudaStreamSynchronize(b->stream));
+  b->h_state.resize(n_windows);
+  *out = b;
+  return SWGN_OK;
+#undef CB
+}
+
+int32_t swgn_batch_size(const swgn_batch* b) { return b ? b->n : 0; }
+
+swgn_status swgn_batch_set_state(swgn_batch* b, int32_t w, const double* state) {
+  if (!b || w < 0 || w >= b->n || !state) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  CU(cudaMemcpyAsync(b->d_wpool + d.woff[W_X], state, sizeof(double) * d.n_state, cudaMemcpyHostToDevice, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_state(swgn_batch* b, int32_t w, double* state) {
+  if (!b || w < 0 || w >= b->n || !state) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  CU(cudaMemcpyAsync(state, b->d_wpool + d.woff[W_X], sizeof(double) * d.n_state, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  return SWGN_OK;
+}
+
+int64_t swgn_batch_states_size(const swgn_batch* b) { return b ? b->state_off[b->n] : 0; }
+
+swgn_status swgn_batch_set_states(swgn_batch* b, const double* states) {
+  if (!b || !states) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const int64_t n = b->state_off[b->n];
+  std::memcpy(b->h_stage, states, sizeof(double) * n);
+  CU(cudaMemcpyAsync(b->d_stage, b->h_stage, sizeof(double) * n, cudaMemcpyHostToDevice, b->stream));
+  launch_gather_states(b->db, b->d_stage, b->d_state_off, 1, b->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(b->stream));
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_states(swgn_batch* b, double* states) {
+  if (!b || !states) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const int64_t n = b->state_off[b->n];
+  launch_gather_states(b->db, b->d_stage, b->d_state_off, 0, b->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(b->h_stage, b->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  std::memcpy(states, b->h_stage, sizeof(double) * n);
+  return SWGN_OK;
+}
+
+static cudaEvent_t get_event(swgn_batch* b, size_t i) {
+  while (b->ev.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    b->ev.push_back(e);
+  }
+  return b->ev[i];
+}
+
+swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
+  if (!b) return fail(SWGN_ERR_INVALID, "null batch");
+  CU(cudaSetDevice(b->device));
+  cudaStream_t s = b->stream;
+  const DeviceBatch& db = b->db;
+  const int max_iter = b->opt.max_num_iterations;
+  // every iteration can retry its linear solve while mu < 1 (mu starts at 1e-12, x10 per retry)
+  const int tick_limit = (max_iter + 2) * 16;
+  int launches = 0, n_schur = 0;
+  CU(cudaEventRecord(get_event(b, 0), s));
+  launch_eval(db, EVAL_INIT, RUN_STATE_MACHINE, s);
+  ++launches;
+  b->h_counters[0] = b->h_counters[1] = -1;
+  bool done = false;
+  int tick = 0;
+  for (; tick < tick_limit && !done; ++tick) {
+    const int slot = tick & 1;
+    CU(cudaMemsetAsync(b->d_counters + slot, 0, sizeof(int32_t), s));
+    launch_begin(db, tick, s);
+    ++launches;
+    CU(cudaMemcpyAsync(b->h_counters + slot, b->d_counters + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (tick >= max_iter) {
+      // no window can still be running before tick max_iter unless it converged early; from
+      // here on wait for the count of active windows
+      CU(cudaStreamSynchronize(s));
+      if (b->h_counters[slot] == 0) {
+        done = true;
+        break;
+      }
+    }
+    CU(cudaEventRecord(get_event(b, 2 + 2 * n_schur), s));
+    launch_schur(db, RUN_STATE_MACHINE, s);
+    CU(cudaEventRecord(get_event(b, 3 + 2 * n_schur), s));
+    ++n_schur;
+    launch_chol(db, RUN_STATE_MACHINE, s);
+    launch_backsub(db, RUN_STATE_MACHINE, s);
+    launch_step(db, s);
+    launch_eval(db, EVAL_CANDIDATE, RUN_STATE_MACHINE, s);
+    launch_end(db, s);
+    launch_eval(db, EVAL_ACCEPTED, RUN_STATE_MACHINE, s);
+    launches += 7;
+  }
+  launch_finish(db, s);
+  ++launches;
+  CU(cudaEventRecord(get_event(b, 1), s));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(b->h_state.data(), b->d_state, sizeof(TRState) * b->n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (!done && tick >= tick_limit) return fail(SWGN_ERR_CUDA, "tick limit reached with active windows");
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]));
+  b->total_ms = ms;
+  b->schur_ms = 0;
+  for (int i = 0; i < n_schur; ++i) {
+    CU(cudaEventElapsedTime(&ms, b->ev[2 + 2 * i], b->ev[3 + 2 * i]));
+    b->schur_ms += ms;
+  }
+  b->schur_launches = n_schur;
+  b->kernel_launches = launches;
+  b->solved = true;
+  if (summaries) {
+    for (int w = 0; w < b->n; ++w) {
+      const TRState& t = b->h_state[w];
+      swgn_summary& m = summaries[w];
+      m.initial_cost = t.initial_cost;
+      m.final_cost = t.final_cost;
+      m.fixed_cost = t.fixed_cost;
+      m.num_successful_steps = t.num_successful;
+      m.num_unsuccessful_steps = t.num_unsuccessful;
+      m.num_iterations = t.iteration;
+      m.num_linear_solves = t.num_linear_solves;
+      m.termination_type = t.termination;
+      m.n_e = b->desc[w].n_e;
+      m.n_f = b->desc[w].n_f;
+      m.n_residuals = b->desc[w].n_res;
+    }
+  }
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_last_timing(const swgn_batch* b, double* total_ms, double* schur_ms, int32_t* schur_launches,
+                                   int32_t* kernel_launches) {
+  if (!b || !b->solved) return fail(SWGN_ERR_INVALID, "no solve has run");
+  if (total_ms) *total_ms = b->total_ms;
+  if (schur_ms) *schur_ms = b->schur_ms;
+  if (schur_launches) *schur_launches = b->schur_launches;
+  if (kernel_launches) *kernel_launches = b->kernel_launches;
+  return SWGN_OK;
+}
+
+// algorithmic bytes of one Schur elimination of window w (SURVEY.md 8d formula)
+int64_t swgn_batch_schur_bytes(const swgn_batch* b, int32_t w) {
+  if (!b || w < 0 || w >= b->n) return 0;
+  return 8 * b->schur_doubles[w];
+}
+
+swgn_status swgn_batch_get_reduced(swgn_batch* b, int32_t w, double* S, double* r, int32_t* n) {
+  if (!b || w < 0 || w >= b->n || !n) return fail(SWGN_ERR_INVALID, "bad arguments");
+  const WinDesc& d = b->desc[w];
+  *n = d.n_f;
+  if (!S && !r) return SWGN_OK;
+  CU(cudaSetDevice(b->device));
+  TRState t;
+  CU(cudaMemcpy(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost));
+  int src = -1;
+  if (t.have_reduced) src = W_S;                  // export-mode solve: S was not factorised
+  else if (b->has_scopy && b->db.keep_copy) src = W_SCOPY;  // staged linear solve kept a copy
+  if (src < 0) return fail(SWGN_ERR_INVALID, "no reduced system available: run an export-mode solve (is_optimize = 0) or swgn_batch_linear_solve");
+  std::vector<double> h((size_t)d.n_f * d.ld);
+  CU(cudaMemcpy(h.data(), b->d_wpool + d.woff[src], sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < d.n_f; ++i) {
+    if (S)
+      for (int j = 0; j < d.n_f; ++j) S[(size_t)i * d.n_f + j] = (j >= i) ? h[(size_t)i * d.ld + j] : 0.0;
+    if (r) r[i] = h[(size_t)i * d.ld + d.n_f];
+  }
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_cholesky(swgn_batch* b, int32_t w, double* L, int32_t* n) {
+  if (!b || w < 0 || w >= b->n || !n) return fail(SWGN_ERR_INVALID, "bad arguments");
+  const WinDesc& d = b->desc[w];
+  *n = d.n_f;
+  if (!L) return SWGN_OK;
+  CU(cudaSetDevice(b->device));
+  TRState t;
+  CU(cudaMemcpy(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost));
+  if (!t.have_factor) return fail(SWGN_ERR_INVALID, "no Cholesky factor available (last reduced solve failed or export mode)");
+  std::vector<double> h((size_t)d.n_f * d.ld);
+  CU(cudaMemcpy(h.data(), b->d_wpool + d.woff[W_S], sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < d.n_f; ++i)
+    for (int j = 0; j < d.n_f; ++j) L[(size_t)i * d.n_f + j] = (j <= i) ? h[(size_t)j * d.ld + i] : 0.0;
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t w, int32_t n_tail, double* A) {
+  if (!b || w < 0 || w >= b->n || !A || n_tail <= 0 || n_tail > b->desc[w].n_f) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  TRState t;
+  CU(cudaMemcpy(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost));
+  if (!t.have_factor) return fail(SWGN_ERR_INVALID, "no Cholesky factor available");
+  double* dA = nullptr;
+  CU(cudaMalloc(&dA, sizeof(double) * n_tail * n_tail));
+  launch_tail_information(b->db, w, n_tail, dA, b->stream);
+  cudaError_t e = cudaMemcpyAsync(A, dA, sizeof(double) * n_tail * n_tail, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  cudaFree(dA);
+  CU(e);
+  return SWGN_OK;
+}
+
+// ---- staged entry points ---------------------------------------------------------------------
+swgn_status swgn_batch_evaluate(swgn_batch* b, int32_t w, double* cost, double* residuals, double* gradient) {
+  if (!b || w < 0 || w >= b->n) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  launch_eval(b->db, EVAL_FORCE, w, b->stream);
+  CU(cudaGetLastError());
+  TRState t;
+  CU(cudaMemcpyAsync(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost, b->stream));
+  if (residuals) CU(cudaMemcpyAsync(residuals, b->d_wpool + d.woff[W_RES], sizeof(double) * d.n_res, cudaMemcpyDeviceToHost, b->stream));
+  if (gradient) CU(cudaMemcpyAsync(gradient, b->d_wpool + d.woff[W_G], sizeof(double) * d.n_t, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  if (cost) *cost = t.x_cost;
+  return SWGN_OK;
+}
+
+static swgn_status fetch_i(swgn_batch* b, int w, int arr, size_t n, std::vector<int32_t>* out) {
+  out->resize(n);
+  if (n == 0) return SWGN_OK;
+  CU(cudaMemcpy(out->data(), b->d_ipool + b->desc[w].ioff[arr], sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_columns(swgn_batch* b, int32_t w, int32_t* n_cols, int32_t* block, int32_t* offset, int32_t* size) {
+  if (!b || w < 0 || w >= b->n || !n_cols) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  *n_cols = d.n_cols;
+  std::vector<int32_t> t;
+  swgn_status st;
+  if (block) { if ((st = fetch_i(b, w, I_COL_BLOCK, d.n_cols, &t))) return st; std::copy(t.begin(), t.end(), block); }
+  if (offset) { if ((st = fetch_i(b, w, I_COL_POS, d.n_cols, &t))) return st; std::copy(t.begin(), t.end(), offset); }
+  if (size) { if ((st = fetch_i(b, w, I_COL_SIZE, d.n_cols, &t))) return st; std::copy(t.begin(), t.end(), size); }
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_rows(swgn_batch* b, int32_t w, int32_t* n_rows, int32_t* factor, int32_t* offset) {
+  if (!b || w < 0 || w >= b->n || !n_rows) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  *n_rows = d.n_rows;
+  std::vector<int32_t> t;
+  swgn_status st;
+  if (factor) { if ((st = fetch_i(b, w, I_ROW_FACTOR, d.n_rows, &t))) return st; std::copy(t.begin(), t.end(), factor); }
+  if (offset) { if ((st = fetch_i(b, w, I_ROW_RES, d.n_rows, &t))) return st; std::copy(t.begin(), t.end(), offset); }
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_dense_jacobian(swgn_batch* b, int32_t w, double* J) {
+  if (!b || w < 0 || w >= b->n || !J) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  std::vector<int32_t> row_res, row_nres, row_cell, cell_col, cell_val, col_pos, col_size;
+  swgn_status st;
+  if ((st = fetch_i(b, w, I_ROW_RES, d.n_rows, &row_res))) return st;
+  if ((st = fetch_i(b, w, I_ROW_NRES, d.n_rows, &row_nres))) return st;
+  if ((st = fetch_i(b, w, I_ROW_CELL, d.n_rows + 1, &row_cell))) return st;
+  if ((st = fetch_i(b, w, I_CELL_COL, d.n_cells, &cell_col))) return st;
+  if ((st = fetch_i(b, w, I_CELL_VAL, d.n_cells, &cell_val))) return st;
+  if ((st = fetch_i(b, w, I_COL_POS, d.n_cols, &col_pos))) return st;
+  if ((st = fetch_i(b, w, I_COL_SIZE, d.n_cols, &col_size))) return st;
+  std::vector<double> v(std::max(d.n_jac, 1));
+  CU(cudaMemcpy(v.data(), b->d_wpool + d.woff[W_JAC], sizeof(double) * d.n_jac, cudaMemcpyDeviceToHost));
+  std::fill(J, J + (size_t)d.n_res * d.n_t, 0.0);
+  for (int r = 0; r < d.n_rows; ++r)
+    for (int c = row_cell[r]; c < row_cell[r + 1]; ++c) {
+      const int col = cell_col[c], cs = col_size[col];
+      for (int rr = 0; rr < row_nres[r]; ++rr)
+        for (int k = 0; k < cs; ++k) J[(size_t)(row_res[r] + rr) * d.n_t + col_pos[col] + k] = v[cell_val[c] + rr * cs + k];
+    }
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_linear_solve(swgn_batch* b, int32_t w, const double* D, double* x) {
+  if (!b || w < 0 || w >= b->n || !x) return fail(SWGN_ERR_INVALID, "bad arguments");
+  if (!b->has_scopy) return fail(SWGN_ERR_UNSUPPORTED, "staged linear solve is only available for batches of <= 256 windows");
+  CU(cudaSetDevice(b->device));
+  const WinDesc& d = b->desc[w];
+  cudaStream_t s = b->stream;
+  if (D) CU(cudaMemcpyAsync(b->d_wpool + d.woff[W_LMD], D, sizeof(double) * d.n_t, cudaMemcpyHostToDevice, s));
+  else CU(cudaMemsetAsync(b->d_wpool + d.woff[W_LMD], 0, sizeof(double) * d.n_t, s));
+  DeviceBatch db = b->db;
+  db.keep_copy = 1;
+  db.params.export_mode = 0;
+  b->db.keep_copy = 1;  // get_reduced reads the copy from now on
+  launch_eval(db, EVAL_FORCE, w, s);
+  launch_schur(db, w, s);
+  launch_chol(db, w, s);
+  launch_backsub(db, w, s);
+  CU(cudaGetLastError());
+  TRState t;
+  CU(cudaMemcpyAsync(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(x, b->d_wpool + d.woff[W_Y], sizeof(double) * d.n_t, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (!t.chol_ok) return fail(SWGN_ERR_INVALID, "reduced system is not positive definite");
+  return SWGN_OK;
+}
+
+}  // extern "C"

@@ -1,12 +1,13 @@
 // Plain-old-data descriptors shared by the host planner and the CUDA kernels.
 //
-// HBM layout (one swgn_batch): three pools hold every window back to back,
+// HBM layout (one swgn_batch): three pools hold every window back to back (window-major, so one
+// CTA streams one contiguous region),
 //   ipool : int32  index arrays  (structure; read-only after upload)
 //   cpool : double factor constants (read-only after upload)
 //   wpool : double work arrays (state, residuals, block-sparse Jacobian values, vectors, the
-//           reduced system S | rhs, chunk inverses)
+//           reduced system S | rhs, chunk factors and buffers)
 // and WinDesc[w] carries the per-window counts plus 64-bit offsets of each array inside its pool.
-// All per-window arrays start on 16-byte boundaries so kernels can use 128-bit accesses.
+// All per-window arrays start on 16-byte boundaries so kernels can use 128-bit / bulk accesses.
 #pragma once
 #include <stdint.h>
 
@@ -25,25 +26,40 @@ enum IArr {
   I_ROW_FACTOR,     // [n_rows] program-order index of the residual block (read-backs)
   I_CELL_COL,       // [n_cells]
   I_CELL_VAL,       // [n_cells] offset of the cell's values (row-major n_res x col_size) in W_JAC
-  I_CELL_SLOT,      // [n_cells] slot of the cell in its chunk's E'F buffer, -1 for the e-cell/no chunk
+  I_CELL_SLOT,      // [n_cells] offset of the cell's E'F block inside W_EBUF (absolute within the
+                    //           window's W_EBUF), -1 for the e-cell / rows without e-block
+  I_CELL_FIRST,     // [n_cells] 1: first row of its chunk that touches this slot (store, don't add)
   I_RS_ROW,         // [n_res] row block of every residual scalar
   I_CHUNK_ROW,      // [n_chunks+1] row range of every chunk
   I_CHUNK_ECOL,     // [n_chunks]
   I_CHUNK_SLOT,     // [n_chunks+1] CSR into slots
-  I_CHUNK_INV,      // [n_chunks] offset of (E'E + D^2)^-1 inside W_EINV
+  I_CHUNK_FAC,      // [n_chunks] offset of chol(E'E + D^2) (es x es row-major, lower) in W_EFAC
+  I_CHUNK_G,        // [n_chunks] offset of L^-1 E'b (es) inside W_EBUF
   I_SLOT_COL,       // [n_slots] f column of the slot, ascending inside a chunk
-  I_SLOT_BUF,       // [n_slots] offset of the e x f block inside the chunk buffer
+  I_SLOT_BUF,       // [n_slots] offset of the es x fs block L^-1 E'F inside W_EBUF
+  I_TCHUNK,         // [n_tchunks] chunks with e-size <= 3 (one thread each)
+  I_WCHUNK,         // [n_wchunks] chunks with e-size 4..16 (one warp each)
   I_CSC_PTR,        // [n_cols+1]
   I_CSC_ROW,        // [nnz] row block
   I_CSC_VAL,        // [nnz] value offset
+  I_SCELL,          // [n_scells * 6] reduced-system block cell: ps, qs, S offset (row*ld+col),
+                    //                term_begin, term_end, diag flag (1: p == q, add D^2)
+  I_STERM,          // [n_sterms * 2] packed gather term (see STERM_* below)
+  I_STILE,          // [n_stiles] packed 3x3 tile of a cell: cell << 12 | i0 << 6 | j0
   I_PROJ,           // [n_proj * 8]  state_off[3], jac_off[3], res_off, 0
   I_IMU,            // [n_imu * 12]  state_off[4], jac_off[4], res_off, 0,0,0
   I_GNSS,           // [n_gnss * 8]  kind, state_off[3], jac_off[3], res_off
   I_PRIOR,          // [n_prior * 8] n, n_blk, res_off, blk_begin, J_off, r0_off, 0, 0
-  I_PRIOR_BLK,      // [n_prior_blk * 6] state_off, gsize, idx, jac_off, x0_off, 0
+  I_PRIOR_BLK,      // [n_prior_blk * 6] state_off, gsize, idx, jac_off, x0_off, local size
   I_UNIT,           // [n_unit * 4]  state_off, jac_off, res_off, 0
   NUM_IARR
 };
+
+// Gather term of the reduced system: S_pq (+/-)= A^T B with A (m x ps) at JW[a], B (m x qs) at
+// JW[b], where JW is the concatenation W_JAC | W_EBUF | W_RES of the window.
+//   word0 = a (22 bits) | low 10 bits of m << 22
+//   word1 = b (22 bits) | high 9 bits of m << 22 | sign << 31      (sign 1: subtract)
+enum { STERM_OFF_BITS = 22, STERM_OFF_MASK = (1 << 22) - 1, STERM_MAX_M = (1 << 19) - 1 };
 
 enum CArr {
   C_GLOBALS = 0,  // Pbg[3], gravity[3], proj_sqrt_info[4], cauchy_a, pad -> 12
@@ -62,8 +78,10 @@ enum WArr {
   W_XCAND,   // [n_state] candidate point
   W_XBEST,   // [n_state] lowest-cost point seen (what goes back to the user)
   W_X0,      // [n_state] state at upload (restored when a solve fails)
-  W_RES,     // [n_res]
-  W_JAC,     // [n_jac] block-sparse Jacobian values, cells in row order
+  W_JAC,     // [n_jac] block-sparse Jacobian values, cells in row order      \  these three are
+  W_EBUF,    // [n_ebuf] per chunk: L^-1 E'F slot blocks, then L^-1 E'b        | adjacent: "JW"
+  W_RES,     // [n_res]                                                       /
+  W_MRES,    // [n_res] J * v scratch (Cauchy point, model residuals)
   W_DIAG,    // [n_t] sqrt(clamp(colnorm^2))
   W_G,       // [n_t] J^T r
   W_GHAT,    // [n_t] J^T r / diag
@@ -71,9 +89,10 @@ enum WArr {
   W_STEP,    // [n_t] trust-region step (unscaled)
   W_Y,       // [n_t] linear solve output [y_e ; z]
   W_LMD,     // [n_t] LM diagonal D = diag * sqrt(mu)
-  W_S,       // [n_f * ld] reduced system, row-major upper triangle; column n_f holds the rhs
-  W_SCOPY,   // [n_f * ld] copy of S|rhs before factorisation (exports / tests)
-  W_EINV,    // chunk inverses
+  W_EFAC,    // chunk Cholesky factors
+  W_S,       // [n_f * ld] reduced system, row-major upper triangle; column n_f holds the rhs;
+             //            overwritten by its Cholesky factor U (S = U^T U) and U^-T rhs
+  W_SCOPY,   // [n_f * ld] copy of S|rhs before factorisation (staged test entry point only)
   NUM_WARR
 };
 
@@ -84,9 +103,12 @@ enum { IMU_DEV_BLOCKS = 24, IMU_DEV_SQRT = 70 };
 
 enum FactorKind { K_PROJ = 0, K_IMU = 1, K_GNSS = 2, K_PRIOR = 3, K_UNIT = 4 };
 
+enum { MAX_WARP_E = 16, MAX_COL_SIZE = 63 };
+
 struct WinDesc {
   int32_t n_state, n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_cells, n_chunks, n_slots;
-  int32_t n_jac, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, max_buf, n_einv, n_head;
+  int32_t n_jac, n_ebuf, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, n_efac, n_head;
+  int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_stiles, max_prior_n, max_wbuf, pad0;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];
@@ -109,11 +131,12 @@ struct TRState {
   int32_t termination;         // SWGN_CONVERGENCE / NO_CONVERGENCE / FAILURE
   int32_t last_successful;     // iteration_summary_.step_is_successful of the finished iteration
   int32_t need_solve;          // this iteration still needs a (re)try of the linear solve
-  int32_t solve_ok;            // linear solve of this iteration produced a finite GN step
+  int32_t solve_ok;            // the current Gauss-Newton step W_GN is valid
+  int32_t chol_ok;             // the reduced factorisation of this tick succeeded
   int32_t step_valid;          // model_cost_change > 0
   int32_t accepted;            // step accepted at the end of this iteration
-  int32_t eval_failed;
   int32_t have_factor;         // W_S currently holds a Cholesky factor (lhs_out2 available)
+  int32_t have_reduced;        // W_S currently holds S | rhs of an export-mode eliminate
   int32_t pad;
 };
 
@@ -122,7 +145,7 @@ struct SolverParams {
   double initial_radius, max_radius, min_radius, min_relative_decrease;
   double min_lm_diagonal, max_lm_diagonal;
   double function_tolerance, gradient_tolerance, parameter_tolerance, min_mu;
-  int32_t is_optimize, n_parameter_head, keep_reduced, pad;
+  int32_t is_optimize, n_parameter_head, export_mode, pad;
 };
 
 }  // namespace swgn

@@ -1,0 +1,493 @@
+// K3 + K5: Schur elimination of the first ordering group and back-substitution, one CTA per
+// window.  Replaces SchurEliminator<-1,-1,-1>::Eliminate / BackSubstitute
+// (CERES/internal/ceres/schur_eliminator_impl.h:177-306, 309-375) for the predefined ordering of
+// RVI/swf/swf_gnss.cpp:629-783 (landmarks 3x3, every second speed-bias 9x9, epoch clocks 1x1).
+//
+// Formulation (no atomics, deterministic -- the reference serialises S updates with per-cell
+// mutexes, :552):
+//   phase 1, per chunk c (rows sharing e-block e):   L L' = D_e^2 + sum E'E      (chunk factor)
+//            W_f = L^-1 sum E'F_f  for every f-block of the chunk,  w_g = L^-1 sum E'b
+//   phase 2, per 3x3 tile of every touched block cell (p,q) of S (and of the rhs column): gather
+//            S_pq = [p==q] D_p^2 + sum_rows F_p'F_q - sum_chunks W_p'W_q ,
+//            rhs_p = sum_rows F_p'b - sum_chunks W_p'w_g
+//            from host-built term lists (plan.cpp) and store each element of S exactly once.
+//   back-substitution: y_e = L^-T (w_g - sum_f W_f z_f).
+// (E'E + D^2)^-1 of the reference (InvertPSDMatrix, invert_psd_matrix.h:62-67: LLT-solve-identity)
+// is applied in factored form: buffer' inv buffer = (L^-1 buffer)'(L^-1 buffer).
+#include "dev_common.cuh"
+#include "../../include/swgn.h"
+
+namespace swgn {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ---- phase 1, small e-blocks (1..3): one thread per chunk, everything in registers -----------
+template <int ES>
+__device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const double* lmd) {
+  const int32_t* chunk_row = v.I(I_CHUNK_ROW);
+  const int32_t* row_cell = v.I(I_ROW_CELL);
+  const int32_t* row_res = v.I(I_ROW_RES);
+  const int32_t* row_nres = v.I(I_ROW_NRES);
+  const int32_t* cell_col = v.I(I_CELL_COL);
+  const int32_t* cell_val = v.I(I_CELL_VAL);
+  const int32_t* cell_slot = v.I(I_CELL_SLOT);
+  const int32_t* cell_first = v.I(I_CELL_FIRST);
+  const int32_t* col_size = v.I(I_COL_SIZE);
+  const double* J = v.W(W_JAC);
+  const double* R = v.W(W_RES);
+  double* EB = v.W(W_EBUF);
+  const int ecol = v.I(I_CHUNK_ECOL)[chunk];
+  const int epos = v.I(I_COL_POS)[ecol];
+  const int r0 = chunk_row[chunk], r1 = chunk_row[chunk + 1];
+  double ete[ES][ES], g[ES];
+#pragma unroll
+  for (int i = 0; i < ES; ++i) {
+    g[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < ES; ++j) ete[i][j] = 0.0;
+    const double dd = lmd ? lmd[epos + i] : 0.0;
+    ete[i][i] = dd * dd;
+  }
+  for (int r = r0; r < r1; ++r) {  // ChunkDiagonalBlockAndGradient :444-507
+    const double* E = J + cell_val[row_cell[r]];
+    const double* bb = R + row_res[r];
+    const int nres = row_nres[r];
+    for (int rr = 0; rr < nres; ++rr) {
+      double e[ES];
+#pragma unroll
+      for (int i = 0; i < ES; ++i) e[i] = E[rr * ES + i];
+      const double br = bb[rr];
+#pragma unroll
+      for (int i = 0; i < ES; ++i) {
+        g[i] += e[i] * br;
+#pragma unroll
+        for (int j = i; j < ES; ++j) ete[i][j] += e[i] * e[j];
+      }
+    }
+  }
+  // L L' = ete (lower L, row-major); a non-positive pivot poisons the chunk with NaN so that the
+  // reduced factorisation fails and the caller retries with a larger mu (dogleg_strategy.cc:589)
+  double L[ES][ES];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < ES; ++j) {
+    double dj = ete[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k];
+    if (!(dj > 0.0)) ok = false;
+    dj = sqrt(dj);
+    L[j][j] = dj;
+#pragma unroll
+    for (int i = j + 1; i < ES; ++i) {
+      double s = ete[j][i];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / dj;
+    }
+  }
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < ES; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L[i][j] = nan("");
+  }
+  double* fac = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+#pragma unroll
+  for (int i = 0; i < ES; ++i)
+#pragma unroll
+    for (int j = 0; j < ES; ++j) fac[i * ES + j] = (j <= i) ? L[i][j] : 0.0;
+  {  // w_g = L^-1 g
+    double wg[ES];
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+      double s = g[i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s -= L[i][k] * wg[k];
+      wg[i] = s / L[i][i];
+    }
+    double* gp = EB + v.I(I_CHUNK_G)[chunk];
+#pragma unroll
+    for (int i = 0; i < ES; ++i) gp[i] = wg[i];
+  }
+  // W_f (+)= (L^-1 E_rr') F_rr for every residual row rr of every row block
+  for (int r = r0; r < r1; ++r) {
+    const int c0 = row_cell[r], c1 = row_cell[r + 1];
+    if (c1 - c0 < 2) continue;
+    const double* E = J + cell_val[c0];
+    const int nres = row_nres[r];
+    for (int rr = 0; rr < nres; ++rr) {
+      double vv[ES];
+#pragma unroll
+      for (int i = 0; i < ES; ++i) {
+        double s = E[rr * ES + i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= L[i][k] * vv[k];
+        vv[i] = s / L[i][i];
+      }
+      for (int c = c0 + 1; c < c1; ++c) {
+        const int fs = col_size[cell_col[c]];
+        const double* F = J + cell_val[c] + rr * fs;
+        double* Wf = EB + cell_slot[c];
+        const bool store = cell_first[c] && rr == 0;
+        for (int j = 0; j < fs; ++j) {
+          const double f = F[j];
+#pragma unroll
+          for (int i = 0; i < ES; ++i) {
+            const double t = vv[i] * f;
+            Wf[i * fs + j] = store ? t : Wf[i * fs + j] + t;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- phase 1, larger e-blocks (4..16, the 9-dim speed-bias blocks): one warp per chunk --------
+__device__ void chunk_warp(const Win& v, int chunk, const double* lmd, double* sm /* per-warp scratch */) {
+  const int lane = threadIdx.x & 31;
+  const int32_t* chunk_row = v.I(I_CHUNK_ROW);
+  const int32_t* chunk_slot = v.I(I_CHUNK_SLOT);
+  const int32_t* slot_col = v.I(I_SLOT_COL);
+  const int32_t* slot_buf = v.I(I_SLOT_BUF);
+  const int32_t* row_cell = v.I(I_ROW_CELL);
+  const int32_t* row_res = v.I(I_ROW_RES);
+  const int32_t* row_nres = v.I(I_ROW_NRES);
+  const int32_t* cell_col = v.I(I_CELL_COL);
+  const int32_t* cell_val = v.I(I_CELL_VAL);
+  const int32_t* cell_slot = v.I(I_CELL_SLOT);
+  const int32_t* col_size = v.I(I_COL_SIZE);
+  const double* J = v.W(W_JAC);
+  const double* R = v.W(W_RES);
+  double* EB = v.W(W_EBUF);
+  const int ecol = v.I(I_CHUNK_ECOL)[chunk];
+  const int es = col_size[ecol];
+  const int epos = v.I(I_COL_POS)[ecol];
+  const int s0 = chunk_slot[chunk], s1 = chunk_slot[chunk + 1];
+  const int ebase = (s1 > s0) ? slot_buf[s0] : v.I(I_CHUNK_G)[chunk];
+  const int gofs = v.I(I_CHUNK_G)[chunk];
+  // scratch: ete/L [16][16] then the buffer in the global slot layout (slot blocks es x fs, then g)
+  double* ete = sm;
+  double* buf = sm + MAX_WARP_E * MAX_WARP_E;
+  const int nbuf = gofs + es - ebase;
+  for (int k = lane; k < es * es; k += 32) {
+    const int i = k / es, j = k - i * es;
+    const double dd = (lmd && i == j) ? lmd[epos + i] : 0.0;
+    ete[i * MAX_WARP_E + j] = dd * dd;
+  }
+  for (int k = lane; k < nbuf; k += 32) buf[k] = 0.0;
+  __syncwarp();
+  for (int r = chunk_row[chunk]; r < chunk_row[chunk + 1]; ++r) {
+    const int c0 = row_cell[r], c1 = row_cell[r + 1];
+    const double* E = J + cell_val[c0];
+    const double* bb = R + row_res[r];
+    const int nres = row_nres[r];
+    for (int k = lane; k < es * es; k += 32) {  // E'E
+      const int i = k / es, j = k - i * es;
+      if (j < i) continue;
+      double s = 0.0;
+      for (int rr = 0; rr < nres; ++rr) s += E[rr * es + i] * E[rr * es + j];
+      ete[i * MAX_WARP_E + j] += s;
+    }
+    if (lane < es) {  // E'b
+      double s = 0.0;
+      for (int rr = 0; rr < nres; ++rr) s += E[rr * es + lane] * bb[rr];
+      buf[gofs - ebase + lane] += s;
+    }
+    for (int c = c0 + 1; c < c1; ++c) {  // E'F
+      const int fs = col_size[cell_col[c]];
+      const double* F = J + cell_val[c];
+      double* Bf = buf + (cell_slot[c] - ebase);
+      for (int k = lane; k < es * fs; k += 32) {
+        const int i = k / fs, j = k - i * fs;
+        double s = 0.0;
+        for (int rr = 0; rr < nres; ++rr) s += E[rr * es + i] * F[rr * fs + j];
+        Bf[k] += s;
+      }
+    }
+    __syncwarp();
+  }
+  // Cholesky of ete (upper part filled) -> lower L in place (row-major [i][j], j <= i)
+  bool ok = true;
+  for (int j = 0; j < es; ++j) {
+    double dj = ete[j * MAX_WARP_E + j];
+    for (int k = 0; k < j; ++k) dj -= ete[j * MAX_WARP_E + k] * ete[j * MAX_WARP_E + k];
+    if (!(dj > 0.0)) ok = false;
+    dj = sqrt(dj);
+    __syncwarp();
+    if (lane == 0) ete[j * MAX_WARP_E + j] = dj;
+    const int i = j + 1 + lane;
+    if (i < es) {
+      double s = ete[j * MAX_WARP_E + i];
+      for (int k = 0; k < j; ++k) s -= ete[i * MAX_WARP_E + k] * ete[j * MAX_WARP_E + k];
+      ete[i * MAX_WARP_E + j] = s / dj;
+    }
+    __syncwarp();
+  }
+  if (!ok) {
+    for (int k = lane; k < es * es; k += 32) ete[(k / es) * MAX_WARP_E + (k % es)] = nan("");
+    __syncwarp();
+  }
+  double* fac = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+  for (int k = lane; k < es * es; k += 32) {
+    const int i = k / es, j = k - i * es;
+    fac[k] = (j <= i) ? ete[i * MAX_WARP_E + j] : 0.0;
+  }
+  // forward substitution L^-1 on every column of every slot block and on g, then store
+  for (int s = s0; s <= s1; ++s) {
+    const int fs = (s < s1) ? col_size[slot_col[s]] : 1;
+    const int off = ((s < s1) ? slot_buf[s] : gofs) - ebase;
+    for (int j = lane; j < fs; j += 32) {
+      for (int i = 0; i < es; ++i) {
+        double t = buf[off + i * fs + j];
+        for (int k = 0; k < i; ++k) t -= ete[i * MAX_WARP_E + k] * buf[off + k * fs + j];
+        buf[off + i * fs + j] = t / ete[i * MAX_WARP_E + i];
+      }
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < nbuf; k += 32) EB[ebase + k] = buf[k];
+  __syncwarp();
+}
+
+__device__ __forceinline__ void chunk_dispatch(const Win& v, int chunk, const double* lmd) {
+  const int es = v.I(I_COL_SIZE)[v.I(I_CHUNK_ECOL)[chunk]];
+  if (es == 3) chunk_thread<3>(v, chunk, lmd);
+  else if (es == 1) chunk_thread<1>(v, chunk, lmd);
+  else chunk_thread<2>(v, chunk, lmd);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_schur(DeviceBatch b, int only_window) {
+  __shared__ WinDesc sd;
+  extern __shared__ double dyn[];  // kWarps * max_wbuf doubles
+  const int w = only_window >= 0 ? only_window : blockIdx.x;
+  TRState* st = b.state + w;
+  if (only_window < 0 && !(st->active && st->need_solve)) return;
+  const Win v = load_window(b, w, &sd);
+  const WinDesc& d = sd;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double* lmd = v.W(W_LMD);
+  double* S = v.W(W_S);
+  const int nf = d.n_f, ld = d.ld;
+
+  // phase 0: clear the upper triangle and the rhs column (cells never touched must read as 0)
+  for (int i = wid; i < nf; i += kWarps) {
+    double* row = S + (size_t)i * ld;
+    for (int j = i + lane; j <= nf; j += 32) row[j] = 0.0;
+  }
+  // phase 1: chunk factors and buffers
+  {
+    const int32_t* tch = v.I(I_TCHUNK);
+    for (int k = tid; k < d.n_tchunks; k += kThreads) chunk_dispatch(v, tch[k], lmd);
+    const int32_t* wch = v.I(I_WCHUNK);
+    double* sm = dyn + (size_t)wid * b.max_wbuf;
+    for (int k = wid; k < d.n_wchunks; k += kWarps) chunk_warp(v, wch[k], lmd, sm);
+  }
+  __syncthreads();
+  // phase 2: gather every 3x3 tile of the reduced system
+  {
+    const int32_t* stile = v.I(I_STILE);
+    const int32_t* scell = v.I(I_SCELL);
+    const uint32_t* sterm = reinterpret_cast<const uint32_t*>(v.I(I_STERM));
+    const double* JW = v.W(W_JAC);
+    for (int ti = tid; ti < d.n_stiles; ti += kThreads) {
+      const uint32_t packed = (uint32_t)stile[ti];
+      const int32_t* sc = scell + 6 * (packed >> 12);
+      const int i0 = (packed >> 6) & 63, j0 = packed & 63;
+      const int ps = sc[0], qs = sc[1];
+      const int ni = min(3, ps - i0), nj = min(3, qs - j0);
+      double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int t = sc[3]; t < sc[4]; ++t) {
+        const uint32_t w0 = sterm[2 * t], w1 = sterm[2 * t + 1];
+        const double* A = JW + (w0 & STERM_OFF_MASK) + i0;
+        const double* B = JW + (w1 & STERM_OFF_MASK) + j0;
+        const int m = (int)(w0 >> STERM_OFF_BITS) | (int)(((w1 >> STERM_OFF_BITS) & 0x1ffu) << 10);
+        const double sg = (w1 >> 31) ? -1.0 : 1.0;
+        for (int e = 0; e < m; ++e) {
+          const double a0 = sg * A[0], a1 = ni > 1 ? sg * A[1] : 0.0, a2 = ni > 2 ? sg * A[2] : 0.0;
+          const double b0 = B[0], b1 = nj > 1 ? B[1] : 0.0, b2 = nj > 2 ? B[2] : 0.0;
+          acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
+          acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
+          acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+          A += ps;
+          B += qs;
+        }
+      }
+      const int soff = sc[2];
+      if (sc[5]) {  // diagonal block: + D^2  (schur_eliminator_impl.h:194-215)
+        const int frow = soff / ld;  // first row of the block inside S
+        const double* df = lmd + d.n_e + frow;
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii) {
+          const int jj = i0 + ii - j0;
+          if (ii < ni && jj >= 0 && jj < nj) {
+            const double dd = df[i0 + ii];
+            acc[ii][jj] += dd * dd;
+          }
+        }
+      }
+      double* out = S + soff + (size_t)i0 * ld + j0;
+#pragma unroll
+      for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+          if (ii < ni && jj < nj) out[(size_t)ii * ld + jj] = acc[ii][jj];
+    }
+  }
+  if (b.keep_copy) {
+    __syncthreads();
+    double* SC = v.W(W_SCOPY);
+    for (int k = tid; k < nf * ld; k += kThreads) SC[k] = S[k];
+  }
+  if (tid == 0) {
+    st->num_linear_solves += 1;
+    st->have_factor = 0;
+    st->have_reduced = b.params.export_mode ? 1 : 0;
+    st->chol_ok = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Back-substitution + Gauss-Newton step in the scaled space: gn = -diag .* [y_e ; z]
+// (dogleg_strategy.cc:606).  Also closes the linear-solve attempt of this tick: a failed
+// factorisation or a non-finite step multiplies mu by 10 and leaves need_solve set (:589-595).
+// ---------------------------------------------------------------------------------------------
+template <int ES>
+__device__ __forceinline__ void backsub_thread(const Win& v, int chunk, const double* Y, double* Yout) {
+  const int32_t* chunk_slot = v.I(I_CHUNK_SLOT);
+  const int32_t* slot_col = v.I(I_SLOT_COL);
+  const int32_t* slot_buf = v.I(I_SLOT_BUF);
+  const int32_t* col_size = v.I(I_COL_SIZE);
+  const int32_t* col_pos = v.I(I_COL_POS);
+  const double* EB = v.W(W_EBUF);
+  const double* L = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+  const double* wg = EB + v.I(I_CHUNK_G)[chunk];
+  double t[ES];
+#pragma unroll
+  for (int i = 0; i < ES; ++i) t[i] = wg[i];
+  for (int s = chunk_slot[chunk]; s < chunk_slot[chunk + 1]; ++s) {
+    const int fc = slot_col[s], fs = col_size[fc];
+    const double* z = Y + col_pos[fc];
+    const double* Wf = EB + slot_buf[s];
+    for (int j = 0; j < fs; ++j) {
+      const double zj = z[j];
+#pragma unroll
+      for (int i = 0; i < ES; ++i) t[i] -= Wf[i * fs + j] * zj;
+    }
+  }
+  double y[ES];
+#pragma unroll
+  for (int i = ES - 1; i >= 0; --i) {
+    double s = t[i];
+#pragma unroll
+    for (int k = i + 1; k < ES; ++k) s -= L[k * ES + i] * y[k];
+    y[i] = s / L[i * ES + i];
+  }
+  double* out = Yout + col_pos[v.I(I_CHUNK_ECOL)[chunk]];
+#pragma unroll
+  for (int i = 0; i < ES; ++i) out[i] = y[i];
+}
+
+__device__ void backsub_warp(const Win& v, int chunk, const double* Y, double* Yout) {
+  const int lane = threadIdx.x & 31;
+  const int32_t* chunk_slot = v.I(I_CHUNK_SLOT);
+  const int32_t* slot_col = v.I(I_SLOT_COL);
+  const int32_t* slot_buf = v.I(I_SLOT_BUF);
+  const int32_t* col_size = v.I(I_COL_SIZE);
+  const int32_t* col_pos = v.I(I_COL_POS);
+  const double* EB = v.W(W_EBUF);
+  const int ecol = v.I(I_CHUNK_ECOL)[chunk];
+  const int es = col_size[ecol];
+  const double* L = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+  double t = 0.0;
+  if (lane < es) {
+    t = EB[v.I(I_CHUNK_G)[chunk] + lane];
+    for (int s = chunk_slot[chunk]; s < chunk_slot[chunk + 1]; ++s) {
+      const int fc = slot_col[s], fs = col_size[fc];
+      const double* z = Y + col_pos[fc];
+      const double* Wf = EB + slot_buf[s] + lane * fs;
+      for (int j = 0; j < fs; ++j) t -= Wf[j] * z[j];
+    }
+  }
+  // L' y = t, bottom up
+  double y = 0.0;
+  for (int i = es - 1; i >= 0; --i) {
+    double yi = 0.0;
+    if (lane == i) yi = t / L[i * es + i];
+    yi = __shfl_sync(0xffffffffu, yi, i);
+    if (lane == i) y = yi;
+    if (lane < i) t -= L[i * es + lane] * yi;
+  }
+  if (lane < es) Yout[col_pos[ecol] + lane] = y;
+}
+
+__global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_window) {
+  __shared__ WinDesc sd;
+  const int w = only_window >= 0 ? only_window : blockIdx.x;
+  TRState* st = b.state + w;
+  if (only_window < 0 && !(st->active && st->need_solve)) return;
+  const int tid = threadIdx.x, wid = tid >> 5;
+  if (!b.params.export_mode && !st->chol_ok) {  // LINEAR_SOLVER_FAILURE: retry with mu * 10
+    if (tid == 0) st->mu *= 10.0;
+    return;
+  }
+  const Win v = load_window(b, w, &sd);
+  const WinDesc& d = sd;
+  double* Y = v.W(W_Y);
+  double* GN = v.W(W_GN);
+  const double* DG = v.W(W_DIAG);
+  int bad = 0;
+  if (b.params.export_mode) {
+    // schur_complement_solver.cc:172-188: the reduced system is exported and the solve returns
+    // success with a zero step
+    for (int k = tid; k < d.n_t; k += kThreads) { Y[k] = 0.0; GN[k] = 0.0; }
+  } else {
+    const int32_t* tch = v.I(I_TCHUNK);
+    for (int k = tid; k < d.n_tchunks; k += kThreads) {
+      const int chunk = tch[k];
+      const int es = v.I(I_COL_SIZE)[v.I(I_CHUNK_ECOL)[chunk]];
+      if (es == 3) backsub_thread<3>(v, chunk, Y, Y);
+      else if (es == 1) backsub_thread<1>(v, chunk, Y, Y);
+      else backsub_thread<2>(v, chunk, Y, Y);
+    }
+    const int32_t* wch = v.I(I_WCHUNK);
+    for (int k = wid; k < d.n_wchunks; k += kWarps) backsub_warp(v, wch[k], Y, Y);
+    __syncthreads();
+    for (int k = tid; k < d.n_t; k += kThreads) {
+      const double y = Y[k];
+      if (!finite_d(y)) bad = 1;
+      GN[k] = -DG[k] * y;
+    }
+  }
+  bad = block_any(bad);
+  if (tid == 0 && only_window < 0) {
+    if (bad) {
+      st->mu *= 10.0;  // stays in need_solve: retried in the next tick
+    } else {
+      st->need_solve = 0;
+      st->solve_ok = 1;
+    }
+  }
+}
+
+void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
+  const int grid = only_window >= 0 ? 1 : b.n_windows;
+  const size_t dyn = sizeof(double) * (size_t)kWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  k_schur<<<grid, kThreads, dyn, s>>>(b, only_window);
+}
+void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
+  const int grid = only_window >= 0 ? 1 : b.n_windows;
+  k_backsub<<<grid, kThreads, 0, s>>>(b, only_window);
+}
+
+cudaError_t configure_schur(const DeviceBatch& b) {
+  const size_t dyn = sizeof(double) * (size_t)kWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  if (dyn > 48 * 1024) return cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  return cudaSuccess;
+}
+
+}  // namespace swgn

@@ -1,5 +1,6 @@
-// Launch wrappers of the solver kernels (kernels.cu).  One CTA per window everywhere: windows are
-// the unit of data parallelism, a batch is processed by a grid of n_windows CTAs.
+// Launch wrappers of the solver kernels.  One CTA per window everywhere: windows are the unit of
+// data parallelism, a batch is processed by a grid of n_windows CTAs and every
+// kernel masks windows whose trust-region state machine does not need that stage in this tick.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -14,31 +15,35 @@ struct DeviceBatch {
   const double* cpool;
   double* wpool;
   TRState* state;        // [n_windows]
-  int32_t* counters;     // [4]: 0 = windows still active, 1 = windows needing a solve retry
+  int32_t* counters;     // [2]: windows still active after k_begin (ping-pong by tick parity)
   SolverParams params;
-  int max_buf;           // max over windows of the chunk buffer size (doubles)
+  int max_wbuf;          // max over windows of the warp-chunk scratch (doubles)
   int max_nf;            // max reduced-system size
   int max_prior_n;
+  int keep_copy;         // copy S|rhs to W_SCOPY before factorising (staged test entry point)
 };
 
 enum EvalMode { EVAL_INIT = 0, EVAL_ACCEPTED = 1, EVAL_CANDIDATE = 2, EVAL_FORCE = 3 };
+// stages of the staged (test) entry points bypass the state machine for one window
+enum { RUN_STATE_MACHINE = -1 };
 
-size_t schur_smem_bytes(const DeviceBatch& b, int* chunk_warps);
-size_t chol_smem_bytes(const DeviceBatch& b);
-size_t eval_smem_bytes(const DeviceBatch& b);
 cudaError_t configure_kernels(const DeviceBatch& b);
 
-void launch_init(const DeviceBatch& b, cudaStream_t s);
-void launch_eval(const DeviceBatch& b, int mode, cudaStream_t s);
-void launch_grad(const DeviceBatch& b, int mode, cudaStream_t s);
-void launch_begin(const DeviceBatch& b, cudaStream_t s);
-void launch_schur(const DeviceBatch& b, int force, cudaStream_t s);
-void launch_chol(const DeviceBatch& b, int force, cudaStream_t s);
-void launch_backsub(const DeviceBatch& b, int force, cudaStream_t s);
+void launch_eval(const DeviceBatch& b, int mode, int only_window, cudaStream_t s);
+void launch_begin(const DeviceBatch& b, int tick, cudaStream_t s);
+void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s);
+void launch_chol(const DeviceBatch& b, int only_window, cudaStream_t s);
+void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s);
 void launch_step(const DeviceBatch& b, cudaStream_t s);
 void launch_end(const DeviceBatch& b, cudaStream_t s);
 void launch_finish(const DeviceBatch& b, cudaStream_t s);
-// staged helpers for tests
-void launch_set_lm_diagonal(const DeviceBatch& b, int window, const double* D_dev, cudaStream_t s);
+void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s);
+
+// K7/K8: batched RTKLIB-style lambda() and the LambdaSearch decision (k_lambda.cu)
+void launch_lambda_batch(int n_problems, int m, const int32_t* n_dev, const int64_t* aoff_dev,
+                         const int64_t* qoff_dev, const double* a_dev, const double* Q_dev,
+                         double* F_dev, double* s_dev, int32_t* info_dev, double* work_dev,
+                         const int64_t* woff_dev, cudaStream_t s);
+size_t lambda_work_doubles(int n, int m);
 
 }  // namespace swgn

@@ -3,6 +3,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <map>
 #include <numeric>
 
 namespace swgn {
@@ -215,6 +216,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       I[I_CELL_COL].push_back(c.first);
       I[I_CELL_VAL].push_back(n_jac);
       I[I_CELL_SLOT].push_back(-1);
+      I[I_CELL_FIRST].push_back(0);
       f.jac_off[c.second] = n_jac;
       n_jac += f.nres * col_size[c.first];
       schur_doubles += (int64_t)f.nres * col_size[c.first];
@@ -224,8 +226,13 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     n_res += f.nres;
   }
   const int n_cells = (int)I[I_CELL_COL].size();
-  // chunks (schur_eliminator_impl.h:118-156)
-  int n_einv = 0, max_buf = 1;
+  // chunks (schur_eliminator_impl.h:118-156).  Per chunk the kernels keep
+  //   L  = chol(E'E + D_e^2)           (W_EFAC, es x es)
+  //   Wf = L^-1 E'F_f  per f-block     (W_EBUF, es x fs row-major, one "slot" per f-block)
+  //   wg = L^-1 E'b                    (W_EBUF, es)
+  // so that S_pq -= Wp' Wq, rhs_p -= Wp' wg and y_e = L^-T (wg - sum_f Wf z_f).
+  int n_efac = 0, n_ebuf = 0, max_wbuf = 0;
+  std::vector<std::vector<std::pair<int, int>>> col_slots(n_cols);  // f col -> (chunk, slot offset)
   {
     int r = 0;
     I[I_CHUNK_ROW].push_back(0);
@@ -243,23 +250,39 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       std::sort(fcols.begin(), fcols.end());
       fcols.erase(std::unique(fcols.begin(), fcols.end()), fcols.end());
       const int es = col_size[e];
-      int slot0 = (int)I[I_SLOT_COL].size(), buf = 0;
-      for (int fc : fcols) {
-        I[I_SLOT_COL].push_back(fc);
-        I[I_SLOT_BUF].push_back(buf);
-        buf += es * col_size[fc];
+      if (es > MAX_WARP_E) return fail(SWGN_ERR_UNSUPPORTED, "eliminated parameter block larger than 16 tangent dimensions");
+      const int chunk = (int)I[I_CHUNK_ECOL].size();
+      std::vector<int> slot_off(fcols.size());
+      int ncol = 0;
+      for (size_t k = 0; k < fcols.size(); ++k) {
+        slot_off[k] = n_ebuf;
+        I[I_SLOT_COL].push_back(fcols[k]);
+        I[I_SLOT_BUF].push_back(n_ebuf);
+        col_slots[fcols[k]].push_back({chunk, n_ebuf});
+        n_ebuf += es * col_size[fcols[k]];
+        ncol += col_size[fcols[k]];
       }
-      max_buf = std::max(max_buf, buf);
+      I[I_CHUNK_G].push_back(n_ebuf);
+      n_ebuf += es;
+      n_ebuf = (int)align2(n_ebuf);
+      std::vector<char> seen(fcols.size(), 0);
       for (int rr = r; rr < r1; ++rr)
         for (int c = I[I_ROW_CELL][rr] + 1; c < I[I_ROW_CELL][rr + 1]; ++c) {
           int fc = I[I_CELL_COL][c];
           int s = (int)(std::lower_bound(fcols.begin(), fcols.end(), fc) - fcols.begin());
-          I[I_CELL_SLOT][c] = s;
+          I[I_CELL_SLOT][c] = slot_off[s];
+          I[I_CELL_FIRST][c] = seen[s] ? 0 : 1;
+          seen[s] = 1;
         }
-      (void)slot0;
+      if (es <= 3) {
+        I[I_TCHUNK].push_back(chunk);
+      } else {
+        I[I_WCHUNK].push_back(chunk);
+        max_wbuf = std::max(max_wbuf, MAX_WARP_E * MAX_WARP_E + es * (ncol + 1));
+      }
       I[I_CHUNK_ECOL].push_back(e);
-      I[I_CHUNK_INV].push_back(n_einv);
-      n_einv += (int)align2(es * es);
+      I[I_CHUNK_FAC].push_back(n_efac);
+      n_efac += (int)align2(es * es);
       I[I_CHUNK_ROW].push_back(r1);
       I[I_CHUNK_SLOT].push_back((int32_t)I[I_SLOT_COL].size());
       r = r1;
@@ -268,6 +291,76 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   const int n_chunks = (int)I[I_CHUNK_ECOL].size();
   if (n_chunks != n_ecols) return fail(SWGN_ERR_INVALID, "chunk detection does not match the eliminated blocks");
   const int n_slots = (int)I[I_SLOT_COL].size();
+  const int n_jac_al = (int)align2(n_jac), n_ebuf_al = (int)align2(n_ebuf);
+  if ((int64_t)n_jac_al + n_ebuf_al + n_res >= (1 << STERM_OFF_BITS))
+    return fail(SWGN_ERR_TOO_LARGE, "window Jacobian too large for the packed gather terms");
+
+  // ---- gather tables of the reduced system (device Schur kernel, phase 2).  Every touched block
+  // cell (p, q), p <= q, of S -- plus the rhs as block column n_fcols -- lists its terms:
+  //   + F_p' F_q of every row holding both cells      (schur_eliminator_impl.h:667-716, 569-661)
+  //   - Wp' Wq   of every chunk holding both slots    (:514-563)
+  // rhs: + F_p' b per row (all rows: b - E inv g expands to this minus the chunk term) and
+  //      - Wp' wg per chunk (:381-422).
+  const int ld = (n_f + 1 + 3) & ~3;
+  {
+    const int n_fcols = n_cols - n_ecols;
+    auto fpos = [&](int c) { return col_pos[c] - n_e; };  // row/col of the f-block inside S
+    struct T {
+      uint32_t a, b, m, sign;
+    };
+    std::map<std::pair<int, int>, std::vector<T>> cells;  // (p, q) with q == n_cols for the rhs
+    for (int c = n_ecols; c < n_cols; ++c) cells[{c, c}];  // diagonal cells always exist (D^2)
+    const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
+    for (int r = 0; r < n_rows; ++r) {
+      const int nres = I[I_ROW_NRES][r];
+      if (nres > STERM_MAX_M) return fail(SWGN_ERR_TOO_LARGE, "residual block too large");
+      for (int c1 = I[I_ROW_CELL][r]; c1 < I[I_ROW_CELL][r + 1]; ++c1) {
+        const int p = I[I_CELL_COL][c1];
+        if (p < n_ecols) continue;
+        for (int c2 = c1; c2 < I[I_ROW_CELL][r + 1]; ++c2)
+          cells[{p, I[I_CELL_COL][c2]}].push_back({(uint32_t)I[I_CELL_VAL][c1], (uint32_t)I[I_CELL_VAL][c2], (uint32_t)nres, 0u});
+        cells[{p, n_cols}].push_back({(uint32_t)I[I_CELL_VAL][c1], res_base + (uint32_t)I[I_ROW_RES][r], (uint32_t)nres, 0u});
+      }
+    }
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const uint32_t es = (uint32_t)col_size[I[I_CHUNK_ECOL][ch]];
+      for (int s1 = I[I_CHUNK_SLOT][ch]; s1 < I[I_CHUNK_SLOT][ch + 1]; ++s1) {
+        const int p = I[I_SLOT_COL][s1];
+        for (int s2 = s1; s2 < I[I_CHUNK_SLOT][ch + 1]; ++s2)
+          cells[{p, I[I_SLOT_COL][s2]}].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_SLOT_BUF][s2]), es, 1u});
+        cells[{p, n_cols}].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_CHUNK_G][ch]), es, 1u});
+      }
+    }
+    // longest term lists first: neighbouring lanes get similar trip counts
+    std::vector<std::pair<std::pair<int, int>, const std::vector<T>*>> order;
+    for (auto& kv : cells) order.push_back({kv.first, &kv.second});
+    std::stable_sort(order.begin(), order.end(), [](const auto& x, const auto& y) {
+      size_t wx = 0, wy = 0;
+      for (const T& t : *x.second) wx += t.m;
+      for (const T& t : *y.second) wy += t.m;
+      return wx > wy;
+    });
+    if (order.size() >= (1u << 20)) return fail(SWGN_ERR_TOO_LARGE, "too many reduced-system cells");
+    for (size_t ci = 0; ci < order.size(); ++ci) {
+      const int p = order[ci].first.first, q = order[ci].first.second;
+      const int ps = col_size[p], qs = (q == n_cols) ? 1 : col_size[q];
+      if (ps > MAX_COL_SIZE || qs > MAX_COL_SIZE) return fail(SWGN_ERR_UNSUPPORTED, "parameter block larger than 63 tangent dimensions");
+      const int scol = (q == n_cols) ? n_f : fpos(q);
+      const int32_t rec[6] = {ps, qs, fpos(p) * ld + scol, (int32_t)(I[I_STERM].size() / 2),
+                              (int32_t)(I[I_STERM].size() / 2 + order[ci].second->size()), p == q ? 1 : 0};
+      I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 6);
+      for (const T& t : *order[ci].second) {
+        I[I_STERM].push_back((int32_t)(t.a | ((t.m & 1023u) << STERM_OFF_BITS)));
+        I[I_STERM].push_back((int32_t)(t.b | ((t.m >> 10) << STERM_OFF_BITS) | (t.sign << 31)));
+      }
+      for (int i0 = 0; i0 < ps; i0 += 3)
+        for (int j0 = 0; j0 < qs; j0 += 3) {
+          if (p == q && j0 + 2 < i0) continue;  // tile strictly below the diagonal
+          I[I_STILE].push_back((int32_t)((ci << 12) | (i0 << 6) | j0));
+        }
+    }
+    (void)n_fcols;
+  }
   // CSC
   {
     std::vector<int> cnt(n_cols + 1, 0);
@@ -383,15 +476,23 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_chunks = n_chunks;
   d.n_slots = n_slots;
   d.n_jac = n_jac;
-  d.ld = (n_f + 1 + 3) & ~3;
+  d.n_ebuf = n_ebuf;
+  d.ld = ld;
   d.n_proj = g->n_proj;
   d.n_imu = g->n_imu;
   d.n_gnss = g->n_gnss;
   d.n_prior = g->n_prior;
   d.n_prior_blk = n_prior_blk;
   d.n_unit = g->n_unit;
-  d.max_buf = max_buf;
-  d.n_einv = n_einv;
+  d.n_efac = n_efac;
+  d.n_tchunks = (int)I[I_TCHUNK].size();
+  d.n_wchunks = (int)I[I_WCHUNK].size();
+  d.n_scells = (int)(I[I_SCELL].size() / 6);
+  d.n_sterms = (int)(I[I_STERM].size() / 2);
+  d.n_stiles = (int)I[I_STILE].size();
+  d.max_wbuf = max_wbuf;
+  d.max_prior_n = 0;
+  for (int i = 0; i < g->n_prior; ++i) d.max_prior_n = std::max(d.max_prior_n, g->prior_n[i]);
   // tangent size of the trailing parameter_head groups (UpdateSchurHessianOnly's n)
   d.n_head = 0;
   if (n_parameter_head > 0) {
@@ -401,11 +502,12 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   P->state.assign(g->state, g->state + g->n_state);
   int64_t* W = P->wsize;
   W[W_X] = W[W_XCAND] = W[W_XBEST] = W[W_X0] = align2(g->n_state);
-  W[W_RES] = align2(n_res);
-  W[W_JAC] = align2(n_jac);
+  W[W_JAC] = n_jac_al;
+  W[W_EBUF] = n_ebuf_al;
+  W[W_RES] = W[W_MRES] = align2(n_res);
   W[W_DIAG] = W[W_G] = W[W_GHAT] = W[W_GN] = W[W_STEP] = W[W_Y] = W[W_LMD] = align2(n_t);
+  W[W_EFAC] = align2(n_efac);
   W[W_S] = W[W_SCOPY] = align2((int64_t)n_f * d.ld);
-  W[W_EINV] = align2(n_einv);
   P->schur_doubles = schur_doubles + n_t + (int64_t)n_f * (n_f + 1) / 2 + n_f + n_e;
   return SWGN_OK;
 }

@@ -177,6 +177,12 @@ def lib():
         L.swgn_batch_solve.argtypes = [C.c_void_p, P(Summary)]
         L.swgn_batch_last_timing.argtypes = [C.c_void_p, P(f64), P(f64), P(i32), P(i32)]
         L.swgn_batch_get_state.argtypes = [C.c_void_p, i32, P(f64)]
+        L.swgn_batch_schur_bytes.restype = i64
+        L.swgn_batch_schur_bytes.argtypes = [C.c_void_p, i32]
+        L.swgn_batch_states_size.restype = i64
+        L.swgn_batch_states_size.argtypes = [C.c_void_p]
+        L.swgn_batch_set_states.argtypes = [C.c_void_p, P(f64)]
+        L.swgn_batch_get_states.argtypes = [C.c_void_p, P(f64)]
         L.swgn_batch_get_reduced.argtypes = [C.c_void_p, i32, P(f64), P(f64), P(i32)]
         L.swgn_batch_get_cholesky.argtypes = [C.c_void_p, i32, P(f64), P(i32)]
         L.swgn_batch_get_tail_information.argtypes = [C.c_void_p, i32, i32, P(f64)]
@@ -235,6 +241,23 @@ class Batch:
         x = np.zeros(n_state)
         _check(lib().swgn_batch_get_state(self.h, w, _dp(x)), "swgn_batch_get_state")
         return x
+
+    def schur_bytes(self, w):
+        return lib().swgn_batch_schur_bytes(self.h, w)
+
+    def states_size(self):
+        return lib().swgn_batch_states_size(self.h)
+
+    def get_states(self, out=None):
+        if out is None:
+            out = np.zeros(self.states_size())
+        _check(lib().swgn_batch_get_states(self.h, _dp(out)), "swgn_batch_get_states")
+        return out
+
+    def set_states(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.size == self.states_size()
+        _check(lib().swgn_batch_set_states(self.h, _dp(x)), "swgn_batch_set_states")
 
     def get_reduced(self, w):
         n = i32()

@@ -1,0 +1,148 @@
+"""Pins the oracle's Schur eliminate / reduced solve / back-substitute on the reference's own
+known-answer fixtures: CERES/internal/ceres/linear_least_squares_problems.cc problems 2, 3, 4
+(block-sparse definitions :283-515,517-625; hand-computed A'A, S, r, S\\r, A\\b in the comment at
+:135-178) and the dense-reference construction of schur_eliminator_test.cc:83-183 (tolerance
+1e-14 relative at :202-222)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_fixtures():
+    with open(os.path.join(HERE, "golden", "ceres_llsq_problems.json")) as f:
+        return json.load(f)
+
+
+def run_raw(p, use_D):
+    col_sizes = np.array(p["col_sizes"], np.int32)
+    row_sizes = np.array(p["row_sizes"], np.int32)
+    row_ptr = np.array(p["row_ptr"], np.int32)
+    cell_col = np.array(p["cell_col"], np.int32)
+    values = np.array(p["values"], np.float64)
+    b = np.array(p["b"], np.float64)
+    D = np.array(p["D"], np.float64)
+    ne = p["num_eliminate_blocks"]
+    ncols = int(col_sizes.sum())
+    nf = int(col_sizes[ne:].sum())
+    lhs = np.zeros((nf, nf))
+    rhs = np.zeros(nf)
+    x = np.zeros(ncols)
+    L = ob.oracle()
+    st = L.oracle_schur_raw(len(col_sizes), ob._ip(col_sizes), len(row_sizes), ob._ip(row_sizes),
+                            ob._ip(row_ptr), ob._ip(cell_col), ob._dp(values), ob._dp(b),
+                            ob._dp(D) if use_D else None, ne, ob._dp(lhs), ob._dp(rhs), ob._dp(x))
+    return st, lhs, rhs, x
+
+
+def dense(p):
+    col_sizes = p["col_sizes"]
+    pos = np.concatenate([[0], np.cumsum(col_sizes)])
+    nrows = sum(p["row_sizes"])
+    A = np.zeros((nrows, pos[-1]))
+    v = 0
+    r0 = 0
+    for i, rs in enumerate(p["row_sizes"]):
+        for k in range(p["row_ptr"][i], p["row_ptr"][i + 1]):
+            c = p["cell_col"][k]
+            cs = col_sizes[c]
+            A[r0:r0 + rs, pos[c]:pos[c] + cs] = np.array(p["values"][v:v + rs * cs]).reshape(rs, cs)
+            v += rs * cs
+        r0 += rs
+    return A
+
+
+def schur_reference(p, use_D):
+    """schur_eliminator_test.cc:83-130: J = [A; diag(D)], H = J'J, g = J'[b;0],
+    S = R - Q' P^-1 Q, r = g_f - Q' P^-1 g_e, solution by dense solve."""
+    A = dense(p)
+    n = A.shape[1]
+    ne = sum(p["col_sizes"][:p["num_eliminate_blocks"]])
+    J = np.vstack([A, np.diag(p["D"])]) if use_D else A
+    f = np.concatenate([p["b"], np.zeros(n)]) if use_D else np.array(p["b"], float)
+    H = J.T @ J
+    g = J.T @ f
+    P, Q, R = H[:ne, :ne], H[:ne, ne:], H[ne:, ne:]
+    S = R - Q.T @ np.linalg.solve(P, Q)
+    r = g[ne:] - Q.T @ np.linalg.solve(P, g[:ne])
+    x = np.linalg.solve(H, g)
+    return S, r, x
+
+
+def test_problem2_hand_computed_comment_values():
+    """The numbers printed in the reference's comment (D = 0)."""
+    p = load_fixtures()["problem2"]
+    st, lhs, rhs, x = run_raw(p, use_D=False)
+    assert st == 0
+    S = np.triu(lhs) + np.triu(lhs, 1).T
+    g = p["golden"]
+    np.testing.assert_allclose(S, np.array(g["S"]), atol=6e-5)
+    np.testing.assert_allclose(rhs, np.array(g["r"]), atol=6e-5)
+    np.testing.assert_allclose(x[2:], np.array(g["S_solve_r"]), atol=6e-5)
+    np.testing.assert_allclose(x, np.array(g["A_solve_b"]), atol=6e-5)
+    A = dense(p)
+    np.testing.assert_allclose(A.T @ A, np.array(g["AtA"]), atol=0)
+    np.testing.assert_allclose(A.T @ np.array(p["b"]), np.array(g["c"]), atol=0)
+
+
+@pytest.mark.parametrize("name", ["problem2", "problem3", "problem4"])
+@pytest.mark.parametrize("use_D", [True, False])
+def test_schur_against_dense_reference(name, use_D):
+    p = load_fixtures()[name]
+    if name == "problem4" and not use_D:
+        pytest.skip("rank deficient without the diagonal (reference comment :533-534)")
+    st, lhs, rhs, x = run_raw(p, use_D)
+    assert st == 0
+    S_ref, r_ref, x_ref = schur_reference(p, use_D)
+    nf = lhs.shape[0]
+    if nf:
+        S = np.triu(lhs) + np.triu(lhs, 1).T
+        # relative 1e-14 like schur_eliminator_test.cc:202-222
+        assert np.linalg.norm(S - S_ref) / np.linalg.norm(S_ref) < 1e-14
+        assert np.linalg.norm(rhs - r_ref) / np.linalg.norm(r_ref) < 1e-14
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-13
+
+
+def test_random_block_sparse_against_dense_reference():
+    """Same check on random block-sparse systems with the e-block sizes the window uses
+    (1, 3, 9) and mixed row sizes, cf. BlockSparseMatrix::CreateRandomMatrix users."""
+    rng = np.random.default_rng(7)
+    for trial in range(5):
+        e_sizes = list(rng.choice([1, 3, 9], size=6))
+        f_sizes = list(rng.choice([1, 6, 9], size=5))
+        col_sizes = e_sizes + f_sizes
+        ne = len(e_sizes)
+        row_sizes, row_ptr, cell_col, values = [], [0], [], []
+        for e in range(ne):
+            for _ in range(int(rng.integers(2, 5))):
+                rs = int(rng.choice([1, 2, 15]))
+                fs = sorted(rng.choice(len(f_sizes), size=int(rng.integers(0, 4)), replace=False))
+                cells = [e] + [ne + int(f) for f in fs]
+                row_sizes.append(rs)
+                for c in cells:
+                    cell_col.append(c)
+                    values += list(rng.normal(size=rs * col_sizes[c]))
+                row_ptr.append(len(cell_col))
+        for _ in range(3):  # rows without e-block
+            rs = int(rng.choice([1, 4]))
+            fs = sorted(rng.choice(len(f_sizes), size=2, replace=False))
+            row_sizes.append(rs)
+            for f in fs:
+                cell_col.append(ne + int(f))
+                values += list(rng.normal(size=rs * col_sizes[ne + int(f)]))
+            row_ptr.append(len(cell_col))
+        p = dict(col_sizes=[int(c) for c in col_sizes], row_sizes=row_sizes, row_ptr=row_ptr,
+                 cell_col=cell_col, values=values, b=list(rng.normal(size=sum(row_sizes))),
+                 D=list(rng.uniform(0.5, 2.0, size=sum(col_sizes))), num_eliminate_blocks=ne)
+        st, lhs, rhs, x = run_raw(p, True)
+        assert st == 0
+        S_ref, r_ref, x_ref = schur_reference(p, True)
+        S = np.triu(lhs) + np.triu(lhs, 1).T
+        assert np.linalg.norm(S - S_ref) / np.linalg.norm(S_ref) < 1e-13
+        assert np.linalg.norm(rhs - r_ref) / np.linalg.norm(r_ref) < 1e-12
+        assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-11
