@@ -200,6 +200,8 @@ typedef struct swgn_batch swgn_batch;   /* opaque: n independent windows on one 
 
 void swgn_default_options(swgn_options* o);
 const char* swgn_last_error(void);
+const char* swgn_lambda_last_error(void);   /* CUDA error text of the last swgn_lambda_batch /
+                                               swgn_ambiguity_fix failure on this thread */
 const char* swgn_version(void);
 int32_t swgn_device_count(void);
 
@@ -208,10 +210,22 @@ int32_t swgn_device_count(void);
 swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows,
                               const swgn_graph* const* graphs, swgn_batch** out);
 void swgn_batch_destroy(swgn_batch* b);
+/* Host-only: run the preprocessing of one window without touching a device and report
+   info[0..11] = n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_chunks, n_jac, n_scells,
+   n_sterms, n_stiles; info[12..13] = algorithmic Schur bytes (low / high 32 bits).  Returns the
+   same status codes swgn_batch_create would (SWGN_ERR_ORDERING, ...). */
+swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info14);
 int32_t swgn_batch_size(const swgn_batch* b);
 
 /* Re-upload initial states only (structure unchanged): state_w has graphs[w]->n_state doubles. */
 swgn_status swgn_batch_set_state(swgn_batch* b, int32_t window, const double* state);
+
+/* Same structure, new inputs (one frame later in a replayed sequence): re-packs the factor
+   constants (measurements, pre-integration terms, priors) and initial states of all windows from
+   `graphs` and uploads them; fails with SWGN_ERR_INVALID when a graph's structure differs from the
+   one the batch was created with.  bytes_h2d (may be NULL) receives the bytes copied. */
+swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* graphs,
+                                     int64_t* bytes_h2d);
 
 /* The whole trust-region solve = ceres::Solve with DENSE_SCHUR + DOGLEG
    (CERES trust_region_minimizer.cc:67-134).  summaries may be NULL, else n_windows entries.

@@ -54,6 +54,7 @@ struct swgn_batch {
   double* d_stage = nullptr;      // packed states of all windows
   int64_t* d_state_off = nullptr;
   double* h_stage = nullptr;      // pinned
+  double* h_cpool = nullptr;      // pinned staging of the factor constants (update_inputs)
   size_t ipool_n = 0, cpool_n = 0, wpool_n = 0;
   DeviceBatch db;
   std::vector<TRState> h_state;
@@ -109,6 +110,7 @@ void swgn_batch_destroy(swgn_batch* b) {
   cudaFree(b->d_state_off);
   if (b->h_counters) cudaFreeHost(b->h_counters);
   if (b->h_stage) cudaFreeHost(b->h_stage);
+  if (b->h_cpool) cudaFreeHost(b->h_cpool);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -271,6 +273,24 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
 #undef CB
 }
 
+// Host-only planning probe: runs the preprocessing of one window (no device needed) and reports
+// info[0..11] = n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_chunks, n_jac, n_scells, n_sterms,
+// n_stiles; info[12..13] = algorithmic Schur bytes (low, high 32 bits).
+swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info) {
+  if (!g || !info) return fail(SWGN_ERR_INVALID, "bad arguments");
+  WindowPlan p;
+  std::string err;
+  swgn_status st = build_plan(g, n_parameter_head, &p, &err);
+  if (st != SWGN_OK) return fail(st, err);
+  const WinDesc& d = p.d;
+  const int32_t v[12] = {d.n_cols, d.n_ecols, d.n_e, d.n_f, d.n_t, d.n_res, d.n_rows, d.n_chunks, d.n_jac, d.n_scells, d.n_sterms, d.n_stiles};
+  std::memcpy(info, v, sizeof(v));
+  const int64_t bytes = 8 * p.schur_doubles;
+  info[12] = (int32_t)(bytes & 0xffffffff);
+  info[13] = (int32_t)(bytes >> 32);
+  return SWGN_OK;
+}
+
 int32_t swgn_batch_size(const swgn_batch* b) { return b ? b->n : 0; }
 
 swgn_status swgn_batch_set_state(swgn_batch* b, int32_t w, const double* state) {
@@ -288,6 +308,53 @@ swgn_status swgn_batch_get_state(swgn_batch* b, int32_t w, double* state) {
   const WinDesc& d = b->desc[w];
   CU(cudaMemcpyAsync(state, b->d_wpool + d.woff[W_X], sizeof(double) * d.n_state, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
+  return SWGN_OK;
+}
+
+// New measurements and initial states on an unchanged structure (the replayed-sequence case):
+// repack the factor constants and states of every window from the caller's graphs and upload them
+// with two copies from pinned staging.  bytes_h2d receives the bytes moved.
+swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* graphs, int64_t* bytes_h2d) {
+  if (!b || !graphs) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  if (!b->h_cpool) CU(cudaMallocHost(&b->h_cpool, sizeof(double) * std::max<size_t>(b->cpool_n, 2)));
+  std::atomic<int> next(0), bad(0);
+  auto work = [&]() {
+    for (;;) {
+      const int w = next.fetch_add(1);
+      if (w >= b->n) break;
+      const swgn_graph* g = graphs[w];
+      const WinDesc& d = b->desc[w];
+      int64_t sizes[NUM_CARR];
+      constant_sizes(g, sizes);
+      bool ok = g->n_state == d.n_state && g->n_proj == d.n_proj && g->n_imu == d.n_imu && g->n_gnss == d.n_gnss &&
+                g->n_prior == d.n_prior && g->n_unit == d.n_unit;
+      for (int a = 0; ok && a + 1 < NUM_CARR; ++a) ok = d.coff[a] + sizes[a] <= d.coff[a + 1];
+      if (!ok) {
+        bad.store(1);
+        continue;
+      }
+      double* ptr[NUM_CARR];
+      for (int a = 0; a < NUM_CARR; ++a) ptr[a] = b->h_cpool + d.coff[a];
+      pack_constants(g, ptr);
+      std::memcpy(b->h_stage + b->state_off[w], g->state, sizeof(double) * d.n_state);
+    }
+  };
+  {
+    const int nt = std::max(1, std::min<int>(b->n / 16, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  if (bad.load()) return fail(SWGN_ERR_INVALID, "graph structure differs from the one the batch was created with");
+  const int64_t ns = b->state_off[b->n];
+  CU(cudaMemcpyAsync(b->d_cpool, b->h_cpool, sizeof(double) * b->cpool_n, cudaMemcpyHostToDevice, b->stream));
+  CU(cudaMemcpyAsync(b->d_stage, b->h_stage, sizeof(double) * ns, cudaMemcpyHostToDevice, b->stream));
+  launch_gather_states(b->db, b->d_stage, b->d_state_off, 1, b->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(b->stream));
+  if (bytes_h2d) *bytes_h2d = (int64_t)(sizeof(double) * (b->cpool_n + (size_t)ns));
   return SWGN_OK;
 }
 

@@ -3,6 +3,8 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <climits>
+#include <cstring>
 #include <map>
 #include <numeric>
 
@@ -23,6 +25,76 @@ inline int local_size(int size, int manifold) { return manifold == SWGN_MANIFOLD
 inline int64_t align2(int64_t x) { return (x + 1) & ~int64_t(1); }
 
 }  // namespace
+
+void constant_sizes(const swgn_graph* g, int64_t sizes[NUM_CARR]) {
+  sizes[C_GLOBALS] = 12;
+  sizes[C_PROJ_UV] = 2 * (int64_t)g->n_proj;
+  sizes[C_IMU] = (int64_t)IMU_DEV_STRIDE * g->n_imu;
+  sizes[C_GNSS] = (int64_t)GNSS_DEV_STRIDE * g->n_gnss;
+  int64_t nj = 0, nr = 0, nx = 0;
+  for (int i = 0; i < g->n_prior; ++i) {
+    nj += (int64_t)g->prior_n[i] * g->prior_n[i];
+    nr += g->prior_n[i];
+    for (int k = g->prior_blk_begin[i]; k < g->prior_blk_begin[i + 1]; ++k) nx += g->block_size[g->prior_blocks[k]];
+  }
+  sizes[C_PRIOR_J] = nj;
+  sizes[C_PRIOR_R0] = nr;
+  sizes[C_PRIOR_X0] = nx;
+  sizes[C_UNIT] = g->n_unit;
+}
+
+// Factor constants in the device layout (device_types.h CArr); dst[a] has constant_sizes()[a] room.
+void pack_constants(const swgn_graph* g, double* const dst[NUM_CARR]) {
+  {
+    double* c = dst[C_GLOBALS];
+    for (int k = 0; k < 3; ++k) {
+      c[k] = g->Pbg[k];
+      c[3 + k] = g->gravity[k];
+    }
+    for (int k = 0; k < 4; ++k) c[6 + k] = g->proj_sqrt_info[k];
+    c[10] = g->proj_cauchy_a;
+    c[11] = 0.0;
+  }
+  if (g->n_proj) std::memcpy(dst[C_PROJ_UV], g->proj_uv, sizeof(double) * 2 * (size_t)g->n_proj);
+  for (int i = 0; i < g->n_imu; ++i) {
+    const double* src = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
+    double* d = dst[C_IMU] + (size_t)IMU_DEV_STRIDE * i;
+    for (int k = 0; k < 24; ++k) d[k] = src[k];
+    const double* J = src + SWGN_IMU_JACOBIAN;
+    static const int blk[5][2] = {{0, 9}, {0, 12}, {3, 12}, {6, 9}, {6, 12}};  // dp_dba dp_dbg dq_dbg dv_dba dv_dbg
+    for (int bI = 0; bI < 5; ++bI)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) d[IMU_DEV_BLOCKS + bI * 9 + r * 3 + c] = J[(blk[bI][0] + r) * 15 + blk[bI][1] + c];
+    d[69] = 0.0;
+    for (int k = 0; k < 225; ++k) d[IMU_DEV_SQRT + k] = src[SWGN_IMU_SQRT_INFO + k];
+    d[295] = 0.0;
+  }
+  for (int i = 0; i < g->n_gnss; ++i) {
+    const double* src = g->gnss_data + (size_t)SWGN_GNSS_STRIDE * i;
+    double* d = dst[C_GNSS] + (size_t)GNSS_DEV_STRIDE * i;
+    for (int k = 0; k < 9; ++k) d[k] = src[k];
+    d[9] = src[SWGN_GNSS_MEAS];
+    d[10] = src[SWGN_GNSS_LAM];
+    d[11] = src[SWGN_GNSS_WEIGHT];
+  }
+  int64_t oJ = 0, oR = 0, oX = 0;
+  for (int i = 0; i < g->n_prior; ++i) {
+    const int n = g->prior_n[i];
+    std::memcpy(dst[C_PRIOR_J] + oJ, g->prior_J + g->prior_J_begin[i], sizeof(double) * (size_t)n * n);
+    std::memcpy(dst[C_PRIOR_R0] + oR, g->prior_r0 + g->prior_r_begin[i], sizeof(double) * n);
+    const double* x0 = g->prior_x0 + g->prior_x0_begin[i];
+    int x0o = 0;
+    for (int k = g->prior_blk_begin[i]; k < g->prior_blk_begin[i + 1]; ++k) {
+      const int bs = g->block_size[g->prior_blocks[k]];
+      for (int q = 0; q < bs; ++q) dst[C_PRIOR_X0][oX + q] = x0[x0o + q];
+      oX += bs;
+      x0o += bs;
+    }
+    oJ += (int64_t)n * n;
+    oR += n;
+  }
+  for (int i = 0; i < g->n_unit; ++i) dst[C_UNIT][i] = g->unit_istd[i];
+}
 
 swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P, std::string* err) {
   auto fail = [&](swgn_status st, const char* m) {
@@ -194,7 +266,6 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   // ---- cells, Jacobian value offsets, chunks, slots
   std::vector<int32_t>*I = P->iarr;
   for (int a = 0; a < NUM_IARR; ++a) I[a].clear();
-  for (int a = 0; a < NUM_CARR; ++a) P->carr[a].clear();
   int n_res = 0, n_jac = 0;
   int64_t schur_doubles = 0;
   I[I_ROW_CELL].push_back(0);
@@ -387,78 +458,64 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     for (int k = 0; k < col_size[c]; ++k) I[I_TCOL].push_back(c);
   }
 
-  // ---- factor tables + constants (kind-major storage order)
-  std::vector<double>* Cc = P->carr;
-  Cc[C_GLOBALS] = {g->Pbg[0], g->Pbg[1], g->Pbg[2], g->gravity[0], g->gravity[1], g->gravity[2],
-                   g->proj_sqrt_info[0], g->proj_sqrt_info[1], g->proj_sqrt_info[2], g->proj_sqrt_info[3],
-                   g->proj_cauchy_a, 0.0};
+  // ---- factor tables (kind-major storage order); constants are packed by pack_constants()
   auto soff = [&](int b) { return g->block_offset[b]; };
   for (int i = 0; i < g->n_proj; ++i) {
     const Factor& f = fac[kind_begin[0] + i];
     int32_t rec[8] = {soff(f.blocks[0]), soff(f.blocks[1]), soff(f.blocks[2]), f.jac_off[0], f.jac_off[1],
                       f.jac_off[2], f.active ? f.res_off : -1, 0};
     I[I_PROJ].insert(I[I_PROJ].end(), rec, rec + 8);
-    Cc[C_PROJ_UV].push_back(g->proj_uv[2 * i]);
-    Cc[C_PROJ_UV].push_back(g->proj_uv[2 * i + 1]);
   }
   for (int i = 0; i < g->n_imu; ++i) {
     const Factor& f = fac[kind_begin[1] + i];
     int32_t rec[12] = {soff(f.blocks[0]), soff(f.blocks[1]), soff(f.blocks[2]), soff(f.blocks[3]),
                        f.jac_off[0], f.jac_off[1], f.jac_off[2], f.jac_off[3], f.active ? f.res_off : -1, 0, 0, 0};
     I[I_IMU].insert(I[I_IMU].end(), rec, rec + 12);
-    const double* src = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
-    size_t o = Cc[C_IMU].size();
-    Cc[C_IMU].resize(o + IMU_DEV_STRIDE, 0.0);
-    double* dst = Cc[C_IMU].data() + o;
-    for (int k = 0; k < 24; ++k) dst[k] = src[k];
-    const double* J = src + SWGN_IMU_JACOBIAN;
-    static const int blk[5][2] = {{0, 9}, {0, 12}, {3, 12}, {6, 9}, {6, 12}};  // dp_dba dp_dbg dq_dbg dv_dba dv_dbg
-    for (int bI = 0; bI < 5; ++bI)
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) dst[IMU_DEV_BLOCKS + bI * 9 + r * 3 + c] = J[(blk[bI][0] + r) * 15 + blk[bI][1] + c];
-    for (int k = 0; k < 225; ++k) dst[IMU_DEV_SQRT + k] = src[SWGN_IMU_SQRT_INFO + k];
   }
   for (int i = 0; i < g->n_gnss; ++i) {
     const Factor& f = fac[kind_begin[2] + i];
     int32_t rec[8] = {g->gnss_kind[i], soff(f.blocks[0]), soff(f.blocks[1]), f.blocks.size() > 2 ? soff(f.blocks[2]) : 0,
                       f.jac_off[0], f.jac_off[1], f.blocks.size() > 2 ? f.jac_off[2] : -1, f.active ? f.res_off : -1};
     I[I_GNSS].insert(I[I_GNSS].end(), rec, rec + 8);
-    const double* src = g->gnss_data + (size_t)SWGN_GNSS_STRIDE * i;
-    for (int k = 0; k < 9; ++k) Cc[C_GNSS].push_back(src[k]);
-    Cc[C_GNSS].push_back(src[SWGN_GNSS_MEAS]);
-    Cc[C_GNSS].push_back(src[SWGN_GNSS_LAM]);
-    Cc[C_GNSS].push_back(src[SWGN_GNSS_WEIGHT]);
   }
   int n_prior_blk = 0;
-  for (int i = 0; i < g->n_prior; ++i) {
-    const Factor& f = fac[kind_begin[3] + i];
-    const int n = g->prior_n[i];
-    int32_t rec[8] = {n, (int32_t)f.blocks.size(), f.active ? f.res_off : -1, n_prior_blk,
-                      (int32_t)Cc[C_PRIOR_J].size(), (int32_t)Cc[C_PRIOR_R0].size(), 0, 0};
-    I[I_PRIOR].insert(I[I_PRIOR].end(), rec, rec + 8);
-    const double* x0 = g->prior_x0 + g->prior_x0_begin[i];
-    int x0o = 0;
-    for (size_t p = 0; p < f.blocks.size(); ++p) {
-      int b = f.blocks[p];
-      int idx = g->prior_blk_idx[g->prior_blk_begin[i] + p];
-      int ls = local_size(g->block_size[b], g->block_manifold[b]);
-      if (idx < 0 || idx + ls > n) return fail(SWGN_ERR_INVALID, "prior block column range outside J0");
-      int32_t br[6] = {soff(b), g->block_size[b], idx, f.jac_off[p], (int32_t)Cc[C_PRIOR_X0].size(), ls};
-      I[I_PRIOR_BLK].insert(I[I_PRIOR_BLK].end(), br, br + 6);
-      for (int k = 0; k < g->block_size[b]; ++k) Cc[C_PRIOR_X0].push_back(x0[x0o + k]);
-      x0o += g->block_size[b];
-      ++n_prior_blk;
+  {
+    int64_t oJ = 0, oR = 0, oX = 0;
+    for (int i = 0; i < g->n_prior; ++i) {
+      const Factor& f = fac[kind_begin[3] + i];
+      const int n = g->prior_n[i];
+      if (n <= 0) return fail(SWGN_ERR_INVALID, "prior with no rows");
+      int32_t rec[8] = {n, (int32_t)f.blocks.size(), f.active ? f.res_off : -1, n_prior_blk, (int32_t)oJ, (int32_t)oR, 0, 0};
+      I[I_PRIOR].insert(I[I_PRIOR].end(), rec, rec + 8);
+      for (size_t p = 0; p < f.blocks.size(); ++p) {
+        int b = f.blocks[p];
+        int idx = g->prior_blk_idx[g->prior_blk_begin[i] + p];
+        int ls = local_size(g->block_size[b], g->block_manifold[b]);
+        if (idx < 0 || idx + ls > n) return fail(SWGN_ERR_INVALID, "prior block column range outside J0");
+        int32_t br[6] = {soff(b), g->block_size[b], idx, f.jac_off[p], (int32_t)oX, ls};
+        I[I_PRIOR_BLK].insert(I[I_PRIOR_BLK].end(), br, br + 6);
+        oX += g->block_size[b];
+        ++n_prior_blk;
+      }
+      oJ += (int64_t)n * n;
+      oR += n;
+      if (oJ > INT32_MAX) return fail(SWGN_ERR_TOO_LARGE, "prior Jacobians too large");
     }
-    const double* J0 = g->prior_J + g->prior_J_begin[i];
-    Cc[C_PRIOR_J].insert(Cc[C_PRIOR_J].end(), J0, J0 + (size_t)n * n);
-    const double* r0 = g->prior_r0 + g->prior_r_begin[i];
-    Cc[C_PRIOR_R0].insert(Cc[C_PRIOR_R0].end(), r0, r0 + n);
   }
   for (int i = 0; i < g->n_unit; ++i) {
     const Factor& f = fac[kind_begin[4] + i];
     int32_t rec[4] = {soff(f.blocks[0]), f.jac_off[0], f.active ? f.res_off : -1, 0};
     I[I_UNIT].insert(I[I_UNIT].end(), rec, rec + 4);
-    Cc[C_UNIT].push_back(g->unit_istd[i]);
+  }
+  {
+    int64_t sizes[NUM_CARR];
+    constant_sizes(g, sizes);
+    double* ptr[NUM_CARR];
+    for (int a = 0; a < NUM_CARR; ++a) {
+      P->carr[a].assign((size_t)sizes[a], 0.0);
+      ptr[a] = P->carr[a].data();
+    }
+    pack_constants(g, ptr);
   }
 
   // ---- descriptor

@@ -22,6 +22,11 @@ struct WindowPlan {
   int64_t schur_doubles;
 };
 
+// sizes (doubles) and packing of the factor constants in device layout; used at plan time and by
+// swgn_batch_update_inputs (same structure, new measurements)
+void constant_sizes(const swgn_graph* g, int64_t sizes[NUM_CARR]);
+void pack_constants(const swgn_graph* g, double* const dst[NUM_CARR]);
+
 // returns SWGN_OK or an error status with *err filled
 swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* out, std::string* err);
 

@@ -172,9 +172,11 @@ def lib():
         L.swgn_default_options.argtypes = [P(Options)]
         L.swgn_batch_create.argtypes = [P(Options), i32, P(P(Graph)), P(C.c_void_p)]
         L.swgn_batch_destroy.argtypes = [C.c_void_p]
+        L.swgn_plan_probe.argtypes = [P(Graph), i32, P(i32)]
         L.swgn_batch_size.argtypes = [C.c_void_p]
         L.swgn_batch_set_state.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_solve.argtypes = [C.c_void_p, P(Summary)]
+        L.swgn_batch_update_inputs.argtypes = [C.c_void_p, P(P(Graph)), P(i64)]
         L.swgn_batch_last_timing.argtypes = [C.c_void_p, P(f64), P(f64), P(i32), P(i32)]
         L.swgn_batch_get_state.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_schur_bytes.restype = i64
@@ -198,6 +200,17 @@ def lib():
     return _lib
 
 
+def plan_probe(graph_p, n_parameter_head=0):
+    """Host-only preprocessing of one window; returns (status, dict)."""
+    info = (i32 * 14)()
+    st = lib().swgn_plan_probe(graph_p, n_parameter_head, info)
+    keys = ["n_cols", "n_ecols", "n_e", "n_f", "n_t", "n_res", "n_rows", "n_chunks", "n_jac",
+            "n_scells", "n_sterms", "n_stiles"]
+    d = {k: info[i] for i, k in enumerate(keys)}
+    d["schur_bytes"] = (info[12] & 0xffffffff) | (info[13] << 32)
+    return st, d
+
+
 def default_options():
     o = Options()
     lib().swgn_default_options(C.byref(o))
@@ -219,10 +232,18 @@ class Batch:
         self.h = C.c_void_p()
         self.n = n
         self.options = options
+        self._graphs = arr
         _check(L.swgn_batch_create(C.byref(options), n, arr, C.byref(self.h)), "swgn_batch_create")
 
-    def solve(self):
-        sm = (Summary * self.n)()
+    def update_inputs(self, graph_ptrs=None):
+        """Re-upload factor constants and initial states (same structure); returns H2D bytes."""
+        arr = self._graphs if graph_ptrs is None else (P(Graph) * self.n)(*graph_ptrs)
+        nb = i64()
+        _check(lib().swgn_batch_update_inputs(self.h, arr, C.byref(nb)), "swgn_batch_update_inputs")
+        return nb.value
+
+    def solve(self, summaries=None):
+        sm = summaries if summaries is not None else (Summary * self.n)()
         _check(lib().swgn_batch_solve(self.h, sm), "swgn_batch_solve")
         return sm
 

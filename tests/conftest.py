@@ -13,13 +13,12 @@ sys.path.insert(0, os.path.join(ROOT, "rtk-visual-inertial-navigation_b200"))
 sys.path.insert(0, ROOT)
 
 
+# Build the test infrastructure (oracle) and the product libraries before collection: test modules
+# bind the libraries at import time.  Incremental (mtime based), a no-op when everything is fresh.
+import __graft_entry__ as _ge  # noqa: E402
+
+_ge.build_if_needed()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    """Build the test infrastructure (oracle) and the product libraries once per session."""
-    import __graft_entry__ as ge
-    ge.build_if_needed()
-    yield

@@ -1,0 +1,82 @@
+"""The C-ABI library loads, exports every symbol include/swgn.h declares, fails loudly without a
+device, and its host-side planner agrees with the oracle's preprocessing (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import swgn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "swgn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(swgn_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(os.path.join(ROOT, "rtk-visual-inertial-navigation_b200", "libswgn.so"))
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), n
+    assert swgn.lib().swgn_version().decode().startswith("swgn")
+
+
+def test_default_options_are_the_reference_settings():
+    o = swgn.default_options()
+    assert o.max_num_iterations == 8 and o.max_num_consecutive_invalid_steps == 5
+    assert o.initial_trust_region_radius == 1e4 and o.dogleg_min_mu == 1e-12
+    assert o.function_tolerance == 1e-6 and o.gradient_tolerance == 1e-10 and o.parameter_tolerance == 1e-8
+    assert o.min_lm_diagonal == 1e-6 and o.max_lm_diagonal == 1e32 and o.is_optimize == 1
+
+
+@pytest.mark.parametrize("which,wid", [(1, 0), (2, 0), (2, 7)])
+def test_planner_matches_oracle_preprocessing(which, wid):
+    w = swgn.SynthWindow(which, wid)
+    st, d = swgn.plan_probe(w.graph_p, w.options().n_parameter_head)
+    assert st == 0
+    o = ob.OracleSolver(w.graph_p, w.options())
+    assert d["n_cols"] == o.n_col_blocks and d["n_ecols"] == o.n_e_blocks
+    assert d["n_e"] == o.n_e and d["n_f"] == o.n_f and d["n_t"] == o.n_cols
+    assert d["n_res"] == o.n_res and d["n_rows"] == o.n_row_blocks and d["n_chunks"] == o.n_e_blocks
+    # SURVEY.md 8d byte formula, recomputed independently from the graph
+    g = w.graph
+    kinds = [g.gnss_kind[i] for i in range(g.n_gnss)]
+    n_cp, n_pr, n_dop = kinds.count(2), kinds.count(3), kinds.count(4)
+    npri = g.prior_n[0]
+    n_black = g.n_unit  # 1 x (1 + 1) each
+    doubles = (g.n_proj * (2 * 3 + 2 * 6 + 2) + g.n_imu * 15 * (6 + 9 + 6 + 9 + 1) + n_cp * (6 + 1 + 1 + 1) +
+               n_pr * (6 + 1 + 1) + n_dop * (9 + 1 + 6 + 1) + npri * (npri + 1) + 2 * n_black + o.n_cols +
+               o.n_f * (o.n_f + 1) // 2 + o.n_f + o.n_e)
+    assert d["schur_bytes"] == 8 * doubles
+
+
+def test_planner_rejects_dependent_first_group_and_missing_ordering():
+    w = swgn.SynthWindow(1, 0)
+    g = w.graph
+    groups = np.ctypeslib.as_array(g.block_group, shape=(g.n_blocks,))
+    saved = groups.copy()
+    try:
+        groups[0] = 0
+        st, _ = swgn.plan_probe(w.graph_p)
+        assert st == 4  # SWGN_ERR_ORDERING
+        assert b"independent" in swgn.lib().swgn_last_error()
+        groups[:] = saved
+        groups[1] = -1
+        st, _ = swgn.plan_probe(w.graph_p)
+        assert st == 4
+    finally:
+        groups[:] = saved
+
+
+@pytest.mark.skipif(swgn.lib().swgn_device_count() > 0, reason="a CUDA device is present")
+def test_create_fails_loudly_without_a_device():
+    w = swgn.SynthWindow(1, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        swgn.Batch([w.graph_p], w.options())

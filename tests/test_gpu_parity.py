@@ -1,0 +1,335 @@
+"""Parity of the CUDA path (through the C ABI of include/swgn.h) against the CPU oracle and the
+reference's golden fixtures.  Tolerances: the reference is not bit-reproducible with itself
+(pointer-ordered chunks, mutex-ordered S updates: SURVEY.md 7 'parity definition'), so floating
+point stages are compared at stated fp64 tolerances; structure, iteration counts and the integer
+ambiguity decision are compared exactly."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import swgn
+from linear_graph import LinearGraph
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# stated fp64 tolerances
+TOL_RES = 1e-11      # residual vector, relative 2-norm
+TOL_JAC = 1e-12      # Jacobian, relative Frobenius norm
+TOL_S = 1e-12        # reduced system
+TOL_STATE = 1e-6     # state vector after the full solve: max |dx| / max(1, |x|)
+TOL_COST = 1e-6      # final cost, relative
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def state_err(x, xo):
+    return float(np.max(np.abs(x - xo) / np.maximum(1.0, np.abs(xo))))
+
+
+@pytest.mark.parametrize("which,wid", [(1, 0), (1, 5), (2, 0), (2, 1), (2, 9)])
+def test_structure_and_evaluation(which, wid):
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    b = swgn.Batch([w.graph_p], opt)
+    assert all(np.array_equal(x, y) for x, y in zip(b.columns(0), o.columns()))
+    assert all(np.array_equal(x, y) for x, y in zip(b.rows(0), o.rows()))
+    cost, r, g = b.evaluate(0, o.n_res, o.n_cols)
+    ocost, orr, og, oJ = o.evaluate()
+    J = b.dense_jacobian(0, o.n_res, o.n_cols)
+    assert abs(cost - ocost) <= 1e-12 * ocost
+    assert rel(r, orr) < TOL_RES
+    assert rel(J, oJ) < TOL_JAC
+    assert rel(g, og) < 1e-11
+    b.close()
+
+
+@pytest.mark.parametrize("which,wid", [(1, 0), (2, 0), (2, 4)])
+def test_linear_solve_stage(which, wid):
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    b = swgn.Batch([w.graph_p], opt)
+    rng = np.random.default_rng(wid)
+    D = rng.uniform(0.5, 1.5, o.n_cols) * 1e-2
+    x = b.linear_solve(0, D, o.n_cols)
+    st, ox, oS, orhs = o.linear_solve(D)
+    assert st == 0
+    S, rhs = b.get_reduced(0)
+    assert rel(np.triu(S), np.triu(oS)) < TOL_S
+    assert rel(rhs, orhs) < 1e-9
+    assert rel(x, ox) < 1e-6
+    # size-independent property: x solves the damped normal equations of the SAME linearisation
+    _, r, g, J = o.evaluate()
+    lhs = J.T @ (J @ x) + D * D * x
+    assert rel(lhs, g) < 1e-7
+    b.close()
+
+
+@pytest.mark.parametrize("which,wid", [(1, 0), (1, 3), (2, 0), (2, 2), (2, 11)])
+def test_full_solve_matches_oracle(which, wid):
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, osm = o.minimize()
+    assert st == 0
+    assert sm.num_iterations == osm.num_iterations
+    assert sm.num_successful_steps == osm.num_successful_steps
+    assert sm.num_unsuccessful_steps == osm.num_unsuccessful_steps
+    assert sm.termination_type == osm.termination_type
+    assert sm.num_linear_solves == osm.num_linear_solves
+    assert (sm.n_e, sm.n_f, sm.n_residuals) == (osm.n_e, osm.n_f, osm.n_residuals)
+    assert abs(sm.initial_cost - osm.initial_cost) <= 1e-11 * osm.initial_cost
+    assert abs(sm.final_cost - osm.final_cost) <= TOL_COST * osm.final_cost
+    assert state_err(x, o.state()) < TOL_STATE
+    b.close()
+
+
+def test_converged_solve_and_early_termination():
+    """More iterations than needed: function tolerance stops both paths at the same iteration."""
+    w = swgn.SynthWindow(1, 2)
+    opt = w.options()
+    opt.max_num_iterations = 40
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, osm = o.minimize()
+    assert osm.termination_type == 0 and sm.termination_type == 0
+    assert sm.num_iterations == osm.num_iterations < 40
+    assert state_err(b.get_state(0, w.n_state), o.state()) < TOL_STATE
+    b.close()
+
+
+def test_golden_ceres_problems_through_the_abi():
+    """CERES linear_least_squares_problems.cc problems 2 and 4 (hand-computed S, r, S\\r, A\\b)."""
+    with open(os.path.join(HERE, "golden", "ceres_llsq_problems.json")) as f:
+        fx = json.load(f)
+    opt = swgn.default_options()
+    # problem 2, D = 0: the numbers of the reference's comment (:135-178)
+    p = fx["problem2"]
+    lg = LinearGraph(p)
+    b = swgn.Batch([lg.graph_p], opt)
+    x = b.linear_solve(0, None, lg.n_cols)
+    S, r = b.get_reduced(0)
+    g = p["golden"]
+    Sfull = np.triu(S) + np.triu(S, 1).T
+    np.testing.assert_allclose(Sfull, np.array(g["S"]), atol=6e-5)
+    r_doc = np.array(g["r"])
+    r_doc[2] = 4.0323  # typo in the reference's comment, see test_oracle_golden.py
+    np.testing.assert_allclose(r, r_doc, atol=6e-5)
+    np.testing.assert_allclose(x, np.array(g["A_solve_b"]), atol=6e-5)
+    b.close()
+    # problems 2 and 4 with their D against the dense construction of schur_eliminator_test.cc
+    for name in ("problem2", "problem4"):
+        p = fx[name]
+        lg = LinearGraph(p)
+        b = swgn.Batch([lg.graph_p], opt)
+        D = np.array(p["D"], float)
+        x = b.linear_solve(0, D, lg.n_cols)
+        S, r = b.get_reduced(0)
+        from test_oracle_golden import schur_reference
+        S_ref, r_ref, x_ref = schur_reference(p, True)
+        Sfull = np.triu(S) + np.triu(S, 1).T
+        assert rel(Sfull, S_ref) < 1e-14
+        assert rel(r, r_ref) < 1e-14
+        assert rel(x, x_ref) < 1e-13
+        b.close()
+
+
+def test_export_mode():
+    """is_optimize = 0 with a parameter head: one evaluation + one Eliminate, S and r exported,
+    the state left untouched (CERES schur_complement_solver.cc:172-188)."""
+    w = swgn.SynthWindow(2, 1)
+    opt = w.options()
+    opt.is_optimize = 0
+    opt.max_num_iterations = 1
+    b = swgn.Batch([w.graph_p], opt)
+    x0 = b.get_state(0, w.n_state)
+    sm = b.solve()[0]
+    assert np.array_equal(b.get_state(0, w.n_state), x0)
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, osm = o.minimize()
+    assert (sm.num_iterations, sm.num_successful_steps, sm.num_unsuccessful_steps, sm.termination_type) == \
+        (osm.num_iterations, osm.num_successful_steps, osm.num_unsuccessful_steps, osm.termination_type)
+    S, r = b.get_reduced(0)
+    n, oS, orr, _ = o.exports()
+    assert S.shape[0] == n
+    assert rel(np.triu(S), np.triu(oS)) < TOL_S
+    assert rel(r, orr) < 1e-9
+    b.close()
+
+
+def test_cholesky_export_and_tail_information():
+    w = swgn.SynthWindow(2, 2)
+    opt = w.options()
+    b = swgn.Batch([w.graph_p], opt)
+    b.solve()
+    o = ob.OracleSolver(w.graph_p, opt)
+    o.minimize()
+    n, oS, orr, Lo = o.exports()
+    Lg = b.get_cholesky(0)
+    assert np.all(np.triu(Lg, 1) == 0)
+    assert rel(Lg, Lo) < 1e-8
+    A = b.tail_information(0, w.n_amb)
+    Ao = ob.tail_information(Lo, w.n_amb)
+    assert rel(A, Ao) < 1e-8
+    assert np.allclose(A, A.T, rtol=0, atol=1e-9 * np.abs(A).max())
+    b.close()
+
+
+def test_is_use_mask():
+    w = swgn.SynthWindow(1, 4)
+    g = w.graph
+    nfac = g.n_proj + g.n_imu + g.n_gnss + g.n_prior + g.n_unit
+    mask = np.ones(nfac, np.uint8)
+    seen = set()
+    for i in range(g.n_proj):  # keep the first observation of every landmark, drop every other one
+        lm = g.proj_blocks[3 * i + 2]
+        if lm in seen and i % 2 == 0:
+            mask[i] = 0
+        seen.add(lm)
+    g.is_use = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+    try:
+        opt = w.options()
+        b = swgn.Batch([w.graph_p], opt)
+        sm = b.solve()[0]
+        o = ob.OracleSolver(w.graph_p, opt)
+        st, osm = o.minimize()
+        assert sm.n_residuals == osm.n_residuals < 2 * g.n_proj + 15 * g.n_imu + 16
+        assert abs(sm.fixed_cost - osm.fixed_cost) <= 1e-11 * osm.fixed_cost and sm.fixed_cost > 0
+        assert abs(sm.final_cost - osm.final_cost) <= TOL_COST * osm.final_cost
+        assert state_err(b.get_state(0, w.n_state), o.state()) < TOL_STATE
+        b.close()
+    finally:
+        g.is_use = None
+
+
+def test_batch_equals_individual_windows():
+    """Windows are independent: solving them in one batch gives bit-identical states to solving
+    each alone (the kernels are deterministic), and every one matches the oracle."""
+    ws = [swgn.SynthWindow(2, i) for i in range(6)] + [swgn.SynthWindow(1, i) for i in range(3)]
+    opt = ws[0].options()
+    b = swgn.Batch([w.graph_p for w in ws], opt)
+    sms = b.solve()
+    packed = b.get_states()
+    off = 0
+    for i, w in enumerate(ws):
+        x = b.get_state(i, w.n_state)
+        assert np.array_equal(x, packed[off:off + w.n_state])
+        off += w.n_state
+        if i in (0, 5, 7):
+            o1 = w.options()
+            o1.n_parameter_head = opt.n_parameter_head
+            b1 = swgn.Batch([w.graph_p], opt)
+            sm1 = b1.solve()[0]
+            assert np.array_equal(b1.get_state(0, w.n_state), x)
+            assert sm1.final_cost == sms[i].final_cost
+            b1.close()
+    for i in (1, 8):
+        o = ob.OracleSolver(ws[i].graph_p, opt)
+        o.minimize()
+        assert state_err(b.get_state(i, ws[i].n_state), o.state()) < TOL_STATE
+    # restarting from re-uploaded initial states reproduces the result
+    b.set_states(np.concatenate([w.state0() for w in ws]))
+    b.solve()
+    assert np.array_equal(b.get_states(), packed)
+    b.close()
+
+
+def test_lambda_batch_bit_exact():
+    """cfg4 (K8): ragged batch of lambda() problems, integer candidates and squared norms
+    bit-identical to the oracle (itself pinned bit-exactly on the reference's lambda.cpp)."""
+    rng = np.random.default_rng(2026)
+    ns, As, Qs, exp = [], [], [], []
+    for k in range(200):
+        n = int(rng.integers(2, 31))
+        B = rng.normal(size=(n, n + 2))
+        u = rng.normal(size=(n, 1))
+        Q = (B @ B.T + 40.0 * (u @ u.T)) * 10.0 ** rng.integers(-3, 1) + 1e-4 * np.eye(n)
+        Q = 0.5 * (Q + Q.T)
+        a = rng.uniform(-30, 30, size=n)
+        ns.append(n)
+        As.append(a)
+        Qs.append(np.asfortranarray(Q).ravel(order="F"))
+        exp.append(ob.lambda_search(a, Q, 2, "oracle"))
+    F, s, info = swgn.lambda_batch(ns, 2, np.concatenate(As), np.concatenate(Qs))
+    o = 0
+    for k, n in enumerate(ns):
+        ei, eF, es = exp[k]
+        assert info[k] == ei
+        if ei == 0:
+            Fk = F[2 * o:2 * o + 2 * n].reshape(2, n).T
+            assert np.array_equal(Fk, eF)
+            assert np.array_equal(s[2 * k:2 * k + 2], es)
+        o += n
+    # failure path: non positive-definite covariance
+    F, s, info = swgn.lambda_batch([3], 2, np.array([0.1, 0.2, 0.3]), (-np.eye(3)).ravel())
+    assert info[0] == -1
+
+
+@pytest.mark.parametrize("wid", [0, 1, 2, 3])
+def test_ambiguity_fix_decision_bit_exact(wid):
+    """cfg4: covariance recovery + LAMBDA ambiguity fix on the solved BASELINE window; the decision
+    (double-difference rows, integer vectors, squared norms, ratio test) is bit-exact given the
+    same A, y; with the GPU's own A, y the integers and the decision are identical."""
+    w = swgn.SynthWindow(2, wid)
+    opt = w.options()
+    b = swgn.Batch([w.graph_p], opt)
+    b.solve()
+    o = ob.OracleSolver(w.graph_p, opt)
+    o.minimize()
+    nt = w.n_amb
+    n, oS, orr, Lo = o.exports()
+    Ao = ob.tail_information(Lo, nt)
+    offs = w.block_offsets()
+    xo, xg = o.state(), b.get_state(0, w.n_state)
+    yo = np.array([xo[offs[w.first_amb_block + k]] for k in range(nt)])
+    yg = np.array([xg[offs[w.first_amb_block + k]] for k in range(nt)])
+    eb, oa, sf = w.ambiguity_epochs()
+    for last_fix in (0, 1):
+        po, Fo, ro = ob.ambiguity_fix(Ao, yo, eb, oa, sf, last_fix)
+        pg, Fg, rg = swgn.ambiguity_fix(Ao, yo, eb, oa, sf, last_fix)
+        assert (rg.status, rg.n_dd, rg.search_ok, rg.n_different) == (ro.status, ro.n_dd, ro.search_ok, ro.n_different)
+        assert np.array_equal(pg, po) and np.array_equal(Fg, Fo)
+        assert list(rg.s) == list(ro.s) and rg.s0_partial == ro.s0_partial and rg.s1_partial == ro.s1_partial
+    Ag = b.tail_information(0, nt)
+    pg, Fg, rg = swgn.ambiguity_fix(Ag, yg, eb, oa, sf, 0)
+    po, Fo, ro = ob.ambiguity_fix(Ao, yo, eb, oa, sf, 0)
+    assert np.array_equal(pg, po) and rg.search_ok == ro.search_ok
+    assert np.array_equal(np.round(Fg[:, 0]), np.round(Fo[:, 0]))
+    b.close()
+
+
+def test_full_size_batch_properties():
+    """At BASELINE batch shape (many 20-KF windows) the oracle is too slow to check every window;
+    size-independent properties instead: every window reduces its cost by orders of magnitude, the
+    exported Cholesky factor reproduces a symmetric positive-definite S, a few sampled windows
+    match the oracle."""
+    n = 96
+    ws = [swgn.SynthWindow(2, 1000 + i) for i in range(n)]
+    opt = ws[0].options()
+    b = swgn.Batch([w.graph_p for w in ws], opt)
+    sms = b.solve()
+    for i in range(n):
+        assert sms[i].termination_type in (0, 1)
+        assert sms[i].final_cost < 1e-4 * sms[i].initial_cost
+        assert sms[i].num_iterations <= 8
+    for i in (0, 50, 95):
+        L = b.get_cholesky(i)
+        assert np.all(np.diag(L) > 0)
+        o = ob.OracleSolver(ws[i].graph_p, opt)
+        o.minimize()
+        assert state_err(b.get_state(i, ws[i].n_state), o.state()) < TOL_STATE
+    tot, schur, nl, kl = b.timing()
+    assert tot > 0 and schur > 0 and nl >= 8 and kl > nl
+    b.close()

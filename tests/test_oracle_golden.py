@@ -82,7 +82,13 @@ def test_problem2_hand_computed_comment_values():
     S = np.triu(lhs) + np.triu(lhs, 1).T
     g = p["golden"]
     np.testing.assert_allclose(S, np.array(g["S"]), atol=6e-5)
-    np.testing.assert_allclose(rhs, np.array(g["r"]), atol=6e-5)
+    # the comment prints r[2] = 5.0323; its own S\\r = [0.2102 2.1367 0.1388] (and A\\b) only follow
+    # from r[2] = 4.0323 = 17 - 30*67/155, i.e. the printed digit is a typo in the reference.
+    r_doc = np.array(g["r"])
+    assert abs(r_doc[2] - 5.0323) < 1e-12
+    r_doc[2] = 4.0323
+    np.testing.assert_allclose(rhs, r_doc, atol=6e-5)
+    np.testing.assert_allclose(np.linalg.solve(np.array(g["S"]), r_doc), np.array(g["S_solve_r"]), atol=2e-4)
     np.testing.assert_allclose(x[2:], np.array(g["S_solve_r"]), atol=6e-5)
     np.testing.assert_allclose(x, np.array(g["A_solve_b"]), atol=6e-5)
     A = dense(p)
