@@ -4,11 +4,18 @@
 //
 // S (n_f x n_f, row-major upper triangle, leading dimension ld) carries the rhs as column n_f, so
 // the forward substitution U^T w = rhs is the same right-looking update as the factorisation.
-// Blocked right-looking algorithm with an NB-row panel staged in shared memory:
-//   panel  <- S[k0:k0+nb, k0:]           (HBM/L2 -> shared)
-//   factor the panel rows in place (rank-1 steps, all threads)
-//   S[k0:k0+nb, k0:] <- panel            (U rows are final)
-//   trailing S[i, j] -= sum_p U[p,i] U[p,j]   (4x4 register tiles, panel operands from shared)
+// This is the one dense contraction of the path, and the only place tensor cores are used: the
+// FP64 tensor-core instruction mma.sync.m8n8k4.f64 (DMMA) carries both the in-panel updates and
+// the trailing update.  Blocked right-looking algorithm, NB-row panel staged in shared memory:
+//   panel <- S[k0:k0+NB, k0:]                              (HBM/L2 -> shared)
+//   for every 8-row block r of the panel:
+//       8x8 Cholesky of the diagonal tile                  (one warp)
+//       X = U_rr^-T P[r, :]   by substitution               (one thread per column)
+//       P[s, :] -= U[r, s]^T X  for the row blocks s > r    (DMMA, 8x8 tiles in shared memory)
+//   S[k0:k0+NB, k0:] <- panel                              (U rows are final)
+//   S[i, j] -= sum_p U[p,i] U[p,j]  for i, j >= k0+NB       (DMMA, 32x32 tiles per warp, operands
+//                                                           from the shared panel, C read-modify-
+//                                                           written in HBM/L2 exactly once per panel)
 // then the backward solve U z = w in 32-row blocks.  The factor stays in W_S: it is the
 // `lhs_out2 = llt.matrixL()` export (schur_complement_solver.cc:253-258) transposed.
 #include "dev_common.cuh"
@@ -18,12 +25,22 @@ namespace swgn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 
-__global__ void __launch_bounds__(kThreads) k_chol(DeviceBatch b, int only_window, int NB) {
+// D(8x8) += A(8x4, row) * B(4x8, col); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
+// D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_window, int NB, int pw) {
   __shared__ WinDesc sd;
   __shared__ int s_fail;
+  __shared__ double s_rdiag[8];
   __shared__ double s_diag[32][33];
-  extern __shared__ double dyn[];  // panel NB x pw, then wv[n_f], zv[n_f]
+  extern __shared__ __align__(16) double dyn[];  // panel NB x pw, then wv[max_nf], zv[max_nf]
   const int w = only_window >= 0 ? only_window : blockIdx.x;
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
@@ -31,9 +48,9 @@ __global__ void __launch_bounds__(kThreads) k_chol(DeviceBatch b, int only_windo
   const Win v = load_window(b, w, &sd);
   const WinDesc& d = sd;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int la = lane & 3, lb = lane >> 2;
   const int nf = d.n_f, ld = d.ld, ncol = nf + 1;
   double* S = v.W(W_S);
-  const int pw = (b.max_nf + 2) | 1;  // odd panel pitch: conflict-free column walks
   double* P = dyn;
   double* wv = dyn + (size_t)NB * pw;
   double* zv = wv + b.max_nf;
@@ -42,96 +59,153 @@ __global__ void __launch_bounds__(kThreads) k_chol(DeviceBatch b, int only_windo
 
   for (int k0 = 0; k0 < nf; k0 += NB) {
     const int nb = min(NB, nf - k0);
-    const int width = ncol - k0;
-    // ---- stage the panel
-    for (int r = wid; r < nb; r += kThreads / 32) {
-      const double* src = S + (size_t)(k0 + r) * ld + k0;
+    const int Wm = nf - k0;              // matrix columns of the panel (panel col j = global col k0 + j)
+    // panel column of the rhs: right after the matrix columns, except in a final partial panel,
+    // where the identity padding of rows nb..NB-1 occupies columns nb..NB-1 and the rhs moves to NB
+    const int jr = (nb < NB) ? NB : Wm;
+    const int Wp = (jr + 1 + 7) & ~7;    // columns processed inside the panel
+    const int Wz = min(pw - 4, max(Wp, (Wm + 1 + 31 + (NB == 16 ? 16 : 0)) & ~31));  // zero-filled extent (trailing tiles read up to here)
+    // ---- stage the panel: upper part of rows k0..k0+nb, identity on padded rows
+    for (int r = wid; r < NB; r += kWarps) {
+      const double* src = S + (size_t)(k0 + r) * ld;
       double* dst = P + (size_t)r * pw;
-      for (int j = r + lane; j < width; j += 32) dst[j] = src[j];
+      for (int j = lane; j < Wz; j += 32) {
+        double val = 0.0;
+        if (r < nb) {
+          if (j >= r && j < Wm) val = src[k0 + j];
+          else if (j == jr) val = src[nf];
+        } else if (j == r) {
+          val = 1.0;
+        }
+        dst[j] = val;
+      }
     }
     __syncthreads();
-    // ---- factor the panel: row p is scaled by 1/sqrt(pivot), rows below get the rank-1 update
-    for (int p = 0; p < nb; ++p) {
-      const double piv = P[(size_t)p * pw + p];
-      if (!(piv > 0.0)) {  // Eigen LLT: info() == NumericalIssue  -> LINEAR_SOLVER_FAILURE
-        if (tid == 0) s_fail = 1;
+    for (int r8 = 0; r8 * 8 < NB; ++r8) {
+      const int r0 = r8 * 8;
+      // (1) 8x8 Cholesky of the diagonal tile (upper, in place), reciprocal pivots to s_rdiag
+      if (wid == 0) {
+        double* T = P + (size_t)r0 * pw + r0;
+        for (int p = 0; p < 8; ++p) {
+          const double piv = T[(size_t)p * pw + p];
+          if (!(piv > 0.0) && lane == 0) s_fail = 1;  // Eigen LLT: NumericalIssue
+          const double x = sqrt(piv);
+          __syncwarp();
+          if (lane >= p && lane < 8) T[(size_t)p * pw + lane] = (lane == p) ? x : T[(size_t)p * pw + lane] / x;
+          if (lane == 8) s_rdiag[p] = 1.0 / x;
+          __syncwarp();
+          // rows q > p, columns j >= q: 28 pairs at most
+          const int q = p + 1 + lane / 8, j = lane & 7;
+          if (q < 8 && j >= q) T[(size_t)q * pw + j] -= T[(size_t)p * pw + q] * T[(size_t)p * pw + j];
+          if (q + 4 < 8 && j >= q + 4) T[(size_t)(q + 4) * pw + j] -= T[(size_t)p * pw + q + 4] * T[(size_t)p * pw + j];
+          __syncwarp();
+        }
       }
-      const double x = sqrt(piv);
       __syncthreads();
-      double* rowp = P + (size_t)p * pw;
-      for (int j = p + tid; j < width; j += kThreads) rowp[j] = (j == p) ? x : rowp[j] / x;
+      // (2) X = U_rr^-T P[r0:r0+8, j] for every column right of the tile, one thread per column
+      {
+        const double* U = P + (size_t)r0 * pw + r0;
+        for (int j = r0 + 8 + tid; j < Wp; j += kThreads) {
+          double* col = P + (size_t)r0 * pw + j;
+          double x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            double s = col[(size_t)i * pw];
+#pragma unroll
+            for (int p = 0; p < i; ++p) s -= U[(size_t)p * pw + i] * x[p];
+            x[i] = s * s_rdiag[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) col[(size_t)i * pw] = x[i];
+        }
+      }
       __syncthreads();
-      const int nrow = nb - p - 1;
-      if (nrow > 0) {
-        // rows q = p+1 .. nb-1, columns j >= q
-        const int wcols = width - (p + 1);
-        for (int e = tid; e < nrow * wcols; e += kThreads) {
-          const int q = p + 1 + e / wcols;
-          const int j = p + 1 + e % wcols;
-          if (j >= q) P[(size_t)q * pw + j] -= rowp[q] * rowp[j];
+      // (3) DMMA update of the panel's remaining row blocks: P[s0.., j0..] -= U[r0.., s0..]^T X[r0.., j0..]
+      {
+        const int nsb = NB / 8, ntj = Wp / 8;
+        int idx = wid;
+        for (int s8 = r8 + 1; s8 < nsb; ++s8) {
+          const int len = ntj - s8;
+          while (idx < len) {
+            const int s0 = s8 * 8, j0 = (s8 + idx) * 8;
+            double2* cp = reinterpret_cast<double2*>(P + (size_t)(s0 + lb) * pw + j0 + 2 * la);
+            double2 c = *cp;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const double* row = P + (size_t)(r0 + 4 * kk + la) * pw;
+              dmma884(c.x, c.y, -row[s0 + lb], row[j0 + lb]);
+            }
+            *cp = c;
+            idx += kWarps;
+          }
+          idx -= len;
         }
       }
       __syncthreads();
     }
     if (s_fail) break;
     // ---- write the finished U rows back
-    for (int r = wid; r < nb; r += kThreads / 32) {
-      double* dst = S + (size_t)(k0 + r) * ld + k0;
+    for (int r = wid; r < nb; r += kWarps) {
+      double* dst = S + (size_t)(k0 + r) * ld;
       const double* src = P + (size_t)r * pw;
-      for (int j = r + lane; j < width; j += 32) dst[j] = src[j];
+      for (int j = r + lane; j < Wm; j += 32) dst[k0 + j] = src[j];
+      if (lane == 0) dst[nf] = src[jr];
     }
-    // ---- trailing update, 4x4 tiles of the block upper triangle (columns include the rhs)
-    const int t0 = k0 + nb;            // first trailing row/col
-    const int tw = ncol - t0;          // trailing columns (incl. rhs)
-    const int th = nf - t0;            // trailing rows
-    if (th > 0) {
-      const int TJ = (tw + 3) >> 2, TI = (th + 3) >> 2;
-      for (int t = tid; t < TI * TJ; t += kThreads) {
-        const int ti = t / TJ, tj = t - ti * TJ;
-        if (tj < ti) continue;
-        const int i0 = ti * 4, j0 = tj * 4;  // relative to t0
-        double acc[4][4];
+    // ---- trailing update with DMMA: 32x32 tiles (ti <= tj) of S[t0:, t0:], k = NB
+    const int t0 = k0 + NB;
+    if (t0 < nf) {
+      const int th = nf - t0, tw = ncol - t0;
+      const int TI = (th + 31) >> 5, TJ = (tw + 31) >> 5;
+      int idx = wid;
+      for (int ti = 0; ti < TI; ++ti) {
+        const int len = TJ - ti;
+        while (idx < len) {
+          const int tj = ti + idx;
+          double acc[4][4][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-        const double* pa = P + nb + i0;  // panel column of trailing row i: (t0 + i0) - k0 = nb + i0
-        const double* pb = P + nb + j0;
-        const bool full_tile = (i0 + 4 <= th) && (j0 + 4 <= tw);
-        if (full_tile) {
-          for (int p = 0; p < nb; ++p) {
-            const double* ra = pa + (size_t)p * pw;
-            const double* rb = pb + (size_t)p * pw;
-            const double a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3];
-            const double b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
-            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2; acc[0][3] += a0 * b3;
-            acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2; acc[1][3] += a1 * b3;
-            acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2; acc[2][3] += a2 * b3;
-            acc[3][0] += a3 * b0; acc[3][1] += a3 * b1; acc[3][2] += a3 * b2; acc[3][3] += a3 * b3;
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+          const double* pa = P + NB + 32 * ti + lb;
+          const double* pb = P + NB + 32 * tj + lb;
+          for (int kk = 0; kk < NB / 4; ++kk) {
+            const size_t ro = (size_t)(4 * kk + la) * pw;
+            double a[4], bb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              a[q] = pa[ro + 8 * q];
+              bb[q] = pb[ro + 8 * q];
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
           }
-        } else {
-          for (int p = 0; p < nb; ++p) {
-            const double* ra = pa + (size_t)p * pw;
-            const double* rb = pb + (size_t)p * pw;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const double av = (i0 + a < th) ? ra[a] : 0.0;
+          for (int mi = 0; mi < 4; ++mi) {
+            const int gi = t0 + 32 * ti + 8 * mi + lb;
+            if (gi >= nf) continue;
+            double* row = S + (size_t)gi * ld;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) acc[a][c] += av * ((j0 + c < tw) ? rb[c] : 0.0);
+            for (int ni = 0; ni < 4; ++ni) {
+              const int gj = t0 + 32 * tj + 8 * ni + 2 * la;
+              const bool v0 = gj >= gi && gj <= nf, v1 = gj + 1 >= gi && gj + 1 <= nf;
+              if (v0 && v1) {
+                double2* p2 = reinterpret_cast<double2*>(row + gj);
+                double2 c = *p2;
+                c.x -= acc[mi][ni][0];
+                c.y -= acc[mi][ni][1];
+                *p2 = c;
+              } else if (v0) {
+                row[gj] -= acc[mi][ni][0];
+              } else if (v1) {
+                row[gj + 1] -= acc[mi][ni][1];
+              }
             }
           }
+          idx += kWarps;
         }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int i = i0 + a;
-          if (i >= th) continue;
-          double* row = S + (size_t)(t0 + i) * ld + t0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int j = j0 + c;
-            if (j < tw && j >= i) row[j] -= acc[a][c];
-          }
-        }
+        idx -= len;
       }
     }
     __syncthreads();
@@ -197,26 +271,40 @@ __global__ void k_tail_information(DeviceBatch b, int window, int n_tail, double
 }
 
 int chol_block(const DeviceBatch& b) { return b.max_nf <= 760 ? 32 : 16; }
+int chol_pitch(const DeviceBatch& b) {
+  const int NB = chol_block(b);
+  const int need = (b.max_nf + 1 + (NB == 16 ? 16 : 0) + 31) & ~31;
+  return (need > NB + 8 ? need : NB + 8) + 4;  // = 4 or 12 mod 16: conflict-free DMMA fragment loads
+}
 size_t chol_smem(const DeviceBatch& b) {
-  const int pw = (b.max_nf + 2) | 1;
-  return sizeof(double) * ((size_t)chol_block(b) * pw + 2 * (size_t)b.max_nf);
+  return sizeof(double) * ((size_t)chol_block(b) * chol_pitch(b) + 2 * (size_t)b.max_nf);
 }
 
 }  // namespace
 
 void launch_chol(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
-  k_chol<<<grid, kThreads, chol_smem(b), s>>>(b, only_window, chol_block(b));
+  k_chol<<<grid, kThreads, chol_smem(b), s>>>(b, only_window, chol_block(b), chol_pitch(b));
 }
 
 void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s) {
   k_tail_information<<<8, 256, 0, s>>>(b, window, n_tail, A_dev);
 }
 
+// The opt-in dynamic shared memory limit is per function and per device: batches with different
+// reduced-system sizes share it, so it only ever grows.
 cudaError_t configure_chol(const DeviceBatch& b) {
+  static size_t granted[64] = {0};
   const size_t dyn = chol_smem(b);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;
-  return cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || dyn > granted[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) granted[dev] = dyn;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace swgn

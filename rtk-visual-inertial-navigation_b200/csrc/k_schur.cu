@@ -485,8 +485,16 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
 }
 
 cudaError_t configure_schur(const DeviceBatch& b) {
+  static size_t granted[64] = {0};
   const size_t dyn = sizeof(double) * (size_t)kWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
-  if (dyn > 48 * 1024) return cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (dyn > 227 * 1024) return cudaErrorInvalidValue;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dyn > 48 * 1024 && (dev < 0 || dev >= 64 || dyn > granted[dev])) {
+    cudaError_t e = cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) granted[dev] = dyn;
+  }
   return cudaSuccess;
 }
 
