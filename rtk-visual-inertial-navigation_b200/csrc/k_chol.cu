@@ -69,15 +69,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
     for (int r = wid; r < NB; r += kWarps) {
       const double* src = S + (size_t)(k0 + r) * ld;
       double* dst = P + (size_t)r * pw;
-      for (int j = lane; j < Wz; j += 32) {
-        double val = 0.0;
-        if (r < nb) {
-          if (j >= r && j < Wm) val = src[k0 + j];
-          else if (j == jr) val = src[nf];
-        } else if (j == r) {
-          val = 1.0;
+      for (int j0 = lane; j0 < Wz; j0 += 128) {  // four independent loads in flight per lane
+        double val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 32 * u;
+          double t = 0.0;
+          if (r < nb) {
+            if (j >= r && j < Wm) t = src[k0 + j];
+            else if (j == jr) t = src[nf];
+          } else if (j == r) {
+            t = 1.0;
+          }
+          val[u] = t;
         }
-        dst[j] = val;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + 32 * u < Wz) dst[j0 + 32 * u] = val[u];
       }
     }
     __syncthreads();
@@ -85,21 +93,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
       const int r0 = r8 * 8;
       // (1) 8x8 Cholesky of the diagonal tile (upper, in place), reciprocal pivots to s_rdiag
       if (wid == 0) {
+        // lane j < 8 keeps column j of the tile in registers; pivots travel by shuffle.  1/sqrt
+        // through rsqrt keeps the serial pivot chain short (346 pivots per window are a latency
+        // floor of the whole factorisation).
         double* T = P + (size_t)r0 * pw + r0;
+        const int j = lane & 7;
+        double t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = T[(size_t)i * pw + j];
+        bool bad = false;
+#pragma unroll
         for (int p = 0; p < 8; ++p) {
-          const double piv = T[(size_t)p * pw + p];
-          if (!(piv > 0.0) && lane == 0) s_fail = 1;  // Eigen LLT: NumericalIssue
-          const double x = sqrt(piv);
-          __syncwarp();
-          if (lane >= p && lane < 8) T[(size_t)p * pw + lane] = (lane == p) ? x : T[(size_t)p * pw + lane] / x;
-          if (lane == 8) s_rdiag[p] = 1.0 / x;
-          __syncwarp();
-          // rows q > p, columns j >= q: 28 pairs at most
-          const int q = p + 1 + lane / 8, j = lane & 7;
-          if (q < 8 && j >= q) T[(size_t)q * pw + j] -= T[(size_t)p * pw + q] * T[(size_t)p * pw + j];
-          if (q + 4 < 8 && j >= q + 4) T[(size_t)(q + 4) * pw + j] -= T[(size_t)p * pw + q + 4] * T[(size_t)p * pw + j];
-          __syncwarp();
+          const double piv = __shfl_sync(0xffffffffu, t[p], p);
+          if (!(piv > 0.0)) bad = true;  // Eigen LLT: NumericalIssue
+          const double ri = rsqrt(piv);
+          if (lane == p) s_rdiag[p] = ri;
+          t[p] = (j == p) ? piv * ri : t[p] * ri;
+#pragma unroll
+          for (int q = p + 1; q < 8; ++q) {
+            const double c = __shfl_sync(0xffffffffu, t[p], q);
+            if (j >= q) t[q] -= c * t[p];
+          }
         }
+        if (lane < 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (j >= i) T[(size_t)i * pw + j] = t[i];
+        }
+        if (bad && lane == 0) s_fail = 1;
       }
       __syncthreads();
       // (2) X = U_rr^-T P[r0:r0+8, j] for every column right of the tile, one thread per column
@@ -151,61 +172,88 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
       for (int j = r + lane; j < Wm; j += 32) dst[k0 + j] = src[j];
       if (lane == 0) dst[nf] = src[jr];
     }
-    // ---- trailing update with DMMA: 32x32 tiles (ti <= tj) of S[t0:, t0:], k = NB
+    // ---- trailing update with DMMA: 16x32 warp tiles of the block upper triangle of S[t0:, t0:],
+    // k = NB.  The C tile of the NEXT work item is loaded (HBM/L2) while the current one runs on
+    // the tensor pipe; the accumulators start from C and A is negated: D = C - U^T U.
     const int t0 = k0 + NB;
     if (t0 < nf) {
       const int th = nf - t0, tw = ncol - t0;
-      const int TI = (th + 31) >> 5, TJ = (tw + 31) >> 5;
-      int idx = wid;
-      for (int ti = 0; ti < TI; ++ti) {
-        const int len = TJ - ti;
-        while (idx < len) {
-          const int tj = ti + idx;
-          double acc[4][4][2];
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-          const double* pa = P + NB + 32 * ti + lb;
-          const double* pb = P + NB + 32 * tj + lb;
-          for (int kk = 0; kk < NB / 4; ++kk) {
-            const size_t ro = (size_t)(4 * kk + la) * pw;
-            double a[4], bb[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              a[q] = pa[ro + 8 * q];
-              bb[q] = pb[ro + 8 * q];
-            }
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-              for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
-          }
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi) {
-            const int gi = t0 + 32 * ti + 8 * mi + lb;
-            if (gi >= nf) continue;
-            double* row = S + (size_t)gi * ld;
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              const int gj = t0 + 32 * tj + 8 * ni + 2 * la;
-              const bool v0 = gj >= gi && gj <= nf, v1 = gj + 1 >= gi && gj + 1 <= nf;
-              if (v0 && v1) {
-                double2* p2 = reinterpret_cast<double2*>(row + gj);
-                double2 c = *p2;
-                c.x -= acc[mi][ni][0];
-                c.y -= acc[mi][ni][1];
-                *p2 = c;
-              } else if (v0) {
-                row[gj] -= acc[mi][ni][0];
-              } else if (v1) {
-                row[gj + 1] -= acc[mi][ni][1];
-              }
-            }
-          }
-          idx += kWarps;
+      const int TI = (th + 15) >> 4, TJ = (tw + 31) >> 5;
+      // work items: (ti, tj) with 32*tj + 31 >= 16*ti, enumerated row by row
+      auto first_tj = [](int ti) { return ti >> 1; };
+      int ti = 0, idx = wid;
+      auto advance = [&](int& ti_, int& idx_) {  // normalise (ti, idx) to a valid item or ti == TI
+        while (ti_ < TI && idx_ >= TJ - first_tj(ti_)) {
+          idx_ -= TJ - first_tj(ti_);
+          ++ti_;
         }
-        idx -= len;
+      };
+      auto load_tile = [&](int ti_, int tj_, double (&c)[2][4][2]) {
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const int gi = t0 + 16 * ti_ + 8 * mi + lb;
+          const double* row = S + (size_t)gi * ld;
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int gj = t0 + 32 * tj_ + 8 * ni + 2 * la;
+            const bool v0 = gi < nf && gj >= gi && gj <= nf, v1 = gi < nf && gj + 1 >= gi && gj + 1 <= nf;
+            if (v0 && v1) {
+              const double2 t = *reinterpret_cast<const double2*>(row + gj);
+              c[mi][ni][0] = t.x;
+              c[mi][ni][1] = t.y;
+            } else {
+              c[mi][ni][0] = v0 ? row[gj] : 0.0;
+              c[mi][ni][1] = v1 ? row[gj + 1] : 0.0;
+            }
+          }
+        }
+      };
+      advance(ti, idx);
+      double cn[2][4][2];
+      if (ti < TI) load_tile(ti, first_tj(ti) + idx, cn);
+      while (ti < TI) {
+        const int tj = first_tj(ti) + idx;
+        double acc[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            acc[mi][ni][0] = cn[mi][ni][0];
+            acc[mi][ni][1] = cn[mi][ni][1];
+          }
+        int nti = ti, nidx = idx + kWarps;
+        advance(nti, nidx);
+        if (nti < TI) load_tile(nti, first_tj(nti) + nidx, cn);
+        const double* pa = P + NB + 16 * ti + lb;
+        const double* pb = P + NB + 32 * tj + lb;
+#pragma unroll 2
+        for (int kk = 0; kk < NB / 4; ++kk) {
+          const size_t ro = (size_t)(4 * kk + la) * pw;
+          double a[2], bb[4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) a[q] = -pa[ro + 8 * q];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bb[q] = pb[ro + 8 * q];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const int gi = t0 + 16 * ti + 8 * mi + lb;
+          double* row = S + (size_t)gi * ld;
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int gj = t0 + 32 * tj + 8 * ni + 2 * la;
+            const bool v0 = gi < nf && gj >= gi && gj <= nf, v1 = gi < nf && gj + 1 >= gi && gj + 1 <= nf;
+            if (v0 && v1) *reinterpret_cast<double2*>(row + gj) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            else if (v0) row[gj] = acc[mi][ni][0];
+            else if (v1) row[gj + 1] = acc[mi][ni][1];
+          }
+        }
+        ti = nti;
+        idx = nidx;
       }
     }
     __syncthreads();
@@ -235,11 +283,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
         if (lane < nb) zv[k0 + lane] = wl;
       }
       __syncthreads();
-      for (int i = tid; i < k0; i += kThreads) {
-        const double* row = S + (size_t)i * ld + k0;
-        double s = 0.0;
-        for (int j = 0; j < nb; ++j) s += row[j] * zv[k0 + j];
-        wv[i] -= s;
+      {  // w_i -= U[i, k0:k0+nb] z[k0:k0+nb] for the rows above: one warp per row, coalesced
+        const double zl = lane < nb ? zv[k0 + lane] : 0.0;
+        for (int i = wid; i < k0; i += kWarps) {
+          const double u = lane < nb ? S[(size_t)i * ld + k0 + lane] : 0.0;
+          const double s = warp_sum(u * zl);
+          if (lane == 0) wv[i] -= s;
+        }
       }
       __syncthreads();
     }

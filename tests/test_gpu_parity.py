@@ -308,8 +308,23 @@ def test_ambiguity_fix_decision_bit_exact(wid):
     Ag = b.tail_information(0, nt)
     pg, Fg, rg = swgn.ambiguity_fix(Ag, yg, eb, oa, sf, 0)
     po, Fo, ro = ob.ambiguity_fix(Ao, yo, eb, oa, sf, 0)
-    assert np.array_equal(pg, po) and rg.search_ok == ro.search_ok
-    assert np.array_equal(np.round(Fg[:, 0]), np.round(Fo[:, 0]))
+    # The GPU state differs from the oracle's at the 1e-7 level (stated tolerance), which may flip
+    # the near-tied choice of a reference satellite (swf_lambda.cpp:24-52); the decision itself --
+    # ratio test and the fixed integer relations between ambiguities -- must be the same.  Compare
+    # the integers in a reference-independent form: N_a - N_c for all a, c of one group.
+    assert rg.search_ok == ro.search_ok and rg.n_dd == ro.n_dd
+
+    def relations(pairs, F):
+        groups = {}
+        for (a, ref), f in zip(pairs, np.round(F[:, 0])):
+            groups.setdefault(int(ref), {int(ref): 0.0})[int(a)] = float(f)
+        out = {}
+        for ref, g in groups.items():
+            base = min(g)
+            out[frozenset(g)] = {a: v - g[base] for a, v in g.items()}
+        return out
+
+    assert relations(pg, Fg) == relations(po, Fo)
     b.close()
 
 
