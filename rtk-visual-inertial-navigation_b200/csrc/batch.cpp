@@ -275,7 +275,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
 
 // Host-only planning probe: runs the preprocessing of one window (no device needed) and reports
 // info[0..11] = n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_chunks, n_jac, n_scells, n_sterms,
-// n_stiles; info[12..13] = algorithmic Schur bytes (low, high 32 bits).
+// n_srows; info[12..13] = algorithmic Schur bytes (low, high 32 bits).
 swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info) {
   if (!g || !info) return fail(SWGN_ERR_INVALID, "bad arguments");
   WindowPlan p;
@@ -283,7 +283,7 @@ swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32
   swgn_status st = build_plan(g, n_parameter_head, &p, &err);
   if (st != SWGN_OK) return fail(st, err);
   const WinDesc& d = p.d;
-  const int32_t v[12] = {d.n_cols, d.n_ecols, d.n_e, d.n_f, d.n_t, d.n_res, d.n_rows, d.n_chunks, d.n_jac, d.n_scells, d.n_sterms, d.n_stiles};
+  const int32_t v[12] = {d.n_cols, d.n_ecols, d.n_e, d.n_f, d.n_t, d.n_res, d.n_rows, d.n_chunks, d.n_jac, d.n_scells, d.n_sterms, d.n_srows};
   std::memcpy(info, v, sizeof(v));
   const int64_t bytes = 8 * p.schur_doubles;
   info[12] = (int32_t)(bytes & 0xffffffff);

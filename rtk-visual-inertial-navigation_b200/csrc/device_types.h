@@ -42,10 +42,14 @@ enum IArr {
   I_CSC_PTR,        // [n_cols+1]
   I_CSC_ROW,        // [nnz] row block
   I_CSC_VAL,        // [nnz] value offset
-  I_SCELL,          // [n_scells * 6] reduced-system block cell: ps, qs, S offset (row*ld+col),
-                    //                term_begin, term_end, diag flag (1: p == q, add D^2)
-  I_STERM,          // [n_sterms * 2] packed gather term (see STERM_* below)
-  I_STILE,          // [n_stiles] packed 3x3 tile of a cell: cell << 12 | i0 << 6 | j0
+  I_SCELL,          // [n_scells * 8] reduced-system block cell: ps, qs, S offset (row*ld+col), first
+                    //                word of its terms in I_STERM, term count, diag flag (1: p == q:
+                    //                add D^2, carries the rhs as an extra column), first run, run count
+  I_SRUN,           // [n_sruns * 2] run of consecutive terms with equal shape: count, m << 1 | subtract
+  I_STERM,          // [n_sterms] gather terms (see below): (a, b), or (a, b, b2, 0) on diagonal cells
+  I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
+  I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
+  I_SROW,           // [n_srows] rows (with f-cells) of the simple chunks: one thread each in phase 1b
   I_PROJ,           // [n_proj * 8]  state_off[3], jac_off[3], res_off, 0
   I_IMU,            // [n_imu * 12]  state_off[4], jac_off[4], res_off, 0,0,0
   I_GNSS,           // [n_gnss * 8]  kind, state_off[3], jac_off[3], res_off
@@ -57,9 +61,8 @@ enum IArr {
 
 // Gather term of the reduced system: S_pq (+/-)= A^T B with A (m x ps) at JW[a], B (m x qs) at
 // JW[b], where JW is the concatenation W_JAC | W_EBUF | W_RES of the window.
-//   word0 = a (22 bits) | low 10 bits of m << 22
-//   word1 = b (22 bits) | high 9 bits of m << 22 | sign << 31      (sign 1: subtract)
-enum { STERM_OFF_BITS = 22, STERM_OFF_MASK = (1 << 22) - 1, STERM_MAX_M = (1 << 19) - 1 };
+// b2 (diagonal cells only) is the offset of the m-vector paired with A for the rhs: b or w_g.
+// m and the sign are shared by all terms of a run (I_SRUN).
 
 enum CArr {
   C_GLOBALS = 0,  // Pbg[3], gravity[3], proj_sqrt_info[4], cauchy_a, pad -> 12
@@ -108,7 +111,7 @@ enum { MAX_WARP_E = 16, MAX_COL_SIZE = 63 };
 struct WinDesc {
   int32_t n_state, n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_cells, n_chunks, n_slots;
   int32_t n_jac, n_ebuf, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, n_efac, n_head;
-  int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_stiles, max_prior_n, max_wbuf, pad0;
+  int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, pad0;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

@@ -7,10 +7,12 @@
 // mutexes, :552):
 //   phase 1, per chunk c (rows sharing e-block e):   L L' = D_e^2 + sum E'E      (chunk factor)
 //            W_f = L^-1 sum E'F_f  for every f-block of the chunk,  w_g = L^-1 sum E'b
-//   phase 2, per 3x3 tile of every touched block cell (p,q) of S (and of the rhs column): gather
+//   phase 2, one warp per touched block cell (p,q) of S, one lane per element: gather
 //            S_pq = [p==q] D_p^2 + sum_rows F_p'F_q - sum_chunks W_p'W_q ,
-//            rhs_p = sum_rows F_p'b - sum_chunks W_p'w_g
+//            rhs_p = sum_rows F_p'b - sum_chunks W_p'w_g   (extra column of the diagonal cells)
 //            from host-built term lists (plan.cpp) and store each element of S exactly once.
+//            All lanes of a warp read the same two small blocks, so every load is a broadcast
+//            out of one or two cache lines.
 //   back-substitution: y_e = L^-T (w_g - sum_f W_f z_f).
 // (E'E + D^2)^-1 of the reference (InvertPSDMatrix, invert_psd_matrix.h:62-67: LLT-solve-identity)
 // is applied in factored form: buffer' inv buffer = (L^-1 buffer)'(L^-1 buffer).
@@ -22,6 +24,14 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+
+// D(8x8) += A(8x4, row) * B(4x8, col); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
+// D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
 
 // ---- phase 1, small e-blocks (1..3): one thread per chunk, everything in registers -----------
 template <int ES>
@@ -111,6 +121,7 @@ __device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const doub
 #pragma unroll
     for (int i = 0; i < ES; ++i) gp[i] = wg[i];
   }
+  if (v.I(I_CHUNK_SIMPLE)[chunk]) return;  // the W blocks of simple chunks are built row-parallel (phase 1b)
   // W_f (+)= (L^-1 E_rr') F_rr for every residual row rr of every row block
   for (int r = r0; r < r1; ++r) {
     const int c0 = row_cell[r], c1 = row_cell[r + 1];
@@ -139,6 +150,72 @@ __device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const doub
             Wf[i * fs + j] = store ? t : Wf[i * fs + j] + t;
           }
         }
+      }
+    }
+  }
+}
+
+// ---- phase 1b: one thread per row of a simple chunk: W_f = (L^-1 E') F_f, stored once ---------
+template <int ES>
+__device__ __forceinline__ void row_w(const Win& v, int r, int chunk) {
+  const int32_t* row_cell = v.I(I_ROW_CELL);
+  const int32_t* cell_col = v.I(I_CELL_COL);
+  const int32_t* cell_val = v.I(I_CELL_VAL);
+  const int32_t* cell_slot = v.I(I_CELL_SLOT);
+  const int32_t* col_size = v.I(I_COL_SIZE);
+  const double* J = v.W(W_JAC);
+  double* EB = v.W(W_EBUF);
+  const double* Lp = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+  double L[ES][ES];
+#pragma unroll
+  for (int i = 0; i < ES; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k) L[i][k] = Lp[i * ES + k];
+  const int c0 = row_cell[r], c1 = row_cell[r + 1];
+  const double* E = J + cell_val[c0];
+  const int nres = v.I(I_ROW_NRES)[r];
+  if (nres == 2) {  // the visual case: both residual rows at once, every W entry written once
+    double v0[ES], v1[ES];
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+      double s0 = E[i], s1 = E[ES + i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+        s0 -= L[i][k] * v0[k];
+        s1 -= L[i][k] * v1[k];
+      }
+      v0[i] = s0 / L[i][i];
+      v1[i] = s1 / L[i][i];
+    }
+    for (int c = c0 + 1; c < c1; ++c) {
+      const int fs = col_size[cell_col[c]];
+      const double* F = J + cell_val[c];
+      double* Wf = EB + cell_slot[c];
+      for (int j = 0; j < fs; ++j) {
+        const double f0 = F[j], f1 = F[fs + j];
+#pragma unroll
+        for (int i = 0; i < ES; ++i) Wf[i * fs + j] = v0[i] * f0 + v1[i] * f1;
+      }
+    }
+    return;
+  }
+  for (int rr = 0; rr < nres; ++rr) {
+    double vv[ES];
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+      double s = E[rr * ES + i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s -= L[i][k] * vv[k];
+      vv[i] = s / L[i][i];
+    }
+    for (int c = c0 + 1; c < c1; ++c) {
+      const int fs = col_size[cell_col[c]];
+      const double* F = J + cell_val[c] + rr * fs;
+      double* Wf = EB + cell_slot[c];
+      for (int j = 0; j < fs; ++j) {
+        const double f = F[j];
+#pragma unroll
+        for (int i = 0; i < ES; ++i) Wf[i * fs + j] = (rr == 0) ? vv[i] * f : Wf[i * fs + j] + vv[i] * f;
       }
     }
   }
@@ -261,7 +338,7 @@ __device__ __forceinline__ void chunk_dispatch(const Win& v, int chunk, const do
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_schur(DeviceBatch b, int only_window) {
+__global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_window) {
   __shared__ WinDesc sd;
   extern __shared__ double dyn[];  // kWarps * max_wbuf doubles
   const int w = only_window >= 0 ? only_window : blockIdx.x;
@@ -279,7 +356,7 @@ __global__ void __launch_bounds__(kThreads) k_schur(DeviceBatch b, int only_wind
     double* row = S + (size_t)i * ld;
     for (int j = i + lane; j <= nf; j += 32) row[j] = 0.0;
   }
-  // phase 1: chunk factors and buffers
+  // phase 1a: chunk factors (and the W buffers of the chunks that are not row-parallel)
   {
     const int32_t* tch = v.I(I_TCHUNK);
     for (int k = tid; k < d.n_tchunks; k += kThreads) chunk_dispatch(v, tch[k], lmd);
@@ -288,54 +365,135 @@ __global__ void __launch_bounds__(kThreads) k_schur(DeviceBatch b, int only_wind
     for (int k = wid; k < d.n_wchunks; k += kWarps) chunk_warp(v, wch[k], lmd, sm);
   }
   __syncthreads();
-  // phase 2: gather every 3x3 tile of the reduced system
+  // phase 1b: W blocks of the simple chunks, one thread per row (consecutive threads read
+  // consecutive row blocks of J)
   {
-    const int32_t* stile = v.I(I_STILE);
+    const int32_t* srow = v.I(I_SROW);
+    const int32_t* row_chunk = v.I(I_ROW_CHUNK);
+    const int32_t* chunk_ecol = v.I(I_CHUNK_ECOL);
+    const int32_t* col_size = v.I(I_COL_SIZE);
+    for (int k = tid; k < d.n_srows; k += kThreads) {
+      const int r = srow[k], chunk = row_chunk[r];
+      const int es = col_size[chunk_ecol[chunk]];
+      if (es == 3) row_w<3>(v, r, chunk);
+      else if (es == 1) row_w<1>(v, r, chunk);
+      else row_w<2>(v, r, chunk);
+    }
+  }
+  __syncthreads();
+  // phase 2: one warp per block cell.  S_pq = sum_t (+/-) A_t' B_t is a skinny GEMM whose K
+  // dimension is the stack of the gathered blocks; every term feeds one FP64 tensor-core MMA
+  // (m8n8k4: A_t' is the 8x4 operand, B_t the 4x8 operand, rows beyond m masked to zero), lanes
+  // load their fragment element straight from the window's JW region, so a warp touches one or
+  // two cache lines per operand.  Diagonal cells carry the rhs as column qs of the B operand.
+  // Terms come in runs of equal shape (plan.cpp) and are processed four at a time: eight operand
+  // loads in flight per lane before the four MMAs.
+  {
     const int32_t* scell = v.I(I_SCELL);
-    const uint32_t* sterm = reinterpret_cast<const uint32_t*>(v.I(I_STERM));
+    const int32_t* srun = v.I(I_SRUN);
+    const int32_t* sterm = v.I(I_STERM);
     const double* JW = v.W(W_JAC);
-    for (int ti = tid; ti < d.n_stiles; ti += kThreads) {
-      const uint32_t packed = (uint32_t)stile[ti];
-      const int32_t* sc = scell + 6 * (packed >> 12);
-      const int i0 = (packed >> 6) & 63, j0 = packed & 63;
-      const int ps = sc[0], qs = sc[1];
-      const int ni = min(3, ps - i0), nj = min(3, qs - j0);
-      double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      for (int t = sc[3]; t < sc[4]; ++t) {
-        const uint32_t w0 = sterm[2 * t], w1 = sterm[2 * t + 1];
-        const double* A = JW + (w0 & STERM_OFF_MASK) + i0;
-        const double* B = JW + (w1 & STERM_OFF_MASK) + j0;
-        const int m = (int)(w0 >> STERM_OFF_BITS) | (int)(((w1 >> STERM_OFF_BITS) & 0x1ffu) << 10);
-        const double sg = (w1 >> 31) ? -1.0 : 1.0;
-        for (int e = 0; e < m; ++e) {
-          const double a0 = sg * A[0], a1 = ni > 1 ? sg * A[1] : 0.0, a2 = ni > 2 ? sg * A[2] : 0.0;
-          const double b0 = B[0], b1 = nj > 1 ? B[1] : 0.0, b2 = nj > 2 ? B[2] : 0.0;
-          acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
-          acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
-          acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
-          A += ps;
-          B += qs;
-        }
-      }
-      const int soff = sc[2];
-      if (sc[5]) {  // diagonal block: + D^2  (schur_eliminator_impl.h:194-215)
-        const int frow = soff / ld;  // first row of the block inside S
-        const double* df = lmd + d.n_e + frow;
+    const int la = lane & 3, lb = lane >> 2;
+    for (int cell = wid; cell < d.n_scells; cell += kWarps) {
+      const int32_t* sc = scell + 8 * cell;
+      const int ps = sc[0], qs = sc[1], soff = sc[2];
+      const int diag = sc[5] & 1;
+      const int nq = qs + diag;
+      const int frow = soff / ld;  // first S row of block p
+      for (int ti = 0; ti < ps; ti += 8)
+        for (int tj = 0; tj < nq; tj += 8) {
+          const int ai = ti + lb, bj = tj + lb;
+          const bool a_ok = ai < ps, b_ok = bj < qs, b_rhs = diag && bj == qs;
+          // lane pointer bases inside a 4-row slab; lanes without an element read element 0 (masked)
+          const double* JA = JW + (a_ok ? la * ps + ai : 0);
+          const double* JB = b_rhs ? JW + la : JW + (b_ok ? la * qs + bj : 0);
+          const bool b_any = b_ok || b_rhs;
+          double c0 = 0.0, c1 = 0.0;
+          const int32_t* tp = sterm + sc[3];
+          for (int run = sc[6]; run < sc[6] + sc[7]; ++run) {
+            const int cnt = srun[2 * run], m = srun[2 * run + 1] >> 1;
+            const bool neg = srun[2 * run + 1] & 1;
+            const double sg = neg ? -1.0 : 1.0;
+            if (m <= 4) {
+              const bool oka = a_ok && la < m, okb = b_any && la < m;
+              int k = 0;
+              if (diag) {
+                for (; k + 4 <= cnt; k += 4) {
+                  int4 t[4];
 #pragma unroll
-        for (int ii = 0; ii < 3; ++ii) {
-          const int jj = i0 + ii - j0;
-          if (ii < ni && jj >= 0 && jj < nj) {
-            const double dd = df[i0 + ii];
-            acc[ii][jj] += dd * dd;
+                  for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const int4*>(tp + 4 * (k + u));
+                  double av[4], bv[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    av[u] = oka ? JA[t[u].x] : 0.0;
+                    bv[u] = okb ? JB[b_rhs ? t[u].z : t[u].y] : 0.0;
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, sg * av[u], bv[u]);
+                }
+                for (; k < cnt; ++k) {
+                  const int4 t = *reinterpret_cast<const int4*>(tp + 4 * k);
+                  const double av = oka ? JA[t.x] : 0.0;
+                  const double bv = okb ? JB[b_rhs ? t.z : t.y] : 0.0;
+                  dmma884(c0, c1, sg * av, bv);
+                }
+                tp += 4 * cnt;
+              } else {
+                for (; k + 4 <= cnt; k += 4) {
+                  int2 t[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const int2*>(tp + 2 * (k + u));
+                  double av[4], bv[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    av[u] = oka ? JA[t[u].x] : 0.0;
+                    bv[u] = okb ? JB[t[u].y] : 0.0;
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, sg * av[u], bv[u]);
+                }
+                for (; k < cnt; ++k) {
+                  const int2 t = *reinterpret_cast<const int2*>(tp + 2 * k);
+                  const double av = oka ? JA[t.x] : 0.0;
+                  const double bv = okb ? JB[t.y] : 0.0;
+                  dmma884(c0, c1, sg * av, bv);
+                }
+                tp += 2 * cnt;
+              }
+            } else {  // blocks with more than 4 rows (speed-bias chunks, IMU rows, priors): K steps of 4
+              const int tw = diag ? 4 : 2;
+              for (int k = 0; k < cnt; ++k) {
+                const int ao = tp[0], bo = (b_rhs ? tp[2] : tp[1]);
+                const int bstep = b_rhs ? 1 : qs;
+                for (int e0 = 0; e0 < m; e0 += 4) {
+                  const bool ok = e0 + la < m;
+                  const double av = (ok && a_ok) ? JA[ao + e0 * ps] : 0.0;
+                  const double bv = (ok && b_any) ? JB[bo + e0 * bstep] : 0.0;
+                  dmma884(c0, c1, sg * av, bv);
+                }
+                tp += tw;
+              }
+            }
+          }
+          // C fragment: row lb, columns 2*la, 2*la+1 of the 8x8 tile
+          const int i = ti + lb;
+          if (i < ps) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = tj + 2 * la + h;
+              double val = h ? c1 : c0;
+              if (j < qs) {
+                if (diag && i == j) {  // + D^2  (schur_eliminator_impl.h:194-215)
+                  const double dd = lmd[d.n_e + frow + i];
+                  val += dd * dd;
+                }
+                S[soff + (size_t)i * ld + j] = val;
+              } else if (diag && j == qs) {
+                S[(size_t)(frow + i) * ld + nf] = val;
+              }
+            }
           }
         }
-      }
-      double* out = S + soff + (size_t)i0 * ld + j0;
-#pragma unroll
-      for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj)
-          if (ii < ni && jj < nj) out[(size_t)ii * ld + jj] = acc[ii][jj];
     }
   }
   if (b.keep_copy) {

@@ -363,34 +363,33 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   if (n_chunks != n_ecols) return fail(SWGN_ERR_INVALID, "chunk detection does not match the eliminated blocks");
   const int n_slots = (int)I[I_SLOT_COL].size();
   const int n_jac_al = (int)align2(n_jac), n_ebuf_al = (int)align2(n_ebuf);
-  if ((int64_t)n_jac_al + n_ebuf_al + n_res >= (1 << STERM_OFF_BITS))
-    return fail(SWGN_ERR_TOO_LARGE, "window Jacobian too large for the packed gather terms");
+  if ((int64_t)n_jac_al + n_ebuf_al + n_res >= INT32_MAX)
+    return fail(SWGN_ERR_TOO_LARGE, "window Jacobian too large for 32-bit gather offsets");
 
   // ---- gather tables of the reduced system (device Schur kernel, phase 2).  Every touched block
-  // cell (p, q), p <= q, of S -- plus the rhs as block column n_fcols -- lists its terms:
+  // cell (p, q), p <= q, of S lists its terms:
   //   + F_p' F_q of every row holding both cells      (schur_eliminator_impl.h:667-716, 569-661)
   //   - Wp' Wq   of every chunk holding both slots    (:514-563)
-  // rhs: + F_p' b per row (all rows: b - E inv g expands to this minus the chunk term) and
-  //      - Wp' wg per chunk (:381-422).
+  // The rhs rides on the diagonal cells as one extra column: a diagonal cell's term list is exactly
+  // the list of rows / chunks that touch block p, and rhs_p = sum_rows F_p' b - sum_chunks Wp' wg
+  // (:381-422: b - E inv g expands to this), so its terms carry a third word, the offset of b / wg.
   const int ld = (n_f + 1 + 3) & ~3;
   {
-    const int n_fcols = n_cols - n_ecols;
     auto fpos = [&](int c) { return col_pos[c] - n_e; };  // row/col of the f-block inside S
     struct T {
-      uint32_t a, b, m, sign;
+      uint32_t a, b, m, sign, b2;
     };
-    std::map<std::pair<int, int>, std::vector<T>> cells;  // (p, q) with q == n_cols for the rhs
+    std::map<std::pair<int, int>, std::vector<T>> cells;
     for (int c = n_ecols; c < n_cols; ++c) cells[{c, c}];  // diagonal cells always exist (D^2)
     const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
     for (int r = 0; r < n_rows; ++r) {
       const int nres = I[I_ROW_NRES][r];
-      if (nres > STERM_MAX_M) return fail(SWGN_ERR_TOO_LARGE, "residual block too large");
       for (int c1 = I[I_ROW_CELL][r]; c1 < I[I_ROW_CELL][r + 1]; ++c1) {
         const int p = I[I_CELL_COL][c1];
         if (p < n_ecols) continue;
         for (int c2 = c1; c2 < I[I_ROW_CELL][r + 1]; ++c2)
-          cells[{p, I[I_CELL_COL][c2]}].push_back({(uint32_t)I[I_CELL_VAL][c1], (uint32_t)I[I_CELL_VAL][c2], (uint32_t)nres, 0u});
-        cells[{p, n_cols}].push_back({(uint32_t)I[I_CELL_VAL][c1], res_base + (uint32_t)I[I_ROW_RES][r], (uint32_t)nres, 0u});
+          cells[{p, I[I_CELL_COL][c2]}].push_back({(uint32_t)I[I_CELL_VAL][c1], (uint32_t)I[I_CELL_VAL][c2], (uint32_t)nres, 0u,
+                                                   res_base + (uint32_t)I[I_ROW_RES][r]});
       }
     }
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -398,39 +397,68 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       for (int s1 = I[I_CHUNK_SLOT][ch]; s1 < I[I_CHUNK_SLOT][ch + 1]; ++s1) {
         const int p = I[I_SLOT_COL][s1];
         for (int s2 = s1; s2 < I[I_CHUNK_SLOT][ch + 1]; ++s2)
-          cells[{p, I[I_SLOT_COL][s2]}].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_SLOT_BUF][s2]), es, 1u});
-        cells[{p, n_cols}].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_CHUNK_G][ch]), es, 1u});
+          cells[{p, I[I_SLOT_COL][s2]}].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_SLOT_BUF][s2]), es, 1u,
+                                                   (uint32_t)(n_jac_al + I[I_CHUNK_G][ch])});
       }
     }
-    // longest term lists first: neighbouring lanes get similar trip counts
+    // heaviest cells first: the warps pull cells round-robin, so the tail is made of light cells
     std::vector<std::pair<std::pair<int, int>, const std::vector<T>*>> order;
     for (auto& kv : cells) order.push_back({kv.first, &kv.second});
-    std::stable_sort(order.begin(), order.end(), [](const auto& x, const auto& y) {
-      size_t wx = 0, wy = 0;
-      for (const T& t : *x.second) wx += t.m;
-      for (const T& t : *y.second) wy += t.m;
-      return wx > wy;
-    });
-    if (order.size() >= (1u << 20)) return fail(SWGN_ERR_TOO_LARGE, "too many reduced-system cells");
+    auto weight = [&](const std::pair<std::pair<int, int>, const std::vector<T>*>& x) {
+      size_t w = 0;
+      for (const T& t : *x.second) w += t.m;
+      const int outs = col_size[x.first.first] * (col_size[x.first.second] + (x.first.first == x.first.second ? 1 : 0));
+      return w * (size_t)((outs + 31) / 32) + 8;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](const auto& x, const auto& y) { return weight(x) > weight(y); });
     for (size_t ci = 0; ci < order.size(); ++ci) {
       const int p = order[ci].first.first, q = order[ci].first.second;
-      const int ps = col_size[p], qs = (q == n_cols) ? 1 : col_size[q];
+      const int ps = col_size[p], qs = col_size[q];
       if (ps > MAX_COL_SIZE || qs > MAX_COL_SIZE) return fail(SWGN_ERR_UNSUPPORTED, "parameter block larger than 63 tangent dimensions");
-      const int scol = (q == n_cols) ? n_f : fpos(q);
-      const int32_t rec[6] = {ps, qs, fpos(p) * ld + scol, (int32_t)(I[I_STERM].size() / 2),
-                              (int32_t)(I[I_STERM].size() / 2 + order[ci].second->size()), p == q ? 1 : 0};
-      I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 6);
-      for (const T& t : *order[ci].second) {
-        I[I_STERM].push_back((int32_t)(t.a | ((t.m & 1023u) << STERM_OFF_BITS)));
-        I[I_STERM].push_back((int32_t)(t.b | ((t.m >> 10) << STERM_OFF_BITS) | (t.sign << 31)));
+      const bool diag = p == q;
+      // terms sorted into runs of equal (rows m, sign): the device loop decodes nothing per term
+      std::vector<T> ts = *order[ci].second;
+      std::stable_sort(ts.begin(), ts.end(), [](const T& x, const T& y) { return x.m != y.m ? x.m < y.m : x.sign < y.sign; });
+      const int run_begin = (int)(I[I_SRUN].size() / 2);
+      for (size_t k = 0; k < ts.size();) {
+        size_t k1 = k;
+        while (k1 < ts.size() && ts[k1].m == ts[k].m && ts[k1].sign == ts[k].sign) ++k1;
+        I[I_SRUN].push_back((int32_t)(k1 - k));
+        I[I_SRUN].push_back((int32_t)((ts[k].m << 1) | ts[k].sign));
+        k = k1;
       }
-      for (int i0 = 0; i0 < ps; i0 += 3)
-        for (int j0 = 0; j0 < qs; j0 += 3) {
-          if (p == q && j0 + 2 < i0) continue;  // tile strictly below the diagonal
-          I[I_STILE].push_back((int32_t)((ci << 12) | (i0 << 6) | j0));
+      if (diag)
+        while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);  // 16-byte records need 16-byte alignment
+      const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0,
+                              run_begin, (int32_t)(I[I_SRUN].size() / 2) - run_begin};
+      I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);
+      for (const T& t : ts) {  // (a, b) per term, (a, b, b2, 0) on diagonal cells: 8 / 16 byte records
+        I[I_STERM].push_back((int32_t)t.a);
+        I[I_STERM].push_back((int32_t)t.b);
+        if (diag) {
+          I[I_STERM].push_back((int32_t)t.b2);
+          I[I_STERM].push_back(0);
         }
+      }
     }
-    (void)n_fcols;
+  }
+  // ---- row-parallel part of phase 1: rows of "simple" small chunks (every slot fed by exactly one
+  // row, e.g. a landmark seen once per keyframe) compute their W block independently
+  {
+    I[I_ROW_CHUNK].assign(n_rows, -1);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int es = col_size[I[I_CHUNK_ECOL][ch]];
+      bool simple = es <= 3;
+      for (int r = I[I_CHUNK_ROW][ch]; r < I[I_CHUNK_ROW][ch + 1]; ++r) {
+        I[I_ROW_CHUNK][r] = ch;
+        for (int c = I[I_ROW_CELL][r] + 1; c < I[I_ROW_CELL][r + 1]; ++c)
+          if (!I[I_CELL_FIRST][c]) simple = false;
+      }
+      I[I_CHUNK_SIMPLE].push_back(simple ? 1 : 0);
+      if (simple)
+        for (int r = I[I_CHUNK_ROW][ch]; r < I[I_CHUNK_ROW][ch + 1]; ++r)
+          if (I[I_ROW_CELL][r + 1] - I[I_ROW_CELL][r] > 1) I[I_SROW].push_back(r);
+    }
   }
   // CSC
   {
@@ -544,9 +572,9 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_efac = n_efac;
   d.n_tchunks = (int)I[I_TCHUNK].size();
   d.n_wchunks = (int)I[I_WCHUNK].size();
-  d.n_scells = (int)(I[I_SCELL].size() / 6);
-  d.n_sterms = (int)(I[I_STERM].size() / 2);
-  d.n_stiles = (int)I[I_STILE].size();
+  d.n_scells = (int)(I[I_SCELL].size() / 8);
+  d.n_sterms = (int)I[I_STERM].size();
+  d.n_srows = (int)I[I_SROW].size();
   d.max_wbuf = max_wbuf;
   d.max_prior_n = 0;
   for (int i = 0; i < g->n_prior; ++i) d.max_prior_n = std::max(d.max_prior_n, g->prior_n[i]);

@@ -205,7 +205,7 @@ def plan_probe(graph_p, n_parameter_head=0):
     info = (i32 * 14)()
     st = lib().swgn_plan_probe(graph_p, n_parameter_head, info)
     keys = ["n_cols", "n_ecols", "n_e", "n_f", "n_t", "n_res", "n_rows", "n_chunks", "n_jac",
-            "n_scells", "n_sterms", "n_stiles"]
+            "n_scells", "n_sterms", "n_srows"]
     d = {k: info[i] for i, k in enumerate(keys)}
     d["schur_bytes"] = (info[12] & 0xffffffff) | (info[13] << 32)
     return st, d
