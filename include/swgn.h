@@ -212,9 +212,10 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows,
 void swgn_batch_destroy(swgn_batch* b);
 /* Host-only: run the preprocessing of one window without touching a device and report
    info[0..11] = n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_chunks, n_jac, n_scells,
-   n_sterms, n_srows; info[12..13] = algorithmic Schur bytes (low / high 32 bits).  Returns the
+   n_sterms, n_srows; info[12..13] = algorithmic Schur bytes (low / high 32 bits); info[14] =
+   tensor-core MMAs of one Schur gather pass.  Returns the
    same status codes swgn_batch_create would (SWGN_ERR_ORDERING, ...). */
-swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info14);
+swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info16);
 int32_t swgn_batch_size(const swgn_batch* b);
 
 /* Re-upload initial states only (structure unchanged): state_w has graphs[w]->n_state doubles. */

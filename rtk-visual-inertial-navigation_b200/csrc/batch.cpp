@@ -275,7 +275,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
 
 // Host-only planning probe: runs the preprocessing of one window (no device needed) and reports
 // info[0..11] = n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_chunks, n_jac, n_scells, n_sterms,
-// n_srows; info[12..13] = algorithmic Schur bytes (low, high 32 bits).
+// n_srows; info[12..13] = algorithmic Schur bytes (low, high 32 bits); info[14] = MMAs per gather pass.
 swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info) {
   if (!g || !info) return fail(SWGN_ERR_INVALID, "bad arguments");
   WindowPlan p;
@@ -288,6 +288,8 @@ swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32
   const int64_t bytes = 8 * p.schur_doubles;
   info[12] = (int32_t)(bytes & 0xffffffff);
   info[13] = (int32_t)(bytes >> 32);
+  info[14] = (int32_t)p.n_mma;
+  info[15] = 0;
   return SWGN_OK;
 }
 

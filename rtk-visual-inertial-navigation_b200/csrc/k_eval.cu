@@ -429,7 +429,7 @@ __device__ void eval_imu(const Win& v, const Globals& gl, int i, const double* x
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_eval(DeviceBatch b, int mode, int only_window) {
+__global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, int only_window) {
   __shared__ WinDesc sd;
   __shared__ double red[33];
   __shared__ double imu_scratch[kWarps][kImuScratch];

@@ -33,6 +33,14 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// explicit global-space load (the window base pointer is laundered through an asm barrier below,
+// which would otherwise demote the loads to generic LD)
+__device__ __forceinline__ double ld_global(const double* p) {
+  double v;
+  asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 // ---- phase 1, small e-blocks (1..3): one thread per chunk, everything in registers -----------
 template <int ES>
 __device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const double* lmd) {
@@ -393,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
     const int32_t* srun = v.I(I_SRUN);
     const int32_t* sterm = v.I(I_STERM);
     const double* JW = v.W(W_JAC);
+    asm volatile("" : "+l"(JW));  // keep the window base in a register pair: operand address = one IMAD.WIDE
     const int la = lane & 3, lb = lane >> 2;
     for (int cell = wid; cell < d.n_scells; cell += kWarps) {
       const int32_t* sc = scell + 8 * cell;
@@ -404,38 +413,42 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
         for (int tj = 0; tj < nq; tj += 8) {
           const int ai = ti + lb, bj = tj + lb;
           const bool a_ok = ai < ps, b_ok = bj < qs, b_rhs = diag && bj == qs;
-          // lane pointer bases inside a 4-row slab; lanes without an element read element 0 (masked)
-          const double* JA = JW + (a_ok ? la * ps + ai : 0);
-          const double* JB = b_rhs ? JW + la : JW + (b_ok ? la * qs + bj : 0);
+          // lane offsets inside a 4-row slab (32-bit: one IMAD.WIDE per operand address)
+          const int a_lo = a_ok ? la * ps + ai : 0;
+          const int b_lo = b_rhs ? la : (b_ok ? la * qs + bj : 0);
           const bool b_any = b_ok || b_rhs;
-          double c0 = 0.0, c1 = 0.0;
+          // additions and subtractions accumulate separately: no per-term sign multiply
+          double cp0 = 0.0, cp1 = 0.0, cn0 = 0.0, cn1 = 0.0;
           const int32_t* tp = sterm + sc[3];
           for (int run = sc[6]; run < sc[6] + sc[7]; ++run) {
             const int cnt = srun[2 * run], m = srun[2 * run + 1] >> 1;
             const bool neg = srun[2 * run + 1] & 1;
-            const double sg = neg ? -1.0 : 1.0;
+            double c0 = neg ? cn0 : cp0, c1 = neg ? cn1 : cp1;
             if (m <= 4) {
               const bool oka = a_ok && la < m, okb = b_any && la < m;
               int k = 0;
               if (diag) {
+                const int bsel = b_rhs ? 2 : 1;
                 for (; k + 4 <= cnt; k += 4) {
-                  int4 t[4];
+                  int ao[4], bo[4];
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const int4*>(tp + 4 * (k + u));
+                  for (int u = 0; u < 4; ++u) {
+                    ao[u] = tp[4 * (k + u)];
+                    bo[u] = tp[4 * (k + u) + bsel];
+                  }
                   double av[4], bv[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
-                    av[u] = oka ? JA[t[u].x] : 0.0;
-                    bv[u] = okb ? JB[b_rhs ? t[u].z : t[u].y] : 0.0;
+                    av[u] = oka ? ld_global(JW + (a_lo + ao[u])) : 0.0;
+                    bv[u] = okb ? ld_global(JW + (b_lo + bo[u])) : 0.0;
                   }
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, sg * av[u], bv[u]);
+                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, av[u], bv[u]);
                 }
                 for (; k < cnt; ++k) {
-                  const int4 t = *reinterpret_cast<const int4*>(tp + 4 * k);
-                  const double av = oka ? JA[t.x] : 0.0;
-                  const double bv = okb ? JB[b_rhs ? t.z : t.y] : 0.0;
-                  dmma884(c0, c1, sg * av, bv);
+                  const double av = oka ? ld_global(JW + (a_lo + tp[4 * k])) : 0.0;
+                  const double bv = okb ? ld_global(JW + (b_lo + tp[4 * k + bsel])) : 0.0;
+                  dmma884(c0, c1, av, bv);
                 }
                 tp += 4 * cnt;
               } else {
@@ -446,35 +459,49 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
                   double av[4], bv[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
-                    av[u] = oka ? JA[t[u].x] : 0.0;
-                    bv[u] = okb ? JB[t[u].y] : 0.0;
+                    av[u] = oka ? ld_global(JW + (a_lo + t[u].x)) : 0.0;
+                    bv[u] = okb ? ld_global(JW + (b_lo + t[u].y)) : 0.0;
                   }
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, sg * av[u], bv[u]);
+                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, av[u], bv[u]);
                 }
                 for (; k < cnt; ++k) {
                   const int2 t = *reinterpret_cast<const int2*>(tp + 2 * k);
-                  const double av = oka ? JA[t.x] : 0.0;
-                  const double bv = okb ? JB[t.y] : 0.0;
-                  dmma884(c0, c1, sg * av, bv);
+                  const double av = oka ? ld_global(JW + (a_lo + t.x)) : 0.0;
+                  const double bv = okb ? ld_global(JW + (b_lo + t.y)) : 0.0;
+                  dmma884(c0, c1, av, bv);
                 }
                 tp += 2 * cnt;
               }
             } else {  // blocks with more than 4 rows (speed-bias chunks, IMU rows, priors): K steps of 4
               const int tw = diag ? 4 : 2;
+              const int astep = 4 * ps, bstep = b_rhs ? 4 : 4 * qs;
+              const int nstep = (m + 3) >> 2;
               for (int k = 0; k < cnt; ++k) {
-                const int ao = tp[0], bo = (b_rhs ? tp[2] : tp[1]);
-                const int bstep = b_rhs ? 1 : qs;
-                for (int e0 = 0; e0 < m; e0 += 4) {
-                  const bool ok = e0 + la < m;
-                  const double av = (ok && a_ok) ? JA[ao + e0 * ps] : 0.0;
-                  const double bv = (ok && b_any) ? JB[bo + e0 * bstep] : 0.0;
-                  dmma884(c0, c1, sg * av, bv);
+                int ao = a_lo + tp[0], bo = b_lo + (b_rhs ? tp[2] : tp[1]);
+                int left = m - la;  // rows of this lane's K slot still inside the block
+#pragma unroll 2
+                for (int e = 0; e < nstep; ++e) {
+                  const bool ok = left > 0;
+                  const double av = (ok && a_ok) ? ld_global(JW + (ao)) : 0.0;
+                  const double bv = (ok && b_any) ? ld_global(JW + (bo)) : 0.0;
+                  dmma884(c0, c1, av, bv);
+                  ao += astep;
+                  bo += bstep;
+                  left -= 4;
                 }
                 tp += tw;
               }
             }
+            if (neg) {
+              cn0 = c0;
+              cn1 = c1;
+            } else {
+              cp0 = c0;
+              cp1 = c1;
+            }
           }
+          const double c0 = cp0 - cn0, c1 = cp1 - cn1;
           // C fragment: row lb, columns 2*la, 2*la+1 of the 8x8 tile
           const int i = ti + lb;
           if (i < ps) {

@@ -266,6 +266,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   // ---- cells, Jacobian value offsets, chunks, slots
   std::vector<int32_t>*I = P->iarr;
   for (int a = 0; a < NUM_IARR; ++a) I[a].clear();
+  P->n_mma = 0;
   int n_res = 0, n_jac = 0;
   int64_t schur_doubles = 0;
   I[I_ROW_CELL].push_back(0);
@@ -429,6 +430,10 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       }
       if (diag)
         while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);  // 16-byte records need 16-byte alignment
+      {
+        const int tiles = ((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8);
+        for (const T& t : ts) P->n_mma += (int64_t)tiles * ((t.m + 3) / 4);
+      }
       const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0,
                               run_begin, (int32_t)(I[I_SRUN].size() / 2) - run_begin};
       I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);

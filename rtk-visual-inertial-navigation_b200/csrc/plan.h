@@ -20,6 +20,7 @@ struct WindowPlan {
   // algorithmic traffic of one Schur elimination on the materialised Jacobian, in doubles
   // (SURVEY.md 8d formula): J blocks at their stored size + residuals + D in, S upper + r + y out
   int64_t schur_doubles;
+  int64_t n_mma = 0;                       // tensor-core MMAs of one Schur gather pass (planning statistic)
 };
 
 // sizes (doubles) and packing of the factor constants in device layout; used at plan time and by

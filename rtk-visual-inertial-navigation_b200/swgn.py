@@ -202,12 +202,13 @@ def lib():
 
 def plan_probe(graph_p, n_parameter_head=0):
     """Host-only preprocessing of one window; returns (status, dict)."""
-    info = (i32 * 14)()
+    info = (i32 * 16)()
     st = lib().swgn_plan_probe(graph_p, n_parameter_head, info)
     keys = ["n_cols", "n_ecols", "n_e", "n_f", "n_t", "n_res", "n_rows", "n_chunks", "n_jac",
             "n_scells", "n_sterms", "n_srows"]
     d = {k: info[i] for i, k in enumerate(keys)}
     d["schur_bytes"] = (info[12] & 0xffffffff) | (info[13] << 32)
+    d["n_mma"] = info[14]
     return st, d
 
 
