@@ -550,8 +550,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
     const int32_t* row_nres = v.I(I_ROW_NRES);
     double* G = v.W(W_G);
     double* DG = v.W(W_DIAG);
+    constexpr int kHeavy = 24;  // columns with more row blocks than this are reduced by a whole warp
     for (int t = tid; t < d.n_t; t += kThreads) {
       const int col = tcol[t], k = t - col_pos[col], cs = col_size[col];
+      if (csc_ptr[col + 1] - csc_ptr[col] > kHeavy) continue;
       double g = 0.0, nrm = 0.0;
       for (int e = csc_ptr[col]; e < csc_ptr[col + 1]; ++e) {
         const int row = csc_row[e], nres = row_nres[row];
@@ -565,6 +567,41 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
       }
       G[t] = g;
       DG[t] = sqrt(fmin(fmax(nrm, b.params.min_lm_diagonal), b.params.max_lm_diagonal));
+    }
+    // heavy columns (poses seen by ~100 observations): lanes stride the row blocks, every lane
+    // accumulates all cs columns of its rows, then a deterministic shuffle reduction
+    for (int col = wid; col < d.n_cols; col += kWarps) {
+      const int e0 = csc_ptr[col], e1 = csc_ptr[col + 1];
+      if (e1 - e0 <= kHeavy) continue;
+      const int cs = col_size[col];
+      for (int k0 = 0; k0 < cs; k0 += 9) {  // up to 9 tangent columns per pass (pose 6, speed-bias 9)
+        double g[9], nrm[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] = nrm[k] = 0.0;
+        for (int e = e0 + lane; e < e1; e += 32) {
+          const int row = csc_row[e], nres = row_nres[row];
+          const double* jv = J + csc_val[e] + k0;
+          const double* rv = R + row_res[row];
+          for (int rr = 0; rr < nres; ++rr) {
+            const double r = rv[rr];
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+              if (k0 + k < cs) {
+                const double a = jv[rr * cs + k];
+                g[k] += a * r;
+                nrm[k] += a * a;
+              }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const double gs = warp_sum(g[k]), ns = warp_sum(nrm[k]);
+          if (lane == 0 && k0 + k < cs) {
+            G[col_pos[col] + k0 + k] = gs;
+            DG[col_pos[col] + k0 + k] = sqrt(fmin(fmax(ns, b.params.min_lm_diagonal), b.params.max_lm_diagonal));
+          }
+        }
+      }
     }
     __syncthreads();
     // max |x - Plus(x, -g)| (trust_region_minimizer.cc:266-287) and |x| over the reduced program
