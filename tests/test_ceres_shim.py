@@ -1,0 +1,84 @@
+"""The ceres:: source-compatibility layer (include/ceres/*.h + shim/): host bookkeeping semantics
+(CPU) and the application-style solve through ceres::Problem / ceres::Solve (GPU), compared with
+the same window solved directly through the C ABI and with the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import swgn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f64 = C.c_double
+
+
+def demo():
+    L = C.CDLL(os.path.join(ROOT, "rtk-visual-inertial-navigation_b200", "libswgn_ceres_demo.so"))
+    L.swgn_ceres_selftest.restype = C.c_int
+    L.swgn_ceres_demo_solve.restype = C.c_int
+    L.swgn_ceres_demo_solve.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int), C.POINTER(f64), C.POINTER(f64), C.c_char_p, C.c_int]
+    return L
+
+
+def test_problem_bookkeeping_semantics():
+    assert demo().swgn_ceres_selftest() == 0
+
+
+def run_demo(which, wid, export_mode, n_state, n_f):
+    state = np.zeros(n_state)
+    cost = np.zeros(2)
+    steps = (C.c_int * 2)()
+    hs = C.c_int()
+    mat = np.zeros(max(n_f * n_f, 1))
+    rhs = np.zeros(max(n_f, 1))
+    msg = C.create_string_buffer(512)
+    rc = demo().swgn_ceres_demo_solve(which, wid, export_mode, 0, state.ctypes.data_as(C.POINTER(f64)), cost.ctypes.data_as(C.POINTER(f64)),
+                                      steps, C.byref(hs), mat.ctypes.data_as(C.POINTER(f64)), rhs.ctypes.data_as(C.POINTER(f64)), msg, 512)
+    return rc, state, cost, list(steps), hs.value, mat, rhs, msg.value.decode()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,wid", [(1, 0), (2, 0), (2, 5)])
+def test_solve_through_ceres_api_equals_c_abi_and_oracle(which, wid):
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, osm = o.minimize()
+    rc, state, cost, steps, hs, mat, rhs, msg = run_demo(which, wid, 0, w.n_state, o.n_f)
+    assert rc == osm.termination_type, msg
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    # same flat graph, same device code: bit-identical to the direct C-ABI solve
+    assert np.array_equal(state, x)
+    assert cost[1] == sm.final_cost and steps == [sm.num_successful_steps, sm.num_unsuccessful_steps]
+    xo = o.state()
+    assert np.max(np.abs(state - xo) / np.maximum(1, np.abs(xo))) < 1e-6
+    if opt.n_parameter_head > 0:
+        assert hs == o.n_f
+        Lg = b.get_cholesky(0)
+        assert np.array_equal(mat[:hs * hs].reshape(hs, hs), Lg)  # lhs_out2 mirrors the device factor
+    b.close()
+
+
+@pytest.mark.gpu
+def test_export_mode_through_side_channel():
+    """is_optimize = false + parameter_head: lhs_out / rhs_out / hs_row filled, user state untouched
+    (the GlobalMarge / IntegerSolve call pattern, RVI/swf/swf_image.cpp:401-415, swf_gnss.cpp:135-162)."""
+    w = swgn.SynthWindow(2, 1)
+    opt = w.options()
+    opt.is_optimize = 0
+    opt.max_num_iterations = 1
+    o = ob.OracleSolver(w.graph_p, opt)
+    o.minimize()
+    n, oS, orr, _ = o.exports()
+    rc, state, cost, steps, hs, mat, rhs, msg = run_demo(2, 1, 1, w.n_state, o.n_f)
+    assert rc >= 0, msg
+    assert np.array_equal(state, w.state0())
+    assert hs == n
+    S = mat[:n * n].reshape(n, n)
+    assert np.linalg.norm(np.triu(S) - np.triu(oS)) / np.linalg.norm(np.triu(oS)) < 1e-12
+    assert np.linalg.norm(rhs[:n] - orr) / np.linalg.norm(orr) < 1e-9
