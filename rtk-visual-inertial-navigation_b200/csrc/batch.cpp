@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -55,6 +56,7 @@ struct swgn_batch {
   int64_t* d_state_off = nullptr;
   double* h_stage = nullptr;      // pinned
   double* h_cpool = nullptr;      // pinned staging of the factor constants (update_inputs)
+  long long* d_debug = nullptr;   // SWGN_DEBUG_TIMELINE=1: per-window phase timestamps of k_schur
   size_t ipool_n = 0, cpool_n = 0, wpool_n = 0;
   DeviceBatch db;
   std::vector<TRState> h_state;
@@ -108,6 +110,7 @@ void swgn_batch_destroy(swgn_batch* b) {
   cudaFree(b->d_counters);
   cudaFree(b->d_stage);
   cudaFree(b->d_state_off);
+  cudaFree(b->d_debug);
   if (b->h_counters) cudaFreeHost(b->h_counters);
   if (b->h_stage) cudaFreeHost(b->h_stage);
   if (b->h_cpool) cudaFreeHost(b->h_cpool);
@@ -246,6 +249,11 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   db.max_nf = max_nf;
   db.max_prior_n = max_prior_n;
   db.keep_copy = 0;
+  if (std::getenv("SWGN_DEBUG_TIMELINE")) {
+    CB(cudaMalloc(&b->d_debug, sizeof(long long) * 8 * n_windows));
+    CB(cudaMemset(b->d_debug, 0, sizeof(long long) * 8 * n_windows));
+  }
+  db.debug = b->d_debug;
   SolverParams& P = db.params;
   P.max_num_iterations = options->max_num_iterations;
   P.max_num_consecutive_invalid_steps = options->max_num_consecutive_invalid_steps;
@@ -357,6 +365,13 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(b->stream));
   if (bytes_h2d) *bytes_h2d = (int64_t)(sizeof(double) * (b->cpool_n + (size_t)ns));
+  return SWGN_OK;
+}
+
+// development aid: phase timestamps (clock64) of the last k_schur launch, 8 per window
+swgn_status swgn_batch_debug_timeline(swgn_batch* b, int64_t* out) {
+  if (!b || !b->d_debug || !out) return fail(SWGN_ERR_INVALID, "timeline not enabled (SWGN_DEBUG_TIMELINE=1)");
+  CU(cudaMemcpy(out, b->d_debug, sizeof(long long) * 8 * b->n, cudaMemcpyDeviceToHost));
   return SWGN_OK;
 }
 

@@ -50,6 +50,9 @@ enum IArr {
   I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
   I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
   I_SROW,           // [n_srows] rows (with f-cells) of the simple chunks: one thread each in phase 1b
+  I_ECELL,          // [n_ecells * 8] raw chunk products of the 4..16-dim e-blocks, same record as I_SCELL
+                    //                 with field 2 = output offset (W_EFAC for the [E'E | E'b] cell, W_EBUF for E'F)
+  I_ECELL_G,        // [n_ecells] W_EBUF offset of E'b for the diagonal cell, -1 otherwise
   I_PROJ,           // [n_proj * 8]  state_off[3], jac_off[3], res_off, 0
   I_IMU,            // [n_imu * 12]  state_off[4], jac_off[4], res_off, 0,0,0
   I_GNSS,           // [n_gnss * 8]  kind, state_off[3], jac_off[3], res_off
@@ -111,7 +114,7 @@ enum { MAX_WARP_E = 16, MAX_COL_SIZE = 63 };
 struct WinDesc {
   int32_t n_state, n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_cells, n_chunks, n_slots;
   int32_t n_jac, n_ebuf, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, n_efac, n_head;
-  int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, pad0;
+  int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, n_ecells;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

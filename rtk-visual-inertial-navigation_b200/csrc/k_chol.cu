@@ -283,12 +283,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
         if (lane < nb) zv[k0 + lane] = wl;
       }
       __syncthreads();
-      {  // w_i -= U[i, k0:k0+nb] z[k0:k0+nb] for the rows above: one warp per row, coalesced
+      {  // w_i -= U[i, k0:k0+nb] z[k0:k0+nb] for the rows above: one warp per row (coalesced 256 B
+         // row segments), four rows in flight per warp
         const double zl = lane < nb ? zv[k0 + lane] : 0.0;
-        for (int i = wid; i < k0; i += kWarps) {
-          const double u = lane < nb ? S[(size_t)i * ld + k0 + lane] : 0.0;
-          const double s = warp_sum(u * zl);
-          if (lane == 0) wv[i] -= s;
+        for (int i0 = 4 * wid; i0 < k0; i0 += 4 * kWarps) {
+          double u[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) u[q] = (lane < nb && i0 + q < k0) ? S[(size_t)(i0 + q) * ld + k0 + lane] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double s = warp_sum(u[q] * zl);
+            if (lane == 0 && i0 + q < k0) wv[i0 + q] -= s;
+          }
         }
       }
       __syncthreads();

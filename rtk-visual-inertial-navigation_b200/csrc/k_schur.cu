@@ -22,8 +22,13 @@
 namespace swgn {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;            // k_backsub
 constexpr int kWarps = kThreads / 32;
+// k_schur runs one large CTA per window: the same number of warps per SM, but far fewer windows in
+// flight at a time, so the windows being worked on (JW + S, ~1.7 MB each) stay inside the 126 MB L2
+constexpr int kSchurThreads = 256;
+constexpr int kSchurWarps = kSchurThreads / 32;
+constexpr int kChunkWarps = 8;           // warps with a shared-memory scratch for the 4..16-dim e-blocks
 
 // D(8x8) += A(8x4, row) * B(4x8, col); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
 // D[lane>>2][2*(lane&3) + {0,1}]
@@ -39,6 +44,130 @@ __device__ __forceinline__ double ld_global(const double* p) {
   double v;
   asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
+}
+
+// Bulk L2 prefetch (TMA engine, no registers, no completion tracking): pulls a byte range into L2
+// ahead of the demand loads.  J and the residuals were written by k_eval for the whole batch and
+// have long left L2 when k_schur starts, so every first touch would otherwise pay DRAM latency
+// inside a chain of dependent index -> operand loads.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_range(const void* base, size_t bytes, int tid, int nthreads) {
+  constexpr size_t kChunk = 4096;
+  const char* p = reinterpret_cast<const char*>(base);
+  const size_t aligned = bytes & ~size_t(15);
+  for (size_t off = (size_t)tid * kChunk; off < aligned; off += (size_t)nthreads * kChunk)
+    prefetch_l2_bulk(p + off, (unsigned)((aligned - off) < kChunk ? (aligned - off) : kChunk));
+}
+
+// N gather terms of one run: operand offsets come by shuffle from the lanes that fetched the
+// descriptors, all 2N operand loads are issued before the first MMA, two accumulator pairs
+// alternate so that consecutive MMAs do not depend on each other.
+template <int N>
+__device__ __forceinline__ void gather_batch(const double* JW, int my_a, int my_b, int my_b2, int k0, int diag, bool b_rhs,
+                                             bool oka, bool okb, int a_lo, int b_lo, double& c0, double& c1, double& d0,
+                                             double& d1) {
+  double av[N], bv[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const int ao = __shfl_sync(0xffffffffu, my_a, k0 + u);
+    int bo = __shfl_sync(0xffffffffu, my_b, k0 + u);
+    if (diag) {  // warp-uniform
+      const int bo2 = __shfl_sync(0xffffffffu, my_b2, k0 + u);
+      if (b_rhs) bo = bo2;
+    }
+    av[u] = oka ? ld_global(JW + (a_lo + ao)) : 0.0;
+    bv[u] = okb ? ld_global(JW + (b_lo + bo)) : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    if (u & 1) dmma884(d0, d1, av[u], bv[u]);
+    else dmma884(c0, c1, av[u], bv[u]);
+  }
+}
+
+// One 8x8 tile (rows ti.., columns tj..) of a gathered block cell: C = sum_t (+/-) A_t' B_t over the
+// cell's runs of terms.  Returns the lane's two C fragment values (row lane>>2, columns
+// 2*(lane&3), +1).  `diag` cells carry one extra B column (index qs) fed from the m-vector b2.
+__device__ __forceinline__ void gather_tile(const double* JW, const int32_t* srun, const int32_t* sterm, const int32_t* sc,
+                                            int ti, int tj, int lane, double& out0, double& out1) {
+  const int la = lane & 3, lb = lane >> 2;
+  const int ps = sc[0], qs = sc[1];
+  const int diag = sc[5] & 1;
+  const int ai = ti + lb, bj = tj + lb;
+  const bool a_ok = ai < ps, b_ok = bj < qs, b_rhs = diag && bj == qs;
+  // lane offsets inside a 4-row slab (32-bit: one IMAD.WIDE per operand address)
+  const int a_lo = a_ok ? la * ps + ai : 0;
+  const int b_lo = b_rhs ? la : (b_ok ? la * qs + bj : 0);
+  const bool b_any = b_ok || b_rhs;
+  // additions and subtractions accumulate separately: no per-term sign multiply
+  double cp0 = 0.0, cp1 = 0.0, cn0 = 0.0, cn1 = 0.0;
+  const int32_t* tp = sterm + sc[3];
+  for (int run = sc[6]; run < sc[6] + sc[7]; ++run) {
+    const int cnt = srun[2 * run], m = srun[2 * run + 1] >> 1;
+    const bool neg = srun[2 * run + 1] & 1;
+    double c0 = neg ? cn0 : cp0, c1 = neg ? cn1 : cp1;
+    double d0 = 0.0, d1 = 0.0;
+    if (m <= 4) {
+      const bool oka = a_ok && la < m, okb = b_any && la < m;
+      const int tw = diag ? 4 : 2;
+      // descriptors: one coalesced fetch per 32 terms (lane l holds term tb + l), operands:
+      // eight terms = sixteen independent loads in flight per lane, then the eight MMAs
+      for (int tb = 0; tb < cnt; tb += 32) {
+        const int nn = min(32, cnt - tb);
+        int my_a = 0, my_b = 0, my_b2 = 0;
+        if (lane < nn) {
+          const int32_t* t = tp + tw * (tb + lane);
+          my_a = t[0];
+          my_b = t[1];
+          if (diag) my_b2 = t[2];
+        }
+        int k0 = 0;
+        for (; k0 + 8 <= nn; k0 += 8) gather_batch<8>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+        if (k0 + 4 <= nn) {
+          gather_batch<4>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+          k0 += 4;
+        }
+        if (k0 + 2 <= nn) {
+          gather_batch<2>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+          k0 += 2;
+        }
+        if (k0 < nn) gather_batch<1>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+      }
+      tp += tw * cnt;
+    } else {  // blocks with more than 4 rows (speed-bias chunks, IMU rows, priors): K steps of 4
+      const int tw = diag ? 4 : 2;
+      const int astep = 4 * ps, bstep = b_rhs ? 4 : 4 * qs;
+      const int nstep = (m + 3) >> 2;
+      for (int k = 0; k < cnt; ++k) {
+        int ao = a_lo + tp[0], bo = b_lo + (b_rhs ? tp[2] : tp[1]);
+        int left = m - la;  // rows of this lane's K slot still inside the block
+#pragma unroll 2
+        for (int e = 0; e < nstep; ++e) {
+          const bool ok = left > 0;
+          const double av = (ok && a_ok) ? ld_global(JW + (ao)) : 0.0;
+          const double bv = (ok && b_any) ? ld_global(JW + (bo)) : 0.0;
+          dmma884(c0, c1, av, bv);
+          ao += astep;
+          bo += bstep;
+          left -= 4;
+        }
+        tp += tw;
+      }
+    }
+    c0 += d0;
+    c1 += d1;
+    if (neg) {
+      cn0 = c0;
+      cn1 = c1;
+    } else {
+      cp0 = c0;
+      cp1 = c1;
+    }
+  }
+  out0 = cp0 - cn0;
+  out1 = cp1 - cn1;
 }
 
 // ---- phase 1, small e-blocks (1..3): one thread per chunk, everything in registers -----------
@@ -261,36 +390,16 @@ __device__ void chunk_warp(const Win& v, int chunk, const double* lmd, double* s
     const double dd = (lmd && i == j) ? lmd[epos + i] : 0.0;
     ete[i * MAX_WARP_E + j] = dd * dd;
   }
-  for (int k = lane; k < nbuf; k += 32) buf[k] = 0.0;
   __syncwarp();
-  for (int r = chunk_row[chunk]; r < chunk_row[chunk + 1]; ++r) {
-    const int c0 = row_cell[r], c1 = row_cell[r + 1];
-    const double* E = J + cell_val[c0];
-    const double* bb = R + row_res[r];
-    const int nres = row_nres[r];
-    for (int k = lane; k < es * es; k += 32) {  // E'E
+  // raw products [E'E | E'b] (W_EFAC / g slot) and E'F_f (slot blocks) were gathered by the tensor-core
+  // pass of phase 1a (e-cells); bring them into the warp's scratch and add D^2
+  {
+    const double* rawfac = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+    for (int k = lane; k < es * es; k += 32) {
       const int i = k / es, j = k - i * es;
-      if (j < i) continue;
-      double s = 0.0;
-      for (int rr = 0; rr < nres; ++rr) s += E[rr * es + i] * E[rr * es + j];
-      ete[i * MAX_WARP_E + j] += s;
+      if (j >= i) ete[i * MAX_WARP_E + j] += rawfac[k];
     }
-    if (lane < es) {  // E'b
-      double s = 0.0;
-      for (int rr = 0; rr < nres; ++rr) s += E[rr * es + lane] * bb[rr];
-      buf[gofs - ebase + lane] += s;
-    }
-    for (int c = c0 + 1; c < c1; ++c) {  // E'F
-      const int fs = col_size[cell_col[c]];
-      const double* F = J + cell_val[c];
-      double* Bf = buf + (cell_slot[c] - ebase);
-      for (int k = lane; k < es * fs; k += 32) {
-        const int i = k / fs, j = k - i * fs;
-        double s = 0.0;
-        for (int rr = 0; rr < nres; ++rr) s += E[rr * es + i] * F[rr * fs + j];
-        Bf[k] += s;
-      }
-    }
+    for (int k = lane; k < nbuf; k += 32) buf[k] = EB[ebase + k];
     __syncwarp();
   }
   // Cholesky of ete (upper part filled) -> lower L in place (row-major [i][j], j <= i)
@@ -346,9 +455,9 @@ __device__ __forceinline__ void chunk_dispatch(const Win& v, int chunk, const do
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_window) {
+__global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int only_window) {
   __shared__ WinDesc sd;
-  extern __shared__ double dyn[];  // kWarps * max_wbuf doubles
+  extern __shared__ double dyn[];  // kChunkWarps * max_wbuf doubles
   const int w = only_window >= 0 ? only_window : blockIdx.x;
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
@@ -358,29 +467,76 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
   const double* lmd = v.W(W_LMD);
   double* S = v.W(W_S);
   const int nf = d.n_f, ld = d.ld;
+  long long* dbg = b.debug ? b.debug + 8 * (size_t)w : nullptr;
+#define SWGN_STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+  SWGN_STAMP(0);
+  // start the DRAM -> L2 transfer of everything this CTA will read: Jacobian + residuals, the
+  // index tables of the window (contiguous in ipool), the LM diagonal
+  prefetch_range(v.W(W_JAC), sizeof(double) * (size_t)d.n_jac, tid, kSchurThreads);
+  prefetch_range(v.W(W_RES), sizeof(double) * (size_t)d.n_res, tid, kSchurThreads);
+  prefetch_range(v.I(I_ROW_RES), sizeof(int32_t) * (size_t)(d.ioff[I_PROJ] - d.ioff[I_ROW_RES]), tid, kSchurThreads);
+  prefetch_range(lmd, sizeof(double) * (size_t)d.n_t, tid, kSchurThreads);
 
   // phase 0: clear the upper triangle and the rhs column (cells never touched must read as 0)
-  for (int i = wid; i < nf; i += kWarps) {
+  for (int i = wid; i < nf; i += kSchurWarps) {
     double* row = S + (size_t)i * ld;
     for (int j = i + lane; j <= nf; j += 32) row[j] = 0.0;
   }
-  // phase 1a: chunk factors (and the W buffers of the chunks that are not row-parallel)
+  SWGN_STAMP(1);
+  // phase 1a: factors of the small chunks (one thread each; W buffers too unless row-parallel) and,
+  // on the tensor pipe, the raw products E'[E | b | F] of the larger e-blocks (one warp per e-cell)
   {
     const int32_t* tch = v.I(I_TCHUNK);
-    for (int k = tid; k < d.n_tchunks; k += kThreads) chunk_dispatch(v, tch[k], lmd);
+    for (int k = tid; k < d.n_tchunks; k += kSchurThreads) chunk_dispatch(v, tch[k], lmd);
+    const int32_t* ecell = v.I(I_ECELL);
+    const int32_t* ecell_g = v.I(I_ECELL_G);
+    const int32_t* srun = v.I(I_SRUN);
+    const int32_t* sterm = v.I(I_STERM);
+    const double* JWc = v.W(W_JAC);
+    asm volatile("" : "+l"(JWc));
+    double* EF = v.W(W_EFAC);
+    double* EBw = v.W(W_EBUF);
+    const int la = lane & 3, lb = lane >> 2;
+    for (int cell = wid; cell < d.n_ecells; cell += kSchurWarps) {
+      const int32_t* sc = ecell + 8 * cell;
+      const int ps = sc[0], qs = sc[1], out = sc[2], diag = sc[5] & 1;
+      const int nq = qs + diag;
+      for (int ti = 0; ti < ps; ti += 8)
+        for (int tj = 0; tj < nq; tj += 8) {
+          if (diag && tj + 7 < ti) continue;  // E'E: upper triangle only
+          double c0, c1;
+          gather_tile(JWc, srun, sterm, sc, ti, tj, lane, c0, c1);
+          const int i = ti + lb;
+          if (i < ps) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = tj + 2 * la + h;
+              const double val = h ? c1 : c0;
+              if (j < qs) (diag ? EF : EBw)[out + i * qs + j] = val;
+              else if (diag && j == qs) EBw[ecell_g[cell] + i] = val;
+            }
+          }
+        }
+    }
+  }
+  SWGN_STAMP(2);
+  __syncthreads();
+  SWGN_STAMP(3);
+  // phase 1b: factor + forward substitution of the larger e-blocks (one warp per chunk, shared-memory
+  // scratch), and the W blocks of the simple chunks, one thread per row (consecutive threads read
+  // consecutive row blocks of J)
+  {
     const int32_t* wch = v.I(I_WCHUNK);
     double* sm = dyn + (size_t)wid * b.max_wbuf;
-    for (int k = wid; k < d.n_wchunks; k += kWarps) chunk_warp(v, wch[k], lmd, sm);
+    if (wid < kChunkWarps)
+      for (int k = wid; k < d.n_wchunks; k += kChunkWarps) chunk_warp(v, wch[k], lmd, sm);
   }
-  __syncthreads();
-  // phase 1b: W blocks of the simple chunks, one thread per row (consecutive threads read
-  // consecutive row blocks of J)
   {
     const int32_t* srow = v.I(I_SROW);
     const int32_t* row_chunk = v.I(I_ROW_CHUNK);
     const int32_t* chunk_ecol = v.I(I_CHUNK_ECOL);
     const int32_t* col_size = v.I(I_COL_SIZE);
-    for (int k = tid; k < d.n_srows; k += kThreads) {
+    for (int k = tid; k < d.n_srows; k += kSchurThreads) {
       const int r = srow[k], chunk = row_chunk[r];
       const int es = col_size[chunk_ecol[chunk]];
       if (es == 3) row_w<3>(v, r, chunk);
@@ -389,6 +545,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
     }
   }
   __syncthreads();
+  SWGN_STAMP(4);
   // phase 2: one warp per block cell.  S_pq = sum_t (+/-) A_t' B_t is a skinny GEMM whose K
   // dimension is the stack of the gathered blocks; every term feeds one FP64 tensor-core MMA
   // (m8n8k4: A_t' is the 8x4 operand, B_t the 4x8 operand, rows beyond m masked to zero), lanes
@@ -403,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
     const double* JW = v.W(W_JAC);
     asm volatile("" : "+l"(JW));  // keep the window base in a register pair: operand address = one IMAD.WIDE
     const int la = lane & 3, lb = lane >> 2;
-    for (int cell = wid; cell < d.n_scells; cell += kWarps) {
+    for (int cell = wid; cell < d.n_scells; cell += kSchurWarps) {
       const int32_t* sc = scell + 8 * cell;
       const int ps = sc[0], qs = sc[1], soff = sc[2];
       const int diag = sc[5] & 1;
@@ -411,97 +568,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
       const int frow = soff / ld;  // first S row of block p
       for (int ti = 0; ti < ps; ti += 8)
         for (int tj = 0; tj < nq; tj += 8) {
-          const int ai = ti + lb, bj = tj + lb;
-          const bool a_ok = ai < ps, b_ok = bj < qs, b_rhs = diag && bj == qs;
-          // lane offsets inside a 4-row slab (32-bit: one IMAD.WIDE per operand address)
-          const int a_lo = a_ok ? la * ps + ai : 0;
-          const int b_lo = b_rhs ? la : (b_ok ? la * qs + bj : 0);
-          const bool b_any = b_ok || b_rhs;
-          // additions and subtractions accumulate separately: no per-term sign multiply
-          double cp0 = 0.0, cp1 = 0.0, cn0 = 0.0, cn1 = 0.0;
-          const int32_t* tp = sterm + sc[3];
-          for (int run = sc[6]; run < sc[6] + sc[7]; ++run) {
-            const int cnt = srun[2 * run], m = srun[2 * run + 1] >> 1;
-            const bool neg = srun[2 * run + 1] & 1;
-            double c0 = neg ? cn0 : cp0, c1 = neg ? cn1 : cp1;
-            if (m <= 4) {
-              const bool oka = a_ok && la < m, okb = b_any && la < m;
-              int k = 0;
-              if (diag) {
-                const int bsel = b_rhs ? 2 : 1;
-                for (; k + 4 <= cnt; k += 4) {
-                  int ao[4], bo[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    ao[u] = tp[4 * (k + u)];
-                    bo[u] = tp[4 * (k + u) + bsel];
-                  }
-                  double av[4], bv[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    av[u] = oka ? ld_global(JW + (a_lo + ao[u])) : 0.0;
-                    bv[u] = okb ? ld_global(JW + (b_lo + bo[u])) : 0.0;
-                  }
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, av[u], bv[u]);
-                }
-                for (; k < cnt; ++k) {
-                  const double av = oka ? ld_global(JW + (a_lo + tp[4 * k])) : 0.0;
-                  const double bv = okb ? ld_global(JW + (b_lo + tp[4 * k + bsel])) : 0.0;
-                  dmma884(c0, c1, av, bv);
-                }
-                tp += 4 * cnt;
-              } else {
-                for (; k + 4 <= cnt; k += 4) {
-                  int2 t[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const int2*>(tp + 2 * (k + u));
-                  double av[4], bv[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    av[u] = oka ? ld_global(JW + (a_lo + t[u].x)) : 0.0;
-                    bv[u] = okb ? ld_global(JW + (b_lo + t[u].y)) : 0.0;
-                  }
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) dmma884(c0, c1, av[u], bv[u]);
-                }
-                for (; k < cnt; ++k) {
-                  const int2 t = *reinterpret_cast<const int2*>(tp + 2 * k);
-                  const double av = oka ? ld_global(JW + (a_lo + t.x)) : 0.0;
-                  const double bv = okb ? ld_global(JW + (b_lo + t.y)) : 0.0;
-                  dmma884(c0, c1, av, bv);
-                }
-                tp += 2 * cnt;
-              }
-            } else {  // blocks with more than 4 rows (speed-bias chunks, IMU rows, priors): K steps of 4
-              const int tw = diag ? 4 : 2;
-              const int astep = 4 * ps, bstep = b_rhs ? 4 : 4 * qs;
-              const int nstep = (m + 3) >> 2;
-              for (int k = 0; k < cnt; ++k) {
-                int ao = a_lo + tp[0], bo = b_lo + (b_rhs ? tp[2] : tp[1]);
-                int left = m - la;  // rows of this lane's K slot still inside the block
-#pragma unroll 2
-                for (int e = 0; e < nstep; ++e) {
-                  const bool ok = left > 0;
-                  const double av = (ok && a_ok) ? ld_global(JW + (ao)) : 0.0;
-                  const double bv = (ok && b_any) ? ld_global(JW + (bo)) : 0.0;
-                  dmma884(c0, c1, av, bv);
-                  ao += astep;
-                  bo += bstep;
-                  left -= 4;
-                }
-                tp += tw;
-              }
-            }
-            if (neg) {
-              cn0 = c0;
-              cn1 = c1;
-            } else {
-              cp0 = c0;
-              cp1 = c1;
-            }
-          }
-          const double c0 = cp0 - cn0, c1 = cp1 - cn1;
+          double c0, c1;
+          gather_tile(JW, srun, sterm, sc, ti, tj, lane, c0, c1);
           // C fragment: row lb, columns 2*la, 2*la+1 of the 8x8 tile
           const int i = ti + lb;
           if (i < ps) {
@@ -523,10 +591,20 @@ __global__ void __launch_bounds__(kThreads, 3) k_schur(DeviceBatch b, int only_w
         }
     }
   }
+  SWGN_STAMP(5);
+  if (dbg) {
+    __syncthreads();
+    SWGN_STAMP(6);
+    if (tid == 0) {
+      unsigned smid;
+      asm("mov.u32 %0, %smid;" : "=r"(smid));
+      dbg[7] = smid;
+    }
+  }
   if (b.keep_copy) {
     __syncthreads();
     double* SC = v.W(W_SCOPY);
-    for (int k = tid; k < nf * ld; k += kThreads) SC[k] = S[k];
+    for (int k = tid; k < nf * ld; k += kSchurThreads) SC[k] = S[k];
   }
   if (tid == 0) {
     st->num_linear_solves += 1;
@@ -661,8 +739,8 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
 
 void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
-  const size_t dyn = sizeof(double) * (size_t)kWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
-  k_schur<<<grid, kThreads, dyn, s>>>(b, only_window);
+  const size_t dyn = sizeof(double) * (size_t)kChunkWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  k_schur<<<grid, kSchurThreads, dyn, s>>>(b, only_window);
 }
 void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
@@ -671,7 +749,7 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
 
 cudaError_t configure_schur(const DeviceBatch& b) {
   static size_t granted[64] = {0};
-  const size_t dyn = sizeof(double) * (size_t)kWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  const size_t dyn = sizeof(double) * (size_t)kChunkWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;
   int dev = 0;
   cudaGetDevice(&dev);

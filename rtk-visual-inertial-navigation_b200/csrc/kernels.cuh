@@ -21,6 +21,7 @@ struct DeviceBatch {
   int max_nf;            // max reduced-system size
   int max_prior_n;
   int keep_copy;         // copy S|rhs to W_SCOPY before factorising (staged test entry point)
+  long long* debug;      // optional [n_windows * 8] phase timestamps of k_schur (SWGN_DEBUG_TIMELINE=1), else null
 };
 
 enum EvalMode { EVAL_INIT = 0, EVAL_ACCEPTED = 1, EVAL_CANDIDATE = 2, EVAL_FORCE = 3 };

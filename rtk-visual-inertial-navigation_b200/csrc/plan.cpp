@@ -447,6 +447,59 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       }
     }
   }
+  // ---- raw products of the larger e-blocks (4..16 tangent dims: the speed-bias blocks), gathered
+  // by the same tensor-core code as the reduced system: per chunk one "diagonal" cell
+  // [E'E | E'b] (es x es+1, written to W_EFAC / the chunk's g slot) and one cell E'F_f per slot
+  // (es x fs, written to the slot's W_EBUF block); terms = the rows of the chunk.
+  {
+    struct T {
+      uint32_t a, b, m, b2;
+    };
+    const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
+    auto emit = [&](int ps, int qs, int out, bool diag, int gout, std::vector<T>& ts) {
+      std::stable_sort(ts.begin(), ts.end(), [](const T& x, const T& y) { return x.m < y.m; });
+      const int run_begin = (int)(I[I_SRUN].size() / 2);
+      for (size_t k = 0; k < ts.size();) {
+        size_t k1 = k;
+        while (k1 < ts.size() && ts[k1].m == ts[k].m) ++k1;
+        I[I_SRUN].push_back((int32_t)(k1 - k));
+        I[I_SRUN].push_back((int32_t)(ts[k].m << 1));
+        k = k1;
+      }
+      if (diag)
+        while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);
+      const int32_t rec[8] = {ps, qs, out, (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, run_begin,
+                              (int32_t)(I[I_SRUN].size() / 2) - run_begin};
+      I[I_ECELL].insert(I[I_ECELL].end(), rec, rec + 8);
+      I[I_ECELL_G].push_back(gout);
+      for (const T& t : ts) {
+        I[I_STERM].push_back((int32_t)t.a);
+        I[I_STERM].push_back((int32_t)t.b);
+        if (diag) {
+          I[I_STERM].push_back((int32_t)t.b2);
+          I[I_STERM].push_back(0);
+        }
+        P->n_mma += (int64_t)((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8) * ((t.m + 3) / 4);
+      }
+    };
+    for (int wc = 0; wc < (int)I[I_WCHUNK].size(); ++wc) {
+      const int ch = I[I_WCHUNK][wc];
+      const int es = col_size[I[I_CHUNK_ECOL][ch]];
+      std::vector<T> diag_terms;
+      std::map<int, std::vector<T>> slot_terms;  // slot buffer offset -> rows
+      for (int r = I[I_CHUNK_ROW][ch]; r < I[I_CHUNK_ROW][ch + 1]; ++r) {
+        const uint32_t nres = (uint32_t)I[I_ROW_NRES][r];
+        const int c0 = I[I_ROW_CELL][r];
+        const uint32_t eoff = (uint32_t)I[I_CELL_VAL][c0];
+        diag_terms.push_back({eoff, eoff, nres, res_base + (uint32_t)I[I_ROW_RES][r]});
+        for (int c = c0 + 1; c < I[I_ROW_CELL][r + 1]; ++c)
+          slot_terms[I[I_CELL_SLOT][c]].push_back({eoff, (uint32_t)I[I_CELL_VAL][c], nres, 0u});
+      }
+      emit(es, es, I[I_CHUNK_FAC][ch], true, I[I_CHUNK_G][ch], diag_terms);
+      for (int s = I[I_CHUNK_SLOT][ch]; s < I[I_CHUNK_SLOT][ch + 1]; ++s)
+        emit(es, col_size[I[I_SLOT_COL][s]], I[I_SLOT_BUF][s], false, -1, slot_terms[I[I_SLOT_BUF][s]]);
+    }
+  }
   // ---- row-parallel part of phase 1: rows of "simple" small chunks (every slot fed by exactly one
   // row, e.g. a landmark seen once per keyframe) compute their W block independently
   {
@@ -580,6 +633,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_scells = (int)(I[I_SCELL].size() / 8);
   d.n_sterms = (int)I[I_STERM].size();
   d.n_srows = (int)I[I_SROW].size();
+  d.n_ecells = (int)I[I_ECELL_G].size();
   d.max_wbuf = max_wbuf;
   d.max_prior_n = 0;
   for (int i = 0; i < g->n_prior; ++i) d.max_prior_n = std::max(d.max_prior_n, g->prior_n[i]);
