@@ -26,9 +26,27 @@ constexpr int kThreads = 256;            // k_backsub
 constexpr int kWarps = kThreads / 32;
 // k_schur runs one large CTA per window: the same number of warps per SM, but far fewer windows in
 // flight at a time, so the windows being worked on (JW + S, ~1.7 MB each) stay inside the 126 MB L2
+// k_schur: a thread-block CLUSTER per window.  The per-window working set (JW + S + index tables,
+// ~2 MB) is far larger than what one SM's worth of the 126 MB L2 can keep while hundreds of
+// windows are in flight, and the phases are latency bound; eight CTAs on eight SMs work through one
+// window eight times faster, so only a few dozen windows are in flight and their data stays in L2
+// between the phases.
 constexpr int kSchurThreads = 256;
 constexpr int kSchurWarps = kSchurThreads / 32;
-constexpr int kChunkWarps = 8;           // warps with a shared-memory scratch for the 4..16-dim e-blocks
+constexpr int kCluster = 1;
+constexpr int kClusterThreads = kCluster * kSchurThreads;
+constexpr int kClusterWarps = kCluster * kSchurWarps;
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// barrier over all threads of the cluster; release/acquire at cluster scope orders the global
+// writes of one phase before the reads of the next
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // D(8x8) += A(8x4, row) * B(4x8, col); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
 // D[lane>>2][2*(lane&3) + {0,1}]
@@ -61,30 +79,53 @@ __device__ __forceinline__ void prefetch_range(const void* base, size_t bytes, i
     prefetch_l2_bulk(p + off, (unsigned)((aligned - off) < kChunk ? (aligned - off) : kChunk));
 }
 
-// N gather terms of one run: operand offsets come by shuffle from the lanes that fetched the
-// descriptors, all 2N operand loads are issued before the first MMA, two accumulator pairs
-// alternate so that consecutive MMAs do not depend on each other.
-template <int N>
-__device__ __forceinline__ void gather_batch(const double* JW, int my_a, int my_b, int my_b2, int k0, int diag, bool b_rhs,
-                                             bool oka, bool okb, int a_lo, int b_lo, double& c0, double& c1, double& d0,
-                                             double& d1) {
+// N gather terms of one run, straight-line: the N descriptors are loaded by every lane from the same
+// address (broadcast, one cache line), all 2N operand loads are issued before the first MMA, and two
+// accumulator pairs alternate so that consecutive MMAs do not depend on each other.  No shuffles and
+// no branches inside: the scheduler sees one basic block with N independent load chains.
+template <int N, bool DIAG>
+__device__ __forceinline__ void gather_batch(const double* JW, const int32_t* tp, bool b_rhs, bool oka, bool okb, int a_lo,
+                                             int b_lo, double& c0, double& c1, double& d0, double& d1) {
+  int ao[N], bo[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    if (DIAG) {
+      const int4 t = *reinterpret_cast<const int4*>(tp + 4 * u);
+      ao[u] = t.x;
+      bo[u] = b_rhs ? t.z : t.y;
+    } else {
+      const int2 t = *reinterpret_cast<const int2*>(tp + 2 * u);
+      ao[u] = t.x;
+      bo[u] = t.y;
+    }
+  }
   double av[N], bv[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) {
-    const int ao = __shfl_sync(0xffffffffu, my_a, k0 + u);
-    int bo = __shfl_sync(0xffffffffu, my_b, k0 + u);
-    if (diag) {  // warp-uniform
-      const int bo2 = __shfl_sync(0xffffffffu, my_b2, k0 + u);
-      if (b_rhs) bo = bo2;
-    }
-    av[u] = oka ? ld_global(JW + (a_lo + ao)) : 0.0;
-    bv[u] = okb ? ld_global(JW + (b_lo + bo)) : 0.0;
+    av[u] = oka ? ld_global(JW + (a_lo + ao[u])) : 0.0;
+    bv[u] = okb ? ld_global(JW + (b_lo + bo[u])) : 0.0;
   }
 #pragma unroll
   for (int u = 0; u < N; ++u) {
     if (u & 1) dmma884(d0, d1, av[u], bv[u]);
     else dmma884(c0, c1, av[u], bv[u]);
   }
+}
+template <bool DIAG>
+__device__ __forceinline__ void gather_run(const double* JW, const int32_t* tp, int cnt, bool b_rhs, bool oka, bool okb,
+                                           int a_lo, int b_lo, double& c0, double& c1, double& d0, double& d1) {
+  constexpr int TW = DIAG ? 4 : 2;
+  int k = 0;
+  for (; k + 8 <= cnt; k += 8) gather_batch<8, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+  if (k + 4 <= cnt) {
+    gather_batch<4, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+    k += 4;
+  }
+  if (k + 2 <= cnt) {
+    gather_batch<2, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+    k += 2;
+  }
+  if (k < cnt) gather_batch<1, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
 }
 
 // One 8x8 tile (rows ti.., columns tj..) of a gathered block cell: C = sum_t (+/-) A_t' B_t over the
@@ -112,29 +153,8 @@ __device__ __forceinline__ void gather_tile(const double* JW, const int32_t* sru
     if (m <= 4) {
       const bool oka = a_ok && la < m, okb = b_any && la < m;
       const int tw = diag ? 4 : 2;
-      // descriptors: one coalesced fetch per 32 terms (lane l holds term tb + l), operands:
-      // eight terms = sixteen independent loads in flight per lane, then the eight MMAs
-      for (int tb = 0; tb < cnt; tb += 32) {
-        const int nn = min(32, cnt - tb);
-        int my_a = 0, my_b = 0, my_b2 = 0;
-        if (lane < nn) {
-          const int32_t* t = tp + tw * (tb + lane);
-          my_a = t[0];
-          my_b = t[1];
-          if (diag) my_b2 = t[2];
-        }
-        int k0 = 0;
-        for (; k0 + 8 <= nn; k0 += 8) gather_batch<8>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-        if (k0 + 4 <= nn) {
-          gather_batch<4>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-          k0 += 4;
-        }
-        if (k0 + 2 <= nn) {
-          gather_batch<2>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-          k0 += 2;
-        }
-        if (k0 < nn) gather_batch<1>(JW, my_a, my_b, my_b2, k0, diag, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-      }
+      if (diag) gather_run<true>(JW, tp, cnt, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
+      else gather_run<false>(JW, tp, cnt, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
       tp += tw * cnt;
     } else {  // blocks with more than 4 rows (speed-bias chunks, IMU rows, priors): K steps of 4
       const int tw = diag ? 4 : 2;
@@ -455,30 +475,32 @@ __device__ __forceinline__ void chunk_dispatch(const Win& v, int chunk, const do
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int only_window) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int only_window) {
   __shared__ WinDesc sd;
   extern __shared__ double dyn[];  // kChunkWarps * max_wbuf doubles
-  const int w = only_window >= 0 ? only_window : blockIdx.x;
+  const int w = only_window >= 0 ? only_window : blockIdx.x / kCluster;
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
   const Win v = load_window(b, w, &sd);
   const WinDesc& d = sd;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int crank = (int)cluster_ctarank();
+  const int gtid = crank * kSchurThreads + tid, gwid = crank * kSchurWarps + wid;  // within the cluster
   const double* lmd = v.W(W_LMD);
   double* S = v.W(W_S);
   const int nf = d.n_f, ld = d.ld;
   long long* dbg = b.debug ? b.debug + 8 * (size_t)w : nullptr;
-#define SWGN_STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+#define SWGN_STAMP(i) do { if (dbg && gtid == 0) dbg[i] = clock64(); } while (0)
   SWGN_STAMP(0);
   // start the DRAM -> L2 transfer of everything this CTA will read: Jacobian + residuals, the
   // index tables of the window (contiguous in ipool), the LM diagonal
-  prefetch_range(v.W(W_JAC), sizeof(double) * (size_t)d.n_jac, tid, kSchurThreads);
-  prefetch_range(v.W(W_RES), sizeof(double) * (size_t)d.n_res, tid, kSchurThreads);
-  prefetch_range(v.I(I_ROW_RES), sizeof(int32_t) * (size_t)(d.ioff[I_PROJ] - d.ioff[I_ROW_RES]), tid, kSchurThreads);
-  prefetch_range(lmd, sizeof(double) * (size_t)d.n_t, tid, kSchurThreads);
+  prefetch_range(v.W(W_JAC), sizeof(double) * (size_t)d.n_jac, gtid, kClusterThreads);
+  prefetch_range(v.W(W_RES), sizeof(double) * (size_t)d.n_res, gtid, kClusterThreads);
+  prefetch_range(v.I(I_ROW_RES), sizeof(int32_t) * (size_t)(d.ioff[I_PROJ] - d.ioff[I_ROW_RES]), gtid, kClusterThreads);
+  prefetch_range(lmd, sizeof(double) * (size_t)d.n_t, gtid, kClusterThreads);
 
   // phase 0: clear the upper triangle and the rhs column (cells never touched must read as 0)
-  for (int i = wid; i < nf; i += kSchurWarps) {
+  for (int i = gwid; i < nf; i += kClusterWarps) {
     double* row = S + (size_t)i * ld;
     for (int j = i + lane; j <= nf; j += 32) row[j] = 0.0;
   }
@@ -487,7 +509,7 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
   // on the tensor pipe, the raw products E'[E | b | F] of the larger e-blocks (one warp per e-cell)
   {
     const int32_t* tch = v.I(I_TCHUNK);
-    for (int k = tid; k < d.n_tchunks; k += kSchurThreads) chunk_dispatch(v, tch[k], lmd);
+    for (int k = gtid; k < d.n_tchunks; k += kClusterThreads) chunk_dispatch(v, tch[k], lmd);
     const int32_t* ecell = v.I(I_ECELL);
     const int32_t* ecell_g = v.I(I_ECELL_G);
     const int32_t* srun = v.I(I_SRUN);
@@ -497,7 +519,7 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
     double* EF = v.W(W_EFAC);
     double* EBw = v.W(W_EBUF);
     const int la = lane & 3, lb = lane >> 2;
-    for (int cell = wid; cell < d.n_ecells; cell += kSchurWarps) {
+    for (int cell = gwid; cell < d.n_ecells; cell += kClusterWarps) {
       const int32_t* sc = ecell + 8 * cell;
       const int ps = sc[0], qs = sc[1], out = sc[2], diag = sc[5] & 1;
       const int nq = qs + diag;
@@ -520,7 +542,7 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
     }
   }
   SWGN_STAMP(2);
-  __syncthreads();
+  cluster_sync();
   SWGN_STAMP(3);
   // phase 1b: factor + forward substitution of the larger e-blocks (one warp per chunk, shared-memory
   // scratch), and the W blocks of the simple chunks, one thread per row (consecutive threads read
@@ -528,15 +550,14 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
   {
     const int32_t* wch = v.I(I_WCHUNK);
     double* sm = dyn + (size_t)wid * b.max_wbuf;
-    if (wid < kChunkWarps)
-      for (int k = wid; k < d.n_wchunks; k += kChunkWarps) chunk_warp(v, wch[k], lmd, sm);
+    for (int k = gwid; k < d.n_wchunks; k += kClusterWarps) chunk_warp(v, wch[k], lmd, sm);
   }
   {
     const int32_t* srow = v.I(I_SROW);
     const int32_t* row_chunk = v.I(I_ROW_CHUNK);
     const int32_t* chunk_ecol = v.I(I_CHUNK_ECOL);
     const int32_t* col_size = v.I(I_COL_SIZE);
-    for (int k = tid; k < d.n_srows; k += kSchurThreads) {
+    for (int k = gtid; k < d.n_srows; k += kClusterThreads) {
       const int r = srow[k], chunk = row_chunk[r];
       const int es = col_size[chunk_ecol[chunk]];
       if (es == 3) row_w<3>(v, r, chunk);
@@ -544,7 +565,7 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
       else row_w<2>(v, r, chunk);
     }
   }
-  __syncthreads();
+  cluster_sync();
   SWGN_STAMP(4);
   // phase 2: one warp per block cell.  S_pq = sum_t (+/-) A_t' B_t is a skinny GEMM whose K
   // dimension is the stack of the gathered blocks; every term feeds one FP64 tensor-core MMA
@@ -560,7 +581,7 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
     const double* JW = v.W(W_JAC);
     asm volatile("" : "+l"(JW));  // keep the window base in a register pair: operand address = one IMAD.WIDE
     const int la = lane & 3, lb = lane >> 2;
-    for (int cell = wid; cell < d.n_scells; cell += kSchurWarps) {
+    for (int cell = gwid; cell < d.n_scells; cell += kClusterWarps) {
       const int32_t* sc = scell + 8 * cell;
       const int ps = sc[0], qs = sc[1], soff = sc[2];
       const int diag = sc[5] & 1;
@@ -593,20 +614,20 @@ __global__ void __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int o
   }
   SWGN_STAMP(5);
   if (dbg) {
-    __syncthreads();
+    cluster_sync();
     SWGN_STAMP(6);
-    if (tid == 0) {
+    if (gtid == 0) {
       unsigned smid;
       asm("mov.u32 %0, %smid;" : "=r"(smid));
       dbg[7] = smid;
     }
   }
   if (b.keep_copy) {
-    __syncthreads();
+    cluster_sync();
     double* SC = v.W(W_SCOPY);
-    for (int k = tid; k < nf * ld; k += kSchurThreads) SC[k] = S[k];
+    for (int k = gtid; k < nf * ld; k += kClusterThreads) SC[k] = S[k];
   }
-  if (tid == 0) {
+  if (gtid == 0) {
     st->num_linear_solves += 1;
     st->have_factor = 0;
     st->have_reduced = b.params.export_mode ? 1 : 0;
@@ -739,8 +760,8 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
 
 void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
-  const size_t dyn = sizeof(double) * (size_t)kChunkWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
-  k_schur<<<grid, kSchurThreads, dyn, s>>>(b, only_window);
+  const size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  k_schur<<<grid * kCluster, kSchurThreads, dyn, s>>>(b, only_window);
 }
 void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
@@ -749,7 +770,7 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
 
 cudaError_t configure_schur(const DeviceBatch& b) {
   static size_t granted[64] = {0};
-  const size_t dyn = sizeof(double) * (size_t)kChunkWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  const size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;
   int dev = 0;
   cudaGetDevice(&dev);
