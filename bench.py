@@ -135,6 +135,7 @@ def run_swgn(args, rank, local_rank, world):
     import __graft_entry__ as ge
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (no NCCL version banner)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

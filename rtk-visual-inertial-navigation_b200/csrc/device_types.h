@@ -42,6 +42,8 @@ enum IArr {
   I_CSC_PTR,        // [n_cols+1]
   I_CSC_ROW,        // [nnz] row block
   I_CSC_VAL,        // [nnz] value offset
+  I_CSC_NRES,       // [nnz] residual rows of that row block
+  I_CSC_RES,        // [nnz] first residual row of that row block
   I_SCELL,          // [n_scells * 8] reduced-system block cell: ps, qs, S offset (row*ld+col), first
                     //                word of its terms in I_STERM, term count, diag flag (1: p == q:
                     //                add D^2, carries the rhs as an extra column), first run, run count

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
   __shared__ int s_fail;
   __shared__ double s_rdiag[8];
   __shared__ double s_diag[32][33];
-  extern __shared__ __align__(16) double dyn[];  // panel NB x pw, then wv[max_nf], zv[max_nf]
+  extern __shared__ __align__(16) double dyn[];  // panel NB x pw, then wv, zv, rdg [max_nf each]
   const int w = only_window >= 0 ? only_window : blockIdx.x;
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
   double* P = dyn;
   double* wv = dyn + (size_t)NB * pw;
   double* zv = wv + b.max_nf;
+  double* rdg = zv + b.max_nf;  // 1 / U[i][i], filled as the pivots are computed
   if (tid == 0) s_fail = 0;
   __syncthreads();
 
@@ -107,7 +108,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
           const double piv = __shfl_sync(0xffffffffu, t[p], p);
           if (!(piv > 0.0)) bad = true;  // Eigen LLT: NumericalIssue
           const double ri = rsqrt(piv);
-          if (lane == p) s_rdiag[p] = ri;
+          if (lane == p) {
+            s_rdiag[p] = ri;
+            if (k0 + r0 + p < nf) rdg[k0 + r0 + p] = ri;
+          }
           t[p] = (j == p) ? piv * ri : t[p] * ri;
 #pragma unroll
           for (int q = p + 1; q < 8; ++q) {
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
         double wl = lane < nb ? wv[k0 + lane] : 0.0;
         for (int i = nb - 1; i >= 0; --i) {
           double zi = 0.0;
-          if (lane == i) zi = wl / s_diag[i][i];
+          if (lane == i) zi = wl * rdg[k0 + i];
           zi = __shfl_sync(0xffffffffu, zi, i);
           if (lane == i) wl = zi;
           if (lane < i) wl -= s_diag[lane][i] * zi;
@@ -333,7 +337,7 @@ int chol_pitch(const DeviceBatch& b) {
   return (need > NB + 8 ? need : NB + 8) + 4;  // = 4 or 12 mod 16: conflict-free DMMA fragment loads
 }
 size_t chol_smem(const DeviceBatch& b) {
-  return sizeof(double) * ((size_t)chol_block(b) * chol_pitch(b) + 2 * (size_t)b.max_nf);
+  return sizeof(double) * ((size_t)chol_block(b) * chol_pitch(b) + 3 * (size_t)b.max_nf);
 }
 
 }  // namespace

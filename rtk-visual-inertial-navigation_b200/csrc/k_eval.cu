@@ -551,22 +551,40 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
     double* G = v.W(W_G);
     double* DG = v.W(W_DIAG);
     constexpr int kHeavy = 24;  // columns with more row blocks than this are reduced by a whole warp
-    for (int t = tid; t < d.n_t; t += kThreads) {
-      const int col = tcol[t], k = t - col_pos[col], cs = col_size[col];
-      if (csc_ptr[col + 1] - csc_ptr[col] > kHeavy) continue;
-      double g = 0.0, nrm = 0.0;
-      for (int e = csc_ptr[col]; e < csc_ptr[col + 1]; ++e) {
-        const int row = csc_row[e], nres = row_nres[row];
-        const double* jv = J + csc_val[e] + k;
-        const double* rv = R + row_res[row];
-        for (int rr = 0; rr < nres; ++rr) {
-          const double a = jv[rr * cs];
-          g += a * rv[rr];
-          nrm += a * a;
+    const int32_t* csc_nres = v.I(I_CSC_NRES);
+    const int32_t* csc_res = v.I(I_CSC_RES);
+    // light columns (landmarks, clocks, ambiguities): one thread per column BLOCK, all its tangent
+    // components at once, so the index loads are shared by the cs components
+    for (int col = tid; col < d.n_cols; col += kThreads) {
+      const int e0 = csc_ptr[col], e1 = csc_ptr[col + 1];
+      if (e1 - e0 > kHeavy) continue;
+      const int cs = col_size[col];
+      for (int k0 = 0; k0 < cs; k0 += 9) {
+        double g[9], nrm[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] = nrm[k] = 0.0;
+        for (int e = e0; e < e1; ++e) {
+          const int nres = csc_nres[e];
+          const double* jv = J + csc_val[e] + k0;
+          const double* rv = R + csc_res[e];
+          for (int rr = 0; rr < nres; ++rr) {
+            const double r = rv[rr];
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+              if (k0 + k < cs) {
+                const double a = jv[rr * cs + k];
+                g[k] += a * r;
+                nrm[k] += a * a;
+              }
+          }
         }
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          if (k0 + k < cs) {
+            G[col_pos[col] + k0 + k] = g[k];
+            DG[col_pos[col] + k0 + k] = sqrt(fmin(fmax(nrm[k], b.params.min_lm_diagonal), b.params.max_lm_diagonal));
+          }
       }
-      G[t] = g;
-      DG[t] = sqrt(fmin(fmax(nrm, b.params.min_lm_diagonal), b.params.max_lm_diagonal));
     }
     // heavy columns (poses seen by ~100 observations): lanes stride the row blocks, every lane
     // accumulates all cs columns of its rows, then a deterministic shuffle reduction
@@ -579,9 +597,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
 #pragma unroll
         for (int k = 0; k < 9; ++k) g[k] = nrm[k] = 0.0;
         for (int e = e0 + lane; e < e1; e += 32) {
-          const int row = csc_row[e], nres = row_nres[row];
+          const int nres = csc_nres[e];
           const double* jv = J + csc_val[e] + k0;
-          const double* rv = R + row_res[row];
+          const double* rv = R + csc_res[e];
           for (int rr = 0; rr < nres; ++rr) {
             const double r = rv[rr];
 #pragma unroll

@@ -526,12 +526,16 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     I[I_CSC_PTR].assign(cnt.begin(), cnt.end());
     I[I_CSC_ROW].assign(n_cells, 0);
     I[I_CSC_VAL].assign(n_cells, 0);
+    I[I_CSC_NRES].assign(n_cells, 0);
+    I[I_CSC_RES].assign(n_cells, 0);
     std::vector<int> cur(cnt.begin(), cnt.end() - 1);
     for (int r = 0; r < n_rows; ++r)
       for (int c = I[I_ROW_CELL][r]; c < I[I_ROW_CELL][r + 1]; ++c) {
         int col = I[I_CELL_COL][c];
         I[I_CSC_ROW][cur[col]] = r;
         I[I_CSC_VAL][cur[col]] = I[I_CELL_VAL][c];
+        I[I_CSC_NRES][cur[col]] = I[I_ROW_NRES][r];
+        I[I_CSC_RES][cur[col]] = I[I_ROW_RES][r];
         cur[col]++;
       }
   }
