@@ -250,8 +250,8 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   db.max_prior_n = max_prior_n;
   db.keep_copy = 0;
   if (std::getenv("SWGN_DEBUG_TIMELINE")) {
-    CB(cudaMalloc(&b->d_debug, sizeof(long long) * 8 * n_windows));
-    CB(cudaMemset(b->d_debug, 0, sizeof(long long) * 8 * n_windows));
+    CB(cudaMalloc(&b->d_debug, sizeof(long long) * 16 * n_windows));
+    CB(cudaMemset(b->d_debug, 0, sizeof(long long) * 16 * n_windows));
   }
   db.debug = b->d_debug;
   SolverParams& P = db.params;
@@ -368,10 +368,11 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
   return SWGN_OK;
 }
 
-// development aid: phase timestamps (clock64) of the last k_schur launch, 8 per window
+// development aid: phase timestamps (clock64) of the last k_schur launch (8 per window), then the
+// accumulated phase cycles of the last k_chol launch (8 per window)
 swgn_status swgn_batch_debug_timeline(swgn_batch* b, int64_t* out) {
   if (!b || !b->d_debug || !out) return fail(SWGN_ERR_INVALID, "timeline not enabled (SWGN_DEBUG_TIMELINE=1)");
-  CU(cudaMemcpy(out, b->d_debug, sizeof(long long) * 8 * b->n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, b->d_debug, sizeof(long long) * 16 * b->n, cudaMemcpyDeviceToHost));
   return SWGN_OK;
 }
 

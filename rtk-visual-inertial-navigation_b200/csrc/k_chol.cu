@@ -35,11 +35,37 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// ---- TMA (bulk async copy) staging of the panel rows: global -> shared, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_window, int NB, int pw) {
   __shared__ WinDesc sd;
   __shared__ int s_fail;
-  __shared__ double s_rdiag[8];
+  __shared__ double s_rdiag[2][8];
   __shared__ double s_diag[32][33];
+  __shared__ __align__(8) uint64_t s_bar;
   extern __shared__ __align__(16) double dyn[];  // panel NB x pw, then wv, zv, rdg [max_nf each]
   const int w = only_window >= 0 ? only_window : blockIdx.x;
   TRState* st = b.state + w;
@@ -55,8 +81,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
   double* wv = dyn + (size_t)NB * pw;
   double* zv = wv + b.max_nf;
   double* rdg = zv + b.max_nf;  // 1 / U[i][i], filled as the pivots are computed
-  if (tid == 0) s_fail = 0;
+  if (tid == 0) {
+    s_fail = 0;
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  unsigned bar_phase = 0;
+  long long* dbg = b.debug ? b.debug + 8 * (size_t)(b.n_windows + w) : nullptr;  // second half: k_schur owns the first
+  long long t_prev = dbg ? clock64() : 0, acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = t_prev;
+#define CHOL_STAMP(i) do { if (dbg && tid == 0) { const long long t_ = clock64(); acc_t[i] += t_ - t_prev; t_prev = t_; } } while (0)
 
   for (int k0 = 0; k0 < nf; k0 += NB) {
     const int nb = min(NB, nf - k0);
@@ -66,30 +101,48 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
     const int jr = (nb < NB) ? NB : Wm;
     const int Wp = (jr + 1 + 7) & ~7;    // columns processed inside the panel
     const int Wz = min(pw - 4, max(Wp, (Wm + 1 + 31 + (NB == 16 ? 16 : 0)) & ~31));  // zero-filled extent (trailing tiles read up to here)
-    // ---- stage the panel: upper part of rows k0..k0+nb, identity on padded rows
-    for (int r = wid; r < NB; r += kWarps) {
-      const double* src = S + (size_t)(k0 + r) * ld;
-      double* dst = P + (size_t)r * pw;
-      for (int j0 = lane; j0 < Wz; j0 += 128) {  // four independent loads in flight per lane
-        double val[4];
+    // ---- stage the panel.  Full panels: one bulk async copy (TMA) per row, S[k0+r, k0:ld] ->
+    // P[r, 0:ld-k0], issued by one thread and awaited on an mbarrier; entries left of the diagonal
+    // come along (finite, never read), columns beyond ld-k0 are zero-filled by the other threads.
+    // The final partial panel needs identity padding and the relocated rhs: staged by hand.
+    if (nb == NB) {
+      const int ncopy = ld - k0;  // doubles per row, a multiple of 4
+      if (tid == 0) {
+        mbar_expect_tx(&s_bar, (unsigned)(NB * ncopy * sizeof(double)));
+        for (int r = 0; r < NB; ++r) bulk_g2s(P + (size_t)r * pw, S + (size_t)(k0 + r) * ld + k0, (unsigned)(ncopy * sizeof(double)), &s_bar);
+      }
+      for (int e = tid; e < NB * (Wz - ncopy); e += kThreads) {
+        const int r = e / (Wz - ncopy), j = ncopy + e % (Wz - ncopy);
+        P[(size_t)r * pw + j] = 0.0;
+      }
+      mbar_wait(&s_bar, bar_phase);
+      bar_phase ^= 1;
+    } else {
+      for (int r = wid; r < NB; r += kWarps) {
+        const double* src = S + (size_t)(k0 + r) * ld;
+        double* dst = P + (size_t)r * pw;
+        for (int j0 = lane; j0 < Wz; j0 += 128) {  // four independent loads in flight per lane
+          double val[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 32 * u;
-          double t = 0.0;
-          if (r < nb) {
-            if (j >= r && j < Wm) t = src[k0 + j];
-            else if (j == jr) t = src[nf];
-          } else if (j == r) {
-            t = 1.0;
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u;
+            double t = 0.0;
+            if (r < nb) {
+              if (j >= r && j < Wm) t = src[k0 + j];
+              else if (j == jr) t = src[nf];
+            } else if (j == r) {
+              t = 1.0;
+            }
+            val[u] = t;
           }
-          val[u] = t;
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (j0 + 32 * u < Wz) dst[j0 + 32 * u] = val[u];
+          for (int u = 0; u < 4; ++u)
+            if (j0 + 32 * u < Wz) dst[j0 + 32 * u] = val[u];
+        }
       }
     }
     __syncthreads();
+    CHOL_STAMP(0);
     for (int r8 = 0; r8 * 8 < NB; ++r8) {
       const int r0 = r8 * 8;
       // (1) 8x8 Cholesky of the diagonal tile (upper, in place), reciprocal pivots to s_rdiag
@@ -109,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
           if (!(piv > 0.0)) bad = true;  // Eigen LLT: NumericalIssue
           const double ri = rsqrt(piv);
           if (lane == p) {
-            s_rdiag[p] = ri;
+            s_rdiag[0][p] = ri;
             if (k0 + r0 + p < nf) rdg[k0 + r0 + p] = ri;
           }
           t[p] = (j == p) ? piv * ri : t[p] * ri;
@@ -127,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
         if (bad && lane == 0) s_fail = 1;
       }
       __syncthreads();
+      CHOL_STAMP(5);
       // (2) X = U_rr^-T P[r0:r0+8, j] for every column right of the tile, one thread per column
       {
         const double* U = P + (size_t)r0 * pw + r0;
@@ -138,13 +192,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
             double s = col[(size_t)i * pw];
 #pragma unroll
             for (int p = 0; p < i; ++p) s -= U[(size_t)p * pw + i] * x[p];
-            x[i] = s * s_rdiag[i];
+            x[i] = s * s_rdiag[0][i];
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) col[(size_t)i * pw] = x[i];
         }
       }
       __syncthreads();
+      CHOL_STAMP(6);
       // (3) DMMA update of the panel's remaining row blocks: P[s0.., j0..] -= U[r0.., s0..]^T X[r0.., j0..]
       {
         const int nsb = NB / 8, ntj = Wp / 8;
@@ -167,7 +222,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
         }
       }
       __syncthreads();
+      CHOL_STAMP(7);
     }
+    CHOL_STAMP(1);
     if (s_fail) break;
     // ---- write the finished U rows back
     for (int r = wid; r < nb; r += kWarps) {
@@ -176,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
       for (int j = r + lane; j < Wm; j += 32) dst[k0 + j] = src[j];
       if (lane == 0) dst[nf] = src[jr];
     }
+    CHOL_STAMP(2);
     // ---- trailing update with DMMA: 16x32 warp tiles of the block upper triangle of S[t0:, t0:],
     // k = NB.  The C tile of the NEXT work item is loaded (HBM/L2) while the current one runs on
     // the tensor pipe; the accumulators start from C and A is negated: D = C - U^T U.
@@ -261,22 +319,56 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
       }
     }
     __syncthreads();
+    CHOL_STAMP(3);
   }
 
   const int fail = s_fail;
   if (!fail) {
-    // ---- backward solve U z = w  (w = column n_f), 32-row blocks from the bottom
-    for (int i = tid; i < nf; i += kThreads) wv[i] = S[(size_t)i * ld + nf];
-    __syncthreads();
+    // ---- backward solve U z = w (w = column n_f), 32-row blocks from the bottom, row oriented:
+    // t_i = w_i - U[i, k0+32:] z[k0+32:] for the 32 rows of the block (one warp per four rows,
+    // lanes stride the columns: coalesced row segments, four rows in flight), then the 32x32
+    // triangular solve by one warp with the stored reciprocal pivots
     for (int k0 = ((nf - 1) / 32) * 32; k0 >= 0; k0 -= 32) {
       const int nb = min(32, nf - k0);
+      const int c0 = k0 + nb;  // first column right of the block
       for (int e = tid; e < nb * nb; e += kThreads) {
         const int r = e / nb, c = e - r * nb;
         s_diag[r][c] = (c >= r) ? S[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
       }
+      {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const int rbase = 4 * wid;  // rows rbase..rbase+3 of the block
+        const double* rowp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rowp[q] = S + (size_t)(k0 + min(rbase + q, nb - 1)) * ld;  // clamped: extra rows are discarded below
+        int j = c0 + lane;
+        for (; j + 96 < nf; j += 128) {  // sixteen independent loads in flight per lane
+          double u[4][4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[t][q] = rowp[q][j + 32 * t];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const double zj = zv[j + 32 * t];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += u[t][q] * zj;
+          }
+        }
+        for (; j < nf; j += 32) {
+          const double zj = zv[j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += rowp[q][j] * zj;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double s = warp_sum(acc[q]);
+          if (lane == 0 && rbase + q < nb) wv[rbase + q] = S[(size_t)(k0 + rbase + q) * ld + nf] - s;
+        }
+      }
       __syncthreads();
       if (wid == 0) {
-        double wl = lane < nb ? wv[k0 + lane] : 0.0;
+        double wl = lane < nb ? wv[lane] : 0.0;
         for (int i = nb - 1; i >= 0; --i) {
           double zi = 0.0;
           if (lane == i) zi = wl * rdg[k0 + i];
@@ -287,24 +379,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
         if (lane < nb) zv[k0 + lane] = wl;
       }
       __syncthreads();
-      {  // w_i -= U[i, k0:k0+nb] z[k0:k0+nb] for the rows above: one warp per row (coalesced 256 B
-         // row segments), four rows in flight per warp
-        const double zl = lane < nb ? zv[k0 + lane] : 0.0;
-        for (int i0 = 4 * wid; i0 < k0; i0 += 4 * kWarps) {
-          double u[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) u[q] = (lane < nb && i0 + q < k0) ? S[(size_t)(i0 + q) * ld + k0 + lane] : 0.0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double s = warp_sum(u[q] * zl);
-            if (lane == 0 && i0 + q < k0) wv[i0 + q] -= s;
-          }
-        }
-      }
-      __syncthreads();
     }
     double* Y = v.W(W_Y) + d.n_e;
     for (int i = tid; i < nf; i += kThreads) Y[i] = zv[i];
+  }
+  CHOL_STAMP(4);
+  if (dbg && tid == 0) {
+    for (int i = 0; i < 5; ++i) dbg[i] = acc_t[i];
+    dbg[1] = acc_t[5] + acc_t[6] + acc_t[7] + acc_t[1];
+    dbg[5] = clock64() - t_begin;
+    dbg[6] = acc_t[5];
+    dbg[7] = acc_t[6];
   }
   if (tid == 0) {
     st->chol_ok = fail ? 0 : 1;

@@ -21,14 +21,21 @@ for _ in range(2):
     b.solve()
 L = swgn.lib()
 L.swgn_batch_debug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
-out = np.zeros(8 * n, np.int64)
+out = np.zeros(16 * n, np.int64)
 assert L.swgn_batch_debug_timeline(b.h, out.ctypes.data_as(C.POINTER(C.c_int64))) == 0
-t = out.reshape(n, 8)
+t = out[:8 * n].reshape(n, 8)
+tc = out[8 * n:].reshape(n, 8)
 names = ["P0 zero", "P1a chunks", "wait barrier", "P1b rows", "P2 gather", "tail barrier"]
 d = np.diff(t[:, :7], axis=1).astype(float)
 print("per-CTA phase durations [cycles]: median / p90 / max")
 for i, nm in enumerate(names):
     print("  %-14s %9.0f %9.0f %9.0f" % (nm, np.median(d[:, i]), np.percentile(d[:, i], 90), d[:, i].max()))
+if len(sys.argv) > 2 and sys.argv[2] == "chol":
+    names = ["stage panel", "in-panel", "write-back", "trailing", "back-solve", "total", " potrf+sync", " trsm+sync"]
+    print("k_chol per-CTA accumulated phase cycles: median / p90 / max")
+    for i, nm in enumerate(names):
+        print("  %-14s %9.0f %9.0f %9.0f" % (nm, np.median(tc[:, i]), np.percentile(tc[:, i], 90), tc[:, i].max()))
+    sys.exit(0)
 tot = (t[:, 6] - t[:, 0]).astype(float)
 print("  %-14s %9.0f %9.0f %9.0f" % ("total", np.median(tot), np.percentile(tot, 90), tot.max()))
 span = t[:, 6].max() - t[:, 0].min()
