@@ -47,7 +47,7 @@ enum IArr {
   I_SCELL,          // [n_scells * 8] reduced-system block cell: ps, qs, S offset (row*ld+col), first
                     //                word of its terms in I_STERM, term count, diag flag (1: p == q:
                     //                add D^2, carries the rhs as an extra column), first run, run count
-  I_SRUN,           // [n_sruns * 2] run of consecutive terms with equal shape: count, m << 1 | subtract
+  I_SRUN,           // (unused)
   I_STERM,          // [n_sterms] gather terms (see below): (a, b), or (a, b, b2, 0) on diagonal cells
   I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
   I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
@@ -66,8 +66,9 @@ enum IArr {
 
 // Gather term of the reduced system: S_pq (+/-)= A^T B with A (m x ps) at JW[a], B (m x qs) at
 // JW[b], where JW is the concatenation W_JAC | W_EBUF | W_RES of the window.
-// b2 (diagonal cells only) is the offset of the m-vector paired with A for the rhs: b or w_g.
-// m and the sign are shared by all terms of a run (I_SRUN).
+// Blocks with more than 4 rows are split into slabs of <= 4 rows by the planner, so every entry is one MMA:
+//   word0 = a (28 bits) | rows-1 << 28 | subtract << 30 ;  word1 = b ;  diagonal cells: word2 = b2, word3 = 0
+// b2 is the offset of the m-vector paired with A for the rhs column: b or w_g.
 
 enum CArr {
   C_GLOBALS = 0,  // Pbg[3], gravity[3], proj_sqrt_info[4], cauchy_a, pad -> 12

@@ -79,31 +79,34 @@ __device__ __forceinline__ void prefetch_range(const void* base, size_t bytes, i
     prefetch_l2_bulk(p + off, (unsigned)((aligned - off) < kChunk ? (aligned - off) : kChunk));
 }
 
-// N gather terms of one run, straight-line: the N descriptors are loaded by every lane from the same
+// N consecutive gather terms, straight-line: the N descriptors are loaded by every lane from the same
 // address (broadcast, one cache line), all 2N operand loads are issued before the first MMA, and two
 // accumulator pairs alternate so that consecutive MMAs do not depend on each other.  No shuffles and
-// no branches inside: the scheduler sees one basic block with N independent load chains.
+// no branches inside: the scheduler sees one basic block with N independent load chains.  Every
+// descriptor packs its own row count (<= 4) and sign, so a cell is one uninterrupted stream.
 template <int N, bool DIAG>
-__device__ __forceinline__ void gather_batch(const double* JW, const int32_t* tp, bool b_rhs, bool oka, bool okb, int a_lo,
-                                             int b_lo, double& c0, double& c1, double& d0, double& d1) {
-  int ao[N], bo[N];
+__device__ __forceinline__ void gather_batch(const double* JW, const int32_t* tp, bool b_rhs, bool a_ok, bool b_any, int la,
+                                             int a_lo, int b_lo, double& c0, double& c1, double& d0, double& d1) {
+  int w0[N], bo[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) {
     if (DIAG) {
       const int4 t = *reinterpret_cast<const int4*>(tp + 4 * u);
-      ao[u] = t.x;
+      w0[u] = t.x;
       bo[u] = b_rhs ? t.z : t.y;
     } else {
       const int2 t = *reinterpret_cast<const int2*>(tp + 2 * u);
-      ao[u] = t.x;
+      w0[u] = t.x;
       bo[u] = t.y;
     }
   }
   double av[N], bv[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) {
-    av[u] = oka ? ld_global(JW + (a_lo + ao[u])) : 0.0;
-    bv[u] = okb ? ld_global(JW + (b_lo + bo[u])) : 0.0;
+    const bool ok = la <= ((w0[u] >> 28) & 3);
+    const double a = (ok && a_ok) ? ld_global(JW + (a_lo + (w0[u] & 0x0fffffff))) : 0.0;
+    av[u] = (w0[u] & (1 << 30)) ? -a : a;
+    bv[u] = (ok && b_any) ? ld_global(JW + (b_lo + bo[u])) : 0.0;
   }
 #pragma unroll
   for (int u = 0; u < N; ++u) {
@@ -111,30 +114,14 @@ __device__ __forceinline__ void gather_batch(const double* JW, const int32_t* tp
     else dmma884(c0, c1, av[u], bv[u]);
   }
 }
-template <bool DIAG>
-__device__ __forceinline__ void gather_run(const double* JW, const int32_t* tp, int cnt, bool b_rhs, bool oka, bool okb,
-                                           int a_lo, int b_lo, double& c0, double& c1, double& d0, double& d1) {
-  constexpr int TW = DIAG ? 4 : 2;
-  int k = 0;
-  for (; k + 8 <= cnt; k += 8) gather_batch<8, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-  if (k + 4 <= cnt) {
-    gather_batch<4, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-    k += 4;
-  }
-  if (k + 2 <= cnt) {
-    gather_batch<2, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-    k += 2;
-  }
-  if (k < cnt) gather_batch<1, DIAG>(JW, tp + TW * k, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-}
 
 // One 8x8 tile (rows ti.., columns tj..) of a gathered block cell: C = sum_t (+/-) A_t' B_t over the
-// cell's runs of terms.  Returns the lane's two C fragment values (row lane>>2, columns
-// 2*(lane&3), +1).  `diag` cells carry one extra B column (index qs) fed from the m-vector b2.
-__device__ __forceinline__ void gather_tile(const double* JW, const int32_t* srun, const int32_t* sterm, const int32_t* sc,
-                                            int ti, int tj, int lane, double& out0, double& out1) {
+// cell's terms.  Returns the lane's two C fragment values (row lane>>2, columns 2*(lane&3), +1).
+// `diag` cells carry one extra B column (index qs) fed from the m-vector b2.
+__device__ __forceinline__ void gather_tile(const double* JW, const int32_t* sterm, const int32_t* sc, int ti, int tj, int lane,
+                                            double& out0, double& out1) {
   const int la = lane & 3, lb = lane >> 2;
-  const int ps = sc[0], qs = sc[1];
+  const int ps = sc[0], qs = sc[1], cnt = sc[4];
   const int diag = sc[5] & 1;
   const int ai = ti + lb, bj = tj + lb;
   const bool a_ok = ai < ps, b_ok = bj < qs, b_rhs = diag && bj == qs;
@@ -142,52 +129,22 @@ __device__ __forceinline__ void gather_tile(const double* JW, const int32_t* sru
   const int a_lo = a_ok ? la * ps + ai : 0;
   const int b_lo = b_rhs ? la : (b_ok ? la * qs + bj : 0);
   const bool b_any = b_ok || b_rhs;
-  // additions and subtractions accumulate separately: no per-term sign multiply
-  double cp0 = 0.0, cp1 = 0.0, cn0 = 0.0, cn1 = 0.0;
+  double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
   const int32_t* tp = sterm + sc[3];
-  for (int run = sc[6]; run < sc[6] + sc[7]; ++run) {
-    const int cnt = srun[2 * run], m = srun[2 * run + 1] >> 1;
-    const bool neg = srun[2 * run + 1] & 1;
-    double c0 = neg ? cn0 : cp0, c1 = neg ? cn1 : cp1;
-    double d0 = 0.0, d1 = 0.0;
-    if (m <= 4) {
-      const bool oka = a_ok && la < m, okb = b_any && la < m;
-      const int tw = diag ? 4 : 2;
-      if (diag) gather_run<true>(JW, tp, cnt, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-      else gather_run<false>(JW, tp, cnt, b_rhs, oka, okb, a_lo, b_lo, c0, c1, d0, d1);
-      tp += tw * cnt;
-    } else {  // blocks with more than 4 rows (speed-bias chunks, IMU rows, priors): K steps of 4
-      const int tw = diag ? 4 : 2;
-      const int astep = 4 * ps, bstep = b_rhs ? 4 : 4 * qs;
-      const int nstep = (m + 3) >> 2;
-      for (int k = 0; k < cnt; ++k) {
-        int ao = a_lo + tp[0], bo = b_lo + (b_rhs ? tp[2] : tp[1]);
-        int left = m - la;  // rows of this lane's K slot still inside the block
-#pragma unroll 2
-        for (int e = 0; e < nstep; ++e) {
-          const bool ok = left > 0;
-          const double av = (ok && a_ok) ? ld_global(JW + (ao)) : 0.0;
-          const double bv = (ok && b_any) ? ld_global(JW + (bo)) : 0.0;
-          dmma884(c0, c1, av, bv);
-          ao += astep;
-          bo += bstep;
-          left -= 4;
-        }
-        tp += tw;
-      }
-    }
-    c0 += d0;
-    c1 += d1;
-    if (neg) {
-      cn0 = c0;
-      cn1 = c1;
-    } else {
-      cp0 = c0;
-      cp1 = c1;
-    }
+  int k = 0;
+  if (diag) {
+    for (; k + 8 <= cnt; k += 8) gather_batch<8, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
+    if (k + 4 <= cnt) { gather_batch<4, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 4; }
+    if (k + 2 <= cnt) { gather_batch<2, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 2; }
+    if (k < cnt) gather_batch<1, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
+  } else {
+    for (; k + 8 <= cnt; k += 8) gather_batch<8, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
+    if (k + 4 <= cnt) { gather_batch<4, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 4; }
+    if (k + 2 <= cnt) { gather_batch<2, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 2; }
+    if (k < cnt) gather_batch<1, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
   }
-  out0 = cp0 - cn0;
-  out1 = cp1 - cn1;
+  out0 = c0 + d0;
+  out1 = c1 + d1;
 }
 
 // ---- phase 1, small e-blocks (1..3): one thread per chunk, everything in registers -----------
@@ -512,7 +469,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
     for (int k = gtid; k < d.n_tchunks; k += kClusterThreads) chunk_dispatch(v, tch[k], lmd);
     const int32_t* ecell = v.I(I_ECELL);
     const int32_t* ecell_g = v.I(I_ECELL_G);
-    const int32_t* srun = v.I(I_SRUN);
     const int32_t* sterm = v.I(I_STERM);
     const double* JWc = v.W(W_JAC);
     asm volatile("" : "+l"(JWc));
@@ -527,7 +483,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
         for (int tj = 0; tj < nq; tj += 8) {
           if (diag && tj + 7 < ti) continue;  // E'E: upper triangle only
           double c0, c1;
-          gather_tile(JWc, srun, sterm, sc, ti, tj, lane, c0, c1);
+          gather_tile(JWc, sterm, sc, ti, tj, lane, c0, c1);
           const int i = ti + lb;
           if (i < ps) {
 #pragma unroll
@@ -576,7 +532,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   // loads in flight per lane before the four MMAs.
   {
     const int32_t* scell = v.I(I_SCELL);
-    const int32_t* srun = v.I(I_SRUN);
     const int32_t* sterm = v.I(I_STERM);
     const double* JW = v.W(W_JAC);
     asm volatile("" : "+l"(JW));  // keep the window base in a register pair: operand address = one IMAD.WIDE
@@ -590,7 +545,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
       for (int ti = 0; ti < ps; ti += 8)
         for (int tj = 0; tj < nq; tj += 8) {
           double c0, c1;
-          gather_tile(JW, srun, sterm, sc, ti, tj, lane, c0, c1);
+          gather_tile(JW, sterm, sc, ti, tj, lane, c0, c1);
           // C fragment: row lb, columns 2*la, 2*la+1 of the 8x8 tile
           const int i = ti + lb;
           if (i < ps) {

@@ -364,8 +364,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   if (n_chunks != n_ecols) return fail(SWGN_ERR_INVALID, "chunk detection does not match the eliminated blocks");
   const int n_slots = (int)I[I_SLOT_COL].size();
   const int n_jac_al = (int)align2(n_jac), n_ebuf_al = (int)align2(n_ebuf);
-  if ((int64_t)n_jac_al + n_ebuf_al + n_res >= INT32_MAX)
-    return fail(SWGN_ERR_TOO_LARGE, "window Jacobian too large for 32-bit gather offsets");
+  if ((int64_t)n_jac_al + n_ebuf_al + n_res >= (1 << 28))
+    return fail(SWGN_ERR_TOO_LARGE, "window Jacobian too large for the 28-bit gather offsets");
 
   // ---- gather tables of the reduced system (device Schur kernel, phase 2).  Every touched block
   // cell (p, q), p <= q, of S lists its terms:
@@ -417,28 +417,23 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       const int ps = col_size[p], qs = col_size[q];
       if (ps > MAX_COL_SIZE || qs > MAX_COL_SIZE) return fail(SWGN_ERR_UNSUPPORTED, "parameter block larger than 63 tangent dimensions");
       const bool diag = p == q;
-      // terms sorted into runs of equal (rows m, sign): the device loop decodes nothing per term
-      std::vector<T> ts = *order[ci].second;
-      std::stable_sort(ts.begin(), ts.end(), [](const T& x, const T& y) { return x.m != y.m ? x.m < y.m : x.sign < y.sign; });
-      const int run_begin = (int)(I[I_SRUN].size() / 2);
-      for (size_t k = 0; k < ts.size();) {
-        size_t k1 = k;
-        while (k1 < ts.size() && ts[k1].m == ts[k].m && ts[k1].sign == ts[k].sign) ++k1;
-        I[I_SRUN].push_back((int32_t)(k1 - k));
-        I[I_SRUN].push_back((int32_t)((ts[k].m << 1) | ts[k].sign));
-        k = k1;
+      // flat term stream: blocks with more than 4 rows are split into K slabs of <= 4 rows, and every
+      // entry packs (offset, rows, sign) so that the device loop is one straight-line batch after another
+      //   word0 = a | rows-1 << 28 | subtract << 30        word1 = b        [word2 = b2, word3 = 0]
+      std::vector<T> ts;
+      for (const T& t : *order[ci].second)
+        for (uint32_t e0 = 0; e0 < t.m; e0 += 4)
+          ts.push_back({t.a + e0 * (uint32_t)ps, t.b + e0 * (uint32_t)qs, std::min(4u, t.m - e0), t.sign, t.b2 + e0});
+      {
+        const int tiles = ((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8);
+        P->n_mma += (int64_t)tiles * (int64_t)ts.size();
       }
       if (diag)
         while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);  // 16-byte records need 16-byte alignment
-      {
-        const int tiles = ((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8);
-        for (const T& t : ts) P->n_mma += (int64_t)tiles * ((t.m + 3) / 4);
-      }
-      const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0,
-                              run_begin, (int32_t)(I[I_SRUN].size() / 2) - run_begin};
+      const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
       I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);
       for (const T& t : ts) {  // (a, b) per term, (a, b, b2, 0) on diagonal cells: 8 / 16 byte records
-        I[I_STERM].push_back((int32_t)t.a);
+        I[I_STERM].push_back((int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30)));
         I[I_STERM].push_back((int32_t)t.b);
         if (diag) {
           I[I_STERM].push_back((int32_t)t.b2);
@@ -456,31 +451,25 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       uint32_t a, b, m, b2;
     };
     const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
-    auto emit = [&](int ps, int qs, int out, bool diag, int gout, std::vector<T>& ts) {
-      std::stable_sort(ts.begin(), ts.end(), [](const T& x, const T& y) { return x.m < y.m; });
-      const int run_begin = (int)(I[I_SRUN].size() / 2);
-      for (size_t k = 0; k < ts.size();) {
-        size_t k1 = k;
-        while (k1 < ts.size() && ts[k1].m == ts[k].m) ++k1;
-        I[I_SRUN].push_back((int32_t)(k1 - k));
-        I[I_SRUN].push_back((int32_t)(ts[k].m << 1));
-        k = k1;
-      }
+    auto emit = [&](int ps, int qs, int out, bool diag, int gout, const std::vector<T>& rows) {
+      std::vector<T> ts;
+      for (const T& t : rows)
+        for (uint32_t e0 = 0; e0 < t.m; e0 += 4)
+          ts.push_back({t.a + e0 * (uint32_t)ps, t.b + e0 * (uint32_t)qs, std::min(4u, t.m - e0), t.b2 + e0});
       if (diag)
         while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);
-      const int32_t rec[8] = {ps, qs, out, (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, run_begin,
-                              (int32_t)(I[I_SRUN].size() / 2) - run_begin};
+      const int32_t rec[8] = {ps, qs, out, (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
       I[I_ECELL].insert(I[I_ECELL].end(), rec, rec + 8);
       I[I_ECELL_G].push_back(gout);
       for (const T& t : ts) {
-        I[I_STERM].push_back((int32_t)t.a);
+        I[I_STERM].push_back((int32_t)(t.a | ((t.m - 1) << 28)));
         I[I_STERM].push_back((int32_t)t.b);
         if (diag) {
           I[I_STERM].push_back((int32_t)t.b2);
           I[I_STERM].push_back(0);
         }
-        P->n_mma += (int64_t)((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8) * ((t.m + 3) / 4);
       }
+      P->n_mma += (int64_t)((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8) * (int64_t)ts.size();
     };
     for (int wc = 0; wc < (int)I[I_WCHUNK].size(); ++wc) {
       const int ch = I[I_WCHUNK][wc];
