@@ -239,6 +239,21 @@ def run_swgn(args, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = schur_bytes / (schur_ms * 1e-3) / 1e9
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (592-window launch),
+    # scaled per window to this launch: dram__bytes_read.sum + dram__bytes_write.sum
+    traffic, traffic_src = None, None
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r01_k_schur_592win.md")).read()
+
+        def grab(name):
+            import re
+            m = re.search(r"\| %s \| ([0-9.]+) \| (\w+) \|" % re.escape(name), txt)
+            return float(m.group(1)) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m.group(2)]
+        per_window = (grab("dram__bytes_read.sum") + grab("dram__bytes_write.sum")) / 592.0
+        traffic = per_window * (schur_bytes / max(1, n_schur)) / float(np.mean(schur_bytes_w))
+        traffic_src = "profiles/r01_k_schur_592win.md (ncu --set full, 592-window launch), scaled per window"
+    except Exception:
+        pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ncpu = min(W, max(cores, args.ref_windows))
@@ -256,7 +271,7 @@ def run_swgn(args, rank, local_rank, world):
                    "failed_windows": int(n_fail), "median_cost_reduction": float(np.median(final_costs / init_costs)),
                    "host_generate_s": round(t_gen, 2), "host_plan_upload_s": round(t_create, 2)},
         "roofline": {"kernel": "k_schur", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                      "bytes_per_launch": schur_bytes / max(1, n_schur), "launches": n_schur, "avg_launch_ms": schur_ms / max(1, n_schur), "share_of_step": schur_ms / dev_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
