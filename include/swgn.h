@@ -83,6 +83,18 @@ enum {
   SWGN_IMU_STRIDE = 474
 };
 
+/* per-hidden-frame record of an IMUGNSSFactor chain (fields of IMUGNSSBase,
+   RVI/factor/gnss_imu_factor.h:52-77), SWGN_CHAIN_FRAME_STRIDE doubles */
+enum {
+  SWGN_CHAIN_POSE = 0,       /* [7] gnss_poses[i]: current hidden pose (px,py,pz,qx,qy,qz,qw)  */
+  SWGN_CHAIN_SB = 7,         /* [9] gnss_speed_bias[i]: current hidden (v, ba, bg)             */
+  SWGN_CHAIN_POSE_LIN = 16,  /* [7] gnss_poses_lin[i]: linearisation point of the GNSS info    */
+  SWGN_CHAIN_SB_LIN = 23,    /* [9] gnss_speed_bias_lin[i]                                     */
+  SWGN_CHAIN_RHS = 32,       /* [15] pose_rhses[i]                                             */
+  SWGN_CHAIN_HESSIAN = 48,   /* [225] pose_hessians[i], 15x15 row-major (symmetric)            */
+  SWGN_CHAIN_FRAME_STRIDE = 274
+};
+
 /*
  * One sliding window as a flat factor graph: the content of the reference's long-lived
  * `ceres::Problem my_problem` plus `options.linear_solver_ordering` at the moment of Solve.
@@ -142,15 +154,41 @@ typedef struct swgn_graph {
   const double* unit_istd;
 
   /* residual-block program order (the order of AddResidualBlock calls).  Entry k encodes
-     (kind << 28 | index) with kind 0 proj, 1 imu, 2 gnss, 3 prior, 4 unit.  May be NULL:
-     then the order is proj, imu, gnss, prior, unit.  It only influences summation order.  */
+     (kind << 28 | index) with kind 0 proj, 1 imu, 2 gnss, 3 prior, 4 unit, 5 chain.  May be
+     NULL: then the order is proj, imu, gnss, prior, unit, chain.  It only influences summation
+     order.  */
   int32_t n_order;
   const uint32_t* order;
 
   /* ResidualBlock::is_use masks (CERES/internal/ceres/residual_block.h:135), one byte per
-     factor in the same kind-major layout as above (proj, imu, gnss, prior, unit); NULL = all
-     used. */
+     factor in the same kind-major layout as above (proj, imu, gnss, prior, unit, chain); NULL =
+     all used. */
   const uint8_t* is_use;
+
+  /* IMUGNSSFactor <30+k; 7,9,7,9,1 x k> (RVI/factor/gnss_imu_factor.cpp:678-835): the m GNSS
+     frames between two consecutive keyframes i and j are hidden inside one stateful factor.
+     Every Jacobian evaluation re-eliminates the chain  kf_i -IMU- h_0 -IMU- ... h_{m-1} -IMU- kf_j
+     (each hidden frame carries its pre-linearised GNSS information over (pose, speed-bias, N))
+     frame by frame, and factors the resulting (30+k)^2 information matrix into J = sqrt(S) V^T;
+     cost-only evaluations use the linearised residual r - J*INC; hidden states follow by
+     back-substitution at the next Jacobian evaluation.
+     Parameter order of chain c: chain_blocks[chain_blk_begin[c] ..] = pose_i, sb_i, pose_j, sb_j,
+     then k = chain_blk_begin[c+1]-chain_blk_begin[c]-4 scalar phase-bias blocks (gnss_phase_biases).
+     Hidden frames of chain c: [chain_frame_begin[c], chain_frame_begin[c+1]) in chain_frame_data
+     (SWGN_CHAIN_FRAME_STRIDE each); chain_frame_N holds pose_phase_biases_hessians[i] (15 x k
+     row-major) of every hidden frame back to back in the same order; chain_N holds per chain
+     phase_biases_hessians (k x k row-major) followed by phase_biases_rhs (k); chain_imu_data
+     holds m+1 SWGN_IMU_STRIDE records per chain: imu_factors[0..m-1] then last_imu_factor.
+     The "middle marginalisation" link (pose1_pose2_hessians, gnss_imu_factor.cpp:741-760) is not
+     represented. */
+  int32_t n_chain;
+  const int32_t* chain_blk_begin;    /* n_chain + 1                                           */
+  const int32_t* chain_blocks;
+  const int32_t* chain_frame_begin;  /* n_chain + 1                                           */
+  const double* chain_frame_data;
+  const double* chain_frame_N;
+  const double* chain_N;
+  const double* chain_imu_data;
 } swgn_graph;
 
 /* ---- solver options: the subset of ceres::Solver::Options the reference sets, with the
@@ -261,6 +299,13 @@ swgn_status swgn_batch_get_cholesky(swgn_batch* b, int32_t window, double* L, in
    n_tail rows; A is n_tail x n_tail row-major. */
 swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t window, int32_t n_tail,
                                             double* A);
+
+/* Hidden GNSS-frame states of the IMUGNSSFactor chains of `window` after the last Jacobian
+   evaluation (the reference updates gnss_poses[i] / gnss_speed_bias[i] in user memory,
+   gnss_imu_factor.cpp:601-632): 16 doubles (pose 7, speed-bias 9) per hidden frame in graph
+   order; n_frames may be queried with frames NULL. */
+swgn_status swgn_batch_get_chain_frames(swgn_batch* b, int32_t window, int32_t* n_frames,
+                                        double* frames);
 
 /* ---- staged entry points (used by the parity tests; each is one device pass) ------------- */
 /* Evaluate r, cost, gradient g = J^T r at the current state (ProgramEvaluator::Evaluate).

@@ -85,6 +85,20 @@ int oracle_evaluate(void* h, double* cost, double* residuals, double* gradient, 
   return 0;
 }
 
+// cost-only evaluation (what the trust-region loop does for a candidate point: no Jacobians are
+// requested from the cost functions, trust_region_minimizer.cc:761-787)
+int oracle_evaluate_cost(void* h, double* cost, double* residuals) {
+  Solver* s = (Solver*)h;
+  std::vector<double> x;
+  gather_x(s, &x);
+  std::vector<double> r(s->num_residuals);
+  double c = 0.0;
+  if (!s->Evaluate(x.data(), &c, r.data(), nullptr, false)) return 1;
+  if (cost) *cost = c;
+  if (residuals) std::memcpy(residuals, r.data(), sizeof(double) * r.size());
+  return 0;
+}
+
 // one DENSE_SCHUR linear solve on the linearisation at the current user state
 int oracle_linear_solve(void* h, const double* D, double* x_out, double* S, double* rhs) {
   Solver* s = (Solver*)h;
@@ -119,6 +133,19 @@ void oracle_set_state(void* h, const double* state) {
   Solver* s = (Solver*)h;
   std::memcpy(s->state.data(), state, sizeof(double) * s->state.size());
 }
+// current hidden states of every IMUGNSSFactor chain (16 doubles per hidden frame), in the order
+// the chains were given in the graph; returns the total number of hidden frames
+int oracle_chain_frames(void* h, double* out) {
+  Solver* s = (Solver*)h;
+  // residual_blocks is in program order; recover graph order through a stable scan per chain kind
+  int total = 0;
+  for (auto& rb : s->residual_blocks) {
+    const int m = chain_factor_frames(rb->cost.get(), out ? out + 16 * total : nullptr);
+    total += m;
+  }
+  return total;
+}
+
 int oracle_num_iteration_records(void* h) { return (int)((Solver*)h)->iterations.size(); }
 void oracle_iteration_records(void* h, double* cost, double* radius, int32_t* successful) {
   Solver* s = (Solver*)h;

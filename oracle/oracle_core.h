@@ -133,6 +133,10 @@ CostFunction* make_gnss_factor(int kind, const double* record);
 CostFunction* make_prior_factor(int n, const std::vector<int>& sizes, const std::vector<int>& idx,
                                 const double* x0, const double* J0, const double* r0);
 CostFunction* make_unit_factor(double istd);
+// IMUGNSSFactor (RVI/factor/gnss_imu_factor.cpp:678-835); arrays as in swgn_graph's chain_* fields
+CostFunction* make_chain_factor(const AppGlobals* g, int m, int k, const double* frames, const double* frameN,
+                                const double* chainN, const double* imu_data);
+int chain_factor_frames(const CostFunction* c, double* out16_per_frame);
 
 // range model: RVI/gnss/src/common_function.cpp:103-108,126-139,411-421
 double dot_rtk(const double* a, const double* b, int n);

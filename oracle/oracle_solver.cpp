@@ -30,7 +30,7 @@ bool Solver::Build(const swgn_graph* g, const swgn_options* o) {
     b.user_state = state.data() + g->block_offset[i];
   }
   // factors in kind-major storage, then arranged in program order
-  std::vector<std::unique_ptr<ResidualBlock>> byk[5];
+  std::vector<std::unique_ptr<ResidualBlock>> byk[6];
   for (int i = 0; i < g->n_proj; ++i) {
     auto rb = std::make_unique<ResidualBlock>();
     rb->cost.reset(make_projection_factor(&globals, g->proj_uv + 2 * i));
@@ -70,23 +70,43 @@ bool Solver::Build(const swgn_graph* g, const swgn_options* o) {
     rb->blocks.push_back(&blocks[g->unit_block[i]]);
     byk[4].push_back(std::move(rb));
   }
+  {  // IMUGNSSFactor chains
+    size_t frame_n_off = 0, chain_n_off = 0, imu_off = 0;
+    for (int i = 0; i < g->n_chain; ++i) {
+      const int b0 = g->chain_blk_begin[i], b1 = g->chain_blk_begin[i + 1];
+      const int f0 = g->chain_frame_begin[i], m = g->chain_frame_begin[i + 1] - f0, k = b1 - b0 - 4;
+      if (k < 0 || m < 1) {
+        error = "bad chain factor";
+        return false;
+      }
+      auto rb = std::make_unique<ResidualBlock>();
+      rb->cost.reset(make_chain_factor(&globals, m, k, g->chain_frame_data + (size_t)SWGN_CHAIN_FRAME_STRIDE * f0,
+                                       g->chain_frame_N + frame_n_off, g->chain_N + chain_n_off,
+                                       g->chain_imu_data + imu_off));
+      for (int b = b0; b < b1; ++b) rb->blocks.push_back(&blocks[g->chain_blocks[b]]);
+      byk[5].push_back(std::move(rb));
+      frame_n_off += (size_t)m * 15 * k;
+      chain_n_off += (size_t)k * k + k;
+      imu_off += (size_t)(m + 1) * SWGN_IMU_STRIDE;
+    }
+  }
   if (g->is_use) {
     size_t k = 0;
-    for (int kind = 0; kind < 5; ++kind)
+    for (int kind = 0; kind < 6; ++kind)
       for (auto& rb : byk[kind]) rb->is_use = g->is_use[k++] != 0;
   }
   residual_blocks.clear();
   if (g->order) {
     for (int k = 0; k < g->n_order; ++k) {
       uint32_t kind = g->order[k] >> 28, idx = g->order[k] & 0x0fffffffu;
-      if (kind > 4 || idx >= byk[kind].size() || !byk[kind][idx]) {
+      if (kind > 5 || idx >= byk[kind].size() || !byk[kind][idx]) {
         error = "bad program order entry";
         return false;
       }
       residual_blocks.push_back(std::move(byk[kind][idx]));
     }
   } else {
-    for (int kind = 0; kind < 5; ++kind)
+    for (int kind = 0; kind < 6; ++kind)
       for (auto& rb : byk[kind]) residual_blocks.push_back(std::move(rb));
   }
   for (size_t i = 0; i < residual_blocks.size(); ++i) residual_blocks[i]->program_index = (int)i;

@@ -158,7 +158,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   b->state_off.resize(n_windows + 1);
   b->has_scopy = n_windows <= 256;
   size_t io = 0, co = 0, wo = 0;
-  int max_wbuf = 0, max_nf = 0, max_prior_n = 0;
+  int max_wbuf = 0, max_nf = 0, max_prior_n = 0, max_chain = 0, max_chain_k = 0;
   auto al = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
   int64_t so = 0;
   for (int w = 0; w < n_windows; ++w) {
@@ -184,6 +184,8 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
     max_wbuf = std::max(max_wbuf, d.max_wbuf);
     max_nf = std::max(max_nf, d.n_f);
     max_prior_n = std::max(max_prior_n, d.max_prior_n);
+    max_chain = std::max(max_chain, d.n_chain);
+    max_chain_k = std::max(max_chain_k, d.max_chain_k);
     if (options->n_parameter_head > 0 && d.n_f >= 1024) {
       swgn_batch_destroy(b);
       return fail(SWGN_ERR_TOO_LARGE, "reduced system has >= 1024 rows with exports requested");
@@ -248,6 +250,9 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   db.max_wbuf = max_wbuf;
   db.max_nf = max_nf;
   db.max_prior_n = max_prior_n;
+  db.max_chain = max_chain;
+  db.max_chain_k = max_chain_k;
+  db.chain_epoch = 1;
   db.keep_copy = 0;
   if (std::getenv("SWGN_DEBUG_TIMELINE")) {
     CB(cudaMalloc(&b->d_debug, sizeof(long long) * 16 * n_windows));
@@ -272,6 +277,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   P.export_mode = (options->n_parameter_head > 0 && !options->is_optimize) ? 1 : 0;
   CB(configure_schur(db));
   CB(configure_chol(db));
+  CB(configure_chain(db));
   launch_gather_states(db, b->d_stage, b->d_state_off, 1, b->stream);
   CB(cudaGetLastError());
   CB(cudaStreamSynchronize(b->stream));
@@ -338,8 +344,11 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
       int64_t sizes[NUM_CARR];
       constant_sizes(g, sizes);
       bool ok = g->n_state == d.n_state && g->n_proj == d.n_proj && g->n_imu == d.n_imu && g->n_gnss == d.n_gnss &&
-                g->n_prior == d.n_prior && g->n_unit == d.n_unit;
+                g->n_prior == d.n_prior && g->n_unit == d.n_unit && g->n_chain == d.n_chain;
+      if (ok && g->n_chain > 0) ok = g->chain_frame_begin[g->n_chain] == d.n_chain_frames;
       for (int a = 0; ok && a + 1 < NUM_CARR; ++a) ok = d.coff[a] + sizes[a] <= d.coff[a + 1];
+      if (ok && w + 1 < b->n) ok = d.coff[NUM_CARR - 1] + sizes[NUM_CARR - 1] <= b->desc[w + 1].coff[0];
+      if (ok && w + 1 == b->n) ok = d.coff[NUM_CARR - 1] + sizes[NUM_CARR - 1] <= (int64_t)b->cpool_n;
       if (!ok) {
         bad.store(1);
         continue;
@@ -364,6 +373,7 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
   launch_gather_states(b->db, b->d_stage, b->d_state_off, 1, b->stream);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(b->stream));
+  b->db.chain_epoch += 1;  // IMUGNSSFactor chains reload their hidden states and forget their history
   if (bytes_h2d) *bytes_h2d = (int64_t)(sizeof(double) * (b->cpool_n + (size_t)ns));
   return SWGN_OK;
 }
@@ -421,8 +431,9 @@ swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
   const int tick_limit = (max_iter + 2) * 16;
   int launches = 0, n_schur = 0;
   CU(cudaEventRecord(get_event(b, 0), s));
+  const int eval_launches = db.max_chain > 0 ? 2 : 1;  // k_chain runs ahead of k_eval when chains exist
   launch_eval(db, EVAL_INIT, RUN_STATE_MACHINE, s);
-  ++launches;
+  launches += eval_launches;
   b->h_counters[0] = b->h_counters[1] = -1;
   bool done = false;
   int tick = 0;
@@ -451,7 +462,7 @@ swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
     launch_eval(db, EVAL_CANDIDATE, RUN_STATE_MACHINE, s);
     launch_end(db, s);
     launch_eval(db, EVAL_ACCEPTED, RUN_STATE_MACHINE, s);
-    launches += 7;
+    launches += 5 + 2 * eval_launches;
   }
   launch_finish(db, s);
   ++launches;
@@ -558,6 +569,31 @@ swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t w, int32_t n_
   if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
   cudaFree(dA);
   CU(e);
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_get_chain_frames(swgn_batch* b, int32_t w, int32_t* n_frames, double* frames) {
+  if (!b || w < 0 || w >= b->n || !n_frames) return fail(SWGN_ERR_INVALID, "bad arguments");
+  const WinDesc& d = b->desc[w];
+  *n_frames = d.n_chain_frames;
+  if (!frames || d.n_chain == 0) return SWGN_OK;
+  CU(cudaSetDevice(b->device));
+  std::vector<int32_t> rec((size_t)d.n_chain * 8);
+  CU(cudaMemcpy(rec.data(), b->d_ipool + d.ioff[I_CHAIN], sizeof(int32_t) * rec.size(), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < d.n_chain; ++c) {
+    const int m = rec[8 * c], k = rec[8 * c + 1], frame0 = rec[8 * c + 6];
+    const ChainLayout L(m, k);
+    std::vector<double> fl(4);
+    const double* src = b->d_wpool + d.woff[W_CHAIN] + rec[8 * c + 5];
+    CU(cudaMemcpy(fl.data(), src + L.w_flags, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+    if (fl[1] == (double)b->db.chain_epoch) {  // evaluated at least once since the inputs were loaded
+      CU(cudaMemcpy(frames + (size_t)16 * frame0, src + L.w_frames, sizeof(double) * 16 * m, cudaMemcpyDeviceToHost));
+    } else {  // untouched: the hidden states are still the uploaded ones
+      std::vector<double> fr((size_t)m * CHAIN_FRAME_STRIDE);
+      CU(cudaMemcpy(fr.data(), b->d_cpool + d.coff[C_CHAIN] + rec[8 * c + 4] + L.c_frame, sizeof(double) * fr.size(), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < m; ++i) std::memcpy(frames + (size_t)16 * (frame0 + i), fr.data() + (size_t)i * CHAIN_FRAME_STRIDE, sizeof(double) * 16);
+    }
+  }
   return SWGN_OK;
 }
 

@@ -61,6 +61,9 @@ enum IArr {
   I_PRIOR,          // [n_prior * 8] n, n_blk, res_off, blk_begin, J_off, r0_off, 0, 0
   I_PRIOR_BLK,      // [n_prior_blk * 6] state_off, gsize, idx, jac_off, x0_off, local size
   I_UNIT,           // [n_unit * 4]  state_off, jac_off, res_off, 0
+  I_CHAIN,          // [n_chain * 8] m (hidden frames), k (phase biases), res_off, first entry in I_CHAIN_BLK,
+                    //               C_CHAIN offset, W_CHAIN offset, first hidden frame of the window, 0
+  I_CHAIN_BLK,      // [(4 + k) * 2 per chain] state_off, jac_off of pose_i, sb_i, pose_j, sb_j, N_0 ..
   NUM_IARR
 };
 
@@ -79,6 +82,9 @@ enum CArr {
   C_PRIOR_R0,
   C_PRIOR_X0,
   C_UNIT,         // [n_unit]
+  C_CHAIN,        // IMUGNSSFactor constants, per chain (ChainLayout): m+1 IMU device records, m frame records
+                  // (the ABI's SWGN_CHAIN_FRAME_STRIDE record: initial hidden state, linearisation point, rhs,
+                  // Hessian), m pose-N Hessians (15 x k), the N-N Hessian (k x k) and the N rhs (k)
   NUM_CARR
 };
 
@@ -102,6 +108,9 @@ enum WArr {
   W_S,       // [n_f * ld] reduced system, row-major upper triangle; column n_f holds the rhs;
              //            overwritten by its Cholesky factor U (S = U^T U) and U^-T rhs
   W_SCOPY,   // [n_f * ld] copy of S|rhs before factorisation (staged test entry point only)
+  W_CHAIN,   // mutable state of the IMUGNSSFactor chains, per chain (ChainLayout): hidden frame states, history
+             // flag, states of the last Jacobian evaluation, INC, saved elimination blocks (hmn_save,
+             // rhsmn_save), schur_jacobian, schur_residual, cost of the current evaluation
   NUM_WARR
 };
 
@@ -110,7 +119,40 @@ enum { IMU_DEV_STRIDE = 296, GNSS_DEV_STRIDE = 12 };
 // dp_dba, dp_dbg, dq_dbg, dv_dba, dv_dbg (row-major), [70..294] sqrt_info 15x15 row-major
 enum { IMU_DEV_BLOCKS = 24, IMU_DEV_SQRT = 70 };
 
-enum FactorKind { K_PROJ = 0, K_IMU = 1, K_GNSS = 2, K_PRIOR = 3, K_UNIT = 4 };
+enum FactorKind { K_PROJ = 0, K_IMU = 1, K_GNSS = 2, K_PRIOR = 3, K_UNIT = 4, K_CHAIN = 5, NUM_KINDS = 6 };
+
+// Offsets (doubles) inside one chain's C_CHAIN constants and W_CHAIN work area; m hidden frames,
+// k phase biases, n = 30 + k residuals.
+enum { CHAIN_FRAME_STRIDE = 274, MAX_CHAIN_K = 48 };
+struct ChainLayout {
+  int m, k, n;
+  // constants
+  int c_imu, c_frame, c_frameN, pn_stride, c_NN, c_Nrhs, c_size;
+  // work
+  int w_frames, w_flags, w_old, w_inc, w_save, save_stride, w_J, w_r, w_size;
+#if defined(__CUDACC__)
+  __host__ __device__
+#endif
+  ChainLayout(int m_, int k_) : m(m_), k(k_), n(30 + k_) {
+    auto al = [](int x) { return (x + 1) & ~1; };
+    c_imu = 0;
+    c_frame = (m + 1) * 296;
+    c_frameN = c_frame + m * CHAIN_FRAME_STRIDE;
+    pn_stride = al(15 * k);
+    c_NN = c_frameN + m * pn_stride;
+    c_Nrhs = c_NN + al(k * k);
+    c_size = c_Nrhs + al(k);
+    w_frames = 0;                       // m x 16: pose 7, speed-bias 9
+    w_flags = m * 16;                   // [0] history_flag, [1] input epoch, [2] cost, [3] evaluation failed
+    w_old = w_flags + 4;                // Pi 7, Bi 9, Pj 7, Bj 9, N k
+    w_inc = w_old + 32 + al(k);         // n
+    w_save = w_inc + al(n);             // per frame: Amm_inv 225 | H12 225 | H1N 15k | H10 225 | rhs 15
+    save_stride = al(3 * 225 + 15 * k + 15);
+    w_J = w_save + m * save_stride;     // n x n schur_jacobian
+    w_r = w_J + al(n * n);              // n schur_residual
+    w_size = w_r + al(n);
+  }
+};
 
 enum { MAX_WARP_E = 16, MAX_COL_SIZE = 63 };
 
@@ -118,6 +160,7 @@ struct WinDesc {
   int32_t n_state, n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_cells, n_chunks, n_slots;
   int32_t n_jac, n_ebuf, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, n_efac, n_head;
   int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, n_ecells;
+  int32_t n_chain, n_chain_frames, max_chain_k, pad_chain;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

@@ -12,6 +12,7 @@
 #include <float.h>
 
 #include "dev_common.cuh"
+#include "dev_imu.cuh"
 #include "../../include/swgn.h"
 
 namespace swgn {
@@ -228,101 +229,16 @@ __device__ __forceinline__ void eval_gnss(const Win& v, int i, const double* x, 
 }
 
 // ---- IMU factor, one warp per factor ----------------------------------------------------------
-__device__ __forceinline__ void put33(double* raw, int r0, int c0, const double* B, double s) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) raw[(r0 + i) * 30 + c0 + j] = s * B[i * 3 + j];
-}
-__device__ __forceinline__ void qleft_br(const Quat& q, double* M) {  // w I + [v]x
-  const double vv[3] = {q.x, q.y, q.z};
-  skew3(vv, M);
-  M[0] += q.w; M[4] += q.w; M[8] += q.w;
-}
-__device__ __forceinline__ void qright_br(const Quat& q, double* M) {  // w I - [v]x
-  const double vv[3] = {q.x, q.y, q.z};
-  double S[9];
-  skew3(vv, S);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) M[i] = -S[i];
-  M[0] += q.w; M[4] += q.w; M[8] += q.w;
-}
-
 __device__ void eval_imu(const Win& v, const Globals& gl, int i, const double* x, double* J, double* R, bool full,
                          bool with_fixed, double* raw /* per-warp scratch */, double& cost, double& fixed, int& bad) {
-  enum { O_P = 0, O_R = 3, O_V = 6, O_BA = 9, O_BG = 12 };
   const int lane = threadIdx.x & 31;
   const int32_t* t = v.I(I_IMU) + 12 * i;
   const int res_off = t[8];
   if (res_off < 0 && !with_fixed) return;
   const double* rec = v.C(C_IMU) + (size_t)IMU_DEV_STRIDE * i;
-  const double* pi = x + t[0];
-  const double* si = x + t[1];
-  const double* pj = x + t[2];
-  const double* sj = x + t[3];
-  const Quat Qi = pose_q(pi), Qj = pose_q(pj);
-  const Quat dq = {rec[SWGN_IMU_DELTA_Q + 3], rec[SWGN_IMU_DELTA_Q], rec[SWGN_IMU_DELTA_Q + 1], rec[SWGN_IMU_DELTA_Q + 2]};
-  const double dt = rec[SWGN_IMU_SUM_DT];
-  const double* dp_dba = rec + IMU_DEV_BLOCKS;
-  const double* dp_dbg = dp_dba + 9;
-  const double* dq_dbg = dp_dba + 18;
-  const double* dv_dba = dp_dba + 27;
-  const double* dv_dbg = dp_dba + 36;
-  double dba[3], dbg[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    dba[k] = si[3 + k] - rec[SWGN_IMU_LIN_BA + k];
-    dbg[k] = si[6 + k] - rec[SWGN_IMU_LIN_BG + k];
-  }
-  double th[3], t1[3], t2[3], cdv[3], cdp[3];
-  m33_vec(dq_dbg, dbg, th);
-  const Quat cdq = qmul(dq, Quat{1.0, th[0] / 2.0, th[1] / 2.0, th[2] / 2.0});
-  m33_vec(dv_dba, dba, t1);
-  m33_vec(dv_dbg, dbg, t2);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) cdv[k] = rec[SWGN_IMU_DELTA_V + k] + t1[k] + t2[k];
-  m33_vec(dp_dba, dba, t1);
-  m33_vec(dp_dbg, dbg, t2);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) cdp[k] = rec[SWGN_IMU_DELTA_P + k] + t1[k] + t2[k];
-  const Quat Qi_inv = qinv(Qi);
-  double QjPbg[3];
-  qrot(Qj, gl.Pbg, QjPbg);
-  const double wi[3] = {rec[SWGN_IMU_GYRI] - si[6], rec[SWGN_IMU_GYRI + 1] - si[7], rec[SWGN_IMU_GYRI + 2] - si[8]};
-  const double wj[3] = {rec[SWGN_IMU_GYRJ] - sj[6], rec[SWGN_IMU_GYRJ + 1] - sj[7], rec[SWGN_IMU_GYRJ + 2] - sj[8]};
-  double Sw[9], wiPbg[3], wjPbg[3];
-  skew3(wi, Sw);
-  m33_vec(Sw, gl.Pbg, wiPbg);
-  skew3(wj, Sw);
-  m33_vec(Sw, gl.Pbg, wjPbg);
-  double a[3], ra[3], bb[3], rb[3], QjwjPbg[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) a[k] = 0.5 * gl.G[k] * dt * dt + ((pj[k] - pi[k]) - QjPbg[k]) - si[k] * dt;
-  qrot(Qi_inv, a, ra);
-  qrot(Qj, wjPbg, QjwjPbg);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) bb[k] = gl.G[k] * dt + (sj[k] - QjwjPbg[k]) - si[k];
-  qrot(Qi_inv, bb, rb);
-  double raw_r[15];
-  const Quat qr = qmul(qinv(cdq), qmul(Qi_inv, Qj));
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    raw_r[O_P + k] = ra[k] - cdp[k] + gl.Pbg[k] + wiPbg[k] * dt;
-    raw_r[O_V + k] = rb[k] - cdv[k] + wiPbg[k];
-    raw_r[O_BA + k] = sj[3 + k] - si[3 + k];
-    raw_r[O_BG + k] = sj[6 + k] - si[6 + k];
-  }
-  raw_r[O_R] = 2 * qr.x;
-  raw_r[O_R + 1] = 2 * qr.y;
-  raw_r[O_R + 2] = 2 * qr.z;
-  const double* sqrt_info = rec + IMU_DEV_SQRT;
-  // residual = sqrt_info * raw_r: lanes 0..14
-  double rk = 0.0;
-  if (lane < 15) {
-#pragma unroll
-    for (int m = 0; m < 15; ++m) rk += sqrt_info[lane * 15 + m] * raw_r[m];
-    if (!finite_d(rk)) bad = 1;
-  }
+  const bool want_jac = full && res_off >= 0;
+  const double rk = imu_residual_raw(rec, gl.Pbg, gl.G, x + t[0], x + t[1], x + t[2], x + t[3], raw, want_jac, lane);
+  if (lane < 15 && !finite_d(rk)) bad = 1;
   const double c = 0.5 * warp_sum(lane < 15 ? rk * rk : 0.0);
   if (res_off < 0) {
     if (lane == 0) fixed += c;
@@ -331,82 +247,7 @@ __device__ void eval_imu(const Win& v, const Globals& gl, int i, const double* x
   if (lane == 0) cost += c;
   if (!full) return;
   if (lane < 15) R[res_off + lane] = rk;
-  // raw Jacobian 15 x 30 (columns: pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9) in the warp's scratch
-  for (int k = lane; k < 15 * 30; k += 32) raw[k] = 0.0;
-  __syncwarp();
-  if (lane < 4) {
-    double Ri_inv[9], M[9];
-    qtoR(Qi_inv, Ri_inv);
-    double SPbg[9];
-    skew3(gl.Pbg, SPbg);
-    if (lane == 0) {  // d/d pose_i   imu_factor.cpp:47-60
-      put33(raw, O_P, 0, Ri_inv, -1.0);
-      skew3(ra, M);
-      put33(raw, O_P, 3, M, 1.0);
-      const Quat ql = qmul(qinv(Qj), Qi);
-      double L[9], Rr[9], LR[9];
-      qleft_br(ql, L);
-      qright_br(cdq, Rr);
-      m33_mul(L, Rr, LR);
-      const double vl[3] = {ql.x, ql.y, ql.z}, vr[3] = {cdq.x, cdq.y, cdq.z};
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) M[r * 3 + cc] = -(vl[r] * (-vr[cc]) + LR[r * 3 + cc]);
-      put33(raw, O_R, 3, M, 1.0);
-      skew3(rb, M);
-      put33(raw, O_V, 3, M, 1.0);
-    } else if (lane == 1) {  // d/d speed-bias_i   :61-75
-      put33(raw, O_P, 6, Ri_inv, -dt);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) M[k] = -dp_dba[k];
-      put33(raw, O_P, 9, M, 1.0);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) M[k] = -dp_dbg[k] + SPbg[k] * dt;
-      put33(raw, O_P, 12, M, 1.0);
-      const Quat q3 = qmul(qmul(qinv(Qj), Qi), dq);
-      double L[9], LB[9];
-      qleft_br(q3, L);
-      m33_mul(L, dq_dbg, LB);
-      put33(raw, O_R, 12, LB, -1.0);
-      put33(raw, O_V, 6, Ri_inv, -1.0);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) M[k] = -dv_dba[k];
-      put33(raw, O_V, 9, M, 1.0);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) M[k] = -dv_dbg[k] + SPbg[k];
-      put33(raw, O_V, 12, M, 1.0);
-      const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-      put33(raw, O_BA, 9, I3, -1.0);
-      put33(raw, O_BG, 12, I3, -1.0);
-    } else if (lane == 2) {  // d/d pose_j   :76-86
-      double Rj[9], RiRj[9];
-      qtoR(Qj, Rj);
-      put33(raw, O_P, 15, Ri_inv, 1.0);
-      m33_mul(Ri_inv, Rj, RiRj);
-      m33_mul(RiRj, SPbg, M);
-      put33(raw, O_P, 18, M, 1.0);
-      const Quat q3 = qmul(qmul(qinv(cdq), qinv(Qi)), Qj);
-      double L[9];
-      qleft_br(q3, L);
-      put33(raw, O_R, 18, L, 1.0);
-      double S2[9];
-      skew3(wjPbg, S2);
-      m33_mul(RiRj, S2, M);
-      put33(raw, O_V, 18, M, 1.0);
-    } else {  // d/d speed-bias_j   :87-96
-      double Rj[9], RiRj[9];
-      qtoR(Qj, Rj);
-      put33(raw, O_V, 21, Ri_inv, 1.0);
-      m33_mul(Ri_inv, Rj, RiRj);
-      m33_mul(RiRj, SPbg, M);
-      put33(raw, O_V, 27, M, -1.0);
-      const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-      put33(raw, O_BA, 24, I3, 1.0);
-      put33(raw, O_BG, 27, I3, 1.0);
-    }
-  }
-  __syncwarp();
+  const double* sqrt_info = rec + IMU_DEV_SQRT;
   // J = sqrt_info * raw, scattered to the four cells
   for (int o = lane; o < 15 * 30; o += 32) {
     const int k = o / 30, cc = o - k * 30;
@@ -529,6 +370,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
           J[jo + o] = J0[(size_t)r * n + idx + c];
         }
       }
+    }
+  }
+
+  {  // IMUGNSSFactor chains: evaluated by k_chain (launched just before this kernel in the same mode)
+    const int32_t* ct = v.I(I_CHAIN);
+    for (int i = tid; i < d.n_chain; i += kThreads) {
+      const int res_off = ct[8 * i + 2];
+      if (res_off < 0 && !with_fixed) continue;
+      const ChainLayout L(ct[8 * i], ct[8 * i + 1]);
+      const double* fl = v.W(W_CHAIN) + ct[8 * i + 5] + L.w_flags;
+      if (fl[3] != 0.0 || !finite_d(fl[2])) bad = 1;
+      if (res_off < 0) fixed += fl[2];
+      else cost += fl[2];
     }
   }
 
@@ -699,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
 void launch_eval(const DeviceBatch& b, int mode, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
   const size_t dyn = sizeof(double) * (size_t)(b.max_prior_n > 0 ? b.max_prior_n : 1);
+  launch_chain(b, mode, only_window, s);
   k_eval<<<grid, kThreads, dyn, s>>>(b, mode, only_window);
 }
 

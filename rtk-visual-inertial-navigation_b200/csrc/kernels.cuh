@@ -20,6 +20,9 @@ struct DeviceBatch {
   int max_wbuf;          // max over windows of the warp-chunk scratch (doubles)
   int max_nf;            // max reduced-system size
   int max_prior_n;
+  int max_chain;         // max IMUGNSSFactor chains per window (0: k_chain is never launched)
+  int max_chain_k;       // max phase biases per chain (shared-memory size of k_chain)
+  int chain_epoch;       // bumped by create / update_inputs: chains reload their hidden states and forget history
   int keep_copy;         // copy S|rhs to W_SCOPY before factorising (staged test entry point)
   long long* debug;      // optional [n_windows * 8] phase timestamps of k_schur (SWGN_DEBUG_TIMELINE=1), else null
 };
@@ -30,7 +33,10 @@ enum { RUN_STATE_MACHINE = -1 };
 
 cudaError_t configure_kernels(const DeviceBatch& b);
 
+// evaluation of every factor; launches k_chain first when the batch holds IMUGNSSFactor chains
 void launch_eval(const DeviceBatch& b, int mode, int only_window, cudaStream_t s);
+void launch_chain(const DeviceBatch& b, int mode, int only_window, cudaStream_t s);
+cudaError_t configure_chain(const DeviceBatch& b);
 void launch_begin(const DeviceBatch& b, int tick, cudaStream_t s);
 void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s);
 void launch_chol(const DeviceBatch& b, int only_window, cudaStream_t s);

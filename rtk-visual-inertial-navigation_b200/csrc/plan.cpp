@@ -41,6 +41,25 @@ void constant_sizes(const swgn_graph* g, int64_t sizes[NUM_CARR]) {
   sizes[C_PRIOR_R0] = nr;
   sizes[C_PRIOR_X0] = nx;
   sizes[C_UNIT] = g->n_unit;
+  int64_t nc = 0;
+  for (int i = 0; i < g->n_chain; ++i) {
+    const int m = g->chain_frame_begin[i + 1] - g->chain_frame_begin[i];
+    const int k = g->chain_blk_begin[i + 1] - g->chain_blk_begin[i] - 4;
+    nc += ChainLayout(m, std::max(k, 0)).c_size;
+  }
+  sizes[C_CHAIN] = nc;
+}
+
+static void pack_imu_record(const double* src, double* d) {
+  for (int k = 0; k < 24; ++k) d[k] = src[k];
+  const double* J = src + SWGN_IMU_JACOBIAN;
+  static const int blk[5][2] = {{0, 9}, {0, 12}, {3, 12}, {6, 9}, {6, 12}};  // dp_dba dp_dbg dq_dbg dv_dba dv_dbg
+  for (int bI = 0; bI < 5; ++bI)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) d[IMU_DEV_BLOCKS + bI * 9 + r * 3 + c] = J[(blk[bI][0] + r) * 15 + blk[bI][1] + c];
+  d[69] = 0.0;
+  for (int k = 0; k < 225; ++k) d[IMU_DEV_SQRT + k] = src[SWGN_IMU_SQRT_INFO + k];
+  d[295] = 0.0;
 }
 
 // Factor constants in the device layout (device_types.h CArr); dst[a] has constant_sizes()[a] room.
@@ -56,19 +75,8 @@ void pack_constants(const swgn_graph* g, double* const dst[NUM_CARR]) {
     c[11] = 0.0;
   }
   if (g->n_proj) std::memcpy(dst[C_PROJ_UV], g->proj_uv, sizeof(double) * 2 * (size_t)g->n_proj);
-  for (int i = 0; i < g->n_imu; ++i) {
-    const double* src = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
-    double* d = dst[C_IMU] + (size_t)IMU_DEV_STRIDE * i;
-    for (int k = 0; k < 24; ++k) d[k] = src[k];
-    const double* J = src + SWGN_IMU_JACOBIAN;
-    static const int blk[5][2] = {{0, 9}, {0, 12}, {3, 12}, {6, 9}, {6, 12}};  // dp_dba dp_dbg dq_dbg dv_dba dv_dbg
-    for (int bI = 0; bI < 5; ++bI)
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) d[IMU_DEV_BLOCKS + bI * 9 + r * 3 + c] = J[(blk[bI][0] + r) * 15 + blk[bI][1] + c];
-    d[69] = 0.0;
-    for (int k = 0; k < 225; ++k) d[IMU_DEV_SQRT + k] = src[SWGN_IMU_SQRT_INFO + k];
-    d[295] = 0.0;
-  }
+  for (int i = 0; i < g->n_imu; ++i)
+    pack_imu_record(g->imu_data + (size_t)SWGN_IMU_STRIDE * i, dst[C_IMU] + (size_t)IMU_DEV_STRIDE * i);
   for (int i = 0; i < g->n_gnss; ++i) {
     const double* src = g->gnss_data + (size_t)SWGN_GNSS_STRIDE * i;
     double* d = dst[C_GNSS] + (size_t)GNSS_DEV_STRIDE * i;
@@ -94,6 +102,30 @@ void pack_constants(const swgn_graph* g, double* const dst[NUM_CARR]) {
     oR += n;
   }
   for (int i = 0; i < g->n_unit; ++i) dst[C_UNIT][i] = g->unit_istd[i];
+  {  // IMUGNSSFactor chains
+    int64_t oc = 0;
+    size_t frame_n_off = 0, chain_n_off = 0, imu_off = 0;
+    for (int i = 0; i < g->n_chain; ++i) {
+      const int f0 = g->chain_frame_begin[i], m = g->chain_frame_begin[i + 1] - f0;
+      const int k = std::max(0, g->chain_blk_begin[i + 1] - g->chain_blk_begin[i] - 4);
+      const ChainLayout L(m, k);
+      double* c = dst[C_CHAIN] + oc;
+      std::fill(c, c + L.c_size, 0.0);
+      for (int q = 0; q <= m; ++q)
+        pack_imu_record(g->chain_imu_data + imu_off + (size_t)SWGN_IMU_STRIDE * q, c + L.c_imu + IMU_DEV_STRIDE * q);
+      if (m > 0)
+        std::memcpy(c + L.c_frame, g->chain_frame_data + (size_t)SWGN_CHAIN_FRAME_STRIDE * f0,
+                    sizeof(double) * (size_t)SWGN_CHAIN_FRAME_STRIDE * (size_t)m);
+      for (int q = 0; q < m; ++q)
+        std::memcpy(c + L.c_frameN + q * L.pn_stride, g->chain_frame_N + frame_n_off + (size_t)15 * k * q, sizeof(double) * 15 * k);
+      std::memcpy(c + L.c_NN, g->chain_N + chain_n_off, sizeof(double) * (size_t)k * k);
+      std::memcpy(c + L.c_Nrhs, g->chain_N + chain_n_off + (size_t)k * k, sizeof(double) * k);
+      oc += L.c_size;
+      frame_n_off += (size_t)m * 15 * k;
+      chain_n_off += (size_t)k * k + k;
+      imu_off += (size_t)(m + 1) * SWGN_IMU_STRIDE;
+    }
+  }
 }
 
 swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P, std::string* err) {
@@ -113,7 +145,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
 
   // ---- factors, kind-major storage
   std::vector<Factor> fac;
-  int kind_begin[6] = {0, 0, 0, 0, 0, 0};
+  int kind_begin[NUM_KINDS + 1] = {0, 0, 0, 0, 0, 0, 0};
   auto add_factor = [&](int kind, int idx, const int32_t* blocks, int n, int nres) -> bool {
     Factor f;
     f.kind = kind;
@@ -153,6 +185,23 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     if (g->block_size[g->unit_block[i]] != 1) return fail(SWGN_ERR_INVALID, "unit factor on a non-scalar block");
   }
   kind_begin[5] = (int)fac.size();
+  static_assert((int)SWGN_CHAIN_FRAME_STRIDE == (int)CHAIN_FRAME_STRIDE, "frame record stride");
+  int n_chain_frames = 0, max_chain_k = 0;
+  for (int i = 0; i < g->n_chain; ++i) {
+    const int b0 = g->chain_blk_begin[i], b1 = g->chain_blk_begin[i + 1];
+    const int m = g->chain_frame_begin[i + 1] - g->chain_frame_begin[i], k = b1 - b0 - 4;
+    if (k < 0 || m < 1) return fail(SWGN_ERR_INVALID, "chain factor needs 4 + k blocks and at least one hidden frame");
+    if (k > MAX_CHAIN_K) return fail(SWGN_ERR_UNSUPPORTED, "chain factor with more than 48 phase biases");
+    if (!add_factor(K_CHAIN, i, g->chain_blocks + b0, b1 - b0, 30 + k)) return fail(SWGN_ERR_INVALID, "bad chain block");
+    static const int csz[4] = {7, 9, 7, 9};
+    for (int p = 0; p < 4 + k; ++p)
+      if (g->block_size[fac.back().blocks[p]] != (p < 4 ? csz[p] : 1)) return fail(SWGN_ERR_INVALID, "chain block size mismatch");
+    for (int p = 0; p < 4; p += 2)
+      if (g->block_manifold[fac.back().blocks[p]] != SWGN_MANIFOLD_POSE) return fail(SWGN_ERR_INVALID, "chain pose block without the pose manifold");
+    n_chain_frames += m;
+    max_chain_k = std::max(max_chain_k, k);
+  }
+  kind_begin[6] = (int)fac.size();
   for (const Factor& f : fac) {
     static const int proj_sz[3] = {7, 7, 3}, imu_sz[4] = {7, 9, 7, 9};
     if (f.kind == K_PROJ)
@@ -174,7 +223,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     std::vector<char> seen(fac.size(), 0);
     for (int k = 0; k < g->n_order; ++k) {
       uint32_t kind = g->order[k] >> 28, idx = g->order[k] & 0x0fffffffu;
-      if (kind > 4 || (int)idx >= kind_begin[kind + 1] - kind_begin[kind]) return fail(SWGN_ERR_INVALID, "bad program order entry");
+      if (kind > 5 || (int)idx >= kind_begin[kind + 1] - kind_begin[kind]) return fail(SWGN_ERR_INVALID, "bad program order entry");
       int f = kind_begin[kind] + (int)idx;
       if (seen[f]) return fail(SWGN_ERR_INVALID, "residual block listed twice in the program order");
       seen[f] = 1;
@@ -586,6 +635,26 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     int32_t rec[4] = {soff(f.blocks[0]), f.jac_off[0], f.active ? f.res_off : -1, 0};
     I[I_UNIT].insert(I[I_UNIT].end(), rec, rec + 4);
   }
+  int64_t chain_work = 0;
+  {
+    int64_t oc = 0;
+    int frame0 = 0;
+    for (int i = 0; i < g->n_chain; ++i) {
+      const Factor& f = fac[kind_begin[5] + i];
+      const int m = g->chain_frame_begin[i + 1] - g->chain_frame_begin[i], k = (int)f.blocks.size() - 4;
+      const ChainLayout L(m, k);
+      if (oc + L.c_size > INT32_MAX || chain_work + L.w_size > INT32_MAX) return fail(SWGN_ERR_TOO_LARGE, "chain factors too large");
+      int32_t rec[8] = {m, k, f.active ? f.res_off : -1, (int32_t)(I[I_CHAIN_BLK].size() / 2), (int32_t)oc, (int32_t)chain_work, frame0, 0};
+      I[I_CHAIN].insert(I[I_CHAIN].end(), rec, rec + 8);
+      for (size_t p = 0; p < f.blocks.size(); ++p) {
+        I[I_CHAIN_BLK].push_back(soff(f.blocks[p]));
+        I[I_CHAIN_BLK].push_back(f.jac_off[p]);
+      }
+      oc += L.c_size;
+      chain_work += L.w_size;
+      frame0 += m;
+    }
+  }
   {
     int64_t sizes[NUM_CARR];
     constant_sizes(g, sizes);
@@ -628,6 +697,9 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_srows = (int)I[I_SROW].size();
   d.n_ecells = (int)I[I_ECELL_G].size();
   d.max_wbuf = max_wbuf;
+  d.n_chain = g->n_chain;
+  d.n_chain_frames = n_chain_frames;
+  d.max_chain_k = max_chain_k;
   d.max_prior_n = 0;
   for (int i = 0; i < g->n_prior; ++i) d.max_prior_n = std::max(d.max_prior_n, g->prior_n[i]);
   // tangent size of the trailing parameter_head groups (UpdateSchurHessianOnly's n)
@@ -645,6 +717,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   W[W_DIAG] = W[W_G] = W[W_GHAT] = W[W_GN] = W[W_STEP] = W[W_Y] = W[W_LMD] = align2(n_t);
   W[W_EFAC] = align2(n_efac);
   W[W_S] = W[W_SCOPY] = align2((int64_t)n_f * d.ld);
+  W[W_CHAIN] = align2(chain_work);
   P->schur_doubles = schur_doubles + n_t + (int64_t)n_f * (n_f + 1) / 2 + n_f + n_e;
   return SWGN_OK;
 }

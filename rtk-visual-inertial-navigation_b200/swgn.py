@@ -31,6 +31,9 @@ class Graph(C.Structure):
         ("n_unit", i32), ("unit_block", P(i32)), ("unit_istd", P(f64)),
         ("n_order", i32), ("order", P(C.c_uint32)),
         ("is_use", P(C.c_uint8)),
+        ("n_chain", i32), ("chain_blk_begin", P(i32)), ("chain_blocks", P(i32)),
+        ("chain_frame_begin", P(i32)), ("chain_frame_data", P(f64)), ("chain_frame_N", P(f64)),
+        ("chain_N", P(f64)), ("chain_imu_data", P(f64)),
     ]
 
 
@@ -62,7 +65,9 @@ class FixResult(C.Structure):
 
 class SynthConfig(C.Structure):
     _fields_ = [("n_keyframes", i32), ("n_landmarks", i32), ("n_gnss_epochs", i32),
-                ("n_sats", i32), ("seed0", C.c_uint64), ("state_noise", f64)]
+                ("n_sats", i32), ("seed0", C.c_uint64), ("state_noise", f64),
+                ("composition", i32), ("hidden_per_gap", i32), ("bias_walk_scale", f64),
+                ("hidden_bias_istd", f64)]
 
 
 def _dp(a):
@@ -95,13 +100,16 @@ def synth_lib():
         L.swgn_synth_ambiguity_epochs.argtypes = [C.c_void_p, P(i32), P(i32), P(i32), P(i32)]
         L.swgn_synth_true_ambiguities.restype = P(f64)
         L.swgn_synth_true_ambiguities.argtypes = [C.c_void_p]
+        L.swgn_synth_chain_truth.restype = i32
+        L.swgn_synth_chain_truth.argtypes = [C.c_void_p, P(f64)]
         _synth = L
     return _synth
 
 
 class SynthWindow:
     """One synthetic window.  which=1: 5 KF x 50 LM VI-only; which=2: the
-    20 KF x 300 LM x 10 GNSS-epoch BASELINE window."""
+    20 KF x 300 LM x 10 GNSS-epoch BASELINE window; which=3: the same window in composition A
+    (GNSS frames hidden inside IMUGNSSFactor chains); which=4: a small composition-A window."""
 
     def __init__(self, which=2, window_id=0, **overrides):
         L = synth_lib()
@@ -144,6 +152,22 @@ class SynthWindow:
         sf = np.zeros(max(n_obs.value, 1), np.int32)
         L.swgn_synth_ambiguity_epochs(self.h, _ip(eb), _ip(oa), _ip(sf), None)
         return eb, oa[:n_obs.value], sf[:n_obs.value]
+
+    def chain_truth(self):
+        """Ground truth of the hidden GNSS frames of the IMUGNSSFactor chains, (n_frames, 16)."""
+        n = synth_lib().swgn_synth_chain_truth(self.h, None)
+        out = np.zeros((max(n, 1), 16))
+        synth_lib().swgn_synth_chain_truth(self.h, _dp(out))
+        return out[:n]
+
+    def chain_frames0(self):
+        """Initial hidden-frame states as given to the solver, (n_frames, 16)."""
+        g = self.graph
+        if g.n_chain == 0:
+            return np.zeros((0, 16))
+        n = g.chain_frame_begin[g.n_chain]
+        a = np.ctypeslib.as_array(g.chain_frame_data, shape=(n, 274))
+        return a[:, :16].copy()
 
     def true_ambiguities(self):
         return np.ctypeslib.as_array(synth_lib().swgn_synth_true_ambiguities(self.h),
@@ -193,6 +217,7 @@ def lib():
         L.swgn_batch_get_rows.argtypes = [C.c_void_p, i32, P(i32), P(i32), P(i32)]
         L.swgn_batch_get_dense_jacobian.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_linear_solve.argtypes = [C.c_void_p, i32, P(f64), P(f64)]
+        L.swgn_batch_get_chain_frames.argtypes = [C.c_void_p, i32, P(i32), P(f64)]
         L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_ambiguity_fix.argtypes = [i32, i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32),
                                          i32, P(i32), P(f64), P(FixResult)]
@@ -300,6 +325,14 @@ class Batch:
         A = np.zeros((n_tail, n_tail))
         _check(lib().swgn_batch_get_tail_information(self.h, w, n_tail, _dp(A)), "tail_information")
         return A
+
+    def chain_frames(self, w):
+        """Hidden GNSS-frame states of window w's IMUGNSSFactor chains, (n_frames, 16)."""
+        n = i32()
+        _check(lib().swgn_batch_get_chain_frames(self.h, w, C.byref(n), None), "get_chain_frames")
+        out = np.zeros((max(n.value, 1), 16))
+        _check(lib().swgn_batch_get_chain_frames(self.h, w, C.byref(n), _dp(out)), "get_chain_frames")
+        return out[:n.value]
 
     def columns(self, w):
         n = i32()

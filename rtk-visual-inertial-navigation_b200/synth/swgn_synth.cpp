@@ -298,6 +298,8 @@ struct swgn_synth {
   std::vector<int32_t> unit_block;
   std::vector<double> unit_istd;
   std::vector<int32_t> epoch_begin, obs_amb, obs_sysfreq;
+  std::vector<int32_t> chain_blk_begin, chain_blocks, chain_frame_begin, chain_frame_block;
+  std::vector<double> chain_frame_data, chain_frame_N, chain_N, chain_imu_data, chain_frame_truth;
   std::vector<double> true_N;
   int32_t info[8];
 };
@@ -308,16 +310,32 @@ void swgn_synth_default_config(int32_t which, swgn_synth_config* c) {
   std::memset(c, 0, sizeof(*c));
   c->seed0 = 20261017ull;
   c->state_noise = 1.0;
+  c->bias_walk_scale = 1.0;
   if (which == 1) {
     c->n_keyframes = 5;
     c->n_landmarks = 50;
     c->n_gnss_epochs = 0;
     c->n_sats = 0;
+  } else if (which == 4) {
+    c->n_keyframes = 6;
+    c->n_landmarks = 40;
+    c->n_gnss_epochs = 2;
+    c->n_sats = 8;
+    c->composition = 1;
+    c->hidden_per_gap = 2;
+    c->bias_walk_scale = 30.0;
+    c->hidden_bias_istd = 10.0;
   } else {
     c->n_keyframes = 20;
     c->n_landmarks = 300;
     c->n_gnss_epochs = 10;
     c->n_sats = 20;
+    if (which == 3) {
+      c->composition = 1;
+      c->hidden_per_gap = 2;
+      c->bias_walk_scale = 30.0;
+      c->hidden_bias_istd = 10.0;
+    }
   }
 }
 
@@ -328,9 +346,12 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
   Rng rng(Rng::splitmix(sd));
   const int nkf = cfg->n_keyframes, nep = cfg->n_gnss_epochs, nsat = nep > 0 ? cfg->n_sats : 0;
   const double sn = cfg->state_noise;
+  const bool compA = cfg->composition == 1;
+  const int hpg = std::max(1, std::min(3, (int)cfg->hidden_per_gap));
 
   // ---- yaml constants (YAML/rtk_visual_inertial_config.yaml:24-28,68-123)
-  const double ACC_N = 0.05, GYR_N = 0.005, ACC_W = 0.0005, GYR_W = 0.00005, GNORM = 9.8;
+  const double bws = cfg->bias_walk_scale > 0.0 ? cfg->bias_walk_scale : 1.0;
+  const double ACC_N = 0.05, GYR_N = 0.005, ACC_W = 0.0005 * bws, GYR_W = 0.00005 * bws, GNORM = 9.8;
   const V3 Pbg = {-0.0051302024, 0.0091942546, 0.308739733};
   const M3 RIC = {{-1.1283524065062611e-02, 9.0570010831436121e-03, 9.9989532092917277e-01,
                    -9.9992100257025784e-01, -5.6404389398068133e-03, -1.1232723065088990e-02,
@@ -369,14 +390,22 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
     for (int k = 0; k < nkf; ++k) {
       frames.push_back({0.25 * k, 0, k, -1});
       if (nep > 0 && (k % 2 == 1) && ep < nep) {
-        frames.push_back({0.25 * k + 0.05, 1, -1, ep});
-        ++ep;
+        if (!compA) {
+          frames.push_back({0.25 * k + 0.05, 1, -1, ep});
+          ++ep;
+        } else if (k + 1 < nkf) {  // hidden frames need a keyframe on both sides
+          for (int h = 0; h < hpg; ++h) frames.push_back({0.25 * k + 0.05 * (h + 1), 1, -1, ep});
+          ++ep;
+        }
       }
     }
   }
   const int F = (int)frames.size();
   int n_epochs_real = 0;
   for (auto& fr : frames) n_epochs_real += fr.is_gnss;
+  const int n_gnss_frames = n_epochs_real;
+  (void)n_gnss_frames;
+  if (compA) n_epochs_real = 0;  // no raw GNSS factors, clock or drift blocks in composition A
 
   // ---- trajectory (IMU origin, ENU): figure-8 of radius 10 m, ~2-3 m/s, +-3 deg roll/pitch
   const double Rr = 10.0, om = 0.2;
@@ -488,6 +517,7 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
 
   // ---- IMU factors between consecutive frames (400 Hz)
   const double dti = 0.0025;
+  std::vector<double> imu_rec;  // record f: frame f -> f + 1
   for (int f = 0; f + 1 < F; ++f) {
     int k0 = (int)std::llround(frames[f].t / dti), k1 = (int)std::llround(frames[f + 1].t / dti);
     auto sample = [&](int k, V3* a, V3* w) {
@@ -509,9 +539,9 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
       delete S;
       return nullptr;
     }
-    size_t base_i = S->imu_data.size();
-    S->imu_data.resize(base_i + SWGN_IMU_STRIDE, 0.0);
-    double* r = S->imu_data.data() + base_i;
+    size_t base_i = imu_rec.size();
+    imu_rec.resize(base_i + SWGN_IMU_STRIDE, 0.0);
+    double* r = imu_rec.data() + base_i;
     r[SWGN_IMU_DELTA_P] = pre.dp.x; r[SWGN_IMU_DELTA_P + 1] = pre.dp.y; r[SWGN_IMU_DELTA_P + 2] = pre.dp.z;
     r[SWGN_IMU_DELTA_Q] = pre.dq.x; r[SWGN_IMU_DELTA_Q + 1] = pre.dq.y;
     r[SWGN_IMU_DELTA_Q + 2] = pre.dq.z; r[SWGN_IMU_DELTA_Q + 3] = pre.dq.w;
@@ -523,8 +553,10 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
     r[SWGN_IMU_SUM_DT] = pre.sum_dt;
     std::memcpy(r + SWGN_IMU_JACOBIAN, pre.jac.data(), sizeof(double) * 225);
     std::memcpy(r + SWGN_IMU_SQRT_INFO, sq.data(), sizeof(double) * 225);
+    if (compA && (frames[f].is_gnss || frames[f + 1].is_gnss)) continue;  // part of a chain factor
     int32_t ib[4] = {b_pose + f, b_sb + f, b_pose + f + 1, b_sb + f + 1};
     S->imu_blocks.insert(S->imu_blocks.end(), ib, ib + 4);
+    S->imu_data.insert(S->imu_data.end(), r, r + SWGN_IMU_STRIDE);
   }
 
   // ---- landmarks and visual tracks
@@ -603,7 +635,108 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
     return norm(rr - rs) + kOmge * (rs.x * rr.y - rs.y * rr.x) / kClight;
   };
   S->epoch_begin.push_back(0);
-  for (int f = 0; f < F; ++f) {
+  if (compA) {
+    // IMUGNSSFactor chains (RVI/factor/gnss_imu_factor.cpp:264-356 AddMargInfo): every hidden GNSS
+    // frame carries A = J'J, b = J'r0 of its carrier-phase / pseudorange / Doppler rows linearised
+    // at the frame's initial estimate (ambiguities at 0), split into pose_hessians (15x15),
+    // pose_phase_biases_hessians (15xk), pose_rhses, and accumulated phase_biases_hessians / rhs.
+    const int k = nsat;
+    S->chain_blk_begin.push_back(0);
+    S->chain_frame_begin.push_back(0);
+    int f = 0;
+    while (f < F) {
+      if (!frames[f].is_gnss) { ++f; continue; }
+      int f1 = f;
+      while (f1 < F && frames[f1].is_gnss) ++f1;  // hidden run [f, f1), keyframes f-1 and f1
+      const int m = f1 - f;
+      std::vector<double> NN((size_t)k * k, 0.0), Nr(k, 0.0);
+      for (int h = f; h < f1; ++h) {
+        const double t = frames[h].t;
+        const double* pl = bp0(b_pose + h);
+        const double* sl = bp0(b_sb + h);
+        const double* pt = bp(b_pose + h);
+        const double* st = bp(b_sb + h);
+        size_t o = S->chain_frame_data.size();
+        S->chain_frame_data.resize(o + SWGN_CHAIN_FRAME_STRIDE, 0.0);
+        double* fr = S->chain_frame_data.data() + o;
+        for (int q = 0; q < 7; ++q) fr[SWGN_CHAIN_POSE + q] = fr[SWGN_CHAIN_POSE_LIN + q] = pl[q];
+        for (int q = 0; q < 9; ++q) fr[SWGN_CHAIN_SB + q] = fr[SWGN_CHAIN_SB_LIN + q] = sl[q];
+        for (int q = 0; q < 7; ++q) S->chain_frame_truth.push_back(pt[q]);
+        for (int q = 0; q < 9; ++q) S->chain_frame_truth.push_back(st[q]);
+        S->chain_frame_block.push_back(b_pose + h);
+        std::vector<double> PN((size_t)15 * k, 0.0);
+        double* Hp = fr + SWGN_CHAIN_HESSIAN;
+        double* bpv = fr + SWGN_CHAIN_RHS;
+        const V3 xt = V3{pt[0], pt[1], pt[2]} + base, xl = V3{pl[0], pl[1], pl[2]} + base;
+        const V3 vt = {st[0], st[1], st[2]}, vl = {sl[0], sl[1], sl[2]};
+        for (int s = 0; s < nsat; ++s) {
+          const V3 sp = sat_pos0[s] + t * sat_vel[s];
+          const double lam = lams[sat_sys[s]];
+          const double sinel = std::sin(sat_el[s]);
+          const V3 el = (1.0 / norm(xl - sp)) * (xl - sp);
+          const double ev[3] = {el.x, el.y, el.z};
+          const double rho_t = range_sagnac(xt, sp), rho_l = range_sagnac(xl, sp);
+          // carrier phase: r = w (rho - N lam - L)
+          {
+            const double w = sinel / (0.003 * lam);
+            const double L = rho_t - S->true_N[s] * lam + 0.003 * lam * rng.normal();
+            const double r0 = w * (rho_l - L), jn = -w * lam;
+            for (int a = 0; a < 3; ++a) {
+              for (int c = 0; c < 3; ++c) Hp[a * 15 + c] += w * ev[a] * w * ev[c];
+              PN[(size_t)a * k + s] += w * ev[a] * jn;
+              bpv[a] += w * ev[a] * r0;
+            }
+            NN[(size_t)s * k + s] += jn * jn;
+            Nr[s] += jn * r0;
+          }
+          // pseudorange: r = w (rho - P)
+          {
+            const double w = sinel / 0.3;
+            const double P1 = rho_t + 0.3 * rng.normal();
+            const double r0 = w * (rho_l - P1);
+            for (int a = 0; a < 3; ++a) {
+              for (int c = 0; c < 3; ++c) Hp[a * 15 + c] += w * ev[a] * w * ev[c];
+              bpv[a] += w * ev[a] * r0;
+            }
+          }
+          // Doppler: r = w ((v - v_sat).e + D)
+          {
+            const double w = sinel * sinel / 0.05;
+            const V3 et = (1.0 / norm(xt - sp)) * (xt - sp);
+            const double D = -dot(vt - sat_vel[s], et) + 0.05 * rng.normal();
+            const double r0 = w * (dot(vl - sat_vel[s], el) + D);
+            for (int a = 0; a < 3; ++a) {
+              for (int c = 0; c < 3; ++c) Hp[(6 + a) * 15 + 6 + c] += w * ev[a] * w * ev[c];
+              bpv[6 + a] += w * ev[a] * r0;
+            }
+          }
+          S->obs_amb.push_back(s);
+          S->obs_sysfreq.push_back(sat_sys[s] * 2);
+        }
+        if (cfg->hidden_bias_istd > 0.0) {  // weak absolute bias information at the linearisation point
+          const double wa = cfg->hidden_bias_istd, wg = 10.0 * cfg->hidden_bias_istd;
+          for (int a = 0; a < 3; ++a) {
+            Hp[(9 + a) * 15 + 9 + a] += wa * wa;
+            Hp[(12 + a) * 15 + 12 + a] += wg * wg;
+          }
+        }
+        S->epoch_begin.push_back((int32_t)S->obs_amb.size());
+        S->chain_frame_N.insert(S->chain_frame_N.end(), PN.begin(), PN.end());
+      }
+      S->chain_N.insert(S->chain_N.end(), NN.begin(), NN.end());
+      S->chain_N.insert(S->chain_N.end(), Nr.begin(), Nr.end());
+      for (int h = f - 1; h < f1; ++h)
+        S->chain_imu_data.insert(S->chain_imu_data.end(), imu_rec.begin() + (size_t)SWGN_IMU_STRIDE * h,
+                                 imu_rec.begin() + (size_t)SWGN_IMU_STRIDE * (h + 1));
+      int32_t cb[4] = {b_pose + f - 1, b_sb + f - 1, b_pose + f1, b_sb + f1};
+      S->chain_blocks.insert(S->chain_blocks.end(), cb, cb + 4);
+      for (int s = 0; s < nsat; ++s) S->chain_blocks.push_back(b_N + s);
+      S->chain_blk_begin.push_back((int32_t)S->chain_blocks.size());
+      S->chain_frame_begin.push_back(S->chain_frame_begin.back() + m);
+      f = f1;
+    }
+  }
+  for (int f = 0; f < F && !compA; ++f) {
     if (!frames[f].is_gnss) continue;
     const int e = frames[f].epoch;
     const double t = frames[f].t;
@@ -720,11 +853,13 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
     for (int e = 0; e < n_epochs_real; ++e)
       for (int k = 0; k < 3; ++k) S->block_group[b_clk + 3 * e + k] = 0;
     int index = 0;
+    auto in_problem = [&](int f) { return !(compA && frames[f].is_gnss); };
     for (int f = 1; f < F; ++f)  // sb0 is a keep-block of the prior
-      if (index++ % 2 == 0) S->block_group[b_sb + f] = 0;
+      if (in_problem(f) && index++ % 2 == 0) S->block_group[b_sb + f] = 0;
     for (int f = 1; f < F; ++f)
-      if (S->block_group[b_sb + f] < 0) S->block_group[b_sb + f] = ors++;
-    for (int f = 1; f < F; ++f) S->block_group[b_pose + f] = ors++;
+      if (in_problem(f) && S->block_group[b_sb + f] < 0) S->block_group[b_sb + f] = ors++;
+    for (int f = 1; f < F; ++f)
+      if (in_problem(f)) S->block_group[b_pose + f] = ors++;
     if (n_epochs_real > 0) S->block_group[b_black] = ors++;
     for (int e = 0; e < n_epochs_real; ++e) S->block_group[b_drift + e] = ors++;
     S->block_group[b_pose + 0] = ors++;
@@ -785,6 +920,16 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
   g.n_order = 0;
   g.order = nullptr;
   g.is_use = nullptr;
+  g.n_chain = (int32_t)S->chain_blk_begin.size() - (S->chain_blk_begin.empty() ? 0 : 1);
+  if (g.n_chain > 0) {
+    g.chain_blk_begin = S->chain_blk_begin.data();
+    g.chain_blocks = S->chain_blocks.data();
+    g.chain_frame_begin = S->chain_frame_begin.data();
+    g.chain_frame_data = S->chain_frame_data.data();
+    g.chain_frame_N = S->chain_frame_N.data();
+    g.chain_N = S->chain_N.data();
+    g.chain_imu_data = S->chain_imu_data.data();
+  }
 
   std::memset(&S->opt, 0, sizeof(S->opt));
   S->opt.max_num_iterations = 8;
@@ -828,5 +973,10 @@ int32_t swgn_synth_ambiguity_epochs(const swgn_synth* s, int32_t* epoch_begin, i
   return ne;
 }
 const double* swgn_synth_true_ambiguities(const swgn_synth* s) { return s->true_N.data(); }
+int32_t swgn_synth_chain_truth(const swgn_synth* s, double* frames16) {
+  const int32_t n = (int32_t)(s->chain_frame_truth.size() / 16);
+  if (frames16) std::memcpy(frames16, s->chain_frame_truth.data(), sizeof(double) * s->chain_frame_truth.size());
+  return n;
+}
 
 }  // extern "C"

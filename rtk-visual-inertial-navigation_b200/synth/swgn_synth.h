@@ -25,11 +25,25 @@ typedef struct swgn_synth_config {
   int32_t n_sats;          /* split 8:7:5 over GPS/BDS/GAL (scaled)                           */
   uint64_t seed0;          /* window w is seeded with splitmix64(seed0 + w)                   */
   double state_noise;      /* scale of the initial-state perturbation (1.0 = SURVEY values)   */
+  int32_t composition;     /* 0 = "B": GNSS epochs are explicit frames with raw GNSS factors;
+                              1 = "A" (reference-faithful): the GNSS frames between
+                              two keyframes are hidden inside one IMUGNSSFactor chain that carries
+                              their pre-linearised GNSS information                            */
+  int32_t hidden_per_gap;  /* composition A: GNSS frames per keyframe gap that has any (1..3)  */
+  double bias_walk_scale;  /* multiplies the yaml acc_w / gyr_w bias random-walk densities (1.0 =
+                              yaml).  With the yaml values the eliminated chain Hessian spans 16
+                              decades (1e12 .. 1e-4 = its own rounding noise), and the reference's
+                              absolute 1e-8 eigenvalue threshold (gnss_imu_factor.cpp:9,483) lets
+                              noise eigenvalues through; the composition-A presets use 30 so that
+                              parity tests compare arithmetic, not amplified rounding noise     */
+  double hidden_bias_istd; /* composition A: 1/sigma of a weak absolute bias term in the hidden
+                              frames' GNSS information (acc bias; gyro bias uses 10x); 0 = none */
 } swgn_synth_config;
 
 typedef struct swgn_synth swgn_synth;
 
-/* cfg 1: 5 KF x 50 LM, VI only; cfg 2: 20 KF x 300 LM x 10 epochs x 20 sats */
+/* cfg 1: 5 KF x 50 LM, VI only; cfg 2: 20 KF x 300 LM x 10 epochs x 20 sats;
+   cfg 3: cfg 2 in composition A (hidden GNSS frames, 2 per gap); cfg 4: 6 KF x 40 LM x 2 gaps x 8 sats, A */
 void swgn_synth_default_config(int32_t which, swgn_synth_config* c);
 swgn_synth* swgn_synth_create(const swgn_synth_config* c, uint64_t window_id);
 void swgn_synth_destroy(swgn_synth* s);
@@ -47,6 +61,9 @@ int32_t swgn_synth_ambiguity_epochs(const swgn_synth* s, int32_t* epoch_begin, i
                                     int32_t* obs_sysfreq, int32_t* n_obs);
 /* true integer ambiguities (n_ambiguities doubles) */
 const double* swgn_synth_true_ambiguities(const swgn_synth* s);
+/* ground truth of the hidden GNSS frames of the chain factors (16 doubles per frame, graph order);
+   returns the number of hidden frames, frames16 may be NULL */
+int32_t swgn_synth_chain_truth(const swgn_synth* s, double* frames16);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,10 @@ def oracle():
         L.oracle_get_state.argtypes = [C.c_void_p, P(f64)]
         L.oracle_set_state.argtypes = [C.c_void_p, P(f64)]
         L.oracle_num_iteration_records.argtypes = [C.c_void_p]
+        L.oracle_evaluate_cost.restype = C.c_int
+        L.oracle_evaluate_cost.argtypes = [C.c_void_p, P(f64), P(f64)]
+        L.oracle_chain_frames.restype = C.c_int
+        L.oracle_chain_frames.argtypes = [C.c_void_p, P(f64)]
         L.oracle_iteration_records.argtypes = [C.c_void_p, P(f64), P(f64), P(i32)]
         L.oracle_get_exports.argtypes = [C.c_void_p, P(f64), P(f64), P(f64)]
         L.oracle_tail_information.argtypes = [P(f64), i32, i32, P(f64)]
@@ -125,6 +129,14 @@ class OracleSolver:
         assert st == 0
         return cost.value, r, g, J
 
+    def evaluate_cost(self):
+        """Cost-only evaluation (no Jacobians requested from the cost functions)."""
+        cost = f64()
+        r = np.zeros(self.n_res)
+        st = oracle().oracle_evaluate_cost(self.h, C.byref(cost), _dp(r))
+        assert st == 0
+        return cost.value, r
+
     def linear_solve(self, D=None):
         x = np.zeros(self.n_cols)
         S = np.zeros((self.n_f, self.n_f))
@@ -149,6 +161,13 @@ class OracleSolver:
     def set_state(self, x):
         x = np.ascontiguousarray(x, np.float64)
         oracle().oracle_set_state(self.h, _dp(x))
+
+    def chain_frames(self):
+        """Current hidden GNSS-frame states of the IMUGNSSFactor chains, (n_frames, 16)."""
+        n = oracle().oracle_chain_frames(self.h, None)
+        out = np.zeros((max(n, 1), 16))
+        oracle().oracle_chain_frames(self.h, _dp(out))
+        return out[:n]
 
     def iteration_records(self):
         n = oracle().oracle_num_iteration_records(self.h)
