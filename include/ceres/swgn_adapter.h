@@ -7,8 +7,9 @@
 //   ceres::swgn::RegisterAdapter(typeid(projection_factor), &adapt_projection);
 //
 // and fills a FactorRecord when ceres::Solve flattens the Problem.  Types without an adapter make
-// Solve() return FAILURE with a message naming the type (the host-evaluated generic path for
-// stateful factors such as IMUGNSSFactor is listed as "next" in SURVEY.md 8f).
+// Solve() return FAILURE with a message naming the type.  The stateful IMUGNSSFactor is described
+// as a chain record (kChain); its hidden GNSS-frame states are written back into the user memory
+// the factor points at (gnss_poses[i], gnss_speed_bias[i]) when Solve returns.
 #ifndef SWGN_CERES_SWGN_ADAPTER_H_
 #define SWGN_CERES_SWGN_ADAPTER_H_
 #include <typeindex>
@@ -19,7 +20,7 @@
 
 namespace ceres {
 namespace swgn {
-enum FactorKind { kProjection = 0, kImu = 1, kGnss = 2, kPrior = 3, kUnit = 4 };
+enum FactorKind { kProjection = 0, kImu = 1, kGnss = 2, kPrior = 3, kUnit = 4, kChain = 5, kNumKinds = 6 };
 struct FactorRecord {
   int kind = -1;
   int gnss_kind = -1;            // SWGN_GNSS_* for kGnss
@@ -30,6 +31,13 @@ struct FactorRecord {
   int prior_n = 0;
   std::vector<int> prior_blk_idx;
   std::vector<double> prior_x0, prior_J, prior_r0;
+  // kChain (IMUGNSSFactor, RVI/factor/gnss_imu_factor.h): m hidden frames and k phase biases (the
+  // residual block's parameters are pose_i, sb_i, pose_j, sb_j, N_0..N_{k-1}); arrays exactly as the
+  // chain_* fields of swgn_graph; chain_pose_ptr / chain_sb_ptr are the user arrays of the hidden
+  // frames (7 and 9 doubles), updated after the solve
+  int chain_m = 0;
+  std::vector<double> chain_frames, chain_frame_N, chain_N, chain_imu;
+  std::vector<double*> chain_pose_ptr, chain_sb_ptr;
 };
 // application globals the device factors read (RVI/parameter/parameters.h:88,94,100; swf.cpp:47)
 struct Globals {

@@ -256,7 +256,10 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
   std::vector<int64_t> prior_x0_begin, prior_J_begin, prior_r_begin;
   std::vector<double> proj_uv, imu_data, gnss_data, prior_x0, prior_J, prior_r0, unit_istd;
   std::vector<uint32_t> order;
-  std::vector<uint8_t> use_by_kind[5];
+  std::vector<uint8_t> use_by_kind[swgn::kNumKinds];
+  std::vector<int32_t> chain_blk_begin{0}, chain_blocks, chain_frame_begin{0};
+  std::vector<double> chain_frames, chain_frame_N, chain_N, chain_imu;
+  std::vector<double*> chain_pose_ptr, chain_sb_ptr;
   double cauchy_a = -1.0;
   bool any_masked = false;
   for (internal::ResidualBlock* rb : problem->residual_block_list()) {
@@ -316,6 +319,24 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
         unit_block.push_back(ids[0]);
         unit_istd.push_back(rec.data[0]);
         break;
+      case swgn::kChain: {
+        idx = (uint32_t)(chain_blk_begin.size() - 1);
+        const int k = (int)ids.size() - 4, m = rec.chain_m;
+        if (k < 0 || m < 1 || rec.chain_frames.size() != (size_t)m * SWGN_CHAIN_FRAME_STRIDE || rec.chain_frame_N.size() != (size_t)m * 15 * k ||
+            rec.chain_N.size() != (size_t)k * k + k || rec.chain_imu.size() != (size_t)(m + 1) * SWGN_IMU_STRIDE ||
+            rec.chain_pose_ptr.size() != (size_t)m || rec.chain_sb_ptr.size() != (size_t)m)
+          return fail(summary, "swgn shim: malformed IMUGNSSFactor chain record");
+        chain_blocks.insert(chain_blocks.end(), ids.begin(), ids.end());
+        chain_blk_begin.push_back((int32_t)chain_blocks.size());
+        chain_frame_begin.push_back(chain_frame_begin.back() + m);
+        chain_frames.insert(chain_frames.end(), rec.chain_frames.begin(), rec.chain_frames.end());
+        chain_frame_N.insert(chain_frame_N.end(), rec.chain_frame_N.begin(), rec.chain_frame_N.end());
+        chain_N.insert(chain_N.end(), rec.chain_N.begin(), rec.chain_N.end());
+        chain_imu.insert(chain_imu.end(), rec.chain_imu.begin(), rec.chain_imu.end());
+        chain_pose_ptr.insert(chain_pose_ptr.end(), rec.chain_pose_ptr.begin(), rec.chain_pose_ptr.end());
+        chain_sb_ptr.insert(chain_sb_ptr.end(), rec.chain_sb_ptr.begin(), rec.chain_sb_ptr.end());
+        break;
+      }
       default:
         return fail(summary, "swgn shim: adapter produced an unknown factor kind");
     }
@@ -324,7 +345,7 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
     any_masked |= !rb->is_use;
   }
   std::vector<uint8_t> is_use;
-  for (int k = 0; k < 5; ++k) is_use.insert(is_use.end(), use_by_kind[k].begin(), use_by_kind[k].end());
+  for (int k = 0; k < swgn::kNumKinds; ++k) is_use.insert(is_use.end(), use_by_kind[k].begin(), use_by_kind[k].end());
 
   swgn_graph g;
   std::memset(&g, 0, sizeof(g));
@@ -368,6 +389,16 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
   g.n_order = (int32_t)order.size();
   g.order = order.data();
   g.is_use = any_masked ? is_use.data() : nullptr;
+  g.n_chain = (int32_t)chain_blk_begin.size() - 1;
+  if (g.n_chain > 0) {
+    g.chain_blk_begin = chain_blk_begin.data();
+    g.chain_blocks = chain_blocks.data();
+    g.chain_frame_begin = chain_frame_begin.data();
+    g.chain_frame_data = chain_frames.data();
+    g.chain_frame_N = chain_frame_N.data();
+    g.chain_N = chain_N.data();
+    g.chain_imu_data = chain_imu.data();
+  }
 
   swgn_options o;
   swgn_default_options(&o);
@@ -414,6 +445,18 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
   if (st == SWGN_OK)
     for (size_t i = 0; i < blocks.size(); ++i)
       if (!bconst[i]) std::memcpy(blocks[i], out.data() + boff[i], sizeof(double) * bsize[i]);
+  // ---- hidden GNSS frames of the IMUGNSSFactor chains back into the arrays the factors point at
+  // (IMUGNSSBase::UpdateHiddenState writes gnss_poses[i] / gnss_speed_bias[i], gnss_imu_factor.cpp:636-645)
+  if (st == SWGN_OK && !chain_pose_ptr.empty()) {
+    int32_t nfr = 0;
+    std::vector<double> fr(16 * chain_pose_ptr.size());
+    st = swgn_batch_get_chain_frames(batch, 0, &nfr, fr.data());
+    if (st == SWGN_OK && nfr == (int32_t)chain_pose_ptr.size())
+      for (int i = 0; i < nfr; ++i) {
+        std::memcpy(chain_pose_ptr[i], fr.data() + 16 * i, sizeof(double) * 7);
+        std::memcpy(chain_sb_ptr[i], fr.data() + 16 * i + 7, sizeof(double) * 9);
+      }
+  }
   // ---- side channel (M2)
   if (st == SWGN_OK && o.n_parameter_head > 0) {
     int32_t n = 0;

@@ -101,6 +101,47 @@ class MarginalizationFactor : public ceres::CostFunction {
   bool Evaluate(double const* const*, double*, double**) const override { return false; }
   MarginalizationInfo* marginalization_info;
 };
+// RVI/factor/gnss_imu_factor.h:18-151 (the public members the device adapter reads)
+struct DynMat {
+  std::vector<double> a;
+  int cols = 0;
+  double operator()(int i, int j) const { return a[(size_t)i * cols + j]; }
+  double operator()(int i) const { return a[i]; }
+};
+struct MarginalizationInfoStub;
+struct IMUGNSSBase {
+  std::vector<double*> gnss_phase_biases, gnss_speed_bias, gnss_speed_bias_lin, gnss_poses, gnss_poses_lin;
+  DynMat phase_biases_hessians, phase_biases_rhs;
+  std::vector<Mat15> pose_hessians;
+  std::vector<DynMat> pose_phase_biases_hessians, pose_rhses;
+  std::vector<IMUFactor*> imu_factors;
+  IMUFactor* last_imu_factor = nullptr;
+  void* gnss_middle_marginfo = nullptr;
+  std::vector<std::unique_ptr<IMUFactor>> owned;
+  std::vector<std::unique_ptr<IntegrationBase>> pre;
+  std::vector<std::array<double, 16>> lin;
+};
+class IMUGNSSFactor : public ceres::CostFunction {
+ public:
+  explicit IMUGNSSFactor(IMUGNSSBase* info) : IMUGNSS_info(info) {
+    for (int s : {7, 9, 7, 9}) mutable_parameter_block_sizes()->push_back(s);
+    for (size_t i = 0; i < info->gnss_phase_biases.size(); ++i) mutable_parameter_block_sizes()->push_back(1);
+    set_num_residuals(30 + (int)info->gnss_phase_biases.size());
+  }
+  bool Evaluate(double const* const*, double*, double**) const override { return false; }
+  IMUGNSSBase* IMUGNSS_info;
+};
+void fill_preintegration(IntegrationBase& p, const double* r) {
+  for (int k = 0; k < 3; ++k) {
+    p.delta_p[k] = r[SWGN_IMU_DELTA_P + k]; p.delta_v[k] = r[SWGN_IMU_DELTA_V + k];
+    p.linearized_ba[k] = r[SWGN_IMU_LIN_BA + k]; p.linearized_bg[k] = r[SWGN_IMU_LIN_BG + k];
+    p.gyri[k] = r[SWGN_IMU_GYRI + k]; p.gyrj[k] = r[SWGN_IMU_GYRJ + k];
+  }
+  for (int k = 0; k < 4; ++k) p.delta_q.v[k] = r[SWGN_IMU_DELTA_Q + k];
+  p.sum_dt = r[SWGN_IMU_SUM_DT];
+  std::memcpy(p.jacobian.a, r + SWGN_IMU_JACOBIAN, sizeof(p.jacobian.a));
+  std::memcpy(p.sqrt_info.a, r + SWGN_IMU_SQRT_INFO, sizeof(p.sqrt_info.a));
+}
 // RVI/factor/pose_local_parameterization.cpp:5-27
 class PoseLocalParameterization : public ceres::LocalParameterization {
   bool Plus(const double* x, const double* d, double* o) const override {
@@ -133,6 +174,7 @@ void register_adapters() {
   ceres::swgn::RegisterAdapter(typeid(SppDopplerFactor), &spp_doppler<SppDopplerFactor>);
   ceres::swgn::RegisterAdapter(typeid(InitialBlackFactor), &unit_prior<InitialBlackFactor>);
   ceres::swgn::RegisterAdapter(typeid(MarginalizationFactor), &marginalization<MarginalizationFactor>);
+  ceres::swgn::RegisterAdapter(typeid(IMUGNSSFactor), &imu_gnss<IMUGNSSFactor>);
 }
 }  // namespace
 
@@ -167,10 +209,18 @@ extern "C" int swgn_ceres_demo_solve(int which, uint64_t window_id, int export_m
   std::vector<std::unique_ptr<IntegrationBase>> pre(g->n_imu);
   std::vector<std::unique_ptr<MarginalizationInfo>> marg(g->n_prior);
   std::vector<std::array<double, 9>> gnss_store(g->n_gnss);  // sat pos, sat vel, base pos
+  // the hidden GNSS frames of the IMUGNSSFactor chains live in application arrays that are NOT part of
+  // the problem (the reference removes them: gnss_imu_factor.cpp:110-113)
+  std::vector<std::unique_ptr<IMUGNSSBase>> chains(g->n_chain);
+  std::vector<int32_t> hid_pose(g->n_chain ? g->chain_frame_begin[g->n_chain] : 0), hid_sb(hid_pose.size());
+  swgn_synth_chain_frame_blocks(S, hid_pose.data(), hid_sb.data());
+  std::vector<char> hidden(g->n_blocks, 0);
+  for (size_t i = 0; i < hid_pose.size(); ++i) hidden[hid_pose[i]] = hidden[hid_sb[i]] = 1;
   int result = -1;
   {
     ceres::Problem problem;
     for (int b = 0; b < g->n_blocks; ++b) {
+      if (hidden[b]) continue;
       if (g->block_manifold[b] == SWGN_MANIFOLD_POSE) problem.AddParameterBlock(mem[b].get(), 7, new PoseLocalParameterization());
       else problem.AddParameterBlock(mem[b].get(), g->block_size[b]);
     }
@@ -184,15 +234,7 @@ extern "C" int swgn_ceres_demo_solve(int which, uint64_t window_id, int export_m
       const double* r = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
       pre[i].reset(new IntegrationBase());
       IntegrationBase& p = *pre[i];
-      for (int k = 0; k < 3; ++k) {
-        p.delta_p[k] = r[SWGN_IMU_DELTA_P + k]; p.delta_v[k] = r[SWGN_IMU_DELTA_V + k];
-        p.linearized_ba[k] = r[SWGN_IMU_LIN_BA + k]; p.linearized_bg[k] = r[SWGN_IMU_LIN_BG + k];
-        p.gyri[k] = r[SWGN_IMU_GYRI + k]; p.gyrj[k] = r[SWGN_IMU_GYRJ + k];
-      }
-      for (int k = 0; k < 4; ++k) p.delta_q.v[k] = r[SWGN_IMU_DELTA_Q + k];
-      p.sum_dt = r[SWGN_IMU_SUM_DT];
-      std::memcpy(p.jacobian.a, r + SWGN_IMU_JACOBIAN, sizeof(p.jacobian.a));
-      std::memcpy(p.sqrt_info.a, r + SWGN_IMU_SQRT_INFO, sizeof(p.sqrt_info.a));
+      fill_preintegration(p, r);
       problem.AddResidualBlock(new IMUFactor(&p), nullptr, mem[g->imu_blocks[4 * i]].get(), mem[g->imu_blocks[4 * i + 1]].get(),
                                mem[g->imu_blocks[4 * i + 2]].get(), mem[g->imu_blocks[4 * i + 3]].get());
     }
@@ -240,8 +282,56 @@ extern "C" int swgn_ceres_demo_solve(int which, uint64_t window_id, int export_m
       problem.AddResidualBlock(new MarginalizationFactor(&m), nullptr, params);
     }
     for (int i = 0; i < g->n_unit; ++i) problem.AddResidualBlock(new InitialBlackFactor(g->unit_istd[i]), nullptr, mem[g->unit_block[i]].get());
+    // chains last: the default program order of the flat graph is proj, imu, gnss, prior, unit, chain
+    {
+      size_t fn_off = 0, cn_off = 0, imu_off = 0;
+      for (int c = 0; c < g->n_chain; ++c) {
+        const int b0 = g->chain_blk_begin[c], k = g->chain_blk_begin[c + 1] - b0 - 4;
+        const int f0 = g->chain_frame_begin[c], m = g->chain_frame_begin[c + 1] - f0;
+        chains[c].reset(new IMUGNSSBase());
+        IMUGNSSBase& B = *chains[c];
+        B.lin.resize(m);
+        for (int q = 0; q < k; ++q) B.gnss_phase_biases.push_back(mem[g->chain_blocks[b0 + 4 + q]].get());
+        B.phase_biases_hessians.cols = k;
+        B.phase_biases_hessians.a.assign(g->chain_N + cn_off, g->chain_N + cn_off + (size_t)k * k);
+        B.phase_biases_rhs.a.assign(g->chain_N + cn_off + (size_t)k * k, g->chain_N + cn_off + (size_t)k * k + k);
+        for (int i = 0; i <= m; ++i) {
+          B.pre.emplace_back(new IntegrationBase());
+          fill_preintegration(*B.pre.back(), g->chain_imu_data + imu_off + (size_t)SWGN_IMU_STRIDE * i);
+          B.owned.emplace_back(new IMUFactor(B.pre.back().get()));
+          if (i < m) B.imu_factors.push_back(B.owned.back().get());
+          else B.last_imu_factor = B.owned.back().get();
+        }
+        for (int i = 0; i < m; ++i) {
+          const double* fr = g->chain_frame_data + (size_t)SWGN_CHAIN_FRAME_STRIDE * (f0 + i);
+          // current hidden state in application memory, linearisation point kept by the factor
+          std::memcpy(mem[hid_pose[f0 + i]].get(), fr + SWGN_CHAIN_POSE, sizeof(double) * 7);
+          std::memcpy(mem[hid_sb[f0 + i]].get(), fr + SWGN_CHAIN_SB, sizeof(double) * 9);
+          std::memcpy(B.lin[i].data(), fr + SWGN_CHAIN_POSE_LIN, sizeof(double) * 16);
+          B.gnss_poses.push_back(mem[hid_pose[f0 + i]].get());
+          B.gnss_speed_bias.push_back(mem[hid_sb[f0 + i]].get());
+          B.gnss_poses_lin.push_back(B.lin[i].data());
+          B.gnss_speed_bias_lin.push_back(B.lin[i].data() + 7);
+          Mat15 ph;
+          std::memcpy(ph.a, fr + SWGN_CHAIN_HESSIAN, sizeof(ph.a));
+          B.pose_hessians.push_back(ph);
+          DynMat pr, pn;
+          pr.a.assign(fr + SWGN_CHAIN_RHS, fr + SWGN_CHAIN_RHS + 15);
+          pn.cols = k;
+          pn.a.assign(g->chain_frame_N + fn_off + (size_t)15 * k * i, g->chain_frame_N + fn_off + (size_t)15 * k * (i + 1));
+          B.pose_rhses.push_back(pr);
+          B.pose_phase_biases_hessians.push_back(pn);
+        }
+        std::vector<double*> params;
+        for (int q = b0; q < g->chain_blk_begin[c + 1]; ++q) params.push_back(mem[g->chain_blocks[q]].get());
+        problem.AddResidualBlock(new IMUGNSSFactor(&B), nullptr, params);
+        fn_off += (size_t)m * 15 * k;
+        cn_off += (size_t)k * k + k;
+        imu_off += (size_t)(m + 1) * SWGN_IMU_STRIDE;
+      }
+    }
     for (int b = 0; b < g->n_blocks; ++b)
-      if (g->block_const[b]) problem.SetParameterBlockConstant(mem[b].get());
+      if (g->block_const[b] && !hidden[b]) problem.SetParameterBlockConstant(mem[b].get());
 
     ceres::Solver::Options options;
     options.linear_solver_type = ceres::DENSE_SCHUR;
@@ -252,7 +342,7 @@ extern "C" int swgn_ceres_demo_solve(int which, uint64_t window_id, int export_m
     options.device = device;
     options.linear_solver_ordering = std::make_shared<ceres::ParameterBlockOrdering>();
     for (int b = 0; b < g->n_blocks; ++b)
-      if (g->block_group[b] >= 0) options.linear_solver_ordering->AddElementToGroup(mem[b].get(), g->block_group[b]);
+      if (g->block_group[b] >= 0 && !hidden[b]) options.linear_solver_ordering->AddElementToGroup(mem[b].get(), g->block_group[b]);
     // the ambiguities to be resolved go last and are announced through the side channel
     ceres::internal::parameter_head.clear();
     int32_t info[8];

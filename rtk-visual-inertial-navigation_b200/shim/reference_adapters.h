@@ -8,6 +8,10 @@
 //   FixedIntegerFactor {N21, istd}, InitialBlackFactor {istd}
 //   MarginalizationFactor::marginalization_info -> {n, keep_block_size/idx/data, linearized_jacobians,
 //                                                   linearized_residuals}   (marginalization_factor.h:109)
+//   IMUGNSSFactor::IMUGNSS_info -> IMUGNSSBase {gnss_poses, gnss_speed_bias, gnss_poses_lin,
+//                                  gnss_speed_bias_lin, gnss_phase_biases, pose_hessians, pose_phase_biases_hessians,
+//                                  pose_rhses, phase_biases_hessians, phase_biases_rhs, imu_factors, last_imu_factor}
+//                                                 (gnss_imu_factor.h:52-77, 134)
 // Vector members are read through operator[] / operator(), so Eigen types and plain arrays both
 // work.  Register once per process, e.g.
 //   ceres::swgn::RegisterAdapter(typeid(projection_factor), &swgn_adapters::projection<projection_factor>);
@@ -99,14 +103,9 @@ bool unit_prior(const CostFunction* cf, FactorRecord* out) {  // InitialBlackFac
   out->data = {f->istd};
   return true;
 }
-// IMUFactor: P = IntegrationBase-like object reachable as f->pre_integration
-template <class F>
-bool imu(const CostFunction* cf, FactorRecord* out) {
-  const F* f = static_cast<const F*>(cf);
-  const auto* p = f->pre_integration;
-  out->kind = ceres::swgn::kImu;
-  out->data.assign(SWGN_IMU_STRIDE, 0.0);
-  double* r = out->data.data();
+// IntegrationBase-like object -> SWGN_IMU_STRIDE record
+template <class P>
+void imu_record(const P* p, double* r) {
   for (int i = 0; i < 3; ++i) {
     r[SWGN_IMU_DELTA_P + i] = p->delta_p[i];
     r[SWGN_IMU_DELTA_V + i] = p->delta_v[i];
@@ -125,6 +124,56 @@ bool imu(const CostFunction* cf, FactorRecord* out) {
       r[SWGN_IMU_JACOBIAN + i * 15 + j] = p->jacobian(i, j);
       r[SWGN_IMU_SQRT_INFO + i * 15 + j] = p->sqrt_info(i, j);
     }
+}
+// IMUFactor: P = IntegrationBase-like object reachable as f->pre_integration
+template <class F>
+bool imu(const CostFunction* cf, FactorRecord* out) {
+  const F* f = static_cast<const F*>(cf);
+  out->kind = ceres::swgn::kImu;
+  out->data.assign(SWGN_IMU_STRIDE, 0.0);
+  imu_record(f->pre_integration, out->data.data());
+  return true;
+}
+// IMUGNSSFactor: B = IMUGNSSBase-like object reachable as f->IMUGNSS_info.  The middle-marginalisation
+// link (gnss_middle_marginfo, pose1_pose2_hessians) has no device representation: such a factor is
+// reported as unsupported instead of being evaluated differently.
+template <class F>
+bool imu_gnss(const CostFunction* cf, FactorRecord* out) {
+  const F* f = static_cast<const F*>(cf);
+  const auto* b = f->IMUGNSS_info;
+  if (b->gnss_middle_marginfo) return false;
+  const int m = (int)b->gnss_poses.size(), k = (int)b->gnss_phase_biases.size();
+  if (m < 1 || (int)b->imu_factors.size() != m || !b->last_imu_factor) return false;
+  out->kind = ceres::swgn::kChain;
+  out->chain_m = m;
+  out->chain_frames.assign((size_t)m * SWGN_CHAIN_FRAME_STRIDE, 0.0);
+  out->chain_frame_N.assign((size_t)m * 15 * k, 0.0);
+  out->chain_N.assign((size_t)k * k + k, 0.0);
+  out->chain_imu.assign((size_t)(m + 1) * SWGN_IMU_STRIDE, 0.0);
+  for (int i = 0; i < m; ++i) {
+    double* fr = out->chain_frames.data() + (size_t)SWGN_CHAIN_FRAME_STRIDE * i;
+    for (int q = 0; q < 7; ++q) {
+      fr[SWGN_CHAIN_POSE + q] = b->gnss_poses[i][q];
+      fr[SWGN_CHAIN_POSE_LIN + q] = b->gnss_poses_lin[i][q];
+    }
+    for (int q = 0; q < 9; ++q) {
+      fr[SWGN_CHAIN_SB + q] = b->gnss_speed_bias[i][q];
+      fr[SWGN_CHAIN_SB_LIN + q] = b->gnss_speed_bias_lin[i][q];
+    }
+    for (int r = 0; r < 15; ++r) {
+      fr[SWGN_CHAIN_RHS + r] = b->pose_rhses[i](r);
+      for (int c = 0; c < 15; ++c) fr[SWGN_CHAIN_HESSIAN + r * 15 + c] = b->pose_hessians[i](r, c);
+      for (int c = 0; c < k; ++c) out->chain_frame_N[((size_t)i * 15 + r) * k + c] = b->pose_phase_biases_hessians[i](r, c);
+    }
+    imu_record(b->imu_factors[i]->pre_integration, out->chain_imu.data() + (size_t)SWGN_IMU_STRIDE * i);
+    out->chain_pose_ptr.push_back(b->gnss_poses[i]);
+    out->chain_sb_ptr.push_back(b->gnss_speed_bias[i]);
+  }
+  imu_record(b->last_imu_factor->pre_integration, out->chain_imu.data() + (size_t)SWGN_IMU_STRIDE * m);
+  for (int r = 0; r < k; ++r) {
+    out->chain_N[(size_t)k * k + r] = b->phase_biases_rhs(r);
+    for (int c = 0; c < k; ++c) out->chain_N[(size_t)r * k + c] = b->phase_biases_hessians(r, c);
+  }
   return true;
 }
 // MarginalizationFactor: M = MarginalizationInfo-like object reachable as f->marginalization_info

@@ -973,6 +973,14 @@ int32_t swgn_synth_ambiguity_epochs(const swgn_synth* s, int32_t* epoch_begin, i
   return ne;
 }
 const double* swgn_synth_true_ambiguities(const swgn_synth* s) { return s->true_N.data(); }
+int32_t swgn_synth_chain_frame_blocks(const swgn_synth* s, int32_t* pose_block, int32_t* sb_block) {
+  const int32_t n = (int32_t)s->chain_frame_block.size();
+  for (int32_t i = 0; i < n; ++i) {
+    if (pose_block) pose_block[i] = s->chain_frame_block[i];
+    if (sb_block) sb_block[i] = s->chain_frame_block[i] + s->info[0];  // speed-bias blocks follow the pose blocks
+  }
+  return n;
+}
 int32_t swgn_synth_chain_truth(const swgn_synth* s, double* frames16) {
   const int32_t n = (int32_t)(s->chain_frame_truth.size() / 16);
   if (frames16) std::memcpy(frames16, s->chain_frame_truth.data(), sizeof(double) * s->chain_frame_truth.size());

@@ -64,6 +64,9 @@ const double* swgn_synth_true_ambiguities(const swgn_synth* s);
 /* ground truth of the hidden GNSS frames of the chain factors (16 doubles per frame, graph order);
    returns the number of hidden frames, frames16 may be NULL */
 int32_t swgn_synth_chain_truth(const swgn_synth* s, double* frames16);
+/* the (unreferenced) parameter blocks of the graph that hold the hidden frames' states in the
+   application's memory layout: pose and speed-bias block index per hidden frame */
+int32_t swgn_synth_chain_frame_blocks(const swgn_synth* s, int32_t* pose_block, int32_t* sb_block);
 
 #ifdef __cplusplus
 }

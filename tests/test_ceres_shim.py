@@ -82,3 +82,38 @@ def test_export_mode_through_side_channel():
     S = mat[:n * n].reshape(n, n)
     assert np.linalg.norm(np.triu(S) - np.triu(oS)) / np.linalg.norm(np.triu(oS)) < 1e-12
     assert np.linalg.norm(rhs[:n] - orr) / np.linalg.norm(orr) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,wid", [(4, 0), (3, 1)])
+def test_imu_gnss_factor_through_ceres_api(which, wid):
+    """IMUGNSSFactor objects (same public members as RVI/factor/gnss_imu_factor.h) added through
+    ceres::Problem::AddResidualBlock: the shim's adapter turns them into chain records, the solve
+    equals the direct C-ABI solve bit for bit, and the hidden GNSS frames are written back into
+    the application arrays the factor points at."""
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    rc, state, cost, steps, hs, mat, rhs, msg = run_demo(which, wid, 0, w.n_state, o.n_f)
+    assert rc >= 0, msg
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    hf = b.chain_frames(0)
+    g = w.graph
+    off = w.block_offsets()
+    L = swgn.synth_lib()
+    n = g.chain_frame_begin[g.n_chain]
+    pb, sb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    L.swgn_synth_chain_frame_blocks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.swgn_synth_chain_frame_blocks(w.h, pb.ctypes.data_as(C.POINTER(C.c_int32)), sb.ctypes.data_as(C.POINTER(C.c_int32)))
+    hidden = np.zeros(w.n_state, bool)
+    for i in range(n):
+        hidden[off[pb[i]]:off[pb[i]] + 7] = True
+        hidden[off[sb[i]]:off[sb[i]] + 9] = True
+        assert np.array_equal(state[off[pb[i]]:off[pb[i]] + 7], hf[i, :7])
+        assert np.array_equal(state[off[sb[i]]:off[sb[i]] + 9], hf[i, 7:])
+    assert not np.array_equal(hf, w.chain_frames0())
+    assert np.array_equal(state[~hidden], x[~hidden])
+    assert cost[1] == sm.final_cost and steps == [sm.num_successful_steps, sm.num_unsuccessful_steps]
+    b.close()
