@@ -22,7 +22,7 @@
 namespace swgn {
 namespace {
 
-constexpr int NT = 64;
+constexpr int NT = 256;
 enum { B_P1 = 0, B_P2 = 1, B_N = 2, B_P0 = 3 };
 constexpr double kEigEps = 1e-8;  // gnss_imu_factor.cpp:9
 
@@ -43,10 +43,10 @@ struct Sm {
     r15 = o; o += 16;
     dx = o; o += 16;
     nval = o; o += k + 1;
-    A = o; o += n * n;
-    V = o; o += n * n;
+    A = o; o += n * (n | 1);
+    V = o; o += n * (n | 1);
     rd = o; o += n;
-    cs = o; o += 2 * n;
+    cs = o; o += 4 * ((n + 1) / 2) + 4;
     red = o; o += 34;
     total = o;
   }
@@ -82,7 +82,7 @@ __device__ void inc15(const double* x, const double* x0, const double* s, const 
 
 }  // namespace
 
-__global__ void __launch_bounds__(NT) k_chain(DeviceBatch b, int mode, int only_window) {
+__global__ void __launch_bounds__(NT, 2) k_chain(DeviceBatch b, int mode, int only_window) {
   __shared__ WinDesc sd;
   extern __shared__ double sm[];
   const int w = only_window >= 0 ? only_window : blockIdx.x;
@@ -377,82 +377,152 @@ __global__ void __launch_bounds__(NT) k_chain(DeviceBatch b, int mode, int only_
     // triangle mirrored (selfadjointView<Upper>)
     double* A = sm + S.A;
     double* V = sm + S.V;
-    {
+    const int ld = n | 1;
+    auto assemble = [&]() {
       for (int o = tid; o < n * n; o += NT) {
         int ra = o / n, cb = o - ra * n;
         if (cb < ra) { const int t = ra; ra = cb; cb = t; }
         const int i = ra < 15 ? 0 : (ra < 30 ? 1 : 2), j = cb < 15 ? 0 : (cb < 30 ? 1 : 2);
         const int a = ra - 15 * i, bb = cb - 15 * j;
         const int i2 = i == 0 ? B_P0 : (i == 1 ? B_P1 : B_N), j2 = j == 0 ? B_P0 : (j == 1 ? B_P1 : B_N);
-        A[o] = (j2 >= i2) ? sm[S.H(i2, j2) + a * S.size(j2) + bb] : sm[S.H(j2, i2) + bb * S.size(i2) + a];
-        V[o] = (o / n == o % n) ? 1.0 : 0.0;
+        A[(o / n) * ld + (o % n)] = (j2 >= i2) ? sm[S.H(i2, j2) + a * S.size(j2) + bb] : sm[S.H(j2, i2) + bb * S.size(i2) + a];
+        V[(o / n) * ld + (o % n)] = (o / n == o % n) ? 1.0 : 0.0;
       }
       for (int q = tid; q < n; q += NT) sm[S.rd + q] = q < 15 ? sm[S.rhs(B_P0) + q] : (q < 30 ? sm[S.rhs(B_P1) + q - 15] : sm[S.rhs(B_N) + q - 30]);
       __syncthreads();
+    };
+    assemble();
+    // Fast path: when H is safely positive definite no eigenvalue is dropped, and ANY square root gives the
+    // solver the same J'J = H, J'r = rhs and |r|^2 = rhs' H^-1 rhs as the reference's sqrt(S) V'.  Try the
+    // Cholesky factor H = L L' (J = L', r = L^-1 rhs) and accept it when 1 / trace(H^-1) = 1 / |L^-1|_F^2,
+    // a lower bound of the smallest eigenvalue, clears the reference's 1e-8 threshold with margin;
+    // otherwise fall through to the eigen-decomposition, which is what drops eigenvalues <= 1e-8.
+    bool use_chol = false;
+    {
+      bool ok = true;
+      for (int j = 0; j < n; ++j) {
+        const double piv = A[j * ld + j];
+        if (!(piv > 0.0) || !finite_d(piv)) { ok = false; break; }  // uniform: every thread reads the same value
+        const double dinv = 1.0 / sqrt(piv);
+        __syncthreads();
+        for (int i = j + tid; i < n; i += NT) A[i * ld + j] = (i == j) ? sqrt(piv) : A[i * ld + j] * dinv;
+        __syncthreads();
+        // trailing update of the lower triangle: A[i][c] -= L[i][j] L[c][j], j < c <= i
+        const int rem = n - 1 - j;
+        for (int o = tid; o < rem * rem; o += NT) {
+          const int i = j + 1 + o / rem, c = j + 1 + o % rem;
+          if (c <= i) A[i * ld + c] -= A[i * ld + j] * A[c * ld + j];
+        }
+        __syncthreads();
+      }
+      if (ok) {
+        // X = L^-1 (lower), one thread per column, into V
+        __syncthreads();
+        double fro = 0.0;
+        for (int c = tid; c < n; c += NT) {
+          for (int i = 0; i < n; ++i) {
+            double acc = (i == c) ? 1.0 : 0.0;
+            if (i < c) { V[i * ld + c] = 0.0; continue; }
+            for (int q = c; q < i; ++q) acc -= A[i * ld + q] * V[q * ld + c];
+            acc /= A[i * ld + i];
+            V[i * ld + c] = acc;
+            fro += acc * acc;
+          }
+        }
+        fro = block_sum(fro, sm + S.red);
+        use_chol = finite_d(fro) && fro > 0.0 && 1.0 / fro > 16.0 * kEigEps;
+      }
+      __syncthreads();
+      if (use_chol) {
+        double* Jd = Wk + L.w_J;
+        double* rdst = Wk + L.w_r;
+        for (int o = tid; o < n * n; o += NT) {
+          const int i = o / n, cc = o - i * n;
+          Jd[o] = cc >= i ? A[cc * ld + i] : 0.0;  // J = L'
+        }
+        for (int i = tid; i < n; i += NT) {
+          double acc = 0.0;
+          for (int cc = 0; cc <= i; ++cc) acc += V[i * ld + cc] * sm[S.rd + cc];
+          rdst[i] = acc;
+        }
+        __syncthreads();
+      } else {
+        assemble();  // A and V were used as scratch: rebuild H and V = I from the blocks
+      }
     }
+    if (!use_chol) {
     // symmetric eigen-decomposition: two-sided Jacobi, round-robin (tournament) ordering, np/2 disjoint
-    // rotations per step; columns then rows of A, columns of V
+    // rotations per step: columns of A and V, then rows of A.  One warp per rotation pair, lanes over the
+    // rows / columns; the leading dimension is odd so that the column pass stays off shared-memory banks.
     {
       const int np = (n + 1) & ~1;  // players (an odd n gets a bye)
       const int half = np / 2;
+      const int wid = tid >> 5, nwarp = NT / 32;
       for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0, dg = 0.0;
-        for (int o = tid; o < n * n; o += NT) {
-          const int ra = o / n, cb = o - ra * n;
-          const double val = A[o] * A[o];
-          if (ra == cb) dg += val;
-          else if (cb > ra) off += val;
-        }
+        for (int ra = wid; ra < n; ra += nwarp)
+          for (int cb = lane; cb < n; cb += 32) {
+            const double val = A[ra * ld + cb] * A[ra * ld + cb];
+            if (ra == cb) dg += val;
+            else if (cb > ra) off += val;
+          }
         off = block_sum(off, sm + S.red);
         dg = block_sum(dg, sm + S.red);
-        if (off <= 1e-32 * (dg + 1e-300)) break;
+        if (off <= 1e-30 * (dg + 1e-300)) break;
         for (int step = 0; step < np - 1; ++step) {
-          // pair t of this step: players a, b (circle method, player np-1 fixed)
+          // pair t of this step: players pa, pb (circle method, player np-1 fixed)
           if (tid < half) {
-            int pa = (tid == 0) ? np - 1 : (step + tid) % (np - 1);
-            int pb = (step + np - 1 - tid) % (np - 1);
-            int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
+            const int pa = (tid == 0) ? np - 1 : (step + tid) % (np - 1);
+            const int pb = (step + np - 1 - tid) % (np - 1);
+            int pp = pa < pb ? pa : pb;
+            const int qq = pa < pb ? pb : pa;
             double cth = 1.0, sth = 0.0;
-            if (q < n) {
-              const double apq = A[p * n + q];
+            if (qq < n) {
+              const double apq = A[pp * ld + qq];
               if (apq != 0.0) {
-                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double theta = (A[qq * ld + qq] - A[pp * ld + pp]) / (2.0 * apq);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 cth = 1.0 / sqrt(t * t + 1.0);
                 sth = t * cth;
+              } else {
+                pp = -1;  // nothing to rotate
               }
+            } else {
+              pp = -1;    // the bye
             }
-            sm[S.cs + 2 * tid] = cth;
-            sm[S.cs + 2 * tid + 1] = sth;
+            sm[S.cs + 4 * tid] = cth;
+            sm[S.cs + 4 * tid + 1] = sth;
+            sm[S.cs + 4 * tid + 2] = (double)pp;
+            sm[S.cs + 4 * tid + 3] = (double)qq;
           }
           __syncthreads();
-          // columns: A <- A R, V <- V R   (work item = (pair, row))
-          for (int o = tid; o < half * n; o += NT) {
-            const int t = o / n, kk = o - t * n;
-            int pa = (t == 0) ? np - 1 : (step + t) % (np - 1);
-            int pb = (step + np - 1 - t) % (np - 1);
-            const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
-            if (q >= n) continue;
-            const double cth = sm[S.cs + 2 * t], sth = sm[S.cs + 2 * t + 1];
-            const double akp = A[kk * n + p], akq = A[kk * n + q];
-            A[kk * n + p] = cth * akp - sth * akq;
-            A[kk * n + q] = sth * akp + cth * akq;
-            const double vkp = V[kk * n + p], vkq = V[kk * n + q];
-            V[kk * n + p] = cth * vkp - sth * vkq;
-            V[kk * n + q] = sth * vkp + cth * vkq;
+          for (int t = wid; t < half; t += nwarp) {  // columns: A <- A R, V <- V R
+            const int pp = (int)sm[S.cs + 4 * t + 2];
+            if (pp < 0) continue;
+            const int qq = (int)sm[S.cs + 4 * t + 3];
+            const double cth = sm[S.cs + 4 * t], sth = sm[S.cs + 4 * t + 1];
+            for (int kk = lane; kk < n; kk += 32) {
+              const double akp = A[kk * ld + pp], akq = A[kk * ld + qq];
+              A[kk * ld + pp] = cth * akp - sth * akq;
+              A[kk * ld + qq] = sth * akp + cth * akq;
+              const double vkp = V[kk * ld + pp], vkq = V[kk * ld + qq];
+              V[kk * ld + pp] = cth * vkp - sth * vkq;
+              V[kk * ld + qq] = sth * vkp + cth * vkq;
+            }
           }
           __syncthreads();
-          // rows: A <- R' A
-          for (int o = tid; o < half * n; o += NT) {
-            const int t = o / n, kk = o - t * n;
-            int pa = (t == 0) ? np - 1 : (step + t) % (np - 1);
-            int pb = (step + np - 1 - t) % (np - 1);
-            const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
-            if (q >= n) continue;
-            const double cth = sm[S.cs + 2 * t], sth = sm[S.cs + 2 * t + 1];
-            const double apk = A[p * n + kk], aqk = A[q * n + kk];
-            A[p * n + kk] = cth * apk - sth * aqk;
-            A[q * n + kk] = sth * apk + cth * aqk;
+          for (int t = wid; t < half; t += nwarp) {  // rows: A <- R' A
+            const int pp = (int)sm[S.cs + 4 * t + 2];
+            if (pp < 0) continue;
+            const int qq = (int)sm[S.cs + 4 * t + 3];
+            const double cth = sm[S.cs + 4 * t], sth = sm[S.cs + 4 * t + 1];
+            for (int kk = lane; kk < n; kk += 32) {
+              const double apk = A[pp * ld + kk], aqk = A[qq * ld + kk];
+              A[pp * ld + kk] = cth * apk - sth * aqk;
+              A[qq * ld + kk] = sth * apk + cth * aqk;
+            }
+            __syncwarp();
+            if (lane == 0) A[pp * ld + qq] = A[qq * ld + pp] = 0.0;  // annihilated exactly
           }
           __syncthreads();
         }
@@ -464,17 +534,18 @@ __global__ void __launch_bounds__(NT) k_chain(DeviceBatch b, int mode, int only_
       double* rdst = Wk + L.w_r;
       for (int o = tid; o < n * n; o += NT) {
         const int i = o / n, cc = o - i * n;
-        const double lam = A[i * n + i];
-        Jd[o] = (lam > kEigEps ? sqrt(lam) : 0.0) * V[cc * n + i];
+        const double lam = A[i * ld + i];
+        Jd[o] = (lam > kEigEps ? sqrt(lam) : 0.0) * V[cc * ld + i];
       }
       for (int i = tid; i < n; i += NT) {
-        const double lam = A[i * n + i];
+        const double lam = A[i * ld + i];
         double acc = 0.0;
-        for (int cc = 0; cc < n; ++cc) acc += V[cc * n + i] * sm[S.rd + cc];
+        for (int cc = 0; cc < n; ++cc) acc += V[cc * ld + i] * sm[S.rd + cc];
         rdst[i] = (lam > kEigEps ? sqrt(1.0 / lam) : 0.0) * acc;
       }
       __syncthreads();
     }
+    }  // !use_chol
   }
 
   // UpdateJacobResidual :495-530

@@ -283,6 +283,53 @@ def test_gpu_chain_evaluation_matches_oracle(which, wid):
     b.close()
 
 
+def _drop_first_phase_bias_information(w):
+    """Zero everything the chains know about their first phase bias: each chain's information matrix
+    gets an exactly singular row/column, which the reference's eigen factorisation drops
+    (gnss_imu_factor.cpp:480-491) and which sends k_chain down its eigen-decomposition path."""
+    g = w.graph
+    fN = 0
+    cN = 0
+    for c in range(g.n_chain):
+        k = g.chain_blk_begin[c + 1] - g.chain_blk_begin[c] - 4
+        m = g.chain_frame_begin[c + 1] - g.chain_frame_begin[c]
+        a = np.ctypeslib.as_array(g.chain_frame_N, shape=(fN + m * 15 * k,))[fN:].reshape(m, 15, k)
+        a[:, :, 0] = 0.0
+        nn = np.ctypeslib.as_array(g.chain_N, shape=(cN + k * k + k,))[cN:]
+        nn[:k * k].reshape(k, k)[0, :] = 0.0
+        nn[:k * k].reshape(k, k)[:, 0] = 0.0
+        nn[k * k] = 0.0
+        fN += m * 15 * k
+        cN += k * k + k
+
+
+@pytest.mark.gpu
+def test_gpu_chain_with_singular_information_uses_the_eigen_path():
+    w = swgn.SynthWindow(4, 0)
+    _drop_first_phase_bias_information(w)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    b = swgn.Batch([w.graph_p], opt)
+    cost, r, g = b.evaluate(0, o.n_res, o.n_cols)
+    ocost, orr, og, oJ = o.evaluate()
+    J = b.dense_jacobian(0, o.n_res, o.n_cols)
+    cols = o.columns()
+    for c, (ro, n) in enumerate(chain_rows(w, o.rows())):
+        idx, _ = chain_columns(w, c, cols)
+        Jc, oJc = J[ro:ro + n][:, idx], oJ[ro:ro + n][:, idx]
+        assert np.all(Jc[:, 30] == 0.0) and np.all(oJc[:, 30] == 0.0)  # nothing known about N_0
+        assert (np.abs(Jc).sum(axis=1) == 0).sum() >= 1                  # at least one dropped eigenvalue
+        H, oH = Jc.T @ Jc, oJc.T @ oJc
+        assert np.abs(H - oH).max() < 1e-10 * np.abs(oH).max()
+        gg, ogg = Jc.T @ r[ro:ro + n], oJc.T @ orr[ro:ro + n]
+        assert np.abs(gg - ogg).max() < 1e-8 * max(1.0, np.abs(ogg).max())
+    assert abs(cost - ocost) < 1e-6 * ocost
+    sm = b.solve()[0]
+    st, osm = o.minimize()
+    assert abs(sm.final_cost - osm.final_cost) < TOL_CHAIN_COST * osm.final_cost
+    b.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which,wid", [(4, 0), (4, 1), (3, 0)])
 def test_gpu_chain_full_solve_matches_oracle(which, wid):
