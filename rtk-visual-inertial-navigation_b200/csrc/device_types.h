@@ -55,6 +55,9 @@ enum IArr {
   I_ECELL,          // [n_ecells * 8] raw chunk products of the 4..16-dim e-blocks, same record as I_SCELL
                     //                 with field 2 = output offset (W_EFAC for the [E'E | E'b] cell, W_EBUF for E'F)
   I_ECELL_G,        // [n_ecells] W_EBUF offset of E'b for the diagonal cell, -1 otherwise
+  I_WSTREAM,        // [n_wstream * 4] per-warp gather streams of the reduced system (phase 2 of k_schur): stages of
+                    //                 1 + SCHUR_STAGE 16-byte records, see "gather stream" below
+  I_WSTREAM_PTR,    // [SCHUR_WARPS + 1] first STAGE of every warp's stream
   I_PROJ,           // [n_proj * 8]  state_off[3], jac_off[3], res_off, 0
   I_IMU,            // [n_imu * 12]  state_off[4], jac_off[4], res_off, 0,0,0
   I_GNSS,           // [n_gnss * 8]  kind, state_off[3], jac_off[3], res_off
@@ -72,6 +75,17 @@ enum IArr {
 // Blocks with more than 4 rows are split into slabs of <= 4 rows by the planner, so every entry is one MMA:
 //   word0 = a (28 bits) | rows-1 << 28 | subtract << 30 ;  word1 = b ;  diagonal cells: word2 = b2, word3 = 0
 // b2 is the offset of the m-vector paired with A for the rhs column: b or w_g.
+
+// Gather stream of the reduced system.  The 8x8 output tiles of all touched block cells of S are dealt to the
+// SCHUR_WARPS warps of the window's CTA (longest first onto the least loaded warp); every warp gets ONE linear
+// stream of stages, each stage = one 16-byte header + SCHUR_STAGE 16-byte term entries of the same tile:
+//   header: w0 = S offset of the block cell (row * ld + col), w1 = first S row of block p,
+//           w2 = 1 when the tile ends with this stage (store it), w3 = meta
+//   term:   w0 = a (28 bits) | rows-1 << 28 | subtract << 30 | padding << 31,  w1 = b,
+//           w2 = b2 (rhs operand of diagonal cells), w3 = 0
+// meta = ps | qs << 6 | (ti / 8) << 12 | (tj / 8) << 15 | diag << 18.  A tile's term list is padded to a multiple
+// of SCHUR_STAGE with entries whose loads are switched off, so a stage is straight-line code.
+enum { SCHUR_WARPS = 8, SCHUR_STAGE = 8 };
 
 enum CArr {
   C_GLOBALS = 0,  // Pbg[3], gravity[3], proj_sqrt_info[4], cauchy_a, pad -> 12
@@ -160,7 +174,7 @@ struct WinDesc {
   int32_t n_state, n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_cells, n_chunks, n_slots;
   int32_t n_jac, n_ebuf, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, n_efac, n_head;
   int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, n_ecells;
-  int32_t n_chain, n_chain_frames, max_chain_k, pad_chain;
+  int32_t n_chain, n_chain_frames, max_chain_k, n_wstream;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

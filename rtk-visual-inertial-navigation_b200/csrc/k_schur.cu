@@ -147,6 +147,146 @@ __device__ __forceinline__ void gather_tile(const double* JW, const int32_t* ste
   out1 = c1 + d1;
 }
 
+// ---- phase 2: per-warp gather streams with a descriptor ring in shared memory -----------------------
+// Every warp owns one linear stream of stages (plan.cpp, "gather stream": a 16-byte header plus SCHUR_STAGE
+// 16-byte term descriptors of one output tile) and consumes it stage by stage:
+//   D(s): header + 8 descriptors of stage s, global -> shared ring by asynchronous copies (cp.async, one
+//         16-byte copy per lane < 9, completion tracked per commit group), issued three stages ahead of use
+//   O(s): the 16 operand fragments of stage s, predicated global loads, straight-line
+//   C(s): 8 FP64 tensor-core MMAs into two alternating accumulator pairs; the tile is stored when the header
+//         says it is complete (each element of S is written exactly once)
+// The descriptors are already in shared memory when a stage starts, so the dependent descriptor -> operand ->
+// MMA chain of the gather costs ONE memory round trip per stage instead of two.  Measured alternatives: 8-byte
+// cp.async copies of the operands into shared rings (LDGSTS issues far below LDG rate at this granularity: 1.5x
+// slower than the direct gather), and operand loads one stage ahead in registers (kRegPipeline below).
+constexpr int kStageRecs = SCHUR_STAGE + 1;  // header + terms
+#ifndef SWGN_REG_PIPELINE
+#define SWGN_REG_PIPELINE 0
+#endif
+#ifndef SWGN_SCHUR_CTAS
+#define SWGN_SCHUR_CTAS 3
+#endif
+// operand loads one stage ahead in registers: 128 registers -> 2 CTAs/SM, measured 4.65 ms per 2048-window launch
+// against 3.56 ms for loads issued in the consuming stage at 80 registers / 3 CTAs/SM (and 4.31 ms before the ring)
+constexpr bool kRegPipeline = SWGN_REG_PIPELINE != 0;
+struct GatherRings {
+  int4 dq[4][kStageRecs + 3];  // descriptor ring: stages k .. k+3 (padded to 12 records)
+};
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// lane constants of one output tile, derived from the meta word of the stage header
+struct TileLane {
+  int meta, a_lo, b_lo;
+  bool a_ok, b_any, b_rhs;
+};
+__device__ __forceinline__ void tile_lane(int meta, int la, int lb, TileLane& T) {
+  T.meta = meta;
+  const int ps = meta & 63, qs = (meta >> 6) & 63, ti = ((meta >> 12) & 7) * 8, tj = ((meta >> 15) & 7) * 8;
+  const int diag = (meta >> 18) & 1;
+  const int ai = ti + lb, bj = tj + lb;
+  T.a_ok = ai < ps;
+  const bool b_ok = bj < qs;
+  T.b_rhs = diag && bj == qs;
+  T.a_lo = T.a_ok ? la * ps + ai : 0;
+  T.b_lo = T.b_rhs ? la : (b_ok ? la * qs + bj : 0);
+  T.b_any = b_ok || T.b_rhs;
+}
+
+// operand fragments of one stage: plain global loads into registers, issued a full stage ahead of use;
+// straight-line (padding entries and out-of-block lanes are predicated off and contribute zeros)
+__device__ __forceinline__ void load_stage(const double* JW, const int4* dq, int la, int lb, TileLane& T, double (&av)[SCHUR_STAGE],
+                                           double (&bv)[SCHUR_STAGE]) {
+  const int meta = dq[0].w;
+  if (meta != T.meta) tile_lane(meta, la, lb, T);  // warp-uniform, once per tile
+#pragma unroll
+  for (int e = 0; e < SCHUR_STAGE; ++e) {
+    const int4 t = dq[1 + e];
+    const bool ok = t.x >= 0 && la <= ((t.x >> 28) & 3);
+    const double a = (ok && T.a_ok) ? ld_global(JW + (T.a_lo + (t.x & 0x0fffffff))) : 0.0;
+    av[e] = (t.x & (1 << 30)) ? -a : a;
+    bv[e] = (ok && T.b_any) ? ld_global(JW + (T.b_lo + (T.b_rhs ? t.z : t.y))) : 0.0;
+  }
+}
+
+__device__ void gather_stream(const double* JW, const int4* gs, int n_stage, GatherRings& R, int lane, double* S, int ld, int nf,
+                              const double* lmd_f /* LM diagonal of the f-blocks */) {
+  const int la = lane & 3, lb = lane >> 2;
+  TileLane T;
+  T.meta = -1;
+  T.a_lo = T.b_lo = 0;
+  T.a_ok = T.b_any = T.b_rhs = false;
+  auto issue_d = [&](int s) {
+    if (s < n_stage && lane < kStageRecs) cp_async16(&R.dq[s & 3][lane], gs + (size_t)s * kStageRecs + lane);
+    cp_async_commit();
+  };
+  if (n_stage <= 0) return;
+  issue_d(0);
+  issue_d(1);
+  issue_d(2);
+  cp_async_wait<2>();  // D(0)
+  __syncwarp();
+  double av[SCHUR_STAGE], bv[SCHUR_STAGE];
+  if (kRegPipeline) load_stage(JW, R.dq[0], la, lb, T, av, bv);
+  double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+  for (int k = 0; k < n_stage; ++k) {
+    cp_async_wait<1>();  // D(k+1) has landed (D(k+2) may still be in flight)
+    __syncwarp();        // ... for every lane; also: all lanes are done with ring slot (k+3)&3 = (k-1)&3
+    issue_d(k + 3);
+    double an[SCHUR_STAGE], bn[SCHUR_STAGE];
+    if (kRegPipeline) {
+      if (k + 1 < n_stage) load_stage(JW, R.dq[(k + 1) & 3], la, lb, T, an, bn);
+    } else {
+      load_stage(JW, R.dq[k & 3], la, lb, T, av, bv);
+    }
+    const int4 hdr = R.dq[k & 3][0];
+#pragma unroll
+    for (int e = 0; e < SCHUR_STAGE; e += 2) {
+      dmma884(c0, c1, av[e], bv[e]);
+      dmma884(d0, d1, av[e + 1], bv[e + 1]);
+    }
+    if (hdr.z & 1) {  // the tile is complete: store it (each element of S is written exactly once)
+      const int meta = hdr.w;
+      const int ps = meta & 63, qs = (meta >> 6) & 63, ti = ((meta >> 12) & 7) * 8, tj = ((meta >> 15) & 7) * 8;
+      const int diag = (meta >> 18) & 1;
+      const int soff = hdr.x, frow = hdr.y;
+      const int i = ti + lb;
+      if (i < ps) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = tj + 2 * la + h;
+          double val = h ? (c1 + d1) : (c0 + d0);
+          if (j < qs) {
+            if (diag && i == j) {  // + D^2  (schur_eliminator_impl.h:194-215)
+              const double dd = lmd_f[frow + i];
+              val += dd * dd;
+            }
+            S[soff + (size_t)i * ld + j] = val;
+          } else if (diag && j == qs) {
+            S[(size_t)(frow + i) * ld + nf] = val;
+          }
+        }
+      }
+      c0 = c1 = d0 = d1 = 0.0;
+    }
+    if (kRegPipeline) {
+#pragma unroll
+      for (int e = 0; e < SCHUR_STAGE; ++e) {
+        av[e] = an[e];
+        bv[e] = bn[e];
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // ---- phase 1, small e-blocks (1..3): one thread per chunk, everything in registers -----------
 template <int ES>
 __device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const double* lmd) {
@@ -432,9 +572,9 @@ __device__ __forceinline__ void chunk_dispatch(const Win& v, int chunk, const do
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads, 3) k_schur(DeviceBatch b, int only_window) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads, SWGN_SCHUR_CTAS) k_schur(DeviceBatch b, int only_window) {
   __shared__ WinDesc sd;
-  extern __shared__ double dyn[];  // kChunkWarps * max_wbuf doubles
+  extern __shared__ __align__(16) double dyn[];  // phase 1: kSchurWarps * max_wbuf doubles; phase 2: the gather rings
   const int w = only_window >= 0 ? only_window : blockIdx.x / kCluster;
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
@@ -530,6 +670,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   // two cache lines per operand.  Diagonal cells carry the rhs as column qs of the B operand.
   // Terms come in runs of equal shape (plan.cpp) and are processed four at a time: eight operand
   // loads in flight per lane before the four MMAs.
+  if (b.gather_stream) {
+    const int32_t* wptr = v.I(I_WSTREAM_PTR);
+    const int4* gs = reinterpret_cast<const int4*>(v.I(I_WSTREAM)) + (size_t)wptr[wid] * kStageRecs;
+    const int n_stage = wptr[wid + 1] - wptr[wid];
+    const double* JW = v.W(W_JAC);
+    asm volatile("" : "+l"(JW));
+    GatherRings* rings = reinterpret_cast<GatherRings*>(dyn);  // phase-1 scratch is dead after the barrier
+    gather_stream(JW, gs, n_stage, rings[wid], lane, S, ld, nf, lmd + d.n_e);
+  } else
   {
     const int32_t* scell = v.I(I_SCELL);
     const int32_t* sterm = v.I(I_STERM);
@@ -713,9 +862,15 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
   }
 }
 
+static size_t schur_dyn_bytes(const DeviceBatch& b) {
+  size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  if (b.gather_stream) dyn = dyn > sizeof(GatherRings) * kSchurWarps ? dyn : sizeof(GatherRings) * kSchurWarps;
+  return dyn;
+}
+
 void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
-  const size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  const size_t dyn = schur_dyn_bytes(b);
   k_schur<<<grid * kCluster, kSchurThreads, dyn, s>>>(b, only_window);
 }
 void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
@@ -725,7 +880,8 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
 
 cudaError_t configure_schur(const DeviceBatch& b) {
   static size_t granted[64] = {0};
-  const size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
+  static_assert(kCluster == 1 && kSchurWarps == SCHUR_WARPS, "the gather streams are dealt to the warps of one CTA");
+  const size_t dyn = schur_dyn_bytes(b);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;
   int dev = 0;
   cudaGetDevice(&dev);

@@ -461,6 +461,12 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       return w * (size_t)((outs + 31) / 32) + 8;
     };
     std::stable_sort(order.begin(), order.end(), [&](const auto& x, const auto& y) { return weight(x) > weight(y); });
+    struct TileJob {
+      uint32_t meta;
+      int32_t soff, frow;
+      std::vector<T> terms;  // a, b already slab-split; b2 valid on diagonal cells
+    };
+    std::vector<TileJob> jobs;
     for (size_t ci = 0; ci < order.size(); ++ci) {
       const int p = order[ci].first.first, q = order[ci].first.second;
       const int ps = col_size[p], qs = col_size[q];
@@ -477,6 +483,15 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
         const int tiles = ((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8);
         P->n_mma += (int64_t)tiles * (int64_t)ts.size();
       }
+      for (int ti = 0; ti < ps; ti += 8)
+        for (int tj = 0; tj < qs + (diag ? 1 : 0); tj += 8) {
+          TileJob jb;
+          jb.meta = (uint32_t)ps | ((uint32_t)qs << 6) | ((uint32_t)(ti / 8) << 12) | ((uint32_t)(tj / 8) << 15) | ((diag ? 1u : 0u) << 18);
+          jb.soff = fpos(p) * ld + fpos(q);
+          jb.frow = fpos(p);
+          jb.terms = ts;
+          jobs.push_back(std::move(jb));
+        }
       if (diag)
         while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);  // 16-byte records need 16-byte alignment
       const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
@@ -489,6 +504,47 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
           I[I_STERM].push_back(0);
         }
       }
+    }
+    // deal the tiles to the warps: longest first onto the least loaded warp, then one linear stream per warp
+    {
+      std::vector<size_t> idx(jobs.size());
+      std::iota(idx.begin(), idx.end(), 0);
+      std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return jobs[x].terms.size() > jobs[y].terms.size(); });  // longest first
+      std::vector<std::vector<size_t>> mine(SCHUR_WARPS);
+      std::vector<size_t> load(SCHUR_WARPS, 0);
+      for (size_t j : idx) {
+        const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        mine[wmin].push_back(j);
+        load[wmin] += (jobs[j].terms.size() + SCHUR_STAGE - 1) / SCHUR_STAGE + 1;
+      }
+      std::vector<int32_t>& WS = I[I_WSTREAM];
+      for (int wv = 0; wv < SCHUR_WARPS; ++wv) {
+        I[I_WSTREAM_PTR].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
+        for (size_t j : mine[wv]) {
+          const TileJob& jb = jobs[j];
+          const size_t nt = jb.terms.size();
+          const size_t n_st = nt == 0 ? 1 : (nt + SCHUR_STAGE - 1) / SCHUR_STAGE;
+          for (size_t st = 0; st < n_st; ++st) {
+            WS.push_back(jb.soff);
+            WS.push_back(jb.frow);
+            WS.push_back(st + 1 == n_st ? 1 : 0);
+            WS.push_back((int32_t)jb.meta);
+            for (size_t e = st * SCHUR_STAGE; e < (st + 1) * SCHUR_STAGE; ++e) {
+              if (e < nt) {
+                const T& t = jb.terms[e];
+                WS.push_back((int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30)));
+                WS.push_back((int32_t)t.b);
+                WS.push_back((int32_t)t.b2);
+                WS.push_back(0);
+              } else {  // padding: bit 31 switches the loads off, the MMA adds zero
+                WS.push_back((int32_t)0x80000000u);
+                WS.push_back(0); WS.push_back(0); WS.push_back(0);
+              }
+            }
+          }
+        }
+      }
+      I[I_WSTREAM_PTR].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
     }
   }
   // ---- raw products of the larger e-blocks (4..16 tangent dims: the speed-bias blocks), gathered
@@ -697,6 +753,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_srows = (int)I[I_SROW].size();
   d.n_ecells = (int)I[I_ECELL_G].size();
   d.max_wbuf = max_wbuf;
+  d.n_wstream = (int)(I[I_WSTREAM].size() / 4);
   d.n_chain = g->n_chain;
   d.n_chain_frames = n_chain_frames;
   d.max_chain_k = max_chain_k;
