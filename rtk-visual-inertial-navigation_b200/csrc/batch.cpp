@@ -253,10 +253,6 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   db.max_chain = max_chain;
   db.max_chain_k = max_chain_k;
   db.chain_epoch = 1;
-  {
-    const char* gm = std::getenv("SWGN_GATHER");
-    db.gather_stream = (gm && std::string(gm) == "direct") ? 0 : 1;
-  }
   db.keep_copy = 0;
   if (std::getenv("SWGN_DEBUG_TIMELINE")) {
     CB(cudaMalloc(&b->d_debug, sizeof(long long) * 16 * n_windows));

@@ -44,11 +44,11 @@ enum IArr {
   I_CSC_VAL,        // [nnz] value offset
   I_CSC_NRES,       // [nnz] residual rows of that row block
   I_CSC_RES,        // [nnz] first residual row of that row block
-  I_SCELL,          // [n_scells * 8] reduced-system block cell: ps, qs, S offset (row*ld+col), first
-                    //                word of its terms in I_STERM, term count, diag flag (1: p == q:
+  I_SCELL,          // [n_scells * 8] directory of the touched block cells of S (the kernel reads I_WSTREAM): ps, qs,
+                    //                S offset (row*ld+col), 0, term count, diag flag (1: p == q:
                     //                add D^2, carries the rhs as an extra column), first run, run count
   I_SRUN,           // (unused)
-  I_STERM,          // [n_sterms] gather terms (see below): (a, b), or (a, b, b2, 0) on diagonal cells
+  I_STERM,          // [n_sterms] gather terms of the e-cells (see below): (a, b), or (a, b, b2, 0) on diagonal cells
   I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
   I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
   I_SROW,           // [n_srows] rows (with f-cells) of the simple chunks: one thread each in phase 1b

@@ -670,7 +670,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   // two cache lines per operand.  Diagonal cells carry the rhs as column qs of the B operand.
   // Terms come in runs of equal shape (plan.cpp) and are processed four at a time: eight operand
   // loads in flight per lane before the four MMAs.
-  if (b.gather_stream) {
+  {
     const int32_t* wptr = v.I(I_WSTREAM_PTR);
     const int4* gs = reinterpret_cast<const int4*>(v.I(I_WSTREAM)) + (size_t)wptr[wid] * kStageRecs;
     const int n_stage = wptr[wid + 1] - wptr[wid];
@@ -678,43 +678,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
     asm volatile("" : "+l"(JW));
     GatherRings* rings = reinterpret_cast<GatherRings*>(dyn);  // phase-1 scratch is dead after the barrier
     gather_stream(JW, gs, n_stage, rings[wid], lane, S, ld, nf, lmd + d.n_e);
-  } else
-  {
-    const int32_t* scell = v.I(I_SCELL);
-    const int32_t* sterm = v.I(I_STERM);
-    const double* JW = v.W(W_JAC);
-    asm volatile("" : "+l"(JW));  // keep the window base in a register pair: operand address = one IMAD.WIDE
-    const int la = lane & 3, lb = lane >> 2;
-    for (int cell = gwid; cell < d.n_scells; cell += kClusterWarps) {
-      const int32_t* sc = scell + 8 * cell;
-      const int ps = sc[0], qs = sc[1], soff = sc[2];
-      const int diag = sc[5] & 1;
-      const int nq = qs + diag;
-      const int frow = soff / ld;  // first S row of block p
-      for (int ti = 0; ti < ps; ti += 8)
-        for (int tj = 0; tj < nq; tj += 8) {
-          double c0, c1;
-          gather_tile(JW, sterm, sc, ti, tj, lane, c0, c1);
-          // C fragment: row lb, columns 2*la, 2*la+1 of the 8x8 tile
-          const int i = ti + lb;
-          if (i < ps) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int j = tj + 2 * la + h;
-              double val = h ? c1 : c0;
-              if (j < qs) {
-                if (diag && i == j) {  // + D^2  (schur_eliminator_impl.h:194-215)
-                  const double dd = lmd[d.n_e + frow + i];
-                  val += dd * dd;
-                }
-                S[soff + (size_t)i * ld + j] = val;
-              } else if (diag && j == qs) {
-                S[(size_t)(frow + i) * ld + nf] = val;
-              }
-            }
-          }
-        }
-    }
   }
   SWGN_STAMP(5);
   if (dbg) {
@@ -864,7 +827,7 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
 
 static size_t schur_dyn_bytes(const DeviceBatch& b) {
   size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
-  if (b.gather_stream) dyn = dyn > sizeof(GatherRings) * kSchurWarps ? dyn : sizeof(GatherRings) * kSchurWarps;
+  dyn = dyn > sizeof(GatherRings) * kSchurWarps ? dyn : sizeof(GatherRings) * kSchurWarps;
   return dyn;
 }
 

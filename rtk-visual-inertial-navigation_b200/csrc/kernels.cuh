@@ -23,8 +23,6 @@ struct DeviceBatch {
   int max_chain;         // max IMUGNSSFactor chains per window (0: k_chain is never launched)
   int max_chain_k;       // max phase biases per chain (shared-memory size of k_chain)
   int chain_epoch;       // bumped by create / update_inputs: chains reload their hidden states and forget history
-  int gather_stream;     // k_schur phase 2: 1 = per-warp gather streams through the async shared-memory pipeline,
-                         // 0 = the direct warp-per-cell gather (SWGN_GATHER=direct; development comparison)
   int keep_copy;         // copy S|rhs to W_SCOPY before factorising (staged test entry point)
   long long* debug;      // optional [n_windows * 8] phase timestamps of k_schur (SWGN_DEBUG_TIMELINE=1), else null
 };

@@ -492,18 +492,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
           jb.terms = ts;
           jobs.push_back(std::move(jb));
         }
-      if (diag)
-        while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);  // 16-byte records need 16-byte alignment
-      const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
-      I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);
-      for (const T& t : ts) {  // (a, b) per term, (a, b, b2, 0) on diagonal cells: 8 / 16 byte records
-        I[I_STERM].push_back((int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30)));
-        I[I_STERM].push_back((int32_t)t.b);
-        if (diag) {
-          I[I_STERM].push_back((int32_t)t.b2);
-          I[I_STERM].push_back(0);
-        }
-      }
+      const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), 0, (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
+      I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);  // cell directory (statistics / read-backs); the kernel reads the streams
     }
     // deal the tiles to the warps: longest first onto the least loaded warp, then one linear stream per warp
     {
