@@ -52,9 +52,12 @@ enum IArr {
   I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
   I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
   I_SROW,           // [n_srows] rows (with f-cells) of the simple chunks: one thread each in phase 1b
-  I_ECELL,          // [n_ecells * 8] raw chunk products of the 4..16-dim e-blocks, same record as I_SCELL
-                    //                 with field 2 = output offset (W_EFAC for the [E'E | E'b] cell, W_EBUF for E'F)
-  I_ECELL_G,        // [n_ecells] W_EBUF offset of E'b for the diagonal cell, -1 otherwise
+  I_ECELL,          // (unused)
+  I_ECELL_G,        // [1] number of e-cells (statistic)
+  I_ESTREAM,        // per-warp gather streams of the raw chunk products E'[E | b | F] of the 4..16-dim e-blocks
+                    // (phase 1a of k_schur); same stage records as I_WSTREAM with header flag bit 1 set:
+                    // w0 = output offset (W_EFAC for the [E'E | E'b] cell, W_EBUF for E'F), w1 = W_EBUF offset of E'b
+  I_ESTREAM_PTR,    // [SCHUR_WARPS + 1]
   I_WSTREAM,        // [n_wstream * 4] per-warp gather streams of the reduced system (phase 2 of k_schur): stages of
                     //                 1 + SCHUR_STAGE 16-byte records, see "gather stream" below
   I_WSTREAM_PTR,    // [SCHUR_WARPS + 1] first STAGE of every warp's stream
@@ -80,7 +83,7 @@ enum IArr {
 // SCHUR_WARPS warps of the window's CTA (longest first onto the least loaded warp); every warp gets ONE linear
 // stream of stages, each stage = one 16-byte header + SCHUR_STAGE 16-byte term entries of the same tile:
 //   header: w0 = S offset of the block cell (row * ld + col), w1 = first S row of block p,
-//           w2 = 1 when the tile ends with this stage (store it), w3 = meta
+//           w2 = bit 0: the tile ends with this stage (store it), bit 1: e-cell target, w3 = meta
 //   term:   w0 = a (28 bits) | rows-1 << 28 | subtract << 30 | padding << 31,  w1 = b,
 //           w2 = b2 (rhs operand of diagonal cells), w3 = 0
 // meta = ps | qs << 6 | (ti / 8) << 12 | (tj / 8) << 15 | diag << 18.  A tile's term list is padded to a multiple

@@ -79,74 +79,6 @@ __device__ __forceinline__ void prefetch_range(const void* base, size_t bytes, i
     prefetch_l2_bulk(p + off, (unsigned)((aligned - off) < kChunk ? (aligned - off) : kChunk));
 }
 
-// N consecutive gather terms, straight-line: the N descriptors are loaded by every lane from the same
-// address (broadcast, one cache line), all 2N operand loads are issued before the first MMA, and two
-// accumulator pairs alternate so that consecutive MMAs do not depend on each other.  No shuffles and
-// no branches inside: the scheduler sees one basic block with N independent load chains.  Every
-// descriptor packs its own row count (<= 4) and sign, so a cell is one uninterrupted stream.
-template <int N, bool DIAG>
-__device__ __forceinline__ void gather_batch(const double* JW, const int32_t* tp, bool b_rhs, bool a_ok, bool b_any, int la,
-                                             int a_lo, int b_lo, double& c0, double& c1, double& d0, double& d1) {
-  int w0[N], bo[N];
-#pragma unroll
-  for (int u = 0; u < N; ++u) {
-    if (DIAG) {
-      const int4 t = *reinterpret_cast<const int4*>(tp + 4 * u);
-      w0[u] = t.x;
-      bo[u] = b_rhs ? t.z : t.y;
-    } else {
-      const int2 t = *reinterpret_cast<const int2*>(tp + 2 * u);
-      w0[u] = t.x;
-      bo[u] = t.y;
-    }
-  }
-  double av[N], bv[N];
-#pragma unroll
-  for (int u = 0; u < N; ++u) {
-    const bool ok = la <= ((w0[u] >> 28) & 3);
-    const double a = (ok && a_ok) ? ld_global(JW + (a_lo + (w0[u] & 0x0fffffff))) : 0.0;
-    av[u] = (w0[u] & (1 << 30)) ? -a : a;
-    bv[u] = (ok && b_any) ? ld_global(JW + (b_lo + bo[u])) : 0.0;
-  }
-#pragma unroll
-  for (int u = 0; u < N; ++u) {
-    if (u & 1) dmma884(d0, d1, av[u], bv[u]);
-    else dmma884(c0, c1, av[u], bv[u]);
-  }
-}
-
-// One 8x8 tile (rows ti.., columns tj..) of a gathered block cell: C = sum_t (+/-) A_t' B_t over the
-// cell's terms.  Returns the lane's two C fragment values (row lane>>2, columns 2*(lane&3), +1).
-// `diag` cells carry one extra B column (index qs) fed from the m-vector b2.
-__device__ __forceinline__ void gather_tile(const double* JW, const int32_t* sterm, const int32_t* sc, int ti, int tj, int lane,
-                                            double& out0, double& out1) {
-  const int la = lane & 3, lb = lane >> 2;
-  const int ps = sc[0], qs = sc[1], cnt = sc[4];
-  const int diag = sc[5] & 1;
-  const int ai = ti + lb, bj = tj + lb;
-  const bool a_ok = ai < ps, b_ok = bj < qs, b_rhs = diag && bj == qs;
-  // lane offsets inside a 4-row slab (32-bit: one IMAD.WIDE per operand address)
-  const int a_lo = a_ok ? la * ps + ai : 0;
-  const int b_lo = b_rhs ? la : (b_ok ? la * qs + bj : 0);
-  const bool b_any = b_ok || b_rhs;
-  double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-  const int32_t* tp = sterm + sc[3];
-  int k = 0;
-  if (diag) {
-    for (; k + 8 <= cnt; k += 8) gather_batch<8, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
-    if (k + 4 <= cnt) { gather_batch<4, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 4; }
-    if (k + 2 <= cnt) { gather_batch<2, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 2; }
-    if (k < cnt) gather_batch<1, true>(JW, tp + 4 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
-  } else {
-    for (; k + 8 <= cnt; k += 8) gather_batch<8, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
-    if (k + 4 <= cnt) { gather_batch<4, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 4; }
-    if (k + 2 <= cnt) { gather_batch<2, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1); k += 2; }
-    if (k < cnt) gather_batch<1, false>(JW, tp + 2 * k, b_rhs, a_ok, b_any, la, a_lo, b_lo, c0, c1, d0, d1);
-  }
-  out0 = c0 + d0;
-  out1 = c1 + d1;
-}
-
 // ---- phase 2: per-warp gather streams with a descriptor ring in shared memory -----------------------
 // Every warp owns one linear stream of stages (plan.cpp, "gather stream": a 16-byte header plus SCHUR_STAGE
 // 16-byte term descriptors of one output tile) and consumes it stage by stage:
@@ -216,8 +148,11 @@ __device__ __forceinline__ void load_stage(const double* JW, const int4* dq, int
   }
 }
 
-__device__ void gather_stream(const double* JW, const int4* gs, int n_stage, GatherRings& R, int lane, double* S, int ld, int nf,
-                              const double* lmd_f /* LM diagonal of the f-blocks */) {
+// ECELL = false: tiles of the reduced system -> S (out0), row stride ld, rhs in column nf, + D^2 on the diagonal;
+// ECELL = true: raw chunk products -> W_EFAC (out0, [E'E] of diagonal cells) / W_EBUF (out1, E'F and E'b)
+template <bool ECELL>
+__device__ void gather_stream(const double* JW, const int4* gs, int n_stage, GatherRings& R, int lane, double* out0, double* out1, int ld,
+                              int nf, const double* lmd_f /* LM diagonal of the f-blocks */) {
   const int la = lane & 3, lb = lane >> 2;
   TileLane T;
   T.meta = -1;
@@ -263,14 +198,17 @@ __device__ void gather_stream(const double* JW, const int4* gs, int n_stage, Gat
         for (int h = 0; h < 2; ++h) {
           const int j = tj + 2 * la + h;
           double val = h ? (c1 + d1) : (c0 + d0);
-          if (j < qs) {
+          if (ECELL) {
+            if (j < qs) (diag ? out0 : out1)[soff + i * qs + j] = val;
+            else if (diag && j == qs) out1[frow + i] = val;
+          } else if (j < qs) {
             if (diag && i == j) {  // + D^2  (schur_eliminator_impl.h:194-215)
               const double dd = lmd_f[frow + i];
               val += dd * dd;
             }
-            S[soff + (size_t)i * ld + j] = val;
+            out0[soff + (size_t)i * ld + j] = val;
           } else if (diag && j == qs) {
-            S[(size_t)(frow + i) * ld + nf] = val;
+            out0[(size_t)(frow + i) * ld + nf] = val;
           }
         }
       }
@@ -607,35 +545,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   {
     const int32_t* tch = v.I(I_TCHUNK);
     for (int k = gtid; k < d.n_tchunks; k += kClusterThreads) chunk_dispatch(v, tch[k], lmd);
-    const int32_t* ecell = v.I(I_ECELL);
-    const int32_t* ecell_g = v.I(I_ECELL_G);
-    const int32_t* sterm = v.I(I_STERM);
+    const int32_t* eptr = v.I(I_ESTREAM_PTR);
+    const int4* gs = reinterpret_cast<const int4*>(v.I(I_ESTREAM)) + (size_t)eptr[wid] * kStageRecs;
     const double* JWc = v.W(W_JAC);
     asm volatile("" : "+l"(JWc));
-    double* EF = v.W(W_EFAC);
-    double* EBw = v.W(W_EBUF);
-    const int la = lane & 3, lb = lane >> 2;
-    for (int cell = gwid; cell < d.n_ecells; cell += kClusterWarps) {
-      const int32_t* sc = ecell + 8 * cell;
-      const int ps = sc[0], qs = sc[1], out = sc[2], diag = sc[5] & 1;
-      const int nq = qs + diag;
-      for (int ti = 0; ti < ps; ti += 8)
-        for (int tj = 0; tj < nq; tj += 8) {
-          if (diag && tj + 7 < ti) continue;  // E'E: upper triangle only
-          double c0, c1;
-          gather_tile(JWc, sterm, sc, ti, tj, lane, c0, c1);
-          const int i = ti + lb;
-          if (i < ps) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int j = tj + 2 * la + h;
-              const double val = h ? c1 : c0;
-              if (j < qs) (diag ? EF : EBw)[out + i * qs + j] = val;
-              else if (diag && j == qs) EBw[ecell_g[cell] + i] = val;
-            }
-          }
-        }
-    }
+    GatherRings* rings = reinterpret_cast<GatherRings*>(dyn);
+    gather_stream<true>(JWc, gs, eptr[wid + 1] - eptr[wid], rings[wid], lane, v.W(W_EFAC), v.W(W_EBUF), 0, 0, nullptr);
   }
   SWGN_STAMP(2);
   cluster_sync();
@@ -677,7 +592,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
     const double* JW = v.W(W_JAC);
     asm volatile("" : "+l"(JW));
     GatherRings* rings = reinterpret_cast<GatherRings*>(dyn);  // phase-1 scratch is dead after the barrier
-    gather_stream(JW, gs, n_stage, rings[wid], lane, S, ld, nf, lmd + d.n_e);
+    gather_stream<false>(JW, gs, n_stage, rings[wid], lane, S, nullptr, ld, nf, lmd + d.n_e);
   }
   SWGN_STAMP(5);
   if (dbg) {

@@ -416,6 +416,57 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   if ((int64_t)n_jac_al + n_ebuf_al + n_res >= (1 << 28))
     return fail(SWGN_ERR_TOO_LARGE, "window Jacobian too large for the 28-bit gather offsets");
 
+  // ---- gather streams (device_types.h "gather stream"): output tiles with their <= 4-row terms are dealt to
+  // the SCHUR_WARPS warps of the window's CTA, longest first onto the least loaded warp; every warp gets
+  // one linear stream of stages (header + SCHUR_STAGE terms of one tile, padded with switched-off terms)
+  struct GTerm {
+    uint32_t a, b, m, sign, b2;
+  };
+  struct TileJob {
+    uint32_t meta, flags;
+    int32_t x, y;  // header words 0 / 1: S offset and first S row, or e-cell output offset and its g offset
+    std::vector<GTerm> terms;
+  };
+  auto deal_streams = [&](const std::vector<TileJob>& jobs, int arr_stream, int arr_ptr) {
+    std::vector<size_t> idx(jobs.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return jobs[x].terms.size() > jobs[y].terms.size(); });
+    std::vector<std::vector<size_t>> mine(SCHUR_WARPS);
+    std::vector<size_t> load(SCHUR_WARPS, 0);
+    for (size_t j : idx) {
+      const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      mine[wmin].push_back(j);
+      load[wmin] += (jobs[j].terms.size() + SCHUR_STAGE - 1) / SCHUR_STAGE + 1;
+    }
+    std::vector<int32_t>& WS = I[arr_stream];
+    for (int wv = 0; wv < SCHUR_WARPS; ++wv) {
+      I[arr_ptr].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
+      for (size_t j : mine[wv]) {
+        const TileJob& jb = jobs[j];
+        const size_t nt = jb.terms.size();
+        const size_t n_st = nt == 0 ? 1 : (nt + SCHUR_STAGE - 1) / SCHUR_STAGE;
+        for (size_t st = 0; st < n_st; ++st) {
+          WS.push_back(jb.x);
+          WS.push_back(jb.y);
+          WS.push_back((int32_t)(jb.flags | (st + 1 == n_st ? 1u : 0u)));
+          WS.push_back((int32_t)jb.meta);
+          for (size_t e = st * SCHUR_STAGE; e < (st + 1) * SCHUR_STAGE; ++e) {
+            if (e < nt) {
+              const GTerm& t = jb.terms[e];
+              WS.push_back((int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30)));
+              WS.push_back((int32_t)t.b);
+              WS.push_back((int32_t)t.b2);
+              WS.push_back(0);
+            } else {  // padding: bit 31 switches the loads off, the MMA adds zero
+              WS.push_back((int32_t)0x80000000u);
+              WS.push_back(0); WS.push_back(0); WS.push_back(0);
+            }
+          }
+        }
+      }
+    }
+    I[arr_ptr].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
+  };
   // ---- gather tables of the reduced system (device Schur kernel, phase 2).  Every touched block
   // cell (p, q), p <= q, of S lists its terms:
   //   + F_p' F_q of every row holding both cells      (schur_eliminator_impl.h:667-716, 569-661)
@@ -426,9 +477,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   const int ld = (n_f + 1 + 3) & ~3;
   {
     auto fpos = [&](int c) { return col_pos[c] - n_e; };  // row/col of the f-block inside S
-    struct T {
-      uint32_t a, b, m, sign, b2;
-    };
+    typedef GTerm T;
     std::map<std::pair<int, int>, std::vector<T>> cells;
     for (int c = n_ecols; c < n_cols; ++c) cells[{c, c}];  // diagonal cells always exist (D^2)
     const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
@@ -461,11 +510,6 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       return w * (size_t)((outs + 31) / 32) + 8;
     };
     std::stable_sort(order.begin(), order.end(), [&](const auto& x, const auto& y) { return weight(x) > weight(y); });
-    struct TileJob {
-      uint32_t meta;
-      int32_t soff, frow;
-      std::vector<T> terms;  // a, b already slab-split; b2 valid on diagonal cells
-    };
     std::vector<TileJob> jobs;
     for (size_t ci = 0; ci < order.size(); ++ci) {
       const int p = order[ci].first.first, q = order[ci].first.second;
@@ -487,102 +531,63 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
         for (int tj = 0; tj < qs + (diag ? 1 : 0); tj += 8) {
           TileJob jb;
           jb.meta = (uint32_t)ps | ((uint32_t)qs << 6) | ((uint32_t)(ti / 8) << 12) | ((uint32_t)(tj / 8) << 15) | ((diag ? 1u : 0u) << 18);
-          jb.soff = fpos(p) * ld + fpos(q);
-          jb.frow = fpos(p);
+          jb.flags = 0;
+          jb.x = fpos(p) * ld + fpos(q);
+          jb.y = fpos(p);
           jb.terms = ts;
           jobs.push_back(std::move(jb));
         }
       const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), 0, (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
       I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);  // cell directory (statistics / read-backs); the kernel reads the streams
     }
-    // deal the tiles to the warps: longest first onto the least loaded warp, then one linear stream per warp
-    {
-      std::vector<size_t> idx(jobs.size());
-      std::iota(idx.begin(), idx.end(), 0);
-      std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return jobs[x].terms.size() > jobs[y].terms.size(); });  // longest first
-      std::vector<std::vector<size_t>> mine(SCHUR_WARPS);
-      std::vector<size_t> load(SCHUR_WARPS, 0);
-      for (size_t j : idx) {
-        const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        mine[wmin].push_back(j);
-        load[wmin] += (jobs[j].terms.size() + SCHUR_STAGE - 1) / SCHUR_STAGE + 1;
-      }
-      std::vector<int32_t>& WS = I[I_WSTREAM];
-      for (int wv = 0; wv < SCHUR_WARPS; ++wv) {
-        I[I_WSTREAM_PTR].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
-        for (size_t j : mine[wv]) {
-          const TileJob& jb = jobs[j];
-          const size_t nt = jb.terms.size();
-          const size_t n_st = nt == 0 ? 1 : (nt + SCHUR_STAGE - 1) / SCHUR_STAGE;
-          for (size_t st = 0; st < n_st; ++st) {
-            WS.push_back(jb.soff);
-            WS.push_back(jb.frow);
-            WS.push_back(st + 1 == n_st ? 1 : 0);
-            WS.push_back((int32_t)jb.meta);
-            for (size_t e = st * SCHUR_STAGE; e < (st + 1) * SCHUR_STAGE; ++e) {
-              if (e < nt) {
-                const T& t = jb.terms[e];
-                WS.push_back((int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30)));
-                WS.push_back((int32_t)t.b);
-                WS.push_back((int32_t)t.b2);
-                WS.push_back(0);
-              } else {  // padding: bit 31 switches the loads off, the MMA adds zero
-                WS.push_back((int32_t)0x80000000u);
-                WS.push_back(0); WS.push_back(0); WS.push_back(0);
-              }
-            }
-          }
-        }
-      }
-      I[I_WSTREAM_PTR].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
-    }
+    deal_streams(jobs, I_WSTREAM, I_WSTREAM_PTR);
   }
   // ---- raw products of the larger e-blocks (4..16 tangent dims: the speed-bias blocks), gathered
-  // by the same tensor-core code as the reduced system: per chunk one "diagonal" cell
-  // [E'E | E'b] (es x es+1, written to W_EFAC / the chunk's g slot) and one cell E'F_f per slot
-  // (es x fs, written to the slot's W_EBUF block); terms = the rows of the chunk.
+  // by the same tensor-core stream code as the reduced system (phase 1a): per chunk one "diagonal" cell
+  // [E'E | E'b] (es x es+1, upper tiles only, written to W_EFAC / the chunk's g slot) and one cell
+  // E'F_f per slot (es x fs, written to the slot's W_EBUF block); terms = the rows of the chunk.
   {
-    struct T {
-      uint32_t a, b, m, b2;
-    };
     const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
-    auto emit = [&](int ps, int qs, int out, bool diag, int gout, const std::vector<T>& rows) {
-      std::vector<T> ts;
-      for (const T& t : rows)
+    std::vector<TileJob> jobs;
+    int n_ecells = 0;
+    auto emit = [&](int ps, int qs, int out, bool diag, int gout, const std::vector<GTerm>& rows) {
+      std::vector<GTerm> ts;
+      for (const GTerm& t : rows)
         for (uint32_t e0 = 0; e0 < t.m; e0 += 4)
-          ts.push_back({t.a + e0 * (uint32_t)ps, t.b + e0 * (uint32_t)qs, std::min(4u, t.m - e0), t.b2 + e0});
-      if (diag)
-        while (I[I_STERM].size() % 4) I[I_STERM].push_back(0);
-      const int32_t rec[8] = {ps, qs, out, (int32_t)I[I_STERM].size(), (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
-      I[I_ECELL].insert(I[I_ECELL].end(), rec, rec + 8);
-      I[I_ECELL_G].push_back(gout);
-      for (const T& t : ts) {
-        I[I_STERM].push_back((int32_t)(t.a | ((t.m - 1) << 28)));
-        I[I_STERM].push_back((int32_t)t.b);
-        if (diag) {
-          I[I_STERM].push_back((int32_t)t.b2);
-          I[I_STERM].push_back(0);
+          ts.push_back({t.a + e0 * (uint32_t)ps, t.b + e0 * (uint32_t)qs, std::min(4u, t.m - e0), 0u, t.b2 + e0});
+      ++n_ecells;
+      for (int ti = 0; ti < ps; ti += 8)
+        for (int tj = 0; tj < qs + (diag ? 1 : 0); tj += 8) {
+          if (diag && tj + 7 < ti) continue;  // E'E: upper triangle only
+          TileJob jb;
+          jb.meta = (uint32_t)ps | ((uint32_t)qs << 6) | ((uint32_t)(ti / 8) << 12) | ((uint32_t)(tj / 8) << 15) | ((diag ? 1u : 0u) << 18);
+          jb.flags = 2;  // e-cell target
+          jb.x = out;
+          jb.y = gout;
+          jb.terms = ts;
+          jobs.push_back(std::move(jb));
+          P->n_mma += (int64_t)ts.size();
         }
-      }
-      P->n_mma += (int64_t)((ps + 7) / 8) * ((qs + (diag ? 1 : 0) + 7) / 8) * (int64_t)ts.size();
     };
     for (int wc = 0; wc < (int)I[I_WCHUNK].size(); ++wc) {
       const int ch = I[I_WCHUNK][wc];
       const int es = col_size[I[I_CHUNK_ECOL][ch]];
-      std::vector<T> diag_terms;
-      std::map<int, std::vector<T>> slot_terms;  // slot buffer offset -> rows
+      std::vector<GTerm> diag_terms;
+      std::map<int, std::vector<GTerm>> slot_terms;  // slot buffer offset -> rows
       for (int r = I[I_CHUNK_ROW][ch]; r < I[I_CHUNK_ROW][ch + 1]; ++r) {
         const uint32_t nres = (uint32_t)I[I_ROW_NRES][r];
         const int c0 = I[I_ROW_CELL][r];
         const uint32_t eoff = (uint32_t)I[I_CELL_VAL][c0];
-        diag_terms.push_back({eoff, eoff, nres, res_base + (uint32_t)I[I_ROW_RES][r]});
+        diag_terms.push_back({eoff, eoff, nres, 0u, res_base + (uint32_t)I[I_ROW_RES][r]});
         for (int c = c0 + 1; c < I[I_ROW_CELL][r + 1]; ++c)
-          slot_terms[I[I_CELL_SLOT][c]].push_back({eoff, (uint32_t)I[I_CELL_VAL][c], nres, 0u});
+          slot_terms[I[I_CELL_SLOT][c]].push_back({eoff, (uint32_t)I[I_CELL_VAL][c], nres, 0u, 0u});
       }
       emit(es, es, I[I_CHUNK_FAC][ch], true, I[I_CHUNK_G][ch], diag_terms);
       for (int s = I[I_CHUNK_SLOT][ch]; s < I[I_CHUNK_SLOT][ch + 1]; ++s)
         emit(es, col_size[I[I_SLOT_COL][s]], I[I_SLOT_BUF][s], false, -1, slot_terms[I[I_SLOT_BUF][s]]);
     }
+    deal_streams(jobs, I_ESTREAM, I_ESTREAM_PTR);
+    I[I_ECELL_G].assign(1, n_ecells);  // (statistic only)
   }
   // ---- row-parallel part of phase 1: rows of "simple" small chunks (every slot fed by exactly one
   // row, e.g. a landmark seen once per keyframe) compute their W block independently
@@ -741,7 +746,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_scells = (int)(I[I_SCELL].size() / 8);
   d.n_sterms = (int)I[I_STERM].size();
   d.n_srows = (int)I[I_SROW].size();
-  d.n_ecells = (int)I[I_ECELL_G].size();
+  d.n_ecells = I[I_ECELL_G].empty() ? 0 : I[I_ECELL_G][0];
   d.max_wbuf = max_wbuf;
   d.n_wstream = (int)(I[I_WSTREAM].size() / 4);
   d.n_chain = g->n_chain;
