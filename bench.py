@@ -250,7 +250,7 @@ def run_swgn(args, rank, local_rank, world):
     # scaled per window to this launch: dram__bytes_read.sum + dram__bytes_write.sum
     traffic, traffic_src = None, None
     try:
-        txt = open(os.path.join(ROOT, "profiles", "r01_k_schur_592win.md")).read()
+        txt = open(os.path.join(ROOT, "profiles", "r01b_k_schur_592win.md")).read()
 
         def grab(name):
             import re
@@ -258,7 +258,7 @@ def run_swgn(args, rank, local_rank, world):
             return float(m.group(1)) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m.group(2)]
         per_window = (grab("dram__bytes_read.sum") + grab("dram__bytes_write.sum")) / 592.0
         traffic = per_window * (schur_bytes / max(1, n_schur)) / float(np.mean(schur_bytes_w))
-        traffic_src = "profiles/r01_k_schur_592win.md (ncu --set full, 592-window launch), scaled per window"
+        traffic_src = "profiles/r01b_k_schur_592win.md (ncu --set full, 592-window launch), scaled per window"
     except Exception:
         pass
     cpu = None
