@@ -18,6 +18,9 @@
 //   * factors a1/a3/a4/a5, MyOrdering, exports, LambdaSearch: the reference holds no test or
 //     golden vector for them and cannot be built here (needs Eigen3/ROS/OpenCV): PARITY UNPINNED
 //     by the reference; pinned by analytic-vs-numeric Jacobian checks only.
+//   * IMUGNSSFactor (oracle_chain.cpp): no test or fixture in the reference either: PARITY
+//     UNPINNED by the reference; pinned on the dense Schur complement of the whole chain
+//     (tests/test_chain_factor.py).
 //
 // RVI/   = /root/reference/rtk_visual_inertial_src/rtk_visual_inertial/src/
 // CERES/ = ceres-solver-modified/ inside /root/reference/ceres-solver-modified.tar
