@@ -300,6 +300,13 @@ swgn_status swgn_batch_get_cholesky(swgn_batch* b, int32_t window, double* L, in
 swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t window, int32_t n_tail,
                                             double* A);
 
+/* UpdateSchur (RVI/swf/swf_gnss.cpp:25-61): after an export-mode solve, Schur-reduce the leading
+   n_f - n_tail rows of the exported (S, r) onto the trailing n_tail rows with the reference's eigen
+   pseudo-inverse (eigenvalues <= 1e-8 dropped): A (n_tail x n_tail row-major, full symmetric) and
+   b (n_tail) are what the reference turns into its next marginalisation prior. */
+swgn_status swgn_batch_get_head_marginal(swgn_batch* b, int32_t window, int32_t n_tail, double* A,
+                                         double* bvec);
+
 /* Hidden GNSS-frame states of the IMUGNSSFactor chains of `window` after the last Jacobian
    evaluation (the reference updates gnss_poses[i] / gnss_speed_bias[i] in user memory,
    gnss_imu_factor.cpp:601-632): 16 doubles (pose 7, speed-bias 9) per hidden frame in graph

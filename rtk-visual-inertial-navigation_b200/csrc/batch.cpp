@@ -572,6 +572,25 @@ swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t w, int32_t n_
   return SWGN_OK;
 }
 
+swgn_status swgn_batch_get_head_marginal(swgn_batch* b, int32_t w, int32_t n_tail, double* A, double* bvec) {
+  if (!b || w < 0 || w >= b->n || !A || !bvec || n_tail <= 0 || n_tail > b->desc[w].n_f) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  TRState t;
+  CU(cudaMemcpy(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost));
+  if (!t.have_reduced) return fail(SWGN_ERR_INVALID, "no reduced system available: run an export-mode solve (is_optimize = 0) first");
+  const int nf = b->desc[w].n_f, m = nf - n_tail;
+  double* dbuf = nullptr;
+  const size_t na = (size_t)n_tail * n_tail, ns = head_marginal_scratch_doubles(m, n_tail);
+  CU(cudaMalloc(&dbuf, sizeof(double) * (na + n_tail + ns)));
+  cudaError_t e = launch_head_marginal(b->db, w, nf, n_tail, dbuf, dbuf + na, dbuf + na + n_tail, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(A, dbuf, sizeof(double) * na, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(bvec, dbuf + na, sizeof(double) * n_tail, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  cudaFree(dbuf);
+  CU(e);
+  return SWGN_OK;
+}
+
 swgn_status swgn_batch_get_chain_frames(swgn_batch* b, int32_t w, int32_t* n_frames, double* frames) {
   if (!b || w < 0 || w >= b->n || !n_frames) return fail(SWGN_ERR_INVALID, "bad arguments");
   const WinDesc& d = b->desc[w];

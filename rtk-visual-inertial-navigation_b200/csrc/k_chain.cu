@@ -16,6 +16,7 @@
 #include <float.h>
 
 #include "dev_common.cuh"
+#include "dev_eig.cuh"
 #include "dev_imu.cuh"
 #include "../../include/swgn.h"
 
@@ -451,83 +452,7 @@ __global__ void __launch_bounds__(NT, 2) k_chain(DeviceBatch b, int mode, int on
       }
     }
     if (!use_chol) {
-    // symmetric eigen-decomposition: two-sided Jacobi, round-robin (tournament) ordering, np/2 disjoint
-    // rotations per step: columns of A and V, then rows of A.  One warp per rotation pair, lanes over the
-    // rows / columns; the leading dimension is odd so that the column pass stays off shared-memory banks.
-    {
-      const int np = (n + 1) & ~1;  // players (an odd n gets a bye)
-      const int half = np / 2;
-      const int wid = tid >> 5, nwarp = NT / 32;
-      for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, dg = 0.0;
-        for (int ra = wid; ra < n; ra += nwarp)
-          for (int cb = lane; cb < n; cb += 32) {
-            const double val = A[ra * ld + cb] * A[ra * ld + cb];
-            if (ra == cb) dg += val;
-            else if (cb > ra) off += val;
-          }
-        off = block_sum(off, sm + S.red);
-        dg = block_sum(dg, sm + S.red);
-        if (off <= 1e-30 * (dg + 1e-300)) break;
-        for (int step = 0; step < np - 1; ++step) {
-          // pair t of this step: players pa, pb (circle method, player np-1 fixed)
-          if (tid < half) {
-            const int pa = (tid == 0) ? np - 1 : (step + tid) % (np - 1);
-            const int pb = (step + np - 1 - tid) % (np - 1);
-            int pp = pa < pb ? pa : pb;
-            const int qq = pa < pb ? pb : pa;
-            double cth = 1.0, sth = 0.0;
-            if (qq < n) {
-              const double apq = A[pp * ld + qq];
-              if (apq != 0.0) {
-                const double theta = (A[qq * ld + qq] - A[pp * ld + pp]) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                cth = 1.0 / sqrt(t * t + 1.0);
-                sth = t * cth;
-              } else {
-                pp = -1;  // nothing to rotate
-              }
-            } else {
-              pp = -1;    // the bye
-            }
-            sm[S.cs + 4 * tid] = cth;
-            sm[S.cs + 4 * tid + 1] = sth;
-            sm[S.cs + 4 * tid + 2] = (double)pp;
-            sm[S.cs + 4 * tid + 3] = (double)qq;
-          }
-          __syncthreads();
-          for (int t = wid; t < half; t += nwarp) {  // columns: A <- A R, V <- V R
-            const int pp = (int)sm[S.cs + 4 * t + 2];
-            if (pp < 0) continue;
-            const int qq = (int)sm[S.cs + 4 * t + 3];
-            const double cth = sm[S.cs + 4 * t], sth = sm[S.cs + 4 * t + 1];
-            for (int kk = lane; kk < n; kk += 32) {
-              const double akp = A[kk * ld + pp], akq = A[kk * ld + qq];
-              A[kk * ld + pp] = cth * akp - sth * akq;
-              A[kk * ld + qq] = sth * akp + cth * akq;
-              const double vkp = V[kk * ld + pp], vkq = V[kk * ld + qq];
-              V[kk * ld + pp] = cth * vkp - sth * vkq;
-              V[kk * ld + qq] = sth * vkp + cth * vkq;
-            }
-          }
-          __syncthreads();
-          for (int t = wid; t < half; t += nwarp) {  // rows: A <- R' A
-            const int pp = (int)sm[S.cs + 4 * t + 2];
-            if (pp < 0) continue;
-            const int qq = (int)sm[S.cs + 4 * t + 3];
-            const double cth = sm[S.cs + 4 * t], sth = sm[S.cs + 4 * t + 1];
-            for (int kk = lane; kk < n; kk += 32) {
-              const double apk = A[pp * ld + kk], aqk = A[qq * ld + kk];
-              A[pp * ld + kk] = cth * apk - sth * aqk;
-              A[qq * ld + kk] = sth * apk + cth * aqk;
-            }
-            __syncwarp();
-            if (lane == 0) A[pp * ld + qq] = A[qq * ld + pp] = 0.0;  // annihilated exactly
-          }
-          __syncthreads();
-        }
-      }
-    }
+    jacobi_eig<NT>(A, V, n, ld, sm + S.cs, sm + S.red);
     // schur_jacobian = sqrt(S) V', schur_residual = S^-1/2 V' rhs, eigenvalues <= eps dropped
     {
       double* Jd = Wk + L.w_J;

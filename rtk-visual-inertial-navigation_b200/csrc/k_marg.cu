@@ -1,0 +1,86 @@
+// UpdateSchur on the device (RVI/swf/swf_gnss.cpp:25-61): after an export-mode solve the reduced system
+// (S, r) = ceres::internal::{lhs_out, rhs_out} sits in W_S; the leading m = n_f - n rows are Schur-reduced
+// onto the trailing n rows (the parameter_head blocks) with an EIGEN PSEUDO-INVERSE of A_mm,
+//   A = A_nn - A_nm V diag(1/lambda_k if lambda_k > 1e-8 else 0) V' A_mn,   b = b_n - A_nm (...) b_m,
+// exactly as the reference does for its marginalisation prior.  One CTA per call: A_mm and V in shared
+// memory when they fit (m <= 100), otherwise in a global scratch (same code, L2-resident); the
+// eigen-decomposition is the CTA-wide Jacobi of dev_eig.cuh (standing in for Eigen::SelfAdjointEigenSolver).
+#include "dev_common.cuh"
+#include "dev_eig.cuh"
+#include "../../include/swgn.h"
+
+namespace swgn {
+namespace {
+constexpr int NT = 256;
+constexpr double kEigEps = 1e-8;  // swf_gnss.cpp:45
+constexpr int kMaxSharedM = 100;
+}  // namespace
+
+// scratch: W (m x (n+1)) then, when m > kMaxSharedM, A_mm and V (m x ld each)
+__global__ void __launch_bounds__(NT) k_head_marginal(DeviceBatch b, int window, int n, double* A_out, double* b_out, double* scratch) {
+  extern __shared__ __align__(16) double sm[];
+  const WinDesc& d = b.desc[window];
+  const double* S = b.wpool + d.woff[W_S];
+  const int nf = d.n_f, ldS = d.ld, m = nf - n;
+  const int tid = threadIdx.x;
+  auto Sfull = [&](int i, int j) { return j >= i ? S[(size_t)i * ldS + j] : S[(size_t)j * ldS + i]; };  // selfadjointView<Upper>
+  if (m == 0) {
+    for (int o = tid; o < n * n; o += NT) A_out[o] = Sfull(o / n, o % n);
+    for (int i = tid; i < n; i += NT) b_out[i] = S[(size_t)i * ldS + nf];
+    return;
+  }
+  const int ld = m | 1;
+  double* W = scratch;  // m x (n + 1)
+  const bool in_smem = m <= kMaxSharedM;
+  double* cs = sm;                       // 4 * ((m + 1) / 2) + 4
+  double* red = cs + 4 * ((m + 1) / 2) + 4;
+  double* A = in_smem ? red + 34 : scratch + (size_t)m * (n + 1);
+  double* V = A + (size_t)m * ld;
+  for (int o = tid; o < m * m; o += NT) {
+    const int i = o / m, j = o - i * m;
+    A[i * ld + j] = Sfull(i, j);
+    V[i * ld + j] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  jacobi_eig<NT>(A, V, m, ld, cs, red);
+  __syncthreads();
+  // W = V' [A_mn | b_m]
+  for (int o = tid; o < m * (n + 1); o += NT) {
+    const int k = o / (n + 1), j = o - k * (n + 1);
+    double acc = 0.0;
+    for (int i = 0; i < m; ++i) acc += V[i * ld + k] * (j < n ? S[(size_t)i * ldS + m + j] : S[(size_t)i * ldS + nf]);
+    W[o] = acc;
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (int o = tid; o < n * (n + 1); o += NT) {
+    const int i = o / (n + 1), j = o - i * (n + 1);
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) {
+      const double lam = A[k * ld + k];
+      if (lam > kEigEps) acc += W[(size_t)k * (n + 1) + i] * (1.0 / lam) * W[(size_t)k * (n + 1) + j];
+    }
+    if (j < n) A_out[(size_t)i * n + j] = Sfull(m + i, m + j) - acc;
+    else b_out[i] = S[(size_t)(m + i) * ldS + nf] - acc;
+  }
+}
+
+size_t head_marginal_scratch_doubles(int m, int n) {
+  size_t w = (size_t)m * (n + 1);
+  if (m > kMaxSharedM) w += 2 * (size_t)m * (m | 1);
+  return w + 2;
+}
+
+cudaError_t launch_head_marginal(const DeviceBatch& b, int window, int n_f, int n, double* A_dev, double* b_dev, double* scratch, cudaStream_t s) {
+  const int m = n_f - n;
+  size_t dyn = sizeof(double) * (size_t)(4 * ((m + 1) / 2) + 4 + 34);
+  if (m <= kMaxSharedM) dyn += sizeof(double) * 2 * (size_t)m * (m | 1);
+  if (dyn > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_head_marginal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+  }
+  k_head_marginal<<<1, NT, dyn, s>>>(b, window, n, A_dev, b_dev, scratch);
+  return cudaGetLastError();
+}
+
+}  // namespace swgn

@@ -44,6 +44,10 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s);
 void launch_step(const DeviceBatch& b, cudaStream_t s);
 void launch_end(const DeviceBatch& b, cudaStream_t s);
 void launch_finish(const DeviceBatch& b, cudaStream_t s);
+// UpdateSchur (RVI/swf/swf_gnss.cpp:25-61): eigen pseudo-inverse Schur reduction of the exported (S, r)
+size_t head_marginal_scratch_doubles(int m, int n);
+cudaError_t launch_head_marginal(const DeviceBatch& b, int window, int n_f, int n, double* A_dev, double* b_dev, double* scratch,
+                                 cudaStream_t s);
 void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s);
 
 // K7/K8: batched RTKLIB-style lambda() and the LambdaSearch decision (k_lambda.cu)

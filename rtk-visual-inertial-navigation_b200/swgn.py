@@ -217,6 +217,7 @@ def lib():
         L.swgn_batch_get_rows.argtypes = [C.c_void_p, i32, P(i32), P(i32), P(i32)]
         L.swgn_batch_get_dense_jacobian.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_linear_solve.argtypes = [C.c_void_p, i32, P(f64), P(f64)]
+        L.swgn_batch_get_head_marginal.argtypes = [C.c_void_p, i32, i32, P(f64), P(f64)]
         L.swgn_batch_get_chain_frames.argtypes = [C.c_void_p, i32, P(i32), P(f64)]
         L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_ambiguity_fix.argtypes = [i32, i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32),
@@ -325,6 +326,13 @@ class Batch:
         A = np.zeros((n_tail, n_tail))
         _check(lib().swgn_batch_get_tail_information(self.h, w, n_tail, _dp(A)), "tail_information")
         return A
+
+    def head_marginal(self, w, n_tail):
+        """UpdateSchur: (A, b) of the trailing n_tail rows after an export-mode solve."""
+        A = np.zeros((n_tail, n_tail))
+        bv = np.zeros(n_tail)
+        _check(lib().swgn_batch_get_head_marginal(self.h, w, n_tail, _dp(A), _dp(bv)), "head_marginal")
+        return A, bv
 
     def chain_frames(self, w):
         """Hidden GNSS-frame states of window w's IMUGNSSFactor chains, (n_frames, 16)."""

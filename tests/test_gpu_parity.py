@@ -169,6 +169,35 @@ def test_export_mode():
     b.close()
 
 
+@pytest.mark.parametrize("which,wid,n_head", [(2, 1, None), (1, 0, 2), (2, 3, 5)])
+def test_update_schur_on_the_device(which, wid, n_head):
+    """UpdateSchur (RVI/swf/swf_gnss.cpp:25-61) after the export-mode solve: (A, b) of the head blocks by
+    the eigen pseudo-inverse Schur reduction, against the oracle's restatement, and the defining
+    property: A z_n = b is the head part of the solution of the full reduced system S z = r."""
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    if n_head is not None:
+        opt.n_parameter_head = n_head
+    opt.is_optimize = 0
+    opt.max_num_iterations = 1
+    b = swgn.Batch([w.graph_p], opt)
+    b.solve()
+    S, r = b.get_reduced(0)
+    st, d = swgn.plan_probe(w.graph_p, opt.n_parameter_head)
+    cb, co, cs = b.columns(0)
+    n_tail = int(cs[len(cs) - opt.n_parameter_head:].sum())
+    A, bv = b.head_marginal(0, n_tail)
+    Sf = np.triu(S) + np.triu(S, 1).T
+    Ao, bo = ob.update_schur(Sf, r, n_tail)
+    # A = A_nn - A_nm A_mm^+ A_mn cancels the leading digits of A_nn (cfg1: |A_nn| ~ 1e9, |A| ~ 1e4), so two
+    # correct evaluations agree to ~1e-16 * |A_nn| / |A|
+    assert rel(A, Ao) < 1e-7 and rel(bv, bo) < 1e-6
+    assert np.allclose(A, A.T, rtol=0, atol=1e-9 * np.abs(A).max())
+    z = np.linalg.solve(Sf, r)
+    assert rel(np.linalg.solve(A, bv), z[-n_tail:]) < 1e-6
+    b.close()
+
+
 def test_cholesky_export_and_tail_information():
     w = swgn.SynthWindow(2, 2)
     opt = w.options()
