@@ -335,6 +335,19 @@ swgn_status swgn_batch_get_dense_jacobian(swgn_batch* b, int32_t window, double*
    min |J x - r|^2 + |D x|^2 (CERES schur_complement_solver.cc:126-202). */
 swgn_status swgn_batch_linear_solve(swgn_batch* b, int32_t window, const double* D, double* x);
 
+/* ---- IMU pre-integration ------------------------------------------------------------------- */
+/* IntegrationBase (RVI/factor/integration_base.cpp:5-142), batched on the device: factor f integrates
+   the samples [sample_begin[f], sample_begin[f+1]) -- 7 doubles per sample: dt, acc[3], gyr[3]; the first
+   sample is (acc_0, gyr_0) of the constructor (its dt is ignored), every further one is one
+   push_back(dt, acc, gyr) = one midpoint step with Jacobian and covariance propagation.  bias holds
+   linearized_ba[3], linearized_bg[3] per factor; noise = ACC_N, GYR_N, ACC_W, GYR_W.  Output: one
+   SWGN_IMU_STRIDE record per factor (exactly what swgn_graph.imu_data / chain_imu_data take), with
+   sqrt_info = LLT(covariance^-1).L' (get_sqrtinfo); info[f] = 0 ok, 1 covariance not invertible /
+   not positive definite (sqrt_info left zero). */
+swgn_status swgn_preintegrate_batch(int32_t device, int32_t n_factors, const int32_t* sample_begin,
+                                    const double* samples, const double* bias, const double noise[4],
+                                    double* records, int32_t* info);
+
 /* ---- ambiguity resolution (K7/K8) --------------------------------------------------------- */
 /* RTKLIB-style lambda()/mlambda as shipped in RVI/gnss/src/lambda.cpp:204-235, batched:
    problem k has n[k] float ambiguities a_k (n[k]) and covariance Q_k (n[k] x n[k], column-major),

@@ -85,6 +85,17 @@ int oracle_evaluate(void* h, double* cost, double* residuals, double* gradient, 
   return 0;
 }
 
+// batched IMU pre-integration, factor f = samples [begin[f], begin[f+1]); returns the number of failures
+int oracle_preintegrate_batch(int n, const int32_t* begin, const double* samples, const double* bias, const double* noise4,
+                              double* records) {
+  int bad = 0;
+  for (int f = 0; f < n; ++f)
+    if (!preintegrate(begin[f + 1] - begin[f], samples + (size_t)7 * begin[f], bias + 6 * f, noise4,
+                      records + (size_t)SWGN_IMU_STRIDE * f))
+      ++bad;
+  return bad;
+}
+
 // cost-only evaluation (what the trust-region loop does for a candidate point: no Jacobians are
 // requested from the cost functions, trust_region_minimizer.cc:761-787)
 int oracle_evaluate_cost(void* h, double* cost, double* residuals) {

@@ -141,6 +141,9 @@ CostFunction* make_chain_factor(const AppGlobals* g, int m, int k, const double*
                                 const double* chainN, const double* imu_data);
 int chain_factor_frames(const CostFunction* c, double* out16_per_frame);
 
+// IMU pre-integration -> SWGN_IMU_STRIDE record (RVI/factor/integration_base.cpp:5-142), oracle_preint.cpp
+bool preintegrate(int n_samples, const double* samples7, const double* bias6, const double* noise4, double* record);
+
 // range model: RVI/gnss/src/common_function.cpp:103-108,126-139,411-421
 double dot_rtk(const double* a, const double* b, int n);
 double distance_rtk(const double* rr, const double* rs, double* e);

@@ -572,6 +572,34 @@ swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t w, int32_t n_
   return SWGN_OK;
 }
 
+swgn_status swgn_preintegrate_batch(int32_t device, int32_t n_factors, const int32_t* sample_begin, const double* samples,
+                                    const double* bias, const double noise[4], double* records, int32_t* info) {
+  if (n_factors <= 0 || !sample_begin || !samples || !bias || !noise || !records) return fail(SWGN_ERR_INVALID, "bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SWGN_ERR_NO_DEVICE, "no usable CUDA device (the solver has no CPU fallback)");
+  for (int f = 0; f < n_factors; ++f)
+    if (sample_begin[f + 1] - sample_begin[f] < 1) return fail(SWGN_ERR_INVALID, "every factor needs at least its initial sample");
+  CU(cudaSetDevice(device));
+  const size_t ns = (size_t)sample_begin[n_factors];
+  int32_t *d_begin = nullptr, *d_info = nullptr;
+  double *d_samples = nullptr, *d_bias = nullptr, *d_rec = nullptr;
+  cudaError_t e = cudaMalloc(&d_begin, sizeof(int32_t) * (n_factors + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_info, sizeof(int32_t) * n_factors);
+  if (e == cudaSuccess) e = cudaMalloc(&d_samples, sizeof(double) * 7 * ns);
+  if (e == cudaSuccess) e = cudaMalloc(&d_bias, sizeof(double) * 6 * n_factors);
+  if (e == cudaSuccess) e = cudaMalloc(&d_rec, sizeof(double) * (size_t)SWGN_IMU_STRIDE * n_factors);
+  if (e == cudaSuccess) e = cudaMemcpy(d_begin, sample_begin, sizeof(int32_t) * (n_factors + 1), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_samples, samples, sizeof(double) * 7 * ns, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_bias, bias, sizeof(double) * 6 * n_factors, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_preintegrate(n_factors, d_begin, d_samples, d_bias, noise, d_rec, d_info, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(records, d_rec, sizeof(double) * (size_t)SWGN_IMU_STRIDE * n_factors, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && info) e = cudaMemcpy(info, d_info, sizeof(int32_t) * n_factors, cudaMemcpyDeviceToHost);
+  cudaFree(d_begin); cudaFree(d_info); cudaFree(d_samples); cudaFree(d_bias); cudaFree(d_rec);
+  CU(e);
+  return SWGN_OK;
+}
+
 swgn_status swgn_batch_get_head_marginal(swgn_batch* b, int32_t w, int32_t n_tail, double* A, double* bvec) {
   if (!b || w < 0 || w >= b->n || !A || !bvec || n_tail <= 0 || n_tail > b->desc[w].n_f) return fail(SWGN_ERR_INVALID, "bad arguments");
   CU(cudaSetDevice(b->device));

@@ -50,6 +50,10 @@ cudaError_t launch_head_marginal(const DeviceBatch& b, int window, int n_f, int 
                                  cudaStream_t s);
 void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s);
 
+// IMU pre-integration (k_preint.cu): one warp per factor; noise4 = ACC_N, GYR_N, ACC_W, GYR_W (host array)
+cudaError_t launch_preintegrate(int n_factors, const int32_t* begin_dev, const double* samples_dev, const double* bias_dev,
+                                const double* noise4, double* records_dev, int32_t* status_dev, cudaStream_t s);
+
 // K7/K8: batched RTKLIB-style lambda() and the LambdaSearch decision (k_lambda.cu)
 void launch_lambda_batch(int n_problems, int m, const int32_t* n_dev, const int64_t* aoff_dev,
                          const int64_t* qoff_dev, const double* a_dev, const double* Q_dev,

@@ -217,6 +217,7 @@ def lib():
         L.swgn_batch_get_rows.argtypes = [C.c_void_p, i32, P(i32), P(i32), P(i32)]
         L.swgn_batch_get_dense_jacobian.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_linear_solve.argtypes = [C.c_void_p, i32, P(f64), P(f64)]
+        L.swgn_preintegrate_batch.argtypes = [i32, i32, P(i32), P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_batch_get_head_marginal.argtypes = [C.c_void_p, i32, i32, P(f64), P(f64)]
         L.swgn_batch_get_chain_frames.argtypes = [C.c_void_p, i32, P(i32), P(f64)]
         L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
@@ -387,6 +388,20 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+def preintegrate_batch(sample_begin, samples, bias, noise, device=0):
+    """IMU pre-integration of n factors on the device -> (records (n, SWGN_IMU_STRIDE), info (n,))."""
+    sample_begin = np.ascontiguousarray(sample_begin, np.int32)
+    n = len(sample_begin) - 1
+    samples = np.ascontiguousarray(samples, np.float64)
+    bias = np.ascontiguousarray(bias, np.float64)
+    noise = np.ascontiguousarray(noise, np.float64)
+    rec = np.zeros((n, 474))
+    info = np.zeros(n, np.int32)
+    _check(lib().swgn_preintegrate_batch(device, n, _ip(sample_begin), _dp(samples), _dp(bias), _dp(noise), _dp(rec), _ip(info)),
+           "swgn_preintegrate_batch")
+    return rec, info
 
 
 def lambda_batch(ns, m, a, Q, device=0):

@@ -973,6 +973,28 @@ int32_t swgn_synth_ambiguity_epochs(const swgn_synth* s, int32_t* epoch_begin, i
   return ne;
 }
 const double* swgn_synth_true_ambiguities(const swgn_synth* s) { return s->true_N.data(); }
+int32_t swgn_synth_preintegrate(int32_t n_samples, const double* samples7, const double* bias6, const double* noise4, double* record) {
+  // the generator's own pre-integration (Preint above) on caller-provided samples: an implementation
+  // independent of oracle/ and of the device kernel, used by the tests as a cross-check
+  if (n_samples < 1) return 1;
+  Preint pre(V3{samples7[1], samples7[2], samples7[3]}, V3{samples7[4], samples7[5], samples7[6]}, V3{bias6[0], bias6[1], bias6[2]},
+             V3{bias6[3], bias6[4], bias6[5]}, noise4[0], noise4[1], noise4[2], noise4[3]);
+  for (int s = 1; s < n_samples; ++s)
+    pre.push(samples7[7 * s], V3{samples7[7 * s + 1], samples7[7 * s + 2], samples7[7 * s + 3]},
+             V3{samples7[7 * s + 4], samples7[7 * s + 5], samples7[7 * s + 6]});
+  std::memset(record, 0, sizeof(double) * SWGN_IMU_STRIDE);
+  double* r = record;
+  r[SWGN_IMU_DELTA_P] = pre.dp.x; r[SWGN_IMU_DELTA_P + 1] = pre.dp.y; r[SWGN_IMU_DELTA_P + 2] = pre.dp.z;
+  r[SWGN_IMU_DELTA_Q] = pre.dq.x; r[SWGN_IMU_DELTA_Q + 1] = pre.dq.y;
+  r[SWGN_IMU_DELTA_Q + 2] = pre.dq.z; r[SWGN_IMU_DELTA_Q + 3] = pre.dq.w;
+  r[SWGN_IMU_DELTA_V] = pre.dv.x; r[SWGN_IMU_DELTA_V + 1] = pre.dv.y; r[SWGN_IMU_DELTA_V + 2] = pre.dv.z;
+  r[SWGN_IMU_SUM_DT] = pre.sum_dt;
+  std::memcpy(r + SWGN_IMU_JACOBIAN, pre.jac.data(), sizeof(double) * 225);
+  Md sq;
+  if (!pre.sqrt_info(&sq)) return 2;
+  std::memcpy(r + SWGN_IMU_SQRT_INFO, sq.data(), sizeof(double) * 225);
+  return 0;
+}
 int32_t swgn_synth_chain_frame_blocks(const swgn_synth* s, int32_t* pose_block, int32_t* sb_block) {
   const int32_t n = (int32_t)s->chain_frame_block.size();
   for (int32_t i = 0; i < n; ++i) {

@@ -68,6 +68,11 @@ int32_t swgn_synth_chain_truth(const swgn_synth* s, double* frames16);
    application's memory layout: pose and speed-bias block index per hidden frame */
 int32_t swgn_synth_chain_frame_blocks(const swgn_synth* s, int32_t* pose_block, int32_t* sb_block);
 
+/* the generator's own IMU pre-integration on caller-provided samples (7 per sample: dt, acc, gyr; sample 0
+   = initial acc/gyr): SWGN_IMU_STRIDE record; returns 0 on success.  Cross-check for the tests. */
+int32_t swgn_synth_preintegrate(int32_t n_samples, const double* samples7, const double* bias6,
+                                const double* noise4, double* record);
+
 #ifdef __cplusplus
 }
 #endif

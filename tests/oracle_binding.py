@@ -48,6 +48,8 @@ def oracle():
         L.oracle_get_state.argtypes = [C.c_void_p, P(f64)]
         L.oracle_set_state.argtypes = [C.c_void_p, P(f64)]
         L.oracle_num_iteration_records.argtypes = [C.c_void_p]
+        L.oracle_preintegrate_batch.restype = C.c_int
+        L.oracle_preintegrate_batch.argtypes = [i32, P(i32), P(f64), P(f64), P(f64), P(f64)]
         L.oracle_evaluate_cost.restype = C.c_int
         L.oracle_evaluate_cost.argtypes = [C.c_void_p, P(f64), P(f64)]
         L.oracle_chain_frames.restype = C.c_int
@@ -197,6 +199,17 @@ def tail_information(Lm, n_tail):
     A = np.zeros((n_tail, n_tail))
     oracle().oracle_tail_information(_dp(Lm), Lm.shape[0], n_tail, _dp(A))
     return A
+
+
+def preintegrate_batch(sample_begin, samples, bias, noise):
+    sample_begin = np.ascontiguousarray(sample_begin, np.int32)
+    n = len(sample_begin) - 1
+    samples = np.ascontiguousarray(samples, np.float64)
+    bias = np.ascontiguousarray(bias, np.float64)
+    noise = np.ascontiguousarray(noise, np.float64)
+    rec = np.zeros((n, 474))
+    bad = oracle().oracle_preintegrate_batch(n, _ip(sample_begin), _dp(samples), _dp(bias), _dp(noise), _dp(rec))
+    return rec, bad
 
 
 def update_schur(S, r, n_tail):
