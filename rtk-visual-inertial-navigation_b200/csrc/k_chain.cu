@@ -271,21 +271,23 @@ __global__ void __launch_bounds__(NT, 2) k_chain(DeviceBatch b, int mode, int on
       {
         double* U = sm + S.H(B_P1, B_P1);
         double* inv = sm + S.inv;
-        if (tid == 0) {
+        if (tid < 32) {  // row kk of U by the lanes j > kk, same arithmetic as the scalar LLT
           bool ok = true;
-          for (int kk = 0; kk < 15 && ok; ++kk) {
+          for (int kk = 0; kk < 15; ++kk) {
             double xx = U[kk * 15 + kk];
             for (int p = 0; p < kk; ++p) xx -= U[p * 15 + kk] * U[p * 15 + kk];
-            if (!(xx > 0.0)) { ok = false; break; }
+            if (!(xx > 0.0)) { ok = false; break; }  // uniform across the warp
             xx = sqrt(xx);
-            U[kk * 15 + kk] = xx;
-            for (int j = kk + 1; j < 15; ++j) {
-              double s = U[kk * 15 + j];
-              for (int p = 0; p < kk; ++p) s -= U[p * 15 + kk] * U[p * 15 + j];
-              U[kk * 15 + j] = s / xx;
+            __syncwarp();
+            if (lane == kk) U[kk * 15 + kk] = xx;
+            if (lane > kk && lane < 15) {
+              double s = U[kk * 15 + lane];
+              for (int p = 0; p < kk; ++p) s -= U[p * 15 + kk] * U[p * 15 + lane];
+              U[kk * 15 + lane] = s / xx;
             }
+            __syncwarp();
           }
-          sm[S.r15 + 15] = ok ? 1.0 : 0.0;
+          if (lane == 0) sm[S.r15 + 15] = ok ? 1.0 : 0.0;
         }
         __syncthreads();
         const bool ok = sm[S.r15 + 15] != 0.0;
@@ -401,19 +403,27 @@ __global__ void __launch_bounds__(NT, 2) k_chain(DeviceBatch b, int mode, int on
     bool use_chol = false;
     {
       bool ok = true;
+      // right-looking, one barrier per column: the trailing update works on the UNSCALED columns
+      // (A[i][c] -= A[i][j] A[c][j] / piv_j, lower triangle; one warp per row, lanes over the columns) and the
+      // columns are scaled to L in one pass at the end
+      const int wid = tid >> 5, nwarp = NT / 32;
       for (int j = 0; j < n; ++j) {
         const double piv = A[j * ld + j];
         if (!(piv > 0.0) || !finite_d(piv)) { ok = false; break; }  // uniform: every thread reads the same value
-        const double dinv = 1.0 / sqrt(piv);
-        __syncthreads();
-        for (int i = j + tid; i < n; i += NT) A[i * ld + j] = (i == j) ? sqrt(piv) : A[i * ld + j] * dinv;
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][c] -= L[i][j] L[c][j], j < c <= i
-        const int rem = n - 1 - j;
-        for (int o = tid; o < rem * rem; o += NT) {
-          const int i = j + 1 + o / rem, c = j + 1 + o % rem;
-          if (c <= i) A[i * ld + c] -= A[i * ld + j] * A[c * ld + j];
+        const double pinv = 1.0 / piv;
+        for (int i = j + 1 + wid; i < n; i += nwarp) {
+          const double lij = A[i * ld + j] * pinv;
+          for (int c = j + 1 + lane; c <= i; c += 32) A[i * ld + c] -= lij * A[c * ld + j];
         }
+        __syncthreads();
+      }
+      if (ok) {
+        for (int o = tid; o < n * n; o += NT) {
+          const int i = o / n, j = o - i * n;
+          if (j < i) A[i * ld + j] *= 1.0 / sqrt(A[j * ld + j]);
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += NT) A[j * ld + j] = sqrt(A[j * ld + j]);
         __syncthreads();
       }
       if (ok) {
