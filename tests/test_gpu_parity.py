@@ -169,6 +169,26 @@ def test_export_mode():
     b.close()
 
 
+@pytest.mark.parametrize("kf,lm", [(10, 100), (10, 1000), (40, 100), (40, 1000)])
+def test_window_size_sweep_corners_match_oracle(kf, lm):
+    """BASELINE configs[4] / SURVEY 8d cfg5: the corners of the keyframes x landmarks sweep (GNSS epochs =
+    KF / 2) solved on the device and by the oracle."""
+    w = swgn.SynthWindow(2, 1, n_keyframes=kf, n_landmarks=lm, n_gnss_epochs=kf // 2)
+    opt = w.options()
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, osm = o.minimize()
+    assert st == 0
+    assert (sm.num_iterations, sm.num_successful_steps, sm.num_unsuccessful_steps, sm.termination_type) == \
+        (osm.num_iterations, osm.num_successful_steps, osm.num_unsuccessful_steps, osm.termination_type)
+    assert abs(sm.final_cost - osm.final_cost) <= TOL_COST * osm.final_cost
+    assert state_err(x, o.state()) < TOL_STATE
+    assert sm.n_f == o.n_f and sm.n_e == o.n_e
+    b.close()
+
+
 @pytest.mark.parametrize("which,wid,n_head", [(2, 1, None), (1, 0, 2), (2, 3, 5)])
 def test_update_schur_on_the_device(which, wid, n_head):
     """UpdateSchur (RVI/swf/swf_gnss.cpp:25-61) after the export-mode solve: (A, b) of the head blocks by
