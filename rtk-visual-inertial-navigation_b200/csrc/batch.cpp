@@ -334,6 +334,13 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
   if (!b || !graphs) return fail(SWGN_ERR_INVALID, "bad arguments");
   CU(cudaSetDevice(b->device));
   if (!b->h_cpool) CU(cudaMallocHost(&b->h_cpool, sizeof(double) * std::max<size_t>(b->cpool_n, 2)));
+  // windows are packed by worker threads in index order while this thread uploads every chunk of
+  // consecutive windows as soon as all of its windows are packed (the pools are window-major, so a chunk is
+  // one contiguous range): packing and the H2D copy overlap
+  const int n_chunks = b->n >= 64 ? 8 : 1;
+  const int per_chunk = (b->n + n_chunks - 1) / n_chunks;
+  std::vector<std::atomic<int>> chunk_done(n_chunks);
+  for (auto& c : chunk_done) c.store(0);
   std::atomic<int> next(0), bad(0);
   auto work = [&]() {
     for (;;) {
@@ -351,25 +358,43 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
       if (ok && w + 1 == b->n) ok = d.coff[NUM_CARR - 1] + sizes[NUM_CARR - 1] <= (int64_t)b->cpool_n;
       if (!ok) {
         bad.store(1);
+        chunk_done[w / per_chunk].fetch_add(1);
         continue;
       }
       double* ptr[NUM_CARR];
       for (int a = 0; a < NUM_CARR; ++a) ptr[a] = b->h_cpool + d.coff[a];
       pack_constants(g, ptr);
       std::memcpy(b->h_stage + b->state_off[w], g->state, sizeof(double) * d.n_state);
+      chunk_done[w / per_chunk].fetch_add(1, std::memory_order_release);
     }
   };
   {
     const int nt = std::max(1, std::min<int>(b->n / 16, (int)std::thread::hardware_concurrency()));
     std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
+    for (int t = 0; t < nt; ++t) th.emplace_back(work);
+    cudaError_t ce = cudaSuccess;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int w0 = c * per_chunk, w1 = std::min(b->n, w0 + per_chunk);
+      if (w0 >= w1) break;
+      while (chunk_done[c].load(std::memory_order_acquire) < w1 - w0) std::this_thread::yield();
+      if (bad.load() || ce != cudaSuccess) continue;
+      const size_t c0 = (size_t)b->desc[w0].coff[0], c1 = w1 < b->n ? (size_t)b->desc[w1].coff[0] : b->cpool_n;
+      ce = cudaMemcpyAsync(b->d_cpool + c0, b->h_cpool + c0, sizeof(double) * (c1 - c0), cudaMemcpyHostToDevice, b->stream);
+      const int64_t s0 = b->state_off[w0], s1 = b->state_off[w1];
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(b->d_stage + s0, b->h_stage + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, b->stream);
+    }
     for (auto& t : th) t.join();
+    if (ce != cudaSuccess) {
+      cudaStreamSynchronize(b->stream);
+      CU(ce);
+    }
   }
-  if (bad.load()) return fail(SWGN_ERR_INVALID, "graph structure differs from the one the batch was created with");
+  if (bad.load()) {
+    cudaStreamSynchronize(b->stream);
+    return fail(SWGN_ERR_INVALID, "graph structure differs from the one the batch was created with");
+  }
   const int64_t ns = b->state_off[b->n];
-  CU(cudaMemcpyAsync(b->d_cpool, b->h_cpool, sizeof(double) * b->cpool_n, cudaMemcpyHostToDevice, b->stream));
-  CU(cudaMemcpyAsync(b->d_stage, b->h_stage, sizeof(double) * ns, cudaMemcpyHostToDevice, b->stream));
   launch_gather_states(b->db, b->d_stage, b->d_state_off, 1, b->stream);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(b->stream));
