@@ -5,9 +5,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -127,6 +129,16 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
     return fail(SWGN_ERR_NO_DEVICE, "no usable CUDA device (the solver has no CPU fallback)");
   CU(cudaSetDevice(options->device));
 
+  const bool dbg_t = std::getenv("SWGN_DEBUG_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
+  double t_mark = t_start;
+  auto mark = [&](const char* what) {
+    if (!dbg_t) return;
+    const double t = now();
+    std::fprintf(stderr, "[swgn_batch_create] %-18s %8.1f ms\n", what, 1e3 * (t - t_mark));
+    t_mark = t;
+  };
   // ---- plan every window (host, structural work only), in parallel
   std::vector<WindowPlan> plans(n_windows);
   std::vector<swgn_status> sts(n_windows, SWGN_OK);
@@ -149,6 +161,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   for (int w = 0; w < n_windows; ++w)
     if (sts[w] != SWGN_OK) return fail(sts[w], "window " + std::to_string(w) + ": " + errs[w]);
 
+  mark("plan");
   swgn_batch* b = new swgn_batch();
   b->n = n_windows;
   b->device = options->device;
@@ -217,27 +230,110 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   CB(cudaMalloc(&b->d_state_off, sizeof(int64_t) * (n_windows + 1)));
   CB(cudaMallocHost(&b->h_counters, sizeof(int32_t) * 4));
   CB(cudaMallocHost(&b->h_stage, sizeof(double) * std::max<int64_t>(so, 2)));
+  mark("alloc");
   CB(cudaMemsetAsync(b->d_wpool, 0, sizeof(double) * std::max<size_t>(wo, 2), b->stream));
   CB(cudaMemsetAsync(b->d_state, 0, sizeof(TRState) * n_windows, b->stream));
   {
-    // pack the pools on the host and upload each with one copy
-    std::vector<int32_t> hi(std::max<size_t>(io, 4), 0);
-    std::vector<double> hc(std::max<size_t>(co, 2), 0.0);
-    for (int w = 0; w < n_windows; ++w) {
-      const WindowPlan& p = plans[w];
-      for (int a = 0; a < NUM_IARR; ++a)
-        if (!p.iarr[a].empty()) std::memcpy(hi.data() + b->desc[w].ioff[a], p.iarr[a].data(), sizeof(int32_t) * p.iarr[a].size());
-      for (int a = 0; a < NUM_CARR; ++a)
-        if (!p.carr[a].empty()) std::memcpy(hc.data() + b->desc[w].coff[a], p.carr[a].data(), sizeof(double) * p.carr[a].size());
-      std::memcpy(b->h_stage + b->state_off[w], p.state.data(), sizeof(double) * p.state.size());
+    // stream the pools through two pinned staging buffers: worker threads pack one chunk of consecutive
+    // windows (the pools are window-major) while the previous chunk is in flight to the device
+    auto i_begin = [&](int w) { return w < n_windows ? (size_t)b->desc[w].ioff[0] : io; };
+    auto c_begin = [&](int w) { return w < n_windows ? (size_t)b->desc[w].coff[0] : co; };
+    auto chunk_bytes = [&](int w0, int w1) {
+      return sizeof(int32_t) * (i_begin(w1) - i_begin(w0)) + 16 + sizeof(double) * (c_begin(w1) - c_begin(w0));
+    };
+    size_t stage_bytes = std::min<size_t>((size_t)128 << 20, chunk_bytes(0, n_windows));
+    for (int w = 0; w < n_windows; ++w) stage_bytes = std::max(stage_bytes, chunk_bytes(w, w + 1));
+    // Pinning memory costs ~0.1 s per allocation, so the two pinned staging buffers are process-wide, created
+    // by the first large batch and reused by every later create (a real replay creates a batch per frame).
+    // Small batches, or a create that finds the pool busy in another thread, stage through one pageable
+    // buffer (the copy is then synchronous with respect to the host).
+    static std::mutex pool_mutex;
+    static unsigned char* pool[2] = {nullptr, nullptr};
+    static size_t pool_bytes = 0;
+    std::unique_lock<std::mutex> pool_lock(pool_mutex, std::defer_lock);
+    bool pinned = chunk_bytes(0, n_windows) >= ((size_t)64 << 20) && pool_lock.try_lock();
+    std::vector<unsigned char> pageable;
+    unsigned char* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaError_t ce = cudaSuccess;
+    if (pinned && pool_bytes < stage_bytes) {
+      for (int q = 0; q < 2; ++q) {
+        if (pool[q]) cudaFreeHost(pool[q]);
+        pool[q] = nullptr;
+      }
+      pool_bytes = 0;
+      if (cudaMallocHost((void**)&pool[0], stage_bytes) == cudaSuccess && cudaMallocHost((void**)&pool[1], stage_bytes) == cudaSuccess) {
+        pool_bytes = stage_bytes;
+      } else {
+        for (int q = 0; q < 2; ++q) {
+          if (pool[q]) cudaFreeHost(pool[q]);
+          pool[q] = nullptr;
+        }
+        cudaGetLastError();
+        pinned = false;
+        pool_lock.unlock();
+      }
     }
-    CB(cudaMemcpyAsync(b->d_ipool, hi.data(), sizeof(int32_t) * hi.size(), cudaMemcpyHostToDevice, b->stream));
-    CB(cudaMemcpyAsync(b->d_cpool, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, b->stream));
-    CB(cudaMemcpyAsync(b->d_desc, b->desc.data(), sizeof(WinDesc) * n_windows, cudaMemcpyHostToDevice, b->stream));
-    CB(cudaMemcpyAsync(b->d_state_off, b->state_off.data(), sizeof(int64_t) * (n_windows + 1), cudaMemcpyHostToDevice, b->stream));
-    CB(cudaMemcpyAsync(b->d_stage, b->h_stage, sizeof(double) * so, cudaMemcpyHostToDevice, b->stream));
-    CB(cudaStreamSynchronize(b->stream));  // hi / hc go out of scope
+    if (pinned) {
+      stage[0] = pool[0];
+      stage[1] = pool[1];
+    } else {
+      pageable.resize(stage_bytes);
+      stage[0] = stage[1] = pageable.data();
+    }
+    for (int q = 0; q < 2 && ce == cudaSuccess; ++q) ce = cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming);
+    const int hw = std::max(1, (int)std::thread::hardware_concurrency());
+    int w0 = 0;
+    for (int c = 0; w0 < n_windows && ce == cudaSuccess; ++c) {
+      int w1 = w0 + 1;
+      while (w1 < n_windows && chunk_bytes(w0, w1 + 1) <= stage_bytes) ++w1;
+      unsigned char* buf = stage[c & 1];
+      if (c >= (pinned ? 2 : 1)) ce = cudaEventSynchronize(ev[(c + (pinned ? 0 : 1)) & 1]);  // the buffer is free again
+      if (ce != cudaSuccess) break;
+      const size_t ib = i_begin(w0), cb = c_begin(w0);
+      const size_t ibytes = (sizeof(int32_t) * (i_begin(w1) - ib) + 15) & ~(size_t)15;
+      int32_t* hi = reinterpret_cast<int32_t*>(buf);
+      double* hc = reinterpret_cast<double*>(buf + ibytes);
+      std::atomic<int> next(w0);
+      auto work = [&]() {
+        for (;;) {
+          const int w = next.fetch_add(1);
+          if (w >= w1) break;
+          const WindowPlan& p = plans[w];
+          std::memset(hi + (i_begin(w) - ib), 0, sizeof(int32_t) * (i_begin(w + 1) - i_begin(w)));
+          std::memset(hc + (c_begin(w) - cb), 0, sizeof(double) * (c_begin(w + 1) - c_begin(w)));
+          for (int a = 0; a < NUM_IARR; ++a)
+            if (!p.iarr[a].empty()) std::memcpy(hi + (b->desc[w].ioff[a] - ib), p.iarr[a].data(), sizeof(int32_t) * p.iarr[a].size());
+          for (int a = 0; a < NUM_CARR; ++a)
+            if (!p.carr[a].empty()) std::memcpy(hc + (b->desc[w].coff[a] - cb), p.carr[a].data(), sizeof(double) * p.carr[a].size());
+          std::memcpy(b->h_stage + b->state_off[w], p.state.data(), sizeof(double) * p.state.size());
+        }
+      };
+      {
+        const int nt = std::max(1, std::min(hw, (w1 - w0) / 4));
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+      }
+      if (i_begin(w1) > ib)
+        ce = cudaMemcpyAsync(b->d_ipool + ib, hi, sizeof(int32_t) * (i_begin(w1) - ib), cudaMemcpyHostToDevice, b->stream);
+      if (ce == cudaSuccess && c_begin(w1) > cb)
+        ce = cudaMemcpyAsync(b->d_cpool + cb, hc, sizeof(double) * (c_begin(w1) - cb), cudaMemcpyHostToDevice, b->stream);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ev[c & 1], b->stream);
+      w0 = w1;
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(b->d_desc, b->desc.data(), sizeof(WinDesc) * n_windows, cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(b->d_state_off, b->state_off.data(), sizeof(int64_t) * (n_windows + 1), cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(b->d_stage, b->h_stage, sizeof(double) * so, cudaMemcpyHostToDevice, b->stream);
+    cudaError_t cs = cudaStreamSynchronize(b->stream);  // the staging buffers go away
+    if (ce == cudaSuccess) ce = cs;
+    for (int q = 0; q < 2; ++q)
+      if (ev[q]) cudaEventDestroy(ev[q]);
+    if (ce != cudaSuccess) return bail(ce, "pool upload");
   }
+  mark("pack + upload");
   DeviceBatch& db = b->db;
   std::memset(&db, 0, sizeof(db));
   db.n_windows = n_windows;
@@ -283,6 +379,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   CB(cudaStreamSynchronize(b->stream));
   b->h_state.resize(n_windows);
   *out = b;
+  mark("configure");
   return SWGN_OK;
 #undef CB
 }
