@@ -307,6 +307,14 @@ swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t window, int32
 swgn_status swgn_batch_get_head_marginal(swgn_batch* b, int32_t window, int32_t n_tail, double* A,
                                          double* bvec);
 
+/* The next window's marginalisation prior in one call: UpdateSchur as above followed by
+   MarginalizationInfo::setmarginalizeinfo(..., Sqrt = true) (RVI/factor/marginalization_factor.cpp:449-475):
+   A = V S V', J0 = sqrt(S) V' (n_tail x n_tail row-major), r0 = S^-1/2 V' b, eigenvalues <= 1e-8 dropped --
+   exactly the prior_J / prior_r0 arrays of swgn_graph (x0 = the current states of the head blocks).
+   A and bvec (may be NULL) return the information form. */
+swgn_status swgn_batch_get_marginal_prior(swgn_batch* b, int32_t window, int32_t n_tail, double* J0,
+                                          double* r0, double* A, double* bvec);
+
 /* Hidden GNSS-frame states of the IMUGNSSFactor chains of `window` after the last Jacobian
    evaluation (the reference updates gnss_poses[i] / gnss_speed_bias[i] in user memory,
    gnss_imu_factor.cpp:601-632): 16 doubles (pose 7, speed-bias 9) per hidden frame in graph

@@ -85,6 +85,26 @@ int oracle_evaluate(void* h, double* cost, double* residuals, double* gradient, 
   return 0;
 }
 
+// MarginalizationInfo::setmarginalizeinfo(..., Sqrt = true)  RVI/factor/marginalization_factor.cpp:449-475:
+// J0 = sqrt(S) V', r0 = S^-1/2 V' b from the eigen-decomposition of A (threshold eps = 1e-8)
+void oracle_prior_sqrt(const double* A, const double* b, int n, double* J0, double* r0) {
+  Mat Am(n, n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Am(i, j) = A[(size_t)i * n + j];
+  std::vector<double> w;
+  Mat V;
+  eig_sym(Am, &w, &V);
+  for (int i = 0; i < n; ++i) {
+    const double S = w[i] > 1e-8 ? w[i] : 0.0, Sinv = w[i] > 1e-8 ? 1.0 / w[i] : 0.0;
+    double dot = 0.0;
+    for (int c = 0; c < n; ++c) {
+      J0[(size_t)i * n + c] = std::sqrt(S) * V(c, i);
+      dot += V(c, i) * b[c];
+    }
+    r0[i] = std::sqrt(Sinv) * dot;
+  }
+}
+
 // batched IMU pre-integration, factor f = samples [begin[f], begin[f+1]); returns the number of failures
 int oracle_preintegrate_batch(int n, const int32_t* begin, const double* samples, const double* bias, const double* noise4,
                               double* records) {

@@ -741,6 +741,30 @@ swgn_status swgn_batch_get_head_marginal(swgn_batch* b, int32_t w, int32_t n_tai
   return SWGN_OK;
 }
 
+swgn_status swgn_batch_get_marginal_prior(swgn_batch* b, int32_t w, int32_t n_tail, double* J0, double* r0, double* A, double* bvec) {
+  if (!b || w < 0 || w >= b->n || !J0 || !r0 || n_tail <= 0 || n_tail > b->desc[w].n_f) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  TRState t;
+  CU(cudaMemcpy(&t, b->d_state + w, sizeof(t), cudaMemcpyDeviceToHost));
+  if (!t.have_reduced) return fail(SWGN_ERR_INVALID, "no reduced system available: run an export-mode solve (is_optimize = 0) first");
+  const int nf = b->desc[w].n_f, m = nf - n_tail;
+  const size_t na = (size_t)n_tail * n_tail;
+  const size_t ns = std::max(head_marginal_scratch_doubles(m, n_tail), prior_sqrt_scratch_doubles(n_tail));
+  double* dbuf = nullptr;  // A | b | J0 | r0 | scratch
+  CU(cudaMalloc(&dbuf, sizeof(double) * (2 * na + 2 * (size_t)n_tail + ns)));
+  double *dA = dbuf, *db = dbuf + na, *dJ = db + n_tail, *dr = dJ + na, *dscr = dr + n_tail;
+  cudaError_t e = launch_head_marginal(b->db, w, nf, n_tail, dA, db, dscr, b->stream);
+  if (e == cudaSuccess) e = launch_prior_sqrt(dA, db, n_tail, dJ, dr, dscr, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(J0, dJ, sizeof(double) * na, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r0, dr, sizeof(double) * n_tail, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess && A) e = cudaMemcpyAsync(A, dA, sizeof(double) * na, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess && bvec) e = cudaMemcpyAsync(bvec, db, sizeof(double) * n_tail, cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  cudaFree(dbuf);
+  CU(e);
+  return SWGN_OK;
+}
+
 swgn_status swgn_batch_get_chain_frames(swgn_batch* b, int32_t w, int32_t* n_frames, double* frames) {
   if (!b || w < 0 || w >= b->n || !n_frames) return fail(SWGN_ERR_INVALID, "bad arguments");
   const WinDesc& d = b->desc[w];

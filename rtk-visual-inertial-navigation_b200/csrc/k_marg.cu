@@ -65,6 +65,53 @@ __global__ void __launch_bounds__(NT) k_head_marginal(DeviceBatch b, int window,
   }
 }
 
+// MarginalizationInfo::setmarginalizeinfo(..., Sqrt = true) (RVI/factor/marginalization_factor.cpp:449-475): the
+// information form (A, b) of the head blocks becomes the next window's prior factor r = r0 + J0 (x [-] x0) with
+//   J0 = sqrt(S) V',  r0 = S^-1/2 V' b,   A = V S V', eigenvalues <= 1e-8 dropped.
+// One CTA; A and V in shared memory when n <= 100, otherwise in the global scratch (2 * n * (n|1) doubles).
+__global__ void __launch_bounds__(NT) k_prior_sqrt(const double* A_in, const double* b_in, int n, double* J0, double* r0, double* scratch) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x;
+  const int ld = n | 1;
+  const bool in_smem = n <= kMaxSharedM;
+  double* cs = sm;
+  double* red = cs + 4 * ((n + 1) / 2) + 4;
+  double* A = in_smem ? red + 34 : scratch;
+  double* V = A + (size_t)n * ld;
+  for (int o = tid; o < n * n; o += NT) {
+    const int i = o / n, j = o - i * n;
+    A[i * ld + j] = j >= i ? A_in[(size_t)i * n + j] : A_in[(size_t)j * n + i];  // SelfAdjointEigenSolver reads one triangle
+    V[i * ld + j] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  jacobi_eig<NT>(A, V, n, ld, cs, red);
+  __syncthreads();
+  for (int o = tid; o < n * n; o += NT) {
+    const int i = o / n, c = o - i * n;
+    const double lam = A[i * ld + i];
+    J0[o] = (lam > kEigEps ? sqrt(lam) : 0.0) * V[c * ld + i];
+  }
+  for (int i = tid; i < n; i += NT) {
+    const double lam = A[i * ld + i];
+    double acc = 0.0;
+    for (int c = 0; c < n; ++c) acc += V[c * ld + i] * b_in[c];
+    r0[i] = (lam > kEigEps ? sqrt(1.0 / lam) : 0.0) * acc;
+  }
+}
+
+size_t prior_sqrt_scratch_doubles(int n) { return n > kMaxSharedM ? 2 * (size_t)n * (n | 1) + 2 : 2; }
+
+cudaError_t launch_prior_sqrt(const double* A_dev, const double* b_dev, int n, double* J0_dev, double* r0_dev, double* scratch, cudaStream_t s) {
+  size_t dyn = sizeof(double) * (size_t)(4 * ((n + 1) / 2) + 4 + 34);
+  if (n <= kMaxSharedM) dyn += sizeof(double) * 2 * (size_t)n * (n | 1);
+  if (dyn > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_prior_sqrt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+  }
+  k_prior_sqrt<<<1, NT, dyn, s>>>(A_dev, b_dev, n, J0_dev, r0_dev, scratch);
+  return cudaGetLastError();
+}
+
 size_t head_marginal_scratch_doubles(int m, int n) {
   size_t w = (size_t)m * (n + 1);
   if (m > kMaxSharedM) w += 2 * (size_t)m * (m | 1);

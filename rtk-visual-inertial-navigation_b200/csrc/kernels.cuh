@@ -48,6 +48,10 @@ void launch_finish(const DeviceBatch& b, cudaStream_t s);
 size_t head_marginal_scratch_doubles(int m, int n);
 cudaError_t launch_head_marginal(const DeviceBatch& b, int window, int n_f, int n, double* A_dev, double* b_dev, double* scratch,
                                  cudaStream_t s);
+// MarginalizationInfo::setmarginalizeinfo (marginalization_factor.cpp:449-475): (A, b) -> prior factor (J0, r0)
+size_t prior_sqrt_scratch_doubles(int n);
+cudaError_t launch_prior_sqrt(const double* A_dev, const double* b_dev, int n, double* J0_dev, double* r0_dev, double* scratch,
+                              cudaStream_t s);
 void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s);
 
 // IMU pre-integration (k_preint.cu): one warp per factor; noise4 = ACC_N, GYR_N, ACC_W, GYR_W (host array)

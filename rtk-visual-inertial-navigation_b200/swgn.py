@@ -219,6 +219,7 @@ def lib():
         L.swgn_batch_linear_solve.argtypes = [C.c_void_p, i32, P(f64), P(f64)]
         L.swgn_preintegrate_batch.argtypes = [i32, i32, P(i32), P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_batch_get_head_marginal.argtypes = [C.c_void_p, i32, i32, P(f64), P(f64)]
+        L.swgn_batch_get_marginal_prior.argtypes = [C.c_void_p, i32, i32, P(f64), P(f64), P(f64), P(f64)]
         L.swgn_batch_get_chain_frames.argtypes = [C.c_void_p, i32, P(i32), P(f64)]
         L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_ambiguity_fix.argtypes = [i32, i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32),
@@ -334,6 +335,13 @@ class Batch:
         bv = np.zeros(n_tail)
         _check(lib().swgn_batch_get_head_marginal(self.h, w, n_tail, _dp(A), _dp(bv)), "head_marginal")
         return A, bv
+
+    def marginal_prior(self, w, n_tail):
+        """UpdateSchur + setmarginalizeinfo: (J0, r0, A, b) of the trailing n_tail rows after an export-mode solve."""
+        J0, A = np.zeros((n_tail, n_tail)), np.zeros((n_tail, n_tail))
+        r0, bv = np.zeros(n_tail), np.zeros(n_tail)
+        _check(lib().swgn_batch_get_marginal_prior(self.h, w, n_tail, _dp(J0), _dp(r0), _dp(A), _dp(bv)), "marginal_prior")
+        return J0, r0, A, bv
 
     def chain_frames(self, w):
         """Hidden GNSS-frame states of window w's IMUGNSSFactor chains, (n_frames, 16)."""

@@ -212,6 +212,17 @@ def preintegrate_batch(sample_begin, samples, bias, noise):
     return rec, bad
 
 
+def prior_sqrt(A, b):
+    A = np.ascontiguousarray(A, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    n = A.shape[0]
+    J0, r0 = np.zeros((n, n)), np.zeros(n)
+    L = oracle()
+    L.oracle_prior_sqrt.argtypes = [P(f64), P(f64), i32, P(f64), P(f64)]
+    L.oracle_prior_sqrt(_dp(A), _dp(b), n, _dp(J0), _dp(r0))
+    return J0, r0
+
+
 def update_schur(S, r, n_tail):
     S = np.ascontiguousarray(S)
     r = np.ascontiguousarray(r)

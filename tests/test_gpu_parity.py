@@ -218,6 +218,37 @@ def test_update_schur_on_the_device(which, wid, n_head):
     b.close()
 
 
+@pytest.mark.parametrize("which,wid,n_head", [(2, 1, None), (1, 0, 2)])
+def test_marginal_prior_on_the_device(which, wid, n_head):
+    """Export-mode solve -> UpdateSchur -> setmarginalizeinfo (marginalization_factor.cpp:449-475): the prior
+    factor (J0, r0) of the head blocks.  J0 = sqrt(S) V' is defined up to the sign / order of the eigenvectors,
+    so J0'J0 = A and J0'r0 = b are checked, against the device's own (A, b) and against the oracle's factor."""
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    if n_head is not None:
+        opt.n_parameter_head = n_head
+    opt.is_optimize = 0
+    opt.max_num_iterations = 1
+    b = swgn.Batch([w.graph_p], opt)
+    b.solve()
+    cb, co, cs = b.columns(0)
+    n_tail = int(cs[len(cs) - opt.n_parameter_head:].sum())
+    J0, r0, A, bv = b.marginal_prior(0, n_tail)
+    A2, b2 = b.head_marginal(0, n_tail)
+    assert np.array_equal(A, A2) and np.array_equal(bv, b2)
+    scale = np.abs(A).max()
+    Au = np.triu(A) + np.triu(A, 1).T  # SelfAdjointEigenSolver reads one triangle; A itself is symmetric to rounding only
+    assert np.abs(J0.T @ J0 - Au).max() < 1e-9 * scale
+    assert np.abs(J0.T @ r0 - bv).max() < 1e-8 * max(1.0, np.abs(bv).max())
+    oJ, orr = ob.prior_sqrt(Au, bv)
+    assert np.abs(oJ.T @ oJ - J0.T @ J0).max() < 1e-9 * scale
+    assert abs(orr @ orr - r0 @ r0) < 1e-8 * (orr @ orr)
+    # the prior drives the same solution as the information form: argmin |r0 + J0 d|^2 = -A^-1 b
+    d = np.linalg.lstsq(J0, -r0, rcond=None)[0]
+    assert rel(d, -np.linalg.solve(A, bv)) < 1e-6
+    b.close()
+
+
 def test_cholesky_export_and_tail_information():
     w = swgn.SynthWindow(2, 2)
     opt = w.options()
