@@ -51,7 +51,11 @@ enum IArr {
   I_STERM,          // [n_sterms] gather terms of the e-cells (see below): (a, b), or (a, b, b2, 0) on diagonal cells
   I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
   I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
-  I_SROW,           // [n_srows] rows (with f-cells) of the simple chunks: one thread each in phase 1b
+  I_SROW,           // [n_srows * 8] rows (with f-cells) of the simple chunks, one thread each in phase 1b; a self-contained
+                    //               record per row so that the thread needs ONE index load before its data loads:
+                    //               E value offset, nres | es << 8 | n_fcells << 16, chunk factor offset (W_EFAC),
+                    //               first f-cell (index into I_CELL_*), then for the first f-cell: value offset,
+                    //               W_EBUF slot offset, tangent size; 0
   I_ECELL,          // (unused)
   I_ECELL_G,        // [1] number of e-cells (statistic)
   I_ESTREAM,        // per-warp gather streams of the raw chunk products E'[E | b | F] of the 4..16-dim e-blocks

@@ -348,24 +348,23 @@ __device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const doub
 }
 
 // ---- phase 1b: one thread per row of a simple chunk: W_f = (L^-1 E') F_f, stored once ---------
+// rec = the row's self-contained record (I_SROW): every data load below depends on that one index load only
 template <int ES>
-__device__ __forceinline__ void row_w(const Win& v, int r, int chunk) {
-  const int32_t* row_cell = v.I(I_ROW_CELL);
-  const int32_t* cell_col = v.I(I_CELL_COL);
-  const int32_t* cell_val = v.I(I_CELL_VAL);
-  const int32_t* cell_slot = v.I(I_CELL_SLOT);
-  const int32_t* col_size = v.I(I_COL_SIZE);
+__device__ __forceinline__ void row_w(const Win& v, const int4 r0, const int4 r1) {
   const double* J = v.W(W_JAC);
   double* EB = v.W(W_EBUF);
-  const double* Lp = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+  const double* Lp = v.W(W_EFAC) + r0.z;
+  const double* E = J + r0.x;
+  const int nres = r0.y & 0xff, n_fcells = r0.y >> 16;
   double L[ES][ES];
 #pragma unroll
   for (int i = 0; i < ES; ++i)
 #pragma unroll
     for (int k = 0; k <= i; ++k) L[i][k] = Lp[i * ES + k];
-  const int c0 = row_cell[r], c1 = row_cell[r + 1];
-  const double* E = J + cell_val[c0];
-  const int nres = v.I(I_ROW_NRES)[r];
+  const int32_t* cell_col = v.I(I_CELL_COL);
+  const int32_t* cell_val = v.I(I_CELL_VAL);
+  const int32_t* cell_slot = v.I(I_CELL_SLOT);
+  const int32_t* col_size = v.I(I_COL_SIZE);
   if (nres == 2) {  // the visual case: both residual rows at once, every W entry written once
     double v0[ES], v1[ES];
 #pragma unroll
@@ -379,10 +378,11 @@ __device__ __forceinline__ void row_w(const Win& v, int r, int chunk) {
       v0[i] = s0 / L[i][i];
       v1[i] = s1 / L[i][i];
     }
-    for (int c = c0 + 1; c < c1; ++c) {
-      const int fs = col_size[cell_col[c]];
-      const double* F = J + cell_val[c];
-      double* Wf = EB + cell_slot[c];
+    for (int q = 0; q < n_fcells; ++q) {
+      const int c = r0.w + q;
+      const int fs = q == 0 ? r1.z : col_size[cell_col[c]];
+      const double* F = J + (q == 0 ? r1.x : cell_val[c]);
+      double* Wf = EB + (q == 0 ? r1.y : cell_slot[c]);
       for (int j = 0; j < fs; ++j) {
         const double f0 = F[j], f1 = F[fs + j];
 #pragma unroll
@@ -400,10 +400,11 @@ __device__ __forceinline__ void row_w(const Win& v, int r, int chunk) {
       for (int k = 0; k < i; ++k) s -= L[i][k] * vv[k];
       vv[i] = s / L[i][i];
     }
-    for (int c = c0 + 1; c < c1; ++c) {
-      const int fs = col_size[cell_col[c]];
-      const double* F = J + cell_val[c] + rr * fs;
-      double* Wf = EB + cell_slot[c];
+    for (int q = 0; q < n_fcells; ++q) {
+      const int c = r0.w + q;
+      const int fs = q == 0 ? r1.z : col_size[cell_col[c]];
+      const double* F = J + (q == 0 ? r1.x : cell_val[c]) + rr * fs;
+      double* Wf = EB + (q == 0 ? r1.y : cell_slot[c]);
       for (int j = 0; j < fs; ++j) {
         const double f = F[j];
 #pragma unroll
@@ -483,15 +484,48 @@ __device__ void chunk_warp(const Win& v, int chunk, const double* lmd, double* s
     const int i = k / es, j = k - i * es;
     fac[k] = (j <= i) ? ete[i * MAX_WARP_E + j] : 0.0;
   }
-  // forward substitution L^-1 on every column of every slot block and on g, then store
-  for (int s = s0; s <= s1; ++s) {
-    const int fs = (s < s1) ? col_size[slot_col[s]] : 1;
-    const int off = ((s < s1) ? slot_buf[s] : gofs) - ebase;
-    for (int j = lane; j < fs; j += 32) {
-      for (int i = 0; i < es; ++i) {
-        double t = buf[off + i * fs + j];
-        for (int k = 0; k < i; ++k) t -= ete[i * MAX_WARP_E + k] * buf[off + k * fs + j];
-        buf[off + i * fs + j] = t / ete[i * MAX_WARP_E + i];
+  // forward substitution L^-1 on every column of every slot block and on g.  The columns of all slots are
+  // flattened over the lanes (a 9-dim e-block has ~40 columns in 6..8 slots: two passes instead of one
+  // pass per slot with 6..9 busy lanes); the slot table is loaded once, one slot per lane
+  const int ns1 = s1 - s0 + 1;  // slots + the g column
+  if (ns1 <= 32) {
+    int my_fs = 0, my_off = 0;
+    if (lane < ns1) {
+      const int s = s0 + lane;
+      my_fs = (s < s1) ? col_size[slot_col[s]] : 1;
+      my_off = ((s < s1) ? slot_buf[s] : gofs) - ebase;
+    }
+    int pre = my_fs;  // inclusive prefix sum of the slot widths
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, ns1 - 1);
+    for (int c = lane; c < ((total + 31) & ~31); c += 32) {
+      int fs = 1, off = 0, j = -1;
+      for (int s = 0; s < ns1; ++s) {
+        const int hi = __shfl_sync(0xffffffffu, pre, s), f = __shfl_sync(0xffffffffu, my_fs, s), o = __shfl_sync(0xffffffffu, my_off, s);
+        if (c < total && c >= hi - f && c < hi) { fs = f; off = o; j = c - (hi - f); }
+      }
+      if (j >= 0) {
+        for (int i = 0; i < es; ++i) {
+          double t = buf[off + i * fs + j];
+          for (int k = 0; k < i; ++k) t -= ete[i * MAX_WARP_E + k] * buf[off + k * fs + j];
+          buf[off + i * fs + j] = t / ete[i * MAX_WARP_E + i];
+        }
+      }
+    }
+  } else {
+    for (int s = s0; s <= s1; ++s) {
+      const int fs = (s < s1) ? col_size[slot_col[s]] : 1;
+      const int off = ((s < s1) ? slot_buf[s] : gofs) - ebase;
+      for (int j = lane; j < fs; j += 32) {
+        for (int i = 0; i < es; ++i) {
+          double t = buf[off + i * fs + j];
+          for (int k = 0; k < i; ++k) t -= ete[i * MAX_WARP_E + k] * buf[off + k * fs + j];
+          buf[off + i * fs + j] = t / ete[i * MAX_WARP_E + i];
+        }
       }
     }
   }
@@ -564,16 +598,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
     for (int k = gwid; k < d.n_wchunks; k += kClusterWarps) chunk_warp(v, wch[k], lmd, sm);
   }
   {
-    const int32_t* srow = v.I(I_SROW);
-    const int32_t* row_chunk = v.I(I_ROW_CHUNK);
-    const int32_t* chunk_ecol = v.I(I_CHUNK_ECOL);
-    const int32_t* col_size = v.I(I_COL_SIZE);
+    const int4* srow = reinterpret_cast<const int4*>(v.I(I_SROW));
     for (int k = gtid; k < d.n_srows; k += kClusterThreads) {
-      const int r = srow[k], chunk = row_chunk[r];
-      const int es = col_size[chunk_ecol[chunk]];
-      if (es == 3) row_w<3>(v, r, chunk);
-      else if (es == 1) row_w<1>(v, r, chunk);
-      else row_w<2>(v, r, chunk);
+      const int4 r0 = srow[2 * k], r1 = srow[2 * k + 1];
+      const int es = (r0.y >> 8) & 0xff;
+      if (es == 3) row_w<3>(v, r0, r1);
+      else if (es == 1) row_w<1>(v, r0, r1);
+      else row_w<2>(v, r0, r1);
     }
   }
   cluster_sync();

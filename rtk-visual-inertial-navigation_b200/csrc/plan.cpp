@@ -604,7 +604,12 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       I[I_CHUNK_SIMPLE].push_back(simple ? 1 : 0);
       if (simple)
         for (int r = I[I_CHUNK_ROW][ch]; r < I[I_CHUNK_ROW][ch + 1]; ++r)
-          if (I[I_ROW_CELL][r + 1] - I[I_ROW_CELL][r] > 1) I[I_SROW].push_back(r);
+          if (I[I_ROW_CELL][r + 1] - I[I_ROW_CELL][r] > 1) {
+            const int c0 = I[I_ROW_CELL][r], nf_cells = I[I_ROW_CELL][r + 1] - c0 - 1;
+            const int32_t rec[8] = {I[I_CELL_VAL][c0], I[I_ROW_NRES][r] | (es << 8) | (nf_cells << 16), I[I_CHUNK_FAC][ch], c0 + 1,
+                                    I[I_CELL_VAL][c0 + 1], I[I_CELL_SLOT][c0 + 1], col_size[I[I_CELL_COL][c0 + 1]], 0};
+            I[I_SROW].insert(I[I_SROW].end(), rec, rec + 8);
+          }
     }
   }
   // CSC
@@ -745,7 +750,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_wchunks = (int)I[I_WCHUNK].size();
   d.n_scells = (int)(I[I_SCELL].size() / 8);
   d.n_sterms = (int)I[I_STERM].size();
-  d.n_srows = (int)I[I_SROW].size();
+  d.n_srows = (int)(I[I_SROW].size() / 8);
   d.n_ecells = I[I_ECELL_G].empty() ? 0 : I[I_ECELL_G][0];
   d.max_wbuf = max_wbuf;
   d.n_wstream = (int)(I[I_WSTREAM].size() / 4);
