@@ -47,7 +47,8 @@ enum IArr {
   I_SCELL,          // [n_scells * 8] directory of the touched block cells of S (the kernel reads I_WSTREAM): ps, qs,
                     //                S offset (row*ld+col), 0, term count, diag flag (1: p == q:
                     //                add D^2, carries the rhs as an extra column), first run, run count
-  I_SRUN,           // (unused)
+  I_TCHUNK_W,       // [n_tchunks_w] small chunks (e-size <= 3) whose slots are fed by several rows (epoch clocks: one row per
+                    //               satellite and observable): one WARP each in phase 1a, lanes over the rows
   I_STERM,          // [n_sterms] gather terms of the e-cells (see below): (a, b), or (a, b, b2, 0) on diagonal cells
   I_ROW_CHUNK,      // [n_rows] chunk of the row, -1 without e-block
   I_CHUNK_SIMPLE,   // [n_chunks] 1: small e-block and every slot is fed by exactly one row
@@ -62,6 +63,7 @@ enum IArr {
                     // (phase 1a of k_schur); same stage records as I_WSTREAM with header flag bit 1 set:
                     // w0 = output offset (W_EFAC for the [E'E | E'b] cell, W_EBUF for E'F), w1 = W_EBUF offset of E'b
   I_ESTREAM_PTR,    // [SCHUR_WARPS + 1]
+  I_TCHUNK_T,       // [n_tchunks_t] the other small chunks: one THREAD each in phase 1a (I_TCHUNK = both lists, for k_backsub)
   I_WSTREAM,        // [n_wstream * 4] per-warp gather streams of the reduced system (phase 2 of k_schur): stages of
                     //                 1 + SCHUR_STAGE 16-byte records, see "gather stream" below
   I_WSTREAM_PTR,    // [SCHUR_WARPS + 1] first STAGE of every warp's stream
@@ -182,6 +184,7 @@ struct WinDesc {
   int32_t n_jac, n_ebuf, ld, n_proj, n_imu, n_gnss, n_prior, n_prior_blk, n_unit, n_efac, n_head;
   int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, n_ecells;
   int32_t n_chain, n_chain_frames, max_chain_k, n_wstream;
+  int32_t n_tchunks_t, n_tchunks_w;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

@@ -347,6 +347,144 @@ __device__ __forceinline__ void chunk_thread(const Win& v, int chunk, const doub
   }
 }
 
+// ---- phase 1a, small e-blocks whose slots are fed by several rows: one warp per chunk, lanes over the rows ----
+// (planner: <= 32 rows, <= 2 residuals and <= 4 f-cells per row, <= 32 slots).  Same arithmetic as chunk_thread, but
+// the rows' index -> Jacobian load chains run side by side instead of one after the other, and the slot sums
+// are warp reductions instead of read-modify-write chains through W_EBUF.
+template <int ES>
+__device__ void chunk_small_warp(const Win& v, int chunk, const double* lmd) {
+  const int lane = threadIdx.x & 31;
+  const int32_t* row_cell = v.I(I_ROW_CELL);
+  const int32_t* cell_col = v.I(I_CELL_COL);
+  const int32_t* cell_val = v.I(I_CELL_VAL);
+  const int32_t* cell_slot = v.I(I_CELL_SLOT);
+  const int32_t* col_size = v.I(I_COL_SIZE);
+  const double* J = v.W(W_JAC);
+  const double* R = v.W(W_RES);
+  double* EB = v.W(W_EBUF);
+  const int ecol = v.I(I_CHUNK_ECOL)[chunk];
+  const int epos = v.I(I_COL_POS)[ecol];
+  const int r0 = v.I(I_CHUNK_ROW)[chunk], r1 = v.I(I_CHUNK_ROW)[chunk + 1];
+  const int s0 = v.I(I_CHUNK_SLOT)[chunk], ns = v.I(I_CHUNK_SLOT)[chunk + 1] - s0;
+  // slot table, one slot per lane
+  int my_fs = 0, my_buf = -1;
+  if (lane < ns) {
+    my_fs = col_size[v.I(I_SLOT_COL)[s0 + lane]];
+    my_buf = v.I(I_SLOT_BUF)[s0 + lane];
+  }
+  // my row
+  const int r = r0 + lane;
+  const bool have = r < r1;
+  int nres = 0, nfc = 0, fval[4] = {0, 0, 0, 0}, fslot[4] = {-1, -1, -1, -1};
+  double e[2][ES], br[2] = {0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int i = 0; i < ES; ++i) e[q][i] = 0.0;
+  if (have) {
+    const int c0 = row_cell[r], c1 = row_cell[r + 1];
+    nres = v.I(I_ROW_NRES)[r];
+    nfc = c1 - c0 - 1;
+    const double* E = J + cell_val[c0];
+    const double* bb = R + v.I(I_ROW_RES)[r];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < nfc) {
+        fval[q] = cell_val[c0 + 1 + q];
+        fslot[q] = cell_slot[c0 + 1 + q];
+      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (q < nres) {
+#pragma unroll
+        for (int i = 0; i < ES; ++i) e[q][i] = E[q * ES + i];
+        br[q] = bb[q];
+      }
+  }
+  double ete[ES][ES], g[ES];
+#pragma unroll
+  for (int i = 0; i < ES; ++i) {
+    g[i] = warp_sum(e[0][i] * br[0] + e[1][i] * br[1]);
+#pragma unroll
+    for (int j = i; j < ES; ++j) ete[i][j] = warp_sum(e[0][i] * e[0][j] + e[1][i] * e[1][j]);
+    const double dd = lmd ? lmd[epos + i] : 0.0;
+    ete[i][i] += dd * dd;
+  }
+  double L[ES][ES];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < ES; ++j) {
+    double dj = ete[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k];
+    if (!(dj > 0.0)) ok = false;
+    dj = sqrt(dj);
+    L[j][j] = dj;
+#pragma unroll
+    for (int i = j + 1; i < ES; ++i) {
+      double s = ete[j][i];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / dj;
+    }
+  }
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < ES; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L[i][j] = nan("");
+  }
+  if (lane == 0) {
+    double* fac = v.W(W_EFAC) + v.I(I_CHUNK_FAC)[chunk];
+#pragma unroll
+    for (int i = 0; i < ES; ++i)
+#pragma unroll
+      for (int j = 0; j < ES; ++j) fac[i * ES + j] = (j <= i) ? L[i][j] : 0.0;
+    double wg[ES];
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+      double s = g[i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s -= L[i][k] * wg[k];
+      wg[i] = s / L[i][i];
+    }
+    double* gp = EB + v.I(I_CHUNK_G)[chunk];
+#pragma unroll
+    for (int i = 0; i < ES; ++i) gp[i] = wg[i];
+  }
+  // vv_q = L^-1 E_q' for my residual rows
+  double vv[2][ES];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+      double s = e[q][i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s -= L[i][k] * vv[q][k];
+      vv[q][i] = s / L[i][i];
+    }
+  // W_f = sum over the rows feeding slot f of vv' F_f: one warp reduction per element of the slot block
+  for (int s = 0; s < ns; ++s) {
+    const int fs = __shfl_sync(0xffffffffu, my_fs, s), sb = __shfl_sync(0xffffffffu, my_buf, s);
+    int mine = -1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (fslot[q] == sb) mine = fval[q];
+    for (int j = 0; j < fs; ++j) {
+      double f0 = 0.0, f1 = 0.0;
+      if (mine >= 0) {
+        f0 = J[mine + j];
+        if (nres > 1) f1 = J[mine + fs + j];
+      }
+#pragma unroll
+      for (int i = 0; i < ES; ++i) {
+        const double w = warp_sum(vv[0][i] * f0 + vv[1][i] * f1);
+        if (lane == 0) EB[sb + i * fs + j] = w;
+      }
+    }
+  }
+}
+
 // ---- phase 1b: one thread per row of a simple chunk: W_f = (L^-1 E') F_f, stored once ---------
 // rec = the row's self-contained record (I_SROW): every data load below depends on that one index load only
 template <int ES>
@@ -577,8 +715,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   // phase 1a: factors of the small chunks (one thread each; W buffers too unless row-parallel) and,
   // on the tensor pipe, the raw products E'[E | b | F] of the larger e-blocks (one warp per e-cell)
   {
-    const int32_t* tch = v.I(I_TCHUNK);
-    for (int k = gtid; k < d.n_tchunks; k += kClusterThreads) chunk_dispatch(v, tch[k], lmd);
+    const int32_t* tcw = v.I(I_TCHUNK_W);
+    for (int k = gwid; k < d.n_tchunks_w; k += kClusterWarps) {
+      const int chunk = tcw[k];
+      const int es = v.I(I_COL_SIZE)[v.I(I_CHUNK_ECOL)[chunk]];
+      if (es == 1) chunk_small_warp<1>(v, chunk, lmd);
+      else if (es == 3) chunk_small_warp<3>(v, chunk, lmd);
+      else chunk_small_warp<2>(v, chunk, lmd);
+    }
+    const int32_t* tch = v.I(I_TCHUNK_T);
+    for (int k = gtid; k < d.n_tchunks_t; k += kClusterThreads) chunk_dispatch(v, tch[k], lmd);
     const int32_t* eptr = v.I(I_ESTREAM_PTR);
     const int4* gs = reinterpret_cast<const int4*>(v.I(I_ESTREAM)) + (size_t)eptr[wid] * kStageRecs;
     const double* JWc = v.W(W_JAC);

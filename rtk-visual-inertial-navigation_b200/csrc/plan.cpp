@@ -602,6 +602,15 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
           if (!I[I_CELL_FIRST][c]) simple = false;
       }
       I[I_CHUNK_SIMPLE].push_back(simple ? 1 : 0);
+      if (es <= 3) {
+        // several rows feed one slot (e.g. all satellites of an epoch share the pose slot of the clock's chunk): a
+        // single thread would walk the rows one dependent load chain after the other -> one warp, lanes over rows
+        const int nrows_ch = I[I_CHUNK_ROW][ch + 1] - I[I_CHUNK_ROW][ch];
+        bool warp_ok = !simple && nrows_ch >= 4 && nrows_ch <= 32 && (I[I_CHUNK_SLOT][ch + 1] - I[I_CHUNK_SLOT][ch]) <= 32;
+        for (int r = I[I_CHUNK_ROW][ch]; warp_ok && r < I[I_CHUNK_ROW][ch + 1]; ++r)
+          if (I[I_ROW_NRES][r] > 2 || I[I_ROW_CELL][r + 1] - I[I_ROW_CELL][r] - 1 > 4) warp_ok = false;
+        I[warp_ok ? I_TCHUNK_W : I_TCHUNK_T].push_back(ch);
+      }
       if (simple)
         for (int r = I[I_CHUNK_ROW][ch]; r < I[I_CHUNK_ROW][ch + 1]; ++r)
           if (I[I_ROW_CELL][r + 1] - I[I_ROW_CELL][r] > 1) {
@@ -747,6 +756,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.n_unit = g->n_unit;
   d.n_efac = n_efac;
   d.n_tchunks = (int)I[I_TCHUNK].size();
+  d.n_tchunks_t = (int)I[I_TCHUNK_T].size();
+  d.n_tchunks_w = (int)I[I_TCHUNK_W].size();
   d.n_wchunks = (int)I[I_WCHUNK].size();
   d.n_scells = (int)(I[I_SCELL].size() / 8);
   d.n_sterms = (int)I[I_STERM].size();
