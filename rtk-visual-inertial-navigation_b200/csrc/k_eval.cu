@@ -417,10 +417,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
         double g[9], nrm[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) g[k] = nrm[k] = 0.0;
+        // the index triple of the next entry is fetched while the current entry's values are in flight
+        int nres_n = 0, val_n = 0, res_n = 0;
+        if (e0 < e1) {
+          nres_n = csc_nres[e0];
+          val_n = csc_val[e0];
+          res_n = csc_res[e0];
+        }
         for (int e = e0; e < e1; ++e) {
-          const int nres = csc_nres[e];
-          const double* jv = J + csc_val[e] + k0;
-          const double* rv = R + csc_res[e];
+          const int nres = nres_n;
+          const double* jv = J + val_n + k0;
+          const double* rv = R + res_n;
+          if (e + 1 < e1) {
+            nres_n = csc_nres[e + 1];
+            val_n = csc_val[e + 1];
+            res_n = csc_res[e + 1];
+          }
           for (int rr = 0; rr < nres; ++rr) {
             const double r = rv[rr];
 #pragma unroll
