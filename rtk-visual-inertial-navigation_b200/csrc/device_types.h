@@ -63,6 +63,9 @@ enum IArr {
                     // (phase 1a of k_schur); same stage records as I_WSTREAM with header flag bit 1 set:
                     // w0 = output offset (W_EFAC for the [E'E | E'b] cell, W_EBUF for E'F), w1 = W_EBUF offset of E'b
   I_ESTREAM_PTR,    // [SCHUR_WARPS + 1]
+  I_CHOL_MASK,      // [2 * ceil(n_f / 32)] per 32-row panel of the reduced system: 64-bit mask (lo, hi) of the 16-column
+                    //               groups that can be non-zero in the panel's rows of U (symbolic block fill-in of the
+                    //               right-looking Cholesky); k_chol skips the tiles of all-zero groups
   I_TCHUNK_T,       // [n_tchunks_t] the other small chunks: one THREAD each in phase 1a (I_TCHUNK = both lists, for k_backsub)
   I_WSTREAM,        // [n_wstream * 4] per-warp gather streams of the reduced system (phase 2 of k_schur): stages of
                     //                 1 + SCHUR_STAGE 16-byte records, see "gather stream" below

@@ -93,8 +93,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
   const long long t_begin = t_prev;
 #define CHOL_STAMP(i) do { if (dbg && tid == 0) { const long long t_ = clock64(); acc_t[i] += t_ - t_prev; t_prev = t_; } } while (0)
 
+  const int32_t* cmask = v.I(I_CHOL_MASK);
   for (int k0 = 0; k0 < nf; k0 += NB) {
     const int nb = min(NB, nf - k0);
+    // 16-column groups (absolute columns 16 g ..) that can be non-zero in this panel's rows: everything else is
+    // an exact zero that stays zero, so its TRSM columns, in-panel tiles and trailing-update tiles are skipped
+    unsigned long long pmask = ~0ull;
+    if (NB == 32 && nb == NB) pmask = (unsigned long long)(unsigned)cmask[2 * (k0 >> 5)] | ((unsigned long long)(unsigned)cmask[2 * (k0 >> 5) + 1] << 32);
+    auto live16 = [&](int abs_col) { return (pmask >> (abs_col >> 4)) & 1ull; };
     const int Wm = nf - k0;              // matrix columns of the panel (panel col j = global col k0 + j)
     // panel column of the rhs: right after the matrix columns, except in a final partial panel,
     // where the identity padding of rows nb..NB-1 occupies columns nb..NB-1 and the rhs moves to NB
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
       {
         const double* U = P + (size_t)r0 * pw + r0;
         for (int j = r0 + 8 + tid; j < Wp; j += kThreads) {
+          if (j >= NB && j < Wm && !live16(k0 + j)) continue;  // structurally zero column of the panel
           double* col = P + (size_t)r0 * pw + j;
           double x[8];
 #pragma unroll
@@ -208,6 +215,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
           const int len = ntj - s8;
           while (idx < len) {
             const int s0 = s8 * 8, j0 = (s8 + idx) * 8;
+            if (j0 >= NB && j0 + 8 <= Wm && !live16(k0 + j0)) {
+              idx += kWarps;
+              continue;
+            }
             double2* cp = reinterpret_cast<double2*>(P + (size_t)(s0 + lb) * pw + j0 + 2 * la);
             double2 c = *cp;
 #pragma unroll
@@ -270,7 +281,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
           }
         }
       };
-      advance(ti, idx);
+      // a tile (ti, tj) only changes when both of its column groups are live in the panel
+      auto tile_live = [&](int ti_, int tj_) {
+        const int ci = t0 + 16 * ti_, cj = t0 + 32 * tj_;
+        return live16(ci) && (live16(cj) || live16(cj + 16));
+      };
+      auto next_live = [&](int& ti_, int& idx_) {
+        for (;;) {
+          advance(ti_, idx_);
+          if (ti_ >= TI || tile_live(ti_, first_tj(ti_) + idx_)) return;
+          idx_ += kWarps;
+        }
+      };
+      next_live(ti, idx);
       double cn[2][4][2];
       if (ti < TI) load_tile(ti, first_tj(ti) + idx, cn);
       while (ti < TI) {
@@ -284,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
             acc[mi][ni][1] = cn[mi][ni][1];
           }
         int nti = ti, nidx = idx + kWarps;
-        advance(nti, nidx);
+        next_live(nti, nidx);
         if (nti < TI) load_tile(nti, first_tj(nti) + nidx, cn);
         const double* pa = P + NB + 16 * ti + lb;
         const double* pb = P + NB + 32 * tj + lb;

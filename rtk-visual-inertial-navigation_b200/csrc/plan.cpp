@@ -541,6 +541,33 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);  // cell directory (statistics / read-backs); the kernel reads the streams
     }
     deal_streams(jobs, I_WSTREAM, I_WSTREAM_PTR);
+    // ---- symbolic fill-in of the blocked Cholesky at the granularity k_chol works at: 32-row panels, 16-column
+    // groups.  A[gi][gj] = "S or U can be non-zero somewhere in rows of group gi, columns of group gj"; eliminating
+    // a panel couples all column groups present in its rows.  The rhs (column n_f) is dense.
+    {
+      const int ng = (n_f + 1 + 15) / 16, n_panels = (n_f + 31) / 32;
+      if (ng <= 64) {
+        std::vector<uint64_t> A(ng, 0);
+        const int grhs = n_f / 16;
+        for (size_t ci = 0; ci < order.size(); ++ci) {
+          const int p = order[ci].first.first, q = order[ci].first.second;
+          const int rp = fpos(p), cq = fpos(q);
+          for (int gi = rp / 16; gi <= (rp + col_size[p] - 1) / 16; ++gi)
+            for (int gj = cq / 16; gj <= (cq + col_size[q] - 1) / 16; ++gj) A[gi] |= 1ull << gj;
+        }
+        for (int g = 0; g < ng; ++g) A[g] |= (1ull << g) | (1ull << grhs);
+        for (int k = 0; k < n_panels; ++k) {
+          const int g0 = 2 * k, g1 = std::min(ng - 1, 2 * k + 1);
+          uint64_t m = (A[g0] | A[g1] | (1ull << g0) | (1ull << g1)) & ~((1ull << g0) - 1);
+          I[I_CHOL_MASK].push_back((int32_t)(uint32_t)(m & 0xffffffffu));
+          I[I_CHOL_MASK].push_back((int32_t)(uint32_t)(m >> 32));
+          for (int gi = g1 + 1; gi < ng; ++gi)
+            if (m & (1ull << gi)) A[gi] |= m & ~((1ull << gi) - 1);
+        }
+      } else {
+        for (int k = 0; k < 2 * n_panels; ++k) I[I_CHOL_MASK].push_back(-1);
+      }
+    }
   }
   // ---- raw products of the larger e-blocks (4..16 tangent dims: the speed-bias blocks), gathered
   // by the same tensor-core stream code as the reduced system (phase 1a): per chunk one "diagonal" cell
