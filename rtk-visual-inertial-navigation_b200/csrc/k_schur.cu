@@ -7,12 +7,11 @@
 // mutexes, :552):
 //   phase 1, per chunk c (rows sharing e-block e):   L L' = D_e^2 + sum E'E      (chunk factor)
 //            W_f = L^-1 sum E'F_f  for every f-block of the chunk,  w_g = L^-1 sum E'b
-//   phase 2, one warp per touched block cell (p,q) of S, one lane per element: gather
-//            S_pq = [p==q] D_p^2 + sum_rows F_p'F_q - sum_chunks W_p'W_q ,
-//            rhs_p = sum_rows F_p'b - sum_chunks W_p'w_g   (extra column of the diagonal cells)
-//            from host-built term lists (plan.cpp) and store each element of S exactly once.
-//            All lanes of a warp read the same two small blocks, so every load is a broadcast
-//            out of one or two cache lines.
+//   phase 2, gather: S_pq = [p==q] D_p^2 + sum_rows F_p'F_q - sum_chunks W_p'W_q ,
+//            rhs_p = sum_rows F_p'b - sum_chunks W_p'w_g   (extra column of the diagonal cells);
+//            the 8x8 output tiles of all touched block cells are dealt to the warps by the planner
+//            (plan.cpp, "gather streams"), every term is one FP64 tensor-core MMA and each element of S
+//            is stored exactly once.
 //   back-substitution: y_e = L^-T (w_g - sum_f W_f z_f).
 // (E'E + D^2)^-1 of the reference (InvertPSDMatrix, invert_psd_matrix.h:62-67: LLT-solve-identity)
 // is applied in factored form: buffer' inv buffer = (L^-1 buffer)'(L^-1 buffer).
@@ -24,29 +23,11 @@ namespace {
 
 constexpr int kThreads = 256;            // k_backsub
 constexpr int kWarps = kThreads / 32;
-// k_schur runs one large CTA per window: the same number of warps per SM, but far fewer windows in
-// flight at a time, so the windows being worked on (JW + S, ~1.7 MB each) stay inside the 126 MB L2
-// k_schur: a thread-block CLUSTER per window.  The per-window working set (JW + S + index tables,
-// ~2 MB) is far larger than what one SM's worth of the 126 MB L2 can keep while hundreds of
-// windows are in flight, and the phases are latency bound; eight CTAs on eight SMs work through one
-// window eight times faster, so only a few dozen windows are in flight and their data stays in L2
-// between the phases.
+// k_schur: one CTA of SCHUR_WARPS warps per window (the gather streams are dealt to exactly these warps).
+// A thread-block cluster per window (8 CTAs, barrier.cluster between the phases) was measured and
+// dropped: the barrier imbalance cost more than the parallelism gained.
 constexpr int kSchurThreads = 256;
 constexpr int kSchurWarps = kSchurThreads / 32;
-constexpr int kCluster = 1;
-constexpr int kClusterThreads = kCluster * kSchurThreads;
-constexpr int kClusterWarps = kCluster * kSchurWarps;
-
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// barrier over all threads of the cluster; release/acquire at cluster scope orders the global
-// writes of one phase before the reads of the next
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 // D(8x8) += A(8x4, row) * B(4x8, col); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
 // D[lane>>2][2*(lane&3) + {0,1}]
@@ -682,17 +663,16 @@ __device__ __forceinline__ void chunk_dispatch(const Win& v, int chunk, const do
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads, SWGN_SCHUR_CTAS) k_schur(DeviceBatch b, int only_window) {
+__global__ void __launch_bounds__(kSchurThreads, SWGN_SCHUR_CTAS) k_schur(DeviceBatch b, int only_window) {
   __shared__ WinDesc sd;
   extern __shared__ __align__(16) double dyn[];  // phase 1: kSchurWarps * max_wbuf doubles; phase 2: the gather rings
-  const int w = only_window >= 0 ? only_window : blockIdx.x / kCluster;
+  const int w = only_window >= 0 ? only_window : blockIdx.x;
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
   const Win v = load_window(b, w, &sd);
   const WinDesc& d = sd;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int crank = (int)cluster_ctarank();
-  const int gtid = crank * kSchurThreads + tid, gwid = crank * kSchurWarps + wid;  // within the cluster
+  const int gtid = tid, gwid = wid;
   const double* lmd = v.W(W_LMD);
   double* S = v.W(W_S);
   const int nf = d.n_f, ld = d.ld;
@@ -701,13 +681,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   SWGN_STAMP(0);
   // start the DRAM -> L2 transfer of everything this CTA will read: Jacobian + residuals, the
   // index tables of the window (contiguous in ipool), the LM diagonal
-  prefetch_range(v.W(W_JAC), sizeof(double) * (size_t)d.n_jac, gtid, kClusterThreads);
-  prefetch_range(v.W(W_RES), sizeof(double) * (size_t)d.n_res, gtid, kClusterThreads);
-  prefetch_range(v.I(I_ROW_RES), sizeof(int32_t) * (size_t)(d.ioff[I_PROJ] - d.ioff[I_ROW_RES]), gtid, kClusterThreads);
-  prefetch_range(lmd, sizeof(double) * (size_t)d.n_t, gtid, kClusterThreads);
+  prefetch_range(v.W(W_JAC), sizeof(double) * (size_t)d.n_jac, gtid, kSchurThreads);
+  prefetch_range(v.W(W_RES), sizeof(double) * (size_t)d.n_res, gtid, kSchurThreads);
+  prefetch_range(v.I(I_ROW_RES), sizeof(int32_t) * (size_t)(d.ioff[I_PROJ] - d.ioff[I_ROW_RES]), gtid, kSchurThreads);
+  prefetch_range(lmd, sizeof(double) * (size_t)d.n_t, gtid, kSchurThreads);
 
   // phase 0: clear the upper triangle and the rhs column (cells never touched must read as 0)
-  for (int i = gwid; i < nf; i += kClusterWarps) {
+  for (int i = gwid; i < nf; i += kSchurWarps) {
     double* row = S + (size_t)i * ld;
     for (int j = i + lane; j <= nf; j += 32) row[j] = 0.0;
   }
@@ -716,7 +696,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   // on the tensor pipe, the raw products E'[E | b | F] of the larger e-blocks (one warp per e-cell)
   {
     const int32_t* tcw = v.I(I_TCHUNK_W);
-    for (int k = gwid; k < d.n_tchunks_w; k += kClusterWarps) {
+    for (int k = gwid; k < d.n_tchunks_w; k += kSchurWarps) {
       const int chunk = tcw[k];
       const int es = v.I(I_COL_SIZE)[v.I(I_CHUNK_ECOL)[chunk]];
       if (es == 1) chunk_small_warp<1>(v, chunk, lmd);
@@ -724,7 +704,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
       else chunk_small_warp<2>(v, chunk, lmd);
     }
     const int32_t* tch = v.I(I_TCHUNK_T);
-    for (int k = gtid; k < d.n_tchunks_t; k += kClusterThreads) chunk_dispatch(v, tch[k], lmd);
+    for (int k = gtid; k < d.n_tchunks_t; k += kSchurThreads) chunk_dispatch(v, tch[k], lmd);
     const int32_t* eptr = v.I(I_ESTREAM_PTR);
     const int4* gs = reinterpret_cast<const int4*>(v.I(I_ESTREAM)) + (size_t)eptr[wid] * kStageRecs;
     const double* JWc = v.W(W_JAC);
@@ -733,7 +713,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
     gather_stream<true>(JWc, gs, eptr[wid + 1] - eptr[wid], rings[wid], lane, v.W(W_EFAC), v.W(W_EBUF), 0, 0, nullptr);
   }
   SWGN_STAMP(2);
-  cluster_sync();
+  __syncthreads();
   SWGN_STAMP(3);
   // phase 1b: factor + forward substitution of the larger e-blocks (one warp per chunk, shared-memory
   // scratch), and the W blocks of the simple chunks, one thread per row (consecutive threads read
@@ -741,11 +721,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   {
     const int32_t* wch = v.I(I_WCHUNK);
     double* sm = dyn + (size_t)wid * b.max_wbuf;
-    for (int k = gwid; k < d.n_wchunks; k += kClusterWarps) chunk_warp(v, wch[k], lmd, sm);
+    for (int k = gwid; k < d.n_wchunks; k += kSchurWarps) chunk_warp(v, wch[k], lmd, sm);
   }
   {
     const int4* srow = reinterpret_cast<const int4*>(v.I(I_SROW));
-    for (int k = gtid; k < d.n_srows; k += kClusterThreads) {
+    for (int k = gtid; k < d.n_srows; k += kSchurThreads) {
       const int4 r0 = srow[2 * k], r1 = srow[2 * k + 1];
       const int es = (r0.y >> 8) & 0xff;
       if (es == 3) row_w<3>(v, r0, r1);
@@ -753,7 +733,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
       else row_w<2>(v, r0, r1);
     }
   }
-  cluster_sync();
+  __syncthreads();
   SWGN_STAMP(4);
   // phase 2: one warp per block cell.  S_pq = sum_t (+/-) A_t' B_t is a skinny GEMM whose K
   // dimension is the stack of the gathered blocks; every term feeds one FP64 tensor-core MMA
@@ -773,7 +753,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
   }
   SWGN_STAMP(5);
   if (dbg) {
-    cluster_sync();
+    __syncthreads();
     SWGN_STAMP(6);
     if (gtid == 0) {
       unsigned smid;
@@ -782,9 +762,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSchurThreads
     }
   }
   if (b.keep_copy) {
-    cluster_sync();
+    __syncthreads();
     double* SC = v.W(W_SCOPY);
-    for (int k = gtid; k < nf * ld; k += kClusterThreads) SC[k] = S[k];
+    for (int k = gtid; k < nf * ld; k += kSchurThreads) SC[k] = S[k];
   }
   if (gtid == 0) {
     st->num_linear_solves += 1;
@@ -926,7 +906,7 @@ static size_t schur_dyn_bytes(const DeviceBatch& b) {
 void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
   const size_t dyn = schur_dyn_bytes(b);
-  k_schur<<<grid * kCluster, kSchurThreads, dyn, s>>>(b, only_window);
+  k_schur<<<grid, kSchurThreads, dyn, s>>>(b, only_window);
 }
 void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
@@ -935,7 +915,7 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
 
 cudaError_t configure_schur(const DeviceBatch& b) {
   static size_t granted[64] = {0};
-  static_assert(kCluster == 1 && kSchurWarps == SCHUR_WARPS, "the gather streams are dealt to the warps of one CTA");
+  static_assert(kSchurWarps == SCHUR_WARPS, "the gather streams are dealt to the warps of one CTA");
   const size_t dyn = schur_dyn_bytes(b);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;
   int dev = 0;
