@@ -564,7 +564,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
 
 void launch_eval(const DeviceBatch& b, int mode, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
-  const size_t dyn = sizeof(double) * (size_t)(b.max_prior_n > 0 ? b.max_prior_n : 1);
+  // two spare doubles: the compiler reads the prior's dx vector with 16-byte shared loads
+  const size_t dyn = sizeof(double) * (((size_t)(b.max_prior_n > 0 ? b.max_prior_n : 1) + 3) & ~(size_t)1);
   launch_chain(b, mode, only_window, s);
   k_eval<<<grid, kThreads, dyn, s>>>(b, mode, only_window);
 }
