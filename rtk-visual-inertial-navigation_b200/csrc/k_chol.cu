@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_wi
             if (j >= q) t[q] -= c * t[p];
           }
         }
+        __syncwarp();  // lanes 8..31 read the same tile above (duplicates of columns 0..7)
         if (lane < 8) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
