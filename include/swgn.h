@@ -254,6 +254,11 @@ void swgn_batch_destroy(swgn_batch* b);
    tensor-core MMAs of one Schur gather pass.  Returns the
    same status codes swgn_batch_create would (SWGN_ERR_ORDERING, ...). */
 swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32_t* info16);
+/* Host-only: the planner's symbolic block fill-in of the reduced system's Cholesky factorisation -- per
+   32-row panel a 64-bit mask of the 16-column groups that can be non-zero in the panel's rows of U (the
+   device factorisation skips everything else).  n_panels may be queried with masks NULL. */
+swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, int32_t* n_panels,
+                                 uint64_t* masks);
 int32_t swgn_batch_size(const swgn_batch* b);
 
 /* Re-upload initial states only (structure unchanged): state_w has graphs[w]->n_state doubles. */

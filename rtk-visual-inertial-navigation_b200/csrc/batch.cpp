@@ -404,6 +404,21 @@ swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32
   return SWGN_OK;
 }
 
+// Host-only: the symbolic fill-in masks k_chol uses (one 64-bit mask of live 16-column groups per 32-row
+// panel of the reduced system); n_panels may be queried with masks NULL.
+swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, int32_t* n_panels, uint64_t* masks) {
+  if (!g || !n_panels) return fail(SWGN_ERR_INVALID, "bad arguments");
+  WindowPlan p;
+  std::string err;
+  swgn_status st = build_plan(g, n_parameter_head, &p, &err);
+  if (st != SWGN_OK) return fail(st, err);
+  const std::vector<int32_t>& m = p.iarr[I_CHOL_MASK];
+  *n_panels = (int32_t)(m.size() / 2);
+  if (masks)
+    for (size_t k = 0; k < m.size() / 2; ++k) masks[k] = (uint64_t)(uint32_t)m[2 * k] | ((uint64_t)(uint32_t)m[2 * k + 1] << 32);
+  return SWGN_OK;
+}
+
 int32_t swgn_batch_size(const swgn_batch* b) { return b ? b->n : 0; }
 
 swgn_status swgn_batch_set_state(swgn_batch* b, int32_t w, const double* state) {

@@ -240,6 +240,19 @@ def plan_probe(graph_p, n_parameter_head=0):
     return st, d
 
 
+def plan_chol_masks(graph_p, n_parameter_head=0):
+    """Host-only: symbolic fill-in masks of the reduced system (one uint64 per 32-row panel)."""
+    L = lib()
+    L.swgn_plan_chol_masks.argtypes = [P(Graph), i32, P(i32), P(C.c_uint64)]
+    n = i32()
+    st = L.swgn_plan_chol_masks(graph_p, n_parameter_head, C.byref(n), None)
+    if st != 0:
+        raise RuntimeError("swgn_plan_chol_masks failed: %s" % L.swgn_last_error().decode())
+    m = np.zeros(max(n.value, 1), np.uint64)
+    L.swgn_plan_chol_masks(graph_p, n_parameter_head, C.byref(n), m.ctypes.data_as(P(C.c_uint64)))
+    return m[:n.value]
+
+
 def default_options():
     o = Options()
     lib().swgn_default_options(C.byref(o))

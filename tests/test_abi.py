@@ -80,3 +80,31 @@ def test_create_fails_loudly_without_a_device():
     w = swgn.SynthWindow(1, 0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         swgn.Batch([w.graph_p], w.options())
+
+
+@pytest.mark.parametrize("which,wid,kw", [(1, 0, {}), (2, 0, {}), (2, 5, {}), (3, 0, {}), (4, 1, {}),
+                                           (2, 1, dict(n_keyframes=40, n_landmarks=100, n_gnss_epochs=20))])
+def test_symbolic_cholesky_masks_cover_the_numeric_factor(which, wid, kw):
+    """k_chol skips the tiles the planner's symbolic fill-in marks as zero (32-row panels x 16-column groups).
+    Host-only check that the masks are conservative: every non-zero of the reduced system AND of its
+    Cholesky factor U (computed densely from the oracle's S) lies in a live group of its panel."""
+    w = swgn.SynthWindow(which, wid, **kw)
+    opt = w.options()
+    masks = swgn.plan_chol_masks(w.graph_p, opt.n_parameter_head)
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, x, S, rhs = o.linear_solve(np.full(o.n_cols, 1e-3))
+    assert st == 0
+    n = o.n_f
+    assert len(masks) == (n + 31) // 32
+    Sf = np.triu(S) + np.triu(S, 1).T
+    U = np.linalg.cholesky(Sf).T
+    for name, M in (("S", np.triu(S)), ("U", U)):
+        for k in range(len(masks)):
+            rows = M[32 * k:min(n, 32 * k + 32)]
+            cols = np.nonzero(np.abs(rows).sum(axis=0) > 0)[0]
+            groups = set(int(c) // 16 for c in cols)
+            live = set(g for g in range(64) if (int(masks[k]) >> g) & 1)
+            assert groups <= live, (name, k, sorted(groups - live))
+    # and the masks do skip something on the BASELINE window (otherwise the feature is dead weight)
+    if which == 2 and not kw:
+        assert sum(bin(int(m)).count("1") for m in masks) < sum((n + 1 + 15) // 16 - 2 * k for k in range(len(masks)))
