@@ -259,6 +259,10 @@ swgn_status swgn_plan_probe(const swgn_graph* g, int32_t n_parameter_head, int32
    device factorisation skips everything else).  n_panels may be queried with masks NULL. */
 swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, int32_t* n_panels,
                                  uint64_t* masks);
+/* Host-only: decode the planner's per-warp gather streams of one window and verify their invariants (operand
+   and store ranges, one end flag per tile); out[0..7] = stages, live terms, padding terms and tiles of the
+   reduced-system streams, min / max stages per warp, stages and live terms of the e-cell streams. */
+swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head, int64_t* out8);
 int32_t swgn_batch_size(const swgn_batch* b);
 
 /* Re-upload initial states only (structure unchanged): state_w has graphs[w]->n_state doubles. */

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -416,6 +417,74 @@ swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, 
   *n_panels = (int32_t)(m.size() / 2);
   if (masks)
     for (size_t k = 0; k < m.size() / 2; ++k) masks[k] = (uint64_t)(uint32_t)m[2 * k] | ((uint64_t)(uint32_t)m[2 * k + 1] << 32);
+  return SWGN_OK;
+}
+
+// Host-only: decode the per-warp gather streams of one window and check their invariants (every operand
+// offset inside the window's J | EBUF | residual range, every store inside S / W_EFAC / W_EBUF, one `end` per
+// tile).  out[0..7] = stages, live terms, padding terms, tiles (end flags) of the reduced-system streams, min and
+// max stages per warp, stages and live terms of the e-cell streams.
+swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head, int64_t* out) {
+  if (!g || !out) return fail(SWGN_ERR_INVALID, "bad arguments");
+  WindowPlan p;
+  std::string err;
+  swgn_status st = build_plan(g, n_parameter_head, &p, &err);
+  if (st != SWGN_OK) return fail(st, err);
+  const WinDesc& d = p.d;
+  const int64_t jw = p.wsize[W_JAC] + p.wsize[W_EBUF] + p.wsize[W_RES];
+  std::memset(out, 0, sizeof(int64_t) * 8);
+  out[4] = INT64_MAX;
+  for (int pass = 0; pass < 2; ++pass) {
+    const std::vector<int32_t>& ws = p.iarr[pass == 0 ? I_WSTREAM : I_ESTREAM];
+    const std::vector<int32_t>& ptr = p.iarr[pass == 0 ? I_WSTREAM_PTR : I_ESTREAM_PTR];
+    if ((int)ptr.size() != SCHUR_WARPS + 1 || ws.size() % (4 * (SCHUR_STAGE + 1)) != 0 ||
+        (size_t)ptr.back() * 4 * (SCHUR_STAGE + 1) != ws.size())
+      return fail(SWGN_ERR_INVALID, "stream table sizes are inconsistent");
+    for (int wv = 0; wv < SCHUR_WARPS; ++wv) {
+      const int64_t n_st = ptr[wv + 1] - ptr[wv];
+      if (n_st < 0) return fail(SWGN_ERR_INVALID, "stream pointers are not monotone");
+      if (pass == 0) {
+        out[4] = std::min(out[4], n_st);
+        out[5] = std::max(out[5], n_st);
+      }
+      bool open = false;
+      int cur_meta = -1;
+      for (int64_t s_ = ptr[wv]; s_ < ptr[wv + 1]; ++s_) {
+        const int32_t* h = ws.data() + (size_t)s_ * 4 * (SCHUR_STAGE + 1);
+        const int meta = h[3], ps = meta & 63, qs = (meta >> 6) & 63, ti = ((meta >> 12) & 7) * 8, tj = ((meta >> 15) & 7) * 8;
+        const int diag = (meta >> 18) & 1, ecell = (h[2] >> 1) & 1;
+        if (ecell != pass || ps < 1 || qs < 1 || ti >= ps || tj >= qs + diag) return fail(SWGN_ERR_INVALID, "bad stage header");
+        if (open && meta != cur_meta) return fail(SWGN_ERR_INVALID, "a tile changed before its end flag");
+        cur_meta = meta;
+        open = true;
+        out[pass == 0 ? 0 : 6] += 1;
+        for (int e = 0; e < SCHUR_STAGE; ++e) {
+          const int32_t* t = h + 4 * (1 + e);
+          if (t[0] < 0) {
+            if (pass == 0) out[2] += 1;
+            continue;
+          }
+          const int rows = ((t[0] >> 28) & 3) + 1;
+          const int64_t a = t[0] & 0x0fffffff, bb = t[1], b2 = t[2];
+          if (a + (int64_t)rows * ps > jw || bb + (int64_t)rows * qs > jw || (diag && b2 + rows > jw)) return fail(SWGN_ERR_INVALID, "operand outside the window");
+          out[pass == 0 ? 1 : 7] += 1;
+        }
+        if (h[2] & 1) {
+          open = false;
+          if (pass == 0) {
+            out[3] += 1;
+            const int64_t last = (int64_t)h[0] + (int64_t)(std::min(ps, ti + 8) - 1) * d.ld + std::min(qs, tj + 8) - 1;
+            if (h[0] < 0 || last >= (int64_t)d.n_f * d.ld || h[1] < 0 || h[1] + ps > d.n_f) return fail(SWGN_ERR_INVALID, "tile store outside S");
+          } else {
+            const int64_t lim = diag ? p.wsize[W_EFAC] : p.wsize[W_EBUF];
+            if (h[0] < 0 || (int64_t)h[0] + (int64_t)ps * qs > lim) return fail(SWGN_ERR_INVALID, "e-cell store outside its buffer");
+          }
+        }
+      }
+      if (open) return fail(SWGN_ERR_INVALID, "a stream ends inside a tile");
+    }
+  }
+  if (out[4] == INT64_MAX) out[4] = 0;
   return SWGN_OK;
 }
 

@@ -108,3 +108,21 @@ def test_symbolic_cholesky_masks_cover_the_numeric_factor(which, wid, kw):
     # and the masks do skip something on the BASELINE window (otherwise the feature is dead weight)
     if which == 2 and not kw:
         assert sum(bin(int(m)).count("1") for m in masks) < sum((n + 1 + 15) // 16 - 2 * k for k in range(len(masks)))
+
+
+@pytest.mark.parametrize("which,wid", [(1, 0), (2, 0), (2, 3), (3, 0), (4, 0)])
+def test_gather_streams_are_well_formed(which, wid):
+    """Host-only: the per-warp gather streams k_schur consumes -- ranges of every operand and store, one end
+    flag per tile, the live terms are exactly the MMAs the planner counted, the warps are balanced."""
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    L = swgn.lib()
+    L.swgn_plan_stream_check.argtypes = [C.POINTER(swgn.Graph), C.c_int32, C.POINTER(C.c_int64)]
+    out = (C.c_int64 * 8)()
+    assert L.swgn_plan_stream_check(w.graph_p, opt.n_parameter_head, out) == 0, L.swgn_last_error()
+    stages, live, pad, tiles, smin, smax, e_stages, e_live = list(out)
+    st, d = swgn.plan_probe(w.graph_p, opt.n_parameter_head)
+    assert live + e_live == d["n_mma"]
+    assert stages * 8 == live + pad and tiles >= d["n_scells"]
+    assert smax - smin <= max(4, 0.05 * smax)      # longest-first dealing keeps the 8 warps level
+    assert pad < 0.45 * live                        # padding to full stages stays a minority
