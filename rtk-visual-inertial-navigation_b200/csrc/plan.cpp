@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <numeric>
 
@@ -147,18 +148,19 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   std::vector<Factor> fac;
   int kind_begin[NUM_KINDS + 1] = {0, 0, 0, 0, 0, 0, 0};
   auto add_factor = [&](int kind, int idx, const int32_t* blocks, int n, int nres) -> bool {
-    Factor f;
+    for (int k = 0; k < n; ++k)
+      if (blocks[k] < 0 || blocks[k] >= nb) return false;
+    fac.emplace_back();
+    Factor& f = fac.back();
     f.kind = kind;
     f.idx = idx;
     f.nres = nres;
-    for (int k = 0; k < n; ++k) {
-      if (blocks[k] < 0 || blocks[k] >= nb) return false;
-      f.blocks.push_back(blocks[k]);
-    }
+    f.blocks.assign(blocks, blocks + n);
     f.jac_off.assign(n, -1);
-    fac.push_back(f);
     return true;
   };
+  fac.reserve((size_t)std::max(0, g->n_proj) + std::max(0, g->n_imu) + std::max(0, g->n_gnss) + std::max(0, g->n_prior) +
+              std::max(0, g->n_unit) + std::max(0, g->n_chain));
   static const int kGnssArity[6] = {2, 3, 3, 2, 3, 2};
   static const int kGnssSizes[6][3] = {{7, 1, 0}, {7, 1, 1}, {7, 1, 1}, {7, 1, 0}, {9, 1, 7}, {1, 1, 0}};
   for (int i = 0; i < g->n_proj; ++i)
@@ -319,6 +321,17 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   int n_res = 0, n_jac = 0;
   int64_t schur_doubles = 0;
   I[I_ROW_CELL].push_back(0);
+  {
+    size_t n_cells_max = 0, n_res_max = 0;
+    for (int r = 0; r < n_rows; ++r) {
+      n_cells_max += fac[rows[r]].blocks.size();
+      n_res_max += (size_t)fac[rows[r]].nres;
+    }
+    for (int a : {I_ROW_RES, I_ROW_NRES, I_ROW_FACTOR, I_ROW_CELL}) I[a].reserve((size_t)n_rows + 1);
+    for (int a : {I_CELL_COL, I_CELL_VAL, I_CELL_SLOT, I_CELL_FIRST}) I[a].reserve(n_cells_max);
+    I[I_RS_ROW].reserve(n_res_max);
+  }
+  std::vector<std::pair<int, int>> cells;  // (col, param slot) of the current row
   for (int r = 0; r < n_rows; ++r) {
     Factor& f = fac[rows[r]];
     f.res_off = n_res;
@@ -326,7 +339,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     I[I_ROW_NRES].push_back(f.nres);
     I[I_ROW_FACTOR].push_back(program_index[rows[r]]);
     for (int k = 0; k < f.nres; ++k) I[I_RS_ROW].push_back(r);
-    std::vector<std::pair<int, int>> cells;  // (col, param slot)
+    cells.clear();
     for (size_t p = 0; p < f.blocks.size(); ++p) {
       int b = f.blocks[p];
       if (g->block_const[b]) continue;
@@ -358,12 +371,14 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     int r = 0;
     I[I_CHUNK_ROW].push_back(0);
     I[I_CHUNK_SLOT].push_back(0);
+    std::vector<int> fcols, slot_off;
+    std::vector<char> seen;
     while (r < n_rows) {
       int first_cell = I[I_ROW_CELL][r];
       int e = I[I_CELL_COL][first_cell];
       if (e >= n_ecols) break;
       int r1 = r;
-      std::vector<int> fcols;
+      fcols.clear();
       while (r1 < n_rows && I[I_CELL_COL][I[I_ROW_CELL][r1]] == e) {
         for (int c = I[I_ROW_CELL][r1] + 1; c < I[I_ROW_CELL][r1 + 1]; ++c) fcols.push_back(I[I_CELL_COL][c]);
         ++r1;
@@ -373,7 +388,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       const int es = col_size[e];
       if (es > MAX_WARP_E) return fail(SWGN_ERR_UNSUPPORTED, "eliminated parameter block larger than 16 tangent dimensions");
       const int chunk = (int)I[I_CHUNK_ECOL].size();
-      std::vector<int> slot_off(fcols.size());
+      slot_off.assign(fcols.size(), 0);
       int ncol = 0;
       for (size_t k = 0; k < fcols.size(); ++k) {
         slot_off[k] = n_ebuf;
@@ -386,7 +401,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       I[I_CHUNK_G].push_back(n_ebuf);
       n_ebuf += es;
       n_ebuf = (int)align2(n_ebuf);
-      std::vector<char> seen(fcols.size(), 0);
+      seen.assign(fcols.size(), 0);
       for (int rr = r; rr < r1; ++rr)
         for (int c = I[I_ROW_CELL][rr] + 1; c < I[I_ROW_CELL][rr + 1]; ++c) {
           int fc = I[I_CELL_COL][c];
@@ -425,41 +440,51 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   struct TileJob {
     uint32_t meta, flags;
     int32_t x, y;  // header words 0 / 1: S offset and first S row, or e-cell output offset and its g offset
-    std::vector<GTerm> terms;
+    const std::vector<GTerm>* terms;  // shared by all tiles of one cell (owned by term_store)
   };
+  std::deque<std::vector<GTerm>> term_store;  // stable addresses
   auto deal_streams = [&](const std::vector<TileJob>& jobs, int arr_stream, int arr_ptr) {
     std::vector<size_t> idx(jobs.size());
     std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return jobs[x].terms.size() > jobs[y].terms.size(); });
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return jobs[x].terms->size() > jobs[y].terms->size(); });
     std::vector<std::vector<size_t>> mine(SCHUR_WARPS);
     std::vector<size_t> load(SCHUR_WARPS, 0);
     for (size_t j : idx) {
       const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
       mine[wmin].push_back(j);
-      load[wmin] += (jobs[j].terms.size() + SCHUR_STAGE - 1) / SCHUR_STAGE + 1;
+      load[wmin] += (jobs[j].terms->size() + SCHUR_STAGE - 1) / SCHUR_STAGE + 1;
     }
     std::vector<int32_t>& WS = I[arr_stream];
+    constexpr size_t kStageInts = 4 * (SCHUR_STAGE + 1);
+    {
+      size_t n_st_total = 0;
+      for (const TileJob& jb : jobs) n_st_total += jb.terms->empty() ? 1 : (jb.terms->size() + SCHUR_STAGE - 1) / SCHUR_STAGE;
+      WS.resize(WS.size() + n_st_total * kStageInts);
+    }
+    int32_t* out = WS.data();
     for (int wv = 0; wv < SCHUR_WARPS; ++wv) {
-      I[arr_ptr].push_back((int32_t)(WS.size() / (4 * (SCHUR_STAGE + 1))));
+      I[arr_ptr].push_back((int32_t)((out - WS.data()) / kStageInts));
       for (size_t j : mine[wv]) {
         const TileJob& jb = jobs[j];
-        const size_t nt = jb.terms.size();
+        const GTerm* terms = jb.terms->data();
+        const size_t nt = jb.terms->size();
         const size_t n_st = nt == 0 ? 1 : (nt + SCHUR_STAGE - 1) / SCHUR_STAGE;
         for (size_t st = 0; st < n_st; ++st) {
-          WS.push_back(jb.x);
-          WS.push_back(jb.y);
-          WS.push_back((int32_t)(jb.flags | (st + 1 == n_st ? 1u : 0u)));
-          WS.push_back((int32_t)jb.meta);
-          for (size_t e = st * SCHUR_STAGE; e < (st + 1) * SCHUR_STAGE; ++e) {
+          out[0] = jb.x;
+          out[1] = jb.y;
+          out[2] = (int32_t)(jb.flags | (st + 1 == n_st ? 1u : 0u));
+          out[3] = (int32_t)jb.meta;
+          out += 4;
+          for (size_t e = st * SCHUR_STAGE; e < (st + 1) * SCHUR_STAGE; ++e, out += 4) {
             if (e < nt) {
-              const GTerm& t = jb.terms[e];
-              WS.push_back((int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30)));
-              WS.push_back((int32_t)t.b);
-              WS.push_back((int32_t)t.b2);
-              WS.push_back(0);
+              const GTerm& t = terms[e];
+              out[0] = (int32_t)(t.a | ((t.m - 1) << 28) | (t.sign << 30));
+              out[1] = (int32_t)t.b;
+              out[2] = (int32_t)t.b2;
+              out[3] = 0;
             } else {  // padding: bit 31 switches the loads off, the MMA adds zero
-              WS.push_back((int32_t)0x80000000u);
-              WS.push_back(0); WS.push_back(0); WS.push_back(0);
+              out[0] = (int32_t)0x80000000u;
+              out[1] = out[2] = out[3] = 0;
             }
           }
         }
@@ -478,8 +503,23 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   {
     auto fpos = [&](int c) { return col_pos[c] - n_e; };  // row/col of the f-block inside S
     typedef GTerm T;
-    std::map<std::pair<int, int>, std::vector<T>> cells;
-    for (int c = n_ecols; c < n_cols; ++c) cells[{c, c}];  // diagonal cells always exist (D^2)
+    // cell (p, q) -> term list, in a flat n_fb x n_fb table (lexicographic order = the order of a map keyed by
+    // (p, q)); two passes: count, then fill into exactly sized lists
+    const int n_fb = n_cols - n_ecols;
+    auto cid = [&](int p, int q) { return (size_t)(p - n_ecols) * n_fb + (size_t)(q - n_ecols); };
+    std::vector<uint32_t> cnt((size_t)n_fb * n_fb, 0);
+    for (int r = 0; r < n_rows; ++r)
+      for (int c1 = I[I_ROW_CELL][r]; c1 < I[I_ROW_CELL][r + 1]; ++c1) {
+        const int p = I[I_CELL_COL][c1];
+        if (p < n_ecols) continue;
+        for (int c2 = c1; c2 < I[I_ROW_CELL][r + 1]; ++c2) ++cnt[cid(p, I[I_CELL_COL][c2])];
+      }
+    for (int ch = 0; ch < n_chunks; ++ch)
+      for (int s1 = I[I_CHUNK_SLOT][ch]; s1 < I[I_CHUNK_SLOT][ch + 1]; ++s1)
+        for (int s2 = s1; s2 < I[I_CHUNK_SLOT][ch + 1]; ++s2) ++cnt[cid(I[I_SLOT_COL][s1], I[I_SLOT_COL][s2])];
+    std::vector<std::vector<T>> cells((size_t)n_fb * n_fb);
+    for (size_t k = 0; k < cells.size(); ++k)
+      if (cnt[k]) cells[k].reserve(cnt[k]);
     const uint32_t res_base = (uint32_t)(n_jac_al + n_ebuf_al);
     for (int r = 0; r < n_rows; ++r) {
       const int nres = I[I_ROW_NRES][r];
@@ -487,8 +527,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
         const int p = I[I_CELL_COL][c1];
         if (p < n_ecols) continue;
         for (int c2 = c1; c2 < I[I_ROW_CELL][r + 1]; ++c2)
-          cells[{p, I[I_CELL_COL][c2]}].push_back({(uint32_t)I[I_CELL_VAL][c1], (uint32_t)I[I_CELL_VAL][c2], (uint32_t)nres, 0u,
-                                                   res_base + (uint32_t)I[I_ROW_RES][r]});
+          cells[cid(p, I[I_CELL_COL][c2])].push_back({(uint32_t)I[I_CELL_VAL][c1], (uint32_t)I[I_CELL_VAL][c2], (uint32_t)nres, 0u,
+                                                      res_base + (uint32_t)I[I_ROW_RES][r]});
       }
     }
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -496,20 +536,27 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       for (int s1 = I[I_CHUNK_SLOT][ch]; s1 < I[I_CHUNK_SLOT][ch + 1]; ++s1) {
         const int p = I[I_SLOT_COL][s1];
         for (int s2 = s1; s2 < I[I_CHUNK_SLOT][ch + 1]; ++s2)
-          cells[{p, I[I_SLOT_COL][s2]}].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_SLOT_BUF][s2]), es, 1u,
-                                                   (uint32_t)(n_jac_al + I[I_CHUNK_G][ch])});
+          cells[cid(p, I[I_SLOT_COL][s2])].push_back({(uint32_t)(n_jac_al + I[I_SLOT_BUF][s1]), (uint32_t)(n_jac_al + I[I_SLOT_BUF][s2]), es, 1u,
+                                                      (uint32_t)(n_jac_al + I[I_CHUNK_G][ch])});
       }
     }
     // heaviest cells first: the warps pull cells round-robin, so the tail is made of light cells
-    std::vector<std::pair<std::pair<int, int>, const std::vector<T>*>> order;
-    for (auto& kv : cells) order.push_back({kv.first, &kv.second});
-    auto weight = [&](const std::pair<std::pair<int, int>, const std::vector<T>*>& x) {
-      size_t w = 0;
-      for (const T& t : *x.second) w += t.m;
-      const int outs = col_size[x.first.first] * (col_size[x.first.second] + (x.first.first == x.first.second ? 1 : 0));
-      return w * (size_t)((outs + 31) / 32) + 8;
+    struct OrderedCell {
+      std::pair<int, int> first;
+      const std::vector<T>* second;
+      size_t weight;
     };
-    std::stable_sort(order.begin(), order.end(), [&](const auto& x, const auto& y) { return weight(x) > weight(y); });
+    std::vector<OrderedCell> order;
+    for (int p = n_ecols; p < n_cols; ++p)
+      for (int q = n_ecols; q < n_cols; ++q) {
+        const std::vector<T>& ts = cells[cid(p, q)];
+        if (ts.empty() && p != q) continue;  // diagonal cells always exist (D^2)
+        size_t w = 0;
+        for (const T& t : ts) w += t.m;
+        const int outs = col_size[p] * (col_size[q] + (p == q ? 1 : 0));
+        order.push_back({{p, q}, &ts, w * (size_t)((outs + 31) / 32) + 8});
+      }
+    std::stable_sort(order.begin(), order.end(), [](const OrderedCell& x, const OrderedCell& y) { return x.weight > y.weight; });
     std::vector<TileJob> jobs;
     for (size_t ci = 0; ci < order.size(); ++ci) {
       const int p = order[ci].first.first, q = order[ci].first.second;
@@ -519,7 +566,13 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       // flat term stream: blocks with more than 4 rows are split into K slabs of <= 4 rows, and every
       // entry packs (offset, rows, sign) so that the device loop is one straight-line batch after another
       //   word0 = a | rows-1 << 28 | subtract << 30        word1 = b        [word2 = b2, word3 = 0]
-      std::vector<T> ts;
+      term_store.emplace_back();
+      std::vector<T>& ts = term_store.back();
+      {
+        size_t n_slabs = 0;
+        for (const T& t : *order[ci].second) n_slabs += (t.m + 3) / 4;
+        ts.reserve(n_slabs);
+      }
       for (const T& t : *order[ci].second)
         for (uint32_t e0 = 0; e0 < t.m; e0 += 4)
           ts.push_back({t.a + e0 * (uint32_t)ps, t.b + e0 * (uint32_t)qs, std::min(4u, t.m - e0), t.sign, t.b2 + e0});
@@ -534,8 +587,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
           jb.flags = 0;
           jb.x = fpos(p) * ld + fpos(q);
           jb.y = fpos(p);
-          jb.terms = ts;
-          jobs.push_back(std::move(jb));
+          jb.terms = &ts;
+          jobs.push_back(jb);
         }
       const int32_t rec[8] = {ps, qs, fpos(p) * ld + fpos(q), 0, (int32_t)ts.size(), diag ? 1 : 0, 0, 0};
       I[I_SCELL].insert(I[I_SCELL].end(), rec, rec + 8);  // cell directory (statistics / read-backs); the kernel reads the streams
@@ -578,7 +631,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     std::vector<TileJob> jobs;
     int n_ecells = 0;
     auto emit = [&](int ps, int qs, int out, bool diag, int gout, const std::vector<GTerm>& rows) {
-      std::vector<GTerm> ts;
+      term_store.emplace_back();
+      std::vector<GTerm>& ts = term_store.back();
       for (const GTerm& t : rows)
         for (uint32_t e0 = 0; e0 < t.m; e0 += 4)
           ts.push_back({t.a + e0 * (uint32_t)ps, t.b + e0 * (uint32_t)qs, std::min(4u, t.m - e0), 0u, t.b2 + e0});
@@ -591,8 +645,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
           jb.flags = 2;  // e-cell target
           jb.x = out;
           jb.y = gout;
-          jb.terms = ts;
-          jobs.push_back(std::move(jb));
+          jb.terms = &ts;
+          jobs.push_back(jb);
           P->n_mma += (int64_t)ts.size();
         }
     };
