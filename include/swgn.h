@@ -247,7 +247,8 @@ int32_t swgn_device_count(void);
    :360-393) and upload n_windows graphs.  Windows are independent. */
 swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows,
                               const swgn_graph* const* graphs, swgn_batch** out);
-void swgn_batch_destroy(swgn_batch* b);
+void swgn_batch_destroy(swgn_batch* b);   /* the batch's device / pinned slabs go to a process-wide cache (<= 4 GB device,
+                                             <= 1 GB pinned) that later creates draw from; larger slabs are freed */
 /* Host-only: run the preprocessing of one window without touching a device and report
    info[0..11] = n_cols, n_ecols, n_e, n_f, n_t, n_res, n_rows, n_chunks, n_jac, n_scells,
    n_sterms, n_srows; info[12..13] = algorithmic Schur bytes (low / high 32 bits); info[14] =

@@ -39,6 +39,63 @@ swgn_status fail(swgn_status st, const std::string& m) {
     if (e_ != cudaSuccess)                                                                        \
       return fail(SWGN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
+
+// ---- device / pinned slabs.  A batch takes ONE device allocation and ONE pinned allocation and carves its
+// arrays out of them; destroyed batches park their slabs in a small process-wide cache so that the
+// create-solve-destroy cycle of a per-frame host (one ceres::Solve per window, as the reference runs it) costs
+// no cudaMalloc / cudaFree / cudaMallocHost after the first frame.  Big slabs are returned to the driver.
+struct SlabCache {
+  struct Slab {
+    void* p;
+    size_t cap;
+    int device;
+  };
+  std::mutex mu;
+  std::vector<Slab> slabs[2];  // [0] device, [1] pinned host
+  size_t held[2] = {0, 0};
+  // per kind: largest slab worth keeping, most bytes held (device memory is plentiful, pinned host memory is not)
+  static constexpr size_t kMaxSlab[2] = {(size_t)2 << 30, (size_t)256 << 20}, kMaxHeld[2] = {(size_t)4 << 30, (size_t)1 << 30};
+  static constexpr size_t kMaxCount = 16, kHeadRoomBelow = (size_t)128 << 20;
+};
+SlabCache g_slabs;
+
+cudaError_t slab_alloc(int kind, int device, size_t bytes, void** out, size_t* cap) {
+  bytes = std::max<size_t>(bytes, 256);
+  {
+    std::lock_guard<std::mutex> lk(g_slabs.mu);
+    auto& v = g_slabs.slabs[kind];
+    int best = -1;
+    for (int i = 0; i < (int)v.size(); ++i)
+      if (v[i].device == device && v[i].cap >= bytes && v[i].cap <= 2 * bytes + ((size_t)1 << 20) && (best < 0 || v[i].cap < v[best].cap))
+        best = i;
+    if (best >= 0) {
+      *out = v[best].p;
+      *cap = v[best].cap;
+      g_slabs.held[kind] -= v[best].cap;
+      v.erase(v.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  // cacheable sizes get 25 % head room (64 KB granules): the next frame's window is rarely the same size, and
+  // pinning a fresh buffer costs ~0.1 s
+  if (bytes <= SlabCache::kHeadRoomBelow) bytes = (bytes + bytes / 4 + 65535) & ~(size_t)65535;
+  *cap = bytes;
+  return kind == 0 ? cudaMalloc(out, bytes) : cudaMallocHost(out, bytes);
+}
+void slab_free(int kind, int device, void* p, size_t cap) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_slabs.mu);
+    auto& v = g_slabs.slabs[kind];
+    if (cap <= SlabCache::kMaxSlab[kind] && g_slabs.held[kind] + cap <= SlabCache::kMaxHeld[kind] && v.size() < SlabCache::kMaxCount) {
+      v.push_back({p, cap, device});
+      g_slabs.held[kind] += cap;
+      return;
+    }
+  }
+  if (kind == 0) cudaFree(p);
+  else cudaFreeHost(p);
+}
 }  // namespace
 
 struct swgn_batch {
@@ -59,6 +116,9 @@ struct swgn_batch {
   int64_t* d_state_off = nullptr;
   double* h_stage = nullptr;      // pinned
   double* h_cpool = nullptr;      // pinned staging of the factor constants (update_inputs)
+  void* d_slab = nullptr;         // every d_* array above is carved out of this one allocation,
+  void* h_slab = nullptr;         // h_counters and h_stage out of this one (slab_alloc / slab_free)
+  size_t d_slab_cap = 0, h_slab_cap = 0;
   long long* d_debug = nullptr;   // SWGN_DEBUG_TIMELINE=1: per-window phase timestamps of k_schur
   size_t ipool_n = 0, cpool_n = 0, wpool_n = 0;
   DeviceBatch db;
@@ -105,17 +165,9 @@ void swgn_batch_destroy(swgn_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
-  cudaFree(b->d_desc);
-  cudaFree(b->d_ipool);
-  cudaFree(b->d_cpool);
-  cudaFree(b->d_wpool);
-  cudaFree(b->d_state);
-  cudaFree(b->d_counters);
-  cudaFree(b->d_stage);
-  cudaFree(b->d_state_off);
+  slab_free(0, b->device, b->d_slab, b->d_slab_cap);
+  slab_free(1, b->device, b->h_slab, b->h_slab_cap);
   cudaFree(b->d_debug);
-  if (b->h_counters) cudaFreeHost(b->h_counters);
-  if (b->h_stage) cudaFreeHost(b->h_stage);
   if (b->h_cpool) cudaFreeHost(b->h_cpool);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -221,16 +273,29 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
     if (e_ != cudaSuccess) return bail(e_, #call); \
   } while (0)
   CB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-  CB(cudaMalloc(&b->d_desc, sizeof(WinDesc) * n_windows));
-  CB(cudaMalloc(&b->d_ipool, sizeof(int32_t) * std::max<size_t>(io, 4)));
-  CB(cudaMalloc(&b->d_cpool, sizeof(double) * std::max<size_t>(co, 2)));
-  CB(cudaMalloc(&b->d_wpool, sizeof(double) * std::max<size_t>(wo, 2)));
-  CB(cudaMalloc(&b->d_state, sizeof(TRState) * n_windows));
-  CB(cudaMalloc(&b->d_counters, sizeof(int32_t) * 4));
-  CB(cudaMalloc(&b->d_stage, sizeof(double) * std::max<int64_t>(so, 2)));
-  CB(cudaMalloc(&b->d_state_off, sizeof(int64_t) * (n_windows + 1)));
-  CB(cudaMallocHost(&b->h_counters, sizeof(int32_t) * 4));
-  CB(cudaMallocHost(&b->h_stage, sizeof(double) * std::max<int64_t>(so, 2)));
+  {
+    // one device slab: [desc | ipool | cpool | wpool | state | counters | stage | state_off], 256-byte aligned parts
+    const size_t sz[8] = {sizeof(WinDesc) * (size_t)n_windows,      sizeof(int32_t) * std::max<size_t>(io, 4),
+                          sizeof(double) * std::max<size_t>(co, 2), sizeof(double) * std::max<size_t>(wo, 2),
+                          sizeof(TRState) * (size_t)n_windows,      sizeof(int32_t) * 4,
+                          sizeof(double) * (size_t)std::max<int64_t>(so, 2), sizeof(int64_t) * ((size_t)n_windows + 1)};
+    size_t off[9] = {0};
+    for (int k = 0; k < 8; ++k) off[k + 1] = al(off[k] + sz[k], 256);
+    CB(slab_alloc(0, b->device, off[8], &b->d_slab, &b->d_slab_cap));
+    char* base = static_cast<char*>(b->d_slab);
+    b->d_desc = reinterpret_cast<WinDesc*>(base + off[0]);
+    b->d_ipool = reinterpret_cast<int32_t*>(base + off[1]);
+    b->d_cpool = reinterpret_cast<double*>(base + off[2]);
+    b->d_wpool = reinterpret_cast<double*>(base + off[3]);
+    b->d_state = reinterpret_cast<TRState*>(base + off[4]);
+    b->d_counters = reinterpret_cast<int32_t*>(base + off[5]);
+    b->d_stage = reinterpret_cast<double*>(base + off[6]);
+    b->d_state_off = reinterpret_cast<int64_t*>(base + off[7]);
+    const size_t hs = sizeof(double) * (size_t)std::max<int64_t>(so, 2);
+    CB(slab_alloc(1, b->device, 256 + hs, &b->h_slab, &b->h_slab_cap));
+    b->h_counters = static_cast<int32_t*>(b->h_slab);
+    b->h_stage = reinterpret_cast<double*>(static_cast<char*>(b->h_slab) + 256);
+  }
   mark("alloc");
   CB(cudaMemsetAsync(b->d_wpool, 0, sizeof(double) * std::max<size_t>(wo, 2), b->stream));
   CB(cudaMemsetAsync(b->d_state, 0, sizeof(TRState) * n_windows, b->stream));
