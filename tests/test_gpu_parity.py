@@ -431,3 +431,28 @@ def test_full_size_batch_properties():
     tot, schur, nl, kl = b.timing()
     assert tot > 0 and schur > 0 and nl >= 8 and kl > nl
     b.close()
+
+
+def test_recycled_slabs_do_not_leak_state_between_batches():
+    """swgn_batch_destroy parks the batch's device / pinned slabs in a process-wide cache and later creates
+    reuse them (batch.cpp slab_alloc): a batch built on recycled memory must give bit-identical results to
+    the one built on fresh memory, whatever the previous tenant left behind (other window, other size,
+    export mode, chains)."""
+    a, c = swgn.SynthWindow(2, 3), swgn.SynthWindow(1, 1)
+    ch = swgn.SynthWindow(4, 0)
+
+    def run(w, **kw):
+        opt = w.options()
+        for k, v in kw.items():
+            setattr(opt, k, v)
+        b = swgn.Batch([w.graph_p], opt)
+        sm = b.solve()[0]
+        x = b.get_state(0, w.n_state).copy()
+        b.close()
+        return x, sm.final_cost, sm.num_iterations
+
+    first = run(a)
+    for other, kw in ((c, {"n_parameter_head": 0}), (ch, {}), (a, {"is_optimize": 0}), (c, {"n_parameter_head": 0})):
+        run(other, **kw)
+        again = run(a)
+        assert np.array_equal(again[0], first[0]) and again[1] == first[1] and again[2] == first[2]
