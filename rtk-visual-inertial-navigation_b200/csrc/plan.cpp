@@ -366,7 +366,6 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   //   wg = L^-1 E'b                    (W_EBUF, es)
   // so that S_pq -= Wp' Wq, rhs_p -= Wp' wg and y_e = L^-T (wg - sum_f Wf z_f).
   int n_efac = 0, n_ebuf = 0, max_wbuf = 0;
-  std::vector<std::vector<std::pair<int, int>>> col_slots(n_cols);  // f col -> (chunk, slot offset)
   {
     int r = 0;
     I[I_CHUNK_ROW].push_back(0);
@@ -394,7 +393,6 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
         slot_off[k] = n_ebuf;
         I[I_SLOT_COL].push_back(fcols[k]);
         I[I_SLOT_BUF].push_back(n_ebuf);
-        col_slots[fcols[k]].push_back({chunk, n_ebuf});
         n_ebuf += es * col_size[fcols[k]];
         ncol += col_size[fcols[k]];
       }
