@@ -265,6 +265,9 @@ swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, 
    reduced-system streams, min / max stages per warp, stages and live terms of the e-cell streams. */
 swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head, int64_t* out8);
 int32_t swgn_batch_size(const swgn_batch* b);
+/* Return the cached device / pinned slabs of destroyed batches to the driver (all devices); returns the bytes
+   released.  Never needed for correctness: the cache is bounded (see swgn_batch_destroy). */
+int64_t swgn_release_cached_memory(void);
 
 /* Re-upload initial states only (structure unchanged): state_w has graphs[w]->n_state doubles. */
 swgn_status swgn_batch_set_state(swgn_batch* b, int32_t window, const double* state);

@@ -160,6 +160,29 @@ int32_t swgn_device_count(void) {
   return n;
 }
 
+int64_t swgn_release_cached_memory(void) {
+  std::vector<SlabCache::Slab> out[2];
+  {
+    std::lock_guard<std::mutex> lk(g_slabs.mu);
+    for (int kind = 0; kind < 2; ++kind) {
+      out[kind].swap(g_slabs.slabs[kind]);
+      g_slabs.held[kind] = 0;
+    }
+  }
+  int64_t bytes = 0;
+  int prev = -1;
+  if (!out[0].empty() || !out[1].empty()) cudaGetDevice(&prev);
+  for (int kind = 0; kind < 2; ++kind)
+    for (const SlabCache::Slab& s : out[kind]) {
+      cudaSetDevice(s.device);
+      if (kind == 0) cudaFree(s.p);
+      else cudaFreeHost(s.p);
+      bytes += (int64_t)s.cap;
+    }
+  if (prev >= 0) cudaSetDevice(prev);
+  return bytes;
+}
+
 void swgn_batch_destroy(swgn_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);

@@ -198,6 +198,8 @@ def lib():
         L.swgn_batch_destroy.argtypes = [C.c_void_p]
         L.swgn_plan_probe.argtypes = [P(Graph), i32, P(i32)]
         L.swgn_batch_size.argtypes = [C.c_void_p]
+        L.swgn_release_cached_memory.restype = C.c_int64
+        L.swgn_release_cached_memory.argtypes = []
         L.swgn_batch_set_state.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_solve.argtypes = [C.c_void_p, P(Summary)]
         L.swgn_batch_update_inputs.argtypes = [C.c_void_p, P(P(Graph)), P(i64)]
@@ -251,6 +253,11 @@ def plan_chol_masks(graph_p, n_parameter_head=0):
     m = np.zeros(max(n.value, 1), np.uint64)
     L.swgn_plan_chol_masks(graph_p, n_parameter_head, C.byref(n), m.ctypes.data_as(P(C.c_uint64)))
     return m[:n.value]
+
+
+def release_cached_memory():
+    """Bytes of cached device / pinned slabs handed back to the driver (swgn_release_cached_memory)."""
+    return int(lib().swgn_release_cached_memory())
 
 
 def default_options():

@@ -28,6 +28,12 @@ def test_library_exports_every_declared_symbol():
     assert swgn.lib().swgn_version().decode().startswith("swgn")
 
 
+def test_release_cached_memory_is_callable_without_a_device():
+    """Nothing is cached before the first batch was destroyed: 0 bytes, no CUDA call, no error."""
+    if swgn.lib().swgn_device_count() == 0:
+        assert swgn.release_cached_memory() == 0
+
+
 def test_default_options_are_the_reference_settings():
     o = swgn.default_options()
     assert o.max_num_iterations == 8 and o.max_num_consecutive_invalid_steps == 5

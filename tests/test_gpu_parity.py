@@ -456,3 +456,8 @@ def test_recycled_slabs_do_not_leak_state_between_batches():
         run(other, **kw)
         again = run(a)
         assert np.array_equal(again[0], first[0]) and again[1] == first[1] and again[2] == first[2]
+    # the parked slabs can be handed back, and a batch built afterwards (fresh memory again) agrees as well
+    assert swgn.release_cached_memory() > 0
+    assert swgn.release_cached_memory() == 0
+    again = run(a)
+    assert np.array_equal(again[0], first[0]) and again[1] == first[1]
