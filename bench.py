@@ -276,7 +276,7 @@ def run_swgn(args, rank, local_rank, world):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_A if args.composition == "A" else WORKLOAD, "windows_per_gpu": W, "iterations_per_window": iters / (args.steps * W * world),
                    "n_f": int(sms[0].n_f), "n_e": int(sms[0].n_e), "n_residuals": int(sms[0].n_residuals),
-                   "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (2.4e-3 * W),
+                   "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (2.9e-3 * W),
                    "failed_windows": int(n_fail), "median_cost_reduction": float(np.median(final_costs / init_costs)),
                    "host_generate_s": round(t_gen, 2), "host_plan_upload_s": round(t_create, 2)},
         "roofline": {"kernel": "k_schur", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
