@@ -6,6 +6,7 @@
 
 #include "ceres/ceres.h"
 #include "ceres/schur_complement_solver.h"
+#include "ceres/small_blas.h"
 
 namespace {
 struct Unary : ceres::SizedCostFunction<1, 1> {
@@ -97,5 +98,122 @@ extern "C" int swgn_ceres_selftest() {
     EXPECT(s.termination_type == ceres::FAILURE && s.message.find("adapter") != std::string::npos);
   }
   EXPECT(ceres::internal::is_optimize == true && ceres::internal::parameter_head.empty());
+  return 0;
+}
+
+// ---- ceres/small_blas.h against the cases of the reference's own small_blas_test.cc (:74-330): A(i,j) = B(i,j) =
+// i + j + 1, C = ones of every size row_stride x col_stride from the product's size up to three times it, the
+// product placed at every admissible (start_row_c, start_col_c), kOperation = +1 / -1 / 0, sizes (5,3,7), (1,1,1),
+// (9,9,9), fixed and dynamic (-1 = Eigen::Dynamic) template arguments; the values are small integers, so the
+// comparison with the triple loop is exact.  Matrix-vector forms: small_blas_test.cc:332-end.
+namespace {
+template <int kRowA, int kColA, int kColB, bool kDynamic, bool kTranspose>
+int small_blas_case() {
+  // plain product: A is kRowA x kColA, B is kColA x kColB, C block kRowA x kColB
+  // transposed:    A is kRowA x kColA, B is kRowA x kColB, C block kColA x kColB (A' B)
+  const int rows_b = kTranspose ? kRowA : kColA;
+  const int rows_c = kTranspose ? kColA : kRowA;
+  std::vector<double> A(kRowA * kColA), B(rows_b * kColB);
+  for (int i = 0; i < kRowA; ++i)
+    for (int j = 0; j < kColA; ++j) A[i * kColA + j] = i + j + 1;
+  for (int i = 0; i < rows_b; ++i)
+    for (int j = 0; j < kColB; ++j) B[i * kColB + j] = i + j + 1;
+  std::vector<double> P(rows_c * kColB, 0.0);
+  for (int i = 0; i < rows_c; ++i)
+    for (int j = 0; j < kColB; ++j)
+      for (int k = 0; k < (kTranspose ? kRowA : kColA); ++k)
+        P[i * kColB + j] += (kTranspose ? A[k * kColA + i] : A[i * kColA + k]) * B[k * kColB + j];
+  constexpr int D = -1;
+  for (int rs = rows_c; rs < 3 * rows_c; ++rs)
+    for (int cs = kColB; cs < 3 * kColB; ++cs) {
+      std::vector<double> Cp(rs * cs, 1.0), Cm(rs * cs, 1.0), Ca(rs * cs, 1.0);
+      std::vector<double> Rp = Cp, Rm = Cm, Ra = Ca;
+      for (int r0 = 0; r0 + rows_c < rs; ++r0)
+        for (int c0 = 0; c0 + kColB < cs; ++c0) {
+          for (int i = 0; i < rows_c; ++i)
+            for (int j = 0; j < kColB; ++j) {
+              Rp[(r0 + i) * cs + c0 + j] += P[i * kColB + j];
+              Rm[(r0 + i) * cs + c0 + j] -= P[i * kColB + j];
+              Ra[(r0 + i) * cs + c0 + j] = P[i * kColB + j];
+            }
+          using namespace ceres::internal;
+          if (!kTranspose) {
+            if (kDynamic) {
+              MatrixMatrixMultiply<D, D, D, D, 1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cp.data(), r0, c0, rs, cs);
+              MatrixMatrixMultiply<D, D, D, D, -1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cm.data(), r0, c0, rs, cs);
+              MatrixMatrixMultiply<D, D, D, D, 0>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Ca.data(), r0, c0, rs, cs);
+            } else {
+              MatrixMatrixMultiply<kRowA, kColA, kColA, kColB, 1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cp.data(), r0, c0, rs, cs);
+              MatrixMatrixMultiply<kRowA, kColA, kColA, kColB, -1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cm.data(), r0, c0, rs, cs);
+              MatrixMatrixMultiply<kRowA, kColA, kColA, kColB, 0>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Ca.data(), r0, c0, rs, cs);
+            }
+          } else {
+            if (kDynamic) {
+              MatrixTransposeMatrixMultiply<D, D, D, D, 1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cp.data(), r0, c0, rs, cs);
+              MatrixTransposeMatrixMultiply<D, D, D, D, -1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cm.data(), r0, c0, rs, cs);
+              MatrixTransposeMatrixMultiply<D, D, D, D, 0>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Ca.data(), r0, c0, rs, cs);
+            } else {
+              MatrixTransposeMatrixMultiply<kRowA, kColA, kRowA, kColB, 1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cp.data(), r0, c0, rs, cs);
+              MatrixTransposeMatrixMultiply<kRowA, kColA, kRowA, kColB, -1>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Cm.data(), r0, c0, rs, cs);
+              MatrixTransposeMatrixMultiply<kRowA, kColA, kRowA, kColB, 0>(A.data(), kRowA, kColA, B.data(), rows_b, kColB, Ca.data(), r0, c0, rs, cs);
+            }
+          }
+          EXPECT(Cp == Rp);
+          EXPECT(Cm == Rm);
+          EXPECT(Ca == Ra);
+        }
+    }
+  return 0;
+}
+template <int kRowA, int kColA>
+int small_blas_vector_case() {
+  std::vector<double> A(kRowA * kColA), b(kColA), bt(kRowA);
+  for (int i = 0; i < kRowA; ++i)
+    for (int j = 0; j < kColA; ++j) A[i * kColA + j] = i + j + 1;
+  for (int j = 0; j < kColA; ++j) b[j] = 2 * j + 1;
+  for (int i = 0; i < kRowA; ++i) bt[i] = 3 * i + 2;
+  std::vector<double> Ab(kRowA, 0.0), Atb(kColA, 0.0);
+  for (int i = 0; i < kRowA; ++i)
+    for (int j = 0; j < kColA; ++j) {
+      Ab[i] += A[i * kColA + j] * b[j];
+      Atb[j] += A[i * kColA + j] * bt[i];
+    }
+  using namespace ceres::internal;
+  std::vector<double> cp(kRowA, 1.0), cm(kRowA, 1.0), ca(kRowA, 1.0), dp(kColA, 1.0), dm(kColA, 1.0), da(kColA, 1.0);
+  MatrixVectorMultiply<kRowA, kColA, 1>(A.data(), kRowA, kColA, b.data(), cp.data());
+  MatrixVectorMultiply<-1, -1, -1>(A.data(), kRowA, kColA, b.data(), cm.data());
+  MatrixVectorMultiply<kRowA, kColA, 0>(A.data(), kRowA, kColA, b.data(), ca.data());
+  MatrixTransposeVectorMultiply<kRowA, kColA, 1>(A.data(), kRowA, kColA, bt.data(), dp.data());
+  MatrixTransposeVectorMultiply<-1, -1, -1>(A.data(), kRowA, kColA, bt.data(), dm.data());
+  MatrixTransposeVectorMultiply<kRowA, kColA, 0>(A.data(), kRowA, kColA, bt.data(), da.data());
+  for (int i = 0; i < kRowA; ++i) EXPECT(cp[i] == 1.0 + Ab[i] && cm[i] == 1.0 - Ab[i] && ca[i] == Ab[i]);
+  for (int j = 0; j < kColA; ++j) EXPECT(dp[j] == 1.0 + Atb[j] && dm[j] == 1.0 - Atb[j] && da[j] == Atb[j]);
+  return 0;
+}
+}  // namespace
+
+extern "C" int swgn_small_blas_selftest() {
+  int rc = 0;
+#define RUN(...)                     \
+  do {                               \
+    if ((rc = __VA_ARGS__())) return rc; \
+  } while (0)
+  RUN(small_blas_case<5, 3, 7, false, false>);
+  RUN(small_blas_case<5, 3, 7, true, false>);
+  RUN(small_blas_case<1, 1, 1, false, false>);
+  RUN(small_blas_case<1, 1, 1, true, false>);
+  RUN(small_blas_case<9, 9, 9, false, false>);
+  RUN(small_blas_case<9, 9, 9, true, false>);
+  RUN(small_blas_case<5, 3, 7, false, true>);
+  RUN(small_blas_case<5, 3, 7, true, true>);
+  RUN(small_blas_case<1, 1, 1, false, true>);
+  RUN(small_blas_case<1, 1, 1, true, true>);
+  RUN(small_blas_case<9, 9, 9, false, true>);
+  RUN(small_blas_case<9, 9, 9, true, true>);
+  RUN(small_blas_vector_case<5, 3>);
+  RUN(small_blas_vector_case<1, 1>);
+  RUN(small_blas_vector_case<9, 9>);
+  RUN(small_blas_vector_case<15, 7>);
+#undef RUN
   return 0;
 }

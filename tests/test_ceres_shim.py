@@ -40,6 +40,14 @@ def run_demo(which, wid, export_mode, n_state, n_f):
     return rc, state, cost, list(steps), hs.value, mat, rhs, msg.value.decode()
 
 
+def test_small_blas_header_on_the_reference_test_cases():
+    """include/ceres/small_blas.h (called directly by the application's GNSS-IMU factor) against the cases of
+    CERES/internal/ceres/small_blas_test.cc: every block placement, kOperation +1 / -1 / 0, fixed and dynamic."""
+    L = demo()
+    L.swgn_small_blas_selftest.restype = C.c_int
+    assert L.swgn_small_blas_selftest() == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which,wid", [(1, 0), (2, 0), (2, 5)])
 def test_solve_through_ceres_api_equals_c_abi_and_oracle(which, wid):
