@@ -308,6 +308,8 @@ int oracle_lambda(int n, int m, const double* a, const double* Q, double* F, dou
   return lambda_rtk(n, m, a, Q, F, s);
 }
 int oracle_matinv(double* A, int n) { return matinv_rtk(A, n); }
+// InvertPSDMatrix<Dynamic>(assume_full_rank = true, m) as the Schur eliminator calls it; 1 = factorisation succeeded
+int oracle_invert_psd(const double* m, int n, double* inv) { return invert_psd(m, n, inv) ? 1 : 0; }
 int oracle_ambiguity_fix(int n, const double* A, const double* y, int n_epochs,
                          const int32_t* epoch_begin, const int32_t* obs_amb,
                          const int32_t* obs_sysfreq, int last_fix, int32_t* dd_pairs, double* F,

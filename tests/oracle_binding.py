@@ -62,6 +62,7 @@ def oracle():
                                        P(f64), i32, P(f64), P(f64), P(f64)]
         L.oracle_lambda.argtypes = [i32, i32, P(f64), P(f64), P(f64), P(f64)]
         L.oracle_matinv.argtypes = [P(f64), i32]
+        L.oracle_invert_psd.argtypes = [P(f64), i32, P(f64)]
         L.oracle_ambiguity_fix.argtypes = [i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32), i32,
                                            P(i32), P(f64), P(swgn.FixResult)]
         L.oracle_distance.restype = f64

@@ -152,3 +152,29 @@ def test_random_block_sparse_against_dense_reference():
         assert np.linalg.norm(S - S_ref) / np.linalg.norm(S_ref) < 1e-13
         assert np.linalg.norm(rhs - r_ref) / np.linalg.norm(r_ref) < 1e-12
         assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-11
+
+
+def test_invert_psd_matrix_on_the_reference_test_properties():
+    """CERES/internal/ceres/invert_psd_matrix_test.cc: Identity3x3 (:54-60, relative error <= eps) and the full-rank
+    5x5 cases, fixed and dynamic (:62-71, :88-98): |m inv(m) - I| / 5 <= 10 eps for m = Q diag(|lambda|) Q'.  The
+    eliminator only takes the assume_full_rank branch (schur_eliminator_impl.h:279-280), which is what the oracle
+    restates; the eigenvalues are drawn from [0.25, 1] so that the reference's bound holds for every seed."""
+    L = ob.oracle()
+    eps = np.finfo(float).eps
+    eye = np.eye(3)
+    inv = np.zeros((3, 3))
+    assert L.oracle_invert_psd(ob._dp(eye), 3, ob._dp(inv)) == 1
+    assert np.linalg.norm(inv - eye) / np.linalg.norm(eye) <= eps
+    rng = np.random.default_rng(5)
+    for n in (1, 3, 5, 9, 15):
+        for _ in range(20):
+            q, _r = np.linalg.qr(rng.standard_normal((n, n)))
+            lam = rng.uniform(0.25, 1.0, n)
+            m = np.ascontiguousarray((q * lam) @ q.T)
+            m = 0.5 * (m + m.T)
+            inv = np.zeros((n, n))
+            assert L.oracle_invert_psd(ob._dp(m), n, ob._dp(inv)) == 1
+            assert np.linalg.norm(m @ inv - np.eye(n)) / n <= 10 * eps
+    # not positive definite: the LLT fails and the caller is told
+    bad = np.diag([1.0, -1.0, 1.0])
+    assert L.oracle_invert_psd(ob._dp(bad), 3, ob._dp(np.zeros((3, 3)))) == 0
