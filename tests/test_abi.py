@@ -132,3 +132,30 @@ def test_gather_streams_are_well_formed(which, wid):
     assert stages * 8 == live + pad and tiles >= d["n_scells"]
     assert smax - smin <= max(4, 0.05 * smax)      # longest-first dealing keeps the 8 warps level
     assert pad < 0.45 * live                        # padding to full stages stays a minority
+
+
+def test_planner_on_the_edges_of_the_reduced_program():
+    """RemoveFixedBlocks corner cases (CERES program_test.cc RemoveFixedBlocks*): nothing constant -> the whole
+    program; every block constant -> empty reduced program, reported (the reference's preprocessor returns
+    CONVERGENCE with the fixed cost there, trust_region_preprocessor.cc:380-384, solver.cc:418-432 -- a stated deviation of the shim);
+    all f-blocks constant -> a valid plan with an empty reduced system; all e-blocks constant -> the first
+    elimination group is empty, which Ceres answers by switching the linear solver: reported as unsupported."""
+    import json
+    from linear_graph import LinearGraph
+    with open(os.path.join(ROOT, "tests", "golden", "ceres_llsq_problems.json")) as f:
+        p = json.load(f)["problem2"]
+    ne = p["num_eliminate_blocks"]
+    st, info = swgn.plan_probe(LinearGraph(p).graph_p, 0)
+    assert st == 0 and info["n_cols"] == len(p["col_sizes"]) and info["n_rows"] == len(p["row_sizes"])
+    lg = LinearGraph(p)
+    lg.block_const[:] = 1
+    st, info = swgn.plan_probe(lg.graph_p, 0)
+    assert st == 1 and b"empty reduced program" in swgn.lib().swgn_last_error()
+    lg = LinearGraph(p)
+    lg.block_const[ne:] = 1
+    st, info = swgn.plan_probe(lg.graph_p, 0)
+    assert st == 0 and info["n_f"] == 0 and info["n_e"] == sum(p["col_sizes"][:ne]) and info["n_scells"] == 0
+    lg = LinearGraph(p)
+    lg.block_const[:ne] = 1
+    st, info = swgn.plan_probe(lg.graph_p, 0)
+    assert st != 0 and b"first elimination group is empty" in swgn.lib().swgn_last_error()

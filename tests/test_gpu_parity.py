@@ -461,3 +461,23 @@ def test_recycled_slabs_do_not_leak_state_between_batches():
     assert swgn.release_cached_memory() == 0
     again = run(a)
     assert np.array_equal(again[0], first[0]) and again[1] == first[1]
+
+
+def test_window_without_retained_blocks_solves_like_the_oracle():
+    """Edge of the reduced program: every f-block constant, so the reduced system is empty (n_f = 0) and the
+    solve is Schur chunks + back-substitution only (problem 2 of the reference's llsq fixtures, e-blocks free)."""
+    with open(os.path.join(HERE, "golden", "ceres_llsq_problems.json")) as f:
+        p = json.load(f)["problem2"]
+    lg = LinearGraph(p)
+    lg.block_const[p["num_eliminate_blocks"]:] = 1
+    opt = swgn.default_options()
+    o = ob.OracleSolver(lg.graph_p, opt)
+    assert o.n_f == 0 and o.n_e == 2
+    _, osm = o.minimize()
+    b = swgn.Batch([lg.graph_p], opt)
+    sm = b.solve()[0]
+    x = b.get_state(0, lg.n_cols)
+    b.close()
+    assert sm.termination_type == osm.termination_type and sm.num_iterations == osm.num_iterations
+    assert abs(sm.final_cost - osm.final_cost) <= 1e-12 * osm.final_cost
+    np.testing.assert_allclose(x, o.state(), rtol=0, atol=1e-12)
