@@ -264,6 +264,12 @@ swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, 
    and store ranges, one end flag per tile); out[0..7] = stages, live terms, padding terms and tiles of the
    reduced-system streams, min / max stages per warp, stages and live terms of the e-cell streams. */
 swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head, int64_t* out8);
+/* Host-only: the planner's ordering of one window -- column blocks of the reduced program in elimination order
+   (graph block id per column; reorder_program.cc:209-245) and row blocks in Jacobian order (index of the residual
+   block in program order per row; reorder_program.cc:247-326).  Either array may be NULL; *n_cols / *n_rows
+   receive the counts (what swgn_batch_get_columns / _get_rows return from a device batch). */
+swgn_status swgn_plan_order(const swgn_graph* g, int32_t n_parameter_head, int32_t* n_cols, int32_t* col_block,
+                            int32_t* n_rows, int32_t* row_factor);
 int32_t swgn_batch_size(const swgn_batch* b);
 /* Return the cached device / pinned slabs of destroyed batches to the driver (all devices); returns the bytes
    released.  Never needed for correctness: the cache is bounded (see swgn_batch_destroy). */

@@ -512,6 +512,20 @@ swgn_status swgn_plan_chol_masks(const swgn_graph* g, int32_t n_parameter_head, 
 // offset inside the window's J | EBUF | residual range, every store inside S / W_EFAC / W_EBUF, one `end` per
 // tile).  out[0..7] = stages, live terms, padding terms, tiles (end flags) of the reduced-system streams, min and
 // max stages per warp, stages and live terms of the e-cell streams.
+swgn_status swgn_plan_order(const swgn_graph* g, int32_t n_parameter_head, int32_t* n_cols, int32_t* col_block, int32_t* n_rows,
+                            int32_t* row_factor) {
+  if (!g) return fail(SWGN_ERR_INVALID, "bad arguments");
+  WindowPlan p;
+  std::string err;
+  swgn_status st = build_plan(g, n_parameter_head, &p, &err);
+  if (st != SWGN_OK) return fail(st, err);
+  if (n_cols) *n_cols = p.d.n_cols;
+  if (n_rows) *n_rows = p.d.n_rows;
+  if (col_block) std::copy(p.iarr[I_COL_BLOCK].begin(), p.iarr[I_COL_BLOCK].begin() + p.d.n_cols, col_block);
+  if (row_factor) std::copy(p.iarr[I_ROW_FACTOR].begin(), p.iarr[I_ROW_FACTOR].begin() + p.d.n_rows, row_factor);
+  return SWGN_OK;
+}
+
 swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head, int64_t* out) {
   if (!g || !out) return fail(SWGN_ERR_INVALID, "bad arguments");
   WindowPlan p;

@@ -197,6 +197,7 @@ def lib():
         L.swgn_batch_create.argtypes = [P(Options), i32, P(P(Graph)), P(C.c_void_p)]
         L.swgn_batch_destroy.argtypes = [C.c_void_p]
         L.swgn_plan_probe.argtypes = [P(Graph), i32, P(i32)]
+        L.swgn_plan_order.argtypes = [P(Graph), i32, P(i32), P(i32), P(i32), P(i32)]
         L.swgn_batch_size.argtypes = [C.c_void_p]
         L.swgn_release_cached_memory.restype = C.c_int64
         L.swgn_release_cached_memory.argtypes = []
@@ -253,6 +254,18 @@ def plan_chol_masks(graph_p, n_parameter_head=0):
     m = np.zeros(max(n.value, 1), np.uint64)
     L.swgn_plan_chol_masks(graph_p, n_parameter_head, C.byref(n), m.ctypes.data_as(P(C.c_uint64)))
     return m[:n.value]
+
+
+def plan_order(graph_p, n_parameter_head=0):
+    """(status, column block ids in elimination order, residual-block index per row) from the host planner."""
+    L = lib()
+    nc, nr = i32(), i32()
+    st = L.swgn_plan_order(graph_p, n_parameter_head, C.byref(nc), None, C.byref(nr), None)
+    if st != 0:
+        return st, None, None
+    cols, rows = np.zeros(nc.value, np.int32), np.zeros(nr.value, np.int32)
+    st = L.swgn_plan_order(graph_p, n_parameter_head, C.byref(nc), _ip(cols), C.byref(nr), _ip(rows))
+    return st, cols, rows
 
 
 def release_cached_memory():

@@ -51,6 +51,11 @@ def test_planner_matches_oracle_preprocessing(which, wid):
     assert d["n_cols"] == o.n_col_blocks and d["n_ecols"] == o.n_e_blocks
     assert d["n_e"] == o.n_e and d["n_f"] == o.n_f and d["n_t"] == o.n_cols
     assert d["n_res"] == o.n_res and d["n_rows"] == o.n_row_blocks and d["n_chunks"] == o.n_e_blocks
+    # same column and row order as the oracle's preprocessing (CPU view of what the gpu tests read back)
+    st, pcols, prows = swgn.plan_order(w.graph_p, w.options().n_parameter_head)
+    ocols, _, _ = o.columns()
+    orows, _ = o.rows()
+    assert st == 0 and np.array_equal(pcols, ocols) and np.array_equal(prows, orows)
     # SURVEY.md 8d byte formula, recomputed independently from the graph
     g = w.graph
     kinds = [g.gnss_kind[i] for i in range(g.n_gnss)]

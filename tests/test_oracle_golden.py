@@ -178,3 +178,53 @@ def test_invert_psd_matrix_on_the_reference_test_properties():
     # not positive definite: the LLT fails and the caller is told
     bad = np.diag([1.0, -1.0, 1.0])
     assert L.oracle_invert_psd(ob._dp(bad), 3, ob._dp(np.zeros((3, 3)))) == 0
+
+
+def _scalar_graph(rows, groups):
+    """x, y, z scalar blocks; rows = parameter lists of the residual blocks in program order."""
+    from linear_graph import LinearGraph
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    p = {"col_sizes": [1, 1, 1], "num_eliminate_blocks": 2, "row_sizes": [1] * len(rows), "row_ptr": [int(v) for v in row_ptr],
+         "cell_col": [c for r in rows for c in r], "values": [1.0 + 0.1 * k for k in range(int(row_ptr[-1]))],
+         "b": [1.0] * len(rows)}
+    lg = LinearGraph(p)
+    lg.block_group[:] = groups
+    return lg
+
+
+def test_residual_block_order_on_the_reference_fixture():
+    """CERES/internal/ceres/reorder_program_test.cc:64-116 (ReorderResidualBlockNormalFunction): x, y in group 0, z in
+    group 1, residual blocks (x), (z,x), (z,y), (z), (x,y), (y); expected order 4, 1, 0, 5, 2, 3 -- every e-block's
+    bucket filled back to front.  The reference calls LexicographicallyOrderResidualBlocks directly; through the
+    whole preprocessor residual block 4 = (x, y) violates the independence of group 0 (program.cc:413-434, rejected
+    here as in Ceres), so the pinned vector is the same fixture without it: 1, 0, 5, 2, 3."""
+    import swgn
+    X, Y, Z = 0, 1, 2
+    rows = [[X], [Z, X], [Z, Y], [Z], [Y]]  # program order without (x, y)
+    lg = _scalar_graph(rows, [0, 0, 1])
+    o = ob.OracleSolver(lg.graph_p, swgn.default_options())
+    factor, _ = o.rows()
+    assert factor.tolist() == [1, 0, 4, 2, 3]  # = the reference's 1, 0, 5, 2, 3 with block 5 renumbered to 4
+    cols, _, _ = o.columns()
+    assert cols.tolist() == [X, Y, Z]
+    st, pcols, prows = swgn.plan_order(lg.graph_p, 0)  # the host planner of the CUDA path, same vector
+    assert st == 0 and pcols.tolist() == [X, Y, Z] and prows.tolist() == [1, 0, 4, 2, 3]
+    # with (x, y) present the first elimination group is not an independent set
+    lg_bad = _scalar_graph([[X], [Z, X], [Z, Y], [Z], [X, Y], [Y]], [0, 0, 1])
+    with pytest.raises(RuntimeError):
+        ob.OracleSolver(lg_bad.graph_p, swgn.default_options())
+    st, _ = swgn.plan_probe(lg_bad.graph_p, 0)
+    assert st != 0 and b"independent" in swgn.lib().swgn_last_error()
+
+
+def test_apply_ordering_on_the_reference_fixture():
+    """reorder_program_test.cc:138-165 (ApplyOrderingNormal): x -> group 0, y -> group 2, z -> group 1 orders the
+    parameter blocks x, z, y."""
+    import swgn
+    X, Y, Z = 0, 1, 2
+    lg = _scalar_graph([[X], [Z, X], [Z, Y], [Z], [Y]], [0, 2, 1])
+    o = ob.OracleSolver(lg.graph_p, swgn.default_options())
+    cols, _, _ = o.columns()
+    assert cols.tolist() == [X, Z, Y]
+    st, pcols, _ = swgn.plan_order(lg.graph_p, 0)
+    assert st == 0 and pcols.tolist() == [X, Z, Y]
