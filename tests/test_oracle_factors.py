@@ -183,3 +183,42 @@ def test_pose_plus_is_a_retraction():
     ob.oracle().oracle_pose_plus(dp(x), dp(d), dp(out))
     assert abs(np.linalg.norm(out[3:]) - 1) < 1e-15
     np.testing.assert_allclose(out[:3], x[:3] + d[:3])
+
+
+def test_corrector_scales_residuals_and_jacobians_like_the_reference_tests():
+    """CERES/internal/ceres/corrector_test.cc ScalarCorrection / ScalarCorrectionAlphaClamped (:57-139): with rho'' < 0
+    the corrector takes alpha = 0, so residual' = sqrt(rho') residual and J' = sqrt(rho') J, and the cost is rho / 2.
+    Checked on every robustified residual block of a cfg1 window: the same graph evaluated without the loss gives
+    the raw (r, J); Cauchy(1) has rho'' < 0 everywhere (loss_function.cc:73-80)."""
+    import swgn
+    w = swgn.SynthWindow(1, 2)
+    a = w.graph.proj_cauchy_a
+    assert a > 0
+    rob = ob.OracleSolver(w.graph_p, w.options())
+    cost_rob, r_rob, _, J_rob = rob.evaluate()
+    w.graph.proj_cauchy_a = 0.0
+    try:
+        raw = ob.OracleSolver(w.graph_p, w.options())
+        cost_raw, r_raw, _, J_raw = raw.evaluate()
+    finally:
+        w.graph.proj_cauchy_a = a
+    factor, offset = rob.rows()
+    n_checked, cost = 0, 0.0
+    bounds = list(offset) + [rob.n_res]
+    rho = np.zeros(3)
+    for k in range(rob.n_row_blocks):
+        r0, r1 = bounds[k], bounds[k + 1]
+        s = float(r_raw[r0:r1] @ r_raw[r0:r1])
+        if r1 - r0 == 2 and not np.array_equal(r_rob[r0:r1], r_raw[r0:r1]):  # a projection factor under the loss
+            ob.oracle().oracle_cauchy(a, s, dp(rho))
+            assert rho[2] < 0
+            np.testing.assert_allclose(r_rob[r0:r1], np.sqrt(rho[1]) * r_raw[r0:r1], rtol=1e-15, atol=0)
+            np.testing.assert_allclose(J_rob[r0:r1], np.sqrt(rho[1]) * J_raw[r0:r1], rtol=1e-15, atol=1e-300)
+            cost += 0.5 * rho[0]
+            n_checked += 1
+        else:
+            np.testing.assert_array_equal(r_rob[r0:r1], r_raw[r0:r1])
+            np.testing.assert_array_equal(J_rob[r0:r1], J_raw[r0:r1])
+            cost += 0.5 * s
+    assert n_checked == w.graph.n_proj
+    assert abs(cost - cost_rob) <= 1e-13 * cost_rob and cost_rob < cost_raw
