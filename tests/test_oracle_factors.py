@@ -158,9 +158,13 @@ def test_varerr2_uses_single_precision_sine():
 
 
 def test_cauchy_loss_values_and_derivatives():
+    """Includes the points of the reference's loss_function_test.cc:118-126 (CauchyLoss(0.7), CauchyLoss(1.3) at
+    s = 0.357, 1.792 and at 0): value against the closed form, derivatives against central differences."""
     rho = np.zeros(3)
-    for a in (1.0, 2.5):
-        for s in (0.0, 0.3, 7.0, 1e4):
+    ob.oracle().oracle_cauchy(0.7, 0.0, dp(rho))
+    assert rho[0] == 0.0 and rho[1] == 1.0 and abs(rho[2] + 1.0 / 0.49) < 1e-15
+    for a in (1.0, 2.5, 0.7, 1.3):
+        for s in (0.0, 0.3, 7.0, 1e4, 0.357, 1.792):
             ob.oracle().oracle_cauchy(a, s, dp(rho))
             assert abs(rho[0] - a * a * np.log1p(s / (a * a))) <= 1e-12 * max(1, rho[0])
             h = 1e-6 * max(1.0, s)
