@@ -215,8 +215,12 @@ typedef struct swgn_options {
                                             blocks are the LAST n_parameter_head groups of the
                                             ordering (swf_gnss.cpp:775-782)                  */
   int32_t device;                        /* CUDA device ordinal                              */
-  int32_t reserved;
+  int32_t trust_region_strategy;         /* SWGN_DOGLEG (0, the reference's setting, the only one the device
+                                            implements: swgn_batch_create answers SWGN_ERR_UNSUPPORTED otherwise) or
+                                            SWGN_LEVENBERG_MARQUARDT (Ceres' default, levenberg_marquardt_strategy.cc;
+                                            so far restated by the oracle only)                                  */
 } swgn_options;
+enum { SWGN_DOGLEG = 0, SWGN_LEVENBERG_MARQUARDT = 1 };
 
 enum { SWGN_CONVERGENCE = 0, SWGN_NO_CONVERGENCE = 1, SWGN_FAILURE = 2 };
 

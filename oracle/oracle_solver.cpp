@@ -789,6 +789,11 @@ bool Solver::Minimize(swgn_summary* summary) {
   bool reuse = false;
   double alpha = 0.0, dogleg_step_norm = 0.0;
   std::vector<double> diagonal(n), dgrad(n), gn(n), lm_diag(n);
+  // LevenbergMarquardtStrategy state (levenberg_marquardt_strategy.cc:49-62): radius as above, decrease factor,
+  // reuse_diagonal; `diagonal` then holds the clamped SQUARED column norms
+  const bool lm = opt.trust_region_strategy == SWGN_LEVENBERG_MARQUARDT;
+  double decrease_factor = 2.0;
+  bool reuse_diagonal = false;
 
   IterationRecord it = {};
   auto eval_grad_jac = [&]() -> bool {                           // EvaluateGradientAndJacobian
@@ -852,7 +857,24 @@ bool Solver::Minimize(swgn_summary* summary) {
 
     // ---- ComputeTrustRegionStep -> DoglegStrategy::ComputeStep (dogleg_strategy.cc:79-165)
     bool linear_failure = false;
-    if (!reuse) {
+    if (lm) {
+      // LevenbergMarquardtStrategy::ComputeStep :67-149
+      if (!reuse_diagonal) {
+        squared_column_norm(jac, diagonal.data());
+        for (int i = 0; i < n; ++i) diagonal[i] = std::min(std::max(diagonal[i], opt.min_lm_diagonal), opt.max_lm_diagonal);
+      }
+      for (int i = 0; i < n; ++i) lm_diag[i] = std::sqrt(diagonal[i] / radius);
+      bool exported_only = false;
+      bool ok = LinearSolve(residuals.data(), lm_diag.data(), step.data(), &exported_only);
+      if (exported_only) export_return = true;
+      if (ok)
+        for (int i = 0; i < n; ++i)
+          if (!std::isfinite(step[i])) ok = false;
+      linear_failure = !ok;
+      if (ok)
+        for (int i = 0; i < n; ++i) step[i] = -step[i];
+      reuse_diagonal = true;
+    } else if (!reuse) {
       reuse = true;
       squared_column_norm(jac, diagonal.data());
       for (int i = 0; i < n; ++i)
@@ -892,7 +914,19 @@ bool Solver::Minimize(swgn_summary* summary) {
         for (int i = 0; i < n; ++i) gn[i] *= -diagonal[i];
     }
     it.step_is_valid = 0;
-    if (!linear_failure) {
+    if (!linear_failure && lm) {
+      // model cost change  trust_region_minimizer.cc:414-431 (the step is already in the unscaled space)
+      std::fill(model_residuals.begin(), model_residuals.end(), 0.0);
+      right_multiply(jac, step.data(), model_residuals.data());
+      double mc = 0.0;
+      for (int i = 0; i < nr; ++i) mc += model_residuals[i] * (residuals[i] + model_residuals[i] / 2.0);
+      model_cost_change = -mc;
+      it.step_is_valid = model_cost_change > 0.0;
+      if (it.step_is_valid) {
+        delta = step;
+        num_consecutive_invalid = 0;
+      }
+    } else if (!linear_failure) {
       // ComputeTraditionalDoglegStep :199-253
       double gnorm = norm2(dgrad), gnn = norm2(gn);
       if (gnn <= radius) {
@@ -931,8 +965,14 @@ bool Solver::Minimize(swgn_summary* summary) {
         termination = SWGN_FAILURE;
         break;
       }
-      mu *= mu_increase;                                         // StepIsInvalid
-      reuse = false;
+      if (lm) {  // StepIsInvalid = StepRejected(0)  levenberg_marquardt_strategy.h:61-67
+        radius = radius / decrease_factor;
+        decrease_factor *= 2.0;
+        reuse_diagonal = true;
+      } else {
+        mu *= mu_increase;                                       // StepIsInvalid
+        reuse = false;
+      }
       it.cost = x_cost + fixed_cost;
       it.cost_change = 0.0;
       it.gradient_max_norm = prev_gmax;
@@ -982,11 +1022,18 @@ bool Solver::Minimize(swgn_summary* summary) {
         break;
       }
       it.step_is_successful = 1;
-      // DoglegStrategy::StepAccepted :612-628
-      if (it.relative_decrease < 0.25) radius *= 0.5;
-      if (it.relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
-      mu = std::max(min_mu, 2.0 * mu / mu_increase);
-      reuse = false;
+      if (lm) {  // LevenbergMarquardtStrategy::StepAccepted :151-158
+        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+        radius = std::min(opt.max_trust_region_radius, radius);
+        decrease_factor = 2.0;
+        reuse_diagonal = false;
+      } else {
+        // DoglegStrategy::StepAccepted :612-628
+        if (it.relative_decrease < 0.25) radius *= 0.5;
+        if (it.relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
+        mu = std::max(min_mu, 2.0 * mu / mu_increase);
+        reuse = false;
+      }
       // TrustRegionStepEvaluator::StepAccepted :70-112
       se_cur = candidate_cost;
       se_acc_cand += model_cost_change;
@@ -1011,8 +1058,14 @@ bool Solver::Minimize(swgn_summary* summary) {
       it.step_is_successful = 0;
       it.cost = candidate_cost + fixed_cost;
       it.gradient_max_norm = prev_gmax;
-      radius *= 0.5;                                             // StepRejected :630-633
-      reuse = true;
+      if (lm) {  // LevenbergMarquardtStrategy::StepRejected :160-164
+        radius = radius / decrease_factor;
+        decrease_factor *= 2.0;
+        reuse_diagonal = true;
+      } else {
+        radius *= 0.5;                                           // StepRejected :630-633
+        reuse = true;
+      }
     }
   }
   (void)export_return;

@@ -200,6 +200,8 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
                               swgn_batch** out) {
   if (!options || !graphs || !out || n_windows <= 0) return fail(SWGN_ERR_INVALID, "bad arguments");
   *out = nullptr;
+  if (options->trust_region_strategy != SWGN_DOGLEG)
+    return fail(SWGN_ERR_UNSUPPORTED, "only the DOGLEG trust-region strategy is implemented on the device");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || options->device < 0 || options->device >= ndev)
     return fail(SWGN_ERR_NO_DEVICE, "no usable CUDA device (the solver has no CPU fallback)");

@@ -45,7 +45,7 @@ class Options(C.Structure):
         ("min_lm_diagonal", f64), ("max_lm_diagonal", f64),
         ("function_tolerance", f64), ("gradient_tolerance", f64), ("parameter_tolerance", f64),
         ("dogleg_min_mu", f64),
-        ("is_optimize", i32), ("n_parameter_head", i32), ("device", i32), ("reserved", i32),
+        ("is_optimize", i32), ("n_parameter_head", i32), ("device", i32), ("trust_region_strategy", i32),
     ]
 
 

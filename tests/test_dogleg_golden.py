@@ -126,3 +126,43 @@ def test_gpu_dogleg_on_the_reference_fixtures(name, radius):
     J, r, _ = fixture(name)
     xo, _ = solve_oracle(graph(J, r), options(radius))
     np.testing.assert_allclose(x, xo, rtol=0, atol=1e-12)
+
+
+# ---- Levenberg-Marquardt strategy: restated by the oracle only so far (the device answers SWGN_ERR_UNSUPPORTED)
+def lm_options(radius, iters):
+    opt = options(radius)
+    opt.max_num_iterations = iters
+    opt.trust_region_strategy = 1  # SWGN_LEVENBERG_MARQUARDT
+    return opt
+
+
+@pytest.mark.parametrize("name", ["ellipse", "valley"])
+def test_oracle_levenberg_marquardt_step_and_radius_update(name):
+    """levenberg_marquardt_strategy.cc:67-165 on the same fixtures: the first step is -(J'J + D^2)^-1 J'r with
+    D^2 = clamp(colnorm^2) / radius (= 1 / radius here, min = max diagonal = 1); the model is exact for a linear
+    problem, so rho = 1 and the accepted step multiplies the radius by 3 (radius / max(1/3, 1 - (2 rho - 1)^3)),
+    capped by max_radius; a few iterations reach the minimum."""
+    J, r, minimum = fixture(name)
+    lg = graph(J, r)
+    radius = 4.0
+    o = ob.OracleSolver(lg.graph_p, lm_options(radius, 1))
+    _, sm = o.minimize()
+    x = o.state().copy()
+    want = -np.linalg.solve(J.T @ J + np.eye(6) / radius, J.T @ r)
+    np.testing.assert_allclose(x, want, rtol=0, atol=1e-12)
+    assert sm.num_iterations == 1 and sm.num_unsuccessful_steps == 0
+    opt = lm_options(radius, 6)
+    opt.max_trust_region_radius = 1e16
+    o = ob.OracleSolver(lg.graph_p, opt)
+    _, sm = o.minimize()
+    costs, radii, ok = o.iteration_records()
+    assert all(ok) and np.all(np.diff(costs) < 0)
+    np.testing.assert_allclose(radii[1:] / radii[:-1], 3.0, rtol=1e-6)  # rho = 1 up to rounding
+    np.testing.assert_allclose(o.state(), minimum, atol=1e-4)
+
+
+def test_device_rejects_levenberg_marquardt_loudly():
+    J, r, _ = fixture("valley")
+    lg = graph(J, r)
+    with pytest.raises(RuntimeError, match="DOGLEG"):
+        swgn.Batch([lg.graph_p], lm_options(2.0, 1))
