@@ -274,6 +274,14 @@ swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head
    receive the counts (what swgn_batch_get_columns / _get_rows return from a device batch). */
 swgn_status swgn_plan_order(const swgn_graph* g, int32_t n_parameter_head, int32_t* n_cols, int32_t* col_block,
                             int32_t* n_rows, int32_t* row_factor);
+/* Host-only: the plan of the streamed Schur elimination of one window (k_schur_stream: the Jacobian staged batch by
+   batch through shared memory by TMA, S accumulated on chip): info[0..9] = fits the on-chip budget (else the gather
+   kernel runs the window), batches, accumulator doubles, J / residual / E-buffer / chunk-factor capacity of a stage
+   (doubles), largest record package (ints), retained blocks, dynamic shared memory bytes. */
+swgn_status swgn_plan_stream_info(const swgn_graph* g, int32_t n_parameter_head, int32_t* info16);
+/* Host-only (tests, debugging): copy one of the planner's index arrays (csrc/device_types.h IArr) of a window;
+   *n receives its length, out may be NULL to query it. */
+swgn_status swgn_plan_array(const swgn_graph* g, int32_t n_parameter_head, int32_t array, int32_t* out, int64_t* n);
 int32_t swgn_batch_size(const swgn_batch* b);
 /* Return the cached device / pinned slabs of destroyed batches to the driver (all devices); returns the bytes
    released.  Never needed for correctness: the cache is bounded (see swgn_batch_destroy). */

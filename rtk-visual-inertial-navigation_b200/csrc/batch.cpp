@@ -249,7 +249,8 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   b->state_off.resize(n_windows + 1);
   b->has_scopy = n_windows <= 256;
   size_t io = 0, co = 0, wo = 0;
-  int max_wbuf = 0, max_nf = 0, max_prior_n = 0, max_chain = 0, max_chain_k = 0;
+  int max_wbuf = 0, max_nf = 0, max_prior_n = 0, max_chain = 0, max_chain_k = 0, sb_windows = 0;
+  size_t sb_smem = 0;
   auto al = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
   int64_t so = 0;
   for (int w = 0; w < n_windows; ++w) {
@@ -277,6 +278,10 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
     max_prior_n = std::max(max_prior_n, d.max_prior_n);
     max_chain = std::max(max_chain, d.n_chain);
     max_chain_k = std::max(max_chain_k, d.max_chain_k);
+    if (d.sb_ok) {
+      ++sb_windows;
+      sb_smem = std::max(sb_smem, stream_smem_bytes(d.sb_nbatch, d.sb_acc, d.sb_jcap, d.sb_rcap, d.sb_ecap, d.sb_fcap, d.sb_reccap));
+    }
     if (options->n_parameter_head > 0 && d.n_f >= 1024) {
       swgn_batch_destroy(b);
       return fail(SWGN_ERR_TOO_LARGE, "reduced system has >= 1024 rows with exports requested");
@@ -441,6 +446,9 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   db.max_chain_k = max_chain_k;
   db.chain_epoch = 1;
   db.keep_copy = 0;
+  db.sb_windows = sb_windows;
+  db.gather_windows = n_windows - sb_windows;
+  db.sb_smem = (unsigned)sb_smem;
   if (std::getenv("SWGN_DEBUG_TIMELINE")) {
     CB(cudaMalloc(&b->d_debug, sizeof(long long) * 16 * n_windows));
     CB(cudaMemset(b->d_debug, 0, sizeof(long long) * 16 * n_windows));
@@ -463,6 +471,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   P.n_parameter_head = options->n_parameter_head;
   P.export_mode = (options->n_parameter_head > 0 && !options->is_optimize) ? 1 : 0;
   CB(configure_schur(db));
+  CB(configure_schur_stream(db));
   CB(configure_chol(db));
   CB(configure_chain(db));
   launch_gather_states(db, b->d_stage, b->d_state_off, 1, b->stream);
@@ -589,6 +598,31 @@ swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head
     }
   }
   if (out[4] == INT64_MAX) out[4] = 0;
+  return SWGN_OK;
+}
+
+swgn_status swgn_plan_stream_info(const swgn_graph* g, int32_t n_parameter_head, int32_t* info) {
+  if (!g || !info) return fail(SWGN_ERR_INVALID, "bad arguments");
+  WindowPlan p;
+  std::string err;
+  swgn_status st = build_plan(g, n_parameter_head, &p, &err);
+  if (st != SWGN_OK) return fail(st, err);
+  const StreamPlanInfo& sb = p.sb;
+  std::memset(info, 0, sizeof(int32_t) * 16);
+  const int32_t v[10] = {sb.ok, sb.nbatch, sb.acc, sb.jcap, sb.rcap, sb.ecap, sb.fcap, sb.reccap, sb.n_fb,
+                         (int32_t)stream_smem_bytes(sb.nbatch, sb.acc, sb.jcap, sb.rcap, sb.ecap, sb.fcap, sb.reccap)};
+  std::memcpy(info, v, sizeof(v));
+  return SWGN_OK;
+}
+
+swgn_status swgn_plan_array(const swgn_graph* g, int32_t n_parameter_head, int32_t array, int32_t* out, int64_t* n) {
+  if (!g || !n || array < 0 || array >= NUM_IARR) return fail(SWGN_ERR_INVALID, "bad arguments");
+  WindowPlan p;
+  std::string err;
+  swgn_status st = build_plan(g, n_parameter_head, &p, &err);
+  if (st != SWGN_OK) return fail(st, err);
+  *n = (int64_t)p.iarr[array].size();
+  if (out) std::copy(p.iarr[array].begin(), p.iarr[array].end(), out);
   return SWGN_OK;
 }
 

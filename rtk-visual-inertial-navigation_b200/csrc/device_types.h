@@ -79,6 +79,10 @@ enum IArr {
   I_CHAIN,          // [n_chain * 8] m (hidden frames), k (phase biases), res_off, first entry in I_CHAIN_BLK,
                     //               C_CHAIN offset, W_CHAIN offset, first hidden frame of the window, 0
   I_CHAIN_BLK,      // [(4 + k) * 2 per chain] state_off, jac_off of pose_i, sb_i, pose_j, sb_j, N_0 ..
+  I_SB_HDR,         // [sb_nbatch * SB_HDR_INTS] batch headers of the streamed Schur elimination (see "streamed Schur" below)
+  I_SB_REC,         // record packages of the batches, back to back (every package a multiple of 4 ints)
+  I_ACC_MAP,        // [n_fb * n_fb] block cell (p, q), p <= q, of the reduced system -> offset of its compact accumulator
+                    //               (ps x (qs + [p == q]) doubles, row-major, the extra column of diagonal cells = rhs), -1: untouched
   NUM_IARR
 };
 
@@ -98,6 +102,29 @@ enum IArr {
 // meta = ps | qs << 6 | (ti / 8) << 12 | (tj / 8) << 15 | diag << 18.  A tile's term list is padded to a multiple
 // of SCHUR_STAGE with entries whose loads are switched off, so a stage is straight-line code.
 enum { SCHUR_WARPS = 8, SCHUR_STAGE = 8 };
+
+// Streamed Schur elimination (k_schur_stream.cu): the window's Jacobian is cut, in row order, into BATCHES of whole
+// chunks (all rows of one e-block) and single rows without e-block.  A batch is staged into shared memory by TMA bulk
+// copies (its contiguous J segment, its residual segment, its record package), its chunk products / factors / W blocks
+// are computed on chip, and its terms F'F / -W'W are accumulated into COMPACT accumulators of the touched block cells
+// of S that stay in shared memory for the whole window; S is written to HBM once at the end.
+// Operand area OA (doubles): [stage 0: J | res][stage 1: J | res][wbuf: W (E-buffer segment) | chunk factors]; batch k
+// uses stage k & 1; every offset inside a record is a 16-bit absolute OA offset.
+//   header (SB_HDR_INTS ints): rec_off, rec_len (ints), j_src (doubles, relative to W_JAC, even), j_len (even),
+//           r_src (relative to W_RES, even), r_len, eb_src (W_EBUF), eb_len, ef_src (W_EFAC), ef_len,
+//           n_tchunk, n_trow, n_mchunk, off_tchunk | off_trow << 16, off_mchunk (int offsets inside the package), sec_len
+//   package: the first sec_len ints travel to shared memory with the batch: [SB_WARPS + 1] pointers of the phase-A run
+//           streams, [SB_WARPS + 1] of the phase-C run streams (int offsets inside the package), then the sections
+//           below; the run streams follow and are read from L2 through per-warp cp.async rings:
+//     tchunk (int4): crow list offset, n_rows | es << 16, factor OA | g OA << 16, tangent position of the e-block
+//       crow (int2): E OA | nres << 16, residual OA
+//     trow (2 x int4): E OA, nres | es << 8 | n_fcells << 16, factor OA, offset of the extra f-cell list;
+//                      F OA, W OA, fs, 0        extra f-cell (int4): F OA, W OA, fs, 0
+//     mchunk (2 x int4): es, tangent position, factor OA, n_slots + 1; slot table offset, 0, 0, 0
+//       slot (int2): OA offset of the es x fs block (last entry: g, fs = 1), fs
+//     run (int4 + n x int2): dst, rhs dst, n_terms | first << 16 | ecell << 17, meta (as in the gather streams);
+//       term: a OA | b OA << 16,  b2 OA | rows-1 << 16 | subtract << 18 | padding << 31; n_terms is a multiple of 4
+enum { SB_WARPS = 16, SB_HDR_INTS = 16, SB_JCAP = 2560, SB_TERMCAP = 4096, SB_RING_BYTES = 512, SB_SMEM_BUDGET = 227 * 1024 - 1024 };
 
 enum CArr {
   C_GLOBALS = 0,  // Pbg[3], gravity[3], proj_sqrt_info[4], cauchy_a, pad -> 12
@@ -188,6 +215,8 @@ struct WinDesc {
   int32_t n_tchunks, n_wchunks, n_scells, n_sterms, n_srows, max_prior_n, max_wbuf, n_ecells;
   int32_t n_chain, n_chain_frames, max_chain_k, n_wstream;
   int32_t n_tchunks_t, n_tchunks_w;
+  // streamed Schur elimination: sb_ok = the window fits the on-chip budget (else the gather kernel k_schur runs it)
+  int32_t sb_ok, sb_nbatch, sb_acc, sb_jcap, sb_rcap, sb_ecap, sb_fcap, sb_reccap, n_fb, sb_pad;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

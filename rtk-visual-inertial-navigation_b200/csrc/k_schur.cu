@@ -671,6 +671,7 @@ __global__ void __launch_bounds__(kSchurThreads, SWGN_SCHUR_CTAS) k_schur(Device
   if (only_window < 0 && !(st->active && st->need_solve)) return;
   const Win v = load_window(b, w, &sd);
   const WinDesc& d = sd;
+  if (d.sb_ok) return;  // this window runs the streamed kernel (k_schur_stream.cu)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int gtid = tid, gwid = wid;
   const double* lmd = v.W(W_LMD);
@@ -903,10 +904,16 @@ static size_t schur_dyn_bytes(const DeviceBatch& b) {
   return dyn;
 }
 
-void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
+void launch_schur_gather(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
   const size_t dyn = schur_dyn_bytes(b);
   k_schur<<<grid, kSchurThreads, dyn, s>>>(b, only_window);
+}
+// every window is run by exactly one of the two kernels (WinDesc::sb_ok); a kernel is only launched when the batch
+// holds windows of its kind
+void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s) {
+  if (b.sb_windows > 0) launch_schur_stream(b, only_window, s);
+  if (b.gather_windows > 0) launch_schur_gather(b, only_window, s);
 }
 void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;

@@ -23,6 +23,9 @@ struct DeviceBatch {
   int max_chain;         // max IMUGNSSFactor chains per window (0: k_chain is never launched)
   int max_chain_k;       // max phase biases per chain (shared-memory size of k_chain)
   int chain_epoch;       // bumped by create / update_inputs: chains reload their hidden states and forget history
+  int sb_windows;        // windows whose Schur elimination runs streamed (k_schur_stream); the others run k_schur
+  int gather_windows;
+  unsigned sb_smem;      // dynamic shared memory of k_schur_stream (max over the streamed windows)
   int keep_copy;         // copy S|rhs to W_SCOPY before factorising (staged test entry point)
   long long* debug;      // optional [n_windows * 8] phase timestamps of k_schur (SWGN_DEBUG_TIMELINE=1), else null
 };
@@ -38,7 +41,10 @@ void launch_eval(const DeviceBatch& b, int mode, int only_window, cudaStream_t s
 void launch_chain(const DeviceBatch& b, int mode, int only_window, cudaStream_t s);
 cudaError_t configure_chain(const DeviceBatch& b);
 void launch_begin(const DeviceBatch& b, int tick, cudaStream_t s);
-void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s);
+void launch_schur(const DeviceBatch& b, int only_window, cudaStream_t s);         // dispatches to the two kernels below
+void launch_schur_gather(const DeviceBatch& b, int only_window, cudaStream_t s);
+void launch_schur_stream(const DeviceBatch& b, int only_window, cudaStream_t s);
+cudaError_t configure_schur_stream(const DeviceBatch& b);
 void launch_chol(const DeviceBatch& b, int only_window, cudaStream_t s);
 void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s);
 void launch_step(const DeviceBatch& b, cudaStream_t s);

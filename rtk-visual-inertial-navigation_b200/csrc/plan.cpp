@@ -810,9 +810,21 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     pack_constants(g, ptr);
   }
 
+  // ---- streamed Schur elimination (plan_stream.cpp); windows that do not fit its on-chip budget keep the gather kernel
+  build_stream_plan(P, n_rows, n_cols, n_ecols, n_jac, n_res, col_size, col_pos);
+
   // ---- descriptor
   WinDesc& d = P->d;
   d = WinDesc();
+  d.sb_ok = P->sb.ok;
+  d.sb_nbatch = P->sb.nbatch;
+  d.sb_acc = P->sb.acc;
+  d.sb_jcap = P->sb.jcap;
+  d.sb_rcap = P->sb.rcap;
+  d.sb_ecap = P->sb.ecap;
+  d.sb_fcap = P->sb.fcap;
+  d.sb_reccap = P->sb.reccap;
+  d.n_fb = n_cols - n_ecols;
   d.n_state = g->n_state;
   d.n_cols = n_cols;
   d.n_ecols = n_ecols;

@@ -11,6 +11,11 @@
 
 namespace swgn {
 
+// result of build_stream_plan (plan_stream.cpp): sizes of the on-chip layout of the streamed Schur elimination
+struct StreamPlanInfo {
+  int ok = 0, nbatch = 0, acc = 0, jcap = 0, rcap = 0, ecap = 0, fcap = 0, reccap = 0, n_fb = 0;
+};
+
 struct WindowPlan {
   WinDesc d;                               // counts filled; offsets filled by the batch
   std::vector<int32_t> iarr[NUM_IARR];
@@ -21,7 +26,14 @@ struct WindowPlan {
   // (SURVEY.md 8d formula): J blocks at their stored size + residuals + D in, S upper + r + y out
   int64_t schur_doubles;
   int64_t n_mma = 0;                       // tensor-core MMAs of one Schur gather pass (planning statistic)
+  StreamPlanInfo sb;
 };
+
+// dynamic shared memory of k_schur_stream for a window (or a batch: pass the maxima) with these sizes
+size_t stream_smem_bytes(int nbatch, int acc, int jcap, int rcap, int ecap, int fcap, int reccap);
+// streamed Schur plan of one window: fills I_SB_HDR, I_SB_REC, I_ACC_MAP and P->sb from the row / chunk / slot tables
+void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n_jac, int n_res, const std::vector<int>& col_size,
+                       const std::vector<int>& col_pos);
 
 // sizes (doubles) and packing of the factor constants in device layout; used at plan time and by
 // swgn_batch_update_inputs (same structure, new measurements)
