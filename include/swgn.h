@@ -277,7 +277,8 @@ swgn_status swgn_plan_order(const swgn_graph* g, int32_t n_parameter_head, int32
 /* Host-only: the plan of the streamed Schur elimination of one window (k_schur_stream: the Jacobian staged batch by
    batch through shared memory by TMA, S accumulated on chip): info[0..9] = fits the on-chip budget (else the gather
    kernel runs the window), batches, accumulator doubles, J / residual / E-buffer / chunk-factor capacity of a stage
-   (doubles), largest record package (ints), retained blocks, dynamic shared memory bytes. */
+   (doubles), largest record package (ints), retained blocks, dynamic shared memory bytes; info[10] = the batch would use it (fits and SWGN_SCHUR_STREAM=1 is set:
+   the streamed kernel is opt-in). */
 swgn_status swgn_plan_stream_info(const swgn_graph* g, int32_t n_parameter_head, int32_t* info16);
 /* Host-only (tests, debugging): copy one of the planner's index arrays (csrc/device_types.h IArr) of a window;
    *n receives its length, out may be NULL to query it. */

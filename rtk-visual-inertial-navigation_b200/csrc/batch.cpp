@@ -450,8 +450,8 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   db.gather_windows = n_windows - sb_windows;
   db.sb_smem = (unsigned)sb_smem;
   if (std::getenv("SWGN_DEBUG_TIMELINE")) {
-    CB(cudaMalloc(&b->d_debug, sizeof(long long) * 16 * n_windows));
-    CB(cudaMemset(b->d_debug, 0, sizeof(long long) * 16 * n_windows));
+    CB(cudaMalloc(&b->d_debug, sizeof(long long) * 24 * n_windows));
+    CB(cudaMemset(b->d_debug, 0, sizeof(long long) * 24 * n_windows));
   }
   db.debug = b->d_debug;
   SolverParams& P = db.params;
@@ -609,9 +609,10 @@ swgn_status swgn_plan_stream_info(const swgn_graph* g, int32_t n_parameter_head,
   if (st != SWGN_OK) return fail(st, err);
   const StreamPlanInfo& sb = p.sb;
   std::memset(info, 0, sizeof(int32_t) * 16);
-  const int32_t v[10] = {sb.ok, sb.nbatch, sb.acc, sb.jcap, sb.rcap, sb.ecap, sb.fcap, sb.reccap, sb.n_fb,
+  const int32_t v[10] = {sb.fits, sb.nbatch, sb.acc, sb.jcap, sb.rcap, sb.ecap, sb.fcap, sb.reccap, sb.n_fb,
                          (int32_t)stream_smem_bytes(sb.nbatch, sb.acc, sb.jcap, sb.rcap, sb.ecap, sb.fcap, sb.reccap)};
   std::memcpy(info, v, sizeof(v));
+  info[10] = sb.ok;  // fits AND enabled (SWGN_SCHUR_STREAM=1)
   return SWGN_OK;
 }
 
@@ -726,7 +727,7 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
 // accumulated phase cycles of the last k_chol launch (8 per window)
 swgn_status swgn_batch_debug_timeline(swgn_batch* b, int64_t* out) {
   if (!b || !b->d_debug || !out) return fail(SWGN_ERR_INVALID, "timeline not enabled (SWGN_DEBUG_TIMELINE=1)");
-  CU(cudaMemcpy(out, b->d_debug, sizeof(long long) * 16 * b->n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, b->d_debug, sizeof(long long) * 24 * b->n, cudaMemcpyDeviceToHost));
   return SWGN_OK;
 }
 

@@ -112,18 +112,19 @@ enum { SCHUR_WARPS = 8, SCHUR_STAGE = 8 };
 // uses stage k & 1; every offset inside a record is a 16-bit absolute OA offset.
 //   header (SB_HDR_INTS ints): rec_off, rec_len (ints), j_src (doubles, relative to W_JAC, even), j_len (even),
 //           r_src (relative to W_RES, even), r_len, eb_src (W_EBUF), eb_len, ef_src (W_EFAC), ef_len,
-//           n_tchunk, n_trow, n_mchunk, off_tchunk | off_trow << 16, off_mchunk (int offsets inside the package), sec_len
+//           n_tchunk, off_textra, n_mchunk, off_tchunk, off_mchunk (int offsets inside the package), sec_len
 //   package: the first sec_len ints travel to shared memory with the batch: [SB_WARPS + 1] pointers of the phase-A run
 //           streams, [SB_WARPS + 1] of the phase-C run streams (int offsets inside the package), then the sections
 //           below; the run streams follow and are read from L2 through per-warp cp.async rings:
-//     tchunk (int4): crow list offset, n_rows | es << 16, factor OA | g OA << 16, tangent position of the e-block
-//       crow (int2): E OA | nres << 16, residual OA
-//     trow (2 x int4): E OA, nres | es << 8 | n_fcells << 16, factor OA, offset of the extra f-cell list;
-//                      F OA, W OA, fs, 0        extra f-cell (int4): F OA, W OA, fs, 0
+//     tchunk (int4): offset of its trow list, n_rows | es << 16, factor OA | g OA << 16, tangent position of the e-block
+//       trow (int4, one per row of the chunk): E OA | nres << 16, residual OA, F OA | W OA << 16 of the first f-cell,
+//                      fs | n_fcells << 8 | index of its further f-cells in the textra list << 16
+//       textra (int4): F OA, W OA, fs, 0
 //     mchunk (2 x int4): es, tangent position, factor OA, n_slots + 1; slot table offset, 0, 0, 0
 //       slot (int2): OA offset of the es x fs block (last entry: g, fs = 1), fs
-//     run (int4 + n x int2): dst, rhs dst, n_terms | first << 16 | ecell << 17, meta (as in the gather streams);
-//       term: a OA | b OA << 16,  b2 OA | rows-1 << 16 | subtract << 18 | padding << 31; n_terms is a multiple of 4
+//     run (int4 + n x int2): dst, rhs dst, n_plus | n_minus << 12 | first << 24 | ecell << 25, meta (as in the gather
+//       streams); the n_plus terms that add come first, then the n_minus terms that subtract, both counts multiples of 4
+//       term: a OA | b OA << 16,  b2 OA | row mask << 16 (bit k: row k of the <= 4-row slab exists); all-zero = padding
 enum { SB_WARPS = 16, SB_HDR_INTS = 16, SB_JCAP = 2560, SB_TERMCAP = 4096, SB_RING_BYTES = 512, SB_SMEM_BUDGET = 227 * 1024 - 1024 };
 
 enum CArr {

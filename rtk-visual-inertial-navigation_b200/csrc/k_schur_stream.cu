@@ -18,6 +18,8 @@
 //      deterministic (the reference serialises with per-cell mutexes, :552).
 // The Jacobian is read from HBM exactly once and S is written exactly once, rows at a time, zeros included (no clear
 // pass); the only other traffic is the record stream (8 bytes per MMA term, read through per-warp cp.async rings).
+#include <mutex>
+
 #include "dev_common.cuh"
 #include "../../include/swgn.h"
 
@@ -63,9 +65,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -76,24 +75,27 @@ __device__ __forceinline__ void cp_async_wait() {
 // A warp's stream is a sequence of 16-byte units in global memory (L2): a run header followed by n/2 units of two
 // terms each.  Units arrive in a per-warp ring of 4 chunks x 8 units by cp.async, three chunks ahead of their use.
 struct Ring {
-  int4 u[4][8];
+  int4 u[32];  // 4 chunks x 8 units
 };
 static_assert(sizeof(Ring) == SB_RING_BYTES, "ring size is part of the planner's shared-memory budget");
 
 struct Reader {
   const int4* gs;
-  Ring* R;
+  uint32_t ring;  // shared-space address
   int n_units, issued, ready, lane;
   __device__ __forceinline__ void issue() {
     const int u = issued * 8 + lane;
-    if (lane < 8 && u < n_units) cp_async16(&R->u[issued & 3][lane], gs + u);
+    if (lane < 8 && u < n_units) {
+      const uint32_t dst = ring + 16u * (unsigned)(u & 31);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gs + u) : "memory");
+    }
     cp_async_commit();
     ++issued;
   }
   __device__ __forceinline__ void start(const int4* g, int n, Ring* r, int ln) {
     gs = g;
     n_units = n;
-    R = r;
+    ring = smem_u32(r);
     lane = ln;
     issued = ready = 0;
     __syncwarp();  // every lane is done with the ring contents of the previous stream
@@ -110,20 +112,30 @@ struct Reader {
       issue();
     }
   }
-  __device__ __forceinline__ int4 unit(int u) const { return R->u[(u >> 3) & 3][u & 7]; }
+  __device__ __forceinline__ int4 unit(int u) const {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + 16u * (unsigned)(u & 31)));
+    return v;
+  }
   __device__ __forceinline__ void finish() { cp_async_wait<0>(); }
 };
 
-struct TileLane {
-  int a_lo, b_lo;
-  bool a_ok, b_any, b_rhs;
-};
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
-// Runs of one phase of one batch.  OA = operand area, ACC = accumulators.  ecell runs (phase A) store the raw chunk
-// products into the operand area; the others (phase C) accumulate into the compact block cells of S.
-__device__ void run_stream(const int4* gs, int n_units, Ring* ring, int lane, double* OA, double* ACC) {
+// Runs of one phase of one batch.  oa / acc = shared-space byte addresses of the operand area and of the accumulators.
+// ecell runs (phase A) store the raw chunk products into the operand area; the others (phase C) accumulate into the
+// compact block cells of S.  The inner loop is branch-free: the only predicate is the row mask of the A operand (rows
+// beyond the slab contribute exact zeros; everything the B operand or out-of-block lanes read is finite memory of the
+// operand area -- zero-filled at kernel entry -- and lands in accumulator elements that are never stored).
+__device__ __noinline__ void run_stream(const int4* gs, int n_units, Ring* ring, int lane, uint32_t oa, uint32_t acc) {
   if (n_units <= 0) return;
   const int la = lane & 3, lb = lane >> 2;
+  const unsigned lmask = 1u << (16 + la);
   Reader rd;
   rd.start(gs, n_units, ring, lane);
   int u = 0;
@@ -131,212 +143,234 @@ __device__ void run_stream(const int4* gs, int n_units, Ring* ring, int lane, do
     rd.ensure(u);
     const int4 h = rd.unit(u);
     ++u;
-    const int n = h.z & 0xffff, first = (h.z >> 16) & 1, ecell = (h.z >> 17) & 1;
+    const int n_pos = h.z & 0xfff, n_neg = (h.z >> 12) & 0xfff, first = (h.z >> 24) & 1, ecell = (h.z >> 25) & 1;
     const int meta = h.w;
     const int ps = meta & 63, qs = (meta >> 6) & 63, ti = ((meta >> 12) & 7) * 8, tj = ((meta >> 15) & 7) * 8;
     const int diag = (meta >> 18) & 1;
-    TileLane T;
-    {
-      const int ai = ti + lb, bj = tj + lb;
-      T.a_ok = ai < ps;
-      const bool b_ok = bj < qs;
-      T.b_rhs = diag && bj == qs;
-      T.a_lo = T.a_ok ? la * ps + ai : 0;
-      T.b_lo = T.b_rhs ? la : (b_ok ? la * qs + bj : 0);
-      T.b_any = b_ok || T.b_rhs;
-    }
-    // my two accumulator elements: (i, j) and (i, j + 1)
+    const bool b_rhs = diag && tj + lb == qs;
+    const uint32_t a_lane = oa + 8u * (unsigned)(la * ps + ti + lb);
+    const uint32_t b_lane = oa + 8u * (unsigned)(b_rhs ? la : la * qs + tj + lb);
+    // my two accumulator elements: (i, j) and (i, j + 1); address 0 = not stored
     const int i = ti + lb, j = tj + 2 * la;
-    double* p0 = nullptr;
-    double* p1 = nullptr;
+    uint32_t p0 = 0, p1 = 0;
     if (i < ps) {
       if (ecell) {
-        if (j < qs) p0 = OA + h.x + i * qs + j;
-        else if (diag && j == qs) p0 = OA + h.y + i;
-        if (j + 1 < qs) p1 = OA + h.x + i * qs + j + 1;
-        else if (diag && j + 1 == qs) p1 = OA + h.y + i;
+        if (j < qs) p0 = oa + 8u * (unsigned)(h.x + i * qs + j);
+        else if (diag && j == qs) p0 = oa + 8u * (unsigned)(h.y + i);
+        if (j + 1 < qs) p1 = oa + 8u * (unsigned)(h.x + i * qs + j + 1);
+        else if (diag && j + 1 == qs) p1 = oa + 8u * (unsigned)(h.y + i);
       } else {
         const int stride = qs + diag;
-        if (j < stride) p0 = ACC + h.x + i * stride + j;
-        if (j + 1 < stride) p1 = ACC + h.x + i * stride + j + 1;
+        if (j < stride) p0 = acc + 8u * (unsigned)(h.x + i * stride + j);
+        if (j + 1 < stride) p1 = acc + 8u * (unsigned)(h.x + i * stride + j + 1);
       }
     }
-    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;  // + terms
+    double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;  // - terms
     if (!first) {
-      if (p0) c0 = *p0;
-      if (p1) c1 = *p1;
+      if (p0) c0 = lds_f64(p0);
+      if (p1) c1 = lds_f64(p1);
     }
-    for (int t = 0; t < n; t += 4) {
-      rd.ensure(u + 1);
-      const int4 r0 = rd.unit(u), r1 = rd.unit(u + 1);
-      u += 2;
-      const int w0[4] = {r0.x, r0.z, r1.x, r1.z}, w1[4] = {r0.y, r0.w, r1.y, r1.w};
-      double av[4], bv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ok = w1[e] >= 0 && la <= ((w1[e] >> 16) & 3);
-        const double a = (ok && T.a_ok) ? OA[T.a_lo + (w0[e] & 0xffff)] : 0.0;
-        av[e] = (w1[e] & (1 << 18)) ? -a : a;
-        bv[e] = (ok && T.b_any) ? OA[T.b_lo + (T.b_rhs ? (w1[e] & 0xffff) : ((unsigned)w0[e] >> 16))] : 0.0;
-      }
-      dmma884(c0, c1, av[0], bv[0]);
-      dmma884(d0, d1, av[1], bv[1]);
-      dmma884(c0, c1, av[2], bv[2]);
-      dmma884(d0, d1, av[3], bv[3]);
-    }
-    if (p0) *p0 = c0 + d0;
-    if (p1) *p1 = c1 + d1;
+#define SWGN_GROUP(X0, X1, Y0, Y1)                                                                         \
+  {                                                                                                        \
+    rd.ensure(u + 1);                                                                                      \
+    const int4 r0 = rd.unit(u), r1 = rd.unit(u + 1);                                                       \
+    u += 2;                                                                                                \
+    const int w0[4] = {r0.x, r0.z, r1.x, r1.z}, w1[4] = {r0.y, r0.w, r1.y, r1.w};                          \
+    double av[4], bv[4];                                                                                   \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
+      const double a = lds_f64(a_lane + 8u * ((unsigned)w0[e] & 0xffffu));                                 \
+      av[e] = (w1[e] & lmask) ? a : 0.0;                                                                   \
+      bv[e] = lds_f64(b_lane + 8u * (b_rhs ? ((unsigned)w1[e] & 0xffffu) : ((unsigned)w0[e] >> 16)));      \
+    }                                                                                                      \
+    dmma884(X0, X1, av[0], bv[0]);                                                                         \
+    dmma884(Y0, Y1, av[1], bv[1]);                                                                         \
+    dmma884(X0, X1, av[2], bv[2]);                                                                         \
+    dmma884(Y0, Y1, av[3], bv[3]);                                                                         \
+  }
+    for (int t = 0; t < n_pos; t += 4) SWGN_GROUP(c0, c1, d0, d1)
+    for (int t = 0; t < n_neg; t += 4) SWGN_GROUP(e0, e1, f0, f1)
+#undef SWGN_GROUP
+    if (p0) sts_f64(p0, (c0 + d0) - (e0 + f0));
+    if (p1) sts_f64(p1, (c1 + d1) - (e1 + f1));
   }
   rd.finish();
 }
 
-// ---- phase A, landmark-like chunks: one thread per chunk ---------------------------------------------------------
-// L L' = D^2 + sum E'E (lower L, row-major), w_g = L^-1 sum E'b.  A non-positive pivot poisons the chunk with NaN so
-// that the reduced factorisation fails and the caller retries with a larger mu (dogleg_strategy.cc:589).
+// ---- landmark-like chunks (e-size <= 3, every f-block fed by one row, <= 2 residuals per row): 8 lanes per chunk ----
+// Lanes stride over the chunk's rows: partial E'E / E'b in registers, a 3-step shuffle reduction inside the group,
+// then every lane holds L L' = D^2 + sum E'E and w_g = L^-1 sum E'b (computed redundantly) and writes
+// W_f = (L^-1 E') F_f for its own rows.  A non-positive pivot poisons the chunk with NaN so that the reduced
+// factorisation fails and the caller retries with a larger mu (dogleg_strategy.cc:589).
 template <int ES>
-__device__ __forceinline__ void tchunk_factor(const int4 rec, const int32_t* pkg, double* OA, const double* lmd) {
-  const int n_rows = rec.y & 0xffff;
-  const int2* crow = reinterpret_cast<const int2*>(pkg + rec.x);
-  double ete[ES][ES], g[ES];
+__device__ __noinline__ void tchunk_group(bool active, const int4 rec, const int32_t* pkg, const int32_t* textra, double* OA,
+                                             const double* lmd, int l8) {
+  constexpr int NT = ES * (ES + 1) / 2;
+  const int n_rows = active ? (rec.y & 0xffff) : 0;
+  const int4* rows = reinterpret_cast<const int4*>(pkg + rec.x);
+  double ete[NT], g[ES];
 #pragma unroll
-  for (int i = 0; i < ES; ++i) {
-    g[i] = 0.0;
+  for (int k = 0; k < NT; ++k) ete[k] = 0.0;
 #pragma unroll
-    for (int j = 0; j < ES; ++j) ete[i][j] = 0.0;
-    const double dd = lmd[rec.w + i];
-    ete[i][i] = dd * dd;
-  }
-  for (int r = 0; r < n_rows; ++r) {  // ChunkDiagonalBlockAndGradient, schur_eliminator_impl.h:444-507
-    const int2 cr = crow[r];
-    const double* E = OA + (cr.x & 0xffff);
-    const double* bb = OA + cr.y;
-    const int nres = cr.x >> 16;
-    for (int rr = 0; rr < nres; ++rr) {
+  for (int i = 0; i < ES; ++i) g[i] = 0.0;
+  for (int r = l8; r < n_rows; r += 8) {  // ChunkDiagonalBlockAndGradient, schur_eliminator_impl.h:444-507
+    const int4 rr = rows[r];
+    const double* E = OA + (rr.x & 0xffff);
+    const double* bb = OA + rr.y;
+    const int nres = rr.x >> 16;
+    for (int q = 0; q < nres; ++q) {
       double e[ES];
 #pragma unroll
-      for (int i = 0; i < ES; ++i) e[i] = E[rr * ES + i];
-      const double br = bb[rr];
+      for (int i = 0; i < ES; ++i) e[i] = E[q * ES + i];
+      const double br = bb[q];
+      int k = 0;
 #pragma unroll
       for (int i = 0; i < ES; ++i) {
         g[i] += e[i] * br;
 #pragma unroll
-        for (int j = i; j < ES; ++j) ete[i][j] += e[i] * e[j];
+        for (int j = i; j < ES; ++j) ete[k++] += e[i] * e[j];
       }
     }
   }
-  double L[ES][ES];
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k) ete[k] += __shfl_xor_sync(0xffffffffu, ete[k], o);
+#pragma unroll
+    for (int i = 0; i < ES; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
+  }
+  if (!active) return;
+  double A[ES][ES];
+  {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+#pragma unroll
+      for (int j = i; j < ES; ++j) A[i][j] = ete[k++];
+      const double dd = lmd[rec.w + i];
+      A[i][i] += dd * dd;
+    }
+  }
+  double L[ES][ES], inv[ES];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < ES; ++j) {
-    double dj = ete[j][j];
+    double dj = A[j][j];
 #pragma unroll
     for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k];
     if (!(dj > 0.0)) ok = false;
-    dj = sqrt(dj);
-    L[j][j] = dj;
+    inv[j] = rsqrt(dj);  // no divide / square root in the dependent chain: L_jj = d * rsqrt(d), the rest multiplies by 1 / L_jj
+    L[j][j] = dj * inv[j];
 #pragma unroll
     for (int i = j + 1; i < ES; ++i) {
-      double s = ete[j][i];
+      double t = A[j][i];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      L[i][j] = s / dj;
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = t * inv[j];
     }
   }
   if (!ok) {
 #pragma unroll
-    for (int i = 0; i < ES; ++i)
+    for (int i = 0; i < ES; ++i) {
+      inv[i] = nan("");
 #pragma unroll
       for (int j = 0; j <= i; ++j) L[i][j] = nan("");
+    }
   }
-  double* fac = OA + (rec.z & 0xffff);
+  if (l8 == 0) {
+    double* fac = OA + (rec.z & 0xffff);
 #pragma unroll
-  for (int i = 0; i < ES; ++i)
+    for (int i = 0; i < ES; ++i)
 #pragma unroll
-    for (int j = 0; j < ES; ++j) fac[i * ES + j] = (j <= i) ? L[i][j] : 0.0;
-  double* gp = OA + ((unsigned)rec.z >> 16);
-  double wg[ES];
+      for (int j = 0; j < ES; ++j) fac[i * ES + j] = (j <= i) ? L[i][j] : 0.0;
+    double* gp = OA + ((unsigned)rec.z >> 16);
+    double wg[ES];
 #pragma unroll
-  for (int i = 0; i < ES; ++i) {
-    double s = g[i];
+    for (int i = 0; i < ES; ++i) {
+      double t = g[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= L[i][k] * wg[k];
-    wg[i] = s / L[i][i];
-    gp[i] = wg[i];
+      for (int k = 0; k < i; ++k) t -= L[i][k] * wg[k];
+      wg[i] = t * inv[i];
+      gp[i] = wg[i];
+    }
+  }
+  for (int r = l8; r < n_rows; r += 8) {
+    const int4 rr = rows[r];
+    const int n_fcells = (rr.w >> 8) & 0xff;
+    if (n_fcells == 0) continue;
+    const double* E = OA + (rr.x & 0xffff);
+    const int nres = rr.x >> 16;
+    double v0[ES], v1[ES];  // L^-1 E' for the (<= 2) residual rows
+#pragma unroll
+    for (int i = 0; i < ES; ++i) {
+      double s0 = E[i], s1 = nres > 1 ? E[ES + i] : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+        s0 -= L[i][k] * v0[k];
+        s1 -= L[i][k] * v1[k];
+      }
+      v0[i] = s0 * inv[i];
+      v1[i] = s1 * inv[i];
+    }
+    for (int q = 0; q < n_fcells; ++q) {
+      int f_oa, w_oa, fs;
+      if (q == 0) {
+        f_oa = rr.z & 0xffff;
+        w_oa = (unsigned)rr.z >> 16;
+        fs = rr.w & 0xff;
+      } else {
+        const int4 x = reinterpret_cast<const int4*>(textra)[((unsigned)rr.w >> 16) + q - 1];
+        f_oa = x.x;
+        w_oa = x.y;
+        fs = x.z;
+      }
+      const double* F = OA + f_oa;
+      double* Wf = OA + w_oa;
+      for (int j = 0; j < fs; ++j) {
+        const double f0 = F[j], f1 = nres > 1 ? F[fs + j] : 0.0;
+#pragma unroll
+        for (int i = 0; i < ES; ++i) Wf[i * fs + j] = v0[i] * f0 + v1[i] * f1;
+      }
+    }
   }
 }
 
-// ---- phase B, landmark-like chunks: one thread per row, W_f = (L^-1 E') F_f, written once --------------------------
-template <int ES>
-__device__ __forceinline__ void trow_w(const int4 r0, const int4 r1, const int32_t* pkg, double* OA) {
-  const double* E = OA + r0.x;
-  const double* Lp = OA + r0.z;
-  const int nres = r0.y & 0xff, n_fcells = r0.y >> 16;
-  double L[ES][ES];
-#pragma unroll
-  for (int i = 0; i < ES; ++i)
-#pragma unroll
-    for (int k = 0; k <= i; ++k) L[i][k] = Lp[i * ES + k];
-  double v0[ES], v1[ES];  // L^-1 E' for the (<= 2) residual rows
-#pragma unroll
-  for (int i = 0; i < ES; ++i) {
-    double s0 = E[i], s1 = nres > 1 ? E[ES + i] : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) {
-      s0 -= L[i][k] * v0[k];
-      s1 -= L[i][k] * v1[k];
-    }
-    v0[i] = s0 / L[i][i];
-    v1[i] = s1 / L[i][i];
-  }
-  const int4* extra = reinterpret_cast<const int4*>(pkg + r0.w);
-  for (int q = 0; q < n_fcells; ++q) {
-    const int4 fc = q == 0 ? r1 : extra[q - 1];
-    const double* F = OA + fc.x;
-    double* Wf = OA + fc.y;
-    const int fs = fc.z;
-    for (int j = 0; j < fs; ++j) {
-      const double f0 = F[j], f1 = nres > 1 ? F[fs + j] : 0.0;
-#pragma unroll
-      for (int i = 0; i < ES; ++i) Wf[i * fs + j] = v0[i] * f0 + v1[i] * f1;
-    }
-  }
-}
-
-// ---- phase B, all other chunks: one warp per chunk, in place in the operand area -----------------------------------
-// in: raw E'E (upper part) at fac, raw E'F_f in the slot blocks, raw E'b in the g slot.  out: lower L at fac (upper
-// part zero), W_f = L^-1 E'F_f, w_g = L^-1 E'b.
-__device__ void mchunk_warp(const int4 m0, const int4 m1, const int32_t* pkg, double* OA, const double* lmd) {
+// ---- all other chunks (speed-bias blocks, epoch clocks ...): one warp per chunk, in place in the operand area --------
+// in: raw E'E (upper part) at fac, raw E'F_f in the slot blocks, raw E'b in the g slot (phase A, tensor pipe).
+// out: lower L at fac (upper part zero), W_f = L^-1 E'F_f, w_g = L^-1 E'b.
+// Right-looking Cholesky on the upper triangle (lanes over the trailing elements, rsqrt pivots: no divide or square root
+// in the dependent chain), then the lanes own the columns of [E'F ... | E'b] and forward-substitute them.  Compact loops
+// on purpose: this runs on one or two warps per batch and must stay resident in the instruction cache.
+__device__ __noinline__ void mchunk_warp(const int4 m0, const int4 m1, const int32_t* pkg, double* OA, const double* lmd) {
   const int lane = threadIdx.x & 31;
   const int es = m0.x, epos = m0.y, ns1 = m0.w;
-  double* ete = OA + m0.z;  // es x es row-major
+  double* U = OA + m0.z;  // es x es row-major; upper part = E'E
   const int2* slots = reinterpret_cast<const int2*>(pkg + m1.x);
   if (lane < es) {
     const double dd = lmd[epos + lane];
-    ete[lane * es + lane] += dd * dd;
+    U[lane * es + lane] += dd * dd;
   }
   __syncwarp();
   bool ok = true;
   for (int j = 0; j < es; ++j) {
-    double dj = ete[j * es + j];
-    for (int k = 0; k < j; ++k) dj -= ete[j * es + k] * ete[j * es + k];
+    const double dj = U[j * es + j];
     if (!(dj > 0.0)) ok = false;
-    dj = sqrt(dj);
+    const double dinv = rsqrt(dj);
     __syncwarp();
-    if (lane == 0) ete[j * es + j] = dj;
-    for (int i = j + 1 + lane; i < es; i += 32) {
-      double s = ete[j * es + i];
-      for (int k = 0; k < j; ++k) s -= ete[i * es + k] * ete[j * es + k];
-      ete[i * es + j] = s / dj;
+    // row j of U' (= column j of L): scale by 1 / L_jj; the diagonal keeps 1 / L_jj until the end
+    for (int i = j + lane; i < es; i += 32) U[j * es + i] = i == j ? dinv : U[j * es + i] * dinv;
+    __syncwarp();
+    // trailing update of the upper triangle: u_ik -= l_ij l_kj, j < i <= k
+    const int m = es - j - 1;
+    for (int e = lane; e < m * m; e += 32) {
+      const int a = e / m, c = e - a * m;
+      if (c < a) continue;
+      const int i = j + 1 + a, k = j + 1 + c;
+      U[i * es + k] -= U[j * es + i] * U[j * es + k];
     }
     __syncwarp();
   }
-  for (int k = lane; k < es * es; k += 32) {
-    const int i = k / es, j = k - i * es;
-    if (!ok) ete[k] = nan("");
-    else if (j > i) ete[k] = 0.0;
-  }
-  __syncwarp();
-  // forward substitution on every column of every slot block and on g, columns flattened over the lanes
+  // forward substitution, one column of [E'F ... | E'b] per lane: t_i = (b_i - sum_k<i l_ik t_k) / l_ii, l_ik = U[k][i]
   int total = 0;
   for (int s = 0; s < ns1; ++s) total += slots[s].y;
   for (int c = lane; c < total; c += 32) {
@@ -346,13 +380,26 @@ __device__ void mchunk_warp(const int4 m0, const int4 m1, const int32_t* pkg, do
       ++s;
     }
     const int2 sl = slots[s];
-    const int fs = sl.y, j = c - c0;
-    double* B = OA + sl.x;
+    const int fs = sl.y;
+    double* B = OA + sl.x + (c - c0);
     for (int i = 0; i < es; ++i) {
-      double t = B[i * fs + j];
-      for (int k = 0; k < i; ++k) t -= ete[i * es + k] * B[k * fs + j];
-      B[i * fs + j] = t / ete[i * es + i];
+      double t = B[i * fs];
+      for (int k = 0; k < i; ++k) t -= U[k * es + i] * B[k * fs];
+      B[i * fs] = ok ? t * U[i * es + i] : nan("");
     }
+  }
+  __syncwarp();
+  // U' -> L in place: transpose the strict upper part into the lower part, diagonal back to L_ii, upper part zero
+  for (int e = lane; e < es * es; e += 32) {
+    const int i = e / es, k = e - i * es;
+    if (k > i) U[k * es + i] = U[i * es + k];
+  }
+  __syncwarp();
+  for (int e = lane; e < es * es; e += 32) {
+    const int i = e / es, k = e - i * es;
+    if (!ok) U[e] = nan("");
+    else if (k > i) U[e] = 0.0;
+    else if (k == i) U[e] = 1.0 / U[e];
   }
   __syncwarp();
 }
@@ -385,6 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
   const int scap = d.sb_jcap + d.sb_rcap;
   double* OA = reinterpret_cast<double*>(sec0 + 2 * seccap);
   double* ACC = OA + 2 * scap + d.sb_ecap + d.sb_fcap;
+  const uint32_t oa_s = smem_u32(OA), acc_s = smem_u32(ACC);
+  // operand loads of the MMA runs are not predicated on block shape: whatever they read beyond a block must be finite
+  for (int k = tid; k < (2 * scap + d.sb_ecap + d.sb_fcap + d.sb_acc) / 2; k += kThreads) reinterpret_cast<double2*>(OA)[k] = make_double2(0.0, 0.0);
   const int32_t* ghdr = v.I(I_SB_HDR);
   const int32_t* grec = v.I(I_SB_REC);
   for (int k = tid; k < SB_HDR_INTS * d.sb_nbatch; k += kThreads) hdr[k] = ghdr[k];
@@ -393,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  fence_async_smem();  // the zero fill above is ordered before the bulk copies that land in the same memory
   __syncthreads();
   const double* gJ = v.W(W_JAC);
   const double* gR = v.W(W_RES);
@@ -411,6 +462,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
     if (runs) prefetch_l2_bulk(grec + h[0] + h[15], runs);
   };
   if (tid == 0) load_batch(0);
+  long long t_wait = 0, t_a = 0, t_b = 0, t_c = 0, t_prev = dbg ? clock64() : 0;
+#define SWGN_LAP(acc) do { if (dbg && tid == 0) { const long long t_ = clock64(); acc += t_ - t_prev; t_prev = t_; } } while (0)
 
   for (int k = 0; k < d.sb_nbatch; ++k) {
     const int s = k & 1;
@@ -418,40 +471,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
     const int32_t* pkg = sec0 + s * seccap;
     if (tid == 0 && k + 1 < d.sb_nbatch) load_batch(k + 1);  // stage (k + 1) & 1 was released by the barrier closing batch k - 1
     mbar_wait(&bars[s], (unsigned)((k >> 1) & 1));
+    SWGN_LAP(t_wait);
     const int4* gruns = reinterpret_cast<const int4*>(grec + h[0]);
-    // ---- A
+    // ---- A: landmark-like chunks start to finish (8 lanes each); raw products of the other chunks on the tensor pipe
     {
       const int n_tchunk = h[10];
-      const int4* tch = reinterpret_cast<const int4*>(pkg + (h[13] & 0xffff));
-      for (int c = tid; c < n_tchunk; c += kThreads) {
-        const int4 rec = tch[c];
-        const int es = rec.y >> 16;
-        if (es == 3) tchunk_factor<3>(rec, pkg, OA, lmd);
-        else if (es == 1) tchunk_factor<1>(rec, pkg, OA, lmd);
-        else tchunk_factor<2>(rec, pkg, OA, lmd);
+      const int4* tch = reinterpret_cast<const int4*>(pkg + h[13]);
+      const int32_t* textra = pkg + h[11];
+      for (int c0 = 4 * wid; c0 < n_tchunk; c0 += 4 * SB_WARPS) {
+        const int c = c0 + (lane >> 3);
+        const bool active = c < n_tchunk;
+        const int4 rec = active ? tch[c] : make_int4(0, 3 << 16, 0, 0);
+        // the shuffles of the group reduction need the whole warp on one path: the e-sizes present in the warp's
+        // four chunks take turns
+        for (int es = 3; es >= 1; --es) {
+          const bool mine = active && (rec.y >> 16) == es;
+          if (!__any_sync(0xffffffffu, mine)) continue;
+          if (es == 3) tchunk_group<3>(mine, rec, pkg, textra, OA, lmd, lane & 7);
+          else if (es == 1) tchunk_group<1>(mine, rec, pkg, textra, OA, lmd, lane & 7);
+          else tchunk_group<2>(mine, rec, pkg, textra, OA, lmd, lane & 7);
+        }
       }
       const int p0 = pkg[wid], p1 = pkg[wid + 1];
-      run_stream(gruns + (p0 >> 2), (p1 - p0) >> 2, rings + wid, lane, OA, ACC);
+      run_stream(gruns + (p0 >> 2), (p1 - p0) >> 2, rings + wid, lane, oa_s, acc_s);
     }
-    __syncthreads();
-    // ---- B
-    {
-      const int n_mchunk = h[12];
+    const int n_mchunk = h[12];
+    if (n_mchunk > 0) {  // (uniform over the CTA)
+      __syncthreads();
+      if (dbg && tid == 0) {
+        const long long t_ = clock64();
+        long long* pb = b.debug + 8 * (size_t)(2 * b.n_windows + w);
+        if (k == 2) pb[4] = t_ - t_prev;
+        if (k == 10) pb[5] = t_ - t_prev;
+      }
+      SWGN_LAP(t_a);
+      // ---- B: factor + forward substitution of the other chunks
       const int4* mch = reinterpret_cast<const int4*>(pkg + h[14]);
       for (int c = wid; c < n_mchunk; c += SB_WARPS) mchunk_warp(mch[2 * c], mch[2 * c + 1], pkg, OA, lmd);
-      const int n_trow = h[11];
-      const int4* trw = reinterpret_cast<const int4*>(pkg + ((unsigned)h[13] >> 16));
-      // rows from the far end: the warps busy with the chunks above get the fewest
-      for (int c = kThreads - 1 - tid; c < n_trow; c += kThreads) {
-        const int4 r0 = trw[2 * c], r1 = trw[2 * c + 1];
-        const int es = (r0.y >> 8) & 0xff;
-        if (es == 3) trow_w<3>(r0, r1, pkg, OA);
-        else if (es == 1) trow_w<1>(r0, r1, pkg, OA);
-        else trow_w<2>(r0, r1, pkg, OA);
-      }
     }
     fence_async_smem();  // the W / factor segments written above are read by the bulk stores below
     __syncthreads();
+    if (dbg && tid == 0) {
+      const long long t_ = clock64();
+      long long* pb = b.debug + 8 * (size_t)(2 * b.n_windows + w);
+      if (k == 2) pb[6] = t_ - t_prev;
+      if (k == 10) pb[7] = t_ - t_prev;
+    }
+    SWGN_LAP(t_b);
     // ---- E-buffer and chunk-factor segments to HBM (k_backsub), overlapped with C
     if (tid == 0) {
       double* wb = OA + 2 * scap;
@@ -462,12 +528,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
     // ---- C
     {
       const int p0 = pkg[SB_WARPS + 1 + wid], p1 = pkg[SB_WARPS + 2 + wid];
-      run_stream(gruns + (p0 >> 2), (p1 - p0) >> 2, rings + wid, lane, OA, ACC);
+      run_stream(gruns + (p0 >> 2), (p1 - p0) >> 2, rings + wid, lane, oa_s, acc_s);
     }
     if (tid == 0) bulk_wait_read0();  // the next batch overwrites the W / factor segments
     __syncthreads();
+    if (dbg && tid == 0) {  // per-batch phase times of four sample batches (development aid)
+      const long long t_ = clock64();
+      long long* pb = b.debug + 8 * (size_t)(2 * b.n_windows + w);
+      if (k == 2) pb[0] = t_ - t_prev;
+      if (k == 10) pb[1] = t_ - t_prev;
+      if (k == d.sb_nbatch - 3) pb[2] = t_ - t_prev;
+      if (k == d.sb_nbatch - 2) pb[3] = t_ - t_prev;
+    }
+    SWGN_LAP(t_c);
   }
   SWGN_STAMP(1);
+  if (dbg && tid == 0) {
+    dbg[2] = t_wait;
+    dbg[3] = t_a;
+    dbg[4] = t_b;
+    dbg[5] = t_c;
+  }
   // ---- write S: rows of the upper triangle + rhs column, zeros where no block cell exists.  Lookup tables in the
   // (now idle) section / operand area: block and offset-in-block of every f tangent index, block sizes, cell map.
   {
@@ -511,7 +592,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
       }
     }
   }
-  SWGN_STAMP(5);
   if (dbg) {
     __syncthreads();
     SWGN_STAMP(6);
@@ -534,6 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_schur_stream(DeviceBatch b, int
     st->chol_ok = 0;
   }
 #undef SWGN_STAMP
+#undef SWGN_LAP
 }
 
 void launch_schur_stream(const DeviceBatch& b, int only_window, cudaStream_t s) {
@@ -544,7 +625,16 @@ void launch_schur_stream(const DeviceBatch& b, int only_window, cudaStream_t s) 
 cudaError_t configure_schur_stream(const DeviceBatch& b) {
   if (b.sb_windows <= 0) return cudaSuccess;
   if (b.sb_smem > 227 * 1024) return cudaErrorInvalidValue;
-  return cudaFuncSetAttribute(k_schur_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.sb_smem);
+  // the attribute is per function and device: batches of every size share it, so it only ever grows
+  static std::mutex mu;
+  static unsigned granted[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && b.sb_smem <= granted[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(k_schur_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.sb_smem);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev] = b.sb_smem;
+  return e;
 }
 
 }  // namespace swgn

@@ -13,7 +13,7 @@ namespace swgn {
 
 // result of build_stream_plan (plan_stream.cpp): sizes of the on-chip layout of the streamed Schur elimination
 struct StreamPlanInfo {
-  int ok = 0, nbatch = 0, acc = 0, jcap = 0, rcap = 0, ecap = 0, fcap = 0, reccap = 0, n_fb = 0;
+  int ok = 0, fits = 0, nbatch = 0, acc = 0, jcap = 0, rcap = 0, ecap = 0, fcap = 0, reccap = 0, n_fb = 0;
 };
 
 struct WindowPlan {

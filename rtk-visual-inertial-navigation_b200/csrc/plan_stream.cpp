@@ -199,7 +199,7 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
         amap[cid(p, q)] = off;
         off += col_size[p] * (col_size[q] + (p == q ? 1 : 0));
       }
-    sb.acc = al2(off);
+    sb.acc = std::max(256, al2(off));  // (unpredicated operand loads may run up to ~200 doubles past the operand area)
   }
   // first touch of every accumulator tile: the run that sees it first starts from zero instead of reading it
   std::vector<int> tile_base((size_t)n_fb * n_fb, -1);
@@ -234,7 +234,8 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
     term_lists.clear();
     jobs_a.clear();
     jobs_c.clear();
-    std::vector<int32_t> sec_tchunk, sec_crow, sec_trow, sec_textra, sec_mchunk, sec_slot;
+    std::vector<int32_t> sec_tchunk, sec_trow, sec_textra, sec_mchunk, sec_slot;
+    bool too_many = false;
     for (int ui = bt.u0; ui < bt.u1; ++ui) {
       const Unit& u = units[ui];
       // F'F terms of the rows
@@ -265,20 +266,18 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
                                               oaW(I[I_CHUNK_G][ch]) + e0, std::min(4u, (uint32_t)es - e0), 1u}});
         }
       if (u.simple) {
-        // class T: thread per chunk (factor, w_g), thread per row (W)
-        const int32_t rec[4] = {(int32_t)(sec_crow.size() / 2), (u.r1 - u.r0) | (es << 16), (int32_t)(oaF(I[I_CHUNK_FAC][ch]) | (oaW(I[I_CHUNK_G][ch]) << 16)),
+        // class T: a group of 8 lanes per chunk -- partial E'E / E'b per lane, shuffle reduction, L and w_g, then W row by row
+        const int32_t rec[4] = {(int32_t)(sec_trow.size() / 4), (u.r1 - u.r0) | (es << 16), (int32_t)(oaF(I[I_CHUNK_FAC][ch]) | (oaW(I[I_CHUNK_G][ch]) << 16)),
                                 col_pos[ecol]};
         sec_tchunk.insert(sec_tchunk.end(), rec, rec + 4);
         for (int r = u.r0; r < u.r1; ++r) {
           const int c0 = row_c0(r), nfc = row_c1(r) - c0 - 1, nres = I[I_ROW_NRES][r];
-          sec_crow.push_back((int32_t)(oaJ(I[I_CELL_VAL][c0]) | ((uint32_t)nres << 16)));
-          sec_crow.push_back((int32_t)oaR(I[I_ROW_RES][r]));
-          if (nfc <= 0) continue;
-          const int32_t r0[4] = {(int32_t)oaJ(I[I_CELL_VAL][c0]), nres | (es << 8) | (nfc << 16), (int32_t)oaF(I[I_CHUNK_FAC][ch]),
-                                 (int32_t)(sec_textra.size() / 4)};
-          const int32_t r1[4] = {(int32_t)oaJ(I[I_CELL_VAL][c0 + 1]), (int32_t)oaW(I[I_CELL_SLOT][c0 + 1]), col_size[I[I_CELL_COL][c0 + 1]], 0};
-          sec_trow.insert(sec_trow.end(), r0, r0 + 4);
-          sec_trow.insert(sec_trow.end(), r1, r1 + 4);
+          const uint32_t f_oa = nfc > 0 ? oaJ(I[I_CELL_VAL][c0 + 1]) : 0u, w_oa = nfc > 0 ? oaW(I[I_CELL_SLOT][c0 + 1]) : 0u;
+          const int fs = nfc > 0 ? col_size[I[I_CELL_COL][c0 + 1]] : 0;
+          if (nfc > 255 || sec_textra.size() / 4 > 0xffff) too_many = true;
+          const int32_t rr[4] = {(int32_t)(oaJ(I[I_CELL_VAL][c0]) | ((uint32_t)nres << 16)), (int32_t)oaR(I[I_ROW_RES][r]), (int32_t)(f_oa | (w_oa << 16)),
+                                 (int32_t)((uint32_t)fs | ((uint32_t)std::max(nfc, 0) << 8) | ((uint32_t)(sec_textra.size() / 4) << 16))};
+          sec_trow.insert(sec_trow.end(), rr, rr + 4);
           for (int c = c0 + 2; c < row_c1(r); ++c) {
             const int32_t x[4] = {(int32_t)oaJ(I[I_CELL_VAL][c]), (int32_t)oaW(I[I_CELL_SLOT][c]), col_size[I[I_CELL_COL][c]], 0};
             sec_textra.insert(sec_textra.end(), x, x + 4);
@@ -382,15 +381,14 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
       return off;
     };
     const int off_tchunk = append(sec_tchunk);
-    const int off_crow = append(sec_crow);
     const int off_trow = append(sec_trow);
     const int off_textra = append(sec_textra);
     const int off_mchunk = append(sec_mchunk);
     const int off_slot = append(sec_slot);
     // absolute int offsets of the nested lists
-    for (size_t k = 0; k < sec_tchunk.size() / 4; ++k) pk[off_tchunk + 4 * k] = off_crow + 2 * pk[off_tchunk + 4 * k];
-    for (size_t k = 0; k < sec_trow.size() / 8; ++k) pk[off_trow + 8 * k + 3] = off_textra + 4 * pk[off_trow + 8 * k + 3];
+    for (size_t k = 0; k < sec_tchunk.size() / 4; ++k) pk[off_tchunk + 4 * k] = off_trow + 4 * pk[off_tchunk + 4 * k];
     for (size_t k = 0; k < sec_mchunk.size() / 8; ++k) pk[off_mchunk + 8 * k + 4] = off_slot + 2 * pk[off_mchunk + 8 * k + 4];
+    bool too_long = false;
     auto deal = [&](const std::vector<Job>& jobs, int ptr0) {
       std::vector<size_t> idx(jobs.size());
       std::iota(idx.begin(), idx.end(), 0);
@@ -400,25 +398,32 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
       for (size_t j : idx) {
         const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
         mine[wmin].push_back(j);
-        load[wmin] += (jobs[j].terms->size() + 3) / 4 * 4 + 6;
+        load[wmin] += (jobs[j].terms->size() + 3) / 4 * 4 + 8;
       }
       for (int wv = 0; wv < SB_WARPS; ++wv) {
         pk[ptr0 + wv] = (int32_t)pk.size();
         for (size_t j : mine[wv]) {
           const Job& jb = jobs[j];
-          const size_t nt = jb.terms->size(), np = (nt + 3) / 4 * 4;
+          // + terms first, then - terms, each list padded to a multiple of 4 (a group of MMAs) with all-zero records
+          size_t n_sign[2] = {0, 0};
+          for (const Term& t : *jb.terms) ++n_sign[t.sign];
+          const size_t np[2] = {(n_sign[0] + 3) / 4 * 4, (n_sign[1] + 3) / 4 * 4};
+          if (np[0] > 0xfff || np[1] > 0xfff) too_long = true;
           pk.push_back(jb.dst);
           pk.push_back(jb.dst2);
-          pk.push_back((int32_t)(np | ((size_t)jb.first << 16) | ((size_t)jb.ecell << 17)));
+          pk.push_back((int32_t)(np[0] | (np[1] << 12) | ((size_t)jb.first << 24) | ((size_t)jb.ecell << 25)));
           pk.push_back(jb.meta);
-          for (size_t e = 0; e < np; ++e) {
-            if (e < nt) {
-              const Term& t = (*jb.terms)[e];
+          for (uint32_t sg = 0; sg < 2; ++sg) {
+            size_t e = 0;
+            for (const Term& t : *jb.terms) {
+              if (t.sign != sg) continue;
               pk.push_back((int32_t)(t.a | (t.b << 16)));
-              pk.push_back((int32_t)(t.b2 | ((t.m - 1) << 16) | (t.sign << 18)));
-            } else {
+              pk.push_back((int32_t)(t.b2 | (((1u << t.m) - 1u) << 16)));  // row mask: rows beyond the slab read as zero
+              ++e;
+            }
+            for (; e < np[sg]; ++e) {
               pk.push_back(0);
-              pk.push_back((int32_t)0x80000000u);
+              pk.push_back(0);
             }
           }
         }
@@ -428,12 +433,11 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
     const int sec_len = (int)pk.size();  // what precedes goes to shared memory with the batch; the run streams are read from L2
     deal(jobs_a, 0);
     deal(jobs_c, SB_WARPS + 1);
-    for (const Job& jb : jobs_c)
-      if (jb.terms->size() > 0xfff0) return;  // run length field
+    if (too_long) return;  // run length fields
     const int32_t hdr[SB_HDR_INTS] = {(int32_t)REC.size(), (int32_t)pk.size(), bt.j_src, bt.j_len, bt.r_src, bt.r_len, bt.eb_src, bt.eb_len,
-                                      bt.ef_src, bt.ef_len, (int32_t)(sec_tchunk.size() / 4), (int32_t)(sec_trow.size() / 8),
-                                      (int32_t)(sec_mchunk.size() / 8), off_tchunk | (off_trow << 16), off_mchunk, sec_len};
-    if (off_tchunk > 0xffff || off_trow > 0xffff) return;
+                                      bt.ef_src, bt.ef_len, (int32_t)(sec_tchunk.size() / 4), off_textra,
+                                      (int32_t)(sec_mchunk.size() / 8), off_tchunk, off_mchunk, sec_len};
+    if (too_many) return;
     HDR.insert(HDR.end(), hdr, hdr + SB_HDR_INTS);
     REC.insert(REC.end(), pk.begin(), pk.end());
     reccap = std::max(reccap, sec_len);
@@ -448,8 +452,11 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
   // the write-out of S looks the accumulators up through tables that reuse the section buffers and the operand area
   const size_t tables = sizeof(int32_t) * ((size_t)n_fb * n_fb + (size_t)al4(n_f_total) + 2 * (size_t)al4(n_fb));
   const size_t scratch = sizeof(int32_t) * 2 * (size_t)al4(reccap) + sizeof(double) * (size_t)(2 * (jcap + rcap) + ecap + fcap);
-  static const bool disabled = std::getenv("SWGN_SCHUR_STREAM") && std::atoi(std::getenv("SWGN_SCHUR_STREAM")) == 0;
-  sb.ok = !disabled && sb.nbatch > 0 && sb.nbatch <= 1024 && smem <= (size_t)SB_SMEM_BUDGET && tables <= scratch;
+  // opt-in (SWGN_SCHUR_STREAM=1): on the B200 the streamed kernel cuts the DRAM traffic of the elimination to the
+  // algorithmic bytes but is instruction / latency bound and, as measured, still slower than the gather kernel
+  static const bool enabled = std::getenv("SWGN_SCHUR_STREAM") && std::atoi(std::getenv("SWGN_SCHUR_STREAM")) != 0;
+  sb.fits = sb.nbatch > 0 && sb.nbatch <= 1024 && smem <= (size_t)SB_SMEM_BUDGET && tables <= scratch;
+  sb.ok = enabled && sb.nbatch > 0 && sb.nbatch <= 1024 && smem <= (size_t)SB_SMEM_BUDGET && tables <= scratch;
 }
 
 }  // namespace swgn

@@ -86,18 +86,21 @@ def interpret(graph_p, J, r, D, n_head=0):
         while u < p1:
             dst, dst2, z, meta = (int(x) for x in pkg[u:u + 4])
             u += 4
-            n, first, ecell = z & 0xffff, (z >> 16) & 1, (z >> 17) & 1
+            n_pos, n_neg, first, ecell = z & 0xfff, (z >> 12) & 0xfff, (z >> 24) & 1, (z >> 25) & 1
+            n = n_pos + n_neg
             ps, qs, ti, tj, diag = meta & 63, (meta >> 6) & 63, ((meta >> 12) & 7) * 8, ((meta >> 15) & 7) * 8, (meta >> 18) & 1
-            assert n % 4 == 0
+            assert n_pos % 4 == 0 and n_neg % 4 == 0
             tile = np.zeros((8, 8))
             for t in range(n):
                 w0, w1 = int(pkg[u]) & 0xffffffff, int(pkg[u + 1]) & 0xffffffff
                 u += 2
-                if w1 >> 31:
+                mask = (w1 >> 16) & 15
+                if mask == 0:
+                    assert w0 == 0 and w1 == 0
                     continue
                 n_terms += 1
                 a, bo, b2 = w0 & 0xffff, w0 >> 16, w1 & 0xffff
-                m, sign = ((w1 >> 16) & 3) + 1, -1.0 if (w1 >> 18) & 1 else 1.0
+                m, sign = {1: 1, 3: 2, 7: 3, 15: 4}[mask], 1.0 if t < n_pos else -1.0
                 Am = OA[a:a + m * ps].reshape(m, ps)
                 Bm = OA[bo:bo + m * qs].reshape(m, qs)
                 if diag:
@@ -122,8 +125,8 @@ def interpret(graph_p, J, r, D, n_head=0):
 
     for k, h in enumerate(hdr):
         rec_off, rec_len, j_src, j_len, r_src, r_len, eb_src, eb_len, ef_src, ef_len = (int(x) for x in h[:10])
-        n_tchunk, n_trow, n_mchunk = int(h[10]), int(h[11]), int(h[12])
-        off_tchunk, off_trow, off_mchunk, sec_len = int(h[13]) & 0xffff, int(h[13]) >> 16, int(h[14]), int(h[15])
+        n_tchunk, off_textra, n_mchunk = int(h[10]), int(h[11]), int(h[12])
+        off_tchunk, off_mchunk, sec_len = int(h[13]), int(h[14]), int(h[15])
         assert rec_off % 4 == 0 and rec_len % 4 == 0 and sec_len % 4 == 0 and j_src % 2 == 0 and r_src % 2 == 0
         assert j_len <= jcap and r_len <= rcap and eb_len <= ecap and ef_len <= fcap and sec_len <= info["seccap"]
         pkg = REC[rec_off:rec_off + rec_len]
@@ -133,22 +136,30 @@ def interpret(graph_p, J, r, D, n_head=0):
         OA[s + jcap:s + jcap + r_len] = RES[r_src:r_src + r_len]
         wb, fb = 2 * scap, 2 * scap + ecap
         OA[wb:] = np.nan
-        # A: landmark-like chunks
+        # A: landmark-like chunks (factor, w_g, W row by row)
         for c in range(n_tchunk):
-            crow, y, z, epos = (int(x) for x in pkg[off_tchunk + 4 * c:off_tchunk + 4 * c + 4])
+            trow, y, z, epos = (int(x) for x in pkg[off_tchunk + 4 * c:off_tchunk + 4 * c + 4])
             nrows, es = y & 0xffff, y >> 16
             ete = np.diag(D[epos:epos + es] ** 2)
             g = np.zeros(es)
+            rows = []
             for rr in range(nrows):
-                x0, res = int(pkg[crow + 2 * rr]), int(pkg[crow + 2 * rr + 1])
+                x0, res, fw, w3 = (int(x) & 0xffffffff for x in pkg[trow + 4 * rr:trow + 4 * rr + 4])
                 eo, nres = x0 & 0xffff, x0 >> 16
                 E = OA[eo:eo + nres * es].reshape(nres, es)
                 ete += E.T @ E
                 g += E.T @ OA[res:res + nres]
+                rows.append((E, nres, fw & 0xffff, fw >> 16, w3 & 0xff, (w3 >> 8) & 0xff, w3 >> 16))
             Lm = np.linalg.cholesky(ete)
             fo, go = z & 0xffff, (z >> 16) & 0xffff
             OA[fo:fo + es * es] = Lm.ravel()
             OA[go:go + es] = np.linalg.solve(Lm, g)
+            for E, nres, f_oa, w_oa, fs, nfc, xi in rows:
+                V = np.linalg.solve(Lm, E.T)
+                for q in range(nfc):
+                    fc = (f_oa, w_oa, fs) if q == 0 else tuple(int(x) for x in pkg[off_textra + 4 * (xi + q - 1):off_textra + 4 * (xi + q - 1) + 3])
+                    F = OA[fc[0]:fc[0] + nres * fc[2]].reshape(nres, fc[2])
+                    OA[fc[1]:fc[1] + es * fc[2]] = (V @ F).ravel()
         # A: raw products of the other chunks
         for wv in range(SB_WARPS):
             runs(pkg, int(pkg[wv]), int(pkg[wv + 1]))
@@ -164,18 +175,6 @@ def interpret(graph_p, J, r, D, n_head=0):
                 off, fs = int(pkg[slot0 + 2 * sidx]), int(pkg[slot0 + 2 * sidx + 1])
                 Bm = OA[off:off + es * fs].reshape(es, fs)
                 OA[off:off + es * fs] = np.linalg.solve(Lm, Bm).ravel()
-        # B: rows of the landmark-like chunks
-        for c in range(n_trow):
-            r0 = [int(x) for x in pkg[off_trow + 8 * c:off_trow + 8 * c + 4]]
-            r1 = [int(x) for x in pkg[off_trow + 8 * c + 4:off_trow + 8 * c + 8]]
-            nres, es, nfc = r0[1] & 0xff, (r0[1] >> 8) & 0xff, r0[1] >> 16
-            E = OA[r0[0]:r0[0] + nres * es].reshape(nres, es)
-            Lm = OA[r0[2]:r0[2] + es * es].reshape(es, es)
-            V = np.linalg.solve(Lm, E.T)
-            for q in range(nfc):
-                fc = r1 if q == 0 else [int(x) for x in pkg[r0[3] + 4 * (q - 1):r0[3] + 4 * q]]
-                F = OA[fc[0]:fc[0] + nres * fc[2]].reshape(nres, fc[2])
-                OA[fc[1]:fc[1] + es * fc[2]] = (V @ F).ravel()
         for x in range(eb_len):
             EBUF[eb_src + x] = OA[wb + x]
         for x in range(ef_len):
