@@ -1,19 +1,30 @@
 #!/bin/sh
 # TEST INFRASTRUCTURE.  Builds oracle/_ref/libref_gnss.so from the reference's OWN sources where
-# they lie under /root/reference (nothing is copied): RVI/gnss/src/lambda.cpp and
-# RVI/gnss/src/common_function.cpp are plain C-style code; their shared header pulls in Eigen,
-# marginalization_factor.h and ceres/problem.h only for type names, which oracle/ref_stubs/
-# satisfies.  The rest of the reference (Ceres, factors, estimator) needs Eigen3/ROS/OpenCV and is
-# NOT buildable in this image.  Outputs go to oracle/_ref/ only (git-ignored, travels with gpurun).
+# they lie under /root/reference (nothing is copied):
+#   RVI/gnss/src/lambda.cpp, RVI/gnss/src/common_function.cpp         plain C-style code
+#   RVI/factor/gnss_factor.cpp, projection_factor.cpp, imu_factor.cpp, integration_base.cpp,
+#   pose_local_parameterization.cpp                                   the factor classes of the hot path
+# Eigen, OpenCV and Ceres are not installed in this image: the factor sources are compiled against
+# oracle/ref_stubs/ (a minimal eager stand-in for the part of Eigen's dense API they use, empty OpenCV
+# headers, a type-name stub of marginalization_factor.h) and against this repository's own
+# include/ceres/ headers (CostFunction / SizedCostFunction / LocalParameterization), which doubles as
+# the build test of those headers against unmodified reference code.  NOT buildable here, and not
+# attempted: marginalization_factor.cpp and gnss_imu_factor.cpp (SelfAdjointEigenSolver, pthread
+# pipelines), the estimator (ROS, OpenCV) and Ceres itself (needs Eigen proper).
+# Outputs go to oracle/_ref/ only (git-ignored, travels with gpurun).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-REF=/root/reference/rtk_visual_inertial_src/rtk_visual_inertial/src/gnss
+SRC=/root/reference/rtk_visual_inertial_src/rtk_visual_inertial/src
+REF=$SRC/gnss
 if [ ! -d "$REF" ]; then
   echo "build_ref.sh: $REF not present (GPU box?) - keeping prebuilt oracle/_ref" >&2
   exit 0
 fi
 mkdir -p "$HERE/_ref"
-g++ -O2 -fPIC -shared -ffp-contract=off -I"$HERE/ref_stubs" -I"$REF/include" \
-    "$REF/src/lambda.cpp" "$REF/src/common_function.cpp" "$HERE/ref_shim.cpp" \
-    -o "$HERE/_ref/libref_gnss.so"
+g++ -O2 -fPIC -shared -ffp-contract=off -std=c++14 -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" \
+    -I"$SRC" \
+    "$REF/src/lambda.cpp" "$REF/src/common_function.cpp" \
+    "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
+    "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" \
+    "$HERE/ref_shim.cpp" -o "$HERE/_ref/libref_gnss.so"
 echo "built $HERE/_ref/libref_gnss.so"

@@ -16,3 +16,149 @@ double ref_dot(const double* a, const double* b, int n) { return dot(a, b, n); }
 void ref_xyz2enu(const double* pos, double* E) { xyz2enu(pos, E); }
 void ref_ecef2pos(const double* r, double* pos) { ecef2pos(r, pos); }
 }
+
+// ---- the reference's own factor classes (RVI/factor/*.cpp compiled where they lie, against oracle/ref_stubs' minimal
+// Eigen stand-in and the repository's include/ceres/ headers) behind the same C signature as oracle_factor_eval ----
+#include <memory>
+#include <vector>
+
+#include "../include/swgn.h"
+#include "factor/gnss_factor.h"
+#include "factor/imu_factor.h"
+#include "factor/pose_local_parameterization.h"
+#include "factor/projection_factor.h"
+#include "parameter/parameters.h"
+
+double varerr2(double el, double dt, double mea_var);  // RVI/factor/gnss_factor.cpp:98-103 (no header declares it)
+
+// application globals the factor sources read (defined in RVI/parameter/parameters.cpp, which is not compiled)
+Eigen::Vector3d Pbg;
+Eigen::Matrix3d Rwgw;
+Eigen::Vector3d G;
+double ACC_N, ACC_W, GYR_N, GYR_W;
+
+namespace {
+void set_globals(const double* g /* Pbg3, gravity3, proj sqrt_info 4 */) {
+  Pbg = Eigen::Vector3d(g[0], g[1], g[2]);
+  Rwgw = Eigen::Matrix3d::Identity();
+  G = Eigen::Vector3d(g[3], g[4], g[5]);  // the factors use Rwgw * G
+  projection_factor::sqrt_info(0, 0) = g[6];
+  projection_factor::sqrt_info(0, 1) = g[7];
+  projection_factor::sqrt_info(1, 0) = g[8];
+  projection_factor::sqrt_info(1, 1) = g[9];
+}
+void load_record(IntegrationBase& ib, const double* rec) {
+  for (int i = 0; i < 3; ++i) {
+    ib.delta_p(i) = rec[SWGN_IMU_DELTA_P + i];
+    ib.delta_v(i) = rec[SWGN_IMU_DELTA_V + i];
+    ib.linearized_ba(i) = rec[SWGN_IMU_LIN_BA + i];
+    ib.linearized_bg(i) = rec[SWGN_IMU_LIN_BG + i];
+    ib.gyri(i) = rec[SWGN_IMU_GYRI + i];
+    ib.gyrj(i) = rec[SWGN_IMU_GYRJ + i];
+  }
+  ib.delta_q = Eigen::Quaterniond(rec[SWGN_IMU_DELTA_Q + 3], rec[SWGN_IMU_DELTA_Q], rec[SWGN_IMU_DELTA_Q + 1], rec[SWGN_IMU_DELTA_Q + 2]);
+  ib.sum_dt = rec[SWGN_IMU_SUM_DT];
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) {
+      ib.jacobian(i, j) = rec[SWGN_IMU_JACOBIAN + i * 15 + j];
+      ib.sqrt_info(i, j) = rec[SWGN_IMU_SQRT_INFO + i * 15 + j];
+    }
+  ib.covariance_update = false;  // get_sqrtinfo() returns sqrt_info as loaded
+}
+void store_record(IntegrationBase& ib, double* rec) {
+  for (int k = 0; k < SWGN_IMU_STRIDE; ++k) rec[k] = 0.0;
+  const Eigen::Matrix<double, 15, 15> si = ib.get_sqrtinfo();
+  for (int i = 0; i < 3; ++i) {
+    rec[SWGN_IMU_DELTA_P + i] = ib.delta_p(i);
+    rec[SWGN_IMU_DELTA_V + i] = ib.delta_v(i);
+    rec[SWGN_IMU_LIN_BA + i] = ib.linearized_ba(i);
+    rec[SWGN_IMU_LIN_BG + i] = ib.linearized_bg(i);
+    rec[SWGN_IMU_GYRI + i] = ib.gyri(i);
+    rec[SWGN_IMU_GYRJ + i] = ib.gyrj(i);
+  }
+  rec[SWGN_IMU_DELTA_Q + 0] = ib.delta_q.x();
+  rec[SWGN_IMU_DELTA_Q + 1] = ib.delta_q.y();
+  rec[SWGN_IMU_DELTA_Q + 2] = ib.delta_q.z();
+  rec[SWGN_IMU_DELTA_Q + 3] = ib.delta_q.w();
+  rec[SWGN_IMU_SUM_DT] = ib.sum_dt;
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) {
+      rec[SWGN_IMU_JACOBIAN + i * 15 + j] = ib.jacobian(i, j);
+      rec[SWGN_IMU_SQRT_INFO + i * 15 + j] = si(i, j);
+    }
+}
+}  // namespace
+
+extern "C" {
+// kind 0 projection_factor (record = uv), 1 IMUFactor (record = SWGN_IMU_STRIDE), 2 GNSS (kind2 = SWGN_GNSS_*, record =
+// SWGN_GNSS_STRIDE; the RTK factors take el / dt / var and weigh with their own varerr2: a carrier factor with var <= 0 is
+// built with use_istd = false).  params: concatenated global blocks in factor order; jac_out: concatenated row-major
+// global Jacobians (may be null).
+int ref_factor_eval(int kind, int kind2, const double* globals, const double* record, const double* params, double* residuals,
+                    double* jac_out) {
+  set_globals(globals);
+  std::unique_ptr<ceres::CostFunction> f;
+  std::unique_ptr<IntegrationBase> ib;
+  double sat[3], satv[3], base[3], xyzt[3] = {0, 0, 0};
+  if (kind == 0) {
+    f.reset(new projection_factor(Eigen::Vector3d(record[0], record[1], 1.0)));
+  } else if (kind == 1) {
+    ib.reset(new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero()));
+    load_record(*ib, record);
+    f.reset(new IMUFactor(ib.get()));
+  } else if (kind == 2) {
+    for (int i = 0; i < 3; ++i) {
+      sat[i] = record[SWGN_GNSS_SAT_POS + i];
+      satv[i] = record[SWGN_GNSS_SAT_VEL + i];
+      base[i] = record[SWGN_GNSS_BASE_POS + i];
+    }
+    const double meas = record[SWGN_GNSS_MEAS], lam = record[SWGN_GNSS_LAM], wgt = record[SWGN_GNSS_WEIGHT];
+    const double el = record[SWGN_GNSS_EL], dt = record[SWGN_GNSS_DT], var = record[SWGN_GNSS_VAR];
+    switch (kind2) {
+      case SWGN_GNSS_SPP_PSEUDORANGE: f.reset(new SppPseudorangeFactor(sat, meas, wgt, base)); break;
+      case SWGN_GNSS_SPP_CARRIER: f.reset(new SppCarrierPhaseFactor(sat, meas, wgt, base, lam)); break;
+      case SWGN_GNSS_RTK_CARRIER: f.reset(new RTKCarrierPhaseFactor(sat, meas, lam, el, dt, var, base, var > 0.0, 0, 0)); break;
+      case SWGN_GNSS_RTK_PSEUDORANGE: f.reset(new RTKPseudorangeFactor(sat, meas, el, dt, var, base)); break;
+      case SWGN_GNSS_DOPPLER: f.reset(new SppDopplerFactor(satv, sat, xyzt, meas, wgt, base)); break;
+      case SWGN_GNSS_FIXED_INTEGER: f.reset(new FixedIntegerFactor(meas, wgt)); break;
+      default: return 2;
+    }
+  } else {
+    return 2;
+  }
+  std::vector<const double*> p;
+  std::vector<double*> J;
+  const double* pp = params;
+  double* jp = jac_out;
+  for (int sz : f->parameter_block_sizes()) {
+    p.push_back(pp);
+    pp += sz;
+    J.push_back(jp);
+    if (jp) jp += (size_t)f->num_residuals() * sz;
+  }
+  return f->Evaluate(p.data(), residuals, jac_out ? J.data() : nullptr) ? 0 : 1;
+}
+
+// IntegrationBase: constructor + one push_back per further sample (RVI/factor/integration_base.cpp:5-142), then
+// get_sqrtinfo(); samples = 7 doubles each (dt, acc, gyr), the first one is (acc_0, gyr_0).
+int ref_preintegrate(int n_samples, const double* samples, const double* bias6, const double* noise4, double* record) {
+  ACC_N = noise4[0];
+  GYR_N = noise4[1];
+  ACC_W = noise4[2];
+  GYR_W = noise4[3];
+  IntegrationBase ib(Eigen::Vector3d(samples[1], samples[2], samples[3]), Eigen::Vector3d(samples[4], samples[5], samples[6]),
+                     Eigen::Vector3d(bias6[0], bias6[1], bias6[2]), Eigen::Vector3d(bias6[3], bias6[4], bias6[5]));
+  for (int k = 1; k < n_samples; ++k) {
+    const double* s = samples + 7 * k;
+    ib.push_back(s[0], Eigen::Vector3d(s[1], s[2], s[3]), Eigen::Vector3d(s[4], s[5], s[6]));
+  }
+  store_record(ib, record);
+  return 0;
+}
+
+void ref_pose_plus(const double* x, const double* delta, double* out) {
+  PoseLocalParameterization p;
+  static_cast<const ceres::LocalParameterization&>(p).Plus(x, delta, out);  // (the reference declares its overrides private)
+}
+double ref_varerr2(double el, double dt, double var) { return varerr2(el, dt, var); }
+}

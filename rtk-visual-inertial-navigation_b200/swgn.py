@@ -67,7 +67,10 @@ class SynthConfig(C.Structure):
     _fields_ = [("n_keyframes", i32), ("n_landmarks", i32), ("n_gnss_epochs", i32),
                 ("n_sats", i32), ("seed0", C.c_uint64), ("state_noise", f64),
                 ("composition", i32), ("hidden_per_gap", i32), ("bias_walk_scale", f64),
-                ("hidden_bias_istd", f64)]
+                ("hidden_bias_istd", f64), ("variant", i32), ("pad_", i32)]
+
+
+SYNTH_SPP, SYNTH_FIXED_INTEGER, SYNTH_FREE_EXTRINSIC = 1, 2, 4
 
 
 def _dp(a):
@@ -180,6 +183,35 @@ class SynthWindow:
                 self.h = None
         except Exception:
             pass
+
+
+def state_error_by_kind(w, x, xo):
+    """max |dx| / max(1, |x|) of two state vectors of SynthWindow w per kind of parameter block: pose translation,
+    pose quaternion, speed, accelerometer bias, gyro bias, landmark, ambiguity, other scalars (clocks, drifts)."""
+    g = w.graph
+    out = {}
+
+    def put(name, a, b):
+        if len(a):
+            e = float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+            out[name] = max(out.get(name, 0.0), e)
+    for bi in range(g.n_blocks):
+        o, s = g.block_offset[bi], g.block_size[bi]
+        a, b = x[o:o + s], xo[o:o + s]
+        if s == 7:
+            put("position", a[:3], b[:3])
+            put("quaternion", a[3:], b[3:])
+        elif s == 9:
+            put("speed", a[:3], b[:3])
+            put("acc bias", a[3:6], b[3:6])
+            put("gyro bias", a[6:], b[6:])
+        elif s == 3:
+            put("landmark", a, b)
+        elif w.n_amb and w.first_amb_block <= bi < w.first_amb_block + w.n_amb:
+            put("ambiguity", a, b)
+        else:
+            put("scalar", a, b)
+    return out
 
 
 def lib():

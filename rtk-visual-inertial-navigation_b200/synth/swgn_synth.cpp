@@ -462,7 +462,7 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
   }
   S->block_size[b_ext] = 7;
   S->block_manifold[b_ext] = SWGN_MANIFOLD_POSE;
-  S->block_const[b_ext] = 1;  // ESTIMATE_EXTRINSIC: 0
+  S->block_const[b_ext] = (cfg->variant & SWGN_SYNTH_FREE_EXTRINSIC) ? 0 : 1;  // ESTIMATE_EXTRINSIC
   for (int l = 0; l < cfg->n_landmarks; ++l) S->block_size[b_lm + l] = 3;
   S->block_offset.resize(nb);
   int off = 0;
@@ -502,6 +502,13 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
   std::memcpy(S->state.data(), S->truth.data(), sizeof(double) * off);
   double* X0 = S->state.data();
   auto bp0 = [&](int b) { return X0 + S->block_offset[b]; };
+  if (cfg->variant & SWGN_SYNTH_FREE_EXTRINSIC) {  // a fixed offset (no random draw: the default windows keep their seeds)
+    double* p = bp0(b_ext);
+    const double dt[3] = {0.01, -0.008, 0.005}, th[3] = {0.004, -0.003, 0.002};
+    for (int k = 0; k < 3; ++k) p[k] += sn * dt[k];
+    Q4 q = qnorm(qmul(Q4{p[6], p[3], p[4], p[5]}, Q4{1, sn * th[0] / 2, sn * th[1] / 2, sn * th[2] / 2}));
+    p[3] = q.x; p[4] = q.y; p[5] = q.z; p[6] = q.w;
+  }
   for (int f = 0; f < F; ++f) {
     double* p = bp0(b_pose + f);
     for (int k = 0; k < 3; ++k) p[k] += sn * 0.05 * rng.normal();
@@ -782,11 +789,15 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
       // RB-SD carrier phase: r = w (rho - N lam - L1_lam + clk)
       double var_l = (Lstd * lam) * (Lstd * lam);
       double L1_lam = rho - S->true_N[s] * lam + clk[sys] + Lstd * lam * rng.normal();
-      add(SWGN_GNSS_RTK_CARRIER, b_pose + f, b_N + s, b_clk + 3 * e + sys, L1_lam, weight(var_l), var_l);
+      if (cfg->variant & SWGN_SYNTH_SPP)  // rover-only carrier phase: (pose, clk, N), r = istd (rho + clk - N lam - L1_lam)
+        add(SWGN_GNSS_SPP_CARRIER, b_pose + f, b_clk + 3 * e + sys, b_N + s, L1_lam, weight(var_l), var_l);
+      else
+        add(SWGN_GNSS_RTK_CARRIER, b_pose + f, b_N + s, b_clk + 3 * e + sys, L1_lam, weight(var_l), var_l);
       // RB-SD pseudorange: r = w (rho - P1 + clk)
       double var_p = Pstd * Pstd;
       double P1 = rho + clk[sys] + Pstd * rng.normal();
-      add(SWGN_GNSS_RTK_PSEUDORANGE, b_pose + f, b_clk + 3 * e + sys, -1, P1, weight(var_p), var_p);
+      add((cfg->variant & SWGN_SYNTH_SPP) ? SWGN_GNSS_SPP_PSEUDORANGE : SWGN_GNSS_RTK_PSEUDORANGE, b_pose + f, b_clk + 3 * e + sys, -1, P1,
+          weight(var_p), var_p);
       // Doppler: r = istd (rate + drift + D1_lam)
       V3 ee = (1.0 / norm(xg - sp)) * (xg - sp);
       double rate = dot(vr - sat_vel[s], ee) +
@@ -802,6 +813,25 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
     // InitialBlackFactor on `blackvalue`, once per GNSS frame (RVI/swf/swf_core.cpp:103-105)
     S->unit_block.push_back(b_black);
     S->unit_istd.push_back(1.0);
+  }
+  // FixedIntegerFactor (gnss_factor.cpp:85-96): r = istd ((N_a - N_ref) - N21), as LambdaSearch adds them after a fix
+  if (!compA && (cfg->variant & SWGN_SYNTH_FIXED_INTEGER) && nsat > 0 && n_epochs_real > 0) {
+    int ref_of_sys[3] = {-1, -1, -1};
+    for (int s = 0; s < nsat; ++s) {
+      const int sys = sat_sys[s];
+      if (ref_of_sys[sys] < 0) {
+        ref_of_sys[sys] = s;
+        continue;
+      }
+      S->gnss_kind.push_back(SWGN_GNSS_FIXED_INTEGER);
+      int32_t gb[3] = {b_N + ref_of_sys[sys], b_N + s, -1};
+      S->gnss_blocks.insert(S->gnss_blocks.end(), gb, gb + 3);
+      size_t o = S->gnss_data.size();
+      S->gnss_data.resize(o + SWGN_GNSS_STRIDE, 0.0);
+      double* r = S->gnss_data.data() + o;
+      r[SWGN_GNSS_MEAS] = S->true_N[s] - S->true_N[ref_of_sys[sys]];
+      r[SWGN_GNSS_WEIGHT] = 100.0;
+    }
   }
   // InitialBlackFactor on `blackvalue2` (RVI/swf/swf_core.cpp:553-556)
   S->unit_block.push_back(b_black2);
@@ -860,12 +890,13 @@ swgn_synth* swgn_synth_create(const swgn_synth_config* cfg, uint64_t window_id) 
       if (in_problem(f) && S->block_group[b_sb + f] < 0) S->block_group[b_sb + f] = ors++;
     for (int f = 1; f < F; ++f)
       if (in_problem(f)) S->block_group[b_pose + f] = ors++;
+    if (cfg->variant & SWGN_SYNTH_FREE_EXTRINSIC) S->block_group[b_ext] = ors++;  // after the poses (swf_gnss.cpp:710-717)
     if (n_epochs_real > 0) S->block_group[b_black] = ors++;
     for (int e = 0; e < n_epochs_real; ++e) S->block_group[b_drift + e] = ors++;
     S->block_group[b_pose + 0] = ors++;
     S->block_group[b_sb + 0] = ors++;
     for (int s = 0; s < nsat; ++s) S->block_group[b_N + s] = ors++;
-    S->block_group[b_ext] = ors++;  // constant: removed by the reduced program anyway
+    if (!(cfg->variant & SWGN_SYNTH_FREE_EXTRINSIC)) S->block_group[b_ext] = ors++;  // constant: removed by the reduced program anyway
   }
   // clocks that no satellite of that system touches would be e-blocks without rows: make them
   // constant (the reference only adds the slots it uses)

@@ -38,7 +38,15 @@ typedef struct swgn_synth_config {
                               parity tests compare arithmetic, not amplified rounding noise     */
   double hidden_bias_istd; /* composition A: 1/sigma of a weak absolute bias term in the hidden
                               frames' GNSS information (acc bias; gyro bias uses 10x); 0 = none */
+  int32_t variant;         /* composition B only, bit flags for the factor kinds the default window does not hold:
+                              1 = rover-only SppPseudorangeFactor / SppCarrierPhaseFactor (gnss_factor.cpp:9-80) in place
+                                  of the RB-SD pair; 2 = a FixedIntegerFactor (:85-96) between every ambiguity and the
+                                  first ambiguity of its constellation, as LambdaSearch injects them after a fix
+                                  (swf_lambda.cpp:249-355); 4 = ESTIMATE_EXTRINSIC: the camera extrinsic is a free
+                                  parameter block (ordered after the poses, swf_gnss.cpp:710-717) */
+  int32_t pad_;
 } swgn_synth_config;
+enum { SWGN_SYNTH_SPP = 1, SWGN_SYNTH_FIXED_INTEGER = 2, SWGN_SYNTH_FREE_EXTRINSIC = 4 };
 
 typedef struct swgn_synth swgn_synth;
 

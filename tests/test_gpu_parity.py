@@ -21,8 +21,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 TOL_RES = 1e-11      # residual vector, relative 2-norm
 TOL_JAC = 1e-12      # Jacobian, relative Frobenius norm
 TOL_S = 1e-12        # reduced system
-TOL_STATE = 1e-6     # state vector after the full solve: max |dx| / max(1, |x|)
+TOL_STATE = 1e-6     # state vector after the full solve: max |dx| / max(1, |x|), any block
 TOL_COST = 1e-6      # final cost, relative
+# ... and per kind of parameter block, ~10x what the B200 shows on the BASELINE window after 8 iterations (the landmarks carry
+# the largest difference: 5.9e-8; tools/gpu_stage_check.py prints the table).  cond(J'J + D^2) of these windows is 1e16..1e17,
+# so the differences are amplified rounding of an ill-conditioned solve, not algorithmic ones.
+TOL_STATE_KIND = {"position": 1e-7, "quaternion": 1e-8, "speed": 1e-7, "acc bias": 2e-7, "gyro bias": 1e-8, "landmark": 6e-7,
+                  "ambiguity": 1e-7, "scalar": 2e-7}
 
 
 def rel(a, b):
@@ -63,13 +68,19 @@ def test_linear_solve_stage(which, wid):
     st, ox, oS, orhs = o.linear_solve(D)
     assert st == 0
     S, rhs = b.get_reduced(0)
+    # the per-linear-solve gate (1e-9 on identical linearisation) is applied where it is meaningful:
+    # the reduced system the eliminator produces, and the backward error of the solution
     assert rel(np.triu(S), np.triu(oS)) < TOL_S
-    assert rel(rhs, orhs) < 1e-9
-    assert rel(x, ox) < 1e-6
-    # size-independent property: x solves the damped normal equations of the SAME linearisation
+    assert rel(rhs, orhs) < 1e-12
     _, r, g, J = o.evaluate()
-    lhs = J.T @ (J @ x) + D * D * x
-    assert rel(lhs, g) < 1e-7
+    H = J.T @ J + np.diag(D * D)
+    nH = np.linalg.norm(H, 2)
+
+    def backward(v):
+        return float(np.linalg.norm(H @ v - g) / (nH * np.linalg.norm(v) + np.linalg.norm(g)))
+    assert backward(x) < 1e-16 and backward(ox) < 1e-16
+    # forward error: cond(J'J + D^2) is 1e15..1e17 here (cond * eps ~ 1..40), the two solutions agree far better than that bound
+    assert rel(x, ox) < 1e-7
     b.close()
 
 
@@ -92,6 +103,50 @@ def test_full_solve_matches_oracle(which, wid):
     assert abs(sm.initial_cost - osm.initial_cost) <= 1e-11 * osm.initial_cost
     assert abs(sm.final_cost - osm.final_cost) <= TOL_COST * osm.final_cost
     assert state_err(x, o.state()) < TOL_STATE
+    for kind, err in swgn.state_error_by_kind(w, x, o.state()).items():
+        assert err < TOL_STATE_KIND[kind], (kind, err)
+    b.close()
+
+
+VARIANTS = [swgn.SYNTH_SPP, swgn.SYNTH_FIXED_INTEGER, swgn.SYNTH_FREE_EXTRINSIC,
+            swgn.SYNTH_SPP | swgn.SYNTH_FIXED_INTEGER | swgn.SYNTH_FREE_EXTRINSIC]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("shape", [dict(n_keyframes=8, n_landmarks=60, n_gnss_epochs=4, n_sats=10), {}])
+def test_factor_kinds_the_default_window_does_not_hold(variant, shape):
+    """SppPseudorangeFactor, SppCarrierPhaseFactor, FixedIntegerFactor (gnss_factor.cpp:9-96) and projection factors with a
+    free camera extrinsic (projection_factor.cpp:50-57, ESTIMATE_EXTRINSIC): evaluation, one linear solve, full solve."""
+    w = swgn.SynthWindow(2, 3, variant=variant, **shape)
+    opt = w.options()
+    kinds = set(np.ctypeslib.as_array(w.graph.gnss_kind, shape=(w.graph.n_gnss,)).tolist())
+    if variant & swgn.SYNTH_SPP:
+        assert {0, 1} <= kinds and not ({2, 3} & kinds)
+    if variant & swgn.SYNTH_FIXED_INTEGER:
+        assert 5 in kinds
+    o = ob.OracleSolver(w.graph_p, opt)
+    b = swgn.Batch([w.graph_p], opt)
+    assert all(np.array_equal(x, y) for x, y in zip(b.columns(0), o.columns()))
+    assert all(np.array_equal(x, y) for x, y in zip(b.rows(0), o.rows()))
+    if variant & swgn.SYNTH_FREE_EXTRINSIC:
+        ext_block = 2 * w.n_frames  # the generator's block layout: poses, speed-biases, extrinsic
+        assert ext_block in set(b.columns(0)[0].tolist())
+    cost, r, g = b.evaluate(0, o.n_res, o.n_cols)
+    ocost, orr, og, oJ = o.evaluate()
+    J = b.dense_jacobian(0, o.n_res, o.n_cols)
+    assert abs(cost - ocost) <= 1e-12 * ocost
+    assert rel(r, orr) < TOL_RES and rel(J, oJ) < TOL_JAC and rel(g, og) < 1e-11
+    D = np.random.default_rng(variant).uniform(0.5, 1.5, o.n_cols) * 1e-2
+    x = b.linear_solve(0, D, o.n_cols)
+    st, ox, oS, orhs = o.linear_solve(D)
+    S, rhs = b.get_reduced(0)
+    assert rel(np.triu(S), np.triu(oS)) < TOL_S and rel(rhs, orhs) < 1e-12 and rel(x, ox) < 1e-6
+    sm = b.solve()[0]
+    st, osm = o.minimize()
+    assert (sm.num_iterations, sm.num_successful_steps, sm.termination_type, sm.num_linear_solves) == \
+        (osm.num_iterations, osm.num_successful_steps, osm.termination_type, osm.num_linear_solves)
+    assert abs(sm.final_cost - osm.final_cost) <= TOL_COST * osm.final_cost
+    assert state_err(b.get_state(0, w.n_state), o.state()) < TOL_STATE
     b.close()
 
 

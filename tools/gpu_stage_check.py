@@ -52,6 +52,11 @@ def main():
     S, rhs = b.get_reduced(0)
     print("S rel err", rel(np.triu(S), np.triu(oS)), "rhs rel err", rel(rhs, orhs))
     print("linear solve x rel err", rel(x, ox), " (e part", rel(x[:o.n_e], ox[:o.n_e]), " f part", rel(x[o.n_e:], ox[o.n_e:]), ")")
+    H = oJ.T @ oJ + np.diag(D * D)
+    sv = np.linalg.svd(H, compute_uv=False)
+    cond = sv[0] / sv[-1]
+    be = lambda v: float(np.linalg.norm(H @ v - og) / (np.linalg.norm(H, 2) * np.linalg.norm(v) + np.linalg.norm(og)))
+    print("  cond(J'J + D^2) %.3e -> cond * eps %.3e ; backward error gpu %.3e oracle %.3e" % (cond, cond * 2.2e-16, be(x), be(ox)))
     sm = b.solve()[0]
     ost, osm = o.minimize()
     xs = b.get_state(0, w.n_state)
@@ -60,6 +65,8 @@ def main():
           (sm.final_cost, osm.final_cost, sm.num_iterations, osm.num_iterations, sm.num_successful_steps,
            osm.num_successful_steps, sm.termination_type, osm.termination_type, sm.num_linear_solves, osm.num_linear_solves))
     print("state max abs err", np.abs(xs - xo).max(), "max rel", (np.abs(xs - xo) / np.maximum(1, np.abs(xo))).max())
+    for name, err in swgn.state_error_by_kind(w, xs, xo).items():
+        print("   %-10s max |dx| / max(1, |x|) = %.3e" % (name, err))
     print("timing (total ms, schur ms, schur launches, launches):", b.timing())
     if opt.n_parameter_head > 0:
         Lg = b.get_cholesky(0)
