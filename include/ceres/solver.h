@@ -1,8 +1,10 @@
 // ceres/solver.h -- shim of CERES/include/ceres/solver.h:233-737 (Options), Summary and
 // ceres::Solve (CERES/internal/ceres/solver.cc:604): the fields the reference sets and reads
-// (RVI/swf/swf.cpp:25-30, swf_image.cpp:212-230, swf_core.cpp:409).  The only configuration the
-// device path implements is the reference's: DENSE_SCHUR with a user ordering, DOGLEG
-// (TRADITIONAL) or LEVENBERG_MARQUARDT is rejected as unsupported, jacobi_scaling = false.
+// (RVI/swf/swf.cpp:25-30, swf_image.cpp:212-230, swf_core.cpp:409).  The device path implements the
+// reference's two configurations: DENSE_SCHUR with a user ordering and either TRADITIONAL DOGLEG with
+// jacobi_scaling = false (the sliding-window solve) or LEVENBERG_MARQUARDT with / without jacobi_scaling
+// (Ceres' defaults: the per-epoch GNSS solves, swf_gnss.cpp:204-215,563-573); max_solver_time_in_seconds is
+// accepted and ignored (the device solve is bounded by max_num_iterations).
 #ifndef SWGN_CERES_SOLVER_H_
 #define SWGN_CERES_SOLVER_H_
 #include <memory>

@@ -215,10 +215,15 @@ typedef struct swgn_options {
                                             blocks are the LAST n_parameter_head groups of the
                                             ordering (swf_gnss.cpp:775-782)                  */
   int32_t device;                        /* CUDA device ordinal                              */
-  int32_t trust_region_strategy;         /* SWGN_DOGLEG (0, the reference's setting, the only one the device
-                                            implements: swgn_batch_create answers SWGN_ERR_UNSUPPORTED otherwise) or
-                                            SWGN_LEVENBERG_MARQUARDT (Ceres' default, levenberg_marquardt_strategy.cc;
-                                            so far restated by the oracle only)                                  */
+  int32_t trust_region_strategy;         /* SWGN_DOGLEG (0, what the reference sets for the sliding-window solve,
+                                            swf_image.cpp:205) or SWGN_LEVENBERG_MARQUARDT (Ceres' default,
+                                            levenberg_marquardt_strategy.cc:66-165: what the reference's per-epoch
+                                            GNSS solves run with, swf_gnss.cpp:204-215,563-573)                     */
+  int32_t jacobi_scaling;                /* Solver::Options::jacobi_scaling (Ceres' default is true; the sliding-window
+                                            solve sets false): columns of J scaled by 1 / (1 + |column|) of the initial
+                                            Jacobian (trust_region_minimizer.cc:261-276,437).  Implemented with
+                                            LEVENBERG_MARQUARDT; with DOGLEG swgn_batch_create answers SWGN_ERR_UNSUPPORTED */
+  int32_t reserved_;
 } swgn_options;
 enum { SWGN_DOGLEG = 0, SWGN_LEVENBERG_MARQUARDT = 1 };
 

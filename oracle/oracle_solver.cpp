@@ -750,6 +750,15 @@ void left_multiply(const BlockSparse& A, const double* x, double* y) {  // y += 
         for (int k = 0; k < cs; ++k) y[cp + k] += v[r * cs + k] * x[row.position + r];
     }
 }
+void scale_columns(BlockSparse* A, const double* scale) {  // BlockSparseMatrix::ScaleColumns
+  for (const RowBlock& row : A->rows)
+    for (const Cell& c : row.cells) {
+      const int cs = A->cols[c.block_id].size, cp = A->cols[c.block_id].position;
+      double* v = A->values.data() + c.position;
+      for (int r = 0; r < row.size; ++r)
+        for (int k = 0; k < cs; ++k) v[r * cs + k] *= scale[cp + k];
+    }
+}
 void squared_column_norm(const BlockSparse& A, double* x) {
   std::fill(x, x + A.num_cols, 0.0);
   for (const RowBlock& row : A.rows)
@@ -795,9 +804,21 @@ bool Solver::Minimize(swgn_summary* summary) {
   double decrease_factor = 2.0;
   bool reuse_diagonal = false;
 
+  // Solver::Options::jacobi_scaling (trust_region_minimizer.cc:183,261-276): the scaling vector is computed from the
+  // Jacobian of iteration zero and applied to every later Jacobian; the gradient is taken before the scaling
+  std::vector<double> jacobian_scaling(n, 1.0);
+  bool have_scaling = false;
   IterationRecord it = {};
   auto eval_grad_jac = [&]() -> bool {                           // EvaluateGradientAndJacobian
     if (!Evaluate(x.data(), &x_cost, residuals.data(), gradient.data(), true)) return false;
+    if (opt.jacobi_scaling) {
+      if (!have_scaling) {
+        squared_column_norm(jac, jacobian_scaling.data());
+        for (int i = 0; i < n; ++i) jacobian_scaling[i] = 1.0 / (1.0 + std::sqrt(jacobian_scaling[i]));
+        have_scaling = true;
+      }
+      scale_columns(&jac, jacobian_scaling.data());
+    }
     it.cost = x_cost + fixed_cost;
     for (int i = 0; i < n; ++i) neg_grad[i] = -gradient[i];
     Plus(x.data(), neg_grad.data(), proj.data());
@@ -923,7 +944,7 @@ bool Solver::Minimize(swgn_summary* summary) {
       model_cost_change = -mc;
       it.step_is_valid = model_cost_change > 0.0;
       if (it.step_is_valid) {
-        delta = step;
+        for (int i = 0; i < n; ++i) delta[i] = step[i] * jacobian_scaling[i];  // undo the column scaling :437
         num_consecutive_invalid = 0;
       }
     } else if (!linear_failure) {
@@ -956,7 +977,7 @@ bool Solver::Minimize(swgn_summary* summary) {
       model_cost_change = -mc;
       it.step_is_valid = model_cost_change > 0.0;
       if (it.step_is_valid) {
-        delta = step;  // jacobi_scaling = false
+        for (int i = 0; i < n; ++i) delta[i] = step[i] * jacobian_scaling[i];  // (all ones unless jacobi_scaling)
         num_consecutive_invalid = 0;
       }
     }

@@ -200,8 +200,10 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
                               swgn_batch** out) {
   if (!options || !graphs || !out || n_windows <= 0) return fail(SWGN_ERR_INVALID, "bad arguments");
   *out = nullptr;
-  if (options->trust_region_strategy != SWGN_DOGLEG)
-    return fail(SWGN_ERR_UNSUPPORTED, "only the DOGLEG trust-region strategy is implemented on the device");
+  if (options->trust_region_strategy != SWGN_DOGLEG && options->trust_region_strategy != SWGN_LEVENBERG_MARQUARDT)
+    return fail(SWGN_ERR_UNSUPPORTED, "unknown trust-region strategy");
+  if (options->jacobi_scaling && options->trust_region_strategy != SWGN_LEVENBERG_MARQUARDT)
+    return fail(SWGN_ERR_UNSUPPORTED, "jacobi_scaling is implemented for the LEVENBERG_MARQUARDT strategy only (the reference's DOGLEG solve sets it to false)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || options->device < 0 || options->device >= ndev)
     return fail(SWGN_ERR_NO_DEVICE, "no usable CUDA device (the solver has no CPU fallback)");
@@ -470,6 +472,9 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   P.is_optimize = options->is_optimize;
   P.n_parameter_head = options->n_parameter_head;
   P.export_mode = (options->n_parameter_head > 0 && !options->is_optimize) ? 1 : 0;
+  P.strategy = options->trust_region_strategy;
+  P.jacobi_scaling = options->jacobi_scaling ? 1 : 0;
+  P.max_radius_lm = options->max_trust_region_radius;
   CB(configure_schur(db));
   CB(configure_schur_stream(db));
   CB(configure_chol(db));

@@ -162,6 +162,7 @@ enum WArr {
   W_S,       // [n_f * ld] reduced system, row-major upper triangle; column n_f holds the rhs;
              //            overwritten by its Cholesky factor U (S = U^T U) and U^-T rhs
   W_SCOPY,   // [n_f * ld] copy of S|rhs before factorisation (staged test entry point only)
+  W_SCALE,   // [n_t] Jacobi scaling 1 / (1 + |column of the initial Jacobian|) (jacobi_scaling only)
   W_CHAIN,   // mutable state of the IMUGNSSFactor chains, per chain (ChainLayout): hidden frame states, history
              // flag, states of the last Jacobian evaluation, INC, saved elimination blocks (hmn_save,
              // rhsmn_save), schur_jacobian, schur_residual, cost of the current evaluation
@@ -247,6 +248,7 @@ struct TRState {
   int32_t have_factor;         // W_S currently holds a Cholesky factor (lhs_out2 available)
   int32_t have_reduced;        // W_S currently holds S | rhs of an export-mode eliminate
   int32_t pad;
+  double decrease_factor;      // LevenbergMarquardtStrategy::decrease_factor_
 };
 
 struct SolverParams {
@@ -254,7 +256,10 @@ struct SolverParams {
   double initial_radius, max_radius, min_radius, min_relative_decrease;
   double min_lm_diagonal, max_lm_diagonal;
   double function_tolerance, gradient_tolerance, parameter_tolerance, min_mu;
-  int32_t is_optimize, n_parameter_head, export_mode, pad;
+  int32_t is_optimize, n_parameter_head, export_mode;
+  int32_t strategy;            // SWGN_DOGLEG / SWGN_LEVENBERG_MARQUARDT
+  int32_t jacobi_scaling, pad;
+  double max_radius_lm;        // (= max_radius; LevenbergMarquardtStrategy clamps on acceptance)
 };
 
 }  // namespace swgn

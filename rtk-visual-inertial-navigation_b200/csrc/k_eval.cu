@@ -404,6 +404,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
     const int32_t* row_nres = v.I(I_ROW_NRES);
     double* G = v.W(W_G);
     double* DG = v.W(W_DIAG);
+    double* SC = v.W(W_SCALE);
+    // dogleg / LM diagonal sqrt(clamp(|column|^2)) of the (Jacobi-scaled) Jacobian; the scaling 1 / (1 + |column|) is taken
+    // from the Jacobian of iteration zero and kept (trust_region_minimizer.cc:261-276); J itself stays unscaled in memory
+    const bool jscale = b.params.jacobi_scaling != 0, new_scale = mode == EVAL_INIT;
+    auto diag_of = [&](double ns, int idx) {
+      if (jscale) {
+        double sc;
+        if (new_scale) {
+          sc = 1.0 / (1.0 + sqrt(ns));
+          SC[idx] = sc;
+        } else {
+          sc = SC[idx];
+        }
+        ns = ns * sc * sc;
+      }
+      return sqrt(fmin(fmax(ns, b.params.min_lm_diagonal), b.params.max_lm_diagonal));
+    };
     constexpr int kHeavy = 24;  // columns with more row blocks than this are reduced by a whole warp
     const int32_t* csc_nres = v.I(I_CSC_NRES);
     const int32_t* csc_res = v.I(I_CSC_RES);
@@ -448,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
         for (int k = 0; k < 9; ++k)
           if (k0 + k < cs) {
             G[col_pos[col] + k0 + k] = g[k];
-            DG[col_pos[col] + k0 + k] = sqrt(fmin(fmax(nrm[k], b.params.min_lm_diagonal), b.params.max_lm_diagonal));
+            DG[col_pos[col] + k0 + k] = diag_of(nrm[k], col_pos[col] + k0 + k);
           }
       }
     }
@@ -482,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
           const double gs = warp_sum(g[k]), ns = warp_sum(nrm[k]);
           if (lane == 0 && k0 + k < cs) {
             G[col_pos[col] + k0 + k] = gs;
-            DG[col_pos[col] + k0 + k] = sqrt(fmin(fmax(ns, b.params.min_lm_diagonal), b.params.max_lm_diagonal));
+            DG[col_pos[col] + k0 + k] = diag_of(ns, col_pos[col] + k0 + k);
           }
         }
       }
@@ -530,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
       s.minimum_cost = DBL_MAX;
       s.candidate_cost = 0.0;
       s.radius = P.initial_radius;
+      s.decrease_factor = 2.0;
       s.mu = P.min_mu;
       s.x_norm = sqrt(xn2);
       s.gradient_max_norm = gmax;

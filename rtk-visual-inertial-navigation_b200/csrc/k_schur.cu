@@ -855,8 +855,16 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
   TRState* st = b.state + w;
   if (only_window < 0 && !(st->active && st->need_solve)) return;
   const int tid = threadIdx.x, wid = tid >> 5;
-  if (!b.params.export_mode && !st->chol_ok) {  // LINEAR_SOLVER_FAILURE: retry with mu * 10
-    if (tid == 0) st->mu *= 10.0;
+  const bool lm = b.params.strategy == SWGN_LEVENBERG_MARQUARDT;
+  if (!b.params.export_mode && !st->chol_ok) {  // LINEAR_SOLVER_FAILURE
+    if (tid == 0) {
+      if (lm) {  // no retry loop in LevenbergMarquardtStrategy::ComputeStep: the step is invalid (k_step shrinks the radius)
+        st->need_solve = 0;
+        st->solve_ok = 0;
+      } else {
+        st->mu *= 10.0;  // dogleg: retry with mu * 10
+      }
+    }
     return;
   }
   const Win v = load_window(b, w, &sd);
@@ -889,7 +897,10 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
   }
   bad = block_any(bad);
   if (tid == 0 && only_window < 0) {
-    if (bad) {
+    if (bad && lm) {
+      st->need_solve = 0;
+      st->solve_ok = 0;
+    } else if (bad) {
       st->mu *= 10.0;  // stays in need_solve: retried in the next tick
     } else {
       st->need_solve = 0;

@@ -1,7 +1,9 @@
 // K6: the per-window trust-region state machine -- TrustRegionMinimizer::Minimize
 // (CERES/internal/ceres/trust_region_minimizer.cc:67-134) with the TRADITIONAL_DOGLEG strategy
-// (dogleg_strategy.cc:79-253, 515-638, kMinMu = 1e-12 as modified by the reference, :51) and
-// TrustRegionStepEvaluator (trust_region_step_evaluator.cc:52-112).  The control flow is data
+// (dogleg_strategy.cc:79-253, 515-638, kMinMu = 1e-12 as modified by the reference, :51) or the
+// LEVENBERG_MARQUARDT strategy (levenberg_marquardt_strategy.cc:66-165; with jacobi_scaling the solve runs on the
+// unscaled Jacobian with the damping diagonal divided by the scaling, which is the same linear system in the
+// unscaled variable) and TrustRegionStepEvaluator (trust_region_step_evaluator.cc:52-112).  The control flow is data
 // dependent per window (accept / reject, mu retries, early convergence), so it lives on the device
 // as masks in TRState; the host only issues "ticks" of
 //   k_begin -> k_schur -> k_chol -> k_backsub -> k_step -> k_eval(candidate) -> k_end -> k_eval(accepted)
@@ -80,7 +82,10 @@ __global__ void __launch_bounds__(kThreads) k_begin(DeviceBatch b, int tick) {
         st->iteration += 1;
         st->step_valid = 0;
         st->accepted = 0;
-        if (!st->reuse) {
+        if (P.strategy == SWGN_LEVENBERG_MARQUARDT) {  // every iteration solves with D = sqrt(diagonal / radius)
+          st->need_solve = 1;
+          st->solve_ok = 0;
+        } else if (!st->reuse) {
           st->reuse = 1;
           st->need_solve = 1;
           st->solve_ok = 0;
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) k_begin(DeviceBatch b, int tick) {
         }
       }
     }
-    if (st->active && st->need_solve && !(st->mu < 1.0)) {
+    if (P.strategy == SWGN_DOGLEG && st->active && st->need_solve && !(st->mu < 1.0)) {
       // the mu < max_mu loop of ComputeGaussNewtonStep ran out: linear solver failure (:542-597)
       st->need_solve = 0;
       st->solve_ok = 0;
@@ -132,9 +137,15 @@ __global__ void __launch_bounds__(kThreads) k_begin(DeviceBatch b, int tick) {
     }
   }
   if (s_flag[2]) {
-    const double sm = sqrt(st->mu);
     double* LM = v.W(W_LMD);
-    for (int k = tid; k < d.n_t; k += kThreads) LM[k] = DG[k] * sm;
+    if (P.strategy == SWGN_LEVENBERG_MARQUARDT) {
+      const double ir = 1.0 / sqrt(st->radius);  // lm_diagonal = sqrt(diagonal / radius), :86
+      const double* SC = v.W(W_SCALE);
+      for (int k = tid; k < d.n_t; k += kThreads) LM[k] = P.jacobi_scaling ? DG[k] * ir / SC[k] : DG[k] * ir;
+    } else {
+      const double sm = sqrt(st->mu);
+      for (int k = tid; k < d.n_t; k += kThreads) LM[k] = DG[k] * sm;
+    }
   }
   if (s_flag[3] && tid == 0) atomicAdd(b.counters + (tick & 1), 1);
 }
@@ -157,7 +168,24 @@ __global__ void __launch_bounds__(kThreads) k_step(DeviceBatch b) {
   const SolverParams& P = b.params;
   const int tid = threadIdx.x;
   int valid = 0;
-  if (st->solve_ok) {
+  if (st->solve_ok && P.strategy == SWGN_LEVENBERG_MARQUARDT) {
+    // step = -(linear solution), already in the unscaled space; model cost change (trust_region_minimizer.cc:414-431)
+    const double* Y = v.W(W_Y);
+    double* STEP = v.W(W_STEP);
+    for (int k = tid; k < d.n_t; k += kThreads) STEP[k] = -Y[k];
+    __syncthreads();
+    const double* R = v.W(W_RES);
+    double* MR = v.W(W_MRES);
+    double mc = 0.0;
+    for (int rs = tid; rs < d.n_res; rs += kThreads) {
+      const double m = row_dot(v, rs, STEP);
+      MR[rs] = m;
+      mc += m * (R[rs] + m / 2.0);
+    }
+    mc = block_sum(mc, red);
+    valid = (-mc > 0.0);
+    if (tid == 0) st->model_cost_change = -mc;
+  } else if (st->solve_ok) {
     const double* GN = v.W(W_GN);
     const double* GH = v.W(W_GHAT);
     const double* DG = v.W(W_DIAG);
@@ -225,8 +253,13 @@ __global__ void __launch_bounds__(kThreads) k_step(DeviceBatch b) {
         st->active = 0;
         st->termination = SWGN_FAILURE;
       } else {
-        st->mu *= 10.0;
-        st->reuse = 0;
+        if (P.strategy == SWGN_LEVENBERG_MARQUARDT) {  // StepIsInvalid = StepRejected (levenberg_marquardt_strategy.h:61-67)
+          st->radius = st->radius / st->decrease_factor;
+          st->decrease_factor *= 2.0;
+        } else {
+          st->mu *= 10.0;
+          st->reuse = 0;
+        }
         st->iter_cost = st->x_cost + st->fixed_cost;
         st->last_successful = 0;
       }
@@ -293,10 +326,16 @@ __global__ void __launch_bounds__(kThreads) k_end(DeviceBatch b) {
       if (q > P.min_relative_decrease) {
         accept = 1;
         s.accepted = 1;
-        if (q < 0.25) s.radius *= 0.5;
-        if (q > 0.75) s.radius = fmax(s.radius, 3.0 * s.dogleg_step_norm);
-        s.mu = fmax(P.min_mu, 2.0 * s.mu / 10.0);
-        s.reuse = 0;
+        if (P.strategy == SWGN_LEVENBERG_MARQUARDT) {  // LevenbergMarquardtStrategy::StepAccepted :151-158
+          s.radius = s.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * q - 1.0, 3.0));
+          s.radius = fmin(P.max_radius_lm, s.radius);
+          s.decrease_factor = 2.0;
+        } else {
+          if (q < 0.25) s.radius *= 0.5;
+          if (q > 0.75) s.radius = fmax(s.radius, 3.0 * s.dogleg_step_norm);
+          s.mu = fmax(P.min_mu, 2.0 * s.mu / 10.0);
+          s.reuse = 0;
+        }
         s.se_cur = s.candidate_cost;
         s.se_acc_cand += s.model_cost_change;
         s.se_acc_ref += s.model_cost_change;
@@ -319,8 +358,13 @@ __global__ void __launch_bounds__(kThreads) k_end(DeviceBatch b) {
       } else {
         s.last_successful = 0;
         s.iter_cost = s.candidate_cost + s.fixed_cost;
-        s.radius *= 0.5;
-        s.reuse = 1;
+        if (P.strategy == SWGN_LEVENBERG_MARQUARDT) {  // StepRejected :160-164
+          s.radius = s.radius / s.decrease_factor;
+          s.decrease_factor *= 2.0;
+        } else {
+          s.radius *= 0.5;
+          s.reuse = 1;
+        }
       }
     }
     *st = s;

@@ -873,7 +873,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   W[W_JAC] = n_jac_al;
   W[W_EBUF] = n_ebuf_al;
   W[W_RES] = W[W_MRES] = align2(n_res);
-  W[W_DIAG] = W[W_G] = W[W_GHAT] = W[W_GN] = W[W_STEP] = W[W_Y] = W[W_LMD] = align2(n_t);
+  W[W_DIAG] = W[W_G] = W[W_GHAT] = W[W_GN] = W[W_STEP] = W[W_Y] = W[W_LMD] = W[W_SCALE] = align2(n_t);
   W[W_EFAC] = align2(n_efac);
   W[W_S] = W[W_SCOPY] = align2((int64_t)n_f * d.ld);
   W[W_CHAIN] = align2(chain_work);

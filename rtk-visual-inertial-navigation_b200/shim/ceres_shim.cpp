@@ -222,10 +222,16 @@ void fail(Solver::Summary* s, const std::string& m) {
 
 void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* summary) {
   *summary = Solver::Summary();
-  if (options.linear_solver_type != DENSE_SCHUR || options.trust_region_strategy_type != DOGLEG || options.jacobi_scaling ||
-      options.minimizer_type != TRUST_REGION || options.use_nonmonotonic_steps)
-    return fail(summary, "swgn shim: only DENSE_SCHUR + TRADITIONAL DOGLEG, jacobi_scaling = false, monotonic steps is implemented "
+  // what the device path implements: DENSE_SCHUR with a user ordering, monotonic steps, and either TRADITIONAL DOGLEG with
+  // jacobi_scaling = false (the sliding-window solve, RVI/swf/swf.cpp:25-30) or LEVENBERG_MARQUARDT with or without
+  // jacobi_scaling (Ceres' defaults: the per-epoch GNSS solves, RVI/swf/swf_gnss.cpp:204-215,563-573)
+  if (options.linear_solver_type != DENSE_SCHUR || options.minimizer_type != TRUST_REGION || options.use_nonmonotonic_steps)
+    return fail(summary, "swgn shim: only TRUST_REGION + DENSE_SCHUR with monotonic steps is implemented");
+  if (options.trust_region_strategy_type == DOGLEG && (options.jacobi_scaling || options.dogleg_type != TRADITIONAL_DOGLEG))
+    return fail(summary, "swgn shim: DOGLEG is implemented as TRADITIONAL_DOGLEG with jacobi_scaling = false "
                          "(the reference's configuration, RVI/swf/swf.cpp:25-30)");
+  if (options.trust_region_strategy_type != DOGLEG && options.trust_region_strategy_type != LEVENBERG_MARQUARDT)
+    return fail(summary, "swgn shim: unknown trust-region strategy");
   if (!options.linear_solver_ordering) return fail(summary, "swgn shim: options.linear_solver_ordering is required");
 
   // ---- parameter blocks in insertion order
@@ -413,6 +419,8 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
   o.function_tolerance = options.function_tolerance;
   o.gradient_tolerance = options.gradient_tolerance;
   o.parameter_tolerance = options.parameter_tolerance;
+  o.trust_region_strategy = options.trust_region_strategy_type == DOGLEG ? SWGN_DOGLEG : SWGN_LEVENBERG_MARQUARDT;
+  o.jacobi_scaling = options.jacobi_scaling ? 1 : 0;
   o.is_optimize = internal::is_optimize ? 1 : 0;
   o.n_parameter_head = (int32_t)internal::parameter_head.size();
   o.device = options.device;

@@ -46,6 +46,7 @@ class Options(C.Structure):
         ("function_tolerance", f64), ("gradient_tolerance", f64), ("parameter_tolerance", f64),
         ("dogleg_min_mu", f64),
         ("is_optimize", i32), ("n_parameter_head", i32), ("device", i32), ("trust_region_strategy", i32),
+        ("jacobi_scaling", i32), ("reserved_", i32),
     ]
 
 

@@ -161,8 +161,59 @@ def test_oracle_levenberg_marquardt_step_and_radius_update(name):
     np.testing.assert_allclose(o.state(), minimum, atol=1e-4)
 
 
-def test_device_rejects_levenberg_marquardt_loudly():
+def test_oracle_jacobi_scaling_on_the_first_levenberg_marquardt_step():
+    """Solver::Options::jacobi_scaling (trust_region_minimizer.cc:261-276,437): columns scaled by s = 1 / (1 + |column|) of
+    the initial Jacobian; the strategy works on J diag(s), the step is mapped back with s."""
+    J, r, _ = fixture("ellipse")
+    J = J * np.array([1.0, 30.0, 0.02, 4.0, 1.0, 0.3])  # unequal column norms so that the scaling matters
+    lg = graph(J, r)
+    radius = 4.0
+    opt = lm_options(radius, 1)
+    opt.jacobi_scaling = 1
+    # (Marquardt's diagonal diag(J'J) / radius is invariant under column scaling: only the clamp makes the two differ)
+    opt.min_lm_diagonal, opt.max_lm_diagonal = 0.5, 1e32
+    o = ob.OracleSolver(lg.graph_p, opt)
+    _, sm = o.minimize()
+    sc = 1.0 / (1.0 + np.linalg.norm(J, axis=0))
+    Js = J * sc
+    D2 = np.clip((Js * Js).sum(axis=0), 0.5, 1e32) / radius
+    want = sc * -np.linalg.solve(Js.T @ Js + np.diag(D2), Js.T @ r)
+    np.testing.assert_allclose(o.state(), want, rtol=0, atol=1e-12 * max(1.0, np.abs(want).max()))
+    opt.jacobi_scaling = 0
+    o2 = ob.OracleSolver(lg.graph_p, opt)
+    o2.minimize()
+    assert np.abs(o2.state() - want).max() > 1e-6  # the scaling changes the damped step
+
+
+def test_device_rejects_dogleg_with_jacobi_scaling_loudly():
     J, r, _ = fixture("valley")
     lg = graph(J, r)
-    with pytest.raises(RuntimeError, match="DOGLEG"):
-        swgn.Batch([lg.graph_p], lm_options(2.0, 1))
+    opt = options(2.0)
+    opt.jacobi_scaling = 1
+    with pytest.raises(RuntimeError, match="jacobi_scaling"):
+        swgn.Batch([lg.graph_p], opt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ellipse", "valley"])
+@pytest.mark.parametrize("jacobi", [0, 1])
+def test_gpu_levenberg_marquardt_on_the_reference_fixtures(name, jacobi):
+    """The device's LEVENBERG_MARQUARDT strategy against the oracle (pinned above on the closed-form damped step and the
+    x3 radius update): one iteration and a converged run, with and without jacobi_scaling."""
+    J, r, minimum = fixture(name)
+    J = J * np.array([1.0, 30.0, 0.02, 4.0, 1.0, 0.3])
+    lg = graph(J, r)
+    for iters in (1, 2, 8):
+        opt = lm_options(4.0, iters)
+        opt.jacobi_scaling = jacobi
+        opt.min_lm_diagonal, opt.max_lm_diagonal = 0.5, 1e32
+        o = ob.OracleSolver(lg.graph_p, opt)
+        _, osm = o.minimize()
+        b = swgn.Batch([lg.graph_p], opt)
+        sm = b.solve()[0]
+        x = b.get_state(0, len(lg.state))
+        b.close()
+        assert (sm.num_iterations, sm.num_successful_steps, sm.num_unsuccessful_steps, sm.termination_type) == \
+            (osm.num_iterations, osm.num_successful_steps, osm.num_unsuccessful_steps, osm.termination_type)
+        np.testing.assert_allclose(x, o.state(), rtol=0, atol=1e-10 * max(1.0, np.abs(o.state()).max()))
+        assert abs(sm.final_cost - osm.final_cost) <= 1e-9 * max(osm.final_cost, 1e-12)

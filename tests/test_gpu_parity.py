@@ -150,6 +150,27 @@ def test_factor_kinds_the_default_window_does_not_hold(variant, shape):
     b.close()
 
 
+@pytest.mark.parametrize("which,wid,jacobi,iters", [(1, 0, 0, 8), (1, 4, 1, 8), (2, 0, 0, 8), (2, 6, 1, 8), (2, 1, 1, 20)])
+def test_levenberg_marquardt_solve_matches_oracle(which, wid, jacobi, iters):
+    """Ceres' default strategy (levenberg_marquardt_strategy.cc:66-165) with and without jacobi_scaling on the synthetic
+    windows: same accept / reject sequence and termination as the oracle, state within the dogleg tolerances."""
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    opt.trust_region_strategy = 1
+    opt.jacobi_scaling = jacobi
+    opt.max_num_iterations = iters
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    o = ob.OracleSolver(w.graph_p, opt)
+    st, osm = o.minimize()
+    assert st == 0
+    assert (sm.num_iterations, sm.num_successful_steps, sm.num_unsuccessful_steps, sm.termination_type, sm.num_linear_solves) == \
+        (osm.num_iterations, osm.num_successful_steps, osm.num_unsuccessful_steps, osm.termination_type, osm.num_linear_solves)
+    assert abs(sm.final_cost - osm.final_cost) <= TOL_COST * osm.final_cost
+    assert state_err(b.get_state(0, w.n_state), o.state()) < TOL_STATE
+    b.close()
+
+
 def test_converged_solve_and_early_termination():
     """More iterations than needed: function tolerance stops both paths at the same iteration."""
     w = swgn.SynthWindow(1, 2)
