@@ -26,5 +26,16 @@ g++ -O2 -fPIC -shared -ffp-contract=off -std=c++14 -I"$HERE/ref_stubs" -I"$HERE/
     "$REF/src/lambda.cpp" "$REF/src/common_function.cpp" \
     "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
     "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" \
-    "$HERE/ref_shim.cpp" -o "$HERE/_ref/libref_gnss.so"
+    "$HERE/ref_shim.cpp" "$HERE/ref_globals.cpp" -o "$HERE/_ref/libref_gnss.so"
 echo "built $HERE/_ref/libref_gnss.so"
+# The drop-in demonstration of the ceres:: shim on the reference's own factor classes (shim/ceres_shim_refdemo.cpp):
+# needs the product library (libswgn.so) and the generator, built by __graft_entry__.build() before this script runs.
+PKG="$HERE/../rtk-visual-inertial-navigation_b200"
+if [ -f "$PKG/libswgn.so" ] && [ -f "$PKG/libswgn_synth.so" ]; then
+  g++ -O2 -fPIC -shared -ffp-contract=off -std=c++17 -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" -I"$SRC" -I"$PKG/shim" \
+      "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
+      "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" "$REF/src/common_function.cpp" \
+      "$PKG/shim/ceres_shim.cpp" "$PKG/shim/ceres_shim_refdemo.cpp" "$HERE/ref_globals.cpp" \
+      -o "$HERE/_ref/libswgn_refdemo.so" -L"$PKG" -lswgn -lswgn_synth -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200'
+  echo "built $HERE/_ref/libswgn_refdemo.so"
+fi

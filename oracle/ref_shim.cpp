@@ -31,11 +31,7 @@ void ref_ecef2pos(const double* r, double* pos) { ecef2pos(r, pos); }
 
 double varerr2(double el, double dt, double mea_var);  // RVI/factor/gnss_factor.cpp:98-103 (no header declares it)
 
-// application globals the factor sources read (defined in RVI/parameter/parameters.cpp, which is not compiled)
-Eigen::Vector3d Pbg;
-Eigen::Matrix3d Rwgw;
-Eigen::Vector3d G;
-double ACC_N, ACC_W, GYR_N, GYR_W;
+// (the application globals the factor sources read -- Pbg, Rwgw, G, ACC_N ... -- are defined in oracle/ref_globals.cpp)
 
 namespace {
 void set_globals(const double* g /* Pbg3, gravity3, proj sqrt_info 4 */) {

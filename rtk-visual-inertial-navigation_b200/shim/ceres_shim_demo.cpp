@@ -56,6 +56,7 @@ class RTKCarrierPhaseFactor : public ceres::SizedCostFunction<1, 7, 1, 1> {
   double* satelite_pos;
   double L1_lam, lam, el, base_rover_time_diff, mea_var;
   double* base_pos;
+  bool use_istd = true;
 };
 class RTKPseudorangeFactor : public ceres::SizedCostFunction<1, 7, 1> {
  public:

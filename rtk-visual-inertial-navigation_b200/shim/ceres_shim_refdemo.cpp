@@ -1,0 +1,282 @@
+// Drop-in evidence for the ceres:: shim: a sliding-window problem built from the REFERENCE'S OWN factor classes --
+// RVI/factor/{projection_factor, imu_factor + integration_base, gnss_factor, pose_local_parameterization}.cpp, compiled
+// unmodified where they lie under /root/reference (oracle/build_ref.sh; Eigen is not installed, so against the minimal
+// stand-in of oracle/ref_stubs/) -- registered with the device adapters of shim/reference_adapters.h and solved by
+// ceres::Solve of the shim, i.e. on the GPU.  The costs the device reports are then checked against the costs the
+// reference's own Evaluate() methods give on the CPU at the same states.  TEST INFRASTRUCTURE: it links reference
+// code, is built only where /root/reference exists and lives in oracle/_ref/.
+// Two factor classes of the window cannot be compiled here (marginalization_factor.cpp needs Eigen's eigen-solver,
+// initial_factor.cpp is not on the hot path): they are stood in by classes with the same public members and a
+// restated Evaluate() (marginalization_factor.cpp:410-446, initial_factor.cpp:90-96).
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../synth/swgn_synth.h"
+#include "ceres/ceres.h"
+#include "ceres/schur_complement_solver.h"
+#include "factor/gnss_factor.h"
+#include "factor/imu_factor.h"
+#include "factor/pose_local_parameterization.h"
+#include "factor/projection_factor.h"
+#include "reference_adapters.h"
+
+extern Eigen::Vector3d Pbg;  // defined next to the factor trampolines (oracle/ref_shim.cpp)
+extern Eigen::Matrix3d Rwgw;
+extern Eigen::Vector3d G;
+
+namespace {
+class InitialBlackFactor : public ceres::SizedCostFunction<1, 1> {
+ public:
+  explicit InitialBlackFactor(double s) : istd(s) {}
+  bool Evaluate(double const* const* p, double* r, double** J) const override {
+    r[0] = p[0][0] * istd;
+    if (J && J[0]) J[0][0] = istd;
+    return true;
+  }
+  double istd;
+};
+struct MarginalizationInfo {
+  int m = 0, n = 0;
+  std::vector<int> keep_block_size, keep_block_idx;
+  std::vector<double*> keep_block_data;
+  Eigen::MatrixXd linearized_jacobians;
+  Eigen::VectorXd linearized_residuals;
+};
+class MarginalizationFactor : public ceres::CostFunction {
+ public:
+  explicit MarginalizationFactor(MarginalizationInfo* info) : marginalization_info(info) {
+    for (int s : info->keep_block_size) mutable_parameter_block_sizes()->push_back(s);
+    set_num_residuals(info->n);
+  }
+  bool Evaluate(double const* const* p, double* residuals, double**) const override {  // residual part of :410-433
+    const MarginalizationInfo& I = *marginalization_info;
+    std::vector<double> dx(I.n, 0.0);
+    for (size_t i = 0; i < I.keep_block_size.size(); ++i) {
+      const int size = I.keep_block_size[i], idx = I.keep_block_idx[i] - I.m;
+      const double* x = p[i];
+      const double* x0 = I.keep_block_data[i];
+      if (size != 7) {
+        for (int k = 0; k < size; ++k) dx[idx + k] = x[k] - x0[k];
+      } else {
+        for (int k = 0; k < 3; ++k) dx[idx + k] = x[k] - x0[k];
+        const Eigen::Quaterniond dq = Eigen::Quaterniond(x0[6], x0[3], x0[4], x0[5]).inverse() * Eigen::Quaterniond(x[6], x[3], x[4], x[5]);
+        const double sgn = dq.w() >= 0 ? 1.0 : -1.0;
+        dx[idx + 3] = sgn * 2.0 * dq.x();
+        dx[idx + 4] = sgn * 2.0 * dq.y();
+        dx[idx + 5] = sgn * 2.0 * dq.z();
+      }
+    }
+    for (int r = 0; r < I.n; ++r) {
+      double s = I.linearized_residuals(r);
+      for (int c = 0; c < I.n; ++c) s += I.linearized_jacobians(r, c) * dx[c];
+      residuals[r] = s;
+    }
+    return true;
+  }
+  MarginalizationInfo* marginalization_info;
+};
+
+struct Block {
+  ceres::CostFunction* f;
+  bool cauchy;
+  std::vector<double*> params;
+};
+// 1/2 sum rho(|r|^2) with the reference's own Evaluate() (Cauchy: rho = a^2 log(1 + s / a^2), loss_function.cc:73-80);
+// blocks whose parameters are all constant are the fixed cost
+double cpu_cost(const std::vector<Block>& blocks, double a) {
+  double total = 0.0;
+  std::vector<double> r;
+  for (const Block& b : blocks) {
+    r.assign(b.f->num_residuals(), 0.0);
+    b.f->Evaluate(b.params.data(), r.data(), nullptr);
+    double s = 0.0;
+    for (double v : r) s += v * v;
+    total += 0.5 * (b.cauchy && a > 0 ? a * a * std::log1p(s / (a * a)) : s);
+  }
+  return total;
+}
+
+void register_adapters() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  using namespace swgn_adapters;
+  ceres::swgn::RegisterAdapter(typeid(projection_factor), &projection<projection_factor>);
+  ceres::swgn::RegisterAdapter(typeid(IMUFactor), &imu<IMUFactor>);
+  ceres::swgn::RegisterAdapter(typeid(RTKCarrierPhaseFactor), &rtk_carrier_phase<RTKCarrierPhaseFactor>);
+  ceres::swgn::RegisterAdapter(typeid(RTKPseudorangeFactor), &rtk_pseudorange<RTKPseudorangeFactor>);
+  ceres::swgn::RegisterAdapter(typeid(SppPseudorangeFactor), &spp_pseudorange<SppPseudorangeFactor>);
+  ceres::swgn::RegisterAdapter(typeid(SppCarrierPhaseFactor), &spp_carrier_phase<SppCarrierPhaseFactor>);
+  ceres::swgn::RegisterAdapter(typeid(SppDopplerFactor), &spp_doppler<SppDopplerFactor>);
+  ceres::swgn::RegisterAdapter(typeid(FixedIntegerFactor), &fixed_integer<FixedIntegerFactor>);
+  ceres::swgn::RegisterAdapter(typeid(InitialBlackFactor), &unit_prior<InitialBlackFactor>);
+  ceres::swgn::RegisterAdapter(typeid(MarginalizationFactor), &marginalization<MarginalizationFactor>);
+}
+}  // namespace
+
+// Builds the composition-B synthetic window through the ceres:: API out of reference factor objects, solves it on the
+// device and reports cost_out = {device initial, device final, reference-CPU cost at the initial state, reference-CPU
+// cost at the returned state}.  strategy: 0 DOGLEG (jacobi_scaling false), 1 LEVENBERG_MARQUARDT with Ceres' default
+// jacobi_scaling = true.  Returns the termination type or -1.
+extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int variant, int strategy, int device, double* state_out,
+                                        double* cost_out, int* steps_out, char* message, int message_len) {
+  register_adapters();
+  swgn_synth_config cfg;
+  swgn_synth_default_config(which, &cfg);
+  cfg.variant = variant;
+  if (cfg.composition != 0) return -1;
+  swgn_synth* S = swgn_synth_create(&cfg, window_id);
+  if (!S) return -1;
+  const swgn_graph* g = swgn_synth_graph(S);
+  swgn_options so;
+  swgn_synth_options(S, &so);
+  std::vector<std::unique_ptr<double[]>> mem(g->n_blocks);
+  for (int b = 0; b < g->n_blocks; ++b) {
+    mem[b].reset(new double[g->block_size[b]]);
+    std::memcpy(mem[b].get(), g->state + g->block_offset[b], sizeof(double) * g->block_size[b]);
+  }
+  // the application globals, for the reference's Evaluate() on the CPU and for the device
+  Pbg = Eigen::Vector3d(g->Pbg[0], g->Pbg[1], g->Pbg[2]);
+  Rwgw = Eigen::Matrix3d::Identity();
+  G = Eigen::Vector3d(g->gravity[0], g->gravity[1], g->gravity[2]);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) projection_factor::sqrt_info(i, j) = g->proj_sqrt_info[2 * i + j];
+  ceres::swgn::Globals gl;
+  std::memcpy(gl.Pbg, g->Pbg, sizeof(gl.Pbg));
+  std::memcpy(gl.gravity, g->gravity, sizeof(gl.gravity));
+  std::memcpy(gl.proj_sqrt_info, g->proj_sqrt_info, sizeof(gl.proj_sqrt_info));
+  ceres::swgn::SetGlobals(gl);
+
+  std::vector<std::unique_ptr<IntegrationBase>> pre(g->n_imu);
+  std::vector<std::unique_ptr<MarginalizationInfo>> marg(g->n_prior);
+  std::vector<std::array<double, 12>> gnss_store(g->n_gnss);  // sat pos, sat vel, base pos, xyzt
+  std::vector<Block> blocks;
+  int result = -1;
+  {
+    ceres::Problem problem;
+    for (int b = 0; b < g->n_blocks; ++b) {
+      if (g->block_manifold[b] == SWGN_MANIFOLD_POSE) problem.AddParameterBlock(mem[b].get(), 7, new PoseLocalParameterization());
+      else problem.AddParameterBlock(mem[b].get(), g->block_size[b]);
+    }
+    auto add = [&](ceres::CostFunction* f, ceres::LossFunction* loss, std::vector<double*> params) {
+      problem.AddResidualBlock(f, loss, params);
+      blocks.push_back(Block{f, loss != nullptr, params});
+    };
+    for (int i = 0; i < g->n_proj; ++i)
+      add(new projection_factor(Eigen::Vector3d(g->proj_uv[2 * i], g->proj_uv[2 * i + 1], 1.0)), new ceres::CauchyLoss(g->proj_cauchy_a),
+          {mem[g->proj_blocks[3 * i]].get(), mem[g->proj_blocks[3 * i + 1]].get(), mem[g->proj_blocks[3 * i + 2]].get()});
+    for (int i = 0; i < g->n_imu; ++i) {
+      const double* r = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
+      pre[i].reset(new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero()));
+      IntegrationBase& ib = *pre[i];
+      for (int k = 0; k < 3; ++k) {
+        ib.delta_p(k) = r[SWGN_IMU_DELTA_P + k];
+        ib.delta_v(k) = r[SWGN_IMU_DELTA_V + k];
+        ib.linearized_ba(k) = r[SWGN_IMU_LIN_BA + k];
+        ib.linearized_bg(k) = r[SWGN_IMU_LIN_BG + k];
+        ib.gyri(k) = r[SWGN_IMU_GYRI + k];
+        ib.gyrj(k) = r[SWGN_IMU_GYRJ + k];
+      }
+      ib.delta_q = Eigen::Quaterniond(r[SWGN_IMU_DELTA_Q + 3], r[SWGN_IMU_DELTA_Q], r[SWGN_IMU_DELTA_Q + 1], r[SWGN_IMU_DELTA_Q + 2]);
+      ib.sum_dt = r[SWGN_IMU_SUM_DT];
+      for (int a = 0; a < 15; ++a)
+        for (int c = 0; c < 15; ++c) {
+          ib.jacobian(a, c) = r[SWGN_IMU_JACOBIAN + a * 15 + c];
+          ib.sqrt_info(a, c) = r[SWGN_IMU_SQRT_INFO + a * 15 + c];
+        }
+      ib.covariance_update = false;
+      add(new IMUFactor(&ib), nullptr,
+          {mem[g->imu_blocks[4 * i]].get(), mem[g->imu_blocks[4 * i + 1]].get(), mem[g->imu_blocks[4 * i + 2]].get(), mem[g->imu_blocks[4 * i + 3]].get()});
+    }
+    for (int i = 0; i < g->n_gnss; ++i) {
+      const double* r = g->gnss_data + (size_t)SWGN_GNSS_STRIDE * i;
+      std::memcpy(gnss_store[i].data(), r, sizeof(double) * 9);
+      double* sat = gnss_store[i].data();
+      double* vel = sat + 3;
+      double* base = sat + 6;
+      double* xyzt = sat + 9;
+      const int32_t* bl = g->gnss_blocks + 3 * i;
+      const double meas = r[SWGN_GNSS_MEAS], lam = r[SWGN_GNSS_LAM], wgt = r[SWGN_GNSS_WEIGHT];
+      const double el = r[SWGN_GNSS_EL], dt = r[SWGN_GNSS_DT], var = r[SWGN_GNSS_VAR];
+      std::vector<double*> p = {mem[bl[0]].get(), mem[bl[1]].get()};
+      if (bl[2] >= 0) p.push_back(mem[bl[2]].get());
+      switch (g->gnss_kind[i]) {
+        case SWGN_GNSS_SPP_PSEUDORANGE: add(new SppPseudorangeFactor(sat, meas, wgt, base), nullptr, p); break;
+        case SWGN_GNSS_SPP_CARRIER: add(new SppCarrierPhaseFactor(sat, meas, wgt, base, lam), nullptr, p); break;
+        case SWGN_GNSS_RTK_CARRIER: add(new RTKCarrierPhaseFactor(sat, meas, lam, el, dt, var, base, true, 0, 0), nullptr, p); break;
+        case SWGN_GNSS_RTK_PSEUDORANGE: add(new RTKPseudorangeFactor(sat, meas, el, dt, var, base), nullptr, p); break;
+        case SWGN_GNSS_DOPPLER: add(new SppDopplerFactor(vel, sat, xyzt, meas, wgt, base), nullptr, p); break;
+        case SWGN_GNSS_FIXED_INTEGER: add(new FixedIntegerFactor(meas, wgt), nullptr, p); break;
+      }
+    }
+    for (int i = 0; i < g->n_prior; ++i) {
+      marg[i].reset(new MarginalizationInfo());
+      MarginalizationInfo& m = *marg[i];
+      m.n = g->prior_n[i];
+      m.m = 0;
+      std::vector<double*> params;
+      const double* x0 = g->prior_x0 + g->prior_x0_begin[i];
+      for (int k = g->prior_blk_begin[i]; k < g->prior_blk_begin[i + 1]; ++k) {
+        const int b = g->prior_blocks[k];
+        m.keep_block_size.push_back(g->block_size[b]);
+        m.keep_block_idx.push_back(g->prior_blk_idx[k]);
+        m.keep_block_data.push_back(const_cast<double*>(x0));
+        x0 += g->block_size[b];
+        params.push_back(mem[b].get());
+      }
+      m.linearized_jacobians.resize(m.n, m.n);
+      m.linearized_residuals = Eigen::VectorXd(m.n);
+      for (int a = 0; a < m.n; ++a) {
+        m.linearized_residuals(a) = g->prior_r0[g->prior_r_begin[i] + a];
+        for (int c = 0; c < m.n; ++c) m.linearized_jacobians(a, c) = g->prior_J[g->prior_J_begin[i] + (size_t)a * m.n + c];
+      }
+      add(new MarginalizationFactor(&m), nullptr, params);
+    }
+    for (int i = 0; i < g->n_unit; ++i) add(new InitialBlackFactor(g->unit_istd[i]), nullptr, {mem[g->unit_block[i]].get()});
+    for (int b = 0; b < g->n_blocks; ++b)
+      if (g->block_const[b]) problem.SetParameterBlockConstant(mem[b].get());
+
+    ceres::Solver::Options options;  // Ceres' defaults: LEVENBERG_MARQUARDT, jacobi_scaling = true
+    options.linear_solver_type = ceres::DENSE_SCHUR;
+    if (strategy == 0) {
+      options.trust_region_strategy_type = ceres::DOGLEG;
+      options.jacobi_scaling = false;
+    }
+    options.max_num_iterations = so.max_num_iterations;
+    options.device = device;
+    options.linear_solver_ordering = std::make_shared<ceres::ParameterBlockOrdering>();
+    for (int b = 0; b < g->n_blocks; ++b)
+      if (g->block_group[b] >= 0) options.linear_solver_ordering->AddElementToGroup(mem[b].get(), g->block_group[b]);
+    ceres::internal::parameter_head.clear();
+    int32_t info[8];
+    swgn_synth_info(S, info);
+    for (int k = 0; k < so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(mem[info[5] + k].get());
+    ceres::internal::is_optimize = true;
+    const double cpu_initial = cpu_cost(blocks, g->proj_cauchy_a);
+    ceres::Solver::Summary summary;
+    ceres::Solve(options, &problem, &summary);
+    const double cpu_final = cpu_cost(blocks, g->proj_cauchy_a);
+    if (message && message_len > 0) std::snprintf(message, message_len, "%s | %s", summary.message.c_str(), summary.BriefReport().c_str());
+    if (summary.termination_type != ceres::FAILURE || summary.num_successful_steps >= 0) {
+      result = summary.termination_type;
+      if (cost_out) {
+        cost_out[0] = summary.initial_cost;
+        cost_out[1] = summary.final_cost;
+        cost_out[2] = cpu_initial;
+        cost_out[3] = cpu_final;
+      }
+      if (steps_out) {
+        steps_out[0] = summary.num_successful_steps;
+        steps_out[1] = summary.num_unsuccessful_steps;
+      }
+    }
+    ceres::internal::parameter_head.clear();
+  }
+  if (state_out)
+    for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], mem[b].get(), sizeof(double) * g->block_size[b]);
+  swgn_synth_destroy(S);
+  return result;
+}

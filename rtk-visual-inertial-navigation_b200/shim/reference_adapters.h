@@ -57,8 +57,10 @@ inline void gnss_common(FactorRecord* out, int kind, const double* sat, const do
 template <class F>
 bool rtk_carrier_phase(const CostFunction* cf, FactorRecord* out) {
   const F* f = static_cast<const F*>(cf);
+  // use_istd = false: sqrt_info is 1 (gnss_factor.cpp:116-117), as the per-epoch phase-bias initialisation builds the
+  // factor (swf_gnss.cpp:355,367: use_istd = false, mea_var = 0)
   gnss_common(out, SWGN_GNSS_RTK_CARRIER, f->satelite_pos, nullptr, f->base_pos, f->L1_lam, f->lam,
-              rtk_weight(f->el, f->base_rover_time_diff, f->mea_var));
+              f->use_istd ? rtk_weight(f->el, f->base_rover_time_diff, f->mea_var) : 1.0);
   out->data[SWGN_GNSS_EL] = f->el;
   out->data[SWGN_GNSS_DT] = f->base_rover_time_diff;
   out->data[SWGN_GNSS_VAR] = f->mea_var;
@@ -69,6 +71,9 @@ bool rtk_pseudorange(const CostFunction* cf, FactorRecord* out) {
   const F* f = static_cast<const F*>(cf);
   gnss_common(out, SWGN_GNSS_RTK_PSEUDORANGE, f->satelite_pos, nullptr, f->base_pos, f->P1, 0.0,
               rtk_weight(f->el, f->base_rover_time_diff, f->mea_var));
+  out->data[SWGN_GNSS_EL] = f->el;
+  out->data[SWGN_GNSS_DT] = f->base_rover_time_diff;
+  out->data[SWGN_GNSS_VAR] = f->mea_var;
   return true;
 }
 template <class F>

@@ -125,3 +125,49 @@ def test_imu_gnss_factor_through_ceres_api(which, wid):
     assert np.array_equal(state[~hidden], x[~hidden])
     assert cost[1] == sm.final_cost and steps == [sm.num_successful_steps, sm.num_unsuccessful_steps]
     b.close()
+
+
+def refdemo():
+    """oracle/_ref/libswgn_refdemo.so: shim/ceres_shim_refdemo.cpp + the reference's own factor sources (oracle/build_ref.sh)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libswgn_refdemo.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.swgn_ceres_refdemo_solve.restype = C.c_int
+    L.swgn_ceres_refdemo_solve.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_int),
+                                           C.c_char_p, C.c_int]
+    return L
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libswgn_refdemo.so")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("which,wid,variant,strategy", [(1, 0, 0, 0), (2, 0, 0, 0), (2, 2, 7, 0), (2, 1, 0, 1), (1, 3, 4, 1)])
+def test_reference_factor_classes_drop_in_through_the_shim(which, wid, variant, strategy):
+    """A window built from the REFERENCE'S OWN projection_factor / IMUFactor + IntegrationBase / RTK*, Spp*, FixedInteger
+    factor classes and PoseLocalParameterization (compiled unmodified from /root/reference), registered with
+    shim/reference_adapters.h and solved by the shim's ceres::Solve on the device, with the reference's DOGLEG settings
+    (strategy 0) and with Ceres' defaults LEVENBERG_MARQUARDT + jacobi_scaling (strategy 1).  The device's costs must be
+    the costs the reference's own Evaluate() methods give on the CPU at the same states, and the state must be the one
+    the C ABI returns for the same graph."""
+    w = swgn.SynthWindow(which, wid, variant=variant)
+    state = np.zeros(w.n_state)
+    cost = np.zeros(4)
+    steps = (C.c_int * 2)()
+    msg = C.create_string_buffer(512)
+    rc = refdemo().swgn_ceres_refdemo_solve(which, wid, variant, strategy, 0, state.ctypes.data_as(C.POINTER(f64)),
+                                            cost.ctypes.data_as(C.POINTER(f64)), steps, msg, 512)
+    assert rc in (0, 1), msg.value.decode()
+    dev_initial, dev_final, cpu_initial, cpu_final = cost
+    assert abs(dev_initial - cpu_initial) <= 1e-11 * cpu_initial, (dev_initial, cpu_initial)
+    assert abs(dev_final - cpu_final) <= 1e-9 * cpu_final, (dev_final, cpu_final)
+    assert dev_final < 1e-3 * dev_initial
+    opt = w.options()
+    if strategy == 1:
+        opt.trust_region_strategy = 1
+        opt.jacobi_scaling = 1
+    b = swgn.Batch([w.graph_p], opt)
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    b.close()
+    assert (steps[0], steps[1]) == (sm.num_successful_steps, sm.num_unsuccessful_steps)
+    assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9

@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_dogleg_golden.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_ceres_shim.py -x -q -m gpu 2>&1 | tail -25
