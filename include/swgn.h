@@ -298,8 +298,10 @@ swgn_status swgn_batch_set_state(swgn_batch* b, int32_t window, const double* st
 
 /* Same structure, new inputs (one frame later in a replayed sequence): re-packs the factor
    constants (measurements, pre-integration terms, priors) and initial states of all windows from
-   `graphs` and uploads them; fails with SWGN_ERR_INVALID when a graph's structure differs from the
-   one the batch was created with.  bytes_h2d (may be NULL) receives the bytes copied. */
+   `graphs` and uploads them; fails with SWGN_ERR_INVALID when a graph is NULL or its structure -- block table,
+   constness, ordering groups, any factor's block list or kind, prior / chain shapes, program order, is_use masks --
+   differs from the one the batch was created with (a fingerprint of all of these is kept per window).
+   bytes_h2d (may be NULL) receives the bytes copied. */
 swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* graphs,
                                      int64_t* bytes_h2d);
 

@@ -58,6 +58,9 @@ struct SlabCache {
   static constexpr size_t kMaxCount = 16, kHeadRoomBelow = (size_t)128 << 20;
 };
 SlabCache g_slabs;
+}  // namespace
+extern "C" int64_t swgn_release_cached_memory(void);
+namespace {
 
 cudaError_t slab_alloc(int kind, int device, size_t bytes, void** out, size_t* cap) {
   bytes = std::max<size_t>(bytes, 256);
@@ -80,7 +83,16 @@ cudaError_t slab_alloc(int kind, int device, size_t bytes, void** out, size_t* c
   // pinning a fresh buffer costs ~0.1 s
   if (bytes <= SlabCache::kHeadRoomBelow) bytes = (bytes + bytes / 4 + 65535) & ~(size_t)65535;
   *cap = bytes;
-  return kind == 0 ? cudaMalloc(out, bytes) : cudaMallocHost(out, bytes);
+  cudaError_t e = kind == 0 ? cudaMalloc(out, bytes) : cudaMallocHost(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    // the parked slabs of destroyed batches (other size classes, other devices) may be what is in the way: hand them
+    // back to the driver and try once more
+    cudaGetLastError();
+    swgn_release_cached_memory();
+    cudaSetDevice(device);
+    e = kind == 0 ? cudaMalloc(out, bytes) : cudaMallocHost(out, bytes);
+  }
+  return e;
 }
 void slab_free(int kind, int device, void* p, size_t cap) {
   if (!p) return;
@@ -98,7 +110,54 @@ void slab_free(int kind, int device, void* p, size_t cap) {
 }
 }  // namespace
 
+// Everything of a graph that the planner turned into index tables: block table, ordering, constness, every factor's
+// block list, prior shapes, chain shapes, program order and is_use masks.  swgn_batch_update_inputs re-packs constants
+// against the tables of the batch, so a graph is only accepted when this fingerprint is the one it was planned with.
+static uint64_t structure_fingerprint(const swgn_graph* g) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t bytes) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < bytes; ++i) h = (h ^ c[i]) * 1099511628211ull;
+  };
+  auto arr = [&](const int32_t* p, size_t n) {
+    const uint64_t tag = p ? n : ~0ull;
+    mix(&tag, sizeof(tag));
+    if (p && n) mix(p, sizeof(int32_t) * n);
+  };
+  const int32_t counts[10] = {g->n_blocks, g->n_state, g->n_proj, g->n_imu, g->n_gnss, g->n_prior, g->n_unit, g->n_order, g->n_chain,
+                              g->proj_cauchy_a > 0 ? 1 : 0};
+  mix(counts, sizeof(counts));
+  const size_t nb = (size_t)std::max(0, g->n_blocks);
+  arr(g->block_size, nb);
+  arr(g->block_manifold, nb);
+  arr(g->block_const, nb);
+  arr(g->block_group, nb);
+  arr(g->block_offset, nb);
+  arr(g->proj_blocks, 3 * (size_t)std::max(0, g->n_proj));
+  arr(g->imu_blocks, 4 * (size_t)std::max(0, g->n_imu));
+  arr(g->gnss_kind, (size_t)std::max(0, g->n_gnss));
+  arr(g->gnss_blocks, 3 * (size_t)std::max(0, g->n_gnss));
+  const size_t np = (size_t)std::max(0, g->n_prior);
+  arr(g->prior_n, np);
+  arr(g->prior_blk_begin, np ? np + 1 : 0);
+  const size_t npb = np && g->prior_blk_begin ? (size_t)g->prior_blk_begin[np] : 0;
+  arr(g->prior_blocks, npb);
+  arr(g->prior_blk_idx, npb);
+  arr(g->unit_block, (size_t)std::max(0, g->n_unit));
+  arr(reinterpret_cast<const int32_t*>(g->order), g->order ? (size_t)std::max(0, g->n_order) : 0);
+  const size_t nc = (size_t)std::max(0, g->n_chain);
+  arr(g->chain_blk_begin, nc ? nc + 1 : 0);
+  arr(g->chain_blocks, nc && g->chain_blk_begin ? (size_t)g->chain_blk_begin[nc] : 0);
+  arr(g->chain_frame_begin, nc ? nc + 1 : 0);
+  const size_t nf = (size_t)std::max(0, g->n_proj) + std::max(0, g->n_imu) + std::max(0, g->n_gnss) + np + std::max(0, g->n_unit) + nc;
+  const uint64_t use_tag = g->is_use ? nf : ~0ull;
+  mix(&use_tag, sizeof(use_tag));
+  if (g->is_use) mix(g->is_use, nf);
+  return h;
+}
+
 struct swgn_batch {
+  std::vector<uint64_t> fingerprint;  // per window: structure_fingerprint of the graph it was planned from
   int n = 0, device = 0;
   swgn_options opt;
   cudaStream_t stream = nullptr;
@@ -126,6 +185,7 @@ struct swgn_batch {
   bool has_scopy = false;
   // timing of the last solve
   std::vector<cudaEvent_t> ev;  // [0] start, [1] stop, then pairs around every Schur launch
+  cudaEvent_t ev_count[2] = {nullptr, nullptr};  // the active-window counter of a tick has reached the host
   double total_ms = 0, schur_ms = 0;
   int schur_launches = 0, kernel_launches = 0;
   bool solved = false;
@@ -187,7 +247,10 @@ void swgn_batch_destroy(swgn_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->ev)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->ev_count)
+    if (e) cudaEventDestroy(e);
   slab_free(0, b->device, b->d_slab, b->d_slab_cap);
   slab_free(1, b->device, b->h_slab, b->h_slab_cap);
   cudaFree(b->d_debug);
@@ -249,6 +312,8 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   b->desc.resize(n_windows);
   b->schur_doubles.resize(n_windows);
   b->state_off.resize(n_windows + 1);
+  b->fingerprint.resize(n_windows);
+  for (int w = 0; w < n_windows; ++w) b->fingerprint[w] = structure_fingerprint(graphs[w]);
   b->has_scopy = n_windows <= 256;
   size_t io = 0, co = 0, wo = 0;
   int max_wbuf = 0, max_nf = 0, max_prior_n = 0, max_chain = 0, max_chain_k = 0, sb_windows = 0;
@@ -609,6 +674,7 @@ swgn_status swgn_plan_stream_check(const swgn_graph* g, int32_t n_parameter_head
 swgn_status swgn_plan_stream_info(const swgn_graph* g, int32_t n_parameter_head, int32_t* info) {
   if (!g || !info) return fail(SWGN_ERR_INVALID, "bad arguments");
   WindowPlan p;
+  p.want_stream_plan = true;
   std::string err;
   swgn_status st = build_plan(g, n_parameter_head, &p, &err);
   if (st != SWGN_OK) return fail(st, err);
@@ -624,6 +690,7 @@ swgn_status swgn_plan_stream_info(const swgn_graph* g, int32_t n_parameter_head,
 swgn_status swgn_plan_array(const swgn_graph* g, int32_t n_parameter_head, int32_t array, int32_t* out, int64_t* n) {
   if (!g || !n || array < 0 || array >= NUM_IARR) return fail(SWGN_ERR_INVALID, "bad arguments");
   WindowPlan p;
+  p.want_stream_plan = true;
   std::string err;
   swgn_status st = build_plan(g, n_parameter_head, &p, &err);
   if (st != SWGN_OK) return fail(st, err);
@@ -674,9 +741,15 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
       const swgn_graph* g = graphs[w];
       const WinDesc& d = b->desc[w];
       int64_t sizes[NUM_CARR];
-      constant_sizes(g, sizes);
+      if (g) constant_sizes(g, sizes);
+      if (!g) {
+        bad.store(1);
+        chunk_done[w / per_chunk].fetch_add(1);
+        continue;
+      }
       bool ok = g->n_state == d.n_state && g->n_proj == d.n_proj && g->n_imu == d.n_imu && g->n_gnss == d.n_gnss &&
                 g->n_prior == d.n_prior && g->n_unit == d.n_unit && g->n_chain == d.n_chain;
+      if (ok) ok = structure_fingerprint(g) == b->fingerprint[w];
       if (ok && g->n_chain > 0) ok = g->chain_frame_begin[g->n_chain] == d.n_chain_frames;
       for (int a = 0; ok && a + 1 < NUM_CARR; ++a) ok = d.coff[a] + sizes[a] <= d.coff[a + 1];
       if (ok && w + 1 < b->n) ok = d.coff[NUM_CARR - 1] + sizes[NUM_CARR - 1] <= b->desc[w + 1].coff[0];
@@ -764,8 +837,8 @@ swgn_status swgn_batch_get_states(swgn_batch* b, double* states) {
 
 static cudaEvent_t get_event(swgn_batch* b, size_t i) {
   while (b->ev.size() <= i) {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;  // (recording on a null event fails with a CUDA error the caller reports)
     b->ev.push_back(e);
   }
   return b->ev[i];
@@ -787,12 +860,22 @@ swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
   b->h_counters[0] = b->h_counters[1] = -1;
   bool done = false;
   int tick = 0;
+  for (int q = 0; q < 2; ++q)
+    if (!b->ev_count[q]) CU(cudaEventCreateWithFlags(&b->ev_count[q], cudaEventDisableTiming));
+  cudaEvent_t* ev_count = b->ev_count;
   for (; tick < tick_limit && !done; ++tick) {
     const int slot = tick & 1;
+    // the count of active windows of tick - 2 has usually reached the host by now: when it is zero, no later tick has
+    // anything to do (checked without waiting; a solve that converges early stops issuing launches)
+    if (tick >= 2 && tick < max_iter && cudaEventQuery(ev_count[slot]) == cudaSuccess && b->h_counters[slot] == 0) {
+      done = true;
+      break;
+    }
     CU(cudaMemsetAsync(b->d_counters + slot, 0, sizeof(int32_t), s));
     launch_begin(db, tick, s);
     ++launches;
     CU(cudaMemcpyAsync(b->h_counters + slot, b->d_counters + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(ev_count[slot], s));
     if (tick >= max_iter) {
       // no window can still be running before tick max_iter unless it converged early; from
       // here on wait for the count of active windows

@@ -18,6 +18,8 @@
 //                                                           written in HBM/L2 exactly once per panel)
 // then the backward solve U z = w in 32-row blocks.  The factor stays in W_S: it is the
 // `lhs_out2 = llt.matrixL()` export (schur_complement_solver.cc:253-258) transposed.
+#include <mutex>
+
 #include "dev_common.cuh"
 #include "../../include/swgn.h"
 
@@ -463,7 +465,9 @@ void launch_tail_information(const DeviceBatch& b, int window, int n_tail, doubl
 // The opt-in dynamic shared memory limit is per function and per device: batches with different
 // reduced-system sizes share it, so it only ever grows.
 cudaError_t configure_chol(const DeviceBatch& b) {
+  static std::mutex mu;  // batches are created from several host threads
   static size_t granted[64] = {0};
+  std::lock_guard<std::mutex> lk(mu);
   const size_t dyn = chol_smem(b);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;
   int dev = 0;

@@ -15,6 +15,8 @@
 //   back-substitution: y_e = L^-T (w_g - sum_f W_f z_f).
 // (E'E + D^2)^-1 of the reference (InvertPSDMatrix, invert_psd_matrix.h:62-67: LLT-solve-identity)
 // is applied in factored form: buffer' inv buffer = (L^-1 buffer)'(L^-1 buffer).
+#include <mutex>
+
 #include "dev_common.cuh"
 #include "../../include/swgn.h"
 
@@ -932,7 +934,9 @@ void launch_backsub(const DeviceBatch& b, int only_window, cudaStream_t s) {
 }
 
 cudaError_t configure_schur(const DeviceBatch& b) {
+  static std::mutex mu;  // batches are created from several host threads
   static size_t granted[64] = {0};
+  std::lock_guard<std::mutex> lk(mu);
   static_assert(kSchurWarps == SCHUR_WARPS, "the gather streams are dealt to the warps of one CTA");
   const size_t dyn = schur_dyn_bytes(b);
   if (dyn > 227 * 1024) return cudaErrorInvalidValue;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // ---- run streams ---------------------------------------------------------------------------------------------
 // A warp's stream is a sequence of 16-byte units in global memory (L2): a run header followed by n/2 units of two
-// terms each.  Units arrive in a per-warp ring of 4 chunks x 8 units by cp.async, three chunks ahead of their use.
+// terms each.  Units arrive in a per-warp ring of 4 chunks x 8 units by cp.async, two chunks ahead of their use.
 struct Ring {
   int4 u[32];  // 4 chunks x 8 units
 };
@@ -101,13 +101,14 @@ struct Reader {
     __syncwarp();  // every lane is done with the ring contents of the previous stream
     issue();
     issue();
-    issue();
   }
-  // unit u (and everything before it) has landed
+  // unit u (and everything before it) has landed.  Two chunks are in flight in a ring of four: the chunk issued here
+  // (ready + 2) reuses the slot of chunk ready - 2, which every lane has left behind -- a group of two units may still
+  // straddle chunks ready - 1 and ready when this is called for its second unit.
   __device__ __forceinline__ void ensure(int u) {
     while (u >= ready * 8) {
-      cp_async_wait<2>();
-      __syncwarp();  // ... for every lane; also: all lanes are past chunk ready - 1, whose slot the next issue reuses
+      cp_async_wait<1>();
+      __syncwarp();  // ... for every lane
       ++ready;
       issue();
     }

@@ -811,7 +811,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   }
 
   // ---- streamed Schur elimination (plan_stream.cpp); windows that do not fit its on-chip budget keep the gather kernel
-  build_stream_plan(P, n_rows, n_cols, n_ecols, n_jac, n_res, col_size, col_pos);
+  P->sb = StreamPlanInfo();
+  if (P->want_stream_plan || stream_enabled()) build_stream_plan(P, n_rows, n_cols, n_ecols, n_jac, n_res, col_size, col_pos);
 
   // ---- descriptor
   WinDesc& d = P->d;

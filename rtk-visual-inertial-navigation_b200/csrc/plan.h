@@ -27,7 +27,9 @@ struct WindowPlan {
   int64_t schur_doubles;
   int64_t n_mma = 0;                       // tensor-core MMAs of one Schur gather pass (planning statistic)
   StreamPlanInfo sb;
+  bool want_stream_plan = false;           // plan the streamed Schur elimination even when it is not enabled (probes, tests)
 };
+bool stream_enabled();                     // SWGN_SCHUR_STREAM=1
 
 // dynamic shared memory of k_schur_stream for a window (or a batch: pass the maxima) with these sizes
 size_t stream_smem_bytes(int nbatch, int acc, int jcap, int rcap, int ecap, int fcap, int reccap);

@@ -40,6 +40,11 @@ struct Job {
 
 }  // namespace
 
+bool stream_enabled() {
+  static const bool enabled = std::getenv("SWGN_SCHUR_STREAM") && std::atoi(std::getenv("SWGN_SCHUR_STREAM")) != 0;
+  return enabled;
+}
+
 size_t stream_smem_bytes(int nbatch, int acc, int jcap, int rcap, int ecap, int fcap, int seccap) {
   // [2 mbarriers | per-warp record rings | batch headers | 2 section buffers | operand area | accumulators], 16-byte aligned parts
   size_t b = 16 + (size_t)SB_WARPS * SB_RING_BYTES;
@@ -454,7 +459,7 @@ void build_stream_plan(WindowPlan* P, int n_rows, int n_cols, int n_ecols, int n
   const size_t scratch = sizeof(int32_t) * 2 * (size_t)al4(reccap) + sizeof(double) * (size_t)(2 * (jcap + rcap) + ecap + fcap);
   // opt-in (SWGN_SCHUR_STREAM=1): on the B200 the streamed kernel cuts the DRAM traffic of the elimination to the
   // algorithmic bytes but is instruction / latency bound and, as measured, still slower than the gather kernel
-  static const bool enabled = std::getenv("SWGN_SCHUR_STREAM") && std::atoi(std::getenv("SWGN_SCHUR_STREAM")) != 0;
+  const bool enabled = stream_enabled();
   sb.fits = sb.nbatch > 0 && sb.nbatch <= 1024 && smem <= (size_t)SB_SMEM_BUDGET && tables <= scratch;
   sb.ok = enabled && sb.nbatch > 0 && sb.nbatch <= 1024 && smem <= (size_t)SB_SMEM_BUDGET && tables <= scratch;
 }

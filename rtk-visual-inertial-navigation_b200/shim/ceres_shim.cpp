@@ -257,6 +257,40 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
     boff.push_back((int32_t)state.size());
     state.insert(state.end(), p, p + info.size);
   }
+  // ---- a problem without a variable parameter block never reaches the device: like Ceres (solver.cc Minimize:
+  // "No non-constant parameter blocks found", reduced program empty) it converges at once with the fixed cost, which is
+  // evaluated -- as Ceres does in Program::RemoveFixedBlocks, program.cc:304-411 -- by the user's own cost functions
+  {
+    bool any_variable = false;
+    for (internal::ResidualBlock* rb : problem->residual_block_list())
+      for (double* p : rb->parameter_blocks())
+        if (!bmap.at(p).constant) any_variable = true;
+    if (!any_variable) {
+      double fixed = 0.0;
+      std::vector<double> r;
+      for (internal::ResidualBlock* rb : problem->residual_block_list()) {
+        const CostFunction* cf = rb->cost_function();
+        r.assign(cf->num_residuals(), 0.0);
+        if (!cf->Evaluate(rb->parameter_blocks().data(), r.data(), nullptr)) return fail(summary, "swgn shim: evaluation of a fixed residual block failed");
+        double sq = 0.0;
+        for (double v : r) sq += v * v;
+        if (rb->loss_function()) {
+          double rho[3];
+          rb->loss_function()->Evaluate(sq, rho);
+          sq = rho[0];
+        }
+        fixed += 0.5 * sq;
+      }
+      summary->termination_type = CONVERGENCE;
+      summary->message = "Function tolerance reached. No non-constant parameter blocks found.";
+      summary->initial_cost = summary->final_cost = summary->fixed_cost = fixed;
+      summary->num_successful_steps = summary->num_unsuccessful_steps = summary->num_linear_solves = 0;
+      summary->num_parameter_blocks = (int)blocks.size();
+      summary->num_residual_blocks = (int)problem->residual_block_list().size();
+      summary->num_parameter_blocks_reduced = summary->num_residuals_reduced = 0;
+      return;
+    }
+  }
   // ---- residual blocks through the adapters
   std::vector<int32_t> proj_blocks, imu_blocks, gnss_kind, gnss_blocks, prior_n, prior_blk_begin{0}, prior_blocks, prior_blk_idx, unit_block;
   std::vector<int64_t> prior_x0_begin, prior_J_begin, prior_r_begin;

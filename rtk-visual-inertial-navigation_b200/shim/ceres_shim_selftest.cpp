@@ -1,6 +1,7 @@
 // Host-only checks of the ceres::Problem bookkeeping (no device): the semantics the reference
 // relies on (CERES/internal/ceres/problem_impl.cc:280-478,886; problem_test.cc): pointer identity,
 // cascading RemoveParameterBlock, residual-block index reuse, constness, ordering groups, is_use.
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -14,6 +15,12 @@ struct Unary : ceres::SizedCostFunction<1, 1> {
 };
 struct Binary : ceres::SizedCostFunction<2, 3, 1> {
   bool Evaluate(double const* const*, double*, double**) const override { return true; }
+};
+struct Scaled : ceres::SizedCostFunction<1, 1> {  // r = 3 x
+  bool Evaluate(double const* const* p, double* r, double**) const override {
+    r[0] = 3.0 * p[0][0];
+    return true;
+  }
 };
 int g_deleted = 0;
 struct Counted : ceres::SizedCostFunction<1, 1> {
@@ -96,6 +103,26 @@ extern "C" int swgn_ceres_selftest() {
     opt.linear_solver_ordering->AddElementToGroup(y, 0);
     ceres::Solve(opt, &p, &s);  // Unary has no adapter registered
     EXPECT(s.termination_type == ceres::FAILURE && s.message.find("adapter") != std::string::npos);
+  }
+  {  // a problem without a variable parameter block converges at once with the fixed cost, evaluated by the user's own
+     // cost and loss functions, like Ceres (solver.cc: "No non-constant parameter blocks found"); no device is touched
+    ceres::Problem p;
+    double a[1] = {2.0}, b[1] = {-1.0};
+    p.AddResidualBlock(new Scaled, nullptr, a);
+    p.AddResidualBlock(new Scaled, new ceres::CauchyLoss(1.0), b);
+    p.SetParameterBlockConstant(a);
+    p.SetParameterBlockConstant(b);
+    ceres::Solver::Options opt;
+    opt.linear_solver_type = ceres::DENSE_SCHUR;
+    opt.linear_solver_ordering = std::make_shared<ceres::ParameterBlockOrdering>();
+    opt.linear_solver_ordering->AddElementToGroup(a, 0);
+    opt.linear_solver_ordering->AddElementToGroup(b, 1);
+    ceres::Solver::Summary s;
+    ceres::Solve(opt, &p, &s);
+    const double want = 0.5 * 36.0 + 0.5 * std::log(1.0 + 9.0);
+    EXPECT(s.termination_type == ceres::CONVERGENCE && s.IsSolutionUsable());
+    EXPECT(std::fabs(s.fixed_cost - want) < 1e-14 && s.initial_cost == s.fixed_cost && s.final_cost == s.fixed_cost);
+    EXPECT(a[0] == 2.0 && b[0] == -1.0);
   }
   EXPECT(ceres::internal::is_optimize == true && ceres::internal::parameter_head.empty());
   return 0;

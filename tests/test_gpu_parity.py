@@ -557,3 +557,29 @@ def test_window_without_retained_blocks_solves_like_the_oracle():
     assert sm.termination_type == osm.termination_type and sm.num_iterations == osm.num_iterations
     assert abs(sm.final_cost - osm.final_cost) <= 1e-12 * osm.final_cost
     np.testing.assert_allclose(x, o.state(), rtol=0, atol=1e-12)
+
+
+def test_update_inputs_rejects_a_graph_with_another_structure():
+    """Same factor counts, different structure (two projection factors exchange their landmarks; a block turns constant; a
+    NULL graph): swgn_batch_update_inputs must answer SWGN_ERR_INVALID instead of repacking against the old tables."""
+    w = swgn.SynthWindow(1, 0)
+    b = swgn.Batch([w.graph_p], w.options())
+    assert b.update_inputs([w.graph_p]) > 0  # unchanged structure: accepted
+    w2 = swgn.SynthWindow(1, 0)
+    g = w2.graph
+    k = next(i for i in range(1, g.n_proj) if g.proj_blocks[3 * i + 2] != g.proj_blocks[2])
+    g.proj_blocks[2], g.proj_blocks[3 * k + 2] = g.proj_blocks[3 * k + 2], g.proj_blocks[2]
+    with pytest.raises(RuntimeError, match="structure"):
+        b.update_inputs([w2.graph_p])
+    g.proj_blocks[2], g.proj_blocks[3 * k + 2] = g.proj_blocks[3 * k + 2], g.proj_blocks[2]
+    assert b.update_inputs([w2.graph_p]) > 0
+    g.block_const[0] = 1
+    with pytest.raises(RuntimeError, match="structure"):
+        b.update_inputs([w2.graph_p])
+    g.block_const[0] = 0
+    null = (C.POINTER(swgn.Graph) * 1)()
+    nb = C.c_int64()
+    assert swgn.lib().swgn_batch_update_inputs(b.h, null, C.byref(nb)) == 1  # SWGN_ERR_INVALID
+    sm = b.solve()[0]  # the batch is still usable
+    assert sm.termination_type in (0, 1)
+    b.close()

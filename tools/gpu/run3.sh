@@ -1,2 +1,3 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_ceres_shim.py -x -q -m gpu 2>&1 | tail -25
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 600 python tools/single_window_latency.py 2>&1 | tail -3
