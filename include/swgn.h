@@ -428,6 +428,18 @@ swgn_status swgn_ambiguity_fix(int32_t device, int32_t n, const double* A, const
                                int32_t last_fix, int32_t* dd_pairs /* 2 per row: (a, ref) */,
                                double* F /* n_dd x 2 column-major */, swgn_fix_result* result);
 
+/* The same decision for EVERY window of a batch after its solve, without a host loop (BASELINE configs[3] over a batch):
+   launch 1 computes, per window, A = the tail information of the last Cholesky factor (UpdateSchurHessianOnly) and y = the
+   current values of the n_tail scalar blocks at the end of the ordering (the float ambiguities, parameter_head); launch 2
+   runs the double-difference construction, lambda() and the ratio tests, one thread per window.  Epochs are given as a
+   CSR of CSRs: window w owns the epochs [win_epoch[w], win_epoch[w+1]) of epoch_begin (total_epochs + 1 global offsets
+   into obs_amb / obs_sysfreq, semantics as above); last_fix (may be NULL = all 0) holds one flag per window.
+   results: n_windows entries (status 3 also for windows without a factor); dd_pairs (2 * n_tail ints per window) and F
+   (2 * n_tail doubles per window, n_dd x 2 column-major) may be NULL. */
+swgn_status swgn_batch_ambiguity_fix(swgn_batch* b, int32_t n_tail, const int32_t* win_epoch, const int32_t* epoch_begin,
+                                     const int32_t* obs_amb, const int32_t* obs_sysfreq, const int32_t* last_fix,
+                                     swgn_fix_result* results, int32_t* dd_pairs, double* F);
+
 #ifdef __cplusplus
 }
 #endif

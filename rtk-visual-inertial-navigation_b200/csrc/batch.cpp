@@ -1005,6 +1005,62 @@ swgn_status swgn_batch_get_tail_information(swgn_batch* b, int32_t w, int32_t n_
   return SWGN_OK;
 }
 
+swgn_status swgn_batch_ambiguity_fix(swgn_batch* b, int32_t n_tail, const int32_t* win_epoch, const int32_t* epoch_begin,
+                                     const int32_t* obs_amb, const int32_t* obs_sysfreq, const int32_t* last_fix,
+                                     swgn_fix_result* results, int32_t* dd_pairs, double* F) {
+  if (!b || n_tail <= 0 || !win_epoch || !epoch_begin || !obs_amb || !obs_sysfreq || !results) return fail(SWGN_ERR_INVALID, "bad arguments");
+  const int nw = b->n;
+  if (win_epoch[0] < 0) return fail(SWGN_ERR_INVALID, "bad epoch list");
+  for (int w = 0; w < nw; ++w)
+    if (win_epoch[w + 1] < win_epoch[w] + 1) return fail(SWGN_ERR_INVALID, "every window needs at least one epoch");
+  const int n_ep = win_epoch[nw];
+  for (int e = 0; e < n_ep; ++e)
+    if (epoch_begin[e + 1] < epoch_begin[e] || epoch_begin[e] < 0) return fail(SWGN_ERR_INVALID, "epoch offsets are not monotone");
+  const int n_obs = epoch_begin[n_ep];
+  CU(cudaSetDevice(b->device));
+  cudaStream_t s = b->stream;
+  const size_t n = (size_t)n_tail, nwk = fix_work_doubles(n_tail), niw = fix_work_ints(n_tail);
+  // one device block: A | y | F | work (doubles), then results, then the int arrays
+  const size_t n_dbl = (size_t)nw * (n * n + n + 2 * n + nwk);
+  const size_t n_int = (size_t)nw * (1 + 2 * n + niw + 1) + (size_t)(nw + 1) + (size_t)(n_ep + 1) + 2 * (size_t)(n_obs + 1);
+  const size_t bytes = sizeof(double) * n_dbl + sizeof(swgn_fix_result) * (size_t)nw + sizeof(int32_t) * n_int + 64;
+  char* dbuf = nullptr;
+  CU(cudaMalloc(&dbuf, bytes));
+  double* dA = reinterpret_cast<double*>(dbuf);
+  double* dy = dA + (size_t)nw * n * n;
+  double* dF = dy + (size_t)nw * n;
+  double* dwork = dF + (size_t)nw * 2 * n;
+  swgn_fix_result* dres = reinterpret_cast<swgn_fix_result*>(dwork + (size_t)nw * nwk);
+  int32_t* dhave = reinterpret_cast<int32_t*>(dres + nw);
+  int32_t* dpairs = dhave + nw;
+  int32_t* diwork = dpairs + (size_t)nw * 2 * n;
+  int32_t* dlast = diwork + (size_t)nw * niw;
+  int32_t* dwin = dlast + nw;
+  int32_t* deb = dwin + (nw + 1);
+  int32_t* doa = deb + (n_ep + 1);
+  int32_t* dsf = doa + (n_obs + 1);
+  cudaError_t e = cudaMemcpyAsync(dwin, win_epoch, sizeof(int32_t) * (nw + 1), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(deb, epoch_begin, sizeof(int32_t) * (n_ep + 1), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && n_obs > 0) e = cudaMemcpyAsync(doa, obs_amb, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && n_obs > 0) e = cudaMemcpyAsync(dsf, obs_sysfreq, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = last_fix ? cudaMemcpyAsync(dlast, last_fix, sizeof(int32_t) * nw, cudaMemcpyHostToDevice, s)
+                                     : cudaMemsetAsync(dlast, 0, sizeof(int32_t) * nw, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dF, 0, sizeof(double) * (size_t)nw * 2 * n, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dpairs, 0, sizeof(int32_t) * (size_t)nw * 2 * n, s);
+  if (e == cudaSuccess) {
+    launch_tail_information_batch(b->db, n_tail, dA, dy, dhave, s);
+    launch_ambiguity_fix_batch(nw, n_tail, dA, dy, dwin, deb, doa, dsf, dlast, dhave, dpairs, dF, dres, dwork, diwork, s);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(results, dres, sizeof(swgn_fix_result) * (size_t)nw, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && dd_pairs) e = cudaMemcpyAsync(dd_pairs, dpairs, sizeof(int32_t) * (size_t)nw * 2 * n, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && F) e = cudaMemcpyAsync(F, dF, sizeof(double) * (size_t)nw * 2 * n, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(dbuf);
+  CU(e);
+  return SWGN_OK;
+}
+
 swgn_status swgn_preintegrate_batch(int32_t device, int32_t n_factors, const int32_t* sample_begin, const double* samples,
                                     const double* bias, const double noise[4], double* records, int32_t* info) {
   if (n_factors <= 0 || !sample_begin || !samples || !bias || !noise || !records) return fail(SWGN_ERR_INVALID, "bad arguments");

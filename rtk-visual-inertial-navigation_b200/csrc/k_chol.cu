@@ -441,6 +441,33 @@ __global__ void k_tail_information(DeviceBatch b, int window, int n_tail, double
   }
 }
 
+// ... for every window of the batch at once (one CTA per window), together with y = the current values of the n_tail
+// scalar blocks at the end of the ordering (the float ambiguities) and a flag whether the window holds a factor
+__global__ void k_tail_information_batch(DeviceBatch b, int n_tail, double* A_all, double* y_all, int32_t* have_A) {
+  const int w = blockIdx.x;
+  const WinDesc& d = b.desc[w];
+  const TRState* st = b.state + w;
+  const int ok = st->have_factor && d.n_f >= n_tail && d.n_cols - d.n_ecols >= n_tail;
+  if (threadIdx.x == 0) have_A[w] = ok;
+  if (!ok) return;
+  const double* S = b.wpool + d.woff[W_S];
+  const int nf = d.n_f, ld = d.ld, m = nf - n_tail;
+  double* A = A_all + (size_t)w * n_tail * n_tail;
+  for (int e = threadIdx.x; e < n_tail * n_tail; e += blockDim.x) {
+    const int i = e / n_tail, j = e - i * n_tail;
+    double s = 0.0;
+    for (int k = 0; k < n_tail; ++k) {
+      const double li = (k <= i) ? S[(size_t)(m + k) * ld + m + i] : 0.0;
+      const double lj = (k <= j) ? S[(size_t)(m + k) * ld + m + j] : 0.0;
+      s += li * lj;
+    }
+    A[e] = s;
+  }
+  const int32_t* col_state = b.ipool + d.ioff[I_COL_STATE];
+  const double* x = b.wpool + d.woff[W_X];
+  for (int k = threadIdx.x; k < n_tail; k += blockDim.x) y_all[(size_t)w * n_tail + k] = x[col_state[d.n_cols - n_tail + k]];
+}
+
 int chol_block(const DeviceBatch& b) { return b.max_nf <= 760 ? 32 : 16; }
 int chol_pitch(const DeviceBatch& b) {
   const int NB = chol_block(b);
@@ -456,6 +483,10 @@ size_t chol_smem(const DeviceBatch& b) {
 void launch_chol(const DeviceBatch& b, int only_window, cudaStream_t s) {
   const int grid = only_window >= 0 ? 1 : b.n_windows;
   k_chol<<<grid, kThreads, chol_smem(b), s>>>(b, only_window, chol_block(b), chol_pitch(b));
+}
+
+void launch_tail_information_batch(const DeviceBatch& b, int n_tail, double* A_all, double* y_all, int32_t* have_A, cudaStream_t s) {
+  k_tail_information_batch<<<b.n_windows, 128, 0, s>>>(b, n_tail, A_all, y_all, have_A);
 }
 
 void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s) {

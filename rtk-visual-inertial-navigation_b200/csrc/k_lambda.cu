@@ -340,8 +340,7 @@ struct FixArgs {
   int32_t* iwork;  // 6 n + n_obs
 };
 
-__global__ void k_ambiguity_fix(FixArgs g) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__device__ void ambiguity_fix_one(const FixArgs& g) {
   const int n = g.n;
   swgn_fix_result res;
   res.n_dd = 0; res.status = 0; res.search_ok = 0; res.n_different = 0;
@@ -511,7 +510,56 @@ __global__ void k_ambiguity_fix(FixArgs g) {
   *g.res = res;
 }
 
+__global__ void k_ambiguity_fix(FixArgs g) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  ambiguity_fix_one(g);
+}
+
 }  // namespace
+
+size_t fix_work_doubles(int n) { return (size_t)8 * n * n + (size_t)8 * n + lambda_work_doubles(n, 2); }
+size_t fix_work_ints(int n) { return (size_t)6 * n + 8; }
+
+// One thread per window: the same sequential decision code, thousands of windows side by side.
+__global__ void k_ambiguity_fix_batch(int n_windows, int n, const double* A_all, const double* y_all, const int32_t* win_epoch,
+                                      const int32_t* epoch_begin, const int32_t* obs_amb, const int32_t* obs_sysfreq,
+                                      const int32_t* last_fix, const int32_t* have_A, int32_t* dd_pairs, double* F, swgn_fix_result* res,
+                                      double* work, int32_t* iwork, size_t nwork, size_t niwork) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_windows) return;
+  if (!have_A[w]) {  // no Cholesky factor (the last reduced solve failed): nothing to search
+    swgn_fix_result r;
+    r.n_dd = 0; r.status = 3; r.search_ok = 0; r.n_different = 0;
+    r.s[0] = r.s[1] = 0.0; r.s0_partial = r.s1_partial = 0.0;
+    res[w] = r;
+    return;
+  }
+  FixArgs g;
+  g.n = n;
+  g.n_epochs = win_epoch[w + 1] - win_epoch[w];
+  g.last_fix = last_fix ? last_fix[w] : 0;
+  g.A = A_all + (size_t)w * n * n;
+  g.y = y_all + (size_t)w * n;
+  g.epoch_begin = epoch_begin + win_epoch[w];
+  g.obs_amb = obs_amb;
+  g.obs_sysfreq = obs_sysfreq;
+  g.dd_pairs = dd_pairs + (size_t)2 * n * w;
+  g.F = F + (size_t)2 * n * w;
+  g.res = res + w;
+  g.work = work + nwork * w;
+  g.iwork = iwork + niwork * w;
+  ambiguity_fix_one(g);
+}
+
+void launch_ambiguity_fix_batch(int n_windows, int n, const double* A_all, const double* y_all, const int32_t* win_epoch,
+                                const int32_t* epoch_begin, const int32_t* obs_amb, const int32_t* obs_sysfreq, const int32_t* last_fix,
+                                const int32_t* have_A, int32_t* dd_pairs, double* F, swgn_fix_result* res, double* work, int32_t* iwork,
+                                cudaStream_t s) {
+  const int threads = 32;
+  k_ambiguity_fix_batch<<<(n_windows + threads - 1) / threads, threads, 0, s>>>(n_windows, n, A_all, y_all, win_epoch, epoch_begin, obs_amb,
+                                                                               obs_sysfreq, last_fix, have_A, dd_pairs, F, res, work, iwork,
+                                                                               fix_work_doubles(n), fix_work_ints(n));
+}
 
 size_t lambda_work_doubles(int n, int m) { return (size_t)3 * n * n + (size_t)n * m + (size_t)8 * n + 8; }
 
@@ -603,8 +651,8 @@ extern "C" swgn_status swgn_ambiguity_fix(int32_t device, int32_t n, const doubl
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SWGN_ERR_NO_DEVICE;
   swgn_status st = SWGN_OK;
   const int n_obs = epoch_begin[n_epochs];
-  const size_t nwork = (size_t)8 * n * n + (size_t)8 * n + swgn::lambda_work_doubles(n, 2);
-  const size_t niwork = (size_t)6 * n + 8;
+  const size_t nwork = swgn::fix_work_doubles(n);
+  const size_t niwork = swgn::fix_work_ints(n);
   double *d_A = nullptr, *d_y = nullptr, *d_F = nullptr, *d_work = nullptr;
   int32_t *d_eb = nullptr, *d_oa = nullptr, *d_sf = nullptr, *d_pairs = nullptr, *d_iwork = nullptr;
   swgn_fix_result* d_res = nullptr;

@@ -6,6 +6,8 @@
 
 #include "device_types.h"
 
+struct swgn_fix_result;
+
 namespace swgn {
 
 struct DeviceBatch {
@@ -70,5 +72,14 @@ void launch_lambda_batch(int n_problems, int m, const int32_t* n_dev, const int6
                          double* F_dev, double* s_dev, int32_t* info_dev, double* work_dev,
                          const int64_t* woff_dev, cudaStream_t s);
 size_t lambda_work_doubles(int n, int m);
+// K7 + K8 for a whole batch: tail information and float ambiguities of every window (one CTA each), then the
+// LambdaSearch decision of every window (one thread each)
+void launch_tail_information_batch(const DeviceBatch& b, int n_tail, double* A_all, double* y_all, int32_t* have_A, cudaStream_t s);
+size_t fix_work_doubles(int n);
+size_t fix_work_ints(int n);
+void launch_ambiguity_fix_batch(int n_windows, int n, const double* A_all, const double* y_all, const int32_t* win_epoch,
+                                const int32_t* epoch_begin, const int32_t* obs_amb, const int32_t* obs_sysfreq, const int32_t* last_fix,
+                                const int32_t* have_A, int32_t* dd_pairs, double* F, struct ::swgn_fix_result* res, double* work,
+                                int32_t* iwork, cudaStream_t s);
 
 }  // namespace swgn

@@ -260,6 +260,7 @@ def lib():
         L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_ambiguity_fix.argtypes = [i32, i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32),
                                          i32, P(i32), P(f64), P(FixResult)]
+        L.swgn_batch_ambiguity_fix.argtypes = [C.c_void_p, i32, P(i32), P(i32), P(i32), P(i32), P(i32), P(FixResult), P(i32), P(f64)]
         _lib = L
     return _lib
 
@@ -451,6 +452,26 @@ class Batch:
             Dp = _dp(D)
         _check(lib().swgn_batch_linear_solve(self.h, w, Dp, _dp(x)), "linear_solve")
         return x
+
+    def ambiguity_fix_all(self, n_tail, epochs, last_fix=None):
+        """LambdaSearch decision of every window in two launches.  epochs: per window (epoch_begin, obs_amb, obs_sysfreq)
+        as returned by SynthWindow.ambiguity_epochs().  Returns (results, dd_pairs (n, n_tail, 2), F (n, 2, n_tail))."""
+        win, eb, oa, sf = [0], [0], [], []
+        for (e, a, f) in epochs:
+            base = eb[-1]
+            eb.extend((np.asarray(e[1:]) + base).tolist())
+            oa.extend(np.asarray(a).tolist())
+            sf.extend(np.asarray(f).tolist())
+            win.append(len(eb) - 1)
+        win, eb = np.array(win, np.int32), np.array(eb, np.int32)
+        oa, sf = np.array(oa + [0], np.int32), np.array(sf + [0], np.int32)
+        res = (FixResult * self.n)()
+        pairs = np.zeros((self.n, n_tail, 2), np.int32)
+        F = np.zeros((self.n, 2, n_tail))
+        lf = None if last_fix is None else np.ascontiguousarray(last_fix, np.int32)
+        _check(lib().swgn_batch_ambiguity_fix(self.h, n_tail, _ip(win), _ip(eb), _ip(oa), _ip(sf), None if lf is None else _ip(lf), res,
+                                              _ip(pairs), _dp(F)), "swgn_batch_ambiguity_fix")
+        return res, pairs, F
 
     def close(self):
         if self.h:

@@ -583,3 +583,35 @@ def test_update_inputs_rejects_a_graph_with_another_structure():
     sm = b.solve()[0]  # the batch is still usable
     assert sm.termination_type in (0, 1)
     b.close()
+
+
+def test_batched_ambiguity_fix_equals_the_per_window_calls():
+    """swgn_batch_ambiguity_fix: tail information + float ambiguities + LambdaSearch decision of every window in two
+    launches.  Bit-identical to the per-window entry points (swgn_batch_get_tail_information + swgn_ambiguity_fix) fed
+    with the same device data, for both values of last_fix; a window without a factor reports status 3."""
+    ws = [swgn.SynthWindow(2, wid) for wid in (0, 1, 2, 3, 7, 12)]
+    opt = ws[0].options()
+    b = swgn.Batch([w.graph_p for w in ws], opt)
+    b.solve()
+    nt = ws[0].n_amb
+    epochs = [w.ambiguity_epochs() for w in ws]
+    for last in (0, 1):
+        res, pairs, F = b.ambiguity_fix_all(nt, epochs, [last] * len(ws))
+        for i, w in enumerate(ws):
+            offs = w.block_offsets()
+            x = b.get_state(i, w.n_state)
+            y = np.array([x[offs[w.first_amb_block + k]] for k in range(nt)])
+            A = b.tail_information(i, nt)
+            p1, F1, r1 = swgn.ambiguity_fix(A, y, *epochs[i], last_fix=last)
+            r = res[i]
+            assert (r.status, r.n_dd, r.search_ok, r.n_different) == (r1.status, r1.n_dd, r1.search_ok, r1.n_different)
+            assert list(r.s) == list(r1.s) and r.s0_partial == r1.s0_partial and r.s1_partial == r1.s1_partial
+            assert np.array_equal(pairs[i, :r.n_dd], p1)
+            assert np.array_equal(F[i].ravel()[:2 * r.n_dd].reshape(2, r.n_dd).T, F1)
+    assert any(res[i].status == 0 for i in range(len(ws)))
+    b.close()
+    # before any solve there is no Cholesky factor: every window answers status 3
+    b = swgn.Batch([ws[0].graph_p], opt)
+    res, _, _ = b.ambiguity_fix_all(nt, epochs[:1])
+    assert res[0].status == 3
+    b.close()
