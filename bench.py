@@ -139,7 +139,6 @@ def run_swgn(args, rank, local_rank, world):
     import __graft_entry__ as ge
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (no NCCL version banner)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -198,11 +197,15 @@ def run_swgn(args, rank, local_rank, world):
     init_costs = np.array([sms[i].initial_cost for i in range(W)])
     n_fail = sum(1 for i in range(W) if sms[i].termination_type == 2)
 
-    # ---- end-to-end leg through the C ABI with host buffers: H2D of the step's inputs (factor
-    # constants + initial states, pinned staging), solve, D2H of states and summaries
-    e2e_s, e2e_iters, h2d = 0.0, 0, 0
+    # ---- end-to-end leg through the C ABI with host buffers: H2D of the step's inputs (factor constants + initial
+    # states, pinned staging), solve, D2H of states and summaries.  (a) serial: update_inputs -> solve -> get_states;
+    # (b) double-buffered, the headline: the NEXT step's inputs are packed and uploaded into a shadow block on a copy stream
+    # by a second host thread (swgn_batch_prefetch_inputs) while the current step solves on the one compute stream, and
+    # become live between two solves (swgn_batch_commit_inputs).  Every step's H2D and D2H are inside the timed region.
+    import threading
+    e2e_serial_s, e2e_s, e2e_iters, h2d = 0.0, 0.0, 0, 0
     out = np.zeros(b.states_size())
-    for k in range(1 + args.steps):
+    for k in range(1 + max(1, args.steps // 2)):
         barrier()
         t0 = time.perf_counter()
         h2d = b.update_inputs()
@@ -211,9 +214,54 @@ def run_swgn(args, rank, local_rank, world):
         dt = time.perf_counter() - t0
         if k == 0:
             continue  # first call allocates the pinned staging buffer
-        e2e_s += dt
+        e2e_serial_s += dt
+    e2e_serial_s /= max(1, args.steps // 2)
+    b.prefetch_inputs()  # (allocates the shadow blocks; untimed)
+    b.commit_inputs()
+    b.prefetch_inputs()
+    b.commit_inputs()
+    b.prefetch_inputs()  # inputs of the first timed step, staged like every later step's: during the step before it
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        b.commit_inputs()
+        t = threading.Thread(target=b.prefetch_inputs)  # the next step's inputs (ctypes releases the GIL)
+        t.start()
+        b.solve(sms)
+        b.get_states(out)
+        t.join()
         e2e_iters += sum(sms[i].num_iterations for i in range(W))
+    e2e_s = time.perf_counter() - t0
     d2h = out.nbytes + W * 160  # states + TRState records
+    # ---- cfg4 leg (BASELINE configs[3]): covariance recovery + LAMBDA fix decision of every window of the solved batch in
+    # two launches (swgn_batch_ambiguity_fix); the bit-exact check against the oracle lives in tests/test_gpu_parity.py
+    cfg4 = None
+    if args.composition == "B" and ws[0].n_amb > 0:
+        epochs = swgn.Batch.pack_epochs([w.ambiguity_epochs() for w in ws])
+        b.ambiguity_fix_all(ws[0].n_amb, epochs)
+        t0 = time.perf_counter()
+        res, _, _ = b.ambiguity_fix_all(ws[0].n_amb, epochs)
+        t_fix = time.perf_counter() - t0
+        cfg4 = {"windows": W, "n_ambiguities": int(ws[0].n_amb), "ms": 1e3 * t_fix, "windows_per_s": W / t_fix,
+                "searched": sum(1 for i in range(W) if res[i].status == 0), "ratio_test_passed": sum(1 for i in range(W) if res[i].search_ok),
+                "note": "wall time of the C-ABI call incl. H2D of the epoch lists and D2H of the results"}
+    # ---- strong-scaling leg (BASELINE configs[2] as written: `--windows` windows in total, sharded over the ranks)
+    strong = None
+    if world > 1:
+        Ws = max(1, W // world)
+        bs = swgn.Batch([w.graph_p for w in ws[:Ws]], opt)
+        xs0 = np.concatenate([w.state0() for w in ws[:Ws]])
+        sms_s = (swgn.Summary * Ws)()
+        s_ms, s_it = 0.0, 0
+        for k in range(1 + args.steps):
+            bs.set_states(xs0)
+            bs.solve(sms_s)
+            if k == 0:
+                continue
+            s_ms += bs.timing()[0]
+            s_it += sum(sms_s[i].num_iterations for i in range(Ws))
+        bs.close()
+        strong = [s_ms, float(s_it), Ws]
     # cold path: planning + allocation + upload + solve + read-back of a fresh batch
     # (twice, the second one reported: the first grows the process-wide pinned staging pool to this batch size)
     for _ in range(2):
@@ -227,12 +275,12 @@ def run_swgn(args, rank, local_rank, world):
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, e2e_serial_s, strong[0]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([float(iters), float(e2e_iters), float(launches), float(n_fail)], dtype=torch.float64, device="cuda")
+        s = torch.tensor([float(iters), float(e2e_iters), float(launches), float(n_fail), strong[1]], dtype=torch.float64, device="cuda")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s = t.tolist()
-        iters, e2e_iters, launches, n_fail = s.tolist()
+        dev_ms, e2e_s, e2e_serial_s, strong[0] = t.tolist()
+        iters, e2e_iters, launches, n_fail, strong[1] = s.tolist()
     if rank != 0:
         b.close()
         if dist is not None:
@@ -248,28 +296,37 @@ def run_swgn(args, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = schur_bytes / (schur_ms * 1e-3) / 1e9
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (592-window launch),
-    # scaled per window to this launch: dram__bytes_read.sum + dram__bytes_write.sum
+    # DRAM traffic of the same kernel from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of one
+    # launch), scaled per window to this launch
     traffic, traffic_src = None, None
     try:
-        txt = open(os.path.join(ROOT, "profiles", "r01b_k_schur_592win.md")).read()
+        cap = "r02_k_schur_4096win.md" if os.path.exists(os.path.join(ROOT, "profiles", "r02_k_schur_4096win.md")) else "r01b_k_schur_592win.md"
+        cap_windows = 4096.0 if cap.startswith("r02") else 592.0
+        txt = open(os.path.join(ROOT, "profiles", cap)).read()
 
         def grab(name):
             import re
             m = re.search(r"\| %s \| ([0-9.]+) \| (\w+) \|" % re.escape(name), txt)
             return float(m.group(1)) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m.group(2)]
-        per_window = (grab("dram__bytes_read.sum") + grab("dram__bytes_write.sum")) / 592.0
+        per_window = (grab("dram__bytes_read.sum") + grab("dram__bytes_write.sum")) / cap_windows
         traffic = per_window * (schur_bytes / max(1, n_schur)) / float(np.mean(schur_bytes_w))
-        traffic_src = "profiles/r01b_k_schur_592win.md (ncu --set full, 592-window launch), scaled per window"
+        traffic_src = "profiles/%s (ncu, %d-window launch), per window x windows of this launch" % (cap, int(cap_windows))
     except Exception:
         pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ncpu = min(W, max(cores, args.ref_windows))
         ci, ct = cpu_leg(ws[:ncpu], ws[0].options(), cores)
+        # BASELINE.md 3 variants.  The port solves one window on ONE thread (the reference parallelises a single solve over 4
+        # threads, RVI/swf/swf.cpp:29; the port does not): (i) one window at a time on one thread = the latency of one solve;
+        # (i') four windows side by side on four threads = what a perfectly scaling 4-thread solve would reach; (iii) above
+        c1i, c1t = cpu_leg(ws[:min(W, 4)], ws[0].options(), 1)
+        c4i, c4t = cpu_leg(ws[:min(W, 16)], ws[0].options(), min(4, cores))
         cpu = {"value": ci / ct, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d of the same cfg2 windows, one window per OpenMP thread on %d threads, minimiser time only "
-                         "(CPU restatement of the modified-Ceres path)" % (ncpu, cores)}
+                         "(CPU restatement of the modified-Ceres path)" % (ncpu, cores),
+               "variants": {"one_window_at_a_time_1_thread": c1i / c1t, "four_windows_on_4_threads": c4i / c4t,
+                            "one_window_per_core_%d_threads" % cores: ci / ct}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -285,14 +342,63 @@ def run_swgn(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps,
+                "mode": "double-buffered inputs: step k+1 is packed and uploaded (copy stream, second host thread) while step k solves",
+                "serial_value": (e2e_iters / args.steps) / e2e_serial_s, "serial_ms_per_step": 1e3 * e2e_serial_s,
                 "cold_value": cold_iters / t_cold, "cold_note": "fresh batch of %d windows in a warm process: host planning, device allocation, upload, solve, read-back" % min(W, 512)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "cfg4_ambiguity_fix": cfg4,
+        "strong_scaling": None if strong is None else {
+            "value": strong[1] / (strong[0] * 1e-3), "unit": UNIT, "windows_total": int(strong[2]) * world, "windows_per_gpu": int(strong[2]),
+            "ms_per_step": strong[0] / args.steps, "note": "the same `--windows` windows in total, sharded over the ranks (device-resident, max over ranks)"},
     }
     print(json.dumps(line), flush=True)
     b.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_sweep(args):
+    """BASELINE configs[4]: keyframes x landmarks sweep, GNSS epochs = KF / 2; per shape the Schur kernel's achieved
+    algorithmic GB/s (CUDA events around its launches) next to the whole-solve throughput.  One JSON line."""
+    import __graft_entry__ as ge
+    ge.build_if_needed()
+    import swgn
+    peak = 6553.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    rows = []
+    n = args.sweep_windows
+    for kf in (10, 20, 40):
+        for lm in (100, 300, 1000):
+            with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+                ws = list(ex.map(lambda i: swgn.SynthWindow(2, i, n_keyframes=kf, n_landmarks=lm, n_gnss_epochs=kf // 2), range(n)))
+            b = swgn.Batch([w.graph_p for w in ws], ws[0].options())
+            x0 = np.concatenate([w.state0() for w in ws])
+            tot = sch = nb = 0.0
+            its = 0
+            sm = None
+            for rep in range(1 + args.steps):
+                b.set_states(x0)
+                sm = b.solve()
+                if rep == 0:
+                    continue
+                t, s_, nl, nk = b.timing()
+                tot += t
+                sch += s_
+                nls = np.array([sm[i].num_linear_solves for i in range(n)], np.float64)
+                nb += float((nls * np.array([b.schur_bytes(i) for i in range(n)], np.float64)).sum())
+                its += sum(sm[i].num_iterations for i in range(n))
+            gbs = nb / (sch * 1e-3) / 1e9
+            rows.append({"keyframes": kf, "landmarks": lm, "windows": n, "n_e": int(sm[0].n_e), "n_f": int(sm[0].n_f),
+                         "schur_mb_per_window_iteration": b.schur_bytes(0) / 1e6, "k_schur_gbs": gbs, "frac": gbs / peak,
+                         "iterations_per_s": its / (tot * 1e-3), "k_schur_share": sch / tot,
+                         "failed": sum(1 for i in range(n) if sm[i].termination_type == 2)})
+            b.close()
+            del ws
+    print(json.dumps({"metric": "k_schur algorithmic GB/s over the window-size sweep", "unit": "GB/s", "peak": peak, "sweep": rows}), flush=True)
 
 
 def main():
@@ -306,7 +412,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--composition", default="B", choices=["A", "B"],
                     help="B (default): the BASELINE cfg2 window with explicit GNSS frames; A: GNSS frames hidden in IMUGNSSFactor chains")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: window-size sweep of the Schur kernel (one GPU), one JSON line")
+    ap.add_argument("--sweep-windows", type=int, default=888)
     args = ap.parse_args()
+    if args.sweep:
+        return run_sweep(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

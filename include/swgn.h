@@ -305,6 +305,14 @@ swgn_status swgn_batch_set_state(swgn_batch* b, int32_t window, const double* st
 swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* graphs,
                                      int64_t* bytes_h2d);
 
+/* Double-buffered variant for a replayed sequence: swgn_batch_prefetch_inputs packs and uploads the NEXT step's inputs
+   into a shadow block on a private copy stream -- it may run on another host thread while swgn_batch_solve /
+   swgn_batch_get_states of the current step run (not concurrently with swgn_batch_update_inputs or another prefetch of
+   the same batch); swgn_batch_commit_inputs, called between two solves, makes the prefetched inputs the live ones
+   (constants by address, states by one scatter launch).  Same checks and errors as swgn_batch_update_inputs. */
+swgn_status swgn_batch_prefetch_inputs(swgn_batch* b, const swgn_graph* const* graphs, int64_t* bytes_h2d);
+swgn_status swgn_batch_commit_inputs(swgn_batch* b);
+
 /* The whole trust-region solve = ceres::Solve with DENSE_SCHUR + DOGLEG
    (CERES trust_region_minimizer.cc:67-134).  summaries may be NULL, else n_windows entries.
    With is_optimize == 0 this is the export-mode solve. */

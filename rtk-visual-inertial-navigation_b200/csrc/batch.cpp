@@ -175,6 +175,13 @@ struct swgn_batch {
   int64_t* d_state_off = nullptr;
   double* h_stage = nullptr;      // pinned
   double* h_cpool = nullptr;      // pinned staging of the factor constants (update_inputs)
+  // double-buffered inputs (swgn_batch_prefetch_inputs / _commit_inputs)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_prefetch = nullptr;
+  double* blocks[2] = {nullptr, nullptr};  // [constants | packed states]; they alternate as live / shadow
+  int live_block = -1;            // -1: the constants inside the slab are live (until the first commit)
+  int prefetched = -1;            // block holding prefetched, not yet committed inputs
+  double* h_stage2 = nullptr;     // pinned staging of the prefetched states
   void* d_slab = nullptr;         // every d_* array above is carved out of this one allocation,
   void* h_slab = nullptr;         // h_counters and h_stage out of this one (slab_alloc / slab_free)
   size_t d_slab_cap = 0, h_slab_cap = 0;
@@ -255,6 +262,14 @@ void swgn_batch_destroy(swgn_batch* b) {
   slab_free(1, b->device, b->h_slab, b->h_slab_cap);
   cudaFree(b->d_debug);
   if (b->h_cpool) cudaFreeHost(b->h_cpool);
+  if (b->copy_stream) {
+    cudaStreamSynchronize(b->copy_stream);
+    cudaStreamDestroy(b->copy_stream);
+  }
+  if (b->ev_prefetch) cudaEventDestroy(b->ev_prefetch);
+  if (b->h_stage2) cudaFreeHost(b->h_stage2);
+  for (double* blk : b->blocks)
+    if (blk) cudaFree(blk);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -721,11 +736,9 @@ swgn_status swgn_batch_get_state(swgn_batch* b, int32_t w, double* state) {
 
 // New measurements and initial states on an unchanged structure (the replayed-sequence case):
 // repack the factor constants and states of every window from the caller's graphs and upload them
-// with two copies from pinned staging.  bytes_h2d receives the bytes moved.
-swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* graphs, int64_t* bytes_h2d) {
-  if (!b || !graphs) return fail(SWGN_ERR_INVALID, "bad arguments");
-  CU(cudaSetDevice(b->device));
-  if (!b->h_cpool) CU(cudaMallocHost(&b->h_cpool, sizeof(double) * std::max<size_t>(b->cpool_n, 2)));
+// chunk by chunk from pinned staging into (d_cpool, d_stage) on `stream`.
+static swgn_status pack_and_upload(swgn_batch* b, const swgn_graph* const* graphs, double* h_cpool, double* h_stage, double* d_cpool,
+                                   double* d_stage, cudaStream_t stream) {
   // windows are packed by worker threads in index order while this thread uploads every chunk of
   // consecutive windows as soon as all of its windows are packed (the pools are window-major, so a chunk is
   // one contiguous range): packing and the H2D copy overlap
@@ -760,9 +773,9 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
         continue;
       }
       double* ptr[NUM_CARR];
-      for (int a = 0; a < NUM_CARR; ++a) ptr[a] = b->h_cpool + d.coff[a];
+      for (int a = 0; a < NUM_CARR; ++a) ptr[a] = h_cpool + d.coff[a];
       pack_constants(g, ptr);
-      std::memcpy(b->h_stage + b->state_off[w], g->state, sizeof(double) * d.n_state);
+      std::memcpy(h_stage + b->state_off[w], g->state, sizeof(double) * d.n_state);
       chunk_done[w / per_chunk].fetch_add(1, std::memory_order_release);
     }
   };
@@ -777,27 +790,77 @@ swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* gra
       while (chunk_done[c].load(std::memory_order_acquire) < w1 - w0) std::this_thread::yield();
       if (bad.load() || ce != cudaSuccess) continue;
       const size_t c0 = (size_t)b->desc[w0].coff[0], c1 = w1 < b->n ? (size_t)b->desc[w1].coff[0] : b->cpool_n;
-      ce = cudaMemcpyAsync(b->d_cpool + c0, b->h_cpool + c0, sizeof(double) * (c1 - c0), cudaMemcpyHostToDevice, b->stream);
+      ce = cudaMemcpyAsync(d_cpool + c0, h_cpool + c0, sizeof(double) * (c1 - c0), cudaMemcpyHostToDevice, stream);
       const int64_t s0 = b->state_off[w0], s1 = b->state_off[w1];
-      if (ce == cudaSuccess)
-        ce = cudaMemcpyAsync(b->d_stage + s0, b->h_stage + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, b->stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_stage + s0, h_stage + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, stream);
     }
     for (auto& t : th) t.join();
     if (ce != cudaSuccess) {
-      cudaStreamSynchronize(b->stream);
+      cudaStreamSynchronize(stream);
       CU(ce);
     }
   }
   if (bad.load()) {
-    cudaStreamSynchronize(b->stream);
+    cudaStreamSynchronize(stream);
     return fail(SWGN_ERR_INVALID, "graph structure differs from the one the batch was created with");
   }
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_update_inputs(swgn_batch* b, const swgn_graph* const* graphs, int64_t* bytes_h2d) {
+  if (!b || !graphs) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  if (!b->h_cpool) CU(cudaMallocHost(&b->h_cpool, sizeof(double) * std::max<size_t>(b->cpool_n, 2)));
+  const swgn_status st = pack_and_upload(b, graphs, b->h_cpool, b->h_stage, b->d_cpool, b->d_stage, b->stream);
+  if (st != SWGN_OK) return st;
   const int64_t ns = b->state_off[b->n];
   launch_gather_states(b->db, b->d_stage, b->d_state_off, 1, b->stream);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(b->stream));
   b->db.chain_epoch += 1;  // IMUGNSSFactor chains reload their hidden states and forget their history
   if (bytes_h2d) *bytes_h2d = (int64_t)(sizeof(double) * (b->cpool_n + (size_t)ns));
+  return SWGN_OK;
+}
+
+// Double-buffered inputs for a replayed sequence: the next step's constants and states are packed and uploaded into a
+// SHADOW block [constants | packed states] on a private copy stream while the current solve runs on the batch's stream;
+// commit makes that block the live one (same layout, WinDesc::coff) and scatters its states.  Two blocks alternate; the
+// pool inside the batch's slab is only live until the first commit.
+swgn_status swgn_batch_prefetch_inputs(swgn_batch* b, const swgn_graph* const* graphs, int64_t* bytes_h2d) {
+  if (!b || !graphs) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  const size_t nc = std::max<size_t>(b->cpool_n, 2), ns = (size_t)std::max<int64_t>(b->state_off[b->n], 2);
+  if (!b->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&b->ev_prefetch, cudaEventDisableTiming));
+    CU(cudaMallocHost(&b->h_stage2, sizeof(double) * ns));
+  }
+  if (!b->h_cpool) CU(cudaMallocHost(&b->h_cpool, sizeof(double) * nc));
+  const int target = b->live_block == 0 ? 1 : 0;
+  if (!b->blocks[target]) CU(cudaMalloc(&b->blocks[target], sizeof(double) * (nc + ns)));
+  CU(cudaStreamSynchronize(b->copy_stream));  // the pinned staging of the previous prefetch is free again
+  b->prefetched = -1;
+  const swgn_status st = pack_and_upload(b, graphs, b->h_cpool, b->h_stage2, b->blocks[target], b->blocks[target] + nc, b->copy_stream);
+  if (st != SWGN_OK) return st;
+  CU(cudaEventRecord(b->ev_prefetch, b->copy_stream));
+  b->prefetched = target;
+  if (bytes_h2d) *bytes_h2d = (int64_t)(sizeof(double) * (b->cpool_n + (size_t)b->state_off[b->n]));
+  return SWGN_OK;
+}
+
+swgn_status swgn_batch_commit_inputs(swgn_batch* b) {
+  if (!b) return fail(SWGN_ERR_INVALID, "bad arguments");
+  if (b->prefetched < 0) return fail(SWGN_ERR_INVALID, "no prefetched inputs: call swgn_batch_prefetch_inputs first");
+  CU(cudaSetDevice(b->device));
+  const size_t nc = std::max<size_t>(b->cpool_n, 2);
+  CU(cudaStreamWaitEvent(b->stream, b->ev_prefetch, 0));
+  b->live_block = b->prefetched;
+  b->prefetched = -1;
+  b->d_cpool = b->blocks[b->live_block];
+  b->db.cpool = b->d_cpool;
+  launch_gather_states(b->db, b->d_cpool + nc, b->d_state_off, 1, b->stream);
+  CU(cudaGetLastError());
+  b->db.chain_epoch += 1;  // IMUGNSSFactor chains reload their hidden states and forget their history
   return SWGN_OK;
 }
 

@@ -237,6 +237,8 @@ def lib():
         L.swgn_batch_set_state.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_solve.argtypes = [C.c_void_p, P(Summary)]
         L.swgn_batch_update_inputs.argtypes = [C.c_void_p, P(P(Graph)), P(i64)]
+        L.swgn_batch_prefetch_inputs.argtypes = [C.c_void_p, P(P(Graph)), P(i64)]
+        L.swgn_batch_commit_inputs.argtypes = [C.c_void_p]
         L.swgn_batch_last_timing.argtypes = [C.c_void_p, P(f64), P(f64), P(i32), P(i32)]
         L.swgn_batch_get_state.argtypes = [C.c_void_p, i32, P(f64)]
         L.swgn_batch_schur_bytes.restype = i64
@@ -337,6 +339,16 @@ class Batch:
         nb = i64()
         _check(lib().swgn_batch_update_inputs(self.h, arr, C.byref(nb)), "swgn_batch_update_inputs")
         return nb.value
+
+    def prefetch_inputs(self, graph_ptrs=None):
+        """Pack and upload the next step's inputs into the shadow block (may run on another thread during solve())."""
+        arr = self._graphs if graph_ptrs is None else (P(Graph) * self.n)(*graph_ptrs)
+        nb = i64()
+        _check(lib().swgn_batch_prefetch_inputs(self.h, arr, C.byref(nb)), "swgn_batch_prefetch_inputs")
+        return nb.value
+
+    def commit_inputs(self):
+        _check(lib().swgn_batch_commit_inputs(self.h), "swgn_batch_commit_inputs")
 
     def solve(self, summaries=None):
         sm = summaries if summaries is not None else (Summary * self.n)()
@@ -453,18 +465,27 @@ class Batch:
         _check(lib().swgn_batch_linear_solve(self.h, w, Dp, _dp(x)), "linear_solve")
         return x
 
+    @staticmethod
+    def pack_epochs(epochs):
+        """Per-window (epoch_begin, obs_amb, obs_sysfreq) lists -> the CSR of CSRs swgn_batch_ambiguity_fix takes."""
+        win, eb, oa, sf = [0], [np.zeros(1, np.int64)], [], []
+        base = 0
+        for (e, a, f) in epochs:
+            e = np.asarray(e, np.int64)
+            eb.append(e[1:] + base)
+            base += int(e[-1])
+            oa.append(np.asarray(a, np.int32))
+            sf.append(np.asarray(f, np.int32))
+            win.append(win[-1] + len(e) - 1)
+        pad = np.zeros(1, np.int32)
+        return (np.array(win, np.int32), np.concatenate(eb).astype(np.int32), np.concatenate(oa + [pad]), np.concatenate(sf + [pad]))
+
     def ambiguity_fix_all(self, n_tail, epochs, last_fix=None):
         """LambdaSearch decision of every window in two launches.  epochs: per window (epoch_begin, obs_amb, obs_sysfreq)
-        as returned by SynthWindow.ambiguity_epochs().  Returns (results, dd_pairs (n, n_tail, 2), F (n, 2, n_tail))."""
-        win, eb, oa, sf = [0], [0], [], []
-        for (e, a, f) in epochs:
-            base = eb[-1]
-            eb.extend((np.asarray(e[1:]) + base).tolist())
-            oa.extend(np.asarray(a).tolist())
-            sf.extend(np.asarray(f).tolist())
-            win.append(len(eb) - 1)
-        win, eb = np.array(win, np.int32), np.array(eb, np.int32)
-        oa, sf = np.array(oa + [0], np.int32), np.array(sf + [0], np.int32)
+        as returned by SynthWindow.ambiguity_epochs(), or the result of pack_epochs().  Returns (results, dd_pairs
+        (n, n_tail, 2), F (n, 2, n_tail))."""
+        win, eb, oa, sf = epochs if (len(epochs) == 4 and isinstance(epochs[0], np.ndarray) and epochs[0].dtype == np.int32
+                                     and len(epochs[0]) == self.n + 1) else self.pack_epochs(epochs)
         res = (FixResult * self.n)()
         pairs = np.zeros((self.n, n_tail, 2), np.int32)
         F = np.zeros((self.n, 2, n_tail))

@@ -615,3 +615,39 @@ def test_batched_ambiguity_fix_equals_the_per_window_calls():
     res, _, _ = b.ambiguity_fix_all(nt, epochs[:1])
     assert res[0].status == 3
     b.close()
+
+
+def test_prefetched_inputs_give_the_same_solve_as_a_fresh_batch():
+    """swgn_batch_prefetch_inputs (from a second host thread, while a solve is running) + swgn_batch_commit_inputs: the next
+    solve must be bit-identical to a fresh batch created from the new inputs; twice, so that both shadow blocks are used."""
+    import threading
+    ws = [swgn.SynthWindow(2, wid) for wid in (0, 1)]
+    opt = ws[0].options()
+    b = swgn.Batch([w.graph_p for w in ws], opt)
+    b.solve()
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        nxt = [swgn.SynthWindow(2, wid) for wid in (0, 1)]  # same structure, new measurements and initial states
+        for w in nxt:
+            g = w.graph
+            uv = np.ctypeslib.as_array(g.proj_uv, shape=(2 * g.n_proj,))
+            uv += rng.normal(size=uv.shape) * 1e-4
+            st = np.ctypeslib.as_array(g.state, shape=(g.n_state,))
+            offs = w.block_offsets()
+            for k in range(w.n_amb):
+                st[offs[w.first_amb_block + k]] += 0.01 * rng.normal()
+        t = threading.Thread(target=lambda: b.prefetch_inputs([w.graph_p for w in nxt]))
+        t.start()
+        b.solve()  # the current step keeps running on the live inputs
+        t.join()
+        b.commit_inputs()
+        sm = b.solve()
+        fresh = swgn.Batch([w.graph_p for w in nxt], opt)
+        fsm = fresh.solve()
+        for i, w in enumerate(nxt):
+            assert sm[i].num_iterations == fsm[i].num_iterations and sm[i].final_cost == fsm[i].final_cost
+            assert np.array_equal(b.get_state(i, w.n_state), fresh.get_state(i, w.n_state))
+        fresh.close()
+    with pytest.raises(RuntimeError, match="prefetch"):
+        b.commit_inputs()
+    b.close()
