@@ -6,8 +6,9 @@
 //
 //   ceres::swgn::RegisterAdapter(typeid(projection_factor), &adapt_projection);
 //
-// and fills a FactorRecord when ceres::Solve flattens the Problem.  Types without an adapter make
-// Solve() return FAILURE with a message naming the type.  The stateful IMUGNSSFactor is described
+// and fills a FactorRecord when ceres::Solve flattens the Problem.  Types without an adapter are HOST-EVALUATED (kHost):
+// their own Evaluate() is called on the host at every evaluation point and the residuals / Jacobians are uploaded --
+// correct for any CostFunction (the reference's initialisation factors), at two host round trips per iteration.  The stateful IMUGNSSFactor is described
 // as a chain record (kChain); its hidden GNSS-frame states are written back into the user memory
 // the factor points at (gnss_poses[i], gnss_speed_bias[i]) when Solve returns.
 #ifndef SWGN_CERES_SWGN_ADAPTER_H_
@@ -20,7 +21,7 @@
 
 namespace ceres {
 namespace swgn {
-enum FactorKind { kProjection = 0, kImu = 1, kGnss = 2, kPrior = 3, kUnit = 4, kChain = 5, kNumKinds = 6 };
+enum FactorKind { kProjection = 0, kImu = 1, kGnss = 2, kPrior = 3, kUnit = 4, kChain = 5, kHost = 6, kNumKinds = 7 };
 struct FactorRecord {
   int kind = -1;
   int gnss_kind = -1;            // SWGN_GNSS_* for kGnss

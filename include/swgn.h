@@ -100,6 +100,9 @@ enum {
  * `ceres::Problem my_problem` plus `options.linear_solver_ordering` at the moment of Solve.
  * All arrays are caller-owned and only read.
  */
+typedef int32_t (*swgn_host_eval_fn)(void* user, int32_t factor, double const* const* parameters, double* residuals,
+                                     double** jacobians);
+
 typedef struct swgn_graph {
   /* parameter blocks (identity in the reference = raw double*, here = index) */
   int32_t n_blocks;
@@ -154,8 +157,8 @@ typedef struct swgn_graph {
   const double* unit_istd;
 
   /* residual-block program order (the order of AddResidualBlock calls).  Entry k encodes
-     (kind << 28 | index) with kind 0 proj, 1 imu, 2 gnss, 3 prior, 4 unit, 5 chain.  May be
-     NULL: then the order is proj, imu, gnss, prior, unit, chain.  It only influences summation
+     (kind << 28 | index) with kind 0 proj, 1 imu, 2 gnss, 3 prior, 4 unit, 5 chain, 6 host.  May be
+     NULL: then the order is proj, imu, gnss, prior, unit, chain, host.  It only influences summation
      order.  */
   int32_t n_order;
   const uint32_t* order;
@@ -189,6 +192,22 @@ typedef struct swgn_graph {
   const double* chain_frame_N;
   const double* chain_N;
   const double* chain_imu_data;
+
+  /* Host-evaluated residual blocks: cost functions the device has no factor kind for (the contract of
+     CERES/include/ceres/cost_function.h:116 -- e.g. the reference's initialisation factors RVI/factor/initial_factor.cpp,
+     mag_factor.cpp, pose0_factor.cpp).  Factor i has host_nres[i] residuals over the blocks host_blocks[host_blk_begin[i] ..
+     host_blk_begin[i+1]); every evaluation of the window calls host_eval on the calling thread of swgn_batch_solve with
+     the current values of those blocks (one pointer per block, global sizes) and receives residuals and row-major
+     num_residuals x global-size Jacobians (jacobians may be NULL = residuals only), which are uploaded; pose blocks use
+     the first 6 columns (the reference's parameterization Jacobian is [I6; 0]).  This costs two host round trips per
+     trust-region iteration for the whole batch: meant for small initialisation problems, not for the timed workloads.
+     No loss function.  Kind code 6 in `order` / is_use (after the chains). */
+  int32_t n_host;
+  const int32_t* host_nres;
+  const int32_t* host_blk_begin;     /* n_host + 1 */
+  const int32_t* host_blocks;
+  swgn_host_eval_fn host_eval;       /* return 0 on success */
+  void* host_user;
 } swgn_graph;
 
 /* ---- solver options: the subset of ceres::Solver::Options the reference sets, with the

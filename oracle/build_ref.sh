@@ -4,6 +4,7 @@
 #   RVI/gnss/src/lambda.cpp, RVI/gnss/src/common_function.cpp         plain C-style code
 #   RVI/factor/gnss_factor.cpp, projection_factor.cpp, imu_factor.cpp, integration_base.cpp,
 #   pose_local_parameterization.cpp                                   the factor classes of the hot path
+#   RVI/factor/initial_factor.cpp, pose0_factor.cpp                   initialisation factors (host-evaluated through the shim)
 # Eigen, OpenCV and Ceres are not installed in this image: the factor sources are compiled against
 # oracle/ref_stubs/ (a minimal eager stand-in for the part of Eigen's dense API they use, empty OpenCV
 # headers, a type-name stub of marginalization_factor.h) and against this repository's own
@@ -35,6 +36,7 @@ if [ -f "$PKG/libswgn.so" ] && [ -f "$PKG/libswgn_synth.so" ]; then
   g++ -O2 -fPIC -shared -ffp-contract=off -std=c++17 -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" -I"$SRC" -I"$PKG/shim" \
       "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
       "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" "$REF/src/common_function.cpp" \
+      "$SRC/factor/initial_factor.cpp" "$SRC/factor/pose0_factor.cpp" \
       "$PKG/shim/ceres_shim.cpp" "$PKG/shim/ceres_shim_refdemo.cpp" "$HERE/ref_globals.cpp" \
       -o "$HERE/_ref/libswgn_refdemo.so" -L"$PKG" -lswgn -lswgn_synth -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200'
   echo "built $HERE/_ref/libswgn_refdemo.so"

@@ -99,7 +99,7 @@ bool Solver::Build(const swgn_graph* g, const swgn_options* o) {
   if (g->order) {
     for (int k = 0; k < g->n_order; ++k) {
       uint32_t kind = g->order[k] >> 28, idx = g->order[k] & 0x0fffffffu;
-      if (kind > 5 || idx >= byk[kind].size() || !byk[kind][idx]) {
+      if (kind > 5 || idx >= byk[kind].size() || !byk[kind][idx]) {  // (host-evaluated factors, kind 6, are not restated)
         error = "bad program order entry";
         return false;
       }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <climits>
@@ -149,14 +150,29 @@ static uint64_t structure_fingerprint(const swgn_graph* g) {
   arr(g->chain_blk_begin, nc ? nc + 1 : 0);
   arr(g->chain_blocks, nc && g->chain_blk_begin ? (size_t)g->chain_blk_begin[nc] : 0);
   arr(g->chain_frame_begin, nc ? nc + 1 : 0);
-  const size_t nf = (size_t)std::max(0, g->n_proj) + std::max(0, g->n_imu) + std::max(0, g->n_gnss) + np + std::max(0, g->n_unit) + nc;
+  const size_t nh = (size_t)std::max(0, g->n_host);
+  arr(g->host_nres, nh);
+  arr(g->host_blk_begin, nh ? nh + 1 : 0);
+  arr(g->host_blocks, nh && g->host_blk_begin ? (size_t)g->host_blk_begin[nh] : 0);
+  const size_t nf = (size_t)std::max(0, g->n_proj) + std::max(0, g->n_imu) + std::max(0, g->n_gnss) + np + std::max(0, g->n_unit) + nc + nh;
   const uint64_t use_tag = g->is_use ? nf : ~0ull;
   mix(&use_tag, sizeof(use_tag));
   if (g->is_use) mix(g->is_use, nf);
   return h;
 }
 
+// host-evaluated residual blocks of one window (swgn_graph.host_*): what swgn_batch_solve needs to call back
+struct HostFactors {
+  swgn_host_eval_fn fn = nullptr;
+  void* user = nullptr;
+  std::vector<int32_t> nres, blk_begin, blk_state, blk_size;  // per factor / per block: state offset and global size
+  int64_t buf_doubles = 0;
+};
+
 struct swgn_batch {
+  std::vector<HostFactors> host;       // per window (empty vectors when the window has none)
+  bool any_host = false;
+  std::vector<double> h_hoststate, h_hostbuf;
   std::vector<uint64_t> fingerprint;  // per window: structure_fingerprint of the graph it was planned from
   int n = 0, device = 0;
   swgn_options opt;
@@ -329,6 +345,22 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   b->state_off.resize(n_windows + 1);
   b->fingerprint.resize(n_windows);
   for (int w = 0; w < n_windows; ++w) b->fingerprint[w] = structure_fingerprint(graphs[w]);
+  b->host.resize(n_windows);
+  for (int w = 0; w < n_windows; ++w) {
+    const swgn_graph* g = graphs[w];
+    if (g->n_host <= 0) continue;
+    HostFactors& h = b->host[w];
+    b->any_host = true;
+    h.fn = g->host_eval;
+    h.user = g->host_user;
+    h.nres.assign(g->host_nres, g->host_nres + g->n_host);
+    h.blk_begin.assign(g->host_blk_begin, g->host_blk_begin + g->n_host + 1);
+    for (int k = 0; k < g->host_blk_begin[g->n_host]; ++k) {
+      h.blk_state.push_back(g->block_offset[g->host_blocks[k]]);
+      h.blk_size.push_back(g->block_size[g->host_blocks[k]]);
+    }
+    h.buf_doubles = plans[w].d.n_hostbuf;
+  }
   b->has_scopy = n_windows <= 256;
   size_t io = 0, co = 0, wo = 0;
   int max_wbuf = 0, max_nf = 0, max_prior_n = 0, max_chain = 0, max_chain_k = 0, sb_windows = 0;
@@ -907,6 +939,46 @@ static cudaEvent_t get_event(swgn_batch* b, size_t i) {
   return b->ev[i];
 }
 
+// Evaluate the host-evaluated residual blocks of every window at the point the next k_eval launch will use (W_X, or
+// W_XCAND for a candidate evaluation) with the application's own cost functions and upload the records.  Two host round
+// trips per trust-region iteration: the price of cost functions the device has no kind for.
+static swgn_status host_evaluate(swgn_batch* b, int state_arr, int only_window) {
+  if (!b->any_host) return SWGN_OK;
+  cudaStream_t s = b->stream;
+  for (int w = 0; w < b->n; ++w) {
+    if (only_window >= 0 && w != only_window) continue;
+    HostFactors& h = b->host[w];
+    if (h.nres.empty()) continue;
+    const WinDesc& d = b->desc[w];
+    b->h_hoststate.resize((size_t)d.n_state);
+    CU(cudaMemcpyAsync(b->h_hoststate.data(), b->d_wpool + d.woff[state_arr], sizeof(double) * d.n_state, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    b->h_hostbuf.assign((size_t)h.buf_doubles, 0.0);
+    int64_t off = 0;
+    std::vector<const double*> params;
+    std::vector<double*> jac;
+    for (size_t i = 0; i < h.nres.size(); ++i) {
+      params.clear();
+      jac.clear();
+      double* r = b->h_hostbuf.data() + off;
+      int64_t jo = off + h.nres[i];
+      for (int k = h.blk_begin[i]; k < h.blk_begin[i + 1]; ++k) {
+        params.push_back(b->h_hoststate.data() + h.blk_state[k]);
+        jac.push_back(b->h_hostbuf.data() + jo);
+        jo += (int64_t)h.nres[i] * h.blk_size[k];
+      }
+      if (h.fn(h.user, (int32_t)i, params.data(), r, jac.data()) != 0) {
+        const double nanv = std::nan("");  // an evaluation failure reads as a non-finite residual: Ceres' "evaluation failed"
+        r[0] = nanv;
+      }
+      off = jo;
+    }
+    CU(cudaMemcpyAsync(b->d_wpool + d.woff[W_HOSTBUF], b->h_hostbuf.data(), sizeof(double) * (size_t)h.buf_doubles, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return SWGN_OK;
+}
+
 swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
   if (!b) return fail(SWGN_ERR_INVALID, "null batch");
   CU(cudaSetDevice(b->device));
@@ -918,6 +990,10 @@ swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
   int launches = 0, n_schur = 0;
   CU(cudaEventRecord(get_event(b, 0), s));
   const int eval_launches = db.max_chain > 0 ? 2 : 1;  // k_chain runs ahead of k_eval when chains exist
+  {
+    const swgn_status hs = host_evaluate(b, W_X, -1);
+    if (hs != SWGN_OK) return hs;
+  }
   launch_eval(db, EVAL_INIT, RUN_STATE_MACHINE, s);
   launches += eval_launches;
   b->h_counters[0] = b->h_counters[1] = -1;
@@ -955,8 +1031,16 @@ swgn_status swgn_batch_solve(swgn_batch* b, swgn_summary* summaries) {
     launch_chol(db, RUN_STATE_MACHINE, s);
     launch_backsub(db, RUN_STATE_MACHINE, s);
     launch_step(db, s);
+    if (b->any_host) {
+      const swgn_status hs = host_evaluate(b, W_XCAND, -1);
+      if (hs != SWGN_OK) return hs;
+    }
     launch_eval(db, EVAL_CANDIDATE, RUN_STATE_MACHINE, s);
     launch_end(db, s);
+    if (b->any_host) {
+      const swgn_status hs = host_evaluate(b, W_X, -1);  // (a rejected step left W_X where it was: same values, same records)
+      if (hs != SWGN_OK) return hs;
+    }
     launch_eval(db, EVAL_ACCEPTED, RUN_STATE_MACHINE, s);
     launches += 5 + 2 * eval_launches;
   }
@@ -1225,6 +1309,10 @@ swgn_status swgn_batch_evaluate(swgn_batch* b, int32_t w, double* cost, double* 
   if (!b || w < 0 || w >= b->n) return fail(SWGN_ERR_INVALID, "bad arguments");
   CU(cudaSetDevice(b->device));
   const WinDesc& d = b->desc[w];
+  {
+    const swgn_status hs = host_evaluate(b, W_X, w);
+    if (hs != SWGN_OK) return hs;
+  }
   launch_eval(b->db, EVAL_FORCE, w, b->stream);
   CU(cudaGetLastError());
   TRState t;
@@ -1305,6 +1393,10 @@ swgn_status swgn_batch_linear_solve(swgn_batch* b, int32_t w, const double* D, d
   db.keep_copy = 1;
   db.params.export_mode = 0;
   b->db.keep_copy = 1;  // get_reduced reads the copy from now on
+  {
+    const swgn_status hs = host_evaluate(b, W_X, w);
+    if (hs != SWGN_OK) return hs;
+  }
   launch_eval(db, EVAL_FORCE, w, s);
   launch_schur(db, w, s);
   launch_chol(db, w, s);

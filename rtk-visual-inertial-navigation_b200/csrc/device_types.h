@@ -79,6 +79,9 @@ enum IArr {
   I_CHAIN,          // [n_chain * 8] m (hidden frames), k (phase biases), res_off, first entry in I_CHAIN_BLK,
                     //               C_CHAIN offset, W_CHAIN offset, first hidden frame of the window, 0
   I_CHAIN_BLK,      // [(4 + k) * 2 per chain] state_off, jac_off of pose_i, sb_i, pose_j, sb_j, N_0 ..
+  I_HOST,           // [n_host * 4] res_off (-1: not in the reduced program), first entry in I_HOST_BLK, number of blocks,
+                    //              offset of the factor's record [r | J_0 | J_1 ...] (row-major nres x GLOBAL size) in W_HOSTBUF
+  I_HOST_BLK,       // [4 per block] state_off, jac_off (-1 constant), global size, tangent size
   I_SB_HDR,         // [sb_nbatch * SB_HDR_INTS] batch headers of the streamed Schur elimination (see "streamed Schur" below)
   I_SB_REC,         // record packages of the batches, back to back (every package a multiple of 4 ints)
   I_ACC_MAP,        // [n_fb * n_fb] block cell (p, q), p <= q, of the reduced system -> offset of its compact accumulator
@@ -163,6 +166,7 @@ enum WArr {
              //            overwritten by its Cholesky factor U (S = U^T U) and U^-T rhs
   W_SCOPY,   // [n_f * ld] copy of S|rhs before factorisation (staged test entry point only)
   W_SCALE,   // [n_t] Jacobi scaling 1 / (1 + |column of the initial Jacobian|) (jacobi_scaling only)
+  W_HOSTBUF, // residuals and global-size Jacobians of the host-evaluated factors, uploaded before every evaluation
   W_CHAIN,   // mutable state of the IMUGNSSFactor chains, per chain (ChainLayout): hidden frame states, history
              // flag, states of the last Jacobian evaluation, INC, saved elimination blocks (hmn_save,
              // rhsmn_save), schur_jacobian, schur_residual, cost of the current evaluation
@@ -174,7 +178,7 @@ enum { IMU_DEV_STRIDE = 296, GNSS_DEV_STRIDE = 12 };
 // dp_dba, dp_dbg, dq_dbg, dv_dba, dv_dbg (row-major), [70..294] sqrt_info 15x15 row-major
 enum { IMU_DEV_BLOCKS = 24, IMU_DEV_SQRT = 70 };
 
-enum FactorKind { K_PROJ = 0, K_IMU = 1, K_GNSS = 2, K_PRIOR = 3, K_UNIT = 4, K_CHAIN = 5, NUM_KINDS = 6 };
+enum FactorKind { K_PROJ = 0, K_IMU = 1, K_GNSS = 2, K_PRIOR = 3, K_UNIT = 4, K_CHAIN = 5, K_HOST = 6, NUM_KINDS = 7 };
 
 // Offsets (doubles) inside one chain's C_CHAIN constants and W_CHAIN work area; m hidden frames,
 // k phase biases, n = 30 + k residuals.
@@ -218,7 +222,8 @@ struct WinDesc {
   int32_t n_chain, n_chain_frames, max_chain_k, n_wstream;
   int32_t n_tchunks_t, n_tchunks_w;
   // streamed Schur elimination: sb_ok = the window fits the on-chip budget (else the gather kernel k_schur runs it)
-  int32_t sb_ok, sb_nbatch, sb_acc, sb_jcap, sb_rcap, sb_ecap, sb_fcap, sb_reccap, n_fb, sb_pad;
+  int32_t sb_ok, sb_nbatch, sb_acc, sb_jcap, sb_rcap, sb_ecap, sb_fcap, sb_reccap, n_fb, n_host;
+  int32_t n_hostbuf, pad1_;
   int64_t ioff[NUM_IARR];
   int64_t coff[NUM_CARR];
   int64_t woff[NUM_WARR];

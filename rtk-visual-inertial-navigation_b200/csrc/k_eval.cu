@@ -373,6 +373,51 @@ __global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, i
     }
   }
 
+  {  // host-evaluated factors: residuals and global-size Jacobians were computed by the application's own cost functions at
+     // this evaluation point and uploaded (swgn_graph.host_eval); the tangent Jacobian is the first `lsize` columns
+    const int32_t* ht = v.I(I_HOST);
+    const int32_t* hb = v.I(I_HOST_BLK);
+    const int32_t* row_nres = v.I(I_ROW_NRES);
+    const int32_t* rs_row = v.I(I_RS_ROW);
+    const double* HB = v.W(W_HOSTBUF);
+    for (int i = 0; i < d.n_host; ++i) {
+      const int res_off = ht[4 * i], blk0 = ht[4 * i + 1], nblk = ht[4 * i + 2];
+      if (res_off < 0 && !with_fixed) continue;
+      const double* rec = HB + ht[4 * i + 3];
+      // number of residuals: active factors read it from their row block; inactive ones from the record layout
+      int nres;
+      if (res_off >= 0) {
+        nres = row_nres[rs_row[res_off]];
+      } else {
+        int gsum = 0;
+        for (int kb = 0; kb < nblk; ++kb) gsum += hb[4 * (blk0 + kb) + 2];
+        const int next = (i + 1 < d.n_host) ? ht[4 * (i + 1) + 3] : d.n_hostbuf;
+        nres = (next - ht[4 * i + 3]) / (1 + gsum);
+      }
+      for (int r = tid; r < nres; r += kThreads) {
+        const double rv = rec[r];
+        if (!finite_d(rv)) bad = 1;
+        if (res_off < 0) { fixed += 0.5 * rv * rv; continue; }
+        cost += 0.5 * rv * rv;
+        if (full) R[res_off + r] = rv;
+      }
+      if (full && res_off >= 0) {
+        const double* Jg = rec + nres;
+        for (int kb = 0; kb < nblk; ++kb) {
+          const int jo = hb[4 * (blk0 + kb) + 1], gs = hb[4 * (blk0 + kb) + 2], ls = hb[4 * (blk0 + kb) + 3];
+          if (jo >= 0)
+            for (int o = tid; o < nres * ls; o += kThreads) {
+              const int r = o / ls, c = o - r * ls;
+              const double jv = Jg[r * gs + c];
+              if (!finite_d(jv)) bad = 1;
+              J[jo + o] = jv;
+            }
+          Jg += nres * gs;
+        }
+      }
+    }
+  }
+
   {  // IMUGNSSFactor chains: evaluated by k_chain (launched just before this kernel in the same mode)
     const int32_t* ct = v.I(I_CHAIN);
     for (int i = tid; i < d.n_chain; i += kThreads) {

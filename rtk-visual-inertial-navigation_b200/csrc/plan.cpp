@@ -146,7 +146,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
 
   // ---- factors, kind-major storage
   std::vector<Factor> fac;
-  int kind_begin[NUM_KINDS + 1] = {0, 0, 0, 0, 0, 0, 0};
+  int kind_begin[NUM_KINDS + 1] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto add_factor = [&](int kind, int idx, const int32_t* blocks, int n, int nres) -> bool {
     for (int k = 0; k < n; ++k)
       if (blocks[k] < 0 || blocks[k] >= nb) return false;
@@ -160,7 +160,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     return true;
   };
   fac.reserve((size_t)std::max(0, g->n_proj) + std::max(0, g->n_imu) + std::max(0, g->n_gnss) + std::max(0, g->n_prior) +
-              std::max(0, g->n_unit) + std::max(0, g->n_chain));
+              std::max(0, g->n_unit) + std::max(0, g->n_chain) + std::max(0, g->n_host));
   static const int kGnssArity[6] = {2, 3, 3, 2, 3, 2};
   static const int kGnssSizes[6][3] = {{7, 1, 0}, {7, 1, 1}, {7, 1, 1}, {7, 1, 0}, {9, 1, 7}, {1, 1, 0}};
   for (int i = 0; i < g->n_proj; ++i)
@@ -204,6 +204,13 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     max_chain_k = std::max(max_chain_k, k);
   }
   kind_begin[6] = (int)fac.size();
+  for (int i = 0; i < g->n_host; ++i) {
+    if (!g->host_nres || !g->host_blk_begin || !g->host_blocks || !g->host_eval) return fail(SWGN_ERR_INVALID, "host-evaluated factors without tables / callback");
+    const int b0 = g->host_blk_begin[i], b1 = g->host_blk_begin[i + 1];
+    if (b1 <= b0 || g->host_nres[i] <= 0) return fail(SWGN_ERR_INVALID, "bad host factor");
+    if (!add_factor(K_HOST, i, g->host_blocks + b0, b1 - b0, g->host_nres[i])) return fail(SWGN_ERR_INVALID, "bad host factor block");
+  }
+  kind_begin[7] = (int)fac.size();
   for (const Factor& f : fac) {
     static const int proj_sz[3] = {7, 7, 3}, imu_sz[4] = {7, 9, 7, 9};
     if (f.kind == K_PROJ)
@@ -225,7 +232,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
     std::vector<char> seen(fac.size(), 0);
     for (int k = 0; k < g->n_order; ++k) {
       uint32_t kind = g->order[k] >> 28, idx = g->order[k] & 0x0fffffffu;
-      if (kind > 5 || (int)idx >= kind_begin[kind + 1] - kind_begin[kind]) return fail(SWGN_ERR_INVALID, "bad program order entry");
+      if (kind > 6 || (int)idx >= kind_begin[kind + 1] - kind_begin[kind]) return fail(SWGN_ERR_INVALID, "bad program order entry");
       int f = kind_begin[kind] + (int)idx;
       if (seen[f]) return fail(SWGN_ERR_INVALID, "residual block listed twice in the program order");
       seen[f] = 1;
@@ -799,6 +806,20 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
       frame0 += m;
     }
   }
+  int64_t hostbuf = 0;
+  for (int i = 0; i < g->n_host; ++i) {
+    const Factor& f = fac[kind_begin[6] + i];
+    if (hostbuf > INT32_MAX / 2) return fail(SWGN_ERR_TOO_LARGE, "host-evaluated factors too large");
+    int32_t rec[4] = {f.active ? f.res_off : -1, (int32_t)(I[I_HOST_BLK].size() / 4), (int32_t)f.blocks.size(), (int32_t)hostbuf};
+    I[I_HOST].insert(I[I_HOST].end(), rec, rec + 4);
+    hostbuf += f.nres;
+    for (size_t p = 0; p < f.blocks.size(); ++p) {
+      const int b = f.blocks[p];
+      int32_t br[4] = {soff(b), f.jac_off[p], g->block_size[b], local_size(g->block_size[b], g->block_manifold[b])};
+      I[I_HOST_BLK].insert(I[I_HOST_BLK].end(), br, br + 4);
+      hostbuf += (int64_t)f.nres * g->block_size[b];
+    }
+  }
   {
     int64_t sizes[NUM_CARR];
     constant_sizes(g, sizes);
@@ -858,6 +879,8 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   d.max_wbuf = max_wbuf;
   d.n_wstream = (int)(I[I_WSTREAM].size() / 4);
   d.n_chain = g->n_chain;
+  d.n_host = g->n_host;
+  d.n_hostbuf = (int32_t)hostbuf;
   d.n_chain_frames = n_chain_frames;
   d.max_chain_k = max_chain_k;
   d.max_prior_n = 0;
@@ -878,6 +901,7 @@ swgn_status build_plan(const swgn_graph* g, int n_parameter_head, WindowPlan* P,
   W[W_EFAC] = align2(n_efac);
   W[W_S] = W[W_SCOPY] = align2((int64_t)n_f * d.ld);
   W[W_CHAIN] = align2(chain_work);
+  W[W_HOSTBUF] = align2(hostbuf);
   P->schur_doubles = schur_doubles + n_t + (int64_t)n_f * (n_f + 1) / 2 + n_f + n_e;
   return SWGN_OK;
 }

@@ -300,17 +300,30 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
   std::vector<int32_t> chain_blk_begin{0}, chain_blocks, chain_frame_begin{0};
   std::vector<double> chain_frames, chain_frame_N, chain_N, chain_imu;
   std::vector<double*> chain_pose_ptr, chain_sb_ptr;
+  std::vector<const CostFunction*> host_cf;  // cost functions without a device adapter
+  std::vector<int32_t> host_nres, host_blk_begin{0}, host_blocks;
   double cauchy_a = -1.0;
   bool any_masked = false;
   for (internal::ResidualBlock* rb : problem->residual_block_list()) {
     const CostFunction* cf = rb->cost_function();
     auto it = swgn::registry().find(std::type_index(typeid(*cf)));
-    if (it == swgn::registry().end())
-      return fail(summary, std::string("swgn shim: no device adapter registered for cost function type ") + typeid(*cf).name());
-    swgn::FactorRecord rec;
-    if (!it->second(cf, &rec)) return fail(summary, std::string("swgn shim: adapter failed for ") + typeid(*cf).name());
     std::vector<int32_t> ids;
     for (double* p : rb->parameter_blocks()) ids.push_back(index_of.at(p));
+    if (it == swgn::registry().end()) {
+      // no device kind for this cost function: it is evaluated on the host by its own Evaluate() (cost_function.h:116)
+      if (rb->loss_function()) return fail(summary, std::string("swgn shim: a loss function on the host-evaluated cost function ") + typeid(*cf).name() + " is not supported");
+      if (ids.size() != cf->parameter_block_sizes().size()) return fail(summary, "swgn shim: parameter block count mismatch");
+      order.push_back(((uint32_t)swgn::kHost << 28) | (uint32_t)host_cf.size());
+      use_by_kind[swgn::kHost].push_back(rb->is_use ? 1 : 0);
+      any_masked |= !rb->is_use;
+      host_cf.push_back(cf);
+      host_nres.push_back(cf->num_residuals());
+      host_blocks.insert(host_blocks.end(), ids.begin(), ids.end());
+      host_blk_begin.push_back((int32_t)host_blocks.size());
+      continue;
+    }
+    swgn::FactorRecord rec;
+    if (!it->second(cf, &rec)) return fail(summary, std::string("swgn shim: adapter failed for ") + typeid(*cf).name());
     const LossFunction* loss = rb->loss_function();
     if (loss) {
       const CauchyLoss* cl = dynamic_cast<const CauchyLoss*>(loss);
@@ -429,6 +442,17 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
   g.n_order = (int32_t)order.size();
   g.order = order.data();
   g.is_use = any_masked ? is_use.data() : nullptr;
+  g.n_host = (int32_t)host_cf.size();
+  if (g.n_host > 0) {
+    g.host_nres = host_nres.data();
+    g.host_blk_begin = host_blk_begin.data();
+    g.host_blocks = host_blocks.data();
+    g.host_user = &host_cf;
+    g.host_eval = [](void* user, int32_t factor, double const* const* parameters, double* residuals, double** jacobians) -> int32_t {
+      const auto& cfs = *static_cast<const std::vector<const CostFunction*>*>(user);
+      return cfs[factor]->Evaluate(parameters, residuals, jacobians) ? 0 : 1;
+    };
+  }
   g.n_chain = (int32_t)chain_blk_begin.size() - 1;
   if (g.n_chain > 0) {
     g.chain_blk_begin = chain_blk_begin.data();

@@ -5,9 +5,12 @@
 // ceres::Solve of the shim, i.e. on the GPU.  The costs the device reports are then checked against the costs the
 // reference's own Evaluate() methods give on the CPU at the same states.  TEST INFRASTRUCTURE: it links reference
 // code, is built only where /root/reference exists and lives in oracle/_ref/.
-// Two factor classes of the window cannot be compiled here (marginalization_factor.cpp needs Eigen's eigen-solver,
-// initial_factor.cpp is not on the hot path): they are stood in by classes with the same public members and a
-// restated Evaluate() (marginalization_factor.cpp:410-446, initial_factor.cpp:90-96).
+// One factor class of the window cannot be compiled here (marginalization_factor.cpp needs Eigen's eigen-solver): it is
+// stood in by a class with the same public members and a restated Evaluate() (marginalization_factor.cpp:410-446).
+// With host_factors != 0 the window also gets the reference's INITIALISATION factors -- InitialPoseFactor,
+// InitialBiasFactor, InitialFactor11 (RVI/factor/initial_factor.cpp) and InitPose0Factor (pose0_factor.cpp) -- for
+// which no device adapter exists: the shim evaluates them on the host through their own Evaluate() (generic
+// CostFunction contract, CERES/include/ceres/cost_function.h:116).
 #include <array>
 #include <cmath>
 #include <cstring>
@@ -19,6 +22,8 @@
 #include "ceres/schur_complement_solver.h"
 #include "factor/gnss_factor.h"
 #include "factor/imu_factor.h"
+#include "factor/initial_factor.h"
+#include "factor/pose0_factor.h"
 #include "factor/pose_local_parameterization.h"
 #include "factor/projection_factor.h"
 #include "reference_adapters.h"
@@ -28,16 +33,6 @@ extern Eigen::Matrix3d Rwgw;
 extern Eigen::Vector3d G;
 
 namespace {
-class InitialBlackFactor : public ceres::SizedCostFunction<1, 1> {
- public:
-  explicit InitialBlackFactor(double s) : istd(s) {}
-  bool Evaluate(double const* const* p, double* r, double** J) const override {
-    r[0] = p[0][0] * istd;
-    if (J && J[0]) J[0][0] = istd;
-    return true;
-  }
-  double istd;
-};
 struct MarginalizationInfo {
   int m = 0, n = 0;
   std::vector<int> keep_block_size, keep_block_idx;
@@ -121,8 +116,8 @@ void register_adapters() {
 // device and reports cost_out = {device initial, device final, reference-CPU cost at the initial state, reference-CPU
 // cost at the returned state}.  strategy: 0 DOGLEG (jacobi_scaling false), 1 LEVENBERG_MARQUARDT with Ceres' default
 // jacobi_scaling = true.  Returns the termination type or -1.
-extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int variant, int strategy, int device, double* state_out,
-                                        double* cost_out, int* steps_out, char* message, int message_len) {
+extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int variant, int strategy, int host_factors, int device,
+                                        double* state_out, double* cost_out, int* steps_out, char* message, int message_len) {
   register_adapters();
   swgn_synth_config cfg;
   swgn_synth_default_config(which, &cfg);
@@ -236,6 +231,27 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
       add(new MarginalizationFactor(&m), nullptr, params);
     }
     for (int i = 0; i < g->n_unit; ++i) add(new InitialBlackFactor(g->unit_istd[i]), nullptr, {mem[g->unit_block[i]].get()});
+    if (host_factors) {
+      // the reference's initialisation factors, anchored at the generator's ground truth; no adapter is registered for
+      // them, so the shim evaluates them on the host
+      const double* truth = swgn_synth_truth(S);
+      int32_t info8[8];
+      swgn_synth_info(S, info8);
+      const int F = info8[0];  // frames: poses are blocks 0..F-1, speed-biases F..2F-1
+      const double* p1 = truth + g->block_offset[1];
+      Eigen::Matrix<double, 6, 6> w6 = Eigen::Matrix<double, 6, 6>::Identity();
+      for (int k = 0; k < 6; ++k) w6(k, k) = k < 3 ? 20.0 : 200.0;
+      w6(0, 4) = 3.0;  // (not diagonal on purpose)
+      add(new InitialPoseFactor(Eigen::Vector3d(p1[0], p1[1], p1[2]), Eigen::Quaterniond(p1[6], p1[3], p1[4], p1[5]), w6), nullptr, {mem[1].get()});
+      const double* s2 = truth + g->block_offset[F + 2];
+      Eigen::Matrix<double, 9, 9> w9 = Eigen::Matrix<double, 9, 9>::Identity();
+      for (int k = 0; k < 9; ++k) w9(k, k) = 5.0 + k;
+      add(new InitialBiasFactor(Eigen::Vector3d(s2[0], s2[1], s2[2]), Eigen::Vector3d(s2[3], s2[4], s2[5]), Eigen::Vector3d(s2[6], s2[7], s2[8]), w9), nullptr,
+          {mem[F + 2].get()});
+      const double* p3 = truth + g->block_offset[3];
+      const Eigen::Matrix3d R3 = Eigen::Quaterniond(p3[6], p3[3], p3[4], p3[5]).toRotationMatrix();
+      add(new InitPose0Factor(Eigen::MatrixXd(R3), Eigen::Vector3d(p3[0], p3[1], p3[2]), true, true, 30.0), nullptr, {mem[3].get()});
+    }
     for (int b = 0; b < g->n_blocks; ++b)
       if (g->block_const[b]) problem.SetParameterBlockConstant(mem[b].get());
 

@@ -34,7 +34,12 @@ class Graph(C.Structure):
         ("n_chain", i32), ("chain_blk_begin", P(i32)), ("chain_blocks", P(i32)),
         ("chain_frame_begin", P(i32)), ("chain_frame_data", P(f64)), ("chain_frame_N", P(f64)),
         ("chain_N", P(f64)), ("chain_imu_data", P(f64)),
+        ("n_host", i32), ("host_nres", P(i32)), ("host_blk_begin", P(i32)), ("host_blocks", P(i32)),
+        ("host_eval", C.c_void_p), ("host_user", C.c_void_p),
     ]
+
+
+HOST_EVAL_FN = C.CFUNCTYPE(i32, C.c_void_p, i32, P(P(f64)), P(f64), P(P(f64)))
 
 
 class Options(C.Structure):

@@ -134,8 +134,8 @@ def refdemo():
         return None
     L = C.CDLL(path)
     L.swgn_ceres_refdemo_solve.restype = C.c_int
-    L.swgn_ceres_refdemo_solve.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_int),
-                                           C.c_char_p, C.c_int]
+    L.swgn_ceres_refdemo_solve.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64),
+                                           C.POINTER(C.c_int), C.c_char_p, C.c_int]
     return L
 
 
@@ -154,7 +154,7 @@ def test_reference_factor_classes_drop_in_through_the_shim(which, wid, variant, 
     cost = np.zeros(4)
     steps = (C.c_int * 2)()
     msg = C.create_string_buffer(512)
-    rc = refdemo().swgn_ceres_refdemo_solve(which, wid, variant, strategy, 0, state.ctypes.data_as(C.POINTER(f64)),
+    rc = refdemo().swgn_ceres_refdemo_solve(which, wid, variant, strategy, 0, 0, state.ctypes.data_as(C.POINTER(f64)),
                                             cost.ctypes.data_as(C.POINTER(f64)), steps, msg, 512)
     assert rc in (0, 1), msg.value.decode()
     dev_initial, dev_final, cpu_initial, cpu_final = cost
@@ -171,3 +171,28 @@ def test_reference_factor_classes_drop_in_through_the_shim(which, wid, variant, 
     b.close()
     assert (steps[0], steps[1]) == (sm.num_successful_steps, sm.num_unsuccessful_steps)
     assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libswgn_refdemo.so")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("which,wid,strategy", [(1, 1, 0), (2, 4, 0), (1, 2, 1)])
+def test_reference_initialisation_factors_are_evaluated_on_the_host(which, wid, strategy):
+    """Cost functions without a device adapter -- the reference's own InitialPoseFactor, InitialBiasFactor (initial_factor.cpp)
+    and InitPose0Factor (pose0_factor.cpp), compiled unmodified -- go through the generic CostFunction contract: the shim
+    calls their Evaluate() on the host at every evaluation point.  The device's costs must again be the reference's own."""
+    w = swgn.SynthWindow(which, wid)
+    state = np.zeros(w.n_state)
+    cost = np.zeros(4)
+    steps = (C.c_int * 2)()
+    msg = C.create_string_buffer(512)
+    rc = refdemo().swgn_ceres_refdemo_solve(which, wid, 0, strategy, 1, 0, state.ctypes.data_as(C.POINTER(f64)),
+                                            cost.ctypes.data_as(C.POINTER(f64)), steps, msg, 512)
+    assert rc in (0, 1), msg.value.decode()
+    dev_initial, dev_final, cpu_initial, cpu_final = cost
+    assert abs(dev_initial - cpu_initial) <= 1e-11 * cpu_initial, (dev_initial, cpu_initial)
+    assert abs(dev_final - cpu_final) <= 1e-9 * cpu_final, (dev_final, cpu_final)
+    assert dev_final < 1e-3 * dev_initial
+    # the extra factors pull the window towards the truth they are anchored at: the result differs from the plain window's
+    plain = np.zeros(w.n_state)
+    refdemo().swgn_ceres_refdemo_solve(which, wid, 0, strategy, 0, 0, plain.ctypes.data_as(C.POINTER(f64)), cost.ctypes.data_as(C.POINTER(f64)), steps, msg, 512)
+    assert np.abs(plain - state).max() > 1e-9

@@ -651,3 +651,69 @@ def test_prefetched_inputs_give_the_same_solve_as_a_fresh_batch():
     with pytest.raises(RuntimeError, match="prefetch"):
         b.commit_inputs()
     b.close()
+
+
+def test_host_evaluated_cost_functions_reproduce_the_device_factors():
+    """swgn_graph.host_*: residual blocks the device has no kind for are evaluated by the caller's own cost function on the
+    host at every evaluation point.  Here the IMU factors of a window are taken out of the device kind and handed over as
+    host-evaluated blocks whose callback is the (pinned) CPU restatement of IMUFactor: evaluation, linear solve and the
+    full solve must reproduce the all-device run (rows are ordered differently, so to rounding, not bit for bit)."""
+    w = swgn.SynthWindow(1, 2)
+    opt = w.options()
+    ref = swgn.Batch([w.graph_p], opt)
+    sm0 = ref.solve()[0]
+    x0 = ref.get_state(0, w.n_state)
+    ref.close()
+
+    g = w.graph
+    n_imu = g.n_imu
+    glob = np.array(list(g.Pbg) + list(g.gravity) + list(g.proj_sqrt_info))
+    recs = np.ctypeslib.as_array(g.imu_data, shape=(n_imu, 474)).copy()
+    sizes = (7, 9, 7, 9)
+    calls = {"n": 0, "jac": 0}
+    f = ob.oracle().oracle_factor_eval
+    f.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 5
+
+    def host_eval(user, factor, params, residuals, jacobians):
+        calls["n"] += 1
+        x = np.concatenate([np.ctypeslib.as_array(params[k], shape=(sizes[k],)) for k in range(4)])
+        r = np.zeros(15)
+        J = np.zeros(15 * 32)
+        want_j = bool(jacobians)
+        st = f(1, 0, glob.ctypes.data_as(C.POINTER(C.c_double)), recs[factor].ctypes.data_as(C.POINTER(C.c_double)),
+               x.ctypes.data_as(C.POINTER(C.c_double)), r.ctypes.data_as(C.POINTER(C.c_double)),
+               J.ctypes.data_as(C.POINTER(C.c_double)) if want_j else None)
+        C.memmove(residuals, r.ctypes.data, 15 * 8)
+        if want_j:
+            calls["jac"] += 1
+            o = 0
+            for k in range(4):
+                if jacobians[k]:
+                    C.memmove(jacobians[k], J[o:o + 15 * sizes[k]].ctypes.data, 15 * sizes[k] * 8)
+                o += 15 * sizes[k]
+        return st
+
+    cb = swgn.HOST_EVAL_FN(host_eval)
+    g2 = swgn.Graph()
+    C.memmove(C.byref(g2), C.byref(g), C.sizeof(swgn.Graph))
+    g2.n_imu = 0
+    nres = (C.c_int32 * n_imu)(*([15] * n_imu))
+    begin = (C.c_int32 * (n_imu + 1))(*[4 * i for i in range(n_imu + 1)])
+    g2.n_host = n_imu
+    g2.host_nres = nres
+    g2.host_blk_begin = begin
+    g2.host_blocks = g.imu_blocks
+    g2.host_eval = C.cast(cb, C.c_void_p)
+    g2.host_user = None
+    b = swgn.Batch([C.pointer(g2)], opt)
+    o = ob.OracleSolver(w.graph_p, opt)
+    cost, _, _ = b.evaluate(0, o.n_res, o.n_cols)
+    ocost = o.evaluate()[0]
+    assert abs(cost - ocost) <= 1e-12 * ocost
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    b.close()
+    assert calls["n"] > 2 * n_imu and calls["jac"] > 0
+    assert (sm.num_iterations, sm.num_successful_steps, sm.termination_type) == (sm0.num_iterations, sm0.num_successful_steps, sm0.termination_type)
+    assert abs(sm.final_cost - sm0.final_cost) <= 1e-8 * sm0.final_cost
+    assert state_err(x, x0) < 1e-7
