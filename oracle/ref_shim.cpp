@@ -15,6 +15,19 @@ double ref_velecitydistance(const double* rr, const double* rs, const double* vr
 double ref_dot(const double* a, const double* b, int n) { return dot(a, b, n); }
 void ref_xyz2enu(const double* pos, double* E) { xyz2enu(pos, E); }
 void ref_ecef2pos(const double* r, double* pos) { ecef2pos(r, pos); }
+// update_azel (common_function.cpp:394-408) on a mea_t filled from flat arrays; el is in/out
+void ref_update_azel(const double* globalxyz, int n, const double* satpos3, const unsigned char* svh, double* el) {
+  static mea_t m;
+  double xyz[3] = {globalxyz[0], globalxyz[1], globalxyz[2]};
+  m.obs_count = n;
+  for (int i = 0; i < n; ++i) {
+    for (int c = 0; c < 3; ++c) m.obs_data[i].satellite_pos[c] = satpos3[3 * i + c];
+    m.obs_data[i].SVH = svh[i];
+    m.obs_data[i].el = el[i];
+  }
+  update_azel(xyz, &m);
+  for (int i = 0; i < n; ++i) el[i] = m.obs_data[i].el;
+}
 }
 
 // ---- the reference's own factor classes (RVI/factor/*.cpp compiled where they lie, against oracle/ref_stubs' minimal

@@ -40,6 +40,12 @@ swgn_status fail(swgn_status st, const std::string& m) {
     if (e_ != cudaSuccess)                                                                        \
       return fail(SWGN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
+}  // namespace
+namespace swgn {
+// other translation units of the library (gnss_epoch.cpp) report through the same thread-local message
+swgn_status set_error(swgn_status st, const std::string& m) { return fail(st, m); }
+}  // namespace swgn
+namespace {
 
 // ---- device / pinned slabs.  A batch takes ONE device allocation and ONE pinned allocation and carves its
 // arrays out of them; destroyed batches park their slabs in a small process-wide cache so that the

@@ -261,3 +261,51 @@ def ambiguity_fix(A, y, epoch_begin, obs_amb, obs_sysfreq, last_fix=0):
                                   _ip(pairs), _dp(F), C.byref(res))
     nb = res.n_dd
     return pairs[:2 * nb].reshape(nb, 2), F[:2 * nb].reshape(2, nb).T.copy(), res
+
+
+# ---- per-epoch GNSS preprocessing (oracle/oracle_gnss_epoch.cpp) ---------------------------------------------------
+class OracleGnssTracker:
+    def __init__(self, cfg):
+        import swgn_gnss as G
+        self.G = G
+        L = oracle()
+        L.oracle_gnss_tracker_new.restype = C.c_void_p
+        L.oracle_gnss_tracker_new.argtypes = [P(G.Config)]
+        L.oracle_gnss_tracker_free.argtypes = [C.c_void_p]
+        L.oracle_gnss_tracker_count.argtypes = [C.c_void_p, i32]
+        L.oracle_gnss_tracker_get.argtypes = [C.c_void_p, i32, i32, P(G.Ambiguity)]
+        L.oracle_gnss_tracker_set_value.argtypes = [C.c_void_p, i32, i32, f64]
+        L.oracle_gnss_preprocess.argtypes = [C.c_void_p, P(G.Epoch), P(G.Frame), P(G.Output)]
+        self.h = L.oracle_gnss_tracker_new(C.byref(cfg))
+
+    def count(self, family):
+        return oracle().oracle_gnss_tracker_count(self.h, family)
+
+    def get(self, family, handle):
+        a = self.G.Ambiguity()
+        assert oracle().oracle_gnss_tracker_get(self.h, family, handle, C.byref(a)) == 0
+        return a
+
+    def set_value(self, family, handle, v):
+        oracle().oracle_gnss_tracker_set_value(self.h, family, handle, v)
+
+    def preprocess(self, epoch, frame, out=None):
+        out = out or self.G.OutputBuffers()
+        rc = oracle().oracle_gnss_preprocess(self.h, C.byref(epoch), C.byref(frame), C.byref(out.c))
+        assert rc == 0, rc
+        return out
+
+    def __del__(self):
+        try:
+            oracle().oracle_gnss_tracker_free(self.h)
+        except Exception:
+            pass
+
+
+def update_azel(globalxyz, epoch):
+    import swgn_gnss as G
+    L = oracle()
+    L.oracle_update_azel.argtypes = [P(f64), P(G.Epoch)]
+    L.oracle_update_azel.restype = None
+    x = np.ascontiguousarray(globalxyz, np.float64)
+    L.oracle_update_azel(_dp(x), C.byref(epoch))

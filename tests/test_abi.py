@@ -14,15 +14,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "swgn.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(swgn_[a-z_0-9]+)\s*\(", text)))
+    names = set()
+    for header in ("swgn.h", "swgn_gnss.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(swgn_[a-z_0-9]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
     L = C.CDLL(os.path.join(ROOT, "rtk-visual-inertial-navigation_b200", "libswgn.so"))
     names = declared_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 35 and "swgn_gnss_preprocess" in names
     for n in names:
         assert hasattr(L, n), n
     assert swgn.lib().swgn_version().decode().startswith("swgn")

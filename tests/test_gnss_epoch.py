@@ -1,0 +1,358 @@
+"""Per-epoch GNSS linearisation (include/swgn_gnss.h): GnssPreprocess / AddGnssResidual /
+MarginalizationInfo::marginalize (RVI/swf/swf_gnss.cpp:265-587, swf_core.cpp:87-205, marginalization_factor.cpp:260-377).
+
+CPU part: the oracle restatement against (a) the reference's own update_azel compiled into oracle/_ref, (b) an independent
+numpy assembly of the epoch's normal equations and Schur complement, (c) the bookkeeping expectations of a scripted
+scenario (announced slips, an unannounced jump, an elevation mask, an unhealthy satellite, a data gap).
+GPU part: the product (device elevations / gating residuals, export-mode pass, LEVENBERG_MARQUARDT pass through the C ABI)
+against the oracle, epoch by epoch over the same scenario, for several receivers in one call."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import gnss_scenario as S
+import oracle_binding as ob
+import swgn_gnss as G
+
+CLIGHT = 299792458.0
+_libm = C.CDLL("libm.so.6")
+_libm.sinf.restype = C.c_float
+_libm.sinf.argtypes = [C.c_float]
+
+
+def run_oracle(sc, cfg, n_epochs, hook=None):
+    T = ob.OracleGnssTracker(cfg)
+    dt, black = np.zeros(G.NCLK), 0.02
+    log = []
+    for k in range(n_epochs):
+        e, obs, f = sc.epoch(k)
+        for c in range(G.NCLK):
+            f.gnss_dt[c] = dt[c]
+        f.blackvalue = black
+        if hook:
+            hook(k, e, f)
+        raw = S.copy_epoch(e, obs)
+        f_in = S.copy_frame(f)
+        out = T.preprocess(e, f)
+        dt, black = np.array(f.gnss_dt[:]), f.blackvalue
+        log.append(dict(epoch=e, obs=obs, frame=f, frame_in=f_in, raw=raw, out=out))
+    return T, log
+
+
+def test_update_azel_matches_the_reference_build():
+    L = ob.ref()
+    if L is None:
+        pytest.skip("oracle/_ref not built")
+    L.ref_update_azel.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ubyte), C.POINTER(C.c_double)]
+    cfg = G.default_config()
+    sc = S.Scenario(3, cfg=cfg)
+    for k in (0, 5):
+        e, obs, f = sc.epoch(k)
+        xyz = np.array([f.pose[c] + e.base_xyz[c] for c in range(3)])
+        sat = np.array([[obs[i].sat_pos[c] for c in range(3)] for i in range(e.n_obs)]).ravel()
+        svh = np.array([obs[i].svh for i in range(e.n_obs)], np.uint8)
+        el = np.full(e.n_obs, -7.0)
+        for i in range(e.n_obs):
+            obs[i].el = -7.0
+        L.ref_update_azel(xyz.ctypes.data_as(C.POINTER(C.c_double)), e.n_obs, sat.ctypes.data_as(C.POINTER(C.c_double)),
+                          svh.ctypes.data_as(C.POINTER(C.c_ubyte)), el.ctypes.data_as(C.POINTER(C.c_double)))
+        ob.update_azel(xyz, e)
+        mine = np.array([obs[i].el for i in range(e.n_obs)])
+        assert np.array_equal(mine, el)          # same libm, same operation order: bit-exact
+        assert (el[svh != 0] == -7.0).all()       # unhealthy satellites are skipped
+        up = el[svh == 0]
+        assert up.min() > np.radians(11.0) and up.max() < np.radians(86.0)
+
+
+def numpy_normal_equations(cfg, e, obs, f):
+    """Independent assembly of A = sum J'J, b = sum J'r of the epoch's factors (RTK carrier, RTK pseudorange, Doppler,
+    InitialBlackFactor; the default configuration) at (pose, speed-bias, black, N = 0, clocks), in the order
+    clocks (slot order) | pose 6 | speed-bias 9 | black | ambiguities (observation order), and its Schur complement."""
+    lams = [[cfg.lams[s][q] for q in range(2)] for s in range(3)]
+    pos = np.array(f.pose[:3]) + np.array(e.base_xyz[:])
+    rows = []   # (dict column -> value, residual)
+    amb = []
+    for i in range(e.n_obs):
+        o = obs[i]
+        if o.rtk_n[0] >= 0 and o.el >= cfg.azelmin:
+            amb.append(o.rtk_n[0])
+
+    def weight(el, var):
+        b = CLIGHT * 5e-12 * e.br_time_diff
+        s = float(_libm.sinf(C.c_float(el)))   # the reference's single-precision sinf, gnss_factor.cpp:100
+        return 1.0 / np.sqrt(var / s / s + b * b)
+    for i in range(e.n_obs):
+        o = obs[i]
+        sat = np.array(o.sat_pos[:])
+        d = pos - sat
+        rho = np.linalg.norm(d)
+        u = d / rho
+        r1 = rho + S.OMGE * (sat[0] * pos[1] - sat[1] * pos[0]) / CLIGHT
+        lam = lams[o.sys][0]
+        if o.el < cfg.azelmin:
+            continue
+        if o.rtk_n[0] >= 0:
+            w = weight(o.el, (o.rtk_lstd[0] * lam) ** 2)
+            rows.append(({("p", 0): w * u[0], ("p", 1): w * u[1], ("p", 2): w * u[2], ("n", o.rtk_n[0]): -w * lam, ("c", o.sys * 2): w},
+                         w * (r1 - 0.0 * lam - o.rtk_l[0] * lam + f.gnss_dt[o.sys * 2])))
+        if o.rtk_p[0] != 0 and o.svh == 0 and o.rtk_pstd[0] <= 2:
+            w = weight(o.el, o.rtk_pstd[0] ** 2)
+            rows.append(({("p", 0): w * u[0], ("p", 1): w * u[1], ("p", 2): w * u[2], ("c", o.sys * 2): w},
+                         w * (r1 - o.rtk_p[0] + f.gnss_dt[o.sys * 2])))
+    for i in range(e.n_obs):
+        o = obs[i]
+        if o.spp_d[0] == 0 or o.svh != 0 or o.spp_dstd[0] > 2 or o.el < cfg.azelmin:
+            continue
+        lam = lams[o.sys][0]
+        w = np.sin(o.el) ** 2 / (o.spp_dstd[0] * lam)
+        sat, vs = np.array(o.sat_pos[:]), np.array(o.sat_vel[:])
+        vr = np.array(f.speed_bias[:3])
+        d = pos - sat
+        rho = np.linalg.norm(d)
+        u = d / rho
+        rate = S.range_rate(pos, sat, vr, vs)
+        jp = w * (np.eye(3) - np.outer(u, u)) @ (vr - vs) / rho
+        rows.append(({("v", 0): w * u[0], ("v", 1): w * u[1], ("v", 2): w * u[2], ("c", 12): w, ("p", 0): jp[0], ("p", 1): jp[1], ("p", 2): jp[2]},
+                     w * (rate + f.gnss_dt[12] + o.spp_d[0] * lam)))
+    rows.append(({("b", 0): 1.0}, f.blackvalue * 1.0))
+    clk = sorted({k[1] for r, _ in rows for k in r if k[0] == "c"})
+    col = {}
+    for s in clk:
+        col[("c", s)] = len(col)
+    m = len(col)
+    for c in range(6):
+        col[("p", c)] = m + c
+    for c in range(9):
+        col[("v", c)] = m + 6 + c
+    col[("b", 0)] = m + 15
+    for a in amb:
+        col[("n", a)] = len(col) if ("n", a) not in col else col[("n", a)]
+    N = m + 16 + len(amb)
+    J = np.zeros((len(rows), N))
+    r = np.zeros(len(rows))
+    for k, (jr, rr) in enumerate(rows):
+        for key, v in jr.items():
+            J[k, col[key]] = v
+        r[k] = rr
+    A, b = J.T @ J, J.T @ r
+    Amm, Amr, Arr = A[:m, :m], A[:m, m:], A[m:, m:]
+    As = Arr - Amr.T @ np.linalg.solve(Amm, Amr)
+    bs = b[m:] - Amr.T @ np.linalg.solve(Amm, b[:m])
+    return As, bs, amb, len(rows)
+
+
+def test_oracle_prior_is_the_schur_complement_of_the_epoch():
+    cfg = G.default_config()
+    sc = S.Scenario(1, cfg=cfg)
+    T, log = run_oracle(sc, cfg, 3)
+    for rec in log:
+        out, e, obs = rec["out"], rec["epoch"], rec["obs"]
+        keep, x0, J0, r0 = out.prior()
+        As, bs, amb, nrows = numpy_normal_equations(cfg, e, obs, rec["frame_in"])
+        assert out.c.n_factors == nrows
+        assert [k[0] for k in keep[:3]] == [G.KEEP_POSE, G.KEEP_SPEED_BIAS, G.KEEP_BLACK]
+        assert [k[1] for k in keep[3:]] == amb and all(k[0] == G.KEEP_AMB_RTK for k in keep[3:])
+        assert [k[2] for k in keep] == [0, 6, 15] + list(range(16, 16 + len(amb)))
+        scale = np.abs(As).max()
+        assert np.abs(J0.T @ J0 - As).max() < 1e-9 * scale
+        assert np.abs(J0.T @ r0 - bs).max() < 1e-9 * np.abs(bs).max()
+        # linearisation point: pose, speed-bias, black as given, ambiguities at zero (PhaseBiasSaveAndReset)
+        assert np.array_equal(x0[:7], np.array(rec["frame_in"].pose[:]))
+        assert np.array_equal(x0[7:16], np.array(rec["frame_in"].speed_bias[:]))
+        assert (x0[17:] == 0).all()
+        # rank: rotation (3) and the IMU biases (6) are unobserved by GNSS
+        assert np.linalg.matrix_rank(J0, tol=1e-6) == J0.shape[0] - 9
+
+
+def test_oracle_bookkeeping_on_the_scripted_scenario():
+    cfg = G.default_config()
+    sc = S.Scenario(0, cfg=cfg)
+    T, log = run_oracle(sc, cfg, 14)
+    new = [tuple(r["out"].c.n_new[:]) for r in log]
+    slips = [r["out"].c.n_slip_rtk for r in log]
+    # epoch 0: 20 satellites, one below the mask, one unhealthy -> 18 ambiguities of each phase family (the SPP list is
+    # maintained whether or not USE_SPP_PHASE is set, as in the reference)
+    assert new[0] == (18, 18, 0) and log[0]["epoch"].n_obs == 20
+    assert new[1] == new[2] == new[3] == (0, 0, 0)
+    assert new[4] == (1, 0, 0) and slips[4] == 0            # announced slip: new RTK ambiguity, no gate hit
+    assert slips[6] == 1 and new[6] == (1, 1, 0)            # unannounced 3-cycle jump: caught by the median gate; resets SPP too
+    assert new[8][0] >= 1                                   # second announced slip
+    assert new[9] == (18, 18, 0)                            # 13 s gap > ambiguity_timeout: everything starts again
+    assert all(n == (0, 0, 0) for n in new[10:])
+    # counters: an ambiguity tracked since epoch 9 has been counted 5 times at the end
+    a = T.get(G.AMB_RTK, T.count(G.AMB_RTK) - 1)
+    assert a.continue_count == 5 and a.last_update_time == log[-1]["epoch"].ros_time
+    # masked satellite: phase measurements zeroed, no handle; unhealthy satellite: untouched, no handle
+    e, obs = log[0]["epoch"], log[0]["obs"]
+    low = [i for i in range(e.n_obs) if obs[i].svh == 0 and obs[i].el < cfg.azelmin]
+    assert len(low) == 1 and obs[low[0]].rtk_l[0] == 0 and obs[low[0]].rtk_n[0] == -1
+    bad = [i for i in range(e.n_obs) if obs[i].svh]
+    assert len(bad) == 1 and obs[bad[0]].rtk_l[0] != 0 and obs[bad[0]].rtk_n[0] == -1
+    # the initialisation solve puts every residual near zero: float ambiguities absorb the range within the
+    # pseudorange noise, clocks within a metre of the truth
+    t_last = log[-1]["epoch"].ros_time - 1000.0
+    for s in (0, 2, 4):
+        assert abs(log[-1]["frame"].gnss_dt[s] - (sc.clk[s] + sc.clk_rate[s] * t_last)) < 1.0
+    for r in log:
+        s = r["out"].c.init_summary
+        assert s.termination_type in (0, 1) and s.final_cost < 50 and s.num_iterations <= 2
+
+
+def test_reset_of_all_phase_biases_and_constant_old_ambiguities():
+    cfg = G.default_config()
+    sc = S.Scenario(2, cfg=cfg)
+
+    def hook(k, e, f):
+        if k == 12:
+            f.not_fix_count = cfg.phase_all_reset_count + 1
+    T, log = run_oracle(sc, cfg, 14, hook)
+    assert log[12]["out"].c.n_new[0] == 18          # not_fix_count above Phase_ALL_RESET_COUNT: every RTK ambiguity restarts
+    # an ambiguity older than init_constant_after epochs is not moved by the initialisation solve
+    cfg2 = G.default_config()
+    cfg2.init_constant_after = 2
+    sc2 = S.Scenario(2, cfg=cfg2)
+    T2 = ob.OracleGnssTracker(cfg2)
+    dt = np.zeros(G.NCLK)
+    before = None
+    for k in range(5):
+        e, obs, f = sc2.epoch(k)
+        for c in range(G.NCLK):
+            f.gnss_dt[c] = dt[c]
+        if k == 4:
+            before = T2.get(G.AMB_RTK, 0).value
+        T2.preprocess(e, f)
+        dt = np.array(f.gnss_dt[:])
+    assert T2.get(G.AMB_RTK, 0).continue_count == 5 and T2.get(G.AMB_RTK, 0).value == before
+
+
+# ---- GPU: product against oracle ------------------------------------------------------------------------------------
+def _compare_epoch(cfg, To, Tp, eo, ep, fo, fp, oo, op):
+    # bookkeeping: identical decisions
+    assert tuple(oo.c.n_new[:]) == tuple(op.c.n_new[:])
+    assert (oo.c.n_slip_rtk, oo.c.n_slip_spp, oo.c.n_factors) == (op.c.n_slip_rtk, op.c.n_slip_spp, op.c.n_factors)
+    assert eo.n_obs == ep.n_obs
+    for i in range(eo.n_obs):
+        a, b = eo.obs[i], ep.obs[i]
+        assert (a.rtk_n[0], a.spp_n[0], a.pcorr_n[0]) == (b.rtk_n[0], b.spp_n[0], b.pcorr_n[0])
+        assert abs(a.el - b.el) < 1e-12
+        assert (a.rtk_l[0], a.spp_l[0], a.spp_p0[0], a.spp_p[0]) == (b.rtk_l[0], b.spp_l[0], b.spp_p0[0], b.spp_p[0])
+    for fam in range(3):
+        assert To.count(fam) == Tp.count(fam)
+        for h in range(To.count(fam)):
+            a, b = To.get(fam, h), Tp.get(fam, h)
+            assert (a.continue_count, a.slip_count, a.half_flag, a.sys, a.f, a.sat, a.last_update_time) == \
+                   (b.continue_count, b.slip_count, b.half_flag, b.sys, b.f, b.sat, b.last_update_time)
+            assert abs(a.value - b.value) < 1e-6 * max(1.0, abs(a.value)), (fam, h, a.value, b.value)
+    # the epoch's prior: same keep blocks, same information (J0 itself is defined up to an orthogonal factor)
+    ko, xo, Jo, ro = oo.prior()
+    kp, xp, Jp, rp = op.prior()
+    assert ko == kp and np.array_equal(xo, xp)
+    Ao, Ap = Jo.T @ Jo, Jp.T @ Jp
+    assert np.abs(Ao - Ap).max() < 1e-9 * np.abs(Ao).max()
+    bo, bp = Jo.T @ ro, Jp.T @ rp
+    assert np.abs(bo - bp).max() < 1e-8 * np.abs(bo).max()
+    assert abs(ro @ ro - rp @ rp) < 1e-8 * max(1.0, ro @ ro)
+    # clocks / blackvalue after the initialisation solve
+    for c in range(G.NCLK):
+        assert abs(fo.gnss_dt[c] - fp.gnss_dt[c]) < 1e-6 * max(1.0, abs(fo.gnss_dt[c]))
+    assert abs(fo.blackvalue - fp.blackvalue) < 1e-9
+    so, sp = oo.c.init_summary, op.c.init_summary
+    assert so.termination_type == sp.termination_type and so.num_iterations == sp.num_iterations
+    assert abs(so.initial_cost - sp.initial_cost) < 1e-9 * so.initial_cost
+    assert abs(so.final_cost - sp.final_cost) < 1e-6 * max(1.0, so.final_cost)
+
+
+def _variant(name):
+    cfg = G.default_config()
+    if name == "spp":       # rover-only: SPP pseudorange / carrier phase + pseudorange corrections, no base station
+        cfg.use_rtk = cfg.use_rtd = 0
+        cfg.use_spp_phase = cfg.use_spp_correction = 1
+        cfg.estimate_pcorrection_period = 3
+    return cfg
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["rtk", "spp"])
+def test_gpu_preprocess_matches_the_oracle_over_a_scenario(variant):
+    """Three receivers (different seeds) through one swgn_gnss_preprocess call per epoch, 14 epochs."""
+    cfg = _variant(variant)
+    seeds = (0, 5, 9)
+    sco = [S.Scenario(s, cfg=cfg) for s in seeds]
+    scp = [S.Scenario(s, cfg=cfg) for s in seeds]
+    To = [ob.OracleGnssTracker(cfg) for _ in seeds]
+    Tp = [G.Tracker(cfg) for _ in seeds]
+    dt = [np.zeros(G.NCLK) for _ in seeds]
+    black = [0.02 for _ in seeds]
+    seen_slip = 0
+    for k in range(14):
+        eo, fo, ep, fp, keep = [], [], [], [], []
+        for r in range(len(seeds)):
+            e1, o1, f1 = sco[r].epoch(k)
+            e2, o2, f2 = scp[r].epoch(k)
+            for f in (f1, f2):
+                for c in range(G.NCLK):
+                    f.gnss_dt[c] = dt[r][c]
+                f.blackvalue = black[r]
+                if k == 12 and r == 1:
+                    f.not_fix_count = cfg.phase_all_reset_count + 1
+            eo.append(e1), fo.append(f1), ep.append(e2), fp.append(f2)
+            keep += [o1, o2]
+        oo = [To[r].preprocess(eo[r], fo[r]) for r in range(len(seeds))]
+        op = G.preprocess(Tp, ep, fp)
+        for r in range(len(seeds)):
+            _compare_epoch(cfg, To[r], Tp[r], eo[r], ep[r], fo[r], fp[r], oo[r], op[r])
+            seen_slip += oo[r].c.n_slip_rtk + oo[r].c.n_slip_spp
+            # both sides continue from the ORACLE's estimates so that rounding differences do not accumulate into
+            # a different decision several epochs later
+            dt[r], black[r] = np.array(fo[r].gnss_dt[:]), fo[r].blackvalue
+            for fam in range(3):
+                for h in range(To[r].count(fam)):
+                    Tp[r].set_value(fam, h, To[r].get(fam, h).value)
+    assert seen_slip >= 3
+
+
+@pytest.mark.gpu
+def test_gpu_gate_residuals_and_records():
+    cfg = G.default_config()
+    sc = S.Scenario(4, cfg=cfg)
+    e, obs, f = sc.epoch(0)
+    rec = np.zeros((e.n_obs, 16))
+    for i in range(e.n_obs):
+        rec[i, 0:3] = obs[i].sat_pos[:]
+        rec[i, 3:6] = np.array(f.pose[:3]) + np.array(e.base_xyz[:])
+        rec[i, 9] = cfg.lams[obs[i].sys][0]
+        rec[i, 10:13] = obs[i].rtk_l[0], 17.0 + i, 3.5
+        rec[i, 13:16] = obs[i].spp_l[0], -4.0 - i, -1.25
+    out = G.gate_residuals(rec)
+    xyz = rec[0, 3:6].copy()
+    ob.update_azel(xyz, e)
+    for i in range(e.n_obs):
+        if obs[i].svh == 0:
+            assert abs(out[i, 0] - obs[i].el) < 1e-13
+        rho = S.sagnac_range(xyz, np.array(obs[i].sat_pos[:]))
+        lam = rec[i, 9]
+        assert abs(out[i, 1] - (rho - rec[i, 11] * lam - rec[i, 10] * lam + rec[i, 12])) < 1e-6
+        assert abs(out[i, 2] - (rho - rec[i, 14] * lam - rec[i, 13] * lam + rec[i, 15])) < 1e-6
+    # the packer after one preprocessing: kinds and block references as AddGnssResidual orders them
+    T = G.Tracker(cfg)
+    G.preprocess([T], [e], [f])
+    kind, blocks, data, clk, amb = T.records(e, f)
+    n_rtk = sum(1 for i in range(e.n_obs) if obs[i].rtk_n[0] >= 0 and obs[i].el >= cfg.azelmin)
+    assert list(kind[:n_rtk]) == [2] * n_rtk and list(kind[n_rtk:2 * n_rtk]) == [3] * n_rtk and list(kind[2 * n_rtk:]) == [4] * n_rtk
+    assert list(clk) == [0, 2, 4, 12] and len(amb) == n_rtk
+    assert (blocks[:n_rtk, 0] == 0).all() and (blocks[2 * n_rtk:, 0] == 1).all() and (blocks[2 * n_rtk:, 2] == 0).all()
+
+
+@pytest.mark.gpu
+def test_gpu_epoch_without_usable_observations():
+    cfg = G.default_config()
+    sc = S.Scenario(6, cfg=cfg)
+    e, obs, f = sc.epoch(0)
+    for i in range(e.n_obs):
+        obs[i].svh = 1
+    T = G.Tracker(cfg)
+    out = G.preprocess([T], [e], [f])[0]
+    keep, x0, J0, r0 = out.prior()
+    assert keep == [(G.KEEP_BLACK, -1, 0)] and J0.shape == (1, 1) and J0[0, 0] == 1.0 and r0[0] == f.blackvalue
+    assert T.count(G.AMB_RTK) == 0
