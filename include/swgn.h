@@ -381,6 +381,12 @@ swgn_status swgn_batch_get_head_marginal(swgn_batch* b, int32_t window, int32_t 
 swgn_status swgn_batch_get_marginal_prior(swgn_batch* b, int32_t window, int32_t n_tail, double* J0,
                                           double* r0, double* A, double* bvec);
 
+/* The same for every window of the batch in two launches (one CTA per window) and one read-back: window w reduces onto its
+   trailing n_tail[w] rows (0 = skip the window); its J0 (n_tail[w]^2 doubles) is written at J0_all + j_off[w], its r0 at
+   r0_all + r_off[w]. */
+swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail, const int64_t* j_off, const int64_t* r_off,
+                                           double* J0_all, double* r0_all);
+
 /* Hidden GNSS-frame states of the IMUGNSSFactor chains of `window` after the last Jacobian
    evaluation (the reference updates gnss_poses[i] / gnss_speed_bias[i] in user memory,
    gnss_imu_factor.cpp:601-632): 16 doubles (pose 7, speed-bias 9) per hidden frame in graph

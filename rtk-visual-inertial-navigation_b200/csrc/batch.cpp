@@ -1285,6 +1285,67 @@ swgn_status swgn_batch_get_marginal_prior(swgn_batch* b, int32_t w, int32_t n_ta
   return SWGN_OK;
 }
 
+swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail, const int64_t* j_off, const int64_t* r_off, double* J0_all,
+                                           double* r0_all) {
+  if (!b || !n_tail || !j_off || !r_off || !J0_all || !r0_all) return fail(SWGN_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(b->device));
+  std::vector<TRState> t(b->n);
+  CU(cudaMemcpy(t.data(), b->d_state, sizeof(TRState) * b->n, cudaMemcpyDeviceToHost));
+  std::vector<int64_t> off((size_t)4 * b->n, 0);
+  int64_t n_out = 0, total = 0;  // results (J0 | r0 of every window) first, so that one copy of n_out doubles brings them back
+  int max_m = 0, max_n = 0;
+  for (int w = 0; w < b->n; ++w) {
+    const int n = n_tail[w];
+    if (n == 0) continue;
+    if (n < 0 || n > b->desc[w].n_f) return fail(SWGN_ERR_INVALID, "bad n_tail");
+    if (!t[w].have_reduced) return fail(SWGN_ERR_INVALID, "no reduced system available: run an export-mode solve (is_optimize = 0) first");
+    off[4 * w + 2] = n_out;
+    n_out += (int64_t)n * n + n;
+  }
+  total = n_out;
+  for (int w = 0; w < b->n; ++w) {
+    const int n = n_tail[w];
+    if (n == 0) continue;
+    const int m = b->desc[w].n_f - n;
+    max_m = std::max(max_m, m);
+    max_n = std::max(max_n, n);
+    off[4 * w] = total;
+    total += (int64_t)n * n;
+    off[4 * w + 1] = total;
+    total += n;
+    off[4 * w + 3] = total;
+    total += (int64_t)std::max(head_marginal_scratch_doubles(m, n), prior_sqrt_scratch_doubles(n));
+  }
+  if (total == 0) return SWGN_OK;
+  double* dbuf = nullptr;
+  int64_t* doff = nullptr;
+  int32_t* dn = nullptr;
+  std::vector<double> host;
+  cudaError_t e = cudaMalloc(&dbuf, sizeof(double) * total);
+  if (e == cudaSuccess) e = cudaMalloc(&doff, sizeof(int64_t) * off.size());
+  if (e == cudaSuccess) e = cudaMalloc(&dn, sizeof(int32_t) * b->n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(doff, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n_tail, sizeof(int32_t) * b->n, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) e = launch_marginal_priors(b->db, max_m, max_n, dn, doff, dbuf, b->stream);
+  if (e == cudaSuccess) {
+    host.resize((size_t)n_out);
+    e = cudaMemcpyAsync(host.data(), dbuf, sizeof(double) * n_out, cudaMemcpyDeviceToHost, b->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  cudaFree(dbuf);
+  cudaFree(doff);
+  cudaFree(dn);
+  CU(e);
+  for (int w = 0; w < b->n; ++w) {
+    const int n = n_tail[w];
+    if (n == 0) continue;
+    const double* src = host.data() + off[4 * w + 2];
+    std::memcpy(J0_all + j_off[w], src, sizeof(double) * (size_t)n * n);
+    std::memcpy(r0_all + r_off[w], src + (size_t)n * n, sizeof(double) * n);
+  }
+  return SWGN_OK;
+}
+
 swgn_status swgn_batch_get_chain_frames(swgn_batch* b, int32_t w, int32_t* n_frames, double* frames) {
   if (!b || w < 0 || w >= b->n || !n_frames) return fail(SWGN_ERR_INVALID, "bad arguments");
   const WinDesc& d = b->desc[w];

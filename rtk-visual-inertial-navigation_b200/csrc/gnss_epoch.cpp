@@ -13,11 +13,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/swgn_gnss.h"
@@ -331,6 +334,28 @@ struct EpochGraph {
   }
 };
 
+// receivers are independent: the host phases run over them on all host threads
+template <class F>
+void parallel_for(int n, F fn) {
+  const int nt = std::max(1, std::min<int>(n / 64, (int)std::thread::hardware_concurrency()));
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const int i0 = next.fetch_add(16);
+      if (i0 >= n) break;
+      for (int i = i0; i < std::min(n, i0 + 16); ++i) fn(i);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+}
+
 double median_of(std::vector<double>& v) {  // std::sort + v[size / 2], swf_gnss.cpp:381-388
   std::sort(v.begin(), v.end());
   return v[v.size() / 2];
@@ -443,6 +468,14 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
       if (trackers[j] == trackers[i]) return set_error(SWGN_ERR_INVALID, "one tracker may appear once per call");
   }
   const swgn_gnss_config cfg = trackers[0]->cfg;
+  const bool dbg = std::getenv("SWGN_GNSS_DEBUG") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gnss] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   if (cudaSetDevice(cfg.device) != cudaSuccess) return set_error(SWGN_ERR_NO_DEVICE, "no usable CUDA device (there is no CPU fallback)");
   swgn_status st = SWGN_OK;
 
@@ -452,7 +485,7 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
   const int64_t n_obs_all = obs0[n];
   std::vector<double> rec((size_t)16 * std::max<int64_t>(n_obs_all, 1), 0.0), gate((size_t)3 * std::max<int64_t>(n_obs_all, 1), 0.0);
   std::vector<int32_t> flags((size_t)std::max<int64_t>(n_obs_all, 1), 0);
-  for (int i = 0; i < n; ++i) {
+  parallel_for(n, [&](int i) {
     swgn_gnss_tracker& T = *trackers[i];
     swgn_epoch& E = *epochs[i];
     const swgn_gnss_frame& F = frames[i];
@@ -511,8 +544,9 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
       }
       flags[obs0[i] + k] = fl;
     }
-  }
+  });
 
+  lap("phase A (host)");
   // ---- device: elevations + gating residuals of every observation of the call ---------------------------------
   {
     double *d_rec = nullptr, *d_out = nullptr;
@@ -532,8 +566,9 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
     }
   }
 
+  lap("gate residuals (device)");
   // ---- phase B: medians, slip conditions, new ambiguities, counters (swf_gnss.cpp:346-500) ---------------------
-  for (int i = 0; i < n; ++i) {
+  parallel_for(n, [&](int i) {
     swgn_gnss_tracker& T = *trackers[i];
     swgn_epoch& E = *epochs[i];
     const swgn_gnss_frame& F = frames[i];
@@ -611,21 +646,25 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
         if (d.pcorr_n[q] >= 0) T.amb[SWGN_AMB_PCORR][d.pcorr_n[q]].continue_count++;
       }
     }
-  }
+  });
 
+  lap("phase B (host)");
   // ---- pack (AddGnssResidual) ------------------------------------------------------------------------------
   std::vector<EpochGraph> G(n);
   std::vector<const swgn_graph*> gp;  // epochs with at least one GNSS factor
   std::vector<int> gi;
-  for (int i = 0; i < n; ++i) {
+  std::vector<char> too_small(n, 0);
+  parallel_for(n, [&](int i) {
     G[i].build(*trackers[i], *epochs[i], frames[i]);
     swgn_gnss_output& O = outputs[i];
     O.n_factors = (int32_t)G[i].kind.size() + 1;
     O.n_keep = 1 + (G[i].B.b_pose >= 0) + (G[i].B.b_sb >= 0) + (int32_t)G[i].B.amb_handle.size();
     O.n = G[i].n_keep_tangent;
     std::memset(&O.init_summary, 0, sizeof(O.init_summary));
-    if (O.n_keep > O.cap_keep || O.n > O.cap_n || !O.keep_kind || !O.keep_handle || !O.keep_idx || !O.x0 || !O.J0 || !O.r0)
-      return set_error(SWGN_ERR_INVALID, "output buffers too small for the epoch's keep blocks");
+    if (O.n_keep > O.cap_keep || O.n > O.cap_n || !O.keep_kind || !O.keep_handle || !O.keep_idx || !O.x0 || !O.J0 || !O.r0) {
+      too_small[i] = 1;
+      return;
+    }
     int kb = 0, col = 0, xo = 0;
     auto keep = [&](int kind, int handle, int tangent, const double* x, int nx) {
       O.keep_kind[kb] = kind;
@@ -644,11 +683,14 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
       // no usable observation: the epoch's prior is the InitialBlackFactor alone (1 x 1: J0 = istd, r0 = istd * x)
       O.J0[0] = G[i].unit_istd;
       O.r0[0] = G[i].unit_istd * frames[i].blackvalue;
-      continue;
     }
-    gi.push_back(i);
+  });
+  for (int i = 0; i < n; ++i) {
+    if (too_small[i]) return set_error(SWGN_ERR_INVALID, "output buffers too small for the epoch's keep blocks");
+    if (!G[i].kind.empty()) gi.push_back(i);
   }
   if (gi.empty()) return SWGN_OK;
+  lap("pack");
 
   swgn_options opt;
   swgn_default_options(&opt);
@@ -668,20 +710,34 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
   opt.n_parameter_head = 1;  // the export switch of the modified Ceres needs a head: the one group holding every keep block
   st = swgn_batch_create(&opt, (int32_t)gp.size(), gp.data(), &batch);
   if (st != SWGN_OK) return st;
+  lap("pass 1 create");
   st = swgn_batch_solve(batch, sums.data());
-  if (std::getenv("SWGN_GNSS_DEBUG"))
-    for (size_t k = 0; k < gi.size(); ++k)
-      std::fprintf(stderr, "[gnss pass 1] epoch %d: status %d term %d cost %.6g -> %.6g it %d solves %d n_e %d n_f %d n_res %d\n", gi[k], (int)st,
-                   sums[k].termination_type, sums[k].initial_cost, sums[k].final_cost, sums[k].num_iterations, sums[k].num_linear_solves,
-                   sums[k].n_e, sums[k].n_f, sums[k].n_residuals);
-  for (size_t k = 0; st == SWGN_OK && k < gi.size(); ++k) {
-    swgn_gnss_output& O = outputs[gi[k]];
-    if (sums[k].n_f != O.n) {
-      st = set_error(SWGN_ERR_INVALID, "internal: reduced system size differs from the keep blocks");
-      break;
+  lap("pass 1 solve");
+  if (st == SWGN_OK) {  // all priors in two launches; every J0 lands in its caller buffer through a staging block
+    std::vector<int32_t> n_tail(gi.size());
+    std::vector<int64_t> j_off(gi.size()), r_off(gi.size());
+    int64_t nj = 0, nr = 0;
+    for (size_t k = 0; k < gi.size(); ++k) {
+      const swgn_gnss_output& O = outputs[gi[k]];
+      if (sums[k].n_f != O.n) {
+        st = set_error(SWGN_ERR_INVALID, "internal: reduced system size differs from the keep blocks");
+        break;
+      }
+      n_tail[k] = O.n;
+      j_off[k] = nj;
+      r_off[k] = nr;
+      nj += (int64_t)O.n * O.n;
+      nr += O.n;
     }
-    st = swgn_batch_get_marginal_prior(batch, (int32_t)k, O.n, O.J0, O.r0, nullptr, nullptr);
+    std::vector<double> Jall((size_t)nj), rall((size_t)nr);
+    if (st == SWGN_OK) st = swgn_batch_get_marginal_priors(batch, n_tail.data(), j_off.data(), r_off.data(), Jall.data(), rall.data());
+    for (size_t k = 0; st == SWGN_OK && k < gi.size(); ++k) {
+      swgn_gnss_output& O = outputs[gi[k]];
+      std::memcpy(O.J0, Jall.data() + j_off[k], sizeof(double) * (size_t)O.n * O.n);
+      std::memcpy(O.r0, rall.data() + r_off[k], sizeof(double) * O.n);
+    }
   }
+  lap("pass 1 priors");
   swgn_batch_destroy(batch);
   batch = nullptr;
   if (st != SWGN_OK) return st;
@@ -705,19 +761,26 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
     opt.n_parameter_head = 0;
     st = swgn_batch_create(&opt, (int32_t)gp.size(), gp.data(), &batch);
     if (st != SWGN_OK) return st;
+    lap("pass 2 create");
     st = swgn_batch_solve(batch, sums.data());
+    lap("pass 2 solve");
+    if (st == SWGN_OK) {
+      xs.resize((size_t)swgn_batch_states_size(batch));
+      st = swgn_batch_get_states(batch, xs.data());  // the states of all epochs back to back, one copy
+    }
+    size_t x0 = 0;
     for (size_t k = 0; st == SWGN_OK && k < gi.size(); ++k) {
       const int i = gi[k];
-      xs.resize(G[i].state.size());
-      st = swgn_batch_get_state(batch, (int32_t)k, xs.data());
-      if (st != SWGN_OK) break;
+      const double* x = xs.data() + x0;
+      x0 += G[i].state.size();
       outputs[i].init_summary = sums[k];
-      frames[i].blackvalue = xs[G[i].offset[G[i].B.b_black]];
-      for (int s : G[i].B.clk_slots) frames[i].gnss_dt[s] = xs[G[i].offset[G[i].B.clk_block[s]]];
+      frames[i].blackvalue = x[G[i].offset[G[i].B.b_black]];
+      for (int s : G[i].B.clk_slots) frames[i].gnss_dt[s] = x[G[i].offset[G[i].B.clk_block[s]]];
       for (size_t a = 0; a < G[i].B.amb_handle.size(); ++a)
-        trackers[i]->amb[G[i].B.amb_family[a]][G[i].B.amb_handle[a]].value = xs[G[i].offset[G[i].B.b_amb0 + (int)a]];
+        trackers[i]->amb[G[i].B.amb_family[a]][G[i].B.amb_handle[a]].value = x[G[i].offset[G[i].B.b_amb0 + (int)a]];
     }
     swgn_batch_destroy(batch);
+    lap("pass 2 read-back");
   }
   return st;
 }

@@ -17,7 +17,7 @@ constexpr int kMaxSharedM = 100;
 }  // namespace
 
 // scratch: W (m x (n+1)) then, when m > kMaxSharedM, A_mm and V (m x ld each)
-__global__ void __launch_bounds__(NT) k_head_marginal(DeviceBatch b, int window, int n, double* A_out, double* b_out, double* scratch) {
+__device__ void head_marginal_body(const DeviceBatch& b, int window, int n, double* A_out, double* b_out, double* scratch) {
   extern __shared__ __align__(16) double sm[];
   const WinDesc& d = b.desc[window];
   const double* S = b.wpool + d.woff[W_S];
@@ -64,12 +64,22 @@ __global__ void __launch_bounds__(NT) k_head_marginal(DeviceBatch b, int window,
     else b_out[i] = S[(size_t)(m + i) * ldS + nf] - acc;
   }
 }
+__global__ void __launch_bounds__(NT) k_head_marginal(DeviceBatch b, int window, int n, double* A_out, double* b_out, double* scratch) {
+  head_marginal_body(b, window, n, A_out, b_out, scratch);
+}
+// every window of the batch: window w reduces onto its trailing n_tail[w] rows (0 = skip); off[4 * w + {0,1,2,3}] are
+// the offsets of its A, b, J0 | r0 (J0 first, r0 behind it) and scratch inside buf
+__global__ void __launch_bounds__(NT) k_head_marginal_batch(DeviceBatch b, const int32_t* n_tail, const int64_t* off, double* buf) {
+  const int w = blockIdx.x, n = n_tail[w];
+  if (n <= 0) return;
+  head_marginal_body(b, w, n, buf + off[4 * w], buf + off[4 * w + 1], buf + off[4 * w + 3]);
+}
 
 // MarginalizationInfo::setmarginalizeinfo(..., Sqrt = true) (RVI/factor/marginalization_factor.cpp:449-475): the
 // information form (A, b) of the head blocks becomes the next window's prior factor r = r0 + J0 (x [-] x0) with
 //   J0 = sqrt(S) V',  r0 = S^-1/2 V' b,   A = V S V', eigenvalues <= 1e-8 dropped.
 // One CTA; A and V in shared memory when n <= 100, otherwise in the global scratch (2 * n * (n|1) doubles).
-__global__ void __launch_bounds__(NT) k_prior_sqrt(const double* A_in, const double* b_in, int n, double* J0, double* r0, double* scratch) {
+__device__ void prior_sqrt_body(const double* A_in, const double* b_in, int n, double* J0, double* r0, double* scratch) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   const int ld = n | 1;
@@ -97,6 +107,15 @@ __global__ void __launch_bounds__(NT) k_prior_sqrt(const double* A_in, const dou
     for (int c = 0; c < n; ++c) acc += V[c * ld + i] * b_in[c];
     r0[i] = (lam > kEigEps ? sqrt(1.0 / lam) : 0.0) * acc;
   }
+}
+__global__ void __launch_bounds__(NT) k_prior_sqrt(const double* A_in, const double* b_in, int n, double* J0, double* r0, double* scratch) {
+  prior_sqrt_body(A_in, b_in, n, J0, r0, scratch);
+}
+__global__ void __launch_bounds__(NT) k_prior_sqrt_batch(const int32_t* n_tail, const int64_t* off, double* buf) {
+  const int w = blockIdx.x, n = n_tail[w];
+  if (n <= 0) return;
+  double* J0 = buf + off[4 * w + 2];
+  prior_sqrt_body(buf + off[4 * w], buf + off[4 * w + 1], n, J0, J0 + (size_t)n * n, buf + off[4 * w + 3]);
 }
 
 size_t prior_sqrt_scratch_doubles(int n) { return n > kMaxSharedM ? 2 * (size_t)n * (n | 1) + 2 : 2; }
@@ -127,6 +146,22 @@ cudaError_t launch_head_marginal(const DeviceBatch& b, int window, int n_f, int 
     if (e != cudaSuccess) return e;
   }
   k_head_marginal<<<1, NT, dyn, s>>>(b, window, n, A_dev, b_dev, scratch);
+  return cudaGetLastError();
+}
+
+// both steps for every window of the batch: two launches, one CTA per window
+cudaError_t launch_marginal_priors(const DeviceBatch& b, int max_m, int max_n, const int32_t* n_tail_dev, const int64_t* off_dev, double* buf,
+                                   cudaStream_t s) {
+  size_t dyn1 = sizeof(double) * (size_t)(4 * ((max_m + 1) / 2) + 4 + 34);
+  if (max_m <= kMaxSharedM) dyn1 += sizeof(double) * 2 * (size_t)max_m * (max_m | 1);
+  size_t dyn2 = sizeof(double) * (size_t)(4 * ((max_n + 1) / 2) + 4 + 34);
+  if (max_n <= kMaxSharedM) dyn2 += sizeof(double) * 2 * (size_t)max_n * (max_n | 1);
+  cudaError_t e = cudaSuccess;
+  if (dyn1 > 48 * 1024) e = cudaFuncSetAttribute(k_head_marginal_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn1);
+  if (e == cudaSuccess && dyn2 > 48 * 1024) e = cudaFuncSetAttribute(k_prior_sqrt_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2);
+  if (e != cudaSuccess) return e;
+  k_head_marginal_batch<<<b.n_windows, NT, dyn1, s>>>(b, n_tail_dev, off_dev, buf);
+  k_prior_sqrt_batch<<<b.n_windows, NT, dyn2, s>>>(n_tail_dev, off_dev, buf);
   return cudaGetLastError();
 }
 

@@ -60,6 +60,9 @@ cudaError_t launch_head_marginal(const DeviceBatch& b, int window, int n_f, int 
 size_t prior_sqrt_scratch_doubles(int n);
 cudaError_t launch_prior_sqrt(const double* A_dev, const double* b_dev, int n, double* J0_dev, double* r0_dev, double* scratch,
                               cudaStream_t s);
+// UpdateSchur + setmarginalizeinfo for every window (n_tail[w] = 0 skips one); off[4w..4w+3] = offsets of A, b, J0|r0, scratch in buf
+cudaError_t launch_marginal_priors(const DeviceBatch& b, int max_m, int max_n, const int32_t* n_tail_dev, const int64_t* off_dev, double* buf,
+                                   cudaStream_t s);
 void launch_tail_information(const DeviceBatch& b, int window, int n_tail, double* A_dev, cudaStream_t s);
 
 // IMU pre-integration (k_preint.cu): one warp per factor; noise4 = ACC_N, GYR_N, ACC_W, GYR_W (host array)

@@ -263,6 +263,7 @@ def lib():
         L.swgn_preintegrate_batch.argtypes = [i32, i32, P(i32), P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_batch_get_head_marginal.argtypes = [C.c_void_p, i32, i32, P(f64), P(f64)]
         L.swgn_batch_get_marginal_prior.argtypes = [C.c_void_p, i32, i32, P(f64), P(f64), P(f64), P(f64)]
+        L.swgn_batch_get_marginal_priors.argtypes = [C.c_void_p, P(i32), P(i64), P(i64), P(f64), P(f64)]
         L.swgn_batch_get_chain_frames.argtypes = [C.c_void_p, i32, P(i32), P(f64)]
         L.swgn_lambda_batch.argtypes = [i32, i32, P(i32), i32, P(f64), P(f64), P(f64), P(f64), P(i32)]
         L.swgn_ambiguity_fix.argtypes = [i32, i32, P(f64), P(f64), i32, P(i32), P(i32), P(i32),
@@ -426,6 +427,17 @@ class Batch:
         r0, bv = np.zeros(n_tail), np.zeros(n_tail)
         _check(lib().swgn_batch_get_marginal_prior(self.h, w, n_tail, _dp(J0), _dp(r0), _dp(A), _dp(bv)), "marginal_prior")
         return J0, r0, A, bv
+
+    def marginal_priors(self, n_tail):
+        """The prior of every window in two launches: list of (J0, r0); n_tail[w] = 0 skips window w (None, None)."""
+        nt = np.ascontiguousarray(n_tail, np.int32)
+        j_off = np.concatenate([[0], np.cumsum(nt.astype(np.int64) ** 2)]).astype(np.int64)
+        r_off = np.concatenate([[0], np.cumsum(nt.astype(np.int64))]).astype(np.int64)
+        J, r = np.zeros(max(int(j_off[-1]), 1)), np.zeros(max(int(r_off[-1]), 1))
+        _check(lib().swgn_batch_get_marginal_priors(self.h, _ip(nt), j_off.ctypes.data_as(P(i64)), r_off.ctypes.data_as(P(i64)), _dp(J), _dp(r)),
+               "marginal_priors")
+        return [(J[j_off[w]:j_off[w + 1]].reshape(nt[w], nt[w]).copy(), r[r_off[w]:r_off[w + 1]].copy()) if nt[w] else (None, None)
+                for w in range(len(nt))]
 
     def chain_frames(self, w):
         """Hidden GNSS-frame states of window w's IMUGNSSFactor chains, (n_frames, 16)."""

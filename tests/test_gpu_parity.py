@@ -325,6 +325,26 @@ def test_marginal_prior_on_the_device(which, wid, n_head):
     b.close()
 
 
+def test_marginal_priors_of_a_whole_batch_equal_the_per_window_calls():
+    ws = [swgn.SynthWindow(2, 1), swgn.SynthWindow(2, 3), swgn.SynthWindow(2, 5)]
+    opt = ws[0].options()
+    opt.is_optimize = 0
+    opt.max_num_iterations = 1
+    b = swgn.Batch([w.graph_p for w in ws], opt)
+    b.solve()
+    nt = []
+    for k in range(3):
+        cb, co, cs = b.columns(k)
+        nt.append(int(cs[len(cs) - opt.n_parameter_head:].sum()))
+    nt[1] = 0  # skipped window
+    got = b.marginal_priors(nt)
+    assert got[1] == (None, None)
+    for k in (0, 2):
+        J0, r0, A, bv = b.marginal_prior(k, nt[k])
+        assert np.array_equal(got[k][0], J0) and np.array_equal(got[k][1], r0)
+    b.close()
+
+
 def test_cholesky_export_and_tail_information():
     w = swgn.SynthWindow(2, 2)
     opt = w.options()
