@@ -7,6 +7,7 @@ scenario (announced slips, an unannounced jump, an elevation mask, an unhealthy 
 GPU part: the product (device elevations / gating residuals, export-mode pass, LEVENBERG_MARQUARDT pass through the C ABI)
 against the oracle, epoch by epoch over the same scenario, for several receivers in one call."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -356,3 +357,32 @@ def test_gpu_epoch_without_usable_observations():
     keep, x0, J0, r0 = out.prior()
     assert keep == [(G.KEEP_BLACK, -1, 0)] and J0.shape == (1, 1) and J0[0, 0] == 1.0 and r0[0] == f.blackvalue
     assert T.count(G.AMB_RTK) == 0
+
+
+_REFDEMO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libswgn_refdemo.so")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(_REFDEMO), reason="oracle/_ref not built")
+def test_gpu_preprocess_through_the_reference_wire_struct():
+    """The epoch goes through a real mea_t (RVI/gnss/include/common_function.h:115-123, compiled from the reference) and the
+    maintainer-side binding shim/reference_gnss_binding.h: same results as the direct call."""
+    L = C.CDLL(_REFDEMO)
+    L.swgn_refdemo_gnss_preprocess.argtypes = [C.c_void_p, C.POINTER(G.Epoch), C.POINTER(G.Frame), C.POINTER(G.Output), C.POINTER(C.c_int)]
+    cfg = G.default_config()
+    sa, sb = S.Scenario(7, cfg=cfg), S.Scenario(7, cfg=cfg)
+    Ta, Tb = G.Tracker(cfg), G.Tracker(cfg)
+    nbytes = C.c_int()
+    for k in range(3):
+        ea, oa, fa = sa.epoch(k)
+        eb, ob_, fb = sb.epoch(k)
+        out_a = G.preprocess([Ta], [ea], [fa])[0]
+        out_b = G.OutputBuffers()
+        assert L.swgn_refdemo_gnss_preprocess(Tb.h, C.byref(eb), C.byref(fb), C.byref(out_b.c), C.byref(nbytes)) == 0
+        ka, xa, Ja, ra = out_a.prior()
+        kb, xb, Jb, rb = out_b.prior()
+        assert ka == kb and np.array_equal(xa, xb) and np.array_equal(Ja, Jb) and np.array_equal(ra, rb)
+        assert [oa[i].el for i in range(ea.n_obs)] == [ob_[i].el for i in range(eb.n_obs)]
+        assert [oa[i].rtk_n[0] for i in range(ea.n_obs)] == [ob_[i].rtk_n[0] for i in range(eb.n_obs)]
+        assert fa.gnss_dt[:] == fb.gnss_dt[:]
+    assert nbytes.value > 64 * 300   # sizeof(mea_t): MAXOBS ObsMea records plus the header
