@@ -93,8 +93,9 @@ typedef struct swgn_ambiguity {
 enum { SWGN_AMB_RTK = 0, SWGN_AMB_SPP = 1, SWGN_AMB_PCORR = 2 };
 
 /* keep blocks of the epoch's prior, in this order: pose, speed-bias, blackvalue, then every ambiguity the epoch's
-   observations point at (RTK, SPP, pseudorange-correction; observation order).  The reference orders them by
-   address (std::map<long,...>, marginalization_factor.cpp:264-277); only the column permutation of J0 depends on it. */
+   observations point at (RTK, SPP, pseudorange-correction; observation order).  The reference's order is the
+   iteration order of a std::unordered_map keyed by address (marginalization_factor.h:76-80,
+   marginalization_factor.cpp:264-277); only the column permutation of J0 depends on it. */
 enum { SWGN_KEEP_POSE = 0, SWGN_KEEP_SPEED_BIAS = 1, SWGN_KEEP_BLACK = 2, SWGN_KEEP_AMB_RTK = 3, SWGN_KEEP_AMB_SPP = 4,
        SWGN_KEEP_AMB_PCORR = 5 };
 typedef struct swgn_gnss_output {

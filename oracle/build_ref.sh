@@ -5,13 +5,14 @@
 #   RVI/factor/gnss_factor.cpp, projection_factor.cpp, imu_factor.cpp, integration_base.cpp,
 #   pose_local_parameterization.cpp                                   the factor classes of the hot path
 #   RVI/factor/initial_factor.cpp, pose0_factor.cpp                   initialisation factors (host-evaluated through the shim)
+#   RVI/factor/marginalization_factor.cpp                             MarginalizationInfo::marginalize / MarginalizationFactor
 # Eigen, OpenCV and Ceres are not installed in this image: the factor sources are compiled against
 # oracle/ref_stubs/ (a minimal eager stand-in for the part of Eigen's dense API they use, empty OpenCV
 # headers, a type-name stub of marginalization_factor.h) and against this repository's own
 # include/ceres/ headers (CostFunction / SizedCostFunction / LocalParameterization), which doubles as
 # the build test of those headers against unmodified reference code.  NOT buildable here, and not
-# attempted: marginalization_factor.cpp and gnss_imu_factor.cpp (SelfAdjointEigenSolver, pthread
-# pipelines), the estimator (ROS, OpenCV) and Ceres itself (needs Eigen proper).
+# attempted: gnss_imu_factor.cpp (internal Ceres headers: small_blas / invert_psd_matrix on Eigen proper),
+# the estimator (ROS, OpenCV) and Ceres itself.
 # Outputs go to oracle/_ref/ only (git-ignored, travels with gpurun).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -22,21 +23,23 @@ if [ ! -d "$REF" ]; then
   exit 0
 fi
 mkdir -p "$HERE/_ref"
-g++ -O2 -fPIC -shared -ffp-contract=off -std=c++14 -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" \
-    -I"$SRC" \
+# (-include: the real <ceres/ceres.h> drags Eigen and <numeric> in, which marginalization_factor.h relies on)
+g++ -O2 -fPIC -shared -ffp-contract=off -std=c++14 -include numeric -include eigen3/Eigen/Dense \
+    -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" -I"$SRC" \
     "$REF/src/lambda.cpp" "$REF/src/common_function.cpp" \
     "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
     "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" \
-    "$HERE/ref_shim.cpp" "$HERE/ref_globals.cpp" -o "$HERE/_ref/libref_gnss.so"
+    "$SRC/factor/initial_factor.cpp" "$SRC/factor/marginalization_factor.cpp" \
+    "$HERE/ref_shim.cpp" "$HERE/ref_marg_shim.cpp" "$HERE/ref_globals.cpp" -lpthread -o "$HERE/_ref/libref_gnss.so"
 echo "built $HERE/_ref/libref_gnss.so"
 # The drop-in demonstration of the ceres:: shim on the reference's own factor classes (shim/ceres_shim_refdemo.cpp):
 # needs the product library (libswgn.so) and the generator, built by __graft_entry__.build() before this script runs.
 PKG="$HERE/../rtk-visual-inertial-navigation_b200"
 if [ -f "$PKG/libswgn.so" ] && [ -f "$PKG/libswgn_synth.so" ]; then
-  g++ -O2 -fPIC -shared -ffp-contract=off -std=c++17 -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" -I"$SRC" -I"$PKG/shim" \
+  g++ -O2 -fPIC -shared -ffp-contract=off -std=c++17 -include numeric -include eigen3/Eigen/Dense -I"$HERE/ref_stubs" -I"$HERE/../include" -I"$REF/include" -I"$SRC" -I"$PKG/shim" \
       "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
       "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" "$REF/src/common_function.cpp" \
-      "$SRC/factor/initial_factor.cpp" "$SRC/factor/pose0_factor.cpp" \
+      "$SRC/factor/initial_factor.cpp" "$SRC/factor/pose0_factor.cpp" "$SRC/factor/marginalization_factor.cpp" \
       "$PKG/shim/ceres_shim.cpp" "$PKG/shim/ceres_shim_refdemo.cpp" "$PKG/shim/gnss_refdemo.cpp" "$HERE/ref_globals.cpp" \
       -o "$HERE/_ref/libswgn_refdemo.so" -L"$PKG" -lswgn -lswgn_synth -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200'
   echo "built $HERE/_ref/libswgn_refdemo.so"

@@ -9,17 +9,20 @@
 // build, load or call anything in this directory.  Nothing under rtk-visual-inertial-navigation_b200/
 // links or includes it.
 //
-// Parity pin status:
-//   * Schur eliminate / reduced solve / back-substitute: pinned on the reference's own
-//     known-answer fixture (CERES linear_least_squares_problems.cc:135-178, problems 2-4) --
-//     tests/test_oracle_golden.py.
-//   * lambda(), matinv(), distance(), velecitydistance(): pinned against the reference's own
-//     sources compiled into oracle/_ref/libref_gnss.so (oracle/build_ref.sh).
-//   * factors a1/a3/a4/a5, MyOrdering, exports, LambdaSearch: the reference holds no test or
-//     golden vector for them and cannot be built here (needs Eigen3/ROS/OpenCV): PARITY UNPINNED
-//     by the reference; pinned by analytic-vs-numeric Jacobian checks only.
-//   * IMUGNSSFactor (oracle_chain.cpp): no test or fixture in the reference either: PARITY
-//     UNPINNED by the reference; pinned on the dense Schur complement of the whole chain
+// Parity pin status (the table in DESIGN.md section 2 lists the test behind every line):
+//   * Schur eliminate / reduced solve / back-substitute: pinned on the reference's own known-answer fixture
+//     (CERES linear_least_squares_problems.cc:135-178, problems 2-4); dogleg / Levenberg-Marquardt steps on the fixtures
+//     of dogleg_strategy_test.cc; loss correction and CauchyLoss on corrector_test.cc / loss_function_test.cc.
+//   * lambda(), matinv(), distance(), velecitydistance(), update_azel(): pinned against the reference's own sources
+//     compiled into oracle/_ref/libref_gnss.so (oracle/build_ref.sh).
+//   * factors a1 / a3 / a4 / a5, IntegrationBase, PoseLocalParameterization, varerr2: pinned on the reference's own classes
+//     (RVI/factor/*.cpp compiled unmodified into oracle/_ref against a minimal Eigen stand-in; GNSS factors bit-exact).
+//   * MarginalizationInfo::marginalize + MarginalizationFactor: pinned on the reference's own marginalization_factor.cpp
+//     compiled into oracle/_ref (tests/test_gnss_epoch.py).
+//   * MyOrdering, exports, LambdaSearch, GnssPreprocess bookkeeping: the reference holds no test or golden vector for them
+//     and the estimator cannot be built here (ROS / OpenCV): PARITY UNPINNED by execution; restated line by line.
+//   * IMUGNSSFactor (oracle_chain.cpp): gnss_imu_factor.cpp needs Ceres-internal headers on Eigen proper and is not
+//     buildable here: PARITY UNPINNED by the reference; pinned on the dense Schur complement of the whole chain
 //     (tests/test_chain_factor.py).
 //
 // RVI/   = /root/reference/rtk_visual_inertial_src/rtk_visual_inertial/src/

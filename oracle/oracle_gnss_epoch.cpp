@@ -8,15 +8,18 @@
 //   SWFOptimization::AddGnssResidual              RVI/swf/swf_core.cpp:87-205 (+ the ADDRESIDUAL macro :10-48)
 //   ResidualBlockInfo::Evaluate, MarginalizationInfo::{addResidualBlockInfo, marginalize, getParameterBlocks}
 //                                                 RVI/factor/marginalization_factor.cpp:7-70,260-400
-// Pin status: update_azel is checked against the reference's own common_function.cpp compiled into
-// oracle/_ref/libref_gnss.so (tests/test_gnss_epoch.py); the factors it evaluates are pinned bit-exact on the
-// reference's classes (tests/test_oracle_ref_factors.py); marginalize() is checked against numpy's Schur complement
-// and eigen-decomposition.  GnssPreprocess itself is a member of SWFOptimization (ROS / OpenCV / whole estimator) and
-// cannot be compiled here: its bookkeeping is restated, not pinned by execution -- PARITY UNPINNED for :265-500.
+// Pin status: update_azel is checked bit-exact against the reference's own common_function.cpp compiled into
+// oracle/_ref/libref_gnss.so; the factors it evaluates are pinned bit-exact on the reference's classes
+// (tests/test_oracle_ref_factors.py); the epoch's prior is pinned on the reference's own MarginalizationInfo::marginalize
+// (marginalization_factor.cpp compiled into oracle/_ref, fed with the reference's own factor classes through
+// oracle/ref_marg_shim.cpp) and on an independent numpy Schur complement (tests/test_gnss_epoch.py).  GnssPreprocess itself
+// is a member of SWFOptimization (ROS / OpenCV / whole estimator) and cannot be compiled here: its bookkeeping is restated,
+// not pinned by execution -- PARITY UNPINNED for :265-500.
 //
-// The one liberty: the reference orders keep blocks by the ADDRESS of the user's doubles; here all parameters of the
-// epoch are laid out in one array (pose, speed-bias, blackvalue, clocks, ambiguities: RTK, SPP, pseudorange correction
-// in observation order) so that address order is that order.
+// The one liberty: the reference keeps parameter blocks in std::unordered_map<long, ...> keyed by ADDRESS, so the order of
+// its keep blocks is whatever that container iterates in (implementation-defined); here an ordered map is used and all
+// parameters of the epoch are laid out in one array (pose, speed-bias, blackvalue, clocks, ambiguities: RTK, SPP,
+// pseudorange correction in observation order) so that the order is that order.  Only a permutation of J0's columns.
 #include <algorithm>
 #include <list>
 #include <numeric>
@@ -365,6 +368,7 @@ void AddGnssResidual(int mode, const std::set<double*>& MargePoint, MargInfo* ma
         const double lam = cfg.lams[d->sys][f];
         gnss_record(rec, d, rover->base_xyz, d->rtk_l[f] * lam, lam,
                     1 / std::sqrt(varerr2(d->el, rover->br_time_diff, std::pow(d->rtk_lstd[f] * lam, 2))), false);
+        rec[SWGN_GNSS_EL] = d->el, rec[SWGN_GNSS_DT] = rover->br_time_diff, rec[SWGN_GNSS_VAR] = std::pow(d->rtk_lstd[f] * lam, 2);
         ADDRESIDUAL({C.para_pose(), C.amb_value(SWGN_AMB_RTK, N), C.para_gnss_dt() + sys * 2 + f},
                     make_gnss_factor(SWGN_GNSS_RTK_CARRIER, rec), SWGN_GNSS_RTK_CARRIER, rec);
       }
@@ -380,6 +384,7 @@ void AddGnssResidual(int mode, const std::set<double*>& MargePoint, MargInfo* ma
         have_base = true;
         gnss_record(rec, d, rover->base_xyz, d->rtk_p[f], 0.0,
                     1 / std::sqrt(varerr2(d->el, rover->br_time_diff, std::pow(d->rtk_pstd[f], 2))), false);
+        rec[SWGN_GNSS_EL] = d->el, rec[SWGN_GNSS_DT] = rover->br_time_diff, rec[SWGN_GNSS_VAR] = std::pow(d->rtk_pstd[f], 2);
         ADDRESIDUAL({C.para_pose(), C.para_gnss_dt() + sys * 2 + f}, make_gnss_factor(SWGN_GNSS_RTK_PSEUDORANGE, rec),
                     SWGN_GNSS_RTK_PSEUDORANGE, rec);
       }
@@ -430,6 +435,27 @@ void AddGnssResidual(int mode, const std::set<double*>& MargePoint, MargInfo* ma
                   SWGN_GNSS_DOPPLER, rec);
     }
   }
+}
+}  // namespace
+
+namespace {
+// the epoch's parameter storage: pose | speed-bias | blackvalue | gnss_dt | ambiguity values (at 0: PhaseBiasSaveAndReset)
+void layout_store(EpochContext& C, swgn_epoch* data, swgn_gnss_frame* frame) {
+  const int NF = SWGN_NFREQ;
+  for (int fam = 0; fam < 3; ++fam)
+    for (int i = 0; i < data->n_obs; i++)
+      for (int f = 0; f < NF; f++) {
+        PB* p = fam == 0 ? C.RTK_Npoint[i * NF + f] : fam == 1 ? C.SPP_Npoint[i * NF + f] : C.PC_Npoint[i * NF + f];
+        if (!p) continue;
+        bool dup = false;
+        for (auto& a : C.amb_order) dup |= a.first == fam && a.second == p;
+        if (!dup) C.amb_order.push_back({fam, p});
+      }
+  C.store.assign(30 + C.amb_order.size(), 0.0);
+  std::copy(frame->pose, frame->pose + 7, C.para_pose());
+  std::copy(frame->speed_bias, frame->speed_bias + 9, C.para_speed_bias());
+  *C.blackvalue() = frame->blackvalue;
+  std::copy(frame->gnss_dt, frame->gnss_dt + SWGN_GNSS_NCLK, C.para_gnss_dt());
 }
 }  // namespace
 
@@ -598,20 +624,7 @@ int gnss_preprocess(GnssTracker* T, swgn_epoch* data, swgn_gnss_frame* frame, sw
     }
 
   // ---- parameter storage (Vector2Double) and RemainPoint, :504-521 -----------------------------------------
-  for (int fam = 0; fam < 3; ++fam)
-    for (i = 0; i < data->n_obs; i++)
-      for (int f = 0; f < NF; f++) {
-        PB* p = fam == 0 ? C.RTK_Npoint[i * NF + f] : fam == 1 ? C.SPP_Npoint[i * NF + f] : C.PC_Npoint[i * NF + f];
-        if (!p) continue;
-        bool dup = false;
-        for (auto& a : C.amb_order) dup |= a.first == fam && a.second == p;
-        if (!dup) C.amb_order.push_back({fam, p});
-      }
-  C.store.assign(30 + C.amb_order.size(), 0.0);
-  std::copy(frame->pose, frame->pose + 7, C.para_pose());
-  std::copy(frame->speed_bias, frame->speed_bias + 9, C.para_speed_bias());
-  *C.blackvalue() = frame->blackvalue;
-  std::copy(frame->gnss_dt, frame->gnss_dt + SWGN_GNSS_NCLK, C.para_gnss_dt());
+  layout_store(C, data, frame);
   std::set<double*> RemainPoint{C.para_pose(), C.para_speed_bias(), C.blackvalue()};
   for (size_t a = 0; a < C.amb_order.size(); ++a) RemainPoint.insert(&C.store[30 + a]);
 
@@ -735,10 +748,53 @@ int gnss_preprocess(GnssTracker* T, swgn_epoch* data, swgn_gnss_frame* frame, sw
   return 0;
 }
 
+// The residual blocks AddGnssResidual builds for an epoch that has been preprocessed already (ambiguity handles in its
+// observations), ambiguities at 0 as during the linearisation: kind (-1 = InitialBlackFactor, record[0] = istd), up to three
+// offsets into the parameter storage per factor (-1 pad) and the record; store_out receives the storage
+// (pose 0 | speed-bias 7 | blackvalue 16 | gnss_dt 17 | ambiguities 30..).  Returns the number of factors.
+int gnss_epoch_factors(GnssTracker* T, swgn_epoch* data, swgn_gnss_frame* frame, int cap, int32_t* kind, int32_t* store_off,
+                       double* records, double* store_out, int32_t* n_store) {
+  const int NF = SWGN_NFREQ;
+  EpochContext C;
+  C.T = T;
+  C.rover = data;
+  C.frame = frame;
+  C.RTK_Npoint.assign(data->n_obs * NF, nullptr);
+  C.SPP_Npoint.assign(data->n_obs * NF, nullptr);
+  C.PC_Npoint.assign(data->n_obs * NF, nullptr);
+  for (int i = 0; i < data->n_obs; ++i)
+    for (int f = 0; f < NF; ++f) {
+      const swgn_obs& d = data->obs[i];
+      if (d.rtk_n[f] >= 0) C.RTK_Npoint[i * NF + f] = T->by_handle[SWGN_AMB_RTK][d.rtk_n[f]];
+      if (d.spp_n[f] >= 0) C.SPP_Npoint[i * NF + f] = T->by_handle[SWGN_AMB_SPP][d.spp_n[f]];
+      if (d.pcorr_n[f] >= 0) C.PC_Npoint[i * NF + f] = T->by_handle[SWGN_AMB_PCORR][d.pcorr_n[f]];
+    }
+  layout_store(C, data, frame);
+  std::vector<Added> problem;
+  AddGnssResidual(NormalMode, std::set<double*>{}, nullptr, &problem, C);
+  if ((int)problem.size() > cap) return -1;
+  for (size_t i = 0; i < problem.size(); ++i) {
+    kind[i] = problem[i].gnss_kind;
+    for (int k = 0; k < 3; ++k)
+      store_off[3 * i + k] = k < (int)problem[i].parameter_blocks.size() ? (int32_t)(problem[i].parameter_blocks[k] - C.store.data()) : -1;
+    double* rec = records + (size_t)SWGN_GNSS_STRIDE * i;
+    std::fill(rec, rec + SWGN_GNSS_STRIDE, 0.0);
+    if (problem[i].gnss_kind < 0) rec[0] = 1.0;
+    else std::copy(problem[i].record.begin(), problem[i].record.end(), rec);
+  }
+  std::copy(C.store.begin(), C.store.end(), store_out);
+  *n_store = (int32_t)C.store.size();
+  return (int)problem.size();
+}
+
 }  // namespace oracle
 
 using namespace oracle;
 extern "C" {
+int oracle_gnss_epoch_factors(void* t, swgn_epoch* e, swgn_gnss_frame* f, int cap, int32_t* kind, int32_t* store_off, double* records,
+                              double* store_out, int32_t* n_store) {
+  return gnss_epoch_factors((GnssTracker*)t, e, f, cap, kind, store_off, records, store_out, n_store);
+}
 void* oracle_gnss_tracker_new(const swgn_gnss_config* cfg) {
   GnssTracker* t = new GnssTracker();
   t->cfg = *cfg;

@@ -15,6 +15,7 @@
 //   back-substitution: y_e = L^-T (w_g - sum_f W_f z_f).
 // (E'E + D^2)^-1 of the reference (InvertPSDMatrix, invert_psd_matrix.h:62-67: LLT-solve-identity)
 // is applied in factored form: buffer' inv buffer = (L^-1 buffer)'(L^-1 buffer).
+#include <cstdlib>
 #include <mutex>
 
 #include "dev_common.cuh"
@@ -914,7 +915,13 @@ __global__ void __launch_bounds__(kThreads) k_backsub(DeviceBatch b, int only_wi
 static size_t schur_dyn_bytes(const DeviceBatch& b) {
   size_t dyn = sizeof(double) * (size_t)kSchurWarps * (size_t)(b.max_wbuf > 0 ? b.max_wbuf : 1);
   dyn = dyn > sizeof(GatherRings) * kSchurWarps ? dyn : sizeof(GatherRings) * kSchurWarps;
-  return dyn;
+  // experiment switch: a floor on the dynamic shared memory caps the CTAs resident per SM (>= 76 KB: 2, >= 114 KB: 1),
+  // i.e. the W / EFAC working set competing for the 126 MB L2
+  static const size_t floor_bytes = []() {
+    const char* e = std::getenv("SWGN_SCHUR_SMEM_FLOOR");
+    return e ? (size_t)std::atol(e) : (size_t)0;
+  }();
+  return dyn > floor_bytes ? dyn : floor_bytes;
 }
 
 void launch_schur_gather(const DeviceBatch& b, int only_window, cudaStream_t s) {

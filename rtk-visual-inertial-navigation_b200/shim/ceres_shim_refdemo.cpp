@@ -1,12 +1,13 @@
 // Drop-in evidence for the ceres:: shim: a sliding-window problem built from the REFERENCE'S OWN factor classes --
-// RVI/factor/{projection_factor, imu_factor + integration_base, gnss_factor, pose_local_parameterization}.cpp, compiled
+// RVI/factor/{projection_factor, imu_factor + integration_base, gnss_factor, marginalization_factor,
+// pose_local_parameterization}.cpp, compiled
 // unmodified where they lie under /root/reference (oracle/build_ref.sh; Eigen is not installed, so against the minimal
 // stand-in of oracle/ref_stubs/) -- registered with the device adapters of shim/reference_adapters.h and solved by
 // ceres::Solve of the shim, i.e. on the GPU.  The costs the device reports are then checked against the costs the
 // reference's own Evaluate() methods give on the CPU at the same states.  TEST INFRASTRUCTURE: it links reference
 // code, is built only where /root/reference exists and lives in oracle/_ref/.
-// One factor class of the window cannot be compiled here (marginalization_factor.cpp needs Eigen's eigen-solver): it is
-// stood in by a class with the same public members and a restated Evaluate() (marginalization_factor.cpp:410-446).
+// The window's prior is the reference's own MarginalizationFactor over a MarginalizationInfo filled through its public
+// members (marginalization_factor.h:40-103), evaluated on the CPU by its own Evaluate() (marginalization_factor.cpp:410-446).
 // With host_factors != 0 the window also gets the reference's INITIALISATION factors -- InitialPoseFactor,
 // InitialBiasFactor, InitialFactor11 (RVI/factor/initial_factor.cpp) and InitPose0Factor (pose0_factor.cpp) -- for
 // which no device adapter exists: the shim evaluates them on the host through their own Evaluate() (generic
@@ -23,6 +24,7 @@
 #include "factor/gnss_factor.h"
 #include "factor/imu_factor.h"
 #include "factor/initial_factor.h"
+#include "factor/marginalization_factor.h"
 #include "factor/pose0_factor.h"
 #include "factor/pose_local_parameterization.h"
 #include "factor/projection_factor.h"
@@ -33,47 +35,6 @@ extern Eigen::Matrix3d Rwgw;
 extern Eigen::Vector3d G;
 
 namespace {
-struct MarginalizationInfo {
-  int m = 0, n = 0;
-  std::vector<int> keep_block_size, keep_block_idx;
-  std::vector<double*> keep_block_data;
-  Eigen::MatrixXd linearized_jacobians;
-  Eigen::VectorXd linearized_residuals;
-};
-class MarginalizationFactor : public ceres::CostFunction {
- public:
-  explicit MarginalizationFactor(MarginalizationInfo* info) : marginalization_info(info) {
-    for (int s : info->keep_block_size) mutable_parameter_block_sizes()->push_back(s);
-    set_num_residuals(info->n);
-  }
-  bool Evaluate(double const* const* p, double* residuals, double**) const override {  // residual part of :410-433
-    const MarginalizationInfo& I = *marginalization_info;
-    std::vector<double> dx(I.n, 0.0);
-    for (size_t i = 0; i < I.keep_block_size.size(); ++i) {
-      const int size = I.keep_block_size[i], idx = I.keep_block_idx[i] - I.m;
-      const double* x = p[i];
-      const double* x0 = I.keep_block_data[i];
-      if (size != 7) {
-        for (int k = 0; k < size; ++k) dx[idx + k] = x[k] - x0[k];
-      } else {
-        for (int k = 0; k < 3; ++k) dx[idx + k] = x[k] - x0[k];
-        const Eigen::Quaterniond dq = Eigen::Quaterniond(x0[6], x0[3], x0[4], x0[5]).inverse() * Eigen::Quaterniond(x[6], x[3], x[4], x[5]);
-        const double sgn = dq.w() >= 0 ? 1.0 : -1.0;
-        dx[idx + 3] = sgn * 2.0 * dq.x();
-        dx[idx + 4] = sgn * 2.0 * dq.y();
-        dx[idx + 5] = sgn * 2.0 * dq.z();
-      }
-    }
-    for (int r = 0; r < I.n; ++r) {
-      double s = I.linearized_residuals(r);
-      for (int c = 0; c < I.n; ++c) s += I.linearized_jacobians(r, c) * dx[c];
-      residuals[r] = s;
-    }
-    return true;
-  }
-  MarginalizationInfo* marginalization_info;
-};
-
 struct Block {
   ceres::CostFunction* f;
   bool cauchy;

@@ -206,11 +206,15 @@ def test_oracle_solve_moves_hidden_frames_towards_truth():
     assert e1[:, 7:10].max() < 0.5 * e0[:, 7:10].max()  # velocity
 
 
-def _oracle_run(which, wid, perturb):
+YAML_DENSITIES = dict(bias_walk_scale=1.0, hidden_bias_istd=0.0)   # yaml/rtk_visual_inertial_config.yaml:24-27 as they are
+
+
+def _oracle_run(which, wid, perturb, overrides=None, initial=False):
     code = ("import sys; sys.path[:0]=[%r,%r]; import numpy as np, swgn, oracle_binding as ob;"
-            "w=swgn.SynthWindow(%d,%d); o=ob.OracleSolver(w.graph_p,w.options()); st,sm=o.minimize();"
-            "print(repr(sm.final_cost)); print(' '.join(repr(float(v)) for v in o.state()))") % (
-                HERE, os.path.join(os.path.dirname(HERE), "rtk-visual-inertial-navigation_b200"), which, wid)
+            "w=swgn.SynthWindow(%d,%d,**%r); o=ob.OracleSolver(w.graph_p,w.options());"
+            + ("c0=o.evaluate()[0]; print(repr(c0)); print('0')" if initial else
+               "st,sm=o.minimize(); print(repr(sm.final_cost)); print(' '.join(repr(float(v)) for v in o.state()))")) % (
+                HERE, os.path.join(os.path.dirname(HERE), "rtk-visual-inertial-navigation_b200"), which, wid, overrides or {})
     env = dict(os.environ)
     if perturb:
         env["ORACLE_CHAIN_PERTURB"] = perturb
@@ -231,6 +235,23 @@ def test_oracle_noise_floor():
     dx = float(np.max(np.abs(x1 - x0) / np.maximum(1.0, np.abs(x0))))
     assert 0 < dc < 0.25 * TOL_CHAIN_COST
     assert dx < 0.25 * TOL_CHAIN_STATE
+
+
+def test_oracle_is_not_reproducible_at_the_yaml_noise_densities():
+    """With the yaml's IMU noise densities the chain's information matrix spans 1e12 .. its own rounding noise and the
+    reference's ABSOLUTE eigenvalue threshold of 1e-8 (gnss_imu_factor.cpp:9,483) lets noise eigenvalues through: a 4e-16
+    relative perturbation of H moves the oracle's INITIAL cost by ~1e-10 relative (amplification > 1e4) and its final cost
+    by more than 1e-4 -- fifty times what the generator's composition-A preset moves by.  This is the reason the full-solve
+    parity tolerances are quoted on the preset, and the reason test_gpu_chain_at_the_yaml_noise_densities compares
+    conditioning-independent quantities instead."""
+    i0, _ = _oracle_run(4, 0, None, YAML_DENSITIES, initial=True)
+    i1, _ = _oracle_run(4, 0, "4e-16", YAML_DENSITIES, initial=True)
+    assert abs(i1 - i0) / i0 > 1e4 * 4e-16
+    c0, x0 = _oracle_run(4, 0, None, YAML_DENSITIES)
+    c1, x1 = _oracle_run(4, 0, "4e-16", YAML_DENSITIES)
+    p0, _ = _oracle_run(4, 0, None)
+    p1, _ = _oracle_run(4, 0, "4e-16")
+    assert abs(c1 - c0) / c0 > 1e-4 > 10 * abs(p1 - p0) / p0
 
 
 @pytest.mark.parametrize("which,wid", [(4, 0), (3, 0)])
@@ -280,6 +301,51 @@ def test_gpu_chain_evaluation_matches_oracle(which, wid):
         assert np.abs(H - Hs).max() < 1e-9 * np.abs(Hs).max()
     assert abs(cost - ocost) < 1e-6 * ocost
     assert np.abs(g - og).max() < 1e-8 * np.abs(og).max()
+    b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,wid", [(4, 0), (4, 1), (3, 0)])
+def test_gpu_chain_at_the_yaml_noise_densities(which, wid):
+    """Composition A with the yaml's noise densities as they are (no preset scaling).  Cost and final states are not
+    reproducible there even by the oracle against itself (test_oracle_is_not_reproducible_at_the_yaml_noise_densities), so
+    the comparison is condition-aware: what the solver consumes -- J'J, J'r of every chain and the whole gradient -- must
+    agree to rounding of the LARGEST entry, the chain information must equal the dense Schur complement of the chain, and the
+    cost may differ by cond(H) x eps only: |cost_gpu - cost_oracle| <= 50 x the oracle's own movement under a 4e-16
+    perturbation of H."""
+    w = swgn.SynthWindow(which, wid, **YAML_DENSITIES)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    b = swgn.Batch([w.graph_p], opt)
+    cost, r, g = b.evaluate(0, o.n_res, o.n_cols)
+    ocost, orr, og, oJ = o.evaluate()
+    J = b.dense_jacobian(0, o.n_res, o.n_cols)
+    rows = chain_rows(w, o.rows())
+    cols = o.columns()
+    worst_cond = 0.0
+    for c, (ro, n) in enumerate(rows):
+        idx, _ = chain_columns(w, c, cols)
+        Jc, oJc = J[ro:ro + n][:, idx], oJ[ro:ro + n][:, idx]
+        H, oH = Jc.T @ Jc, oJc.T @ oJc
+        assert np.abs(H - oH).max() < 1e-9 * np.abs(oH).max()
+        Hs, rs = dense_chain(w, c, w.state0())
+        assert np.abs(H - Hs).max() < 1e-8 * np.abs(Hs).max()
+        gg, ogg = Jc.T @ r[ro:ro + n], oJc.T @ orr[ro:ro + n]
+        assert np.abs(gg - ogg).max() < 1e-7 * max(1.0, np.abs(ogg).max())
+        ev = np.linalg.eigvalsh(Hs)
+        worst_cond = max(worst_cond, ev[-1] / max(ev[ev > 1e-8].min(), 1e-300))
+    assert worst_cond > 1e12            # the point of the test: this is the ill-conditioned regime
+    assert np.abs(g - og).max() < 1e-7 * np.abs(og).max()
+    i0, _ = _oracle_run(which, wid, None, YAML_DENSITIES, initial=True)
+    i1, _ = _oracle_run(which, wid, "4e-16", YAML_DENSITIES, initial=True)
+    floor = max(abs(i1 - i0), 1e-15 * i0)
+    assert abs(cost - ocost) < 50 * floor, (cost, ocost, floor)
+    # one full solve: the device ends at a cost as good as the oracle's (within the oracle's own scatter, measured above at
+    # ~1e-2 relative for cfg3) and never worse than the start
+    sm = b.solve()[0]
+    st, osm = o.minimize()
+    assert sm.termination_type in (0, 1) and sm.final_cost < 1e-3 * sm.initial_cost
+    assert abs(sm.final_cost - osm.final_cost) < 0.1 * osm.final_cost
     b.close()
 
 

@@ -386,3 +386,71 @@ def test_gpu_preprocess_through_the_reference_wire_struct():
         assert [oa[i].rtk_n[0] for i in range(ea.n_obs)] == [ob_[i].rtk_n[0] for i in range(eb.n_obs)]
         assert fa.gnss_dt[:] == fb.gnss_dt[:]
     assert nbytes.value > 64 * 300   # sizeof(mea_t): MAXOBS ObsMea records plus the header
+
+
+def test_oracle_prior_matches_the_reference_marginalization_info():
+    """The reference's own MarginalizationInfo (RVI/factor/marginalization_factor.cpp:58-400, compiled into oracle/_ref) over
+    the reference's own factor objects (RTKCarrierPhaseFactor, RTKPseudorangeFactor, SppDopplerFactor, InitialBlackFactor with
+    the constructor arguments AddGnssResidual passes): addResidualBlockInfo x n, marginalize(true, true),
+    getParameterBlocks().  Its linearised factor carries the same information as the oracle's restatement; the keep blocks
+    come in the reference's unordered_map order and are permuted."""
+    L = ob.ref()
+    if L is None or not hasattr(L, "ref_marginalize"):
+        pytest.skip("oracle/_ref not built")
+    i32, f64, P = C.c_int32, C.c_double, C.POINTER
+    L.ref_marginalize.argtypes = [C.c_int, P(i32), P(i32), P(f64), C.c_int, P(i32), P(i32), P(i32), P(f64), P(i32), P(i32), P(i32), P(i32),
+                                  P(i32), P(f64), P(f64)]
+    O = ob.oracle()
+    O.oracle_gnss_epoch_factors.argtypes = [C.c_void_p, P(G.Epoch), P(G.Frame), C.c_int, P(i32), P(i32), P(f64), P(f64), P(i32)]
+    for variant in ("rtk", "spp"):
+        cfg = _variant(variant)
+        sc = S.Scenario(11, cfg=cfg)
+        T, log = run_oracle(sc, cfg, 5)
+        for rec in log[1:]:
+            e, f_in, out = rec["epoch"], rec["frame_in"], rec["out"]
+            cap = 6 * e.n_obs + 1
+            kind, off, recs = np.zeros(cap, np.int32), np.zeros(3 * cap, np.int32), np.zeros(16 * cap)
+            store, ns = np.zeros(30 + 6 * e.n_obs), i32()
+            nf = O.oracle_gnss_epoch_factors(T.h, C.byref(e), C.byref(f_in), cap, kind.ctypes.data_as(P(i32)), off.ctypes.data_as(P(i32)),
+                                             recs.ctypes.data_as(P(f64)), store.ctypes.data_as(P(f64)), C.byref(ns))
+            assert nf == out.c.n_factors
+            offs = sorted({int(o) for o in off[:3 * nf] if o >= 0})
+            bidx = {o: k for k, o in enumerate(offs)}
+            size = np.array([7 if o == 0 else 9 if o == 7 else 1 for o in offs], np.int32)
+            drop = np.array([1 if 17 <= o < 30 else 0 for o in offs], np.int32)
+            boff = np.array(offs, np.int32)
+            blocks = np.array([bidx[int(o)] if o >= 0 else -1 for o in off[:3 * nf]], np.int32)
+            n, m, nk = i32(), i32(), i32()
+            kb, ki = np.zeros(len(offs), np.int32), np.zeros(len(offs), np.int32)
+            J, r = np.zeros(out.c.n ** 2), np.zeros(out.c.n)
+            rc = L.ref_marginalize(nf, kind.ctypes.data_as(P(i32)), blocks.ctypes.data_as(P(i32)), recs.ctypes.data_as(P(f64)), len(offs),
+                                   size.ctypes.data_as(P(i32)), drop.ctypes.data_as(P(i32)), boff.ctypes.data_as(P(i32)),
+                                   store.ctypes.data_as(P(f64)), C.byref(n), C.byref(m), C.byref(nk), kb.ctypes.data_as(P(i32)),
+                                   ki.ctypes.data_as(P(i32)), J.ctypes.data_as(P(f64)), r.ctypes.data_as(P(f64)))
+            assert rc == 0
+            keep, x0, J0, r0 = out.prior()
+            assert n.value == out.c.n and nk.value == out.c.n_keep and m.value == int(drop.sum())
+            # column permutation: reference keep order -> oracle keep order (both identify blocks by their storage offset)
+            my_off = []
+            for kd, h, idx in keep:
+                if kd == G.KEEP_POSE:
+                    my_off.append(0)
+                elif kd == G.KEEP_SPEED_BIAS:
+                    my_off.append(7)
+                elif kd == G.KEEP_BLACK:
+                    my_off.append(16)
+            amb_offs = [o for o in offs if o >= 30]
+            my_off += amb_offs   # the oracle's ambiguity order is storage order
+            assert len(my_off) == len(keep)
+            tang = lambda o: 6 if o == 0 else 9 if o == 7 else 1
+            ref_cols = {}
+            for k in range(nk.value):
+                o = offs[kb[k]]
+                ref_cols[o] = list(range(ki[k], ki[k] + tang(o)))
+            perm = [c for o in my_off for c in ref_cols[o]]
+            Jr = J.reshape(n.value, n.value)[:, perm]
+            A_ref, A_or = Jr.T @ Jr, J0.T @ J0
+            assert np.abs(A_ref - A_or).max() < 1e-9 * np.abs(A_or).max()
+            b_ref, b_or = Jr.T @ r, J0.T @ r0
+            assert np.abs(b_ref - b_or).max() < 1e-8 * np.abs(b_or).max()
+            assert abs(r @ r - r0 @ r0) < 1e-8 * max(1.0, r0 @ r0)
