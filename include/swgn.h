@@ -461,6 +461,32 @@ swgn_status swgn_ambiguity_fix(int32_t device, int32_t n, const double* A, const
                                int32_t last_fix, int32_t* dd_pairs /* 2 per row: (a, ref) */,
                                double* F /* n_dd x 2 column-major */, swgn_fix_result* result);
 
+/* The prior rebuild that follows FIX_CONTINUE_THRESHOLD consecutive accepted fixes (RVI/swf/swf_lambda.cpp:249-355): the
+   last marginalisation prior, one FixedIntegerFactor(0, istd) tying a dummy scalar to the reference ambiguity of every
+   system / frequency with a fixed double difference, and one FixedIntegerFactor(round(F), istd) per fixed double difference
+   tying the same dummy to its other ambiguity, are linearised at x (the reference evaluates with the phase biases at zero:
+   PhaseBiasSaveAndReset) and the dummies are marginalised out -- on the device: the dummies are elimination group 0 of an
+   export-mode pass and the reduced system goes through the eigen square root, exactly like an epoch's clock terms
+   (include/swgn_gnss.h).  All jobs of one call share two batched passes.  The new prior has the keep blocks and columns of
+   the old one; its linearisation point is x. */
+typedef struct swgn_fixed_integer_job {
+  int32_t n_keep, n;          /* keep blocks / tangent size of last_marg_info                                   */
+  const int32_t* keep_size;   /* global sizes (7 = pose with the reference's parameterization)                  */
+  const int32_t* keep_idx;    /* first tangent column of every keep block                                       */
+  const double* x0;           /* linearisation point of the old prior, global sizes, keep order                 */
+  const double* J0;           /* n x n row-major                                                                */
+  const double* r0;           /* n                                                                              */
+  const double* x;            /* where to linearise: current values of the keep blocks, global sizes            */
+  int32_t n_dd;
+  const int32_t* dd_keep;     /* 2 per double difference: keep-block index of the +1 and of the -1 (reference) ambiguity */
+  const double* F;            /* the fixed integers (the caller rounds, :286)                                   */
+  const int32_t* dd_sysfreq;  /* sys * 2 + f of every double difference, 0..5                                   */
+  double istd;                /* 1 / 0.03 (:312,320)                                                            */
+  double* J0_out;             /* n x n row-major                                                                */
+  double* r0_out;             /* n                                                                              */
+} swgn_fixed_integer_job;
+swgn_status swgn_fixed_integer_prior(int32_t device, int32_t n_jobs, const swgn_fixed_integer_job* jobs);
+
 /* The same decision for EVERY window of a batch after its solve, without a host loop (BASELINE configs[3] over a batch):
    launch 1 computes, per window, A = the tail information of the last Cholesky factor (UpdateSchurHessianOnly) and y = the
    current values of the n_tail scalar blocks at the end of the ordering (the float ambiguities, parameter_head); launch 2

@@ -787,10 +787,63 @@ int gnss_epoch_factors(GnssTracker* T, swgn_epoch* data, swgn_gnss_frame* frame,
   return (int)problem.size();
 }
 
+// The prior rebuild after FIX_CONTINUE_THRESHOLD accepted fixes, RVI/swf/swf_lambda.cpp:249-355: marginalization_info2 =
+// { MarginalizationFactor(last_marg_info) over its keep blocks, FixedIntegerFactor(0, istd) on (tf[sys*2+f], reference
+// ambiguity) once per system / frequency, FixedIntegerFactor(round(F), istd) on (tf[sys*2+f], ambiguity) per fixed double
+// difference }, drop set = the tf dummies, marginalize(false, true), getParameterBlocks().
+int fixed_integer_prior(const swgn_fixed_integer_job* J) {
+  int nx = 0;
+  std::vector<int> sizes(J->keep_size, J->keep_size + J->n_keep), idx(J->keep_idx, J->keep_idx + J->n_keep), xoff;
+  for (int s : sizes) {
+    xoff.push_back(nx);
+    nx += s;
+  }
+  std::vector<double> store(J->x, J->x + nx);  // keep blocks, then double tf[6] = {0} (:247)
+  store.resize(nx + 6, 0.0);
+  double* tf = store.data() + nx;
+  bool tfb[6] = {false};
+  MargInfo marginalization_info2;
+  {
+    ResidualInfo info;
+    info.cost.reset(make_prior_factor(J->n, sizes, idx, J->x0, J->J0, J->r0));
+    for (int k = 0; k < J->n_keep; ++k) info.parameter_blocks.push_back(store.data() + xoff[k]);
+    marginalization_info2.addResidualBlockInfo(info);
+  }
+  auto add_fixed = [&](double* dummy, double* point, double n21) {
+    double rec[SWGN_GNSS_STRIDE] = {0};
+    rec[SWGN_GNSS_MEAS] = n21;
+    rec[SWGN_GNSS_WEIGHT] = J->istd;
+    ResidualInfo info;
+    info.cost.reset(make_gnss_factor(SWGN_GNSS_FIXED_INTEGER, rec));
+    info.parameter_blocks = {dummy, point};
+    info.drop_set = {0};
+    marginalization_info2.addResidualBlockInfo(info);
+  };
+  for (int i = 0; i < J->n_dd; i++) {
+    double* ppoint = store.data() + xoff[J->dd_keep[2 * i]];
+    double* npoint = store.data() + xoff[J->dd_keep[2 * i + 1]];
+    const int sf = J->dd_sysfreq[i];
+    if (tfb[sf] == false) {
+      add_fixed(&tf[sf], npoint, 0.0);
+      tfb[sf] = true;
+    }
+    add_fixed(&tf[sf], ppoint, J->F[i]);
+  }
+  marginalization_info2.marginalize();
+  marginalization_info2.getParameterBlocks();
+  if (marginalization_info2.n != J->n) return -1;
+  for (int r = 0; r < J->n; ++r) {
+    for (int c = 0; c < J->n; ++c) J->J0_out[(size_t)r * J->n + c] = marginalization_info2.linearized_jacobians(r, c);
+    J->r0_out[r] = marginalization_info2.linearized_residuals[r];
+  }
+  return 0;
+}
+
 }  // namespace oracle
 
 using namespace oracle;
 extern "C" {
+int oracle_fixed_integer_prior(const swgn_fixed_integer_job* job) { return fixed_integer_prior(job); }
 int oracle_gnss_epoch_factors(void* t, swgn_epoch* e, swgn_gnss_frame* f, int cap, int32_t* kind, int32_t* store_off, double* records,
                               double* store_out, int32_t* n_store) {
   return gnss_epoch_factors((GnssTracker*)t, e, f, cap, kind, store_off, records, store_out, n_store);

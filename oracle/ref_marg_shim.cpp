@@ -76,4 +76,73 @@ int ref_marginalize(int n_factors, const int32_t* kind, const int32_t* blocks, c
   delete info;  // owns the ResidualBlockInfo objects and their cost functions (marginalization_factor.cpp:46-56)
   return 0;
 }
+
+// RVI/swf/swf_lambda.cpp:249-355 with the reference's own classes: last_marg_info filled through its public members,
+// MarginalizationFactor(last_marg_info), FixedIntegerFactor(0 | F, istd) against the tf dummies, marginalize(false, true).
+// Arguments as swgn_fixed_integer_job (include/swgn.h); the keep blocks come back in the reference's own order
+// (keep_order[k] = index into the job's keep list, keep_col[k] = first column).
+int ref_fixed_integer_prior(int n_keep, int n, const int32_t* keep_size, const int32_t* keep_idx, const double* x0, const double* J0,
+                            const double* r0, const double* x, int n_dd, const int32_t* dd_keep, const double* F,
+                            const int32_t* dd_sysfreq, double istd, int32_t* keep_order, int32_t* keep_col, double* J_out, double* r_out) {
+  std::vector<int> xoff;
+  int nx = 0;
+  for (int k = 0; k < n_keep; ++k) {
+    xoff.push_back(nx);
+    nx += keep_size[k];
+  }
+  std::vector<double> store(x, x + nx), lin(x0, x0 + nx);
+  double tf[6] = {0};
+  bool tfb[6] = {false};
+  MarginalizationInfo* last_marg_info = new MarginalizationInfo();
+  last_marg_info->n = n;
+  last_marg_info->m = 0;
+  for (int k = 0; k < n_keep; ++k) {
+    last_marg_info->keep_block_size.push_back(keep_size[k]);
+    last_marg_info->keep_block_idx.push_back(keep_idx[k]);
+    last_marg_info->keep_block_data.push_back(lin.data() + xoff[k]);
+    last_marg_info->keep_block_addr.push_back(store.data() + xoff[k]);
+  }
+  last_marg_info->linearized_jacobians.resize(n, n);
+  last_marg_info->linearized_residuals = Eigen::VectorXd(n);
+  for (int i = 0; i < n; ++i) {
+    last_marg_info->linearized_residuals(i) = r0[i];
+    for (int j = 0; j < n; ++j) last_marg_info->linearized_jacobians(i, j) = J0[(size_t)i * n + j];
+  }
+  MarginalizationInfo* marginalization_info2 = new MarginalizationInfo();
+  MarginalizationFactor* factormarge = new MarginalizationFactor(last_marg_info);
+  marginalization_info2->addResidualBlockInfo(
+      new ResidualBlockInfo(factormarge, NULL, last_marg_info->keep_block_addr, std::vector<int>{}, std::vector<int>{}));
+  for (int i = 0; i < n_dd; i++) {
+    double* ppoint = store.data() + xoff[dd_keep[2 * i]];
+    double* npoint = store.data() + xoff[dd_keep[2 * i + 1]];
+    const int sf = dd_sysfreq[i];
+    if (tfb[sf] == false) {
+      marginalization_info2->addResidualBlockInfo(new ResidualBlockInfo(new FixedIntegerFactor(0, istd), NULL,
+                                                                        std::vector<double*>{&tf[sf], npoint}, std::vector<int>{0}, std::vector<int>{}));
+      tfb[sf] = true;
+    }
+    marginalization_info2->addResidualBlockInfo(new ResidualBlockInfo(new FixedIntegerFactor(F[i], istd), NULL,
+                                                                      std::vector<double*>{&tf[sf], ppoint}, std::vector<int>{0}, std::vector<int>{}));
+  }
+  marginalization_info2->marginalize(false, true);
+  std::vector<double*> keep = marginalization_info2->getParameterBlocks();
+  if (marginalization_info2->n != n || (int)keep.size() != n_keep) return 2;
+  for (size_t k = 0; k < keep.size(); ++k) {
+    int which = -1;
+    for (int q = 0; q < n_keep; ++q)
+      if (keep[k] == store.data() + xoff[q]) which = q;
+    if (which < 0) return 3;
+    keep_order[k] = which;
+    keep_col[k] = marginalization_info2->keep_block_idx[k] - marginalization_info2->m;
+  }
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) J_out[(size_t)i * n + j] = marginalization_info2->linearized_jacobians(i, j);
+    r_out[i] = marginalization_info2->linearized_residuals(i);
+  }
+  // ~MarginalizationInfo deletes parameter_block_data it allocated and, when m and n are non-zero, its factors; the old
+  // prior's keep_block_data point into `lin` and were never registered in parameter_block_data
+  delete marginalization_info2;
+  delete last_marg_info;
+  return 0;
+}
 }

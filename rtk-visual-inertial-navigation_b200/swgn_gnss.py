@@ -183,3 +183,39 @@ def gate_residuals(rec, device=0):
     out = np.zeros((len(rec), 3))
     _check(_proto().swgn_gnss_gate_residuals(len(rec), _dp(rec), _dp(out), device), "swgn_gnss_gate_residuals")
     return out
+
+
+class FixedIntegerJob(C.Structure):
+    """swgn_fixed_integer_job (include/swgn.h)"""
+    _fields_ = [("n_keep", i32), ("n", i32), ("keep_size", P(i32)), ("keep_idx", P(i32)), ("x0", P(f64)), ("J0", P(f64)), ("r0", P(f64)),
+                ("x", P(f64)), ("n_dd", i32), ("dd_keep", P(i32)), ("F", P(f64)), ("dd_sysfreq", P(i32)), ("istd", f64),
+                ("J0_out", P(f64)), ("r0_out", P(f64))]
+
+
+class FixedIntegerArrays:
+    """numpy storage of one job; .c is the struct pointing into it."""
+
+    def __init__(self, keep_size, keep_idx, x0, J0, r0, x, dd_keep, F, dd_sysfreq, istd=1 / 0.03):
+        self.keep_size = np.ascontiguousarray(keep_size, np.int32)
+        self.keep_idx = np.ascontiguousarray(keep_idx, np.int32)
+        self.x0, self.J0, self.r0 = (np.ascontiguousarray(a, np.float64) for a in (x0, J0, r0))
+        self.x = np.ascontiguousarray(x, np.float64)
+        self.dd_keep = np.ascontiguousarray(dd_keep, np.int32).reshape(-1)
+        self.F = np.ascontiguousarray(F, np.float64)
+        self.dd_sysfreq = np.ascontiguousarray(dd_sysfreq, np.int32)
+        n = len(self.r0)
+        self.J0_out, self.r0_out = np.zeros((n, n)), np.zeros(n)
+        c = FixedIntegerJob()
+        c.n_keep, c.n, c.n_dd, c.istd = len(self.keep_size), n, len(self.F), istd
+        c.keep_size, c.keep_idx, c.dd_keep, c.dd_sysfreq = _ip(self.keep_size), _ip(self.keep_idx), _ip(self.dd_keep), _ip(self.dd_sysfreq)
+        c.x0, c.J0, c.r0, c.x, c.F = _dp(self.x0), _dp(self.J0), _dp(self.r0), _dp(self.x), _dp(self.F)
+        c.J0_out, c.r0_out = _dp(self.J0_out), _dp(self.r0_out)
+        self.c = c
+
+
+def fixed_integer_prior(jobs, device=0):
+    """swgn_fixed_integer_prior for a list of FixedIntegerArrays; results in job.J0_out / job.r0_out."""
+    L = lib()
+    L.swgn_fixed_integer_prior.argtypes = [i32, i32, P(FixedIntegerJob)]
+    arr = (FixedIntegerJob * len(jobs))(*[j.c for j in jobs])
+    _check(L.swgn_fixed_integer_prior(device, len(jobs), arr), "swgn_fixed_integer_prior")

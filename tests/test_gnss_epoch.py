@@ -454,3 +454,96 @@ def test_oracle_prior_matches_the_reference_marginalization_info():
             b_ref, b_or = Jr.T @ r, J0.T @ r0
             assert np.abs(b_ref - b_or).max() < 1e-8 * np.abs(b_or).max()
             assert abs(r @ r - r0 @ r0) < 1e-8 * max(1.0, r0 @ r0)
+
+
+# ---- the prior rebuild after FIX_CONTINUE_THRESHOLD accepted fixes (RVI/swf/swf_lambda.cpp:249-355) --------------------
+def _fixed_integer_job(seed, zero_ambiguities=True):
+    """A job on a real epoch prior: keep = pose, speed-bias, blackvalue, 18 ambiguities; double differences inside every
+    system against its first ambiguity; x = a state near the prior's linearisation point."""
+    cfg = G.default_config()
+    sc = S.Scenario(seed, cfg=cfg)
+    T, log = run_oracle(sc, cfg, 2)
+    out, e, obs = log[1]["out"], log[1]["epoch"], log[1]["obs"]
+    keep, x0, J0, r0 = out.prior()
+    size = [7 if k[0] == G.KEEP_POSE else 9 if k[0] == G.KEEP_SPEED_BIAS else 1 for k in keep]
+    idx = [k[2] for k in keep]
+    rng = np.random.default_rng(seed)
+    x = x0 + 0.01 * rng.normal(size=len(x0))
+    x[3:7] /= np.linalg.norm(x[3:7])
+    amb_keep = [i for i, k in enumerate(keep) if k[0] == G.KEEP_AMB_RTK]
+    sys_of = {k[1]: T.get(G.AMB_RTK, k[1]).sys for k in keep if k[0] == G.KEEP_AMB_RTK}
+    if zero_ambiguities:
+        x[16:] = 0.0   # PhaseBiasSaveAndReset
+    else:
+        x[16:] = rng.normal(size=len(x) - 16) * 3
+    dd, F, sf = [], [], []
+    for s in range(3):
+        members = [i for i in amb_keep if sys_of[keep[i][1]] == s]
+        for a in members[1:]:
+            dd.append((a, members[0]))
+            F.append(float(rng.integers(-40, 40)))
+            sf.append(2 * s)
+    return G.FixedIntegerArrays(size, idx, x0, J0, r0, x, dd, F, sf)
+
+
+def _oracle_fixed_integer(job):
+    O = ob.oracle()
+    O.oracle_fixed_integer_prior.argtypes = [C.POINTER(G.FixedIntegerJob)]
+    assert O.oracle_fixed_integer_prior(C.byref(job.c)) == 0
+    return job.J0_out.copy(), job.r0_out.copy()
+
+
+def test_fixed_integer_prior_oracle_matches_the_reference_classes():
+    """Oracle restatement of swf_lambda.cpp:249-355 against the reference's own MarginalizationInfo / MarginalizationFactor /
+    FixedIntegerFactor executed here (oracle/ref_marg_shim.cpp), and against the closed form: the new information is the old
+    one plus the double-difference constraints w^2 (e_p - e_n)(e_p - e_n)' with the dummies eliminated."""
+    L = ob.ref()
+    if L is None or not hasattr(L, "ref_fixed_integer_prior"):
+        pytest.skip("oracle/_ref not built")
+    i32, f64, P = C.c_int32, C.c_double, C.POINTER
+    L.ref_fixed_integer_prior.argtypes = [C.c_int, C.c_int, P(i32), P(i32), P(f64), P(f64), P(f64), P(f64), C.c_int, P(i32), P(f64), P(i32),
+                                          f64, P(i32), P(i32), P(f64), P(f64)]
+    for seed, zero in ((21, True), (22, False)):
+        job = _fixed_integer_job(seed, zero)
+        Jo, ro = _oracle_fixed_integer(job)
+        n, nk = job.c.n, job.c.n_keep
+        order, col = np.zeros(nk, np.int32), np.zeros(nk, np.int32)
+        Jr, rr = np.zeros((n, n)), np.zeros(n)
+        rc = L.ref_fixed_integer_prior(nk, n, job.c.keep_size, job.c.keep_idx, job.c.x0, job.c.J0, job.c.r0, job.c.x, job.c.n_dd, job.c.dd_keep,
+                                       job.c.F, job.c.dd_sysfreq, job.c.istd, order.ctypes.data_as(P(i32)), col.ctypes.data_as(P(i32)),
+                                       Jr.ctypes.data_as(P(f64)), rr.ctypes.data_as(P(f64)))
+        assert rc == 0
+        tang = [6 if s == 7 else int(s) for s in job.keep_size]
+        ref_cols = {int(order[k]): list(range(col[k], col[k] + tang[order[k]])) for k in range(nk)}
+        perm = [c for q in range(nk) for c in ref_cols[q]]
+        Jr = Jr[:, perm]
+        Ao, Ar = Jo.T @ Jo, Jr.T @ Jr
+        assert np.abs(Ao - Ar).max() < 1e-9 * np.abs(Ao).max()
+        assert np.abs(Jo.T @ ro - Jr.T @ rr).max() < 1e-8 * max(1.0, np.abs(Jo.T @ ro).max())
+        # closed form of the information: per system the dummy couples its members like a star; eliminating it leaves
+        # w^2 (I - 11'/k) on the k members (the reference ambiguity included) in the shifted variables
+        A_old = job.J0.reshape(n, n).T @ job.J0.reshape(n, n)
+        w2 = job.c.istd ** 2
+        add = np.zeros((n, n))
+        for s in sorted(set(job.dd_sysfreq)):
+            pairs = [tuple(job.dd_keep[2 * d:2 * d + 2]) for d in range(job.c.n_dd) if job.dd_sysfreq[d] == s]
+            members = [job.keep_idx[pairs[0][1]]] + [job.keep_idx[p] for p, _ in pairs]
+            k = len(members)
+            add[np.ix_(members, members)] += w2 * (np.eye(k) - np.ones((k, k)) / k)
+        assert np.abs(Ao - (A_old + add)).max() < 1e-8 * np.abs(Ao).max()
+
+
+@pytest.mark.gpu
+def test_gpu_fixed_integer_prior_matches_the_oracle():
+    jobs = [_fixed_integer_job(31, True), _fixed_integer_job(32, False), _fixed_integer_job(33, True)]
+    want = [_oracle_fixed_integer(j) for j in jobs]
+    for j in jobs:
+        j.J0_out[:] = 0
+        j.r0_out[:] = 0
+    G.fixed_integer_prior(jobs)
+    for j, (Jo, ro) in zip(jobs, want):
+        Ag, Ao = j.J0_out.T @ j.J0_out, Jo.T @ Jo
+        assert np.abs(Ag - Ao).max() < 1e-9 * np.abs(Ao).max()
+        bg, bo = j.J0_out.T @ j.r0_out, Jo.T @ ro
+        assert np.abs(bg - bo).max() < 1e-8 * max(1.0, np.abs(bo).max())
+        assert abs(j.r0_out @ j.r0_out - ro @ ro) < 1e-8 * max(1.0, ro @ ro)
