@@ -461,6 +461,25 @@ swgn_status swgn_ambiguity_fix(int32_t device, int32_t n, const double* A, const
                                int32_t last_fix, int32_t* dd_pairs /* 2 per row: (a, ref) */,
                                double* F /* n_dd x 2 column-major */, swgn_fix_result* result);
 
+/* MarginalizationInfo::marginalize (RVI/factor/marginalization_factor.cpp:260-377) + getParameterBlocks for ARBITRARY drop
+   sets -- what MargFrames runs for MargImagSecondNew / MargRoverOld (RVI/swf/swf.cpp:329-341 -> swf_core.cpp:372-390): the
+   factors of graph w are linearised at its state, the blocks with drop[w][b] != 0 are marginalised with the reference's
+   eigen pseudo-inverse (eigenvalues <= 1e-8 dropped) and the remaining information becomes the prior r = r0 + J0 (x [-] x0)
+   over the keep blocks (block-index order; x0 = the graph's state).  On the device this is one export-mode pass per call for
+   all graphs -- drop blocks ordered before the keep blocks in the reduced system, which swgn_batch_get_marginal_priors then
+   reduces and square-roots.  Restrictions: block_group is ignored, no constant blocks, order / is_use / chains / host
+   factors must be absent, every block must be touched by a factor, at least one keep block. */
+typedef struct swgn_marginalize_output {
+  int32_t cap_keep, cap_n;   /* capacities of the caller's buffers                                  */
+  int32_t n_keep, n, m;      /* keep blocks, their tangent size, tangent size of the dropped blocks */
+  int32_t* keep_block;       /* graph block index of every keep block                               */
+  int32_t* keep_idx;         /* its first column in J0                                              */
+  double* J0;                /* n x n row-major                                                     */
+  double* r0;                /* n                                                                   */
+} swgn_marginalize_output;
+swgn_status swgn_marginalize(int32_t device, int32_t n_graphs, const swgn_graph* const* graphs, const uint8_t* const* drop,
+                             swgn_marginalize_output* outputs);
+
 /* The prior rebuild that follows FIX_CONTINUE_THRESHOLD consecutive accepted fixes (RVI/swf/swf_lambda.cpp:249-355): the
    last marginalisation prior, one FixedIntegerFactor(0, istd) tying a dummy scalar to the reference ambiguity of every
    system / frequency with a fixed double difference, and one FixedIntegerFactor(round(F), istd) per fixed double difference

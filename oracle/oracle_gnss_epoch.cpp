@@ -132,7 +132,8 @@ struct ResidualInfo {
   std::vector<int> drop_set;
   std::vector<double> residuals;
   std::vector<Mat> jacobians;
-  void Evaluate() {  // :7-43, loss_function == NULL on this path
+  double cauchy_a = 0.0;  // > 0: loss_function = CauchyLoss(a)
+  void Evaluate() {  // :7-43
     residuals.assign(cost->num_residuals, 0.0);
     std::vector<std::vector<double>> raw(cost->block_sizes.size());
     std::vector<double*> ptr(cost->block_sizes.size());
@@ -146,6 +147,31 @@ struct ResidualInfo {
       Mat J(cost->num_residuals, cost->block_sizes[i]);
       J.a = raw[i];
       jacobians.push_back(J);
+    }
+    if (cauchy_a > 0.0) {  // :21-41
+      double sq_norm = 0.0, rho[3];
+      for (double v : residuals) sq_norm += v * v;
+      cauchy_loss(cauchy_a, sq_norm, rho);
+      const double sqrt_rho1_ = std::sqrt(rho[1]);
+      double residual_scaling_, alpha_sq_norm_;
+      if ((sq_norm == 0.0) || (rho[2] <= 0.0)) {
+        residual_scaling_ = sqrt_rho1_;
+        alpha_sq_norm_ = 0.0;
+      } else {
+        const double D = 1.0 + 2.0 * sq_norm * rho[2] / rho[1];
+        const double alpha = 1.0 - std::sqrt(D);
+        residual_scaling_ = sqrt_rho1_ / (1 - alpha);
+        alpha_sq_norm_ = alpha / sq_norm;
+      }
+      const int nr = cost->num_residuals;
+      for (Mat& J : jacobians) {  // J = sqrt_rho1 (J - alpha_sq_norm r (r' J))
+        for (int c = 0; c < J.c; ++c) {
+          double rtJ = 0.0;
+          for (int r = 0; r < nr; ++r) rtJ += residuals[r] * J(r, c);
+          for (int r = 0; r < nr; ++r) J(r, c) = sqrt_rho1_ * (J(r, c) - alpha_sq_norm_ * residuals[r] * rtJ);
+        }
+      }
+      for (double& v : residuals) v *= residual_scaling_;
     }
   }
 };
@@ -839,10 +865,53 @@ int fixed_integer_prior(const swgn_fixed_integer_job* J) {
   return 0;
 }
 
+// MarginalizationInfo over the factors of a whole swgn_graph with an arbitrary drop set (what MargFrames builds through
+// AddAllResidual(MargeIncludeMode, ...), swf.cpp:329-341, swf_core.cpp:372-390): addResidualBlockInfo per factor,
+// marginalize(false, true), getParameterBlocks.  Keep blocks come out in block-index order (= address order of the state).
+int marginalize_graph(const swgn_graph* g, const uint8_t* drop, int cap_keep, int cap_n, int32_t* n_keep, int32_t* n_out, int32_t* m_out,
+                      int32_t* keep_block, int32_t* keep_idx, double* J0, double* r0) {
+  swgn_options opt;
+  std::memset(&opt, 0, sizeof(opt));
+  Solver s;
+  if (!s.Build(g, &opt)) return -2;
+  MargInfo info;
+  for (auto& rb : s.residual_blocks) {
+    ResidualInfo ri;
+    ri.cost = std::shared_ptr<CostFunction>(rb->cost.get(), [](CostFunction*) {});  // owned by the Solver
+    ri.cauchy_a = rb->cauchy_a;
+    for (size_t k = 0; k < rb->blocks.size(); ++k) {
+      ri.parameter_blocks.push_back(rb->blocks[k]->user_state);
+      if (drop[rb->blocks[k]->graph_index]) ri.drop_set.push_back((int)k);
+    }
+    info.addResidualBlockInfo(ri);
+  }
+  info.marginalize();
+  info.getParameterBlocks();
+  *n_out = info.n;
+  *m_out = info.m;
+  *n_keep = (int)info.keep_block_addr.size();
+  if (*n_keep > cap_keep || info.n > cap_n) return -1;
+  for (int k = 0; k < *n_keep; ++k) {
+    keep_block[k] = -1;
+    for (auto& b : s.blocks)
+      if (b.user_state == info.keep_block_addr[k]) keep_block[k] = b.graph_index;
+    keep_idx[k] = info.keep_block_idx[k] - info.m;
+  }
+  for (int r = 0; r < info.n; ++r) {
+    for (int c = 0; c < info.n; ++c) J0[(size_t)r * info.n + c] = info.linearized_jacobians(r, c);
+    r0[r] = info.linearized_residuals[r];
+  }
+  return 0;
+}
+
 }  // namespace oracle
 
 using namespace oracle;
 extern "C" {
+int oracle_marginalize_graph(const swgn_graph* g, const uint8_t* drop, int cap_keep, int cap_n, int32_t* n_keep, int32_t* n_out,
+                             int32_t* m_out, int32_t* keep_block, int32_t* keep_idx, double* J0, double* r0) {
+  return marginalize_graph(g, drop, cap_keep, cap_n, n_keep, n_out, m_out, keep_block, keep_idx, J0, r0);
+}
 int oracle_fixed_integer_prior(const swgn_fixed_integer_job* job) { return fixed_integer_prior(job); }
 int oracle_gnss_epoch_factors(void* t, swgn_epoch* e, swgn_gnss_frame* f, int cap, int32_t* kind, int32_t* store_off, double* records,
                               double* store_out, int32_t* n_store) {

@@ -563,3 +563,36 @@ def ambiguity_fix(A, y, epoch_begin, obs_amb, obs_sysfreq, last_fix=0, device=0)
                                     last_fix, _ip(pairs), _dp(F), C.byref(res)), "swgn_ambiguity_fix")
     nb = res.n_dd
     return pairs[:2 * nb].reshape(nb, 2), F[:2 * nb].reshape(2, nb).T.copy(), res
+
+
+class MarginalizeOutput(C.Structure):
+    _fields_ = [("cap_keep", i32), ("cap_n", i32), ("n_keep", i32), ("n", i32), ("m", i32),
+                ("keep_block", P(i32)), ("keep_idx", P(i32)), ("J0", P(f64)), ("r0", P(f64))]
+
+
+def marginalize(graph_ps, drops, device=0):
+    """swgn_marginalize: MarginalizationInfo::marginalize for arbitrary drop sets.  graph_ps: pointers to Graph; drops: one uint8
+    array per graph.  Returns [(keep_block, keep_idx, J0, r0, m)]."""
+    n = len(graph_ps)
+    L = lib()
+    L.swgn_marginalize.argtypes = [i32, i32, P(P(Graph)), P(P(C.c_uint8)), P(MarginalizeOutput)]
+    outs = (MarginalizeOutput * n)()
+    keep = []
+    dr = []
+    for w in range(n):
+        g = graph_ps[w].contents
+        cap_n = sum(6 if g.block_manifold[b] == 1 else g.block_size[b] for b in range(g.n_blocks))
+        kb, ki, J, r = np.zeros(g.n_blocks, np.int32), np.zeros(g.n_blocks, np.int32), np.zeros(cap_n * cap_n), np.zeros(cap_n)
+        keep.append((kb, ki, J, r))
+        outs[w].cap_keep, outs[w].cap_n = g.n_blocks, cap_n
+        outs[w].keep_block, outs[w].keep_idx, outs[w].J0, outs[w].r0 = _ip(kb), _ip(ki), _dp(J), _dp(r)
+        dr.append(np.ascontiguousarray(drops[w], np.uint8))
+    garr = (P(Graph) * n)(*graph_ps)
+    darr = (P(C.c_uint8) * n)(*[d.ctypes.data_as(P(C.c_uint8)) for d in dr])
+    _check(L.swgn_marginalize(device, n, garr, darr, outs), "swgn_marginalize")
+    res = []
+    for w in range(n):
+        kb, ki, J, r = keep[w]
+        nn, nk = outs[w].n, outs[w].n_keep
+        res.append((kb[:nk].copy(), ki[:nk].copy(), J[:nn * nn].reshape(nn, nn).copy(), r[:nn].copy(), outs[w].m))
+    return res

@@ -737,3 +737,52 @@ def test_host_evaluated_cost_functions_reproduce_the_device_factors():
     assert (sm.num_iterations, sm.num_successful_steps, sm.termination_type) == (sm0.num_iterations, sm0.num_successful_steps, sm0.termination_type)
     assert abs(sm.final_cost - sm0.final_cost) <= 1e-8 * sm0.final_cost
     assert state_err(x, x0) < 1e-7
+
+
+def _plain_copy(w):
+    """The window's graph with every block variable and no program order: the form swgn_marginalize takes (the reference's
+    MarginalizationInfo knows neither constant blocks nor an ordering)."""
+    g = swgn.Graph()
+    C.memmove(C.byref(g), w.graph_p, C.sizeof(swgn.Graph))
+    free = np.zeros(g.n_blocks, np.int32)
+    g.block_const = free.ctypes.data_as(C.POINTER(C.c_int32))
+    g.n_order = 0
+    g.order = None
+    g.is_use = None
+    return g, free
+
+
+@pytest.mark.parametrize("which,overrides", [(1, {}), (2, dict(n_keyframes=6, n_landmarks=40, n_gnss_epochs=3, n_sats=8))])
+def test_marginalize_with_an_arbitrary_drop_set_matches_the_oracle(which, overrides):
+    """swgn_marginalize = MarginalizationInfo::marginalize + getParameterBlocks (marginalization_factor.cpp:260-400) as MargFrames
+    uses it: drop the oldest frame's pose and speed-bias and the first landmarks, keep everything else.  The oracle side is
+    the restated MarginalizationInfo that tests/test_gnss_epoch.py pins on the reference's own class."""
+    ws = [swgn.SynthWindow(which, wid, **overrides) for wid in (0, 1)]
+    copies = [_plain_copy(w) for w in ws]
+    gps, drops = [], []
+    for w, (g, _) in zip(ws, copies):
+        drop = np.zeros(g.n_blocks, np.uint8)
+        sizes = [g.block_size[b] for b in range(g.n_blocks)]
+        drop[sizes.index(7)] = 1                      # first pose
+        drop[sizes.index(9)] = 1                      # first speed-bias
+        lms = [b for b in range(g.n_blocks) if sizes[b] == 3][:8]
+        drop[lms] = 1
+        gps.append(C.pointer(g))
+        drops.append(drop)
+    got = swgn.marginalize(gps, drops)
+    O = ob.oracle()
+    i32, f64, P = C.c_int32, C.c_double, C.POINTER
+    O.oracle_marginalize_graph.argtypes = [P(swgn.Graph), P(C.c_uint8), C.c_int, C.c_int, P(i32), P(i32), P(i32), P(i32), P(i32), P(f64), P(f64)]
+    for (kb, ki, J0, r0, m), gp, drop in zip(got, gps, drops):
+        n = J0.shape[0]
+        nk, no, mo = i32(), i32(), i32()
+        okb, oki, oJ, orr = np.zeros(len(drop), np.int32), np.zeros(len(drop), np.int32), np.zeros(n * n), np.zeros(n)
+        rc = O.oracle_marginalize_graph(gp, drop.ctypes.data_as(P(C.c_uint8)), len(drop), n, C.byref(nk), C.byref(no), C.byref(mo),
+                                        okb.ctypes.data_as(P(i32)), oki.ctypes.data_as(P(i32)), oJ.ctypes.data_as(P(f64)), orr.ctypes.data_as(P(f64)))
+        assert rc == 0 and no.value == n and mo.value == m and nk.value == len(kb)
+        assert np.array_equal(okb[:nk.value], kb) and np.array_equal(oki[:nk.value], ki)
+        oJ = oJ.reshape(n, n)
+        Ag, Ao = J0.T @ J0, oJ.T @ oJ
+        assert np.abs(Ag - Ao).max() < 1e-9 * np.abs(Ao).max()
+        bg, bo = J0.T @ r0, oJ.T @ orr
+        assert np.abs(bg - bo).max() < 1e-7 * max(1.0, np.abs(bo).max())
