@@ -18,6 +18,9 @@
 namespace swgn {
 namespace {
 
+#ifndef SWGN_EVAL_CTAS
+#define SWGN_EVAL_CTAS 2  // CTAs per SM the register budget is tuned for (2: 128 registers; 3: 80 registers + 512 B of spills measured 3 % slower)
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kImuScratch = 15 * 30 + 16;
@@ -270,7 +273,7 @@ __device__ void eval_imu(const Win& v, const Globals& gl, int i, const double* x
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) k_eval(DeviceBatch b, int mode, int only_window) {
+__global__ void __launch_bounds__(kThreads, SWGN_EVAL_CTAS) k_eval(DeviceBatch b, int mode, int only_window) {
   __shared__ WinDesc sd;
   __shared__ double red[33];
   __shared__ double imu_scratch[kWarps][kImuScratch];
