@@ -103,6 +103,58 @@ def cpu_leg(windows, opt, threads):
     return it.value, t
 
 
+def gnss_epoch_leg(receivers=2048, n_epochs=4):
+    """SURVEY 8f rank 4 next to the headline: swgn_gnss_preprocess for `receivers` receivers per call (20 satellites each,
+    host buffers in and out), and the CPU restatement of GnssPreprocess on one thread on a bounded sample."""
+    import ctypes as C
+    import gnss_scenario as S
+    import swgn_gnss as G
+    cfg = G.default_config()
+    n_sc = 16
+    scs = [S.Scenario(100 + s, cfg=cfg) for s in range(n_sc)]
+    trackers = [G.Tracker(cfg) for _ in range(receivers)]
+    outputs = [G.OutputBuffers(cap_keep=64, cap_n=80) for _ in range(receivers)]
+    dt = [np.zeros(G.NCLK) for _ in range(n_sc)]
+    times = []
+    for k in range(n_epochs):
+        base = [sc.epoch(k) for sc in scs]
+        epochs, frames, keep = [], [], []
+        for r in range(receivers):
+            e, obs, f = base[r % n_sc]
+            e2, o2 = S.copy_epoch(e, obs)
+            f2 = S.copy_frame(f)
+            for c in range(G.NCLK):
+                f2.gnss_dt[c] = dt[r % n_sc][c]
+            epochs.append(e2), frames.append(f2), keep.append(o2)
+        t0 = time.perf_counter()
+        G.preprocess(trackers, epochs, frames, outputs)
+        times.append(time.perf_counter() - t0)
+        for s in range(n_sc):
+            dt[s] = np.array(frames[s].gnss_dt[:])
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob  # TEST INFRASTRUCTURE, here as the timed CPU baseline only
+    n_cpu = 32
+    To = [ob.OracleGnssTracker(cfg) for _ in range(n_cpu)]
+    scs = [S.Scenario(100 + s, cfg=cfg) for s in range(n_sc)]
+    cpu = []
+    for k in range(n_epochs):
+        base = [sc.epoch(k) for sc in scs]
+        t = 0.0
+        for r in range(n_cpu):
+            e, obs, f = base[r % n_sc]
+            e2, o2 = S.copy_epoch(e, obs)
+            f2 = S.copy_frame(f)
+            t0 = time.perf_counter()
+            To[r].preprocess(e2, f2, outputs[r])
+            t += time.perf_counter() - t0
+        cpu.append(t / n_cpu)
+    best = min(times[1:])
+    return {"receivers_per_call": receivers, "satellites": 20, "ms_per_call": 1e3 * best, "epochs_per_s": receivers / best,
+            "cpu_port_epochs_per_s_one_thread": 1.0 / min(cpu),
+            "note": "GnssPreprocess (swf_gnss.cpp:265-587) for one epoch of every receiver per call through the C ABI, host buffers in "
+                    "and out, ctypes marshalling included; the device solves are ~3 ms of a call, the rest is host planning / packing"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -327,6 +379,9 @@ def run_swgn(args, rank, local_rank, world):
                          "(CPU restatement of the modified-Ceres path)" % (ncpu, cores),
                "variants": {"one_window_at_a_time_1_thread": c1i / c1t, "four_windows_on_4_threads": c4i / c4t,
                             "one_window_per_core_%d_threads" % cores: ci / ct}}
+    gnss = None
+    if world == 1 and not args.no_cpu_baseline:
+        gnss = gnss_epoch_leg()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -348,6 +403,7 @@ def run_swgn(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "cfg4_ambiguity_fix": cfg4,
+        "gnss_epoch_preprocess": gnss,
         "strong_scaling": None if strong is None else {
             "value": strong[1] / (strong[0] * 1e-3), "unit": UNIT, "windows_total": int(strong[2]) * world, "windows_per_gpu": int(strong[2]),
             "ms_per_step": strong[0] / args.steps, "note": "the same `--windows` windows in total, sharded over the ranks (device-resident, max over ranks)"},

@@ -1321,9 +1321,10 @@ swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail,
   int64_t* doff = nullptr;
   int32_t* dn = nullptr;
   std::vector<double> host;
-  cudaError_t e = cudaMalloc(&dbuf, sizeof(double) * total);
-  if (e == cudaSuccess) e = cudaMalloc(&doff, sizeof(int64_t) * off.size());
-  if (e == cudaSuccess) e = cudaMalloc(&dn, sizeof(int32_t) * b->n);
+  // stream-ordered allocations: no device-wide synchronisation per call
+  cudaError_t e = cudaMallocAsync((void**)&dbuf, sizeof(double) * total, b->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&doff, sizeof(int64_t) * off.size(), b->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&dn, sizeof(int32_t) * b->n, b->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(doff, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, b->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n_tail, sizeof(int32_t) * b->n, cudaMemcpyHostToDevice, b->stream);
   if (e == cudaSuccess) e = launch_marginal_priors(b->db, max_m, max_n, dn, doff, dbuf, b->stream);
@@ -1331,10 +1332,10 @@ swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail,
     host.resize((size_t)n_out);
     e = cudaMemcpyAsync(host.data(), dbuf, sizeof(double) * n_out, cudaMemcpyDeviceToHost, b->stream);
   }
+  if (dbuf) cudaFreeAsync(dbuf, b->stream);
+  if (doff) cudaFreeAsync(doff, b->stream);
+  if (dn) cudaFreeAsync(dn, b->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
-  cudaFree(dbuf);
-  cudaFree(doff);
-  cudaFree(dn);
   CU(e);
   for (int w = 0; w < b->n; ++w) {
     const int n = n_tail[w];

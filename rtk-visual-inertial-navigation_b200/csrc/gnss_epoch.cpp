@@ -552,20 +552,26 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
     double *d_rec = nullptr, *d_out = nullptr;
     int32_t* d_flags = nullptr;
     if (n_obs_all > 0) {
-      cudaError_t e = cudaMalloc(&d_rec, sizeof(double) * 16 * n_obs_all);
-      if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * 3 * n_obs_all);
-      if (e == cudaSuccess) e = cudaMalloc(&d_flags, sizeof(int32_t) * n_obs_all);
-      if (e == cudaSuccess) e = cudaMemcpy(d_rec, rec.data(), sizeof(double) * 16 * n_obs_all, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(d_flags, flags.data(), sizeof(int32_t) * n_obs_all, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = swgn::launch_gate_residuals((int)n_obs_all, d_rec, d_flags, cfg.azelmin, d_out, 0);
-      if (e == cudaSuccess) e = cudaMemcpy(gate.data(), d_out, sizeof(double) * 3 * n_obs_all, cudaMemcpyDeviceToHost);
-      cudaFree(d_rec);
-      cudaFree(d_out);
-      cudaFree(d_flags);
+      // stream-ordered allocations: no device-wide synchronisation, the pool keeps the blocks for the next call
+      cudaStream_t s = cudaStreamPerThread;
+      cudaError_t e = cudaMallocAsync((void**)&d_rec, sizeof(double) * 16 * n_obs_all, s);
+      if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_out, sizeof(double) * 3 * n_obs_all, s);
+      if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_flags, sizeof(int32_t) * n_obs_all, s);
+      lap("  gate: alloc");
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_rec, rec.data(), sizeof(double) * 16 * n_obs_all, cudaMemcpyHostToDevice, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_flags, flags.data(), sizeof(int32_t) * n_obs_all, cudaMemcpyHostToDevice, s);
+      lap("  gate: h2d");
+      if (e == cudaSuccess) e = swgn::launch_gate_residuals((int)n_obs_all, d_rec, d_flags, cfg.azelmin, d_out, s);
+      if (dbg) cudaStreamSynchronize(s);
+      lap("  gate: kernel");
+      if (e == cudaSuccess) e = cudaMemcpyAsync(gate.data(), d_out, sizeof(double) * 3 * n_obs_all, cudaMemcpyDeviceToHost, s);
+      if (d_rec) cudaFreeAsync(d_rec, s);
+      if (d_out) cudaFreeAsync(d_out, s);
+      if (d_flags) cudaFreeAsync(d_flags, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) return set_error(SWGN_ERR_CUDA, std::string("gating residuals: ") + cudaGetErrorString(e));
     }
   }
-
   lap("gate residuals (device)");
   // ---- phase B: medians, slip conditions, new ambiguities, counters (swf_gnss.cpp:346-500) ---------------------
   parallel_for(n, [&](int i) {
