@@ -18,6 +18,7 @@
 //                                                           written in HBM/L2 exactly once per panel)
 // then the backward solve U z = w in 32-row blocks.  The factor stays in W_S: it is the
 // `lhs_out2 = llt.matrixL()` export (schur_complement_solver.cc:253-258) transposed.
+#include <cstdlib>
 #include <mutex>
 
 #include "dev_common.cuh"
@@ -26,6 +27,9 @@
 namespace swgn {
 namespace {
 
+#ifndef SWGN_CHOL_CTAS
+#define SWGN_CHOL_CTAS 2  // 3 (80 registers, spills) with 16-row panels measured 23 % slower, with 32-row panels 11 % slower
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
@@ -62,7 +66,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 2) k_chol(DeviceBatch b, int only_window, int NB, int pw) {
+__global__ void __launch_bounds__(kThreads, SWGN_CHOL_CTAS) k_chol(DeviceBatch b, int only_window, int NB, int pw) {
   __shared__ WinDesc sd;
   __shared__ int s_fail;
   __shared__ double s_rdiag[2][8];
@@ -468,7 +472,14 @@ __global__ void k_tail_information_batch(DeviceBatch b, int n_tail, double* A_al
   for (int k = threadIdx.x; k < n_tail; k += blockDim.x) y_all[(size_t)w * n_tail + k] = x[col_state[d.n_cols - n_tail + k]];
 }
 
-int chol_block(const DeviceBatch& b) { return b.max_nf <= 760 ? 32 : 16; }
+int chol_block(const DeviceBatch& b) {
+  static const int forced = []() {  // experiment switch
+    const char* e = std::getenv("SWGN_CHOL_NB");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (forced == 16 || forced == 32) return b.max_nf <= 760 ? forced : 16;
+  return b.max_nf <= 760 ? 32 : 16;
+}
 int chol_pitch(const DeviceBatch& b) {
   const int NB = chol_block(b);
   const int need = (b.max_nf + 1 + (NB == 16 ? 16 : 0) + 31) & ~31;
