@@ -447,3 +447,37 @@ def test_gpu_chain_update_inputs_resets_history_and_batches_are_independent():
         assert s1.final_cost == sm1[i].final_cost
         single.close()
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,wid", [(4, 0), (4, 2)])
+def test_gpu_chain_history_survives_between_solves_like_the_reference(which, wid):
+    """IMUGNSSBase::history_flag stays true from one ceres::Solve to the next until Init() (gnss_imu_factor.cpp:33-36,699-713):
+    the first Jacobian evaluation of the second Solve back-substitutes the hidden states with the blocks saved by the last
+    elimination of the first Solve before it re-eliminates.  A batch keeps that history between swgn_batch_solve calls
+    (swgn_batch_update_inputs is the Init()); two solves of 3 iterations each are compared with two Minimize calls on one
+    oracle Solver, whose chain object persists the same way -- and differ from one solve that starts afresh."""
+    w = swgn.SynthWindow(which, wid)
+    opt = w.options()
+    opt.max_num_iterations = 3
+    b = swgn.Batch([w.graph_p], opt)
+    o = ob.OracleSolver(w.graph_p, opt)
+    for leg in range(2):
+        sm = b.solve()[0]
+        st, osm = o.minimize()
+        assert st == 0 and sm.termination_type == osm.termination_type
+        assert abs(sm.initial_cost - osm.initial_cost) < 1e-5 * osm.initial_cost
+        assert abs(sm.final_cost - osm.final_cost) < TOL_CHAIN_COST * osm.final_cost
+        x, xo = b.get_state(0, w.n_state), o.state()
+        assert float(np.max(np.abs(x - xo) / np.maximum(1.0, np.abs(xo)))) < TOL_CHAIN_STATE
+        hf, ho = b.chain_frames(0), o.chain_frames()
+        assert float(np.max(np.abs(hf - ho) / np.maximum(1.0, np.abs(ho)))) < TOL_CHAIN_STATE
+    cost_with_history = sm.initial_cost
+    # the same second leg started afresh (what a create-solve-destroy host gets): the hidden states restart from the
+    # uploaded ones, so its first evaluation sees a different cost
+    b2 = swgn.Batch([w.graph_p], opt)
+    b2.set_state(0, x * 0 + b.get_state(0, w.n_state))
+    sm_fresh = b2.solve()[0]
+    assert abs(sm_fresh.initial_cost - cost_with_history) > 1e-9 * cost_with_history
+    b.close()
+    b2.close()
