@@ -96,6 +96,36 @@ def test_create_fails_loudly_without_a_device():
         swgn.Batch([w.graph_p], w.options())
 
 
+@pytest.mark.skipif(swgn.lib().swgn_device_count() > 0, reason="a CUDA device is present")
+def test_epoch_and_marginalisation_entry_points_fail_loudly_without_a_device():
+    """The host-side phases of include/swgn_gnss.h run anywhere; everything numerical needs the device and says so."""
+    import gnss_scenario as S
+    import swgn_gnss as G
+    cfg = G.default_config()
+    sc = S.Scenario(0, cfg=cfg)
+    e, obs, f = sc.epoch(0)
+    T = G.Tracker(cfg)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.preprocess([T], [e], [f])
+    assert T.count(G.AMB_RTK) == 0          # nothing was decided without the device residuals
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.gate_residuals(np.zeros((2, 16)))
+    w = swgn.SynthWindow(1, 0)
+    g = swgn.Graph()
+    C.memmove(C.byref(g), w.graph_p, C.sizeof(swgn.Graph))
+    free = np.zeros(g.n_blocks, np.int32)
+    g.block_const = free.ctypes.data_as(C.POINTER(C.c_int32))
+    g.n_order, g.order, g.is_use = 0, None, None
+    drop = np.zeros(g.n_blocks, np.uint8)
+    drop[0] = 1
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        swgn.marginalize([C.pointer(g)], [drop])
+    # argument errors are reported before any device is touched
+    job = G.FixedIntegerArrays([1, 1], [0, 1], [0.0, 0.0], np.eye(2), [0.0, 0.0], [0.0, 0.0], [], [], [])
+    with pytest.raises(RuntimeError, match="no fixed double difference"):
+        G.fixed_integer_prior([job])
+
+
 @pytest.mark.parametrize("which,wid,kw", [(1, 0, {}), (2, 0, {}), (2, 5, {}), (3, 0, {}), (4, 1, {}),
                                            (2, 1, dict(n_keyframes=40, n_landmarks=100, n_gnss_epochs=20))])
 def test_symbolic_cholesky_masks_cover_the_numeric_factor(which, wid, kw):
