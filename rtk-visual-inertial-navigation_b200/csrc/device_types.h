@@ -252,8 +252,9 @@ struct TRState {
   int32_t accepted;            // step accepted at the end of this iteration
   int32_t have_factor;         // W_S currently holds a Cholesky factor (lhs_out2 available)
   int32_t have_reduced;        // W_S currently holds S | rhs of an export-mode eliminate
-  int32_t pad;
+  int32_t alpha_valid;         // the Cauchy-point alpha of the current linearisation has been computed (lazily, k_step)
   double decrease_factor;      // LevenbergMarquardtStrategy::decrease_factor_
+  double ghat_sq;              // |J^T r / d|^2, the numerator of alpha
 };
 
 struct SolverParams {

@@ -111,29 +111,22 @@ __global__ void __launch_bounds__(kThreads) k_begin(DeviceBatch b, int tick) {
   }
   const double* DG = v.W(W_DIAG);
   if (s_flag[1]) {
-    // ghat = (J^T r) / d ;  alpha = |ghat|^2 / |J (ghat / d)|^2     (:174-192)
+    // ghat = (J^T r) / d  (:174-180).  The Cauchy point alpha = |ghat|^2 / |J (ghat / d)|^2 (:181-192) costs a pass over
+    // the Jacobian and is only read when the Gauss-Newton step leaves the trust region: k_step computes it then
+    // (same operands, same order of operations, so the value is the one ComputeCauchyPoint would have stored here)
     const double* G = v.W(W_G);
     double* GH = v.W(W_GHAT);
-    double* tmp = v.W(W_STEP);
-    double* MR = v.W(W_MRES);
     double gs = 0.0;
     for (int k = tid; k < d.n_t; k += kThreads) {
       const double gh = G[k] / DG[k];
       GH[k] = gh;
-      tmp[k] = gh / DG[k];
       gs += gh * gh;
     }
-    gs = block_sum(gs, red);  // (barrier: tmp is complete)
-    double js = 0.0;
-    for (int rs = tid; rs < d.n_res; rs += kThreads) {
-      const double m = row_dot(v, rs, tmp);
-      MR[rs] = m;
-      js += m * m;
-    }
-    js = block_sum(js, red);
+    gs = block_sum(gs, red);
     if (tid == 0) {
-      st->alpha = gs / js;
+      st->ghat_sq = gs;
       st->ghat_norm = sqrt(gs);
+      st->alpha_valid = 0;
     }
   }
   if (s_flag[2]) {
@@ -197,6 +190,24 @@ __global__ void __launch_bounds__(kThreads) k_step(DeviceBatch b) {
     }
     gnn2 = block_sum(gnn2, red);
     gdot = block_sum(gdot, red);
+    if (sqrt(gnn2) > st->radius && !st->alpha_valid) {  // ComputeCauchyPoint, deferred from k_begin (uniform per window)
+      double* tmp = STEP;
+      double* MRc = v.W(W_MRES);
+      for (int k = tid; k < d.n_t; k += kThreads) tmp[k] = GH[k] / DG[k];
+      __syncthreads();
+      double js = 0.0;
+      for (int rs = tid; rs < d.n_res; rs += kThreads) {
+        const double m = row_dot(v, rs, tmp);
+        MRc[rs] = m;
+        js += m * m;
+      }
+      js = block_sum(js, red);
+      if (tid == 0) {
+        st->alpha = st->ghat_sq / js;
+        st->alpha_valid = 1;
+      }
+      __syncthreads();
+    }
     if (tid == 0) {
       const double radius = st->radius, alpha = st->alpha, gnorm = st->ghat_norm, gnn = sqrt(gnn2);
       if (gnn <= radius) {
