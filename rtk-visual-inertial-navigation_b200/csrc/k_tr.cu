@@ -366,6 +366,19 @@ __global__ void __launch_bounds__(kThreads) k_end(DeviceBatch b) {
           s.se_ref = s.se_cand;
           s.se_acc_ref = s.se_acc_cand;
         }
+        // The step that exhausts max_num_iterations: Ceres still evaluates residuals and Jacobian at the new point
+        // (HandleSuccessfulStep) and then stops in FinalizeIterationAndCheckIfMinimizerCanContinue, which tests the
+        // iteration count BEFORE the gradient (trust_region_minimizer.cc:303-330) -- nothing that evaluation produces is
+        // read again.  Its cost is the candidate cost (same point, same code), so the evaluation is skipped here, unless
+        // the window holds stateful or host-evaluated factors (IMUGNSSFactor back-substitutes its hidden states during a
+        // Jacobian evaluation).  The one observable difference: a non-finite Jacobian at that last point (finite
+        // residuals) ends as NO_CONVERGENCE with the accepted state instead of FAILURE.
+        if (s.iteration >= P.max_num_iterations && b.desc[w].n_chain == 0 && b.desc[w].n_host == 0) {
+          s.accepted = 0;  // k_eval(accepted) does not run
+          s.x_cost = s.candidate_cost;
+          s.iter_cost = s.x_cost + s.fixed_cost;
+          s.last_successful = 1;
+        }
       } else {
         s.last_successful = 0;
         s.iter_cost = s.candidate_cost + s.fixed_cost;
