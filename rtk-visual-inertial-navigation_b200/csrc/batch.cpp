@@ -593,10 +593,25 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   P.strategy = options->trust_region_strategy;
   P.jacobi_scaling = options->jacobi_scaling ? 1 : 0;
   P.max_radius_lm = options->max_trust_region_radius;
-  CB(configure_schur(db));
-  CB(configure_schur_stream(db));
-  CB(configure_chol(db));
-  CB(configure_chain(db));
+  {
+    // a window whose per-CTA working set exceeds the 227 KB of shared memory (reduced system too wide for the Cholesky
+    // panel, chunk scratch too large) is a size limit of this implementation, not a CUDA failure
+    auto too_large = [&](cudaError_t e, const char* what) {
+      if (e != cudaErrorInvalidValue) return bail(e, what);
+      const std::string m = std::string(what) + ": a window needs more shared memory per CTA than the device offers (largest reduced system " +
+                            std::to_string(db.max_nf) + " rows)";
+      swgn_batch_destroy(b);
+      return fail(SWGN_ERR_TOO_LARGE, m);
+    };
+    cudaError_t e = configure_schur(db);
+    if (e != cudaSuccess) return too_large(e, "configure_schur");
+    e = configure_schur_stream(db);
+    if (e != cudaSuccess) return too_large(e, "configure_schur_stream");
+    e = configure_chol(db);
+    if (e != cudaSuccess) return too_large(e, "configure_chol");
+    e = configure_chain(db);
+    if (e != cudaSuccess) return too_large(e, "configure_chain");
+  }
   launch_gather_states(db, b->d_stage, b->d_state_off, 1, b->stream);
   CB(cudaGetLastError());
   CB(cudaStreamSynchronize(b->stream));

@@ -786,3 +786,18 @@ def test_marginalize_with_an_arbitrary_drop_set_matches_the_oracle(which, overri
         assert np.abs(Ag - Ao).max() < 1e-9 * np.abs(Ao).max()
         bg, bo = J0.T @ r0, oJ.T @ orr
         assert np.abs(bg - bo).max() < 1e-7 * max(1.0, np.abs(bo).max())
+
+
+def test_window_too_wide_for_shared_memory_is_reported_as_too_large():
+    """150 keyframes -> a 1 575-row reduced system: the Cholesky panel plus its vectors exceed 227 KB of shared memory.  The
+    library says so (SWGN_ERR_TOO_LARGE = 5 with the size in the message) instead of surfacing a bare CUDA 'invalid argument'."""
+    w = swgn.SynthWindow(1, 0, n_keyframes=150, n_landmarks=60)
+    opt = w.options()
+    opt.n_parameter_head = 0
+    with pytest.raises(RuntimeError, match="status 5.*shared memory"):
+        swgn.Batch([w.graph_p], opt)
+    # the library is still usable afterwards
+    w2 = swgn.SynthWindow(1, 0)
+    b = swgn.Batch([w2.graph_p], w2.options())
+    assert b.solve()[0].termination_type in (0, 1)
+    b.close()
