@@ -2,7 +2,8 @@
 // (RVI/factor/gnss_imu_factor.cpp:404, kSize = 15, assume_full_rank = true).  Semantics of
 // CERES/internal/ceres/invert_psd_matrix.h:50-74: full rank -> Eigen's inverse() for fixed sizes below 5,
 // otherwise LLT of the upper triangle solved against the identity; rank deficient -> thin-SVD solve.
-// Needs Eigen (the application's build has it; this repository's does not and compiles this to nothing).
+// Needs Eigen (the application's build has it; this repository's own build does not and compiles this to nothing).
+// Exercised by oracle/build_ref.sh, which compiles the reference's gnss_imu_factor.cpp against it and a stand-in Eigen.
 // The device-side counterpart used by the solver is the LLT-solve-identity in csrc/k_chain.cu.
 #ifndef SWGN_CERES_INVERT_PSD_MATRIX_H_
 #define SWGN_CERES_INVERT_PSD_MATRIX_H_

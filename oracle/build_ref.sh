@@ -6,13 +6,14 @@
 #   pose_local_parameterization.cpp                                   the factor classes of the hot path
 #   RVI/factor/initial_factor.cpp, pose0_factor.cpp                   initialisation factors (host-evaluated through the shim)
 #   RVI/factor/marginalization_factor.cpp                             MarginalizationInfo::marginalize / MarginalizationFactor
+#   RVI/factor/gnss_imu_factor.cpp                                    IMUGNSSBase / IMUGNSSFactor (the hidden GNSS-frame chain), through
+#                                                                     this repository's include/ceres/{small_blas,invert_psd_matrix}.h
 # Eigen, OpenCV and Ceres are not installed in this image: the factor sources are compiled against
 # oracle/ref_stubs/ (a minimal eager stand-in for the part of Eigen's dense API they use, empty OpenCV
 # headers, a type-name stub of marginalization_factor.h) and against this repository's own
 # include/ceres/ headers (CostFunction / SizedCostFunction / LocalParameterization), which doubles as
 # the build test of those headers against unmodified reference code.  NOT buildable here, and not
-# attempted: gnss_imu_factor.cpp (internal Ceres headers: small_blas / invert_psd_matrix on Eigen proper),
-# the estimator (ROS, OpenCV) and Ceres itself.
+# attempted: the estimator (ROS, OpenCV) and Ceres itself.
 # Outputs go to oracle/_ref/ only (git-ignored, travels with gpurun).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -29,8 +30,8 @@ g++ -O2 -fPIC -shared -ffp-contract=off -std=c++14 -include numeric -include eig
     "$REF/src/lambda.cpp" "$REF/src/common_function.cpp" \
     "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
     "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" \
-    "$SRC/factor/initial_factor.cpp" "$SRC/factor/marginalization_factor.cpp" \
-    "$HERE/ref_shim.cpp" "$HERE/ref_marg_shim.cpp" "$HERE/ref_globals.cpp" -lpthread -o "$HERE/_ref/libref_gnss.so"
+    "$SRC/factor/initial_factor.cpp" "$SRC/factor/marginalization_factor.cpp" "$SRC/factor/gnss_imu_factor.cpp" \
+    "$HERE/ref_shim.cpp" "$HERE/ref_marg_shim.cpp" "$HERE/ref_globals.cpp" "$HERE/ref_problem_stubs.cpp" -lpthread -o "$HERE/_ref/libref_gnss.so"
 echo "built $HERE/_ref/libref_gnss.so"
 # The drop-in demonstration of the ceres:: shim on the reference's own factor classes (shim/ceres_shim_refdemo.cpp):
 # needs the product library (libswgn.so) and the generator, built by __graft_entry__.build() before this script runs.

@@ -358,6 +358,25 @@ int oracle_factor_eval(int kind, int kind2, const double* globals /*Pbg3,g3,W4*/
   return f->Evaluate(p.data(), residuals, jac_out ? J.data() : nullptr) ? 0 : 1;
 }
 
+// The restated MarginalizationFactor (make_prior_factor) evaluated directly: residuals (n) and the row-major
+// n x global-size Jacobians back to back -- the same signature as oracle/ref_marg_shim.cpp's ref_prior_eval.
+int oracle_prior_eval(int n_keep, int n, const int32_t* keep_size, const int32_t* keep_idx, const double* x0, const double* J0,
+                      const double* r0, const double* x, double* residuals, double* jac_out) {
+  std::vector<int> sizes(keep_size, keep_size + n_keep), idx(keep_idx, keep_idx + n_keep);
+  std::unique_ptr<CostFunction> f(make_prior_factor(n, sizes, idx, x0, J0, r0));
+  std::vector<const double*> p;
+  std::vector<double*> J;
+  const double* pp = x;
+  double* jp = jac_out;
+  for (int sz : sizes) {
+    p.push_back(pp);
+    pp += sz;
+    J.push_back(jp);
+    if (jp) jp += (size_t)n * sz;
+  }
+  return f->Evaluate(p.data(), residuals, jac_out ? J.data() : nullptr) ? 0 : 1;
+}
+
 // CPU baseline: solve n windows, one window per OpenMP thread; returns wall seconds of the
 // minimise phase only (preprocessing excluded, like minimizer_time_in_seconds) and the total
 // number of trust-region iterations executed.

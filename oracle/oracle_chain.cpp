@@ -12,6 +12,8 @@
 //   GetInc                             :676-691
 // The "middle marginalisation" link (pose1_pose2_hessians, :741-760) is not part of the flat graph
 // (include/swgn.h) and is not restated.
+// Pinned on the reference's own IMUGNSSBase::Evaluate, compiled from gnss_imu_factor.cpp into oracle/_ref and executed on
+// the same chains (tests/test_chain_factor.py::test_oracle_chain_matches_the_reference_imugnss_factor).
 #include <cstdlib>
 
 #include "oracle_core.h"

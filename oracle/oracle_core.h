@@ -21,9 +21,10 @@
 //     compiled into oracle/_ref (tests/test_gnss_epoch.py).
 //   * MyOrdering, exports, LambdaSearch, GnssPreprocess bookkeeping: the reference holds no test or golden vector for them
 //     and the estimator cannot be built here (ROS / OpenCV): PARITY UNPINNED by execution; restated line by line.
-//   * IMUGNSSFactor (oracle_chain.cpp): gnss_imu_factor.cpp needs Ceres-internal headers on Eigen proper and is not
-//     buildable here: PARITY UNPINNED by the reference; pinned on the dense Schur complement of the whole chain
-//     (tests/test_chain_factor.py).
+//   * IMUGNSSFactor (oracle_chain.cpp): pinned on the reference's own IMUGNSSBase::Evaluate -- gnss_imu_factor.cpp
+//     compiled unmodified into oracle/_ref and executed on synthetic chains through the Jacobian / cost-only /
+//     Jacobian protocol, hidden-state back-substitution included -- and on the dense Schur complement of the whole
+//     chain (tests/test_chain_factor.py).
 //
 // RVI/   = /root/reference/rtk_visual_inertial_src/rtk_visual_inertial/src/
 // CERES/ = ceres-solver-modified/ inside /root/reference/ceres-solver-modified.tar

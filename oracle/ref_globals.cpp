@@ -5,3 +5,5 @@ Eigen::Vector3d Pbg;
 Eigen::Matrix3d Rwgw;
 Eigen::Vector3d G;
 double ACC_N, ACC_W, GYR_N, GYR_W;
+bool USE_GLOBAL_OPTIMIZATION = false;   // keeps IMUGNSSBase away from the ceres::Problem it is constructed with
+double MAX_TRUST_REGION_RADIUS = 1e4;

@@ -145,4 +145,41 @@ int ref_fixed_integer_prior(int n_keep, int n, const int32_t* keep_size, const i
   delete last_marg_info;
   return 0;
 }
+
+// MarginalizationFactor::Evaluate (marginalization_factor.cpp:410-446) on a MarginalizationInfo filled through its public
+// members: residuals (n) and the row-major n x global-size Jacobians back to back.
+int ref_prior_eval(int n_keep, int n, const int32_t* keep_size, const int32_t* keep_idx, const double* x0, const double* J0,
+                   const double* r0, const double* x, double* residuals, double* jac_out) {
+  std::vector<int> xoff;
+  int nx = 0;
+  for (int k = 0; k < n_keep; ++k) {
+    xoff.push_back(nx);
+    nx += keep_size[k];
+  }
+  std::vector<double> lin(x0, x0 + nx);
+  MarginalizationInfo info;
+  info.n = n;
+  info.m = 0;
+  for (int k = 0; k < n_keep; ++k) {
+    info.keep_block_size.push_back(keep_size[k]);
+    info.keep_block_idx.push_back(keep_idx[k]);
+    info.keep_block_data.push_back(lin.data() + xoff[k]);
+  }
+  info.linearized_jacobians.resize(n, n);
+  info.linearized_residuals = Eigen::VectorXd(n);
+  for (int i = 0; i < n; ++i) {
+    info.linearized_residuals(i) = r0[i];
+    for (int j = 0; j < n; ++j) info.linearized_jacobians(i, j) = J0[(size_t)i * n + j];
+  }
+  MarginalizationFactor f(&info);
+  std::vector<const double*> p;
+  std::vector<double*> J;
+  double* jp = jac_out;
+  for (int k = 0; k < n_keep; ++k) {
+    p.push_back(x + xoff[k]);
+    J.push_back(jp);
+    if (jp) jp += (size_t)n * keep_size[k];
+  }
+  return f.Evaluate(p.data(), residuals, jac_out ? J.data() : nullptr) ? 0 : 1;
+}
 }

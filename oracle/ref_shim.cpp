@@ -171,3 +171,114 @@ void ref_pose_plus(const double* x, const double* delta, double* out) {
 }
 double ref_varerr2(double el, double dt, double var) { return varerr2(el, dt, var); }
 }
+
+// ---- the reference's own IMUGNSSBase / IMUGNSSFactor (RVI/factor/gnss_imu_factor.cpp compiled where it lies, against the
+// Eigen stand-in and this repository's include/ceres/{small_blas,invert_psd_matrix}.h) ------------------------------------
+#include "factor/gnss_imu_factor.h"
+
+namespace {
+struct RefChain {
+  int m = 0, k = 0;
+  std::vector<double> pose0, sb0;                       // para_pose0 / para_speed_bias0 (never read by Evaluate)
+  std::vector<double> hidden, hidden_lin;               // m x 16: pose 7 | speed-bias 9
+  std::vector<double> dummyN;                           // gnss_phase_biases[i] targets
+  std::vector<std::unique_ptr<IntegrationBase>> pre;    // m + 1
+  IMUGNSSBase* base = nullptr;
+  std::unique_ptr<IMUGNSSFactor> factor;
+  ~RefChain() {
+    factor.reset();
+    delete base;  // deletes its IMUFactor objects, not the pre-integrations
+  }
+};
+}  // namespace
+
+extern "C" {
+// Arrays exactly as the chain_* fields of swgn_graph (include/swgn.h): frames m x SWGN_CHAIN_FRAME_STRIDE, frameN m x 15 x k,
+// chainN k x k + k, imu (m + 1) x SWGN_IMU_STRIDE.  The members of IMUGNSSBase are filled directly, the way AddMargInfo /
+// SetLastImuFactor leave them (gnss_imu_factor.cpp:96-117,245-352), then Init().
+void* ref_chain_create(const double* globals, int m, int k, const double* frames, const double* frameN, const double* chainN,
+                       const double* imu) {
+  set_globals(globals);
+  RefChain* C = new RefChain();
+  C->m = m;
+  C->k = k;
+  C->pose0.assign(7, 0.0);
+  C->sb0.assign(9, 0.0);
+  C->hidden.assign((size_t)16 * m, 0.0);
+  C->hidden_lin.assign((size_t)16 * m, 0.0);
+  C->dummyN.assign(std::max(k, 1), 0.0);
+  IMUGNSSBase* B = new IMUGNSSBase(C->pose0.data(), C->sb0.data(), nullptr);
+  C->base = B;
+  for (int i = 0; i <= m; ++i) {
+    C->pre.emplace_back(new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero()));
+    load_record(*C->pre.back(), imu + (size_t)SWGN_IMU_STRIDE * i);
+  }
+  for (int i = 0; i < m; ++i) {
+    const double* f = frames + (size_t)SWGN_CHAIN_FRAME_STRIDE * i;
+    for (int q = 0; q < 7; ++q) {
+      C->hidden[16 * i + q] = f[SWGN_CHAIN_POSE + q];
+      C->hidden_lin[16 * i + q] = f[SWGN_CHAIN_POSE_LIN + q];
+    }
+    for (int q = 0; q < 9; ++q) {
+      C->hidden[16 * i + 7 + q] = f[SWGN_CHAIN_SB + q];
+      C->hidden_lin[16 * i + 7 + q] = f[SWGN_CHAIN_SB_LIN + q];
+    }
+    B->gnss_poses.push_back(&C->hidden[16 * i]);
+    B->gnss_speed_bias.push_back(&C->hidden[16 * i + 7]);
+    B->gnss_poses_lin.push_back(&C->hidden_lin[16 * i]);
+    B->gnss_speed_bias_lin.push_back(&C->hidden_lin[16 * i + 7]);
+    Eigen::Matrix<double, 15, 15, Eigen::RowMajor> H;
+    Eigen::Matrix<double, 15, 1, Eigen::ColMajor> rhs;
+    Eigen::Matrix<double, 15, Eigen::Dynamic, Eigen::RowMajor> HN(15, k);
+    for (int a = 0; a < 15; ++a) {
+      rhs(a) = f[SWGN_CHAIN_RHS + a];
+      for (int b = 0; b < 15; ++b) H(a, b) = f[SWGN_CHAIN_HESSIAN + 15 * a + b];
+      for (int b = 0; b < k; ++b) HN(a, b) = frameN[((size_t)i * 15 + a) * k + b];
+    }
+    B->pose_hessians.push_back(H);
+    B->pose_rhses.push_back(rhs);
+    B->pose_phase_biases_hessians.push_back(HN);
+    B->imu_factors.push_back(new IMUFactor(C->pre[i].get()));
+  }
+  B->last_imu_factor = new IMUFactor(C->pre[m].get());
+  B->pose1_pose2_hessians.setZero();
+  B->phase_biases_hessians.resize(k, k);
+  B->phase_biases_rhs.resize(k);
+  for (int a = 0; a < k; ++a) {
+    B->phase_biases_rhs(a) = chainN[(size_t)k * k + a];
+    for (int b = 0; b < k; ++b) B->phase_biases_hessians(a, b) = chainN[(size_t)a * k + b];
+    B->gnss_phase_biases.push_back(&C->dummyN[a]);
+  }
+  B->gnss_Index = m;
+  B->Init();
+  C->factor.reset(new IMUGNSSFactor(B));
+  return C;
+}
+// params: pose_i 7 | sb_i 9 | pose_j 7 | sb_j 9 | N k.  jac (may be null = cost-only evaluation): the 4 + k row-major
+// (30 + k) x global-size Jacobians back to back.
+int ref_chain_evaluate(void* h, const double* params, double* residuals, double* jac) {
+  RefChain* C = (RefChain*)h;
+  const int n = 30 + C->k;
+  std::vector<const double*> p = {params, params + 7, params + 16, params + 23};
+  for (int a = 0; a < C->k; ++a) p.push_back(params + 32 + a);
+  std::vector<double*> J;
+  if (jac) {
+    double* q = jac;
+    const int sizes[4] = {7, 9, 7, 9};
+    for (int b = 0; b < 4; ++b) {
+      J.push_back(q);
+      q += (size_t)n * sizes[b];
+    }
+    for (int a = 0; a < C->k; ++a) {
+      J.push_back(q);
+      q += n;
+    }
+  }
+  return C->factor->Evaluate(p.data(), residuals, jac ? J.data() : nullptr) ? 0 : 1;
+}
+void ref_chain_frames(void* h, double* out) {
+  RefChain* C = (RefChain*)h;
+  std::copy(C->hidden.begin(), C->hidden.end(), out);
+}
+void ref_chain_destroy(void* h) { delete (RefChain*)h; }
+}

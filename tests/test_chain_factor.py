@@ -209,6 +209,142 @@ def test_oracle_solve_moves_hidden_frames_towards_truth():
 YAML_DENSITIES = dict(bias_walk_scale=1.0, hidden_bias_istd=0.0)   # yaml/rtk_visual_inertial_config.yaml:24-27 as they are
 
 
+def _chain_arrays(w, c):
+    """(m, k, frames, frameN, chainN, imu, blocks) of chain c: the chain_* slices of the graph."""
+    g = w.graph
+    b0 = g.chain_blk_begin[c]
+    k = g.chain_blk_begin[c + 1] - b0 - 4
+    f0, f1 = g.chain_frame_begin[c], g.chain_frame_begin[c + 1]
+    m = f1 - f0
+    nfr = g.chain_frame_begin[g.n_chain]
+    frames = np.ctypeslib.as_array(g.chain_frame_data, shape=(nfr, 274))[f0:f1].copy()
+    fN_off = sum((g.chain_frame_begin[i + 1] - g.chain_frame_begin[i]) * 15 *
+                 (g.chain_blk_begin[i + 1] - g.chain_blk_begin[i] - 4) for i in range(c))
+    cN_off = sum((lambda kk: kk * kk + kk)(g.chain_blk_begin[i + 1] - g.chain_blk_begin[i] - 4) for i in range(c))
+    imu_off = sum((g.chain_frame_begin[i + 1] - g.chain_frame_begin[i] + 1) for i in range(c))
+    frameN = np.ctypeslib.as_array(g.chain_frame_N, shape=(fN_off + m * 15 * k,))[fN_off:].copy()
+    chainN = np.ctypeslib.as_array(g.chain_N, shape=(cN_off + k * k + k,))[cN_off:].copy()
+    imu = np.ctypeslib.as_array(g.chain_imu_data, shape=(imu_off + m + 1, 474))[imu_off:].copy()
+    blocks = [g.chain_blocks[i] for i in range(b0, b0 + 4 + k)]
+    return m, k, frames, frameN, chainN, imu, blocks, (f0, f1)
+
+
+class RefChain:
+    """The reference's own IMUGNSSBase + IMUGNSSFactor (gnss_imu_factor.cpp compiled into oracle/_ref) on one chain."""
+
+    def __init__(self, w, c):
+        self.L = ob.ref()
+        L = self.L
+        L.ref_chain_create.restype = C.c_void_p
+        L.ref_chain_create.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 4
+        L.ref_chain_evaluate.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
+        L.ref_chain_frames.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_chain_destroy.argtypes = [C.c_void_p]
+        g = w.graph
+        self.m, self.k, frames, frameN, chainN, imu, self.blocks, self.frange = _chain_arrays(w, c)
+        gl = np.array(list(g.Pbg) + list(g.gravity) + list(g.proj_sqrt_info))
+        self.off = w.block_offsets()
+        self.h = L.ref_chain_create(ob._dp(gl), self.m, self.k, ob._dp(np.ascontiguousarray(frames)), ob._dp(frameN), ob._dp(chainN),
+                                    ob._dp(np.ascontiguousarray(imu)))
+
+    def params(self, x):
+        sizes = [7, 9, 7, 9] + [1] * self.k
+        return np.concatenate([x[self.off[b]:self.off[b] + s] for b, s in zip(self.blocks, sizes)])
+
+    def evaluate(self, x, jac=True):
+        """(r, J in the tangent layout pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9 | N k) -- J None for a cost-only evaluation"""
+        n = 30 + self.k
+        p = self.params(x)
+        r = np.zeros(n)
+        J = np.zeros(n * (32 + self.k)) if jac else None
+        assert self.L.ref_chain_evaluate(self.h, ob._dp(p), ob._dp(r), ob._dp(J) if jac else None) == 0
+        if not jac:
+            return r, None
+        out, o = [], 0
+        for s in [7, 9, 7, 9] + [1] * self.k:
+            blk = J[o:o + n * s].reshape(n, s)
+            out.append(blk[:, :6] if s == 7 else blk)
+            o += n * s
+        return r, np.hstack(out)
+
+    def frames(self):
+        out = np.zeros((self.m, 16))
+        self.L.ref_chain_frames(self.h, ob._dp(out))
+        return out
+
+    def close(self):
+        self.L.ref_chain_destroy(self.h)
+
+
+@pytest.mark.parametrize("which,wid,overrides", [(4, 0, {}), (4, 2, {}), (4, 1, dict(bias_walk_scale=1.0, hidden_bias_istd=0.0))])
+def test_oracle_chain_matches_the_reference_imugnss_factor(which, wid, overrides):
+    """PIN of SURVEY 8 row a6 on the reference's own code: IMUGNSSBase::Evaluate (gnss_imu_factor.cpp:678-799, with MargPose1,
+    UpdateSchurComponent, UpdateHiddenState, UpdateJacobResidual and IMUFactor::Evaluate2 behind it) is EXECUTED here on the
+    chains of a synthetic window and compared with the oracle's restatement through the protocol a solve drives:
+    Jacobian evaluation at x0 -> cost-only evaluation at x1 (linearised residual r - J INC) -> Jacobian evaluation at x1
+    (back-substitution of the hidden states, then re-elimination).  J = sqrt(S) V' is defined up to the sign / order of the
+    eigenvectors, so J'J, J'r and |r|^2 are compared, and the hidden states themselves."""
+    if ob.ref() is None or not hasattr(ob.ref(), "ref_chain_create"):
+        pytest.skip("oracle/_ref not built")
+    w = swgn.SynthWindow(which, wid, **overrides)
+    opt = w.options()
+    o = ob.OracleSolver(w.graph_p, opt)
+    cols = o.columns()
+    rows = chain_rows(w, o.rows())
+    x0 = w.state0()
+    rng = np.random.default_rng(wid)
+    refs = [RefChain(w, c) for c in range(w.graph.n_chain)]
+    yaml = bool(overrides)
+    tolH, tolg = (1e-8, 1e-6) if yaml else (1e-10, 1e-8)
+
+    def compare(x, with_jac, J_prev):
+        o.set_state(x)
+        if with_jac:
+            ocost, orr, og, oJ = o.evaluate()
+        else:
+            ocost, orr = o.evaluate_cost()
+        out = []
+        for c, R in enumerate(refs):
+            ro, n = rows[c]
+            idx, _ = chain_columns(w, c, cols)
+            r_ref, J_ref = R.evaluate(x, with_jac)
+            r_or = orr[ro:ro + n]
+            if with_jac:
+                J_or = oJ[ro:ro + n][:, idx]
+                H_ref, H_or = J_ref.T @ J_ref, J_or.T @ J_or
+                assert np.abs(H_ref - H_or).max() < tolH * np.abs(H_ref).max()
+                g_ref, g_or = J_ref.T @ r_ref, J_or.T @ r_or
+                assert np.abs(g_ref - g_or).max() < tolg * max(1.0, np.abs(g_ref).max())
+                out.append((J_ref, J_or))
+            else:   # the linearised residual lives in the row space of the last Jacobians
+                J_ref, J_or = J_prev[c]
+                g_ref, g_or = J_ref.T @ r_ref, J_or.T @ r_or
+                assert np.abs(g_ref - g_or).max() < tolg * max(1.0, np.abs(g_ref).max())
+                out.append((J_ref, J_or))
+            assert abs(r_ref @ r_ref - r_or @ r_or) < (1e-3 if yaml else 1e-6) * max(1.0, r_ref @ r_ref)
+        return out
+
+    Js = compare(x0, True, None)
+    # a step of the size a solver takes on the chain's outer blocks
+    x1 = x0.copy()
+    for R in refs:
+        for b, s in zip(R.blocks, [7, 9, 7, 9] + [1] * R.k):
+            d = rng.normal(size=s) * (1e-2 if s > 1 else 0.3)
+            x1[R.off[b]:R.off[b] + s] += d
+            if s == 7:
+                x1[R.off[b] + 3:R.off[b] + 7] /= np.linalg.norm(x1[R.off[b] + 3:R.off[b] + 7])
+    Js = compare(x1, False, Js)
+    Js = compare(x1, True, None)
+    # hidden states after the back-substitution the second Jacobian evaluation performed (UpdateHiddenState :601-646)
+    hf = o.chain_frames()
+    for R in refs:
+        f0, f1 = R.frange
+        a, b = R.frames(), hf[f0:f1]
+        assert np.abs(a - b).max() < (1e-6 if yaml else 1e-9) * max(1.0, np.abs(a).max())
+        assert np.abs(a - w.chain_frames0()[f0:f1]).max() > 1e-6     # they did move
+        R.close()
+
+
 def _oracle_run(which, wid, perturb, overrides=None, initial=False):
     code = ("import sys; sys.path[:0]=[%r,%r]; import numpy as np, swgn, oracle_binding as ob;"
             "w=swgn.SynthWindow(%d,%d,**%r); o=ob.OracleSolver(w.graph_p,w.options());"

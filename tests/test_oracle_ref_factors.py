@@ -168,3 +168,46 @@ def test_pose_plus_against_the_reference_class():
         ob.oracle().oracle_pose_plus(dp(x), dp(d), dp(a))
         ref.ref_pose_plus(dp(x), dp(d), dp(b))
         np.testing.assert_allclose(a, b, rtol=0, atol=4e-16 * max(1.0, np.abs(b).max()))
+
+
+def test_marginalization_factor_against_the_reference_class():
+    """a5: MarginalizationFactor::Evaluate (RVI/factor/marginalization_factor.cpp:410-446) of the reference, compiled into
+    oracle/_ref, against the oracle's restatement: residual r0 + J0 (x [-] x0) with the quaternion difference and its sign fix,
+    Jacobians = column slices of J0 padded to the global size."""
+    R = ob.ref()
+    if R is None or not hasattr(R, "ref_prior_eval"):
+        pytest.skip("oracle/_ref not built")
+    i32, f64, P = C.c_int32, C.c_double, C.POINTER
+    sig = [C.c_int, C.c_int, P(i32), P(i32), P(f64), P(f64), P(f64), P(f64), P(f64), P(f64)]
+    R.ref_prior_eval.argtypes = sig
+    O = ob.oracle()
+    O.oracle_prior_eval.argtypes = sig
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        sizes = np.array([7, 9, 1, 7, 3, 1], np.int32)
+        tang = [6 if s == 7 else int(s) for s in sizes]
+        idx = np.concatenate([[0], np.cumsum(tang)[:-1]]).astype(np.int32)
+        n = int(sum(tang))
+        J0, r0 = rng.normal(size=(n, n)), rng.normal(size=n)
+
+        def state(flip):
+            x = rng.normal(size=int(sizes.sum()))
+            o = 0
+            for s in sizes:
+                if s == 7:
+                    x[o + 3:o + 7] /= np.linalg.norm(x[o + 3:o + 7])
+                    if flip:
+                        x[o + 3:o + 7] *= -1     # exercises the w < 0 branch of the quaternion difference (:425-428)
+                o += s
+            return x
+        x0, x = state(False), state(trial % 2 == 1)
+        nj = n * int(sizes.sum())
+        out = []
+        for L in (R.ref_prior_eval, O.oracle_prior_eval):
+            res, jac = np.zeros(n), np.zeros(nj)
+            assert L(len(sizes), n, sizes.ctypes.data_as(P(i32)), idx.ctypes.data_as(P(i32)), ob._dp(x0), ob._dp(np.ascontiguousarray(J0)),
+                     ob._dp(r0), ob._dp(x), ob._dp(res), ob._dp(jac)) == 0
+            out.append((res, jac))
+        (rr, jr), (ro, jo) = out
+        assert np.abs(rr - ro).max() < 1e-12 * max(1.0, np.abs(rr).max())
+        assert np.array_equal(jr, jo)      # copies of J0's columns: exact
