@@ -41,6 +41,7 @@ if [ -f "$PKG/libswgn.so" ] && [ -f "$PKG/libswgn_synth.so" ]; then
       "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
       "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" "$REF/src/common_function.cpp" \
       "$SRC/factor/initial_factor.cpp" "$SRC/factor/pose0_factor.cpp" "$SRC/factor/marginalization_factor.cpp" \
+      "$SRC/factor/gnss_imu_factor.cpp" \
       "$PKG/shim/ceres_shim.cpp" "$PKG/shim/ceres_shim_refdemo.cpp" "$PKG/shim/gnss_refdemo.cpp" "$HERE/ref_globals.cpp" \
       -o "$HERE/_ref/libswgn_refdemo.so" -L"$PKG" -lswgn -lswgn_synth -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200'
   echo "built $HERE/_ref/libswgn_refdemo.so"

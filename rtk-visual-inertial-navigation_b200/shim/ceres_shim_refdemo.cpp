@@ -22,6 +22,7 @@
 #include "ceres/ceres.h"
 #include "ceres/schur_complement_solver.h"
 #include "factor/gnss_factor.h"
+#include "factor/gnss_imu_factor.h"
 #include "factor/imu_factor.h"
 #include "factor/initial_factor.h"
 #include "factor/marginalization_factor.h"
@@ -70,6 +71,30 @@ void register_adapters() {
   ceres::swgn::RegisterAdapter(typeid(FixedIntegerFactor), &fixed_integer<FixedIntegerFactor>);
   ceres::swgn::RegisterAdapter(typeid(InitialBlackFactor), &unit_prior<InitialBlackFactor>);
   ceres::swgn::RegisterAdapter(typeid(MarginalizationFactor), &marginalization<MarginalizationFactor>);
+  ceres::swgn::RegisterAdapter(typeid(IMUGNSSFactor), &imu_gnss<IMUGNSSFactor>);
+}
+// hidden GNSS-frame states of the last refdemo solve (16 doubles per frame, graph order), as the shim wrote them back
+// into the arrays IMUGNSSBase::gnss_poses / gnss_speed_bias point at
+std::vector<double> g_last_chain_frames;
+IntegrationBase* integration_from_record(const double* r) {
+  IntegrationBase* ib = new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero());
+  for (int k = 0; k < 3; ++k) {
+    ib->delta_p(k) = r[SWGN_IMU_DELTA_P + k];
+    ib->delta_v(k) = r[SWGN_IMU_DELTA_V + k];
+    ib->linearized_ba(k) = r[SWGN_IMU_LIN_BA + k];
+    ib->linearized_bg(k) = r[SWGN_IMU_LIN_BG + k];
+    ib->gyri(k) = r[SWGN_IMU_GYRI + k];
+    ib->gyrj(k) = r[SWGN_IMU_GYRJ + k];
+  }
+  ib->delta_q = Eigen::Quaterniond(r[SWGN_IMU_DELTA_Q + 3], r[SWGN_IMU_DELTA_Q], r[SWGN_IMU_DELTA_Q + 1], r[SWGN_IMU_DELTA_Q + 2]);
+  ib->sum_dt = r[SWGN_IMU_SUM_DT];
+  for (int a = 0; a < 15; ++a)
+    for (int c = 0; c < 15; ++c) {
+      ib->jacobian(a, c) = r[SWGN_IMU_JACOBIAN + a * 15 + c];
+      ib->sqrt_info(a, c) = r[SWGN_IMU_SQRT_INFO + a * 15 + c];
+    }
+  ib->covariance_update = false;
+  return ib;
 }
 }  // namespace
 
@@ -83,7 +108,6 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
   swgn_synth_config cfg;
   swgn_synth_default_config(which, &cfg);
   cfg.variant = variant;
-  if (cfg.composition != 0) return -1;
   swgn_synth* S = swgn_synth_create(&cfg, window_id);
   if (!S) return -1;
   const swgn_graph* g = swgn_synth_graph(S);
@@ -110,6 +134,12 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
   std::vector<std::unique_ptr<MarginalizationInfo>> marg(g->n_prior);
   std::vector<std::array<double, 12>> gnss_store(g->n_gnss);  // sat pos, sat vel, base pos, xyzt
   std::vector<Block> blocks;
+  // composition A: the reference's own IMUGNSSBase objects, members filled the way AddMargInfo / SetLastImuFactor leave
+  // them (gnss_imu_factor.cpp:96-117,245-352); the hidden frames live in `hidden`, which the shim updates after the solve
+  const int n_hidden = g->n_chain > 0 ? g->chain_frame_begin[g->n_chain] : 0;
+  std::vector<double> hidden((size_t)16 * n_hidden), hidden_lin((size_t)16 * n_hidden);
+  std::vector<std::unique_ptr<IMUGNSSBase>> bases;
+  std::vector<std::unique_ptr<IntegrationBase>> chain_pre;
   int result = -1;
   {
     ceres::Problem problem;
@@ -213,6 +243,57 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
       const Eigen::Matrix3d R3 = Eigen::Quaterniond(p3[6], p3[3], p3[4], p3[5]).toRotationMatrix();
       add(new InitPose0Factor(Eigen::MatrixXd(R3), Eigen::Vector3d(p3[0], p3[1], p3[2]), true, true, 30.0), nullptr, {mem[3].get()});
     }
+    {
+      size_t fN = 0, cN = 0, imu = 0;
+      for (int c = 0; c < g->n_chain; ++c) {
+        const int b0 = g->chain_blk_begin[c], k = g->chain_blk_begin[c + 1] - b0 - 4;
+        const int f0 = g->chain_frame_begin[c], m = g->chain_frame_begin[c + 1] - f0;
+        IMUGNSSBase* B = new IMUGNSSBase(mem[g->chain_blocks[b0]].get(), mem[g->chain_blocks[b0 + 1]].get(), &problem);
+        bases.emplace_back(B);
+        for (int i = 0; i < m; ++i) {
+          const double* f = g->chain_frame_data + (size_t)SWGN_CHAIN_FRAME_STRIDE * (f0 + i);
+          double* h = &hidden[(size_t)16 * (f0 + i)];
+          double* hl = &hidden_lin[(size_t)16 * (f0 + i)];
+          std::memcpy(h, f + SWGN_CHAIN_POSE, sizeof(double) * 16);
+          std::memcpy(hl, f + SWGN_CHAIN_POSE_LIN, sizeof(double) * 16);
+          B->gnss_poses.push_back(h);
+          B->gnss_speed_bias.push_back(h + 7);
+          B->gnss_poses_lin.push_back(hl);
+          B->gnss_speed_bias_lin.push_back(hl + 7);
+          Eigen::Matrix<double, 15, 15, Eigen::RowMajor> H;
+          Eigen::Matrix<double, 15, 1, Eigen::ColMajor> rhs;
+          Eigen::Matrix<double, 15, Eigen::Dynamic, Eigen::RowMajor> HN(15, k);
+          for (int a = 0; a < 15; ++a) {
+            rhs(a) = f[SWGN_CHAIN_RHS + a];
+            for (int q = 0; q < 15; ++q) H(a, q) = f[SWGN_CHAIN_HESSIAN + 15 * a + q];
+            for (int q = 0; q < k; ++q) HN(a, q) = g->chain_frame_N[fN + ((size_t)i * 15 + a) * k + q];
+          }
+          B->pose_hessians.push_back(H);
+          B->pose_rhses.push_back(rhs);
+          B->pose_phase_biases_hessians.push_back(HN);
+          chain_pre.emplace_back(integration_from_record(g->chain_imu_data + (size_t)SWGN_IMU_STRIDE * (imu + i)));
+          B->imu_factors.push_back(new IMUFactor(chain_pre.back().get()));
+        }
+        chain_pre.emplace_back(integration_from_record(g->chain_imu_data + (size_t)SWGN_IMU_STRIDE * (imu + m)));
+        B->last_imu_factor = new IMUFactor(chain_pre.back().get());
+        B->pose1_pose2_hessians.setZero();
+        B->phase_biases_hessians.resize(k, k);
+        B->phase_biases_rhs.resize(k);
+        std::vector<double*> params;
+        for (int q = 0; q < 4 + k; ++q) params.push_back(mem[g->chain_blocks[b0 + q]].get());
+        for (int a = 0; a < k; ++a) {
+          B->phase_biases_rhs(a) = g->chain_N[cN + (size_t)k * k + a];
+          for (int q = 0; q < k; ++q) B->phase_biases_hessians(a, q) = g->chain_N[cN + (size_t)a * k + q];
+          B->gnss_phase_biases.push_back(params[4 + a]);
+        }
+        B->gnss_Index = m;
+        B->Init();
+        add(new IMUGNSSFactor(B), nullptr, params);
+        fN += (size_t)m * 15 * k;
+        cN += (size_t)k * k + k;
+        imu += m + 1;
+      }
+    }
     for (int b = 0; b < g->n_blocks; ++b)
       if (g->block_const[b]) problem.SetParameterBlockConstant(mem[b].get());
 
@@ -235,7 +316,12 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
     const double cpu_initial = cpu_cost(blocks, g->proj_cauchy_a);
     ceres::Solver::Summary summary;
     ceres::Solve(options, &problem, &summary);
+    // the reference's stateful chain factors answer a cost-only call with the linearisation of their last Jacobian
+    // evaluation (the CPU call above); forgetting that history makes them eliminate afresh at the returned states, hidden
+    // frames included (the shim wrote those back into `hidden`)
+    for (auto& B : bases) B->history_flag = false;
     const double cpu_final = cpu_cost(blocks, g->proj_cauchy_a);
+    g_last_chain_frames = hidden;
     if (message && message_len > 0) std::snprintf(message, message_len, "%s | %s", summary.message.c_str(), summary.BriefReport().c_str());
     if (summary.termination_type != ceres::FAILURE || summary.num_successful_steps >= 0) {
       result = summary.termination_type;
@@ -256,4 +342,11 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
     for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], mem[b].get(), sizeof(double) * g->block_size[b]);
   swgn_synth_destroy(S);
   return result;
+}
+
+// hidden GNSS-frame states after the last swgn_ceres_refdemo_solve of a composition-A window (16 doubles per frame)
+extern "C" int swgn_ceres_refdemo_chain_frames(double* out, int cap_frames) {
+  const int n = (int)(g_last_chain_frames.size() / 16);
+  if (out && cap_frames >= n) std::memcpy(out, g_last_chain_frames.data(), sizeof(double) * g_last_chain_frames.size());
+  return n;
 }

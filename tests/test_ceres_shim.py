@@ -196,3 +196,42 @@ def test_reference_initialisation_factors_are_evaluated_on_the_host(which, wid, 
     plain = np.zeros(w.n_state)
     refdemo().swgn_ceres_refdemo_solve(which, wid, 0, strategy, 0, 0, plain.ctypes.data_as(C.POINTER(f64)), cost.ctypes.data_as(C.POINTER(f64)), steps, msg, 512)
     assert np.abs(plain - state).max() > 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libswgn_refdemo.so")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("which,wid", [(4, 0), (4, 2), (3, 0)])
+def test_reference_imugnss_factor_drops_in_through_the_shim(which, wid):
+    """Composition A built from the reference's OWN IMUGNSSBase / IMUGNSSFactor objects (gnss_imu_factor.cpp compiled
+    unmodified): the shim's adapter reads the object's public members into a chain record, the factor is evaluated on the
+    device, and after ceres::Solve the hidden GNSS-frame states are back in the arrays gnss_poses[i] / gnss_speed_bias[i]
+    point at.  Checked against (a) the reference class itself on the CPU -- its cost at the initial state, and at the
+    returned state after a fresh elimination there -- and (b) the C ABI solve of the same graph."""
+    L = refdemo()
+    L.swgn_ceres_refdemo_chain_frames.argtypes = [C.POINTER(f64), C.c_int]
+    w = swgn.SynthWindow(which, wid)
+    state = np.zeros(w.n_state)
+    cost = np.zeros(4)
+    steps = (C.c_int * 2)()
+    msg = C.create_string_buffer(512)
+    rc = L.swgn_ceres_refdemo_solve(which, wid, 0, 0, 0, 0, state.ctypes.data_as(C.POINTER(f64)), cost.ctypes.data_as(C.POINTER(f64)), steps, msg, 512)
+    assert rc in (0, 1), msg.value.decode()
+    dev_initial, dev_final, cpu_initial, cpu_final = cost
+    assert abs(dev_initial - cpu_initial) <= 1e-9 * cpu_initial, (dev_initial, cpu_initial)
+    # the device's final cost is the linearised cost of the last accepted candidate; the reference class re-eliminates at
+    # the returned states: equal up to the second-order term of the last step
+    assert abs(dev_final - cpu_final) <= 2e-3 * cpu_final, (dev_final, cpu_final)
+    assert dev_final < 1e-3 * dev_initial
+    n = L.swgn_ceres_refdemo_chain_frames(None, 0)
+    assert n == w.graph.chain_frame_begin[w.graph.n_chain]
+    frames = np.zeros((n, 16))
+    L.swgn_ceres_refdemo_chain_frames(frames.ctypes.data_as(C.POINTER(f64)), n)
+    b = swgn.Batch([w.graph_p], w.options())
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    hf = b.chain_frames(0)
+    b.close()
+    assert (steps[0], steps[1]) == (sm.num_successful_steps, sm.num_unsuccessful_steps)
+    assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9
+    assert float(np.max(np.abs(hf - frames) / np.maximum(1.0, np.abs(frames)))) < 1e-9
+    assert np.abs(frames - w.chain_frames0()).max() > 1e-6
