@@ -132,6 +132,17 @@ swgn_status swgn_gnss_tracker_erase(swgn_gnss_tracker* t, int32_t family, int32_
 swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, swgn_epoch* const* epochs,
                                  swgn_gnss_frame* frames, swgn_gnss_output* outputs);
 
+/* IMUGNSSBase::AddMargInfo (RVI/factor/gnss_imu_factor.cpp:245-352): the epoch's prior becomes one hidden frame of an
+   IMUGNSSFactor chain (the chain_* fields of swgn_graph, include/swgn.h).  Host-side scatter of the prior's information
+   A = J0'J0, b = J0'r0: the pose (6) and speed-bias (9) blocks fill the frame's 15 x 15 pose_hessians and pose_rhses, their
+   coupling with the size-1 keep blocks fills pose_phase_biases_hessians (15 x k), and the size-1 blocks ACCUMULATE into the
+   chain's phase_biases_hessians / phase_biases_rhs (k x k followed by k).  keep_slot[i] names, for every keep block of the
+   prior, its slot 0..k-1 in the chain's phase-bias list (the reference treats EVERY size-1 keep block as one, blackvalue
+   included) or -1 for the pose / speed-bias blocks.  frame: SWGN_CHAIN_FRAME_STRIDE doubles (current hidden states = pose /
+   speed_bias, linearisation point = the prior's x0); frame_N: 15 x k row-major, overwritten; chain_N: k x k + k, added to. */
+swgn_status swgn_gnss_chain_frame(const swgn_gnss_output* prior, const double* pose, const double* speed_bias, int32_t k,
+                                  const int32_t* keep_slot, double* frame, double* frame_N, double* chain_N);
+
 /* ---- staged entry points (parity tests) ----------------------------------------------------------------------- */
 /* update_azel + the gating residuals of swf_gnss.cpp:346-377 for n_obs observations in one launch:
    rec = 16 doubles per observation {sat_pos[3], receiver ECEF[3], base[3] (unused), lam, L_rtk, N_rtk, clk_rtk, L_spp,

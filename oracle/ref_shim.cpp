@@ -282,3 +282,71 @@ void ref_chain_frames(void* h, double* out) {
 }
 void ref_chain_destroy(void* h) { delete (RefChain*)h; }
 }
+
+// IMUGNSSBase::AddMargInfo (gnss_imu_factor.cpp:245-352) executed on real MarginalizationInfo objects: one call per
+// epoch, keep blocks identified across epochs by keep_id (a shared id = the same address, e.g. an ambiguity or the
+// blackvalue seen by several epochs).  Per epoch e: n_keep[e] blocks (sizes / first columns / ids / x0 concatenated over
+// the epochs), n[e], A (n x n row-major) and b concatenated.  Outputs: k, slot_of_id[max_ids] (position in
+// gnss_phase_biases or -1), pose_hessians (E x 225), pose_rhses (E x 15), pose_N (E x 15 x k), NN (k x k), Nrhs (k).
+extern "C" int ref_add_marg_info(int n_epochs, const int32_t* n_keep, const int32_t* keep_size, const int32_t* keep_idx,
+                                 const int32_t* keep_id, const double* x0, const int32_t* n, const double* A, const double* b, int max_ids,
+                                 int32_t* k_out, int32_t* slot_of_id, double* pose_hessians, double* pose_rhses, double* pose_N, double* NN,
+                                 double* Nrhs) {
+  std::vector<std::vector<double>> storage(max_ids, std::vector<double>(9, 0.0));  // user memory of every block
+  std::vector<double> pose0(7, 0.0), sb0(9, 0.0);
+  IMUGNSSBase B(pose0.data(), sb0.data(), nullptr);
+  std::vector<std::unique_ptr<MarginalizationInfo>> infos;
+  std::vector<std::unique_ptr<IntegrationBase>> pres;
+  std::vector<std::vector<double>> lin;
+  size_t ko = 0, xo = 0, ao = 0, bo = 0;
+  for (int e = 0; e < n_epochs; ++e) {
+    MarginalizationInfo* M = new MarginalizationInfo();
+    infos.emplace_back(M);
+    M->n = n[e];
+    M->m = 0;
+    for (int i = 0; i < n_keep[e]; ++i) {
+      const int s = keep_size[ko + i];
+      lin.emplace_back(x0 + xo, x0 + xo + s);
+      xo += s;
+    }
+    for (int i = 0; i < n_keep[e]; ++i) {
+      M->keep_block_size.push_back(keep_size[ko + i]);
+      M->keep_block_idx.push_back(keep_idx[ko + i]);
+      M->keep_block_addr.push_back(storage[keep_id[ko + i]].data());
+      M->keep_block_data.push_back(lin[lin.size() - n_keep[e] + i].data());
+    }
+    M->A.resize(n[e], n[e]);
+    M->b = Eigen::VectorXd(n[e]);
+    for (int r = 0; r < n[e]; ++r) {
+      M->b(r) = b[bo + r];
+      for (int c = 0; c < n[e]; ++c) M->A(r, c) = A[ao + (size_t)r * n[e] + c];
+    }
+    pres.emplace_back(new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero()));
+    std::vector<double> dummy_pose(7, 0.0), dummy_sb(9, 0.0);
+    B.AddMargInfo(M, pres.back().get(), dummy_pose.data(), dummy_sb.data());
+    ko += n_keep[e];
+    ao += (size_t)n[e] * n[e];
+    bo += n[e];
+  }
+  const int k = (int)B.gnss_phase_biases.size();
+  *k_out = k;
+  for (int id = 0; id < max_ids; ++id) {
+    slot_of_id[id] = -1;
+    for (int q = 0; q < k; ++q)
+      if (B.gnss_phase_biases[q] == storage[id].data()) slot_of_id[id] = q;
+  }
+  for (int e = 0; e < n_epochs; ++e) {
+    for (int a = 0; a < 15; ++a) {
+      pose_rhses[15 * e + a] = B.pose_rhses[e](a);
+      for (int c = 0; c < 15; ++c) pose_hessians[225 * e + 15 * a + c] = B.pose_hessians[e](a, c);
+      for (int c = 0; c < k; ++c) pose_N[((size_t)e * 15 + a) * k + c] = c < B.pose_phase_biases_hessians[e].cols() ? B.pose_phase_biases_hessians[e](a, c) : 0.0;
+    }
+  }
+  for (int a = 0; a < k; ++a) {
+    Nrhs[a] = B.phase_biases_rhs(a);
+    for (int c = 0; c < k; ++c) NN[(size_t)a * k + c] = B.phase_biases_hessians(a, c);
+  }
+  // the marginalization infos stay owned here (IMUGNSSBase keeps pointers into them only through the vectors above)
+  B.gnss_poses.clear();
+  return 0;
+}

@@ -418,6 +418,66 @@ swgn_status swgn_gnss_tracker_erase(swgn_gnss_tracker* t, int32_t family, int32_
   return SWGN_OK;
 }
 
+swgn_status swgn_gnss_chain_frame(const swgn_gnss_output* P, const double* pose, const double* speed_bias, int32_t k,
+                                  const int32_t* keep_slot, double* frame, double* frame_N, double* chain_N) {
+  if (!P || !pose || !speed_bias || k < 0 || !keep_slot || !frame || (k > 0 && (!frame_N || !chain_N)) || P->n <= 0 || !P->J0 || !P->r0)
+    return set_error(SWGN_ERR_INVALID, "bad arguments");
+  const int n = P->n;
+  // information form of the prior (marg_info_gnss->A, ->b)
+  std::vector<double> A((size_t)n * n, 0.0), b(n, 0.0);
+  for (int r = 0; r < n; ++r)
+    for (int i = 0; i < n; ++i) {
+      const double ji = P->J0[(size_t)r * n + i];
+      if (ji == 0.0) continue;
+      b[i] += ji * P->r0[r];
+      for (int j = 0; j < n; ++j) A[(size_t)i * n + j] += ji * P->J0[(size_t)r * n + j];
+    }
+  std::fill(frame, frame + SWGN_CHAIN_FRAME_STRIDE, 0.0);
+  std::fill(frame_N, frame_N + (size_t)15 * k, 0.0);
+  std::memcpy(frame + SWGN_CHAIN_POSE, pose, sizeof(double) * 7);
+  std::memcpy(frame + SWGN_CHAIN_SB, speed_bias, sizeof(double) * 9);
+  std::memcpy(frame + SWGN_CHAIN_POSE_LIN, pose, sizeof(double) * 7);       // when the prior has no such block
+  std::memcpy(frame + SWGN_CHAIN_SB_LIN, speed_bias, sizeof(double) * 9);
+  int xo = 0;
+  struct Blk {
+    int idx, row, size, slot;  // column in the prior, row in the 15-vector (-1: phase bias), tangent size, phase-bias slot
+  };
+  std::vector<Blk> blk;
+  for (int i = 0; i < P->n_keep; ++i) {
+    const int kind = P->keep_kind[i];
+    if (kind == SWGN_KEEP_POSE) {
+      std::memcpy(frame + SWGN_CHAIN_POSE_LIN, P->x0 + xo, sizeof(double) * 7);
+      blk.push_back({P->keep_idx[i], 0, 6, -1});
+      xo += 7;
+    } else if (kind == SWGN_KEEP_SPEED_BIAS) {
+      std::memcpy(frame + SWGN_CHAIN_SB_LIN, P->x0 + xo, sizeof(double) * 9);
+      blk.push_back({P->keep_idx[i], 6, 9, -1});
+      xo += 9;
+    } else {
+      if (keep_slot[i] < 0 || keep_slot[i] >= k) return set_error(SWGN_ERR_INVALID, "a size-1 keep block needs a phase-bias slot");
+      blk.push_back({P->keep_idx[i], -1, 1, keep_slot[i]});
+      xo += 1;
+    }
+  }
+  double* H = frame + SWGN_CHAIN_HESSIAN;
+  double* rhs = frame + SWGN_CHAIN_RHS;
+  for (const Blk& p : blk)
+    for (const Blk& q : blk)
+      for (int a = 0; a < p.size; ++a)
+        for (int c = 0; c < q.size; ++c) {
+          const double v = A[(size_t)(p.idx + a) * n + q.idx + c];
+          if (p.row >= 0 && q.row >= 0) H[(p.row + a) * 15 + q.row + c] += v;
+          else if (p.row >= 0) frame_N[(size_t)(p.row + a) * k + q.slot] += v;
+          else if (q.row < 0) chain_N[(size_t)p.slot * k + q.slot] += v;
+        }
+  for (const Blk& p : blk)
+    for (int a = 0; a < p.size; ++a) {
+      if (p.row >= 0) rhs[p.row + a] += b[p.idx + a];
+      else chain_N[(size_t)k * k + p.slot] += b[p.idx + a];
+    }
+  return SWGN_OK;
+}
+
 swgn_status swgn_gnss_gate_residuals(int32_t n_obs, const double* rec, double* out, int32_t device) {
   if (n_obs < 0 || (n_obs > 0 && (!rec || !out))) return set_error(SWGN_ERR_INVALID, "bad arguments");
   if (n_obs == 0) return SWGN_OK;

@@ -547,3 +547,78 @@ def test_gpu_fixed_integer_prior_matches_the_oracle():
         bg, bo = j.J0_out.T @ j.r0_out, Jo.T @ ro
         assert np.abs(bg - bo).max() < 1e-8 * max(1.0, np.abs(bo).max())
         assert abs(j.r0_out @ j.r0_out - ro @ ro) < 1e-8 * max(1.0, ro @ ro)
+
+
+def test_chain_frame_from_the_epoch_prior_matches_the_reference_add_marg_info():
+    """swgn_gnss_chain_frame (host-side scatter, no device) against IMUGNSSBase::AddMargInfo of the reference
+    (gnss_imu_factor.cpp:245-352) executed on real MarginalizationInfo objects: three consecutive epoch priors of one
+    receiver -- ambiguities shared between the epochs, one replaced after a slip, blackvalue treated as a phase bias like
+    the reference does -- become three hidden frames of one chain."""
+    L = ob.ref()
+    if L is None or not hasattr(L, "ref_add_marg_info"):
+        pytest.skip("oracle/_ref not built")
+    i32, f64, P = C.c_int32, C.c_double, C.POINTER
+    L.ref_add_marg_info.argtypes = [C.c_int, P(i32), P(i32), P(i32), P(i32), P(f64), P(i32), P(f64), P(f64), C.c_int, P(i32), P(i32),
+                                    P(f64), P(f64), P(f64), P(f64), P(f64)]
+    lib = G._proto()
+    lib.swgn_gnss_chain_frame.argtypes = [P(G.Output), P(f64), P(f64), i32, P(i32), P(f64), P(f64), P(f64)]
+    cfg = G.default_config()
+    sc = S.Scenario(0, cfg=cfg)
+    T, log = run_oracle(sc, cfg, 6)
+    epochs = log[3:6]     # epoch 4 carries an announced slip: a new ambiguity joins, the old one stays in the chain
+    # identities: 0..2 pose of epoch e, 3..5 speed-bias of epoch e, 6 blackvalue, 7.. ambiguities by handle
+    ids, sizes, idxs, x0s, ns, As, bs, nkeep = [], [], [], [], [], [], [], []
+    for e, rec in enumerate(epochs):
+        keep, x0, J0, r0 = rec["out"].prior()
+        for kd, h, col in keep:
+            ids.append(e if kd == G.KEEP_POSE else 3 + e if kd == G.KEEP_SPEED_BIAS else 6 if kd == G.KEEP_BLACK else 7 + h)
+            sizes.append(7 if kd == G.KEEP_POSE else 9 if kd == G.KEEP_SPEED_BIAS else 1)
+            idxs.append(col)
+        x0 = x0.copy()
+        x0[16] = 0.0   # AddMargInfo asserts that every size-1 block was linearised at 0 (the estimator's blackvalue is 0 there)
+        x0s.append(x0)
+        ns.append(J0.shape[0])
+        As.append((J0.T @ J0).ravel())
+        bs.append(J0.T @ r0)
+        nkeep.append(len(keep))
+    max_ids = max(ids) + 1
+    arr = lambda v, t: np.ascontiguousarray(np.concatenate([np.atleast_1d(x) for x in v]), t)
+    ids_a, sizes_a, idxs_a = arr(ids, np.int32), arr(sizes, np.int32), arr(idxs, np.int32)
+    k_ref = i32()
+    slot = np.zeros(max_ids, np.int32)
+    kcap = max_ids
+    pH, pr, pN, NN, Nr = np.zeros(3 * 225), np.zeros(45), np.zeros(3 * 15 * kcap), np.zeros(kcap * kcap), np.zeros(kcap)
+    rc = L.ref_add_marg_info(3, arr(nkeep, np.int32).ctypes.data_as(P(i32)), sizes_a.ctypes.data_as(P(i32)), idxs_a.ctypes.data_as(P(i32)),
+                             ids_a.ctypes.data_as(P(i32)), ob._dp(arr(x0s, np.float64)), arr(ns, np.int32).ctypes.data_as(P(i32)),
+                             ob._dp(arr(As, np.float64)), ob._dp(arr(bs, np.float64)), max_ids, C.byref(k_ref),
+                             slot.ctypes.data_as(P(i32)), ob._dp(pH), ob._dp(pr), ob._dp(pN), ob._dp(NN), ob._dp(Nr))
+    assert rc == 0
+    k = k_ref.value
+    # the caller's slot rule = the reference's: size-1 keep blocks in order of first appearance
+    order = []
+    for i, s in zip(ids, sizes):
+        if s == 1 and i not in order:
+            order.append(i)
+    assert k == len(order) and all(slot[i] == q for q, i in enumerate(order))
+    assert k > len([i for i in ids[:nkeep[0]] if i >= 6])          # the slip added a phase bias to the chain
+    chain_N = np.zeros(k * k + k)
+    o = 0
+    for e, rec in enumerate(epochs):
+        out = rec["out"]
+        out.x0[16] = 0.0
+        keep_slot = np.array([order.index(i) if s == 1 else -1 for i, s in zip(ids[o:o + nkeep[e]], sizes[o:o + nkeep[e]])], np.int32)
+        o += nkeep[e]
+        frame, frame_N = np.zeros(274), np.zeros(15 * k)
+        pose = np.array(rec["frame_in"].pose[:])
+        sb = np.array(rec["frame_in"].speed_bias[:])
+        st = lib.swgn_gnss_chain_frame(C.byref(out.c), ob._dp(pose), ob._dp(sb), k, keep_slot.ctypes.data_as(P(i32)), ob._dp(frame),
+                                       ob._dp(frame_N), ob._dp(chain_N))
+        assert st == 0
+        H, rhs = frame[48:273], frame[32:47]
+        scale = np.abs(pH[225 * e:225 * e + 225]).max()
+        assert np.abs(H - pH[225 * e:225 * e + 225]).max() < 1e-12 * scale
+        assert np.abs(rhs - pr[15 * e:15 * e + 15]).max() < 1e-12 * max(1.0, np.abs(pr).max())
+        assert np.abs(frame_N - pN[e * 15 * k:(e + 1) * 15 * k]).max() < 1e-12 * scale
+        assert np.array_equal(frame[0:7], pose) and np.array_equal(frame[16:23], pose) and np.array_equal(frame[23:32], sb)
+    assert np.abs(chain_N[:k * k] - NN[:k * k]).max() < 1e-12 * np.abs(NN).max()
+    assert np.abs(chain_N[k * k:] - Nr[:k]).max() < 1e-12 * max(1.0, np.abs(Nr).max())
