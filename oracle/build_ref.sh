@@ -45,4 +45,16 @@ if [ -f "$PKG/libswgn.so" ] && [ -f "$PKG/libswgn_synth.so" ]; then
       "$PKG/shim/ceres_shim.cpp" "$PKG/shim/ceres_shim_refdemo.cpp" "$PKG/shim/gnss_refdemo.cpp" "$HERE/ref_globals.cpp" \
       -o "$HERE/_ref/libswgn_refdemo.so" -L"$PKG" -lswgn -lswgn_synth -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200'
   echo "built $HERE/_ref/libswgn_refdemo.so"
+  # The reference's estimator code for the per-epoch GNSS path (swf_gnss.cpp, swf_core.cpp, swf_lambda.cpp), unmodified, on the
+  # ceres:: shim: oracle/ref_estimator_shim.cpp supplies what lives in translation units that need ROS / OpenCV.
+  g++ -O2 -fPIC -shared -ffp-contract=off -std=c++17 -include numeric -include eigen3/Eigen/Dense -I"$HERE/ref_stubs" -I"$HERE/../include" \
+      -I"$REF/include" -I"$SRC" -I"$SRC/factor" -I"$PKG/shim" \
+      "$SRC/swf/swf_gnss.cpp" "$SRC/swf/swf_core.cpp" "$SRC/swf/swf_lambda.cpp" \
+      "$SRC/factor/gnss_factor.cpp" "$SRC/factor/projection_factor.cpp" "$SRC/factor/imu_factor.cpp" \
+      "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" "$SRC/factor/initial_factor.cpp" \
+      "$SRC/factor/pose0_factor.cpp" "$SRC/factor/mag_factor.cpp" "$SRC/factor/marginalization_factor.cpp" \
+      "$SRC/factor/gnss_imu_factor.cpp" "$REF/src/common_function.cpp" "$REF/src/lambda.cpp" \
+      "$PKG/shim/ceres_shim.cpp" "$HERE/ref_estimator_shim.cpp" "$HERE/ref_globals.cpp" \
+      -o "$HERE/_ref/libref_estimator.so" -L"$PKG" -lswgn -lpthread -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200' -Wl,-z,defs
+  echo "built $HERE/_ref/libref_estimator.so"
 fi

@@ -1,0 +1,296 @@
+// TEST INFRASTRUCTURE.  The reference's ESTIMATOR code for the per-epoch GNSS path -- RVI/swf/swf_gnss.cpp (GnssPreprocess,
+// MyOrdering, UpdateSchur*, PhaseBias*), swf_core.cpp (AddGnssResidual, AddAllResidual) and swf_lambda.cpp (LambdaSearch),
+// compiled UNMODIFIED where they lie -- executed on this repository's ceres:: shim, i.e. with every ceres::Solve inside
+// them running on the device.  Built by oracle/build_ref.sh into oracle/_ref/libref_estimator.so.
+//
+// The estimator class has members and methods that live in translation units which need ROS and OpenCV (swf.cpp,
+// swf_imu.cpp, swf_image.cpp, feature_*.cpp); those are not compiled.  What the executed code needs from them is defined
+// here instead: the constructor (swf.cpp:13-34 + the allocations of ClearState :55-82), Vector2Double (swf.cpp:140-164,
+// restated), empty constructors of the two feature classes, the application globals of parameters.cpp, and abort() bodies
+// for five methods the executed paths never reach.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "swf/swf.h"
+#include "../include/swgn_gnss.h"
+#include "../rtk-visual-inertial-navigation_b200/shim/reference_gnss_binding.h"
+
+// ---- application globals (RVI/parameter/parameters.cpp reads them from the yaml; Pbg, Rwgw, G, ACC_N .. and
+// USE_GLOBAL_OPTIMIZATION / MAX_TRUST_REGION_RADIUS are in ref_globals.cpp) -------------------------------------------------
+bool USE_IMAGE = false, USE_GNSS = true, USE_IMU = true, USE_RTK = true, USE_RTD = true, USE_DOPPLER = true, USE_SPP_PHASE = false;
+bool USE_MAG_INIT_YAW = false, USE_MAG_CORRECT_YAW = false, USE_DIRECT_N_RESOLVE = false, USE_N_RESOLVE = true, USE_SPP_CORRECTION = false;
+bool USE_STEREO = false;
+Eigen::Vector3d ANCHOR_POINT;
+std::vector<Eigen::Matrix3d> RIC;
+std::vector<Eigen::Vector3d> TIC;
+double USE_FEATURE = 0;
+int CARRIER_PHASE_CONTINUE_THRESHOLD = 0, FIX_CONTINUE_THRESHOLD = 0, Phase_ALL_RESET_COUNT = 10;
+int NUM_OF_CAM = 0, ESTIMATE_EXTRINSIC = 0, MAX_NUM_ITERATIONS = 8;
+
+// ---- members defined in translation units that are not compiled ------------------------------------------------------
+FeatureTracker::FeatureTracker() {}
+FeatureManager::FeatureManager(Eigen::Matrix3d _Rs[]) : Rs(_Rs) {}
+SWFOptimization::SWFOptimization() : f_manager{Rs} {
+  for (int i = 0; i < FEATURE_WINDOW_SIZE + GNSS_WINDOW_SIZE + 1; i++) {  // ClearState, swf.cpp:56-72
+    para_gnss_dt[i] = new double[13];
+    para_pose[i] = new double[SIZE_POSE];
+    para_speed_bias[i] = new double[SIZE_SPEEDBIAS];
+    Rs[i].setIdentity();
+    Ps[i].setZero();
+    Vs[i].setZero();
+    Bas[i].setZero();
+    Bgs[i].setZero();
+    for (int s = 0; s < 13; s++) para_gnss_dt[i][s] = 0;
+    rovers[i] = nullptr;
+    i2f[i] = g2f[i] = f2i[i] = f2g[i] = 0;
+    frame_types[i] = ErroFrame;
+  }
+  solver_flag = Initial;
+  last_marg_info = nullptr;
+  rover_count = 0;
+  image_count = 0;
+  fix = false;
+  prev_time = prev_time2 = -1;
+  cur_time = 0;
+  open_ex_estimation = 0;
+  imu_initialize = false;
+  init_gnss = true;
+  pub_init = false;
+  first_imu = true;
+  rtk_fix = false;
+  not_fix_count = 0;
+  gnss_fix_solution_count = 0;
+  my_options.linear_solver_type = ceres::DENSE_SCHUR;
+  my_options.max_num_iterations = MAX_NUM_ITERATIONS;
+  my_options.jacobi_scaling = 0;
+  my_options.trust_region_strategy_type = ceres::DOGLEG;
+  my_options.num_threads = 4;
+  my_options.linear_solver_ordering.reset(new ceres::ParameterBlockOrdering());
+}
+void SWFOptimization::Vector2Double() {  // swf.cpp:140-164 (the feature loop of :177-180 has no effect)
+  for (int i = 0; i < rover_count + image_count; i++) {
+    para_pose[i][0] = Ps[i].x();
+    para_pose[i][1] = Ps[i].y();
+    para_pose[i][2] = Ps[i].z();
+    Quaterniond q{Rs[i]};
+    para_pose[i][3] = q.x();
+    para_pose[i][4] = q.y();
+    para_pose[i][5] = q.z();
+    para_pose[i][6] = q.w();
+    para_speed_bias[i][0] = Vs[i].x();
+    para_speed_bias[i][1] = Vs[i].y();
+    para_speed_bias[i][2] = Vs[i].z();
+    para_speed_bias[i][3] = Bas[i].x();
+    para_speed_bias[i][4] = Bas[i].y();
+    para_speed_bias[i][5] = Bas[i].z();
+    para_speed_bias[i][6] = Bgs[i].x();
+    para_speed_bias[i][7] = Bgs[i].y();
+    para_speed_bias[i][8] = Bgs[i].z();
+  }
+}
+static void not_reached(const char* what) {
+  std::fprintf(stderr, "libref_estimator.so: SWFOptimization::%s is not part of the executed path\n", what);
+  std::abort();
+}
+void SWFOptimization::Double2Vector() { not_reached("Double2Vector"); }
+void SWFOptimization::InitializePos(Eigen::Matrix3d&) { not_reached("InitializePos"); }
+void SWFOptimization::ResetImuGnssFactor(int, MarginalizationInfo*) { not_reached("ResetImuGnssFactor"); }
+void SWFOptimization::SlideWindowFrame(int, int, bool) { not_reached("SlideWindowFrame"); }
+void SWFOptimization::UpdateVisualGnssIndex() { not_reached("UpdateVisualGnssIndex"); }
+MarginalizationInfo* SWFOptimization::MargGNSSFrames(std::set<int>, IMUGNSSBase*) {
+  not_reached("MargGNSSFrames");
+  return nullptr;
+}
+
+// ---- the driver -----------------------------------------------------------------------------------------------------
+namespace {
+struct Estimator {
+  SWFOptimization swf;
+  std::vector<mea_t*> epochs;  // kept alive: the ambiguity lists are pointed at from inside
+  ~Estimator() {
+    for (mea_t* m : epochs) {
+      delete m->marg_info_gnss;
+      delete m;
+    }
+  }
+};
+void set_config(const swgn_gnss_config& c) {
+  USE_IMU = c.use_imu;
+  USE_RTK = c.use_rtk;
+  USE_RTD = c.use_rtd;
+  USE_SPP_PHASE = c.use_spp_phase;
+  USE_SPP_CORRECTION = c.use_spp_correction;
+  USE_DOPPLER = c.use_doppler;
+  Phase_ALL_RESET_COUNT = c.phase_all_reset_count;
+  for (int s = 0; s < 3; ++s)
+    for (int f = 0; f < 2; ++f) lams[s][f] = c.lams[s][f];
+}
+int family_of(SWFOptimization& s, const double* p, int* sat2f, int* pos) {
+  std::list<PBtype>* fam[3] = {s.rtk_phase_bias_variables, s.spp_phase_bias_variables, s.pseudorange_correction_variables};
+  for (int f = 0; f < 3; ++f)
+    for (int i = 0; i < MAXSATNUM * 2; ++i) {
+      int k = 0;
+      for (auto it = fam[f][i].begin(); it != fam[f][i].end(); ++it, ++k)
+        if (&it->value == p) {
+          *sat2f = i;
+          *pos = k;
+          return f;
+        }
+    }
+  return -1;
+}
+}  // namespace
+
+extern "C" {
+void* ref_est_create(const swgn_gnss_config* cfg) {
+  set_config(*cfg);
+  return new Estimator();
+}
+void ref_est_destroy(void* h) { delete (Estimator*)h; }
+
+// SWFOptimization::GnssPreprocess (swf_gnss.cpp:265-587) for one epoch, preceded by the update_azel call of GnssProcess
+// (:177-183).  The estimator is put into the state GnssProcess leaves it in: the epoch is the newest of rover_count
+// frames, its frame holds (pose, speed-bias), para_gnss_dt[0] and blackvalue carry the running estimates.
+// Outputs: the epoch (el, masked measurements), frame (gnss_dt, blackvalue after the initialisation solve) and, for the
+// epoch's marg_info_gnss: n, m, keep blocks in the reference's own order -- kind (SWGN_KEEP_*), for ambiguities
+// sat * 2 + f and the position in that list, first column --, the linearised factor (n x n row-major, n) and its x0.
+int ref_est_gnss_preprocess(void* h, const swgn_gnss_config* cfg, swgn_epoch* epoch, swgn_gnss_frame* frame, int cap_keep, int cap_n,
+                            int32_t* n_out, int32_t* n_keep, int32_t* keep_kind, int32_t* keep_sat2f, int32_t* keep_pos, int32_t* keep_idx,
+                            double* x0, double* J0, double* r0) {
+  Estimator* E = (Estimator*)h;
+  SWFOptimization& S = E->swf;
+  set_config(*cfg);
+  if (epoch->n_obs > MAXOBS) return -1;
+  mea_t* rover = new mea_t();
+  std::memset((void*)rover, 0, sizeof(mea_t));
+  E->epochs.push_back(rover);
+  rover->obs_count = epoch->n_obs;
+  rover->ros_time = epoch->ros_time;
+  rover->br_time_diff = epoch->br_time_diff;
+  for (int c = 0; c < 3; ++c) rover->base_xyz[c] = epoch->base_xyz[c];
+  for (int i = 0; i < epoch->n_obs; ++i) {
+    ObsMea& d = rover->obs_data[i];
+    const swgn_obs& o = epoch->obs[i];
+    d.sat = o.sat;
+    d.sys = o.sys;
+    d.SVH = o.svh;
+    for (int f = 0; f < NFREQ; ++f) {
+      d.RTK_SLIP_COUNT[f] = o.rtk_slip_count[f];
+      d.SPP_SLIP_COUNT[f] = o.spp_slip_count[f];
+      d.half_flag[f] = o.half_flag[f];
+      d.SPP_P[f] = o.spp_p[f];
+      d.SPP_L[f] = o.spp_l[f];
+      d.SPP_D[f] = o.spp_d[f];
+      d.SPP_Lstd[f] = o.spp_lstd[f];
+      d.SPP_Pstd[f] = o.spp_pstd[f];
+      d.SPP_Dstd[f] = o.spp_dstd[f];
+      d.RTK_P[f] = o.rtk_p[f];
+      d.RTK_L[f] = o.rtk_l[f];
+      d.RTK_Pstd[f] = o.rtk_pstd[f];
+      d.RTK_Lstd[f] = o.rtk_lstd[f];
+      d.SPP_P0[f] = o.spp_p0[f];
+    }
+    for (int c = 0; c < 3; ++c) {
+      d.satellite_pos[c] = o.sat_pos[c];
+      d.satellite_vel[c] = o.sat_vel[c];
+    }
+    d.el = o.el;
+    d.sat_var = o.sat_var;
+    d.ion_var = o.ion_var;
+    d.trop_var = o.trop_var;
+  }
+  // estimator state as GnssProcess has it when it calls GnssPreprocess: two frames, the epoch is the newest one
+  S.rover_count = 2;
+  S.image_count = 0;
+  S.g2f[0] = 0;
+  S.g2f[1] = 1;
+  S.frame_types[0] = S.frame_types[1] = SWFOptimization::GnssFrame;
+  S.rovers[1] = rover;
+  S.solver_flag = frame->nonlinear ? SWFOptimization::NonLinear : SWFOptimization::Initial;
+  S.not_fix_count = frame->not_fix_count;
+  S.rover_count_accumulate = frame->epochs_since_start + 1;  // rover_count_accumulate - rover_count + ir with ir = rover_count - 1
+  S.blackvalue = frame->blackvalue;
+  const Eigen::Quaterniond q(frame->pose[6], frame->pose[3], frame->pose[4], frame->pose[5]);
+  for (int i = 0; i < 2; ++i) {
+    S.Ps[i] = Eigen::Vector3d(frame->pose[0], frame->pose[1], frame->pose[2]);
+    S.Rs[i] = q.toRotationMatrix();
+    S.Vs[i] = Eigen::Vector3d(frame->speed_bias[0], frame->speed_bias[1], frame->speed_bias[2]);
+    S.Bas[i] = Eigen::Vector3d(frame->speed_bias[3], frame->speed_bias[4], frame->speed_bias[5]);
+    S.Bgs[i] = Eigen::Vector3d(frame->speed_bias[6], frame->speed_bias[7], frame->speed_bias[8]);
+  }
+  for (int s = 0; s < 13; ++s) S.para_gnss_dt[0][s] = frame->gnss_dt[s];
+  {  // GnssProcess :177-183
+    double globalxyz[3] = {S.Ps[1].x() + rover->base_xyz[0], S.Ps[1].y() + rover->base_xyz[1], S.Ps[1].z() + rover->base_xyz[2]};
+    update_azel(globalxyz, rover);
+  }
+  S.GnssPreprocess(rover);
+
+  // ---- read the results back ----
+  for (int i = 0; i < epoch->n_obs; ++i) {
+    const ObsMea& d = rover->obs_data[i];
+    swgn_obs& o = epoch->obs[i];
+    o.el = d.el;
+    for (int f = 0; f < NFREQ; ++f) {
+      o.rtk_l[f] = d.RTK_L[f];
+      o.spp_l[f] = d.SPP_L[f];
+      o.spp_p[f] = d.SPP_P[f];
+      o.spp_p0[f] = d.SPP_P0[f];
+    }
+  }
+  for (int s = 0; s < 13; ++s) frame->gnss_dt[s] = S.para_gnss_dt[0][s];
+  frame->blackvalue = S.blackvalue;
+  MarginalizationInfo* M = rover->marg_info_gnss;
+  *n_out = M->n;
+  *n_keep = (int)M->keep_block_addr.size();
+  if (*n_keep > cap_keep || M->n > cap_n) return -2;
+  int xo = 0;
+  for (int k = 0; k < *n_keep; ++k) {
+    const double* p = M->keep_block_addr[k];
+    keep_idx[k] = M->keep_block_idx[k] - M->m;
+    keep_sat2f[k] = keep_pos[k] = -1;
+    if (p == S.para_pose[1]) keep_kind[k] = SWGN_KEEP_POSE;
+    else if (p == S.para_speed_bias[1]) keep_kind[k] = SWGN_KEEP_SPEED_BIAS;
+    else if (p == &S.blackvalue) keep_kind[k] = SWGN_KEEP_BLACK;
+    else {
+      const int fam = family_of(S, p, &keep_sat2f[k], &keep_pos[k]);
+      if (fam < 0) return -3;
+      keep_kind[k] = SWGN_KEEP_AMB_RTK + fam;
+    }
+    for (int c = 0; c < M->keep_block_size[k]; ++c) x0[xo++] = M->keep_block_data[k][c];
+  }
+  for (int r = 0; r < M->n; ++r) {
+    for (int c = 0; c < M->n; ++c) J0[(size_t)r * M->n + c] = M->linearized_jacobians(r, c);
+    r0[r] = M->linearized_residuals(r);
+  }
+  return 0;
+}
+
+// the estimator's ambiguity lists: entries of family fam (0 RTK, 1 SPP, 2 pseudorange correction) in list order
+int ref_est_ambiguities(void* h, int fam, int cap, int32_t* sat2f, int32_t* pos, double* value, int32_t* continue_count, int32_t* slip_count,
+                        double* last_update_time) {
+  SWFOptimization& S = ((Estimator*)h)->swf;
+  std::list<PBtype>* lists = fam == 0 ? S.rtk_phase_bias_variables : fam == 1 ? S.spp_phase_bias_variables : S.pseudorange_correction_variables;
+  int n = 0;
+  for (int i = 0; i < MAXSATNUM * 2; ++i) {
+    int k = 0;
+    for (auto it = lists[i].begin(); it != lists[i].end(); ++it, ++k, ++n) {
+      if (n >= cap) return -1;
+      sat2f[n] = i;
+      pos[n] = k;
+      value[n] = it->value;
+      continue_count[n] = it->continue_count;
+      slip_count[n] = it->SLIP_COUNT;
+      last_update_time[n] = it->last_update_time;
+    }
+  }
+  return n;
+}
+void ref_est_set_ambiguity(void* h, int fam, int sat2f, int pos, double value) {
+  SWFOptimization& S = ((Estimator*)h)->swf;
+  std::list<PBtype>* lists = fam == 0 ? S.rtk_phase_bias_variables : fam == 1 ? S.spp_phase_bias_variables : S.pseudorange_correction_variables;
+  auto it = lists[sat2f].begin();
+  std::advance(it, pos);
+  it->value = value;
+}
+}

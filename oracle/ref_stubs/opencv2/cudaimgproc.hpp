@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE stub (see opencv.hpp)
+#pragma once
+#include "opencv.hpp"

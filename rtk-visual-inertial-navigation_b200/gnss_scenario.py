@@ -35,7 +35,7 @@ def range_rate(rr, rs, vr, vs):
 
 
 class Scenario:
-    def __init__(self, seed=0, n_epochs=14, cfg=None, pose_noise=0.01):
+    def __init__(self, seed=0, n_epochs=14, cfg=None, pose_noise=0.01, unhealthy_has_phase=True):
         rng = np.random.default_rng(seed)
         self.rng = rng
         self.cfg = cfg
@@ -45,6 +45,9 @@ class Scenario:
         E = enu_basis(lat, lon)
         self.n_epochs = n_epochs
         self.pose_noise = pose_noise
+        # the reference asserts an ambiguity for every non-zero RTK phase once rover_count > 1 (swf_core.cpp:110), unhealthy
+        # satellites included: real data carries no phase for them
+        self.unhealthy_has_phase = unhealthy_has_phase
         # satellites: system, number, ENU direction, range, velocity
         sys_of = [0] * 8 + [1] * 7 + [2] * 5
         first = [1, 40, 77]
@@ -109,6 +112,8 @@ class Scenario:
             o.spp_p[0] = rho + clk_spp + rng.normal(0, 0.8)
             o.spp_l[0] = (rho - s["N_spp"] * lam + clk_spp) / lam + rng.normal(0, 0.01)
             o.spp_pstd[0], o.spp_lstd[0] = 0.6, 0.02
+            if s["svh"] and not self.unhealthy_has_phase:
+                o.rtk_l[0] = o.spp_l[0] = 0.0
             rate = range_rate(rr, pos, self.v0, s["vel"])
             o.spp_d[0] = -(rate + self.clk[12]) / lam + rng.normal(0, 0.02)
             o.spp_dstd[0] = 0.05

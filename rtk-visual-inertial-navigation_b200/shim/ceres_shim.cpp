@@ -232,12 +232,47 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
                          "(the reference's configuration, RVI/swf/swf.cpp:25-30)");
   if (options.trust_region_strategy_type != DOGLEG && options.trust_region_strategy_type != LEVENBERG_MARQUARDT)
     return fail(summary, "swgn shim: unknown trust-region strategy");
-  if (!options.linear_solver_ordering) return fail(summary, "swgn shim: options.linear_solver_ordering is required");
 
   // ---- parameter blocks in insertion order
   std::vector<double*> blocks;
   problem->GetParameterBlocks(&blocks);
   const auto& bmap = problem->parameter_block_map();
+  // No ordering given (the reference's per-epoch GNSS solves, RVI/swf/swf_gnss.cpp:204-215,563-573): Ceres picks the
+  // elimination group itself, a maximal independent set of the variable blocks found greedily in order of increasing
+  // degree (ReorderProgramForSchurTypeLinearSolver -> ComputeStableSchurOrdering, reorder_program.cc / graph_algorithms.h:
+  // StableIndependentSetOrdering).  Which independent set is eliminated does not change the step of an exact solve.
+  std::shared_ptr<ParameterBlockOrdering> auto_ordering;
+  if (!options.linear_solver_ordering) {
+    std::unordered_map<const double*, std::vector<const double*>> nbr;
+    std::vector<double*> variable;
+    for (double* p : blocks)
+      if (!bmap.at(p).constant) variable.push_back(p);
+    for (internal::ResidualBlock* rb : problem->residual_block_list())
+      for (double* a : rb->parameter_blocks())
+        for (double* c : rb->parameter_blocks())
+          if (a != c && !bmap.at(a).constant && !bmap.at(c).constant) nbr[a].push_back(c);
+    std::stable_sort(variable.begin(), variable.end(), [&](const double* a, const double* c) {
+      auto deg = [&](const double* v) {
+        auto it = nbr.find(v);
+        if (it == nbr.end()) return (size_t)0;
+        std::vector<const double*> u(it->second);
+        std::sort(u.begin(), u.end());
+        return (size_t)(std::unique(u.begin(), u.end()) - u.begin());
+      };
+      return deg(a) < deg(c);
+    });
+    auto_ordering = std::make_shared<ParameterBlockOrdering>();
+    std::unordered_map<const double*, int> colour;  // 0 untouched, 1 in the set, 2 neighbour of the set
+    for (double* v : variable) {
+      if (colour[v] != 0) continue;
+      colour[v] = 1;
+      auto it = nbr.find(v);
+      if (it != nbr.end())
+        for (const double* u : it->second) colour[u] = 2;
+    }
+    for (double* pb : blocks) auto_ordering->AddElementToGroup(pb, colour[pb] == 1 ? 0 : 1);
+  }
+  const ParameterBlockOrdering* ordering = options.linear_solver_ordering ? options.linear_solver_ordering.get() : auto_ordering.get();
   std::unordered_map<const double*, int> index_of;
   std::vector<int32_t> bsize, bman, bconst, bgroup, boff;
   std::vector<double> state;
@@ -253,7 +288,7 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
       bman.push_back(SWGN_MANIFOLD_EUCLIDEAN);
     }
     bconst.push_back(info.constant ? 1 : 0);
-    bgroup.push_back(options.linear_solver_ordering->GroupId(p));
+    bgroup.push_back(ordering->GroupId(p));
     boff.push_back((int32_t)state.size());
     state.insert(state.end(), p, p + info.size);
   }

@@ -622,3 +622,143 @@ def test_chain_frame_from_the_epoch_prior_matches_the_reference_add_marg_info():
         assert np.array_equal(frame[0:7], pose) and np.array_equal(frame[16:23], pose) and np.array_equal(frame[23:32], sb)
     assert np.abs(chain_N[:k * k] - NN[:k * k]).max() < 1e-12 * np.abs(NN).max()
     assert np.abs(chain_N[k * k:] - Nr[:k]).max() < 1e-12 * max(1.0, np.abs(Nr).max())
+
+
+_REF_EST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_estimator.so")
+
+
+class RefEstimator:
+    """The reference's own SWFOptimization::GnssPreprocess (swf_gnss.cpp + swf_core.cpp compiled unmodified into
+    oracle/_ref/libref_estimator.so), running on this repository's ceres:: shim and the device."""
+
+    def __init__(self, cfg):
+        L = C.CDLL(_REF_EST)
+        i32, f64, P = C.c_int32, C.c_double, C.POINTER
+        L.ref_est_create.restype = C.c_void_p
+        L.ref_est_create.argtypes = [P(G.Config)]
+        L.ref_est_destroy.argtypes = [C.c_void_p]
+        L.ref_est_gnss_preprocess.argtypes = [C.c_void_p, P(G.Config), P(G.Epoch), P(G.Frame), C.c_int, C.c_int, P(i32), P(i32), P(i32), P(i32),
+                                              P(i32), P(i32), P(f64), P(f64), P(f64)]
+        L.ref_est_ambiguities.argtypes = [C.c_void_p, C.c_int, C.c_int, P(i32), P(i32), P(f64), P(i32), P(i32), P(f64)]
+        L.ref_est_set_ambiguity.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f64]
+        self.L, self.cfg = L, cfg
+        self.h = L.ref_est_create(C.byref(cfg))
+
+    def preprocess(self, epoch, frame):
+        i32, f64, P = C.c_int32, C.c_double, C.POINTER
+        cap_k, cap_n = 3 + 6 * G.MAXOBS, 16 + 6 * G.MAXOBS
+        n, nk = i32(), i32()
+        kind, s2f, pos, idx = (np.zeros(cap_k, np.int32) for _ in range(4))
+        x0, J0, r0 = np.zeros(cap_n + 3), np.zeros(cap_n * cap_n), np.zeros(cap_n)
+        rc = self.L.ref_est_gnss_preprocess(self.h, C.byref(self.cfg), C.byref(epoch), C.byref(frame), cap_k, cap_n, C.byref(n), C.byref(nk),
+                                            kind.ctypes.data_as(P(i32)), s2f.ctypes.data_as(P(i32)), pos.ctypes.data_as(P(i32)),
+                                            idx.ctypes.data_as(P(i32)), ob._dp(x0), ob._dp(J0), ob._dp(r0))
+        assert rc == 0, rc
+        n, nk = n.value, nk.value
+        keep = [(int(kind[k]), int(s2f[k]), int(pos[k]), int(idx[k])) for k in range(nk)]
+        return keep, x0, J0[:n * n].reshape(n, n).copy(), r0[:n].copy()
+
+    def ambiguities(self, fam):
+        i32, P = C.c_int32, C.POINTER
+        cap = 4096
+        s2f, pos, cc, sl = (np.zeros(cap, np.int32) for _ in range(4))
+        val, lut = np.zeros(cap), np.zeros(cap)
+        n = self.L.ref_est_ambiguities(self.h, fam, cap, s2f.ctypes.data_as(P(i32)), pos.ctypes.data_as(P(i32)), ob._dp(val),
+                                       cc.ctypes.data_as(P(i32)), sl.ctypes.data_as(P(i32)), ob._dp(lut))
+        return {(int(s2f[k]), int(pos[k])): (float(val[k]), int(cc[k]), int(sl[k]), float(lut[k])) for k in range(n)}
+
+    def set_ambiguity(self, fam, s2f, pos, v):
+        self.L.ref_est_set_ambiguity(self.h, fam, s2f, pos, v)
+
+    def close(self):
+        self.L.ref_est_destroy(self.h)
+
+
+def _product_ambiguities(T, fam):
+    """{(sat * 2 + f, position in that list): (handle, value, continue_count, slip_count, last_update_time)}"""
+    out, seen = {}, {}
+    for h in range(T.count(fam)):
+        a = T.get(fam, h)
+        key = a.sat * 2 + a.f
+        out[(key, seen.get(key, 0))] = (h, a.value, a.continue_count, a.slip_count, a.last_update_time)
+        seen[key] = seen.get(key, 0) + 1
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(_REF_EST), reason="oracle/_ref not built")
+@pytest.mark.parametrize("variant", ["rtk", "spp"])
+def test_gpu_preprocess_matches_the_reference_estimator_code(variant):
+    """The reference's GnssPreprocess ITSELF (unmodified swf_gnss.cpp / swf_core.cpp / marginalization_factor.cpp / gnss_factor.cpp,
+    its ceres::Solve calls going through the shim to the device -- with no linear_solver_ordering, as the reference leaves it)
+    against swgn_gnss_preprocess, epoch by epoch over the scripted scenario: same ambiguity bookkeeping (new / reset / counted /
+    timed-out entries per satellite list), same elevations and masks, the same information in the epoch's prior, the same
+    clocks and ambiguity values after the initialisation solve."""
+    cfg = _variant(variant)
+    cfg.estimate_pcorrection_period = 500   # a compile-time constant of the reference (parameters.h:27)
+    scr, scp = S.Scenario(13, cfg=cfg, unhealthy_has_phase=False), S.Scenario(13, cfg=cfg, unhealthy_has_phase=False)
+    R = RefEstimator(cfg)
+    T = G.Tracker(cfg)
+    dt, black = np.zeros(G.NCLK), 0.0    # AddMargInfo-style consumers need blackvalue linearised at 0; the estimator starts it at 0
+    slips = 0
+    for k in range(14):
+        er, obr, fr = scr.epoch(k)
+        ep, obp, fp = scp.epoch(k)
+        for f in (fr, fp):
+            for c in range(G.NCLK):
+                f.gnss_dt[c] = dt[c]
+            f.blackvalue = black
+            if k == 12:
+                f.not_fix_count = cfg.phase_all_reset_count + 1
+        keep_r, x0_r, J_r, r_r = R.preprocess(er, fr)
+        out = G.preprocess([T], [ep], [fp])[0]
+        keep_p, x0_p, J_p, r_p = out.prior()
+        slips += out.c.n_slip_rtk + out.c.n_slip_spp
+        # observations
+        for i in range(er.n_obs):
+            assert abs(obr[i].el - obp[i].el) < 1e-12
+            assert (obr[i].rtk_l[0], obr[i].spp_l[0], obr[i].spp_p0[0], obr[i].spp_p[0]) == (obp[i].rtk_l[0], obp[i].spp_l[0], obp[i].spp_p0[0], obp[i].spp_p[0])
+        # bookkeeping, list by list
+        for fam in range(3):
+            ar, ap = R.ambiguities(fam), _product_ambiguities(T, fam)
+            assert set(ar) == set(ap), (k, fam)
+            for key, (val, cc, sl, lut) in ar.items():
+                h, pval, pcc, psl, plut = ap[key]
+                if fam == G.AMB_PCORR:   # the reference never sets SLIP_COUNT of a pseudorange-correction entry (swf_gnss.cpp:477-487: stack garbage)
+                    sl = psl
+                assert (cc, sl, lut) == (pcc, psl, plut), (k, fam, key)
+                assert abs(val - pval) < 1e-6 * max(1.0, abs(val)), (k, fam, key, val, pval)
+        # the epoch's prior: same keep blocks (the reference's order is its unordered_map's), same information
+        handle_of = {}
+        for fam in range(3):
+            for key, v in _product_ambiguities(T, fam).items():
+                handle_of[(fam, key)] = v[0]
+        cols_p = {}
+        for kd, h, col in keep_p:
+            cols_p[(kd, h)] = col
+        perm, tang = [], {G.KEEP_POSE: 6, G.KEEP_SPEED_BIAS: 9}
+        assert len(keep_r) == len(keep_p)
+        ref_cols = {}
+        for kd, s2f, pos, col in keep_r:
+            h = -1 if kd < G.KEEP_AMB_RTK else handle_of[(kd - G.KEEP_AMB_RTK, (s2f, pos))]
+            ref_cols[(kd, h)] = col
+        for kd, h, col in keep_p:
+            t = tang.get(kd, 1)
+            perm += list(range(ref_cols[(kd, h)], ref_cols[(kd, h)] + t))
+        Jr = J_r[:, perm]
+        A_r, A_p = Jr.T @ Jr, J_p.T @ J_p
+        assert np.abs(A_r - A_p).max() < 1e-9 * np.abs(A_r).max()
+        b_r, b_p = Jr.T @ r_r, J_p.T @ r_p
+        assert np.abs(b_r - b_p).max() < 1e-8 * max(1.0, np.abs(b_r).max())
+        # state after the initialisation solve
+        for c in range(G.NCLK):
+            assert abs(fr.gnss_dt[c] - fp.gnss_dt[c]) < 1e-6 * max(1.0, abs(fr.gnss_dt[c])), (k, c)
+        assert abs(fr.blackvalue - fp.blackvalue) < 1e-9
+        # continue both from the reference's estimates
+        dt, black = np.array(fr.gnss_dt[:]), fr.blackvalue
+        for fam in range(3):
+            ap = _product_ambiguities(T, fam)
+            for key, (val, cc, sl, lut) in R.ambiguities(fam).items():
+                T.set_value(fam, ap[key][0], val)
+    assert slips >= 1 and T.count(G.AMB_RTK) > 30
+    R.close()
