@@ -19,8 +19,10 @@
 //     (RVI/factor/*.cpp compiled unmodified into oracle/_ref against a minimal Eigen stand-in; GNSS factors bit-exact).
 //   * MarginalizationInfo::marginalize + MarginalizationFactor: pinned on the reference's own marginalization_factor.cpp
 //     compiled into oracle/_ref (tests/test_gnss_epoch.py).
-//   * MyOrdering, exports, LambdaSearch, GnssPreprocess bookkeeping: the reference holds no test or golden vector for them
-//     and the estimator cannot be built here (ROS / OpenCV): PARITY UNPINNED by execution; restated line by line.
+//   * LambdaSearch (decision + prior rebuild) and GnssPreprocess: pinned on the reference's own estimator code -- swf_lambda.cpp,
+//     swf_gnss.cpp, swf_core.cpp compiled unmodified into oracle/_ref/libref_estimator.so and executed
+//     (tests/test_gnss_epoch.py).  MyOrdering and the UpdateSchur read-backs need the estimator's full frame / feature state:
+//     PARITY UNPINNED by execution; restated line by line.
 //   * IMUGNSSFactor (oracle_chain.cpp): pinned on the reference's own IMUGNSSBase::Evaluate -- gnss_imu_factor.cpp
 //     compiled unmodified into oracle/_ref and executed on synthetic chains through the Jacobian / cost-only /
 //     Jacobian protocol, hidden-state back-substitution included -- and on the dense Schur complement of the whole

@@ -293,4 +293,85 @@ void ref_est_set_ambiguity(void* h, int fam, int sat2f, int pos, double value) {
   std::advance(it, pos);
   it->value = value;
 }
+
+// SWFOptimization::LambdaSearch (swf_lambda.cpp:82-365, with FindReferenceSatellites :8-53 and lambda()) on the last
+// n_window epochs this estimator preprocessed (they become rovers[0 .. n_window-1], oldest first).  The caller provides
+// what UpdateSchurHessianOnly leaves behind -- A (n x n row-major information of the n ambiguities named by
+// (amb_sat2f, amb_pos) in the RTK lists; b is not read by the decision) -- and last_marg_info as a prior over exactly
+// those ambiguities (J0 n x n row-major, r0).  FIX_CONTINUE_THRESHOLD = 0: an accepted fix rebuilds the prior at once
+// (:249-355).  Outputs: flags = {rtk_fix, fix, last_fix, not_fix_count, gnss_fix_solution_count, prior rebuilt}; when
+// rebuilt, the new last_marg_info: keep_row[k] = row of A its k-th keep block is, its first column, J (n x n), r (n).
+int ref_est_lambda_search(void* h, int n_window, int n, const int32_t* amb_sat2f, const int32_t* amb_pos, const double* A, const double* J0,
+                          const double* r0, int32_t* flags, int32_t* keep_row, int32_t* keep_col, double* Jn, double* rn) {
+  Estimator* E = (Estimator*)h;
+  SWFOptimization& S = E->swf;
+  if (n_window < 1 || n_window > (int)E->epochs.size()) return -1;
+  FIX_CONTINUE_THRESHOLD = 0;
+  USE_GLOBAL_OPTIMIZATION = false;
+  S.rover_count = n_window;
+  S.image_count = 0;
+  for (int i = 0; i < n_window; ++i) {
+    S.rovers[i] = E->epochs[E->epochs.size() - n_window + i];
+    S.g2f[i] = i;
+  }
+  std::vector<double*> addr(n);
+  for (int k = 0; k < n; ++k) {
+    auto it = S.rtk_phase_bias_variables[amb_sat2f[k]].begin();
+    std::advance(it, amb_pos[k]);
+    addr[k] = &it->value;
+  }
+  S.A = Eigen::MatrixXd(n, n);
+  S.b = Eigen::VectorXd(n);
+  S.parameter_block_addr.clear();
+  S.parameter_block_global_size.clear();
+  for (int r = 0; r < n; ++r) {
+    S.b(r) = 0.0;
+    S.parameter_block_addr.push_back(addr[r]);
+    S.parameter_block_global_size.push_back(1);
+    for (int c = 0; c < n; ++c) S.A(r, c) = A[(size_t)r * n + c];
+  }
+  static std::vector<std::vector<double>> lin_keepalive;
+  lin_keepalive.emplace_back(n, 0.0);
+  std::vector<double>& lin = lin_keepalive.back();
+  MarginalizationInfo* M = new MarginalizationInfo();
+  M->n = n;
+  M->m = 0;
+  for (int k = 0; k < n; ++k) {
+    M->keep_block_size.push_back(1);
+    M->keep_block_idx.push_back(k);
+    M->keep_block_data.push_back(&lin[k]);
+    M->keep_block_addr.push_back(addr[k]);
+  }
+  M->linearized_jacobians.resize(n, n);
+  M->linearized_residuals = Eigen::VectorXd(n);
+  for (int r = 0; r < n; ++r) {
+    M->linearized_residuals(r) = r0[r];
+    for (int c = 0; c < n; ++c) M->linearized_jacobians(r, c) = J0[(size_t)r * n + c];
+  }
+  S.last_marg_info = M;
+  S.rtk_fix = false;
+  S.fix = false;
+  S.LambdaSearch();
+  flags[0] = S.rtk_fix;
+  flags[1] = S.fix;
+  flags[2] = S.last_fix;
+  flags[3] = S.not_fix_count;
+  flags[4] = S.gnss_fix_solution_count;
+  flags[5] = S.last_marg_info != M;
+  if (flags[5]) {
+    MarginalizationInfo* N = S.last_marg_info;  // (the old one was deleted by LambdaSearch)
+    if (N->n != n || (int)N->keep_block_addr.size() != n) return -2;
+    for (int k = 0; k < n; ++k) {
+      keep_row[k] = -1;
+      for (int q = 0; q < n; ++q)
+        if (N->keep_block_addr[k] == addr[q]) keep_row[k] = q;
+      keep_col[k] = N->keep_block_idx[k] - N->m;
+    }
+    for (int r = 0; r < n; ++r) {
+      for (int c = 0; c < n; ++c) Jn[(size_t)r * n + c] = N->linearized_jacobians(r, c);
+      rn[r] = N->linearized_residuals(r);
+    }
+  }
+  return 0;
+}
 }

@@ -35,7 +35,7 @@ def range_rate(rr, rs, vr, vs):
 
 
 class Scenario:
-    def __init__(self, seed=0, n_epochs=14, cfg=None, pose_noise=0.01, unhealthy_has_phase=True):
+    def __init__(self, seed=0, n_epochs=14, cfg=None, pose_noise=0.01, unhealthy_has_phase=True, half_flag=1):
         rng = np.random.default_rng(seed)
         self.rng = rng
         self.cfg = cfg
@@ -48,6 +48,7 @@ class Scenario:
         # the reference asserts an ambiguity for every non-zero RTK phase once rover_count > 1 (swf_core.cpp:110), unhealthy
         # satellites included: real data carries no phase for them
         self.unhealthy_has_phase = unhealthy_has_phase
+        self.half_flag = half_flag   # LambdaSearch asserts bits 8 and 2 of it (swf_lambda.cpp:161)
         # satellites: system, number, ENU direction, range, velocity
         sys_of = [0] * 8 + [1] * 7 + [2] * 5
         first = [1, 40, 77]
@@ -104,7 +105,7 @@ class Scenario:
             o.sat, o.sys, o.svh = s["sat"], s["sys"], s["svh"]
             o.rtk_slip_count[0] = s["slip"] & 255
             o.spp_slip_count[0] = s["spp_slip"] & 255
-            o.half_flag[0] = 1
+            o.half_flag[0] = self.half_flag
             clk_rtk, clk_spp = self.clk[s["sys"] * 2] + self.clk_rate[s["sys"] * 2] * t, self.clk[6 + s["sys"] * 2] + self.clk_rate[6 + s["sys"] * 2] * t
             o.rtk_l[0] = (rho - s["N"] * lam + clk_rtk) / lam + rng.normal(0, 0.003)
             o.rtk_p[0] = rho + clk_rtk + rng.normal(0, 0.25)

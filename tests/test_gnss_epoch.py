@@ -762,3 +762,91 @@ def test_gpu_preprocess_matches_the_reference_estimator_code(variant):
                 T.set_value(fam, ap[key][0], val)
     assert slips >= 1 and T.count(G.AMB_RTK) > 30
     R.close()
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EST), reason="oracle/_ref not built")
+@pytest.mark.parametrize("strong", [True, False])
+def test_oracle_lambda_search_matches_the_reference_estimator_code(strong):
+    """SWFOptimization::LambdaSearch ITSELF (unmodified swf_lambda.cpp with FindReferenceSatellites, lambda.cpp and the prior
+    rebuild of :249-355 through the reference's MarginalizationInfo) executed on an estimator holding three preprocessed
+    epochs, against the oracle's restatement of the decision (reference satellites, double-difference gate, lambda(),
+    ratio tests) and of the rebuild.  strong: an informative ambiguity matrix -> the fix is accepted and the prior rebuilt;
+    weak: the ratio test fails, not_fix_count advances, the prior stays."""
+    cfg = G.default_config()
+    sc = S.Scenario(17, cfg=cfg, unhealthy_has_phase=False, half_flag=11)
+    R = RefEstimator(cfg)
+    i32, f64, P = C.c_int32, C.c_double, C.POINTER
+    R.L.ref_est_lambda_search.argtypes = [C.c_void_p, C.c_int, C.c_int, P(i32), P(i32), P(f64), P(f64), P(f64), P(i32), P(i32), P(i32), P(f64), P(f64)]
+    epochs = []
+    dt = np.zeros(G.NCLK)
+    for k in range(3):
+        e, obs, f = sc.epoch(k)
+        f.blackvalue = 0.0
+        f.nonlinear = 0         # no residual gating: the ambiguities keep their first entries whether or not a device is present
+        for c in range(G.NCLK):
+            f.gnss_dt[c] = dt[c]
+        R.preprocess(e, f)      # (its initialisation solve needs the device; without one it reports FAILURE and changes nothing)
+        dt = np.array(f.gnss_dt[:])
+        epochs.append((e, obs))
+    amb = sorted(R.ambiguities(G.AMB_RTK))           # [(sat * 2 + f, position in the list)]
+    n = len(amb)
+    assert n == 18
+    row = {key: r for r, key in enumerate(amb)}
+    rng = np.random.default_rng(3)
+    sys_of = {}
+    for e, obs in epochs:
+        for i in range(e.n_obs):
+            sys_of[obs[i].sat * 2] = obs[i].sys
+    ints = rng.integers(-60, 60, n).astype(float)
+    y = ints + np.array([0.37, -0.81, 0.12])[[sys_of[k[0]] for k in amb]] + rng.normal(0, 0.01 if strong else 0.3, n)
+    for (s2f, pos), v in zip(amb, y):
+        R.set_ambiguity(G.AMB_RTK, s2f, pos, float(v))
+    B = rng.normal(size=(n, n))
+    A = (2500.0 if strong else 3.0) * np.eye(n) + (40.0 if strong else 0.05) * (B @ B.T)
+    J0 = np.linalg.cholesky(A).T.copy()
+    r0 = rng.normal(size=n) * 0.1
+    flags = np.zeros(6, np.int32)
+    keep_row, keep_col = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    Jn, rn = np.zeros((n, n)), np.zeros(n)
+    s2f_a = np.array([k[0] for k in amb], np.int32)
+    pos_a = np.array([k[1] for k in amb], np.int32)
+    rc = R.L.ref_est_lambda_search(R.h, 3, n, s2f_a.ctypes.data_as(P(i32)), pos_a.ctypes.data_as(P(i32)), ob._dp(np.ascontiguousarray(A)),
+                                   ob._dp(J0), ob._dp(r0), flags.ctypes.data_as(P(i32)), keep_row.ctypes.data_as(P(i32)),
+                                   keep_col.ctypes.data_as(P(i32)), ob._dp(Jn), ob._dp(rn))
+    assert rc == 0
+    rtk_fix, fix, last_fix, not_fix_count, n_fix_solutions, rebuilt = [int(v) for v in flags]
+    # ---- the oracle's decision on the same inputs
+    eb, oa, sf = [0], [], []
+    for e, obs in epochs:
+        for i in range(e.n_obs):
+            key = (obs[i].sat * 2, 0)
+            if obs[i].svh == 0 and obs[i].rtk_l[0] != 0 and key in row:
+                oa.append(row[key])
+                sf.append(obs[i].sys * 2)
+        eb.append(len(oa))
+    pairs, F, res = ob.ambiguity_fix(A, y, eb, oa, sf, last_fix=0)
+    assert res.status == 0 and res.n_dd >= 4
+    assert bool(res.search_ok) == bool(rtk_fix) == bool(rebuilt) == strong
+    assert not_fix_count == (0 if strong else 1) and n_fix_solutions == (1 if strong else 0)
+    if not strong:
+        R.close()
+        return
+    # ---- the rebuilt prior: last_marg_info + FixedIntegerFactors of the newest epoch's double differences, dummies dropped
+    newest = set(oa[eb[2]:eb[3]])
+    last_count = 0
+    while last_count < len(pairs) and int(pairs[last_count][0]) in newest:
+        last_count += 1
+    dd = [(int(a), int(b)) for a, b in pairs[:last_count]]
+    Fr = np.round(F[:last_count, 0])
+    assert np.array_equal(Fr, np.round(ints[[a for a, _ in dd]] - ints[[b for _, b in dd]]))   # the integers that were planted
+    sfd = [sys_of[amb[a][0]] * 2 for a, _ in dd]
+    job = G.FixedIntegerArrays([1] * n, list(range(n)), np.zeros(n), J0, r0, np.zeros(n), dd, Fr, sfd)
+    Jo, ro = _oracle_fixed_integer(job)
+    perm = [0] * n
+    for k in range(n):
+        perm[keep_row[k]] = keep_col[k]
+    Jr = Jn[:, perm]
+    A_ref, A_or = Jr.T @ Jr, Jo.T @ Jo
+    assert np.abs(A_ref - A_or).max() < 1e-9 * np.abs(A_ref).max()
+    assert np.abs(Jr.T @ rn - Jo.T @ ro).max() < 1e-8 * max(1.0, np.abs(Jr.T @ rn).max())
+    R.close()
