@@ -54,7 +54,7 @@ if [ -f "$PKG/libswgn.so" ] && [ -f "$PKG/libswgn_synth.so" ]; then
       "$SRC/factor/integration_base.cpp" "$SRC/factor/pose_local_parameterization.cpp" "$SRC/factor/initial_factor.cpp" \
       "$SRC/factor/pose0_factor.cpp" "$SRC/factor/mag_factor.cpp" "$SRC/factor/marginalization_factor.cpp" \
       "$SRC/factor/gnss_imu_factor.cpp" "$REF/src/common_function.cpp" "$REF/src/lambda.cpp" \
-      "$PKG/shim/ceres_shim.cpp" "$HERE/ref_estimator_shim.cpp" "$HERE/ref_globals.cpp" \
-      -o "$HERE/_ref/libref_estimator.so" -L"$PKG" -lswgn -lpthread -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200' -Wl,-z,defs
+      "$PKG/shim/ceres_shim.cpp" "$PKG/shim/ceres_shim_refdemo.cpp" "$HERE/ref_estimator_shim.cpp" "$HERE/ref_globals.cpp" \
+      -o "$HERE/_ref/libref_estimator.so" -L"$PKG" -lswgn -lswgn_synth -lpthread -Wl,-rpath,'$ORIGIN/../../rtk-visual-inertial-navigation_b200' -Wl,-z,defs
   echo "built $HERE/_ref/libref_estimator.so"
 fi

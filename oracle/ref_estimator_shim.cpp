@@ -374,4 +374,40 @@ int ref_est_lambda_search(void* h, int n_window, int n, const int32_t* amb_sat2f
   }
   return 0;
 }
+
+// SWFOptimization::UpdateSchur / UpdateSchurHessianOnly (swf_gnss.cpp:25-94) applied to what the shim exports after a
+// ceres::Solve of a synthetic window built from the reference's factor classes (shim/ceres_shim_refdemo.cpp, linked into
+// this library): hessian_only = 0 -> export-mode solve, then UpdateSchur (A, b of the parameter_head blocks);
+// hessian_only = 1 -> optimising solve, then UpdateSchurHessianOnly (A = L_nn L_nn').
+}
+extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int variant, int strategy, int host_factors, int device,
+                                        double* state_out, double* cost_out, int* steps_out, char* message, int message_len);
+extern "C" void swgn_ceres_refdemo_set_hooks(int is_optimize, void (*after_solve)(ceres::Problem*));
+namespace {
+SWFOptimization* g_us_swf = nullptr;
+int g_us_hessian_only = 0;
+void update_schur_hook(ceres::Problem* problem) {
+  if (g_us_hessian_only) g_us_swf->UpdateSchurHessianOnly(*problem);
+  else g_us_swf->UpdateSchur(*problem);
+}
+}  // namespace
+extern "C" {
+int ref_est_update_schur(int which, uint64_t window_id, int hessian_only, int cap_n, int32_t* n_out, double* A_out, double* b_out) {
+  static SWFOptimization* swf = new SWFOptimization();
+  g_us_swf = swf;
+  g_us_hessian_only = hessian_only;
+  swgn_ceres_refdemo_set_hooks(hessian_only ? 1 : 0, &update_schur_hook);
+  char msg[256];
+  const int rc = swgn_ceres_refdemo_solve(which, window_id, 0, 0, 0, 0, nullptr, nullptr, nullptr, msg, sizeof(msg));
+  swgn_ceres_refdemo_set_hooks(1, nullptr);
+  if (rc < 0) return -1;
+  const int n = (int)swf->A.rows();
+  *n_out = n;
+  if (n > cap_n) return -2;
+  for (int r = 0; r < n; ++r) {
+    if (!hessian_only) b_out[r] = swf->b(r);
+    for (int c = 0; c < n; ++c) A_out[(size_t)r * n + c] = swf->A(r, c);
+  }
+  return 0;
+}
 }

@@ -73,6 +73,11 @@ void register_adapters() {
   ceres::swgn::RegisterAdapter(typeid(MarginalizationFactor), &marginalization<MarginalizationFactor>);
   ceres::swgn::RegisterAdapter(typeid(IMUGNSSFactor), &imu_gnss<IMUGNSSFactor>);
 }
+// test hooks: run the solve in export mode (ceres::internal::is_optimize = false) and / or look at the problem and the
+// shim's exported arrays right after ceres::Solve, before parameter_head is cleared -- where the reference calls UpdateSchur /
+// UpdateSchurHessianOnly (RVI/swf/swf_image.cpp:232-236, swf_core.cpp:445-460)
+int g_refdemo_is_optimize = 1;
+void (*g_refdemo_after_solve)(ceres::Problem*) = nullptr;
 // hidden GNSS-frame states of the last refdemo solve (16 doubles per frame, graph order), as the shim wrote them back
 // into the arrays IMUGNSSBase::gnss_poses / gnss_speed_bias point at
 std::vector<double> g_last_chain_frames;
@@ -312,10 +317,11 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
     int32_t info[8];
     swgn_synth_info(S, info);
     for (int k = 0; k < so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(mem[info[5] + k].get());
-    ceres::internal::is_optimize = true;
+    ceres::internal::is_optimize = g_refdemo_is_optimize != 0;
     const double cpu_initial = cpu_cost(blocks, g->proj_cauchy_a);
     ceres::Solver::Summary summary;
     ceres::Solve(options, &problem, &summary);
+    if (g_refdemo_after_solve) g_refdemo_after_solve(&problem);
     // the reference's stateful chain factors answer a cost-only call with the linearisation of their last Jacobian
     // evaluation (the CPU call above); forgetting that history makes them eliminate afresh at the returned states, hidden
     // frames included (the shim wrote those back into `hidden`)
@@ -349,4 +355,8 @@ extern "C" int swgn_ceres_refdemo_chain_frames(double* out, int cap_frames) {
   const int n = (int)(g_last_chain_frames.size() / 16);
   if (out && cap_frames >= n) std::memcpy(out, g_last_chain_frames.data(), sizeof(double) * g_last_chain_frames.size());
   return n;
+}
+extern "C" void swgn_ceres_refdemo_set_hooks(int is_optimize, void (*after_solve)(ceres::Problem*)) {
+  g_refdemo_is_optimize = is_optimize;
+  g_refdemo_after_solve = after_solve;
 }
