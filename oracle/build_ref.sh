@@ -1,6 +1,6 @@
 #!/bin/sh
-# TEST INFRASTRUCTURE.  Builds oracle/_ref/libref_gnss.so from the reference's OWN sources where
-# they lie under /root/reference (nothing is copied):
+# TEST INFRASTRUCTURE.  Builds oracle/_ref/{libref_gnss.so, libswgn_refdemo.so, libref_estimator.so} from the reference's OWN
+# sources where they lie under /root/reference (nothing is copied):
 #   RVI/gnss/src/lambda.cpp, RVI/gnss/src/common_function.cpp         plain C-style code
 #   RVI/factor/gnss_factor.cpp, projection_factor.cpp, imu_factor.cpp, integration_base.cpp,
 #   pose_local_parameterization.cpp                                   the factor classes of the hot path
