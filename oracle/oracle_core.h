@@ -22,7 +22,7 @@
 //   * LambdaSearch (decision + prior rebuild) and GnssPreprocess: pinned on the reference's own estimator code -- swf_lambda.cpp,
 //     swf_gnss.cpp, swf_core.cpp compiled unmodified into oracle/_ref/libref_estimator.so and executed
 //     (tests/test_gnss_epoch.py); UpdateSchur / UpdateSchurHessianOnly executed on the shim's exports (tests/test_ceres_shim.py).
-//     MyOrdering needs the estimator's full frame / feature state: PARITY UNPINNED by execution; restated line by line.
+//     MyOrdering executed on composition-A windows whose blocks live in an estimator's storage (tests/test_ceres_shim.py).
 //   * IMUGNSSFactor (oracle_chain.cpp): pinned on the reference's own IMUGNSSBase::Evaluate -- gnss_imu_factor.cpp
 //     compiled unmodified into oracle/_ref and executed on synthetic chains through the Jacobian / cost-only /
 //     Jacobian protocol, hidden-state back-substitution included -- and on the dense Schur complement of the whole

@@ -411,3 +411,96 @@ int ref_est_update_schur(int which, uint64_t window_id, int hessian_only, int ca
   return 0;
 }
 }
+
+// ---- SWFOptimization::MyOrdering (swf_gnss.cpp:629-783) executed on a composition-A synthetic window ---------------------
+// The window is built by shim/ceres_shim_refdemo.cpp from the reference's factor classes, but its parameter blocks live in
+// an ESTIMATOR's storage -- para_pose[f], para_speed_bias[f], para_ex_Pose[0], f_manager.feature entries (landmarks),
+// rtk_phase_bias_variables entries (ambiguities), blackvalue2 -- so that MyOrdering recognises them by address; it is then
+// called where MyOptimization calls it (swf_image.cpp:212) and the solve runs with the ordering it produced.
+#include "../rtk-visual-inertial-navigation_b200/synth/swgn_synth.h"
+extern "C" void swgn_ceres_refdemo_set_build_hooks(double* (*block_memory)(int, int),
+                                                   void (*before_solve)(ceres::Problem*, ceres::Solver::Options*, const swgn_graph*, double* const*));
+namespace {
+struct OrderingRun {
+  SWFOptimization* swf = nullptr;
+  int F = 0, n_lm = 0, first_amb = 0, n_amb = 0, n_blocks = 0;
+  std::vector<int32_t> groups;
+  std::vector<FeaturePerId*> features;
+} g_mo;
+double* mo_block_memory(int b, int size) {
+  SWFOptimization& S = *g_mo.swf;
+  if (b < g_mo.F) return S.para_pose[b];
+  if (b < 2 * g_mo.F) return S.para_speed_bias[b - g_mo.F];
+  if (b == 2 * g_mo.F) return S.para_ex_Pose[0];
+  if (b < 2 * g_mo.F + 1 + g_mo.n_lm) {
+    S.f_manager.feature.push_back(FeaturePerId(b - (2 * g_mo.F + 1), 0));
+    return S.f_manager.feature.back().ptsInWorld.data();
+  }
+  if (b >= g_mo.first_amb && b < g_mo.first_amb + g_mo.n_amb) {
+    PBtype n;
+    n.value = 0;
+    n.continue_count = 0;
+    const int sat = b - g_mo.first_amb;
+    S.rtk_phase_bias_variables[sat * 2].push_back(n);
+    return &S.rtk_phase_bias_variables[sat * 2].back().value;
+  }
+  if (b == g_mo.n_blocks - 1) return &S.blackvalue2;
+  (void)size;
+  return &S.blackvalue;  // composition A holds no other scalar block
+}
+void mo_before_solve(ceres::Problem* problem, ceres::Solver::Options* options, const swgn_graph* g, double* const* ptr) {
+  SWFOptimization& S = *g_mo.swf;
+  S.image_count = g_mo.F;
+  S.rover_count = 0;
+  MarginalizationInfo* M = new MarginalizationInfo();
+  if (g->n_prior > 0)
+    for (int k = g->prior_blk_begin[0]; k < g->prior_blk_begin[1]; ++k) M->keep_block_addr.push_back(ptr[g->prior_blocks[k]]);
+  S.last_marg_info = M;
+  // the hidden GNSS frames are not parameter blocks of the reference's problem (SetLastImuFactor removes them,
+  // gnss_imu_factor.cpp:108-113); the window builder added every block of the flat graph
+  for (int b = 0; b < g->n_blocks; ++b) {
+    std::vector<ceres::ResidualBlockId> rbs;
+    problem->GetResidualBlocksForParameterBlock(ptr[b], &rbs);
+    if (rbs.empty()) problem->RemoveParameterBlock(ptr[b]);
+  }
+  S.MyOrdering(*problem, *options);
+  g_mo.groups.assign(g->n_blocks, -1);
+  for (int b = 0; b < g->n_blocks; ++b) g_mo.groups[b] = options->linear_solver_ordering->GroupId(ptr[b]);
+}
+}  // namespace
+extern "C" int ref_est_my_ordering(int which, uint64_t window_id, int cap_blocks, int32_t* n_blocks, int32_t* groups, double* state_out,
+                                   int* steps_out) {
+  swgn_synth_config cfg;
+  swgn_synth_default_config(which, &cfg);
+  if (cfg.composition != 1) return -1;  // MyOrdering knows the blocks of the reference's own graph: composition A
+  swgn_synth* W = swgn_synth_create(&cfg, window_id);
+  if (!W) return -1;
+  const swgn_graph* g = swgn_synth_graph(W);
+  int32_t info[8];
+  swgn_synth_info(W, info);
+  g_mo = OrderingRun();
+  g_mo.swf = new SWFOptimization();
+  g_mo.n_blocks = g->n_blocks;
+  for (int b = 0; b < g->n_blocks; ++b) {
+    if (g->block_size[b] == 9) g_mo.F++;
+    if (g->block_size[b] == 3) g_mo.n_lm++;
+  }
+  g_mo.n_amb = info[4];
+  g_mo.first_amb = info[5];
+  *n_blocks = g->n_blocks;
+  if (g->n_blocks > cap_blocks || g_mo.F > FEATURE_WINDOW_SIZE + GNSS_WINDOW_SIZE) {
+    swgn_synth_destroy(W);
+    return -2;
+  }
+  swgn_synth_destroy(W);
+  NUM_OF_CAM = 1;
+  swgn_ceres_refdemo_set_build_hooks(&mo_block_memory, &mo_before_solve);
+  char msg[256];
+  double cost[4];
+  const int rc = swgn_ceres_refdemo_solve(which, window_id, 0, 0, 0, 0, state_out, cost, steps_out, msg, sizeof(msg));
+  swgn_ceres_refdemo_set_build_hooks(nullptr, nullptr);
+  NUM_OF_CAM = 0;
+  if (rc < 0 || (int)g_mo.groups.size() != *n_blocks) return -3;
+  for (int b = 0; b < *n_blocks; ++b) groups[b] = g_mo.groups[b];
+  return rc;
+}

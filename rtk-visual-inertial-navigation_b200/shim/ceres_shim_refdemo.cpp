@@ -78,6 +78,8 @@ void register_adapters() {
 // UpdateSchurHessianOnly (RVI/swf/swf_image.cpp:232-236, swf_core.cpp:445-460)
 int g_refdemo_is_optimize = 1;
 void (*g_refdemo_after_solve)(ceres::Problem*) = nullptr;
+double* (*g_refdemo_block_memory)(int block, int size) = nullptr;
+void (*g_refdemo_before_solve)(ceres::Problem*, ceres::Solver::Options*, const swgn_graph*, double* const*) = nullptr;
 // hidden GNSS-frame states of the last refdemo solve (16 doubles per frame, graph order), as the shim wrote them back
 // into the arrays IMUGNSSBase::gnss_poses / gnss_speed_bias point at
 std::vector<double> g_last_chain_frames;
@@ -118,10 +120,18 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
   const swgn_graph* g = swgn_synth_graph(S);
   swgn_options so;
   swgn_synth_options(S, &so);
+  // parameter-block memory: this function's own, or the caller's (test hook: the estimator's para_pose / para_speed_bias /
+  // feature / ambiguity storage, so that the reference's MyOrdering can recognise the blocks by address)
   std::vector<std::unique_ptr<double[]>> mem(g->n_blocks);
+  std::vector<double*> ptr(g->n_blocks);
   for (int b = 0; b < g->n_blocks; ++b) {
-    mem[b].reset(new double[g->block_size[b]]);
-    std::memcpy(mem[b].get(), g->state + g->block_offset[b], sizeof(double) * g->block_size[b]);
+    if (g_refdemo_block_memory) {
+      ptr[b] = g_refdemo_block_memory(b, g->block_size[b]);
+    } else {
+      mem[b].reset(new double[g->block_size[b]]);
+      ptr[b] = mem[b].get();
+    }
+    std::memcpy(ptr[b], g->state + g->block_offset[b], sizeof(double) * g->block_size[b]);
   }
   // the application globals, for the reference's Evaluate() on the CPU and for the device
   Pbg = Eigen::Vector3d(g->Pbg[0], g->Pbg[1], g->Pbg[2]);
@@ -149,8 +159,8 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
   {
     ceres::Problem problem;
     for (int b = 0; b < g->n_blocks; ++b) {
-      if (g->block_manifold[b] == SWGN_MANIFOLD_POSE) problem.AddParameterBlock(mem[b].get(), 7, new PoseLocalParameterization());
-      else problem.AddParameterBlock(mem[b].get(), g->block_size[b]);
+      if (g->block_manifold[b] == SWGN_MANIFOLD_POSE) problem.AddParameterBlock(ptr[b], 7, new PoseLocalParameterization());
+      else problem.AddParameterBlock(ptr[b], g->block_size[b]);
     }
     auto add = [&](ceres::CostFunction* f, ceres::LossFunction* loss, std::vector<double*> params) {
       problem.AddResidualBlock(f, loss, params);
@@ -158,7 +168,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
     };
     for (int i = 0; i < g->n_proj; ++i)
       add(new projection_factor(Eigen::Vector3d(g->proj_uv[2 * i], g->proj_uv[2 * i + 1], 1.0)), new ceres::CauchyLoss(g->proj_cauchy_a),
-          {mem[g->proj_blocks[3 * i]].get(), mem[g->proj_blocks[3 * i + 1]].get(), mem[g->proj_blocks[3 * i + 2]].get()});
+          {ptr[g->proj_blocks[3 * i]], ptr[g->proj_blocks[3 * i + 1]], ptr[g->proj_blocks[3 * i + 2]]});
     for (int i = 0; i < g->n_imu; ++i) {
       const double* r = g->imu_data + (size_t)SWGN_IMU_STRIDE * i;
       pre[i].reset(new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero()));
@@ -180,7 +190,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
         }
       ib.covariance_update = false;
       add(new IMUFactor(&ib), nullptr,
-          {mem[g->imu_blocks[4 * i]].get(), mem[g->imu_blocks[4 * i + 1]].get(), mem[g->imu_blocks[4 * i + 2]].get(), mem[g->imu_blocks[4 * i + 3]].get()});
+          {ptr[g->imu_blocks[4 * i]], ptr[g->imu_blocks[4 * i + 1]], ptr[g->imu_blocks[4 * i + 2]], ptr[g->imu_blocks[4 * i + 3]]});
     }
     for (int i = 0; i < g->n_gnss; ++i) {
       const double* r = g->gnss_data + (size_t)SWGN_GNSS_STRIDE * i;
@@ -192,8 +202,8 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
       const int32_t* bl = g->gnss_blocks + 3 * i;
       const double meas = r[SWGN_GNSS_MEAS], lam = r[SWGN_GNSS_LAM], wgt = r[SWGN_GNSS_WEIGHT];
       const double el = r[SWGN_GNSS_EL], dt = r[SWGN_GNSS_DT], var = r[SWGN_GNSS_VAR];
-      std::vector<double*> p = {mem[bl[0]].get(), mem[bl[1]].get()};
-      if (bl[2] >= 0) p.push_back(mem[bl[2]].get());
+      std::vector<double*> p = {ptr[bl[0]], ptr[bl[1]]};
+      if (bl[2] >= 0) p.push_back(ptr[bl[2]]);
       switch (g->gnss_kind[i]) {
         case SWGN_GNSS_SPP_PSEUDORANGE: add(new SppPseudorangeFactor(sat, meas, wgt, base), nullptr, p); break;
         case SWGN_GNSS_SPP_CARRIER: add(new SppCarrierPhaseFactor(sat, meas, wgt, base, lam), nullptr, p); break;
@@ -216,7 +226,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
         m.keep_block_idx.push_back(g->prior_blk_idx[k]);
         m.keep_block_data.push_back(const_cast<double*>(x0));
         x0 += g->block_size[b];
-        params.push_back(mem[b].get());
+        params.push_back(ptr[b]);
       }
       m.linearized_jacobians.resize(m.n, m.n);
       m.linearized_residuals = Eigen::VectorXd(m.n);
@@ -226,7 +236,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
       }
       add(new MarginalizationFactor(&m), nullptr, params);
     }
-    for (int i = 0; i < g->n_unit; ++i) add(new InitialBlackFactor(g->unit_istd[i]), nullptr, {mem[g->unit_block[i]].get()});
+    for (int i = 0; i < g->n_unit; ++i) add(new InitialBlackFactor(g->unit_istd[i]), nullptr, {ptr[g->unit_block[i]]});
     if (host_factors) {
       // the reference's initialisation factors, anchored at the generator's ground truth; no adapter is registered for
       // them, so the shim evaluates them on the host
@@ -238,22 +248,22 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
       Eigen::Matrix<double, 6, 6> w6 = Eigen::Matrix<double, 6, 6>::Identity();
       for (int k = 0; k < 6; ++k) w6(k, k) = k < 3 ? 20.0 : 200.0;
       w6(0, 4) = 3.0;  // (not diagonal on purpose)
-      add(new InitialPoseFactor(Eigen::Vector3d(p1[0], p1[1], p1[2]), Eigen::Quaterniond(p1[6], p1[3], p1[4], p1[5]), w6), nullptr, {mem[1].get()});
+      add(new InitialPoseFactor(Eigen::Vector3d(p1[0], p1[1], p1[2]), Eigen::Quaterniond(p1[6], p1[3], p1[4], p1[5]), w6), nullptr, {ptr[1]});
       const double* s2 = truth + g->block_offset[F + 2];
       Eigen::Matrix<double, 9, 9> w9 = Eigen::Matrix<double, 9, 9>::Identity();
       for (int k = 0; k < 9; ++k) w9(k, k) = 5.0 + k;
       add(new InitialBiasFactor(Eigen::Vector3d(s2[0], s2[1], s2[2]), Eigen::Vector3d(s2[3], s2[4], s2[5]), Eigen::Vector3d(s2[6], s2[7], s2[8]), w9), nullptr,
-          {mem[F + 2].get()});
+          {ptr[F + 2]});
       const double* p3 = truth + g->block_offset[3];
       const Eigen::Matrix3d R3 = Eigen::Quaterniond(p3[6], p3[3], p3[4], p3[5]).toRotationMatrix();
-      add(new InitPose0Factor(Eigen::MatrixXd(R3), Eigen::Vector3d(p3[0], p3[1], p3[2]), true, true, 30.0), nullptr, {mem[3].get()});
+      add(new InitPose0Factor(Eigen::MatrixXd(R3), Eigen::Vector3d(p3[0], p3[1], p3[2]), true, true, 30.0), nullptr, {ptr[3]});
     }
     {
       size_t fN = 0, cN = 0, imu = 0;
       for (int c = 0; c < g->n_chain; ++c) {
         const int b0 = g->chain_blk_begin[c], k = g->chain_blk_begin[c + 1] - b0 - 4;
         const int f0 = g->chain_frame_begin[c], m = g->chain_frame_begin[c + 1] - f0;
-        IMUGNSSBase* B = new IMUGNSSBase(mem[g->chain_blocks[b0]].get(), mem[g->chain_blocks[b0 + 1]].get(), &problem);
+        IMUGNSSBase* B = new IMUGNSSBase(ptr[g->chain_blocks[b0]], ptr[g->chain_blocks[b0 + 1]], &problem);
         bases.emplace_back(B);
         for (int i = 0; i < m; ++i) {
           const double* f = g->chain_frame_data + (size_t)SWGN_CHAIN_FRAME_STRIDE * (f0 + i);
@@ -285,7 +295,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
         B->phase_biases_hessians.resize(k, k);
         B->phase_biases_rhs.resize(k);
         std::vector<double*> params;
-        for (int q = 0; q < 4 + k; ++q) params.push_back(mem[g->chain_blocks[b0 + q]].get());
+        for (int q = 0; q < 4 + k; ++q) params.push_back(ptr[g->chain_blocks[b0 + q]]);
         for (int a = 0; a < k; ++a) {
           B->phase_biases_rhs(a) = g->chain_N[cN + (size_t)k * k + a];
           for (int q = 0; q < k; ++q) B->phase_biases_hessians(a, q) = g->chain_N[cN + (size_t)a * k + q];
@@ -300,7 +310,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
       }
     }
     for (int b = 0; b < g->n_blocks; ++b)
-      if (g->block_const[b]) problem.SetParameterBlockConstant(mem[b].get());
+      if (g->block_const[b]) problem.SetParameterBlockConstant(ptr[b]);
 
     ceres::Solver::Options options;  // Ceres' defaults: LEVENBERG_MARQUARDT, jacobi_scaling = true
     options.linear_solver_type = ceres::DENSE_SCHUR;
@@ -312,12 +322,13 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
     options.device = device;
     options.linear_solver_ordering = std::make_shared<ceres::ParameterBlockOrdering>();
     for (int b = 0; b < g->n_blocks; ++b)
-      if (g->block_group[b] >= 0) options.linear_solver_ordering->AddElementToGroup(mem[b].get(), g->block_group[b]);
+      if (g->block_group[b] >= 0) options.linear_solver_ordering->AddElementToGroup(ptr[b], g->block_group[b]);
     ceres::internal::parameter_head.clear();
     int32_t info[8];
     swgn_synth_info(S, info);
-    for (int k = 0; k < so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(mem[info[5] + k].get());
+    for (int k = 0; k < so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(ptr[info[5] + k]);
     ceres::internal::is_optimize = g_refdemo_is_optimize != 0;
+    if (g_refdemo_before_solve) g_refdemo_before_solve(&problem, &options, g, ptr.data());  // (may replace the ordering)
     const double cpu_initial = cpu_cost(blocks, g->proj_cauchy_a);
     ceres::Solver::Summary summary;
     ceres::Solve(options, &problem, &summary);
@@ -345,7 +356,7 @@ extern "C" int swgn_ceres_refdemo_solve(int which, uint64_t window_id, int varia
     ceres::internal::parameter_head.clear();
   }
   if (state_out)
-    for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], mem[b].get(), sizeof(double) * g->block_size[b]);
+    for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], ptr[b], sizeof(double) * g->block_size[b]);
   swgn_synth_destroy(S);
   return result;
 }
@@ -359,4 +370,9 @@ extern "C" int swgn_ceres_refdemo_chain_frames(double* out, int cap_frames) {
 extern "C" void swgn_ceres_refdemo_set_hooks(int is_optimize, void (*after_solve)(ceres::Problem*)) {
   g_refdemo_is_optimize = is_optimize;
   g_refdemo_after_solve = after_solve;
+}
+extern "C" void swgn_ceres_refdemo_set_build_hooks(double* (*block_memory)(int, int),
+                                                   void (*before_solve)(ceres::Problem*, ceres::Solver::Options*, const swgn_graph*, double* const*)) {
+  g_refdemo_block_memory = block_memory;
+  g_refdemo_before_solve = before_solve;
 }

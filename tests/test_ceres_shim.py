@@ -280,3 +280,42 @@ def test_reference_update_schur_reads_the_shim_exports(wid):
     b.close()
     A3 = A3.reshape(n_amb, n_amb)
     assert np.abs(A3 - A4).max() < 1e-9 * np.abs(A4).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(_REF_EST), reason="oracle/_ref not built")
+@pytest.mark.parametrize("which,wid", [(4, 0), (4, 3), (3, 1)])
+def test_reference_my_ordering_executed_on_a_composition_a_window(which, wid):
+    """SWFOptimization::MyOrdering (RVI/swf/swf_gnss.cpp:629-783, unmodified) executed on a composition-A window whose parameter
+    blocks live in an estimator's own storage (para_pose, para_speed_bias, para_ex_Pose, f_manager.feature, the RTK ambiguity
+    lists, blackvalue2), called where MyOptimization calls it, the solve then running with the ordering it produced.  That
+    ordering is the one the graph generator restates (same elimination set, same sequence of the remaining blocks), and the
+    solve returns the states of the C-ABI solve of the flat graph."""
+    L = C.CDLL(_REF_EST)
+    L.ref_est_my_ordering.argtypes = [C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(f64), C.POINTER(C.c_int)]
+    w = swgn.SynthWindow(which, wid)
+    g = w.graph
+    nb = C.c_int32()
+    groups = np.full(g.n_blocks, -7, np.int32)
+    state = np.zeros(w.n_state)
+    steps = (C.c_int * 2)()
+    rc = L.ref_est_my_ordering(which, wid, g.n_blocks, C.byref(nb), groups.ctypes.data_as(C.POINTER(C.c_int32)), state.ctypes.data_as(C.POINTER(f64)), steps)
+    assert rc in (0, 1) and nb.value == g.n_blocks
+    mine = np.array([g.block_group[b] for b in range(g.n_blocks)])
+    const = np.array([g.block_const[b] for b in range(g.n_blocks)])
+    touched = np.zeros(g.n_blocks, bool)
+    for arr, n in ((g.proj_blocks, 3 * g.n_proj), (g.imu_blocks, 4 * g.n_imu), (g.prior_blocks, g.prior_blk_begin[g.n_prior]),
+                   (g.chain_blocks, g.chain_blk_begin[g.n_chain]), (g.unit_block, g.n_unit)):
+        for k in range(n):
+            touched[arr[k]] = True
+    live = touched & (const == 0)
+    assert (groups[live] >= 0).all() and (groups[~live] == -1).all()
+    assert set(np.where(groups == 0)[0]) == set(np.where(live & (mine == 0))[0])           # the elimination set
+    rest = np.where(live & (groups > 0))[0]
+    assert list(rest[np.argsort(groups[rest], kind="stable")]) == list(rest[np.argsort(mine[rest], kind="stable")])   # the sequence after it
+    b = swgn.Batch([w.graph_p], w.options())
+    sm = b.solve()[0]
+    x = b.get_state(0, w.n_state)
+    b.close()
+    assert (steps[0], steps[1]) == (sm.num_successful_steps, sm.num_unsuccessful_steps)
+    assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9
