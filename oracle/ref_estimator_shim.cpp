@@ -504,3 +504,218 @@ extern "C" int ref_est_my_ordering(int which, uint64_t window_id, int cap_blocks
   for (int b = 0; b < *n_blocks; ++b) groups[b] = g_mo.groups[b];
   return rc;
 }
+
+// ---- SWFOptimization::AddAllResidual(NormalMode, ...) (swf_core.cpp:209-412) executed: the reference's OWN assembly of the
+// sliding-window problem from estimator state -- blackvalue2, IMU / IMUGNSS factors per image gap, visual features from
+// f_manager, the marginalisation prior -- followed by AddParameter2Problem, MyOrdering and ceres::Solve, which is what
+// MyOptimization runs without USE_GLOBAL_OPTIMIZATION (swf_image.cpp:241-250).  The estimator state is filled from a
+// composition-A synthetic window (its flat graph only serves as the source of the numbers).
+extern "C" void swgn_ceres_refdemo_prepare(const swgn_graph* g);
+extern "C" void* swgn_ceres_refdemo_integration(const double* record);
+extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_state, double* state_out, double* chain_frames_out,
+                                        int32_t* n_frames_out) {
+  swgn_synth_config cfg;
+  swgn_synth_default_config(which, &cfg);
+  if (cfg.composition != 1) return -1;
+  swgn_synth* W = swgn_synth_create(&cfg, window_id);
+  if (!W) return -1;
+  const swgn_graph* g = swgn_synth_graph(W);
+  swgn_options so;
+  swgn_synth_options(W, &so);
+  int32_t info[8];
+  swgn_synth_info(W, info);
+  if (g->n_state > cap_state) return -2;
+  swgn_ceres_refdemo_prepare(g);
+  int F = 0, n_lm = 0;
+  for (int b = 0; b < g->n_blocks; ++b) {
+    if (g->block_size[b] == 9) F++;
+    if (g->block_size[b] == 3) n_lm++;
+  }
+  const int b_ext = 2 * F, b_lm = 2 * F + 1, first_amb = info[5], n_amb = info[4], b_black2 = g->n_blocks - 1;
+  SWFOptimization& S = *new SWFOptimization();
+  USE_IMAGE = true;
+  USE_GLOBAL_OPTIMIZATION = false;
+  USE_MAG_CORRECT_YAW = false;
+  NUM_OF_CAM = 1;
+  ESTIMATE_EXTRINSIC = 0;
+  // block -> estimator storage
+  std::vector<double*> ptr(g->n_blocks, nullptr);
+  for (int f = 0; f < F; ++f) {
+    ptr[f] = S.para_pose[f];
+    ptr[F + f] = S.para_speed_bias[f];
+  }
+  ptr[b_ext] = S.para_ex_Pose[0];
+  for (int l = 0; l < n_lm; ++l) {
+    S.f_manager.feature.push_back(FeaturePerId(l, 0));
+    ptr[b_lm + l] = S.f_manager.feature.back().ptsInWorld.data();
+  }
+  for (int a = 0; a < n_amb; ++a) {
+    PBtype n;
+    n.value = 0;
+    n.continue_count = 0;
+    S.rtk_phase_bias_variables[a * 2].push_back(n);
+    ptr[first_amb + a] = &S.rtk_phase_bias_variables[a * 2].back().value;
+  }
+  ptr[b_black2] = &S.blackvalue2;
+  for (int b = 0; b < g->n_blocks; ++b) {
+    if (!ptr[b]) return -3;  // composition A holds no other block
+    std::memcpy(ptr[b], g->state + g->block_offset[b], sizeof(double) * g->block_size[b]);
+  }
+  // frames: keyframes are the pose blocks some factor touches, the others are the hidden GNSS frames of the chains
+  std::vector<char> touched(g->n_blocks, 0);
+  for (int k = 0; k < 3 * g->n_proj; ++k) touched[g->proj_blocks[k]] = 1;
+  for (int k = 0; k < 4 * g->n_imu; ++k) touched[g->imu_blocks[k]] = 1;
+  for (int k = 0; k < g->chain_blk_begin[g->n_chain]; ++k) touched[g->chain_blocks[k]] = 1;
+  S.image_count = 0;
+  S.rover_count = 0;
+  std::vector<int> image_of_frame(F, -1);
+  for (int f = 0; f < F; ++f) {
+    if (touched[f]) {
+      S.frame_types[f] = SWFOptimization::ImagFrame;
+      image_of_frame[f] = S.image_count;
+      S.i2f[S.image_count++] = f;
+    } else {
+      S.frame_types[f] = SWFOptimization::GnssFrame;
+      mea_t* m = new mea_t();
+      std::memset((void*)m, 0, sizeof(mea_t));
+      S.rovers[S.rover_count] = m;
+      S.g2f[S.rover_count++] = f;
+    }
+  }
+  for (int i = 0; i < FEATURE_WINDOW_SIZE + 2; ++i) S.imu_gnss_factor[i] = nullptr;
+  // plain IMU links: pre_integrations[frame_j]
+  for (int i = 0; i < g->n_imu; ++i) {
+    const int fj = g->imu_blocks[4 * i + 2];
+    if (fj != g->imu_blocks[4 * i] + 1) return -4;
+    S.pre_integrations[fj] = (IntegrationBase*)swgn_ceres_refdemo_integration(g->imu_data + (size_t)SWGN_IMU_STRIDE * i);
+  }
+  // chains: IMUGNSSBase objects, members as AddMargInfo / SetLastImuFactor leave them
+  const int n_hidden = g->n_chain > 0 ? g->chain_frame_begin[g->n_chain] : 0;
+  std::vector<double>& hidden = *new std::vector<double>((size_t)16 * n_hidden);
+  std::vector<double>& hidden_lin = *new std::vector<double>((size_t)16 * n_hidden);
+  std::vector<IMUGNSSBase*> bases;
+  {
+    size_t fN = 0, cN = 0, imu = 0;
+    for (int c = 0; c < g->n_chain; ++c) {
+      const int b0 = g->chain_blk_begin[c], k = g->chain_blk_begin[c + 1] - b0 - 4;
+      const int f0 = g->chain_frame_begin[c], m = g->chain_frame_begin[c + 1] - f0;
+      const int fi = g->chain_blocks[b0], fj = g->chain_blocks[b0 + 2];
+      if (fj - fi != m + 1 || image_of_frame[fj] < 0) return -5;
+      IMUGNSSBase* B = new IMUGNSSBase(ptr[fi], ptr[F + fi], &S.my_problem);
+      bases.push_back(B);
+      for (int i = 0; i < m; ++i) {
+        const double* fr = g->chain_frame_data + (size_t)SWGN_CHAIN_FRAME_STRIDE * (f0 + i);
+        double* h = &hidden[(size_t)16 * (f0 + i)];
+        double* hl = &hidden_lin[(size_t)16 * (f0 + i)];
+        std::memcpy(h, fr + SWGN_CHAIN_POSE, sizeof(double) * 16);
+        std::memcpy(hl, fr + SWGN_CHAIN_POSE_LIN, sizeof(double) * 16);
+        B->gnss_poses.push_back(h);
+        B->gnss_speed_bias.push_back(h + 7);
+        B->gnss_poses_lin.push_back(hl);
+        B->gnss_speed_bias_lin.push_back(hl + 7);
+        Eigen::Matrix<double, 15, 15, Eigen::RowMajor> H;
+        Eigen::Matrix<double, 15, 1, Eigen::ColMajor> rhs;
+        Eigen::Matrix<double, 15, Eigen::Dynamic, Eigen::RowMajor> HN(15, k);
+        for (int a = 0; a < 15; ++a) {
+          rhs(a) = fr[SWGN_CHAIN_RHS + a];
+          for (int q = 0; q < 15; ++q) H(a, q) = fr[SWGN_CHAIN_HESSIAN + 15 * a + q];
+          for (int q = 0; q < k; ++q) HN(a, q) = g->chain_frame_N[fN + ((size_t)i * 15 + a) * k + q];
+        }
+        B->pose_hessians.push_back(H);
+        B->pose_rhses.push_back(rhs);
+        B->pose_phase_biases_hessians.push_back(HN);
+        // every frame of the estimator has its pre-integration from the frame before (AddAllResidual reads all of them)
+        S.pre_integrations[fi + 1 + i] = (IntegrationBase*)swgn_ceres_refdemo_integration(g->chain_imu_data + (size_t)SWGN_IMU_STRIDE * (imu + i));
+        B->imu_factors.push_back(new IMUFactor(S.pre_integrations[fi + 1 + i]));
+      }
+      S.pre_integrations[fj] = (IntegrationBase*)swgn_ceres_refdemo_integration(g->chain_imu_data + (size_t)SWGN_IMU_STRIDE * (imu + m));
+      B->last_imu_factor = new IMUFactor(S.pre_integrations[fj]);
+      B->pose1_pose2_hessians.setZero();
+      B->phase_biases_hessians.resize(k, k);
+      B->phase_biases_rhs.resize(k);
+      B->param = {ptr[fi], ptr[F + fi], ptr[fj], ptr[F + fj]};
+      for (int a = 0; a < k; ++a) {
+        B->phase_biases_rhs(a) = g->chain_N[cN + (size_t)k * k + a];
+        for (int q = 0; q < k; ++q) B->phase_biases_hessians(a, q) = g->chain_N[cN + (size_t)a * k + q];
+        B->gnss_phase_biases.push_back(ptr[g->chain_blocks[b0 + 4 + a]]);
+        B->param.push_back(ptr[g->chain_blocks[b0 + 4 + a]]);
+      }
+      B->gnss_Index = m;
+      B->Init();
+      S.imu_gnss_factor[image_of_frame[fj]] = B;  // the gap that ends at image image_of_frame[fj] (swf_core.cpp:224-240)
+      fN += (size_t)m * 15 * k;
+      cN += (size_t)k * k + k;
+      imu += m + 1;
+    }
+  }
+  // visual features: observations of landmark l on consecutive images from its first one
+  {
+    std::vector<std::vector<std::pair<int, int>>> obs(n_lm);  // (image index, projection factor)
+    for (int i = 0; i < g->n_proj; ++i) {
+      const int f = g->proj_blocks[3 * i], l = g->proj_blocks[3 * i + 2] - b_lm;
+      obs[l].push_back({image_of_frame[f], i});
+    }
+    int l = 0;
+    for (auto& feat : S.f_manager.feature) {
+      std::sort(obs[l].begin(), obs[l].end());
+      if (!obs[l].empty()) {
+        feat.start_frame = obs[l][0].first;
+        for (size_t q = 0; q < obs[l].size(); ++q) {
+          if (obs[l][q].first != feat.start_frame + (int)q) return -6;  // the reference walks consecutive images
+          Eigen::Matrix<double, 7, 1> pt;
+          pt.setZero();
+          pt(0) = g->proj_uv[2 * obs[l][q].second];
+          pt(1) = g->proj_uv[2 * obs[l][q].second + 1];
+          pt(2) = 1.0;
+          feat.feature_per_frame.push_back(FeaturePerFrame(pt));
+        }
+      }
+      ++l;
+    }
+  }
+  // the marginalisation prior
+  if (g->n_prior != 1) return -7;
+  {
+    MarginalizationInfo* M = new MarginalizationInfo();
+    const int n = g->prior_n[0];
+    M->n = n;
+    M->m = 0;
+    std::vector<double>& lin = *new std::vector<double>();
+    const double* x0 = g->prior_x0 + g->prior_x0_begin[0];
+    int nx = 0;
+    for (int k = g->prior_blk_begin[0]; k < g->prior_blk_begin[1]; ++k) nx += g->block_size[g->prior_blocks[k]];
+    lin.assign(x0, x0 + nx);
+    int xo = 0;
+    for (int k = g->prior_blk_begin[0]; k < g->prior_blk_begin[1]; ++k) {
+      const int b = g->prior_blocks[k];
+      M->keep_block_size.push_back(g->block_size[b]);
+      M->keep_block_idx.push_back(g->prior_blk_idx[k]);
+      M->keep_block_data.push_back(lin.data() + xo);
+      M->keep_block_addr.push_back(ptr[b]);
+      xo += g->block_size[b];
+    }
+    M->linearized_jacobians.resize(n, n);
+    M->linearized_residuals = Eigen::VectorXd(n);
+    for (int a = 0; a < n; ++a) {
+      M->linearized_residuals(a) = g->prior_r0[g->prior_r_begin[0] + a];
+      for (int c = 0; c < n; ++c) M->linearized_jacobians(a, c) = g->prior_J[g->prior_J_begin[0] + (size_t)a * n + c];
+    }
+    S.last_marg_info = M;
+  }
+  ceres::internal::parameter_head.clear();
+  for (int k = 0; k < so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(ptr[first_amb + k]);
+  ceres::internal::is_optimize = true;
+  {
+    ceres::Problem problem;
+    ceres::Solver::Options options;
+    S.AddAllResidual(SWFOptimization::NormalMode, std::set<double*>{}, nullptr, problem, options, true, true, true);
+  }
+  ceres::internal::parameter_head.clear();
+  for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], ptr[b], sizeof(double) * g->block_size[b]);
+  *n_frames_out = n_hidden;
+  if (chain_frames_out) std::memcpy(chain_frames_out, hidden.data(), sizeof(double) * hidden.size());
+  swgn_synth_destroy(W);
+  USE_IMAGE = false;
+  NUM_OF_CAM = 0;
+  return 0;
+}

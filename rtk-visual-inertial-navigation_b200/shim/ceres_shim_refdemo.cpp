@@ -376,3 +376,19 @@ extern "C" void swgn_ceres_refdemo_set_build_hooks(double* (*block_memory)(int, 
   g_refdemo_block_memory = block_memory;
   g_refdemo_before_solve = before_solve;
 }
+// pieces of the window builder for callers that assemble the problem themselves (oracle/ref_estimator_shim.cpp lets the
+// reference's own AddAllResidual do it): adapters + application globals of graph g, and a pre-integration object from a record
+extern "C" void swgn_ceres_refdemo_prepare(const swgn_graph* g) {
+  register_adapters();
+  Pbg = Eigen::Vector3d(g->Pbg[0], g->Pbg[1], g->Pbg[2]);
+  Rwgw = Eigen::Matrix3d::Identity();
+  G = Eigen::Vector3d(g->gravity[0], g->gravity[1], g->gravity[2]);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) projection_factor::sqrt_info(i, j) = g->proj_sqrt_info[2 * i + j];
+  ceres::swgn::Globals gl;
+  std::memcpy(gl.Pbg, g->Pbg, sizeof(gl.Pbg));
+  std::memcpy(gl.gravity, g->gravity, sizeof(gl.gravity));
+  std::memcpy(gl.proj_sqrt_info, g->proj_sqrt_info, sizeof(gl.proj_sqrt_info));
+  ceres::swgn::SetGlobals(gl);
+}
+extern "C" void* swgn_ceres_refdemo_integration(const double* record) { return integration_from_record(record); }

@@ -319,3 +319,34 @@ def test_reference_my_ordering_executed_on_a_composition_a_window(which, wid):
     b.close()
     assert (steps[0], steps[1]) == (sm.num_successful_steps, sm.num_unsuccessful_steps)
     assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(_REF_EST), reason="oracle/_ref not built")
+@pytest.mark.parametrize("which,wid", [(4, 0), (4, 5), (3, 2)])
+def test_reference_add_all_residual_builds_and_solves_the_window(which, wid):
+    """SWFOptimization::AddAllResidual(NormalMode) (RVI/swf/swf_core.cpp:209-415, unmodified) executed on an estimator
+    filled with a composition-A window: the reference's own loop adds the marginalisation prior, the IMU links, the
+    IMUGNSSFactor of every gap and the projection factors to a ceres::Problem (the shim's), sets the solver options, calls
+    MyOrdering and ceres::Solve.  The states it leaves in para_pose / para_speed_bias / ptsInWorld / the ambiguity lists,
+    and in the hidden GNSS frames of the IMUGNSSBase objects, are those of the C-ABI solve of the flat graph."""
+    L = C.CDLL(_REF_EST)
+    L.ref_est_add_all_residual.argtypes = [C.c_int, C.c_uint64, C.c_int, C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_int32)]
+    w = swgn.SynthWindow(which, wid)
+    g = w.graph
+    state = np.zeros(w.n_state)
+    n_hidden = g.chain_frame_begin[g.n_chain]
+    frames = np.zeros((n_hidden, 16))
+    nf = C.c_int32()
+    rc = L.ref_est_add_all_residual(which, wid, w.n_state, state.ctypes.data_as(C.POINTER(f64)), frames.ctypes.data_as(C.POINTER(f64)), C.byref(nf))
+    assert rc == 0 and nf.value == n_hidden
+    assert np.abs(state - w.state0()).max() > 1e-6            # the solve ran
+    opt = w.options()
+    opt.max_num_iterations = 8                                 # what NormalMode sets (swf_core.cpp:397-401)
+    b = swgn.Batch([w.graph_p], opt)
+    b.solve()
+    x = b.get_state(0, w.n_state)
+    hf = b.chain_frames(0)
+    b.close()
+    assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9
+    assert float(np.max(np.abs(hf - frames) / np.maximum(1.0, np.abs(frames)))) < 1e-9
