@@ -21,10 +21,10 @@ for _ in range(2):
     b.solve()
 L = swgn.lib()
 L.swgn_batch_debug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
-out = np.zeros(16 * n, np.int64)
+out = np.zeros(24 * n, np.int64)
 assert L.swgn_batch_debug_timeline(b.h, out.ctypes.data_as(C.POINTER(C.c_int64))) == 0
 t = out[:8 * n].reshape(n, 8)
-tc = out[8 * n:].reshape(n, 8)
+tc = out[8 * n:16 * n].reshape(n, 8)
 names = ["P0 zero", "P1a chunks", "wait barrier", "P1b rows", "P2 gather", "tail barrier"]
 d = np.diff(t[:, :7], axis=1).astype(float)
 print("per-CTA phase durations [cycles]: median / p90 / max")
