@@ -148,7 +148,12 @@ __global__ void __launch_bounds__(kThreads) k_begin(DeviceBatch b, int tick) {
 // (trust_region_minimizer.cc:414-431), invalid-step handling (:453-486) and the candidate point
 // x [+] step (:761-779).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_step(DeviceBatch b) {
+// 6 CTAs/SM (40 registers, 0.3 KB of spills in the scalar dogleg code of thread 0): the row pass is bound by the
+// latency of its index chain, measured 213.4 / 214.1 / 215.0 / 214.6 k it/s at 4 / 5 / 6 / 8 CTAs per SM
+#ifndef SWGN_STEP_CTAS
+#define SWGN_STEP_CTAS 6
+#endif
+__global__ void __launch_bounds__(kThreads, SWGN_STEP_CTAS) k_step(DeviceBatch b) {
   __shared__ WinDesc sd;
   __shared__ double red[33];
   __shared__ double s_c[4];
