@@ -512,16 +512,27 @@ extern "C" int ref_est_my_ordering(int which, uint64_t window_id, int cap_blocks
 // composition-A synthetic window (its flat graph only serves as the source of the numbers).
 extern "C" void swgn_ceres_refdemo_prepare(const swgn_graph* g);
 extern "C" void* swgn_ceres_refdemo_integration(const double* record);
-extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_state, double* state_out, double* chain_frames_out,
-                                        int32_t* n_frames_out) {
+namespace {
+// An estimator filled from a composition-A synthetic window (see ref_est_add_all_residual)
+struct FilledEstimator {
+  swgn_synth* W = nullptr;
+  const swgn_graph* g = nullptr;
+  swgn_options so;
+  SWFOptimization* S = nullptr;
+  std::vector<double*> ptr;         // block -> estimator storage
+  std::vector<double>* hidden = nullptr;
+  int n_hidden = 0, F = 0, n_lm = 0, b_lm = 0;
+  std::vector<int> image_of_frame;
+};
+int fill_estimator(int which, uint64_t window_id, int cap_state, FilledEstimator& X) {
+
   swgn_synth_config cfg;
   swgn_synth_default_config(which, &cfg);
   if (cfg.composition != 1) return -1;
-  swgn_synth* W = swgn_synth_create(&cfg, window_id);
+  swgn_synth* W = X.W = swgn_synth_create(&cfg, window_id);
   if (!W) return -1;
-  const swgn_graph* g = swgn_synth_graph(W);
-  swgn_options so;
-  swgn_synth_options(W, &so);
+  const swgn_graph* g = X.g = swgn_synth_graph(W);
+  swgn_synth_options(W, &X.so);
   int32_t info[8];
   swgn_synth_info(W, info);
   if (g->n_state > cap_state) return -2;
@@ -532,14 +543,15 @@ extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_s
     if (g->block_size[b] == 3) n_lm++;
   }
   const int b_ext = 2 * F, b_lm = 2 * F + 1, first_amb = info[5], n_amb = info[4], b_black2 = g->n_blocks - 1;
-  SWFOptimization& S = *new SWFOptimization();
+  SWFOptimization& S = *(X.S = new SWFOptimization());
   USE_IMAGE = true;
   USE_GLOBAL_OPTIMIZATION = false;
   USE_MAG_CORRECT_YAW = false;
   NUM_OF_CAM = 1;
   ESTIMATE_EXTRINSIC = 0;
   // block -> estimator storage
-  std::vector<double*> ptr(g->n_blocks, nullptr);
+  std::vector<double*>& ptr = X.ptr;
+  ptr.assign(g->n_blocks, nullptr);
   for (int f = 0; f < F; ++f) {
     ptr[f] = S.para_pose[f];
     ptr[F + f] = S.para_speed_bias[f];
@@ -568,7 +580,8 @@ extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_s
   for (int k = 0; k < g->chain_blk_begin[g->n_chain]; ++k) touched[g->chain_blocks[k]] = 1;
   S.image_count = 0;
   S.rover_count = 0;
-  std::vector<int> image_of_frame(F, -1);
+  std::vector<int>& image_of_frame = X.image_of_frame;
+  image_of_frame.assign(F, -1);
   for (int f = 0; f < F; ++f) {
     if (touched[f]) {
       S.frame_types[f] = SWFOptimization::ImagFrame;
@@ -591,7 +604,7 @@ extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_s
   }
   // chains: IMUGNSSBase objects, members as AddMargInfo / SetLastImuFactor leave them
   const int n_hidden = g->n_chain > 0 ? g->chain_frame_begin[g->n_chain] : 0;
-  std::vector<double>& hidden = *new std::vector<double>((size_t)16 * n_hidden);
+  std::vector<double>& hidden = *(X.hidden = new std::vector<double>((size_t)16 * n_hidden));
   std::vector<double>& hidden_lin = *new std::vector<double>((size_t)16 * n_hidden);
   std::vector<IMUGNSSBase*> bases;
   {
@@ -702,20 +715,103 @@ extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_s
     }
     S.last_marg_info = M;
   }
+  X.n_hidden = n_hidden;
+  X.F = F;
+  X.n_lm = n_lm;
+  X.b_lm = b_lm;
+  return 0;
+}
+void release_estimator(FilledEstimator& X) {
   ceres::internal::parameter_head.clear();
-  for (int k = 0; k < so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(ptr[first_amb + k]);
+  ceres::internal::is_optimize = true;
+  swgn_synth_destroy(X.W);
+  USE_IMAGE = false;
+  NUM_OF_CAM = 0;
+}
+}  // namespace
+
+extern "C" int ref_est_add_all_residual(int which, uint64_t window_id, int cap_state, double* state_out, double* chain_frames_out,
+                                        int32_t* n_frames_out) {
+  FilledEstimator X;
+  const int rc = fill_estimator(which, window_id, cap_state, X);
+  if (rc) return rc;
+  SWFOptimization& S = *X.S;
+  const swgn_graph* g = X.g;
+  int32_t info[8];
+  swgn_synth_info(X.W, info);
+  ceres::internal::parameter_head.clear();
+  for (int k = 0; k < X.so.n_parameter_head; ++k) ceres::internal::parameter_head.push_back(X.ptr[info[5] + k]);
   ceres::internal::is_optimize = true;
   {
     ceres::Problem problem;
     ceres::Solver::Options options;
     S.AddAllResidual(SWFOptimization::NormalMode, std::set<double*>{}, nullptr, problem, options, true, true, true);
   }
-  ceres::internal::parameter_head.clear();
-  for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], ptr[b], sizeof(double) * g->block_size[b]);
-  *n_frames_out = n_hidden;
-  if (chain_frames_out) std::memcpy(chain_frames_out, hidden.data(), sizeof(double) * hidden.size());
-  swgn_synth_destroy(W);
-  USE_IMAGE = false;
-  NUM_OF_CAM = 0;
+  for (int b = 0; b < g->n_blocks; ++b) std::memcpy(state_out + g->block_offset[b], X.ptr[b], sizeof(double) * g->block_size[b]);
+  *n_frames_out = X.n_hidden;
+  if (chain_frames_out) std::memcpy(chain_frames_out, X.hidden->data(), sizeof(double) * X.hidden->size());
+  release_estimator(X);
   return 0;
+}
+
+// SWFOptimization::AddAllResidual(MargeIncludeMode2) (RVI/swf/swf_core.cpp:209-468), the marginalisation of the oldest image
+// frame as MargFrames runs it (RVI/swf/swf.cpp:343-364): MargePoint = the frame's pose and speed-bias and every landmark whose
+// track starts there.  The reference code collects the factors touching them, appends the blocks to keep to
+// ceres::internal::parameter_head, calls MyOrdering, ceres::Solve (export mode), UpdateSchur and
+// MarginalizationInfo::setmarginalizeinfo / getParameterBlocks.  Returns the new prior: drop flags per block, the keep blocks
+// (graph block index, first column) in the reference's order, linearized_jacobians (n x n row-major), linearized_residuals.
+extern "C" int ref_est_marginalize_oldest(int which, uint64_t window_id, int cap_n, uint8_t* drop_out, int32_t* n_out, int32_t* n_keep_out,
+                                          int32_t* keep_block_out, int32_t* keep_idx_out, double* J0_out, double* r0_out) {
+  FilledEstimator X;
+  const int rc = fill_estimator(which, window_id, 1 << 30, X);
+  if (rc) return rc;
+  SWFOptimization& S = *X.S;
+  const swgn_graph* g = X.g;
+  std::set<double*> marge{S.para_pose[0], S.para_speed_bias[0]};
+  std::memset(drop_out, 0, g->n_blocks);
+  drop_out[0] = drop_out[X.F] = 1;
+  {
+    int l = 0;
+    for (auto& feat : S.f_manager.feature) {
+      if ((int)feat.feature_per_frame.size() >= FEATURE_CONTINUE && feat.start_frame == 0) {
+        marge.insert(feat.ptsInWorld.data());
+        drop_out[X.b_lm + l] = 1;
+      }
+      ++l;
+    }
+  }
+  ceres::internal::parameter_head.clear();
+  ceres::internal::is_optimize = true;
+  MarginalizationInfo* M = new MarginalizationInfo();
+  {
+    ceres::Problem problem;
+    ceres::Solver::Options options;
+    S.AddAllResidual(SWFOptimization::MargeIncludeMode2, marge, M, problem, options, true, true, true);
+  }
+  int ret = 0;
+  if (S.last_marg_info != M) {
+    ret = -10;
+  } else {
+    const int n = (int)M->linearized_jacobians.rows();
+    *n_out = n;
+    *n_keep_out = (int32_t)M->keep_block_addr.size();
+    if (n > cap_n || n != (int)M->linearized_jacobians.cols()) {
+      ret = -11;
+    } else {
+      for (size_t k = 0; k < M->keep_block_addr.size(); ++k) {
+        int b = -1;
+        for (int q = 0; q < g->n_blocks; ++q)
+          if (X.ptr[q] == M->keep_block_addr[k]) b = q;
+        if (b < 0 || M->keep_block_size[k] != g->block_size[b]) ret = -12;
+        keep_block_out[k] = b;
+        keep_idx_out[k] = M->keep_block_idx[k];
+      }
+      for (int a = 0; a < n; ++a) {
+        r0_out[a] = M->linearized_residuals(a);
+        for (int c = 0; c < n; ++c) J0_out[(size_t)a * n + c] = M->linearized_jacobians(a, c);
+      }
+    }
+  }
+  release_estimator(X);
+  return ret;
 }

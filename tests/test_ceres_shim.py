@@ -350,3 +350,86 @@ def test_reference_add_all_residual_builds_and_solves_the_window(which, wid):
     b.close()
     assert float(np.max(np.abs(x - state) / np.maximum(1.0, np.abs(state)))) < 1e-9
     assert float(np.max(np.abs(hf - frames) / np.maximum(1.0, np.abs(frames)))) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(_REF_EST), reason="oracle/_ref not built")
+@pytest.mark.parametrize("which,wid", [(4, 0), (4, 1), (3, 0)])
+def test_reference_marginalisation_of_the_oldest_frame_through_the_shim(which, wid):
+    """SWFOptimization::AddAllResidual(MargeIncludeMode2) (RVI/swf/swf_core.cpp:209-468, unmodified), the marginalisation of the
+    oldest image frame as MargFrames runs it (RVI/swf/swf.cpp:343-364), executed on an estimator filled with a composition-A
+    window: the reference's code collects the factors that touch the frame's pose, speed-bias and the landmarks whose tracks start
+    there, appends the blocks to keep to parameter_head, calls MyOrdering, ceres::Solve in export mode (the shim, on the device),
+    UpdateSchur and MarginalizationInfo::setmarginalizeinfo.  The information (J0'J0, J0'r0) of the prior it ends with equals the
+    one the C ABI returns for the same factors, the same drop set and the extrinsic free as in that mode
+    (AddParameter2Problem(problem, true), swf_core.cpp:365)."""
+    L = C.CDLL(_REF_EST)
+    i32, P = C.c_int32, C.POINTER
+    L.ref_est_marginalize_oldest.argtypes = [C.c_int, C.c_uint64, C.c_int, P(C.c_uint8), P(i32), P(i32), P(i32), P(i32), P(f64), P(f64)]
+    w = swgn.SynthWindow(which, wid)
+    g0 = w.graph
+    nb, cap = g0.n_blocks, 1024
+    drop = np.zeros(nb, np.uint8)
+    n, nk = i32(), i32()
+    kb, ki = np.zeros(nb, np.int32), np.zeros(nb, np.int32)
+    J, r = np.zeros(cap * cap), np.zeros(cap)
+    rc = L.ref_est_marginalize_oldest(which, wid, cap, drop.ctypes.data_as(P(C.c_uint8)), C.byref(n), C.byref(nk), kb.ctypes.data_as(P(i32)),
+                                      ki.ctypes.data_as(P(i32)), J.ctypes.data_as(P(f64)), r.ctypes.data_as(P(f64)))
+    assert rc == 0
+    n, nk = n.value, nk.value
+    kb, ki = kb[:nk], ki[:nk]
+    Jr, rr = J[:n * n].reshape(n, n), r[:n]
+    assert drop.sum() > 2 and nk > 3
+    # ---- the same marginalisation through the C ABI
+    g = swgn.Graph()
+    C.memmove(C.byref(g), w.graph_p, C.sizeof(swgn.Graph))
+    sizes = np.array([g.block_size[b] for b in range(nb)])
+    F = int((sizes == 9).sum())
+    touching = lambda blocks: any(drop[b] for b in blocks)
+    pj = [i for i in range(g.n_proj) if touching(g.proj_blocks[3 * i:3 * i + 3])]
+    im = [i for i in range(g.n_imu) if touching(g.imu_blocks[4 * i:4 * i + 4])]
+    assert g.n_gnss == 0 and g.n_host == 0 and 0 < len(pj) < g.n_proj and len(im) == 1
+    # only the factors that touch a dropped block (and the prior, the unit factor) enter the problem; the chains touch none
+    proj_blocks = np.array([g.proj_blocks[3 * i + k] for i in pj for k in range(3)], np.int32)
+    proj_uv = np.array([g.proj_uv[2 * i + k] for i in pj for k in range(2)])
+    imu_blocks = np.array([g.imu_blocks[4 * i + k] for i in im for k in range(4)], np.int32)
+    imu_data = np.concatenate([np.ctypeslib.as_array(g.imu_data, ((g.n_imu * 474),))[474 * i:474 * (i + 1)] for i in im]).copy()
+    g.n_proj, g.proj_blocks, g.proj_uv = len(pj), proj_blocks.ctypes.data_as(P(i32)), proj_uv.ctypes.data_as(P(f64))
+    g.n_imu, g.imu_blocks, g.imu_data = len(im), imu_blocks.ctypes.data_as(P(i32)), imu_data.ctypes.data_as(P(f64))
+    g.n_chain = 0
+    touched = np.zeros(nb, bool)
+    touched[proj_blocks] = True
+    touched[imu_blocks] = True
+    touched[[g.prior_blocks[k] for k in range(g.prior_blk_begin[g.n_prior])]] = True
+    konst = np.array([g.block_const[b] for b in range(nb)], np.int32)
+    konst[2 * F] = 0                                   # the extrinsic is left variable in this mode
+    keep = [b for b in range(nb) if touched[b] and not drop[b] and not konst[b] and b != nb - 1]
+    assert sorted(keep) == sorted(kb.tolist())         # the reference kept the same blocks
+    group = np.zeros(nb, np.int32)
+    group[0], group[F] = 2, 1                          # pose and speed-bias of the frame; its landmarks stay in group 0
+    for k, b in enumerate(keep):
+        group[b] = 3 + k
+    g.block_const = konst.ctypes.data_as(P(i32))
+    g.block_group = group.ctypes.data_as(P(i32))
+    g.is_use = None
+    g.n_order, g.order = 0, None
+    opt = w.options()
+    opt.is_optimize, opt.max_num_iterations, opt.n_parameter_head = 0, 1, len(keep)
+    b = swgn.Batch([C.pointer(g)], opt)
+    b.solve()
+    cb, co, cs = b.columns(0)
+    assert list(cb[len(cb) - len(keep):]) == keep
+    J0, r0, A, bv = b.marginal_prior(0, n)
+    b.close()
+    # ---- same information, the reference's block order mapped onto the device's
+    tang = {b_: (6 if sizes[b_] == 7 else int(sizes[b_])) for b_ in keep}
+    dev_off, o = {}, 0
+    for b_ in keep:
+        dev_off[b_] = o
+        o += tang[b_]
+    assert o == n
+    perm = np.concatenate([np.arange(dev_off[b_], dev_off[b_] + tang[b_]) for b_ in kb[np.argsort(ki)]])
+    Ar, br = Jr.T @ Jr, Jr.T @ rr
+    Ad, bd = (J0.T @ J0)[np.ix_(perm, perm)], (J0.T @ r0)[perm]
+    assert np.abs(Ar - Ad).max() < 1e-9 * np.abs(Ad).max(), np.abs(Ar - Ad).max() / np.abs(Ad).max()   # measured 3e-12 .. 6e-12
+    assert np.abs(br - bd).max() < 1e-9 * max(1.0, np.abs(bd).max()), np.abs(br - bd).max()                 # measured 1e-11 .. 7e-11
