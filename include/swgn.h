@@ -467,8 +467,9 @@ swgn_status swgn_ambiguity_fix(int32_t device, int32_t n, const double* A, const
    eigen pseudo-inverse (eigenvalues <= 1e-8 dropped) and the remaining information becomes the prior r = r0 + J0 (x [-] x0)
    over the keep blocks (block-index order; x0 = the graph's state).  On the device this is one export-mode pass per call for
    all graphs -- drop blocks ordered before the keep blocks in the reduced system, which swgn_batch_get_marginal_priors then
-   reduces and square-roots.  Restrictions: block_group is ignored, no constant blocks, order / is_use / chains / host
-   factors must be absent, every block must be touched by a factor, at least one keep block. */
+   reduces and square-roots.  block_group is ignored; constant blocks stay constants of their factors and blocks no factor touches take
+   no part (neither is a keep block).  Restrictions: order / is_use / chains / host factors must be absent, at least one keep
+   block. */
 typedef struct swgn_marginalize_output {
   int32_t cap_keep, cap_n;   /* capacities of the caller's buffers                                  */
   int32_t n_keep, n, m;      /* keep blocks, their tangent size, tangent size of the dropped blocks */

@@ -40,15 +40,26 @@ extern "C" swgn_status swgn_marginalize(int32_t device, int32_t n_graphs, const 
     const int nb = g->n_blocks;
     Q.size.assign(g->block_size, g->block_size + nb);
     Q.manifold.assign(g->block_manifold, g->block_manifold + nb);
-    Q.konst.assign(nb, 0);
+    Q.konst.assign(g->block_const, g->block_const + nb);
     Q.group.resize(nb);
     Q.offset.assign(g->block_offset, g->block_offset + nb);
     Q.state.assign(g->state, g->state + g->n_state);
+    // blocks no factor touches take no part (the reference only ever sees the blocks of the residual blocks it was given)
+    std::vector<char> touched(nb, 0);
+    auto touch = [&](const int32_t* blocks, int64_t count) {
+      for (int64_t k = 0; k < count; ++k)
+        if (blocks[k] >= 0 && blocks[k] < nb) touched[blocks[k]] = 1;
+    };
+    touch(g->proj_blocks, (int64_t)3 * g->n_proj);
+    touch(g->imu_blocks, (int64_t)4 * g->n_imu);
+    touch(g->gnss_blocks, (int64_t)3 * g->n_gnss);
+    if (g->n_prior > 0) touch(g->prior_blocks, g->prior_blk_begin[g->n_prior]);
+    touch(g->unit_block, g->n_unit);
     int n = 0, m = 0, nk = 0;
     for (int b = 0; b < nb; ++b) {
-      if (g->block_const[b]) return set_error(SWGN_ERR_UNSUPPORTED, tag + "constant blocks are not supported here");
       const int t = g->block_manifold[b] == SWGN_MANIFOLD_POSE ? 6 : g->block_size[b];
       Q.group[b] = drop[w][b] ? 1 : 2;
+      if (g->block_const[b] || !touched[b]) continue;  // constant: stays a constant of the factors; untouched: not in the problem
       if (drop[w][b]) {
         m += t;
       } else {
@@ -106,7 +117,7 @@ extern "C" swgn_status swgn_marginalize(int32_t device, int32_t n_graphs, const 
     int64_t nj = 0, nr = 0;
     for (int w = 0; w < n_graphs; ++w) {
       if (sums[w].n_f != outputs[w].n + outputs[w].m) {
-        st = set_error(SWGN_ERR_INVALID, "graph " + std::to_string(w) + ": a block is not touched by any factor");
+        st = set_error(SWGN_ERR_INVALID, "graph " + std::to_string(w) + ": internal: reduced system size differs from the drop and keep blocks");
         break;
       }
       n_tail[w] = outputs[w].n;

@@ -421,6 +421,14 @@ def test_reference_marginalisation_of_the_oldest_frame_through_the_shim(which, w
     assert list(cb[len(cb) - len(keep):]) == keep
     J0, r0, A, bv = b.marginal_prior(0, n)
     b.close()
+    # swgn_marginalize on the same factors: constant and untouched blocks take no part, the keep blocks come in block order
+    # (blackvalue2, which MyOrdering eliminates in group 0, is dropped explicitly)
+    drop2 = drop.copy()
+    drop2[nb - 1] = 1
+    (mkb, mki, mJ, mr, mm), = swgn.marginalize([C.pointer(g)], [drop2])
+    assert list(mkb) == keep and mJ.shape == (n, n)
+    assert np.abs(mJ.T @ mJ - J0.T @ J0).max() < 1e-9 * np.abs(J0.T @ J0).max()
+    assert np.abs(mJ.T @ mr - J0.T @ r0).max() < 1e-9 * max(1.0, np.abs(J0.T @ r0).max())
     # ---- same information, the reference's block order mapped onto the device's
     tang = {b_: (6 if sizes[b_] == 7 else int(sizes[b_])) for b_ in keep}
     dev_off, o = {}, 0
