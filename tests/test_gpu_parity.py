@@ -752,8 +752,9 @@ def _plain_copy(w):
     return g, free
 
 
-@pytest.mark.parametrize("which,overrides", [(1, {}), (2, dict(n_keyframes=6, n_landmarks=40, n_gnss_epochs=3, n_sats=8))])
-def test_marginalize_with_an_arbitrary_drop_set_matches_the_oracle(which, overrides):
+@pytest.mark.parametrize("which,overrides,drop_nothing", [(1, {}, False), (2, dict(n_keyframes=6, n_landmarks=40, n_gnss_epochs=3, n_sats=8), False),
+                                                          (1, dict(n_keyframes=3, n_landmarks=12), True)])
+def test_marginalize_with_an_arbitrary_drop_set_matches_the_oracle(which, overrides, drop_nothing):
     """swgn_marginalize = MarginalizationInfo::marginalize + getParameterBlocks (marginalization_factor.cpp:260-400) as MargFrames
     uses it: drop the oldest frame's pose and speed-bias and the first landmarks, keep everything else.  The oracle side is
     the restated MarginalizationInfo that tests/test_gnss_epoch.py pins on the reference's own class."""
@@ -763,10 +764,11 @@ def test_marginalize_with_an_arbitrary_drop_set_matches_the_oracle(which, overri
     for w, (g, _) in zip(ws, copies):
         drop = np.zeros(g.n_blocks, np.uint8)
         sizes = [g.block_size[b] for b in range(g.n_blocks)]
-        drop[sizes.index(7)] = 1                      # first pose
-        drop[sizes.index(9)] = 1                      # first speed-bias
-        lms = [b for b in range(g.n_blocks) if sizes[b] == 3][:8]
-        drop[lms] = 1
+        if not drop_nothing:                          # (nothing dropped: the square root of the whole information, as
+            drop[sizes.index(7)] = 1                  #  InitializeSqrtInfo builds the first prior, swf_core.cpp:479-543)
+            drop[sizes.index(9)] = 1                  # first pose, first speed-bias
+            lms = [b for b in range(g.n_blocks) if sizes[b] == 3][:8]
+            drop[lms] = 1
         gps.append(C.pointer(g))
         drops.append(drop)
     got = swgn.marginalize(gps, drops)
