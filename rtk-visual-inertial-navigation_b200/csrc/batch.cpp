@@ -44,6 +44,21 @@ swgn_status fail(swgn_status st, const std::string& m) {
 namespace swgn {
 // other translation units of the library (gnss_epoch.cpp) report through the same thread-local message
 swgn_status set_error(swgn_status st, const std::string& m) { return fail(st, m); }
+// The device's default memory pool releases what is unused at every synchronisation (release threshold 0), so a call that
+// takes its scratch with cudaMallocAsync re-grows the pool each time: 50-70 ms per 80 MB, and now and then a stall of
+// hundreds of ms when the release coincides with the next allocation.  Keep the pool's memory once it has grown.
+void keep_pool_memory(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[device] = true;
+}
 }  // namespace swgn
 namespace {
 
@@ -1337,6 +1352,7 @@ swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail,
   int32_t* dn = nullptr;
   std::vector<double> host;
   // stream-ordered allocations: no device-wide synchronisation per call
+  swgn::keep_pool_memory(b->device);
   cudaError_t e = cudaMallocAsync((void**)&dbuf, sizeof(double) * total, b->stream);
   if (e == cudaSuccess) e = cudaMallocAsync((void**)&doff, sizeof(int64_t) * off.size(), b->stream);
   if (e == cudaSuccess) e = cudaMallocAsync((void**)&dn, sizeof(int32_t) * b->n, b->stream);

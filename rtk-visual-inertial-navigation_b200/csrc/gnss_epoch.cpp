@@ -27,6 +27,7 @@
 
 namespace swgn {
 swgn_status set_error(swgn_status st, const std::string& m);
+void keep_pool_memory(int device);
 cudaError_t launch_gate_residuals(int n, const double* rec_dev, const int32_t* flags_dev, double azelmin, double* out_dev,
                                   cudaStream_t s);
 }  // namespace swgn
@@ -614,6 +615,7 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
     if (n_obs_all > 0) {
       // stream-ordered allocations: no device-wide synchronisation, the pool keeps the blocks for the next call
       cudaStream_t s = cudaStreamPerThread;
+      swgn::keep_pool_memory(cfg.device);
       cudaError_t e = cudaMallocAsync((void**)&d_rec, sizeof(double) * 16 * n_obs_all, s);
       if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_out, sizeof(double) * 3 * n_obs_all, s);
       if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_flags, sizeof(int32_t) * n_obs_all, s);
