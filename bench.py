@@ -291,12 +291,15 @@ def run_swgn(args, rank, local_rank, world):
     if args.composition == "B" and ws[0].n_amb > 0:
         epochs = swgn.Batch.pack_epochs([w.ambiguity_epochs() for w in ws])
         b.ambiguity_fix_all(ws[0].n_amb, epochs)
-        t0 = time.perf_counter()
-        res, _, _ = b.ambiguity_fix_all(ws[0].n_amb, epochs)
-        t_fix = time.perf_counter() - t0
-        cfg4 = {"windows": W, "n_ambiguities": int(ws[0].n_amb), "ms": 1e3 * t_fix, "windows_per_s": W / t_fix,
+        t_calls = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res, _, _ = b.ambiguity_fix_all(ws[0].n_amb, epochs)
+            t_calls.append(time.perf_counter() - t0)
+        t_fix = min(t_calls)
+        cfg4 = {"windows": W, "n_ambiguities": int(ws[0].n_amb), "ms": 1e3 * t_fix, "ms_calls": [round(1e3 * t, 2) for t in t_calls], "windows_per_s": W / t_fix,
                 "searched": sum(1 for i in range(W) if res[i].status == 0), "ratio_test_passed": sum(1 for i in range(W) if res[i].search_ok),
-                "note": "wall time of the C-ABI call incl. H2D of the epoch lists and D2H of the results"}
+                "note": "wall time of the C-ABI call incl. H2D of the epoch lists and D2H of the results; best of three calls"}
     # ---- strong-scaling leg (BASELINE configs[2] as written: `--windows` windows in total, sharded over the ranks)
     strong = None
     if world > 1:

@@ -1208,7 +1208,8 @@ swgn_status swgn_batch_ambiguity_fix(swgn_batch* b, int32_t n_tail, const int32_
   const size_t n_int = (size_t)nw * (1 + 2 * n + niw + 1) + (size_t)(nw + 1) + (size_t)(n_ep + 1) + 2 * (size_t)(n_obs + 1);
   const size_t bytes = sizeof(double) * n_dbl + sizeof(swgn_fix_result) * (size_t)nw + sizeof(int32_t) * n_int + 64;
   char* dbuf = nullptr;
-  CU(cudaMalloc(&dbuf, bytes));
+  swgn::keep_pool_memory(b->device);
+  CU(cudaMallocAsync((void**)&dbuf, bytes, s));  // stream-ordered: no device-wide synchronisation per call
   double* dA = reinterpret_cast<double*>(dbuf);
   double* dy = dA + (size_t)nw * n * n;
   double* dF = dy + (size_t)nw * n;
@@ -1238,8 +1239,8 @@ swgn_status swgn_batch_ambiguity_fix(swgn_batch* b, int32_t n_tail, const int32_
   if (e == cudaSuccess) e = cudaMemcpyAsync(results, dres, sizeof(swgn_fix_result) * (size_t)nw, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess && dd_pairs) e = cudaMemcpyAsync(dd_pairs, dpairs, sizeof(int32_t) * (size_t)nw * 2 * n, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess && F) e = cudaMemcpyAsync(F, dF, sizeof(double) * (size_t)nw * 2 * n, cudaMemcpyDeviceToHost, s);
+  cudaFreeAsync(dbuf, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(dbuf);
   CU(e);
   return SWGN_OK;
 }
