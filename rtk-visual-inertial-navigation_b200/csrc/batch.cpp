@@ -1316,10 +1316,22 @@ swgn_status swgn_batch_get_marginal_prior(swgn_batch* b, int32_t w, int32_t n_ta
   return SWGN_OK;
 }
 
-swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail, const int64_t* j_off, const int64_t* r_off, double* J0_all,
-                                           double* r0_all) {
-  if (!b || !n_tail || !j_off || !r_off || !J0_all || !r0_all) return fail(SWGN_ERR_INVALID, "bad arguments");
+}  // extern "C"
+namespace swgn {
+// UpdateSchur + setmarginalizeinfo of every window in two launches; (J0, r0) of window w land in J0_ptr[w] / r0_ptr[w]
+// (windows with n_tail[w] = 0 are skipped).  The results come back through a pinned staging slab (parked in the slab cache
+// between calls) in one copy and are scattered from there: the callers' buffers are pageable and separate per window.
+swgn_status batch_marginal_priors_to(swgn_batch* b, const int32_t* n_tail, double* const* J0_ptr, double* const* r0_ptr) {
+  if (!b || !n_tail || !J0_ptr || !r0_ptr) return fail(SWGN_ERR_INVALID, "bad arguments");
   CU(cudaSetDevice(b->device));
+  const bool dbg_t = std::getenv("SWGN_DEBUG_TIMING") != nullptr;
+  auto t_mark = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!dbg_t) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[swgn_batch_get_marginal_priors] %-18s %6.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_mark).count());
+    t_mark = t;
+  };
   std::vector<TRState> t(b->n);
   CU(cudaMemcpy(t.data(), b->d_state, sizeof(TRState) * b->n, cudaMemcpyDeviceToHost));
   std::vector<int64_t> off((size_t)4 * b->n, 0);
@@ -1348,10 +1360,12 @@ swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail,
     total += (int64_t)std::max(head_marginal_scratch_doubles(m, n), prior_sqrt_scratch_doubles(n));
   }
   if (total == 0) return SWGN_OK;
+  mark("states + offsets");
   double* dbuf = nullptr;
   int64_t* doff = nullptr;
   int32_t* dn = nullptr;
-  std::vector<double> host;
+  void* hslab = nullptr;
+  size_t hcap = 0;
   // stream-ordered allocations: no device-wide synchronisation per call
   swgn::keep_pool_memory(b->device);
   cudaError_t e = cudaMallocAsync((void**)&dbuf, sizeof(double) * total, b->stream);
@@ -1360,23 +1374,45 @@ swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail,
   if (e == cudaSuccess) e = cudaMemcpyAsync(doff, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, b->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n_tail, sizeof(int32_t) * b->n, cudaMemcpyHostToDevice, b->stream);
   if (e == cudaSuccess) e = launch_marginal_priors(b->db, max_m, max_n, dn, doff, dbuf, b->stream);
-  if (e == cudaSuccess) {
-    host.resize((size_t)n_out);
-    e = cudaMemcpyAsync(host.data(), dbuf, sizeof(double) * n_out, cudaMemcpyDeviceToHost, b->stream);
+  if (dbg_t) {
+    mark("alloc + launch");
+    cudaStreamSynchronize(b->stream);
+    mark("kernels");
   }
+  if (e == cudaSuccess) e = slab_alloc(1, b->device, sizeof(double) * (size_t)n_out, &hslab, &hcap);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hslab, dbuf, sizeof(double) * n_out, cudaMemcpyDeviceToHost, b->stream);
   if (dbuf) cudaFreeAsync(dbuf, b->stream);
   if (doff) cudaFreeAsync(doff, b->stream);
   if (dn) cudaFreeAsync(dn, b->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
-  CU(e);
+  if (e != cudaSuccess) {
+    slab_free(1, b->device, hslab, hcap);
+    CU(e);
+  }
+  mark("read-back");
   for (int w = 0; w < b->n; ++w) {
     const int n = n_tail[w];
     if (n == 0) continue;
-    const double* src = host.data() + off[4 * w + 2];
-    std::memcpy(J0_all + j_off[w], src, sizeof(double) * (size_t)n * n);
-    std::memcpy(r0_all + r_off[w], src + (size_t)n * n, sizeof(double) * n);
+    const double* src = static_cast<const double*>(hslab) + off[4 * w + 2];
+    std::memcpy(J0_ptr[w], src, sizeof(double) * (size_t)n * n);
+    std::memcpy(r0_ptr[w], src + (size_t)n * n, sizeof(double) * n);
   }
+  slab_free(1, b->device, hslab, hcap);
+  mark("scatter");
   return SWGN_OK;
+}
+}  // namespace swgn
+extern "C" {
+
+swgn_status swgn_batch_get_marginal_priors(swgn_batch* b, const int32_t* n_tail, const int64_t* j_off, const int64_t* r_off, double* J0_all,
+                                           double* r0_all) {
+  if (!b || !n_tail || !j_off || !r_off || !J0_all || !r0_all) return fail(SWGN_ERR_INVALID, "bad arguments");
+  std::vector<double*> Jp(b->n), rp(b->n);
+  for (int w = 0; w < b->n; ++w) {
+    Jp[w] = J0_all + j_off[w];
+    rp[w] = r0_all + r_off[w];
+  }
+  return swgn::batch_marginal_priors_to(b, n_tail, Jp.data(), rp.data());
 }
 
 swgn_status swgn_batch_get_chain_frames(swgn_batch* b, int32_t w, int32_t* n_frames, double* frames) {

@@ -28,6 +28,7 @@
 namespace swgn {
 swgn_status set_error(swgn_status st, const std::string& m);
 void keep_pool_memory(int device);
+swgn_status batch_marginal_priors_to(swgn_batch* b, const int32_t* n_tail, double* const* J0_ptr, double* const* r0_ptr);
 cudaError_t launch_gate_residuals(int n, const double* rec_dev, const int32_t* flags_dev, double azelmin, double* out_dev,
                                   cudaStream_t s);
 }  // namespace swgn
@@ -781,10 +782,9 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
   lap("pass 1 create");
   st = swgn_batch_solve(batch, sums.data());
   lap("pass 1 solve");
-  if (st == SWGN_OK) {  // all priors in two launches; every J0 lands in its caller buffer through a staging block
+  if (st == SWGN_OK) {  // all priors in two launches; every (J0, r0) is scattered from one pinned staging block into its caller buffer
     std::vector<int32_t> n_tail(gi.size());
-    std::vector<int64_t> j_off(gi.size()), r_off(gi.size());
-    int64_t nj = 0, nr = 0;
+    std::vector<double*> Jp(gi.size()), rp(gi.size());
     for (size_t k = 0; k < gi.size(); ++k) {
       const swgn_gnss_output& O = outputs[gi[k]];
       if (sums[k].n_f != O.n) {
@@ -792,18 +792,10 @@ swgn_status swgn_gnss_preprocess(int32_t n, swgn_gnss_tracker* const* trackers, 
         break;
       }
       n_tail[k] = O.n;
-      j_off[k] = nj;
-      r_off[k] = nr;
-      nj += (int64_t)O.n * O.n;
-      nr += O.n;
+      Jp[k] = O.J0;
+      rp[k] = O.r0;
     }
-    std::vector<double> Jall((size_t)nj), rall((size_t)nr);
-    if (st == SWGN_OK) st = swgn_batch_get_marginal_priors(batch, n_tail.data(), j_off.data(), r_off.data(), Jall.data(), rall.data());
-    for (size_t k = 0; st == SWGN_OK && k < gi.size(); ++k) {
-      swgn_gnss_output& O = outputs[gi[k]];
-      std::memcpy(O.J0, Jall.data() + j_off[k], sizeof(double) * (size_t)O.n * O.n);
-      std::memcpy(O.r0, rall.data() + r_off[k], sizeof(double) * O.n);
-    }
+    if (st == SWGN_OK) st = swgn::batch_marginal_priors_to(batch, n_tail.data(), Jp.data(), rp.data());
   }
   lap("pass 1 priors");
   swgn_batch_destroy(batch);

@@ -13,6 +13,7 @@
 
 namespace swgn {
 swgn_status set_error(swgn_status st, const std::string& m);
+swgn_status batch_marginal_priors_to(swgn_batch* b, const int32_t* n_tail, double* const* J0_ptr, double* const* r0_ptr);
 }
 using swgn::set_error;
 
@@ -113,25 +114,17 @@ extern "C" swgn_status swgn_marginalize(int32_t device, int32_t n_graphs, const 
   st = swgn_batch_solve(batch, sums.data());
   if (st == SWGN_OK) {
     std::vector<int32_t> n_tail(n_graphs);
-    std::vector<int64_t> j_off(n_graphs), r_off(n_graphs);
-    int64_t nj = 0, nr = 0;
+    std::vector<double*> Jp(n_graphs), rp(n_graphs);
     for (int w = 0; w < n_graphs; ++w) {
       if (sums[w].n_f != outputs[w].n + outputs[w].m) {
         st = set_error(SWGN_ERR_INVALID, "graph " + std::to_string(w) + ": internal: reduced system size differs from the drop and keep blocks");
         break;
       }
       n_tail[w] = outputs[w].n;
-      j_off[w] = nj;
-      r_off[w] = nr;
-      nj += (int64_t)outputs[w].n * outputs[w].n;
-      nr += outputs[w].n;
+      Jp[w] = outputs[w].J0;
+      rp[w] = outputs[w].r0;
     }
-    std::vector<double> Jall((size_t)nj), rall((size_t)nr);
-    if (st == SWGN_OK) st = swgn_batch_get_marginal_priors(batch, n_tail.data(), j_off.data(), r_off.data(), Jall.data(), rall.data());
-    for (int w = 0; st == SWGN_OK && w < n_graphs; ++w) {
-      std::memcpy(outputs[w].J0, Jall.data() + j_off[w], sizeof(double) * (size_t)outputs[w].n * outputs[w].n);
-      std::memcpy(outputs[w].r0, rall.data() + r_off[w], sizeof(double) * outputs[w].n);
-    }
+    if (st == SWGN_OK) st = swgn::batch_marginal_priors_to(batch, n_tail.data(), Jp.data(), rp.data());
   }
   swgn_batch_destroy(batch);
   return st;
