@@ -338,21 +338,28 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   std::vector<WindowPlan> plans(n_windows);
   std::vector<swgn_status> sts(n_windows, SWGN_OK);
   std::vector<std::string> errs(n_windows);
-  {
+  std::vector<uint64_t> fingerprints(n_windows);
+  // per-window host work on all host threads (batches of thousands of tiny graphs -- the per-epoch GNSS problems -- spend
+  // as long in the constructors, destructors and fingerprints of their plans as in the planning itself)
+  auto on_all_threads = [&](auto&& per_window) {
     const int nt = std::max(1, std::min<int>(n_windows / 4, (int)std::thread::hardware_concurrency()));
     std::atomic<int> next(0);
     auto work = [&]() {
       for (;;) {
-        const int w = next.fetch_add(1);
-        if (w >= n_windows) break;
-        sts[w] = build_plan(graphs[w], options->n_parameter_head, &plans[w], &errs[w]);
+        const int w0 = next.fetch_add(8);
+        if (w0 >= n_windows) break;
+        for (int w = w0; w < std::min(n_windows, w0 + 8); ++w) per_window(w);
       }
     };
     std::vector<std::thread> th;
     for (int t = 1; t < nt; ++t) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
-  }
+  };
+  on_all_threads([&](int w) {
+    sts[w] = build_plan(graphs[w], options->n_parameter_head, &plans[w], &errs[w]);
+    if (sts[w] == SWGN_OK) fingerprints[w] = structure_fingerprint(graphs[w]);
+  });
   for (int w = 0; w < n_windows; ++w)
     if (sts[w] != SWGN_OK) return fail(sts[w], "window " + std::to_string(w) + ": " + errs[w]);
 
@@ -364,8 +371,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
   b->desc.resize(n_windows);
   b->schur_doubles.resize(n_windows);
   b->state_off.resize(n_windows + 1);
-  b->fingerprint.resize(n_windows);
-  for (int w = 0; w < n_windows; ++w) b->fingerprint[w] = structure_fingerprint(graphs[w]);
+  b->fingerprint = std::move(fingerprints);
   b->host.resize(n_windows);
   for (int w = 0; w < n_windows; ++w) {
     const swgn_graph* g = graphs[w];
@@ -564,6 +570,7 @@ swgn_status swgn_batch_create(const swgn_options* options, int32_t n_windows, co
       if (ev[q]) cudaEventDestroy(ev[q]);
     if (ce != cudaSuccess) return bail(ce, "pool upload");
   }
+  on_all_threads([&](int w) { plans[w] = WindowPlan(); });  // the tables are on the device: release them in parallel
   mark("pack + upload");
   DeviceBatch& db = b->db;
   std::memset(&db, 0, sizeof(db));
